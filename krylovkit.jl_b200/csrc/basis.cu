@@ -1,0 +1,986 @@
+// basis.cu — OrthonormalBasis operations on the device slab: project!!, unproject!!,
+// the orthogonalize!! family (fused CGS / CGS2, pipelined MGS), basistransform!,
+// rank1update!, Householder, block products, and the fused Lanczos expansion step.
+// Reference semantics: KrylovKit.jl src/orthonormal.jl, src/factorizations/lanczos.jl.
+#include "tsk.cuh"
+#include <cmath>
+#include <algorithm>
+
+// blas1.cu
+int32_t b2k_enqueue_dot(b2k_ctx* ctx, const void* q, void* x, int64_t n, const void* qprev,
+                        int sprev_slot, int slot, int accum_slot);
+int32_t b2k_enqueue_axpy_dev(b2k_ctx* ctx, void* x, const void* q, int s_slot, int64_t n);
+// spmv.cu
+int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
+                          double a0, double a1, bool shifted, const VecRef* dotv, int dot_slot);
+
+using namespace tsk;
+
+namespace {
+
+// ---------------------------------------------------------------- kernels ----
+
+template <typename T, bool UPDATE, bool PROJECT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_phase(const __grid_constant__ PhaseParams<T> p, const __grid_constant__ ColList cl) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemView sm(smem);
+    const int64_t ntiles = (p.n + Cfg<T>::R - 1) / Cfg<T>::R;
+    const bool ragged = (p.n % Cfg<T>::R) != 0 && ((ntiles - 1) % gridDim.x) == blockIdx.x;
+    pipe_setup(sm, ragged);
+    Pipe st;
+    if (threadIdx.x >= NCONS) producer_phase<T>(p, cl, sm, st);
+    else consumer_phase<T, UPDATE, PROJECT>(p, sm, st);
+}
+
+// Cooperative fused Gram-Schmidt kernel: up to three phases in one launch, separated by
+// grid barriers.  kind: 0 = project, 1 = update+project, 2 = update (+norm).
+template <typename T>
+struct FusedParams {
+    PhaseParams<T> ph[3];
+    int32_t kind[3];
+    int32_t nph;
+    unsigned* barrier;
+    unsigned barrier_base;   // counter value before this launch
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ ColList cl) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemView sm(smem);
+    const int64_t n = fp.ph[0].n;
+    const int64_t ntiles = (n + Cfg<T>::R - 1) / Cfg<T>::R;
+    const bool ragged = (n % Cfg<T>::R) != 0 && ((ntiles - 1) % gridDim.x) == blockIdx.x;
+    pipe_setup(sm, ragged);
+    Pipe st;
+    const bool prod = threadIdx.x >= NCONS;
+    for (int i = 0; i < fp.nph; ++i) {
+        if (prod) {
+            producer_phase<T>(fp.ph[i], cl, sm, st);
+        } else {
+            if (fp.kind[i] == 0) consumer_phase<T, false, true>(fp.ph[i], sm, st);
+            else if (fp.kind[i] == 1) consumer_phase<T, true, true>(fp.ph[i], sm, st);
+            else consumer_phase<T, true, false>(fp.ph[i], sm, st);
+        }
+        if (i + 1 < fp.nph) grid_barrier(fp.barrier, fp.barrier_base + (unsigned)(i + 1) * gridDim.x);
+    }
+}
+
+// res[off + j] = sum_g A[g*stride + j] (+ sum_g B[g*stride + j]);  res[noff] = sum_g N[g]
+__global__ void k_finalize(const double* __restrict__ A, const double* __restrict__ B,
+                           const double* __restrict__ N, int G, int stride, int k,
+                           double* __restrict__ res, int off, int noff) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) {
+        double a = 0.0;
+        for (int g = 0; g < G; ++g) a += A[(size_t)g * stride + j];
+        if (B) {
+            double b = 0.0;
+            for (int g = 0; g < G; ++g) b += B[(size_t)g * stride + j];
+            a += b;
+        }
+        res[off + j] = a;
+    }
+    if (N && j == 0) {
+        double s = 0.0;
+        for (int g = 0; g < G; ++g) s += N[g];
+        res[noff] = s;
+    }
+}
+
+// out[j] = (T) res[j]  (dense adjoint: projection coefficients become a device vector)
+template <typename T>
+__global__ void k_res_to_vec(const double* __restrict__ res, T* __restrict__ out, int k,
+                             T alpha) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) out[j] = alpha * (T)res[j];
+}
+
+// Lanczos tail: res[0] = alpha0 + s[k-1]  (lanczos.jl:321 `α += s[end]`)
+__global__ void k_lanczos_alpha(double* res, int alpha_slot, int s_last_slot, int out_slot) {
+    if (threadIdx.x == 0) res[out_slot] = res[alpha_slot] + res[s_last_slot];
+}
+
+// basistransform!: cols[0..keep) <- Q[:, cols[0..m)] * U, in place, tile resident in the ring
+struct TransformParams {
+    void* base;
+    int64_t ld, n;
+    int32_t m, keep, ldu;
+    const double* U;     // device, column-major m x keep
+    int32_t u_in_smem;
+};
+
+constexpr int TR_OFF_U = NS * SLOT_BYTES;                 // after the ring
+constexpr int TR_U_BYTES = 232448 - TR_OFF_U - 256;       // bytes available for U
+constexpr int TR_OFF_BAR = TR_OFF_U + TR_U_BYTES;
+constexpr int TR_SMEM = TR_OFF_BAR + 2 * NS * 8;
+constexpr int JB = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
+    using CF = Cfg<T>;
+    constexpr int R = CF::R, C = CF::C;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full = smem_u32(smem + TR_OFF_BAR), empty = full + NS * 8;
+    T* Us = reinterpret_cast<T*>(smem + TR_OFF_U);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, NCONS / 32);
+        }
+        fence_mbar_init();
+    }
+    if (p.u_in_smem)
+        for (int i = threadIdx.x; i < p.m * p.keep; i += blockDim.x) {
+            const int r = i % p.m, c = i / p.m;
+            Us[i] = (T)p.U[(size_t)c * p.ldu + r];
+        }
+    __syncthreads();
+    const int nch = (p.m + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    T* base = reinterpret_cast<T*>(p.base);
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= NCONS) {
+        const int lane = threadIdx.x & 31;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t bytes = (uint32_t)((rt * sizeof(T) + 15) & ~(size_t)15);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(empty + 8 * s, ph ^ 1);
+                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+                if (lane == 0) mbar_expect_tx(full + 8 * s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(ring + s * SLOT_BYTES + lane * R * (int)sizeof(T),
+                             base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes, full + 8 * s);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        const int tid = threadIdx.x, lane = tid & 31;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t s0 = s, ph0 = ph;
+            for (int c = 0; c < nch; ++c) {   // wait for the whole tile
+                mbar_wait(full + 8 * s, ph);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+            for (int jb = 0; jb < p.keep; jb += JB) {
+                T acc[JB];
+#pragma unroll
+                for (int t = 0; t < JB; ++t) acc[t] = (T)0;
+                uint32_t ss = s0;
+                for (int c = 0; c < nch; ++c) {
+                    const T* slot = reinterpret_cast<const T*>(smem + ss * SLOT_BYTES);
+                    const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+                    for (int jj = 0; jj < ncol; ++jj) {
+                        const T q = slot[jj * R + tid];
+                        const int i = c * C + jj;
+                        if (p.u_in_smem) {
+#pragma unroll
+                            for (int t = 0; t < JB; ++t)
+                                if (jb + t < p.keep) acc[t] = fma(q, Us[(jb + t) * p.m + i], acc[t]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < JB; ++t)
+                                if (jb + t < p.keep)
+                                    acc[t] = fma(q, (T)__ldg(p.U + (size_t)(jb + t) * p.ldu + i), acc[t]);
+                        }
+                    }
+                    if (++ss == NS) ss = 0;
+                }
+                if (tid < rt) {
+#pragma unroll
+                    for (int t = 0; t < JB; ++t)
+                        if (jb + t < p.keep) base[(int64_t)cl.c[jb + t] * p.ld + r0 + tid] = acc[t];
+                }
+            }
+            // release the tile
+            uint32_t ss = s0;
+            __syncwarp();
+            for (int c = 0; c < nch; ++c) {
+                if (lane == 0) mbar_arrive(empty + 8 * ss);
+                if (++ss == NS) ss = 0;
+            }
+            (void)ph0;
+        }
+    }
+}
+
+// rank1update!: b[cols[i]] = beta*b[cols[i]] + (alpha*conj(x[i])) * y   — orthonormal.jl:219-227
+struct CoefList {
+    double c[256];
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_rank1(T* __restrict__ base, int64_t ld, int64_t n, int k, const T* __restrict__ y, T beta,
+        int beta_mode, const __grid_constant__ ColList cl, const __grid_constant__ CoefList cf) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += stride) {
+        const T yv = y[r];
+        for (int i = 0; i < k; ++i) {
+            T* col = base + (int64_t)cl.c[i] * ld;
+            const T a = (T)cf.c[i];
+            if (beta_mode == 1) col[r] = fma(a, yv, col[r]);
+            else if (beta_mode == 0) col[r] = a * yv;
+            else col[r] = fma(a, yv, beta * col[r]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launch helpers ----
+
+template <typename T, bool U, bool P>
+int32_t launch_phase_t(b2k_ctx* ctx, const PhaseParams<T>& p, const ColList& cl, int grid) {
+    k_phase<T, U, P><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p, cl);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+template <typename T>
+int32_t launch_phase(b2k_ctx* ctx, const PhaseParams<T>& p, const ColList& cl, int kind, int grid) {
+    if (kind == 0) return launch_phase_t<T, false, true>(ctx, p, cl, grid);
+    if (kind == 1) return launch_phase_t<T, true, true>(ctx, p, cl, grid);
+    return launch_phase_t<T, true, false>(ctx, p, cl, grid);
+}
+
+template <typename T>
+int grid_for_rows(const b2k_ctx* ctx, int64_t n) {
+    int64_t ntiles = (n + Cfg<T>::R - 1) / Cfg<T>::R;
+    if (ntiles < 1) ntiles = 1;
+    return (int)std::min<int64_t>(ntiles, ctx->num_sms);
+}
+
+template <typename T>
+int32_t launch_fused(b2k_ctx* ctx, FusedParams<T>& fp, const ColList& cl, int grid) {
+    // the barrier counter only ever increases; wrap-around is handled by the signed compare
+    fp.barrier = ctx->d_sync + 1;
+    fp.barrier_base = ctx->barrier_base;
+    ctx->barrier_base += (unsigned)(fp.nph - 1) * (unsigned)grid;
+    void* args[] = {(void*)&fp, (void*)&cl};
+    B2K_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_gs_fused<T>, dim3(grid), dim3(NTHREADS),
+                                              args, SMEM_BYTES, ctx->stream));
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+int32_t enqueue_finalize(b2k_ctx* ctx, const double* A, const double* B, const double* N, int G,
+                         int k, int off, int noff) {
+    const int threads = 128;
+    const int blocks = std::max(1, (k + threads - 1) / threads);
+    k_finalize<<<blocks, threads, 0, ctx->stream>>>(A, B, N, G, B2K_KSTRIDE, k, ctx->d_res, off, noff);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+struct Panel {
+    void* base;      // space base pointer
+    int64_t ld, n;
+    int32_t sharded;
+    std::vector<int32_t> idx;
+};
+
+int32_t make_panel(b2k_ctx* ctx, const b2k_vec* cols, int32_t k, Panel* pn) {
+    int32_t sp = 0;
+    B2K_TRY(b2k_resolve_cols(ctx, cols, k, &sp, &pn->idx));
+    if (k == 0) {
+        pn->base = nullptr;
+        return B2K_OK;
+    }
+    const B2kSpace& s = ctx->spaces[sp];
+    pn->base = s.base;
+    pn->ld = s.ld;
+    pn->n = s.n;
+    pn->sharded = s.sharded;
+    return B2K_OK;
+}
+
+template <typename T>
+void fill_cols(ColList& cl, const std::vector<int32_t>& idx, int off, int cnt) {
+    for (int i = 0; i < cnt; ++i) cl.c[i] = idx[off + i];
+}
+
+template <typename T>
+PhaseParams<T> base_params(const Panel& pn, int k, const void* x, void* xout) {
+    PhaseParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.base = (const T*)pn.base;
+    p.ld = pn.ld;
+    p.n = pn.n;
+    p.k = k;
+    p.x = (const T*)x;
+    p.xout = (T*)xout;
+    p.nvec = 1;
+    p.beta_mode = 1;
+    p.betax = (T)1;
+    p.alphac = (T)1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------
+// project: d_res[0..k) = Q^T x   (all passes), single-GPU or dist (allreduce by caller)
+// ------------------------------------------------------------------------------------
+template <typename T>
+int32_t project_t(b2k_ctx* ctx, const Panel& pn, const VecRef& x, int k, int res_off) {
+    const int grid = grid_for_rows<T>(ctx, pn.n);
+    const int KC = kcap<T>();
+    for (int off = 0; off < k; off += KC) {
+        const int kk = std::min(KC, k - off);
+        ColList cl;
+        fill_cols<T>(cl, pn.idx, off, kk);
+        PhaseParams<T> p = base_params<T>(pn, kk, x.ptr, nullptr);
+        p.part_h = b2k_part_set(ctx, 0);
+        B2K_TRY((launch_phase_t<T, false, true>(ctx, p, cl, grid)));
+        B2K_TRY(enqueue_finalize(ctx, b2k_part_set(ctx, 0), nullptr, nullptr, grid, kk,
+                                 res_off + off, 0));
+    }
+    return B2K_OK;
+}
+
+// unproject: y = beta*y + alpha * sum_j Q[:,j] c[j], coefficients from d_coef (double) or a
+// device T vector.  Multi-pass when k > KCAP (beta applies to the first pass only).
+template <typename T>
+int32_t unproject_t(b2k_ctx* ctx, const Panel& pn, const VecRef& y, int k, const double* dcoef,
+                    const T* coef_t, double alpha, double beta, double* part_n) {
+    const int grid = grid_for_rows<T>(ctx, pn.n);
+    const int KC = kcap<T>();
+    int off = 0;
+    do {
+        const int kk = std::min(KC, k - off);
+        ColList cl;
+        fill_cols<T>(cl, pn.idx, off, kk);
+        PhaseParams<T> p = base_params<T>(pn, kk, y.ptr, y.ptr);
+        p.store_x = 1;
+        p.coef = dcoef ? dcoef + off : nullptr;
+        p.coef_t = coef_t ? coef_t + off : nullptr;
+        p.coef_sets = 1;
+        p.coef_stride = 0;
+        p.alphac = (T)alpha;
+        if (off == 0) {
+            p.beta_mode = beta == 0.0 ? 0 : (beta == 1.0 ? 1 : 2);
+            p.betax = (T)beta;
+        }
+        p.part_n = (off + kk >= k) ? part_n : nullptr;
+        B2K_TRY((launch_phase_t<T, true, false>(ctx, p, cl, grid)));
+        off += kk;
+    } while (off < k);
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Gram-Schmidt drivers (device side: everything stays enqueued; results land in d_res)
+// d_res layout for orthogonalize: [0..k) h, [k] ||v||^2
+// ------------------------------------------------------------------------------------
+struct GsPlan {
+    bool prologue = false;      // Lanczos three-term prologue in the first phase
+    const void* e1 = nullptr;
+    const void* e2 = nullptr;
+    double c1 = 0, c2 = 0;
+    int c2_slot = -1;           // if >= 0: c2 = -d_res[c2_slot] is not known on host -> unsupported here
+};
+
+// One classical Gram-Schmidt pass set.  passes = 1 (CGS) or 2 (CGS2).  Results:
+// d_res[0..k) = h (sum over passes), d_res[k] = ||v_out||^2.  Single-GPU fused path.
+template <typename T>
+int32_t cgs_fused_t(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int passes,
+                    bool use_coop) {
+    const int grid = grid_for_rows<T>(ctx, pn.n);
+    ColList cl;
+    fill_cols<T>(cl, pn.idx, 0, k);
+    double* PA = b2k_part_set(ctx, 0);
+    double* PB = b2k_part_set(ctx, 1);
+    double* PN = b2k_part_set(ctx, 2);
+    FusedParams<T> fp;
+    memset(&fp, 0, sizeof(fp));
+    int nph = 0;
+    {   // phase A: h1 = Q^T v
+        PhaseParams<T> p = base_params<T>(pn, k, v.ptr, nullptr);
+        p.part_h = PA;
+        fp.ph[nph] = p; fp.kind[nph] = 0; ++nph;
+    }
+    if (passes == 2) {   // phase B: v1 = v - Q h1 ; h2 = Q^T v1
+        PhaseParams<T> p = base_params<T>(pn, k, v.ptr, v.ptr);
+        p.store_x = 1;
+        p.coef = PA; p.coef_sets = grid; p.coef_stride = B2K_KSTRIDE;
+        p.alphac = (T)-1;
+        p.part_h = PB;
+        fp.ph[nph] = p; fp.kind[nph] = 1; ++nph;
+    }
+    {   // phase C: v2 = v1 - Q h_last ; ||v2||^2
+        PhaseParams<T> p = base_params<T>(pn, k, v.ptr, v.ptr);
+        p.store_x = 1;
+        p.coef = (passes == 2) ? PB : PA; p.coef_sets = grid; p.coef_stride = B2K_KSTRIDE;
+        p.alphac = (T)-1;
+        p.part_n = PN;
+        fp.ph[nph] = p; fp.kind[nph] = 2; ++nph;
+    }
+    fp.nph = nph;
+    if (use_coop) {
+        B2K_TRY(launch_fused<T>(ctx, fp, cl, grid));
+    } else {
+        for (int i = 0; i < nph; ++i) B2K_TRY(launch_phase<T>(ctx, fp.ph[i], cl, fp.kind[i], grid));
+    }
+    B2K_TRY(enqueue_finalize(ctx, PA, passes == 2 ? PB : nullptr, PN, grid, k, 0, k));
+    return B2K_OK;
+}
+
+// Distributed / large-k classical Gram-Schmidt: project (all passes) -> allreduce -> update.
+// d_res[res_off..+k) receives this pass's h, d_res[nslot] = ||v||^2 (local partial sum, reduced).
+template <typename T>
+int32_t cgs_pass_unfused_t(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res_off,
+                           int nslot) {
+    B2K_TRY(project_t<T>(ctx, pn, v, k, res_off));
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res + res_off, k, pn.sharded));
+    B2K_TRY(unproject_t<T>(ctx, pn, v, k, ctx->d_res + res_off, nullptr, -1.0, 1.0,
+                           b2k_part_set(ctx, 2)));
+    const int grid = grid_for_rows<T>(ctx, pn.n);
+    // norm partials -> d_res[nslot]
+    k_finalize<<<1, 32, 0, ctx->stream>>>(b2k_part_set(ctx, 2), nullptr, b2k_part_set(ctx, 2), grid,
+                                          B2K_KSTRIDE, 0, ctx->d_res, 0, nslot);
+    B2K_LAUNCH_CHECK(ctx);
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res + nslot, 1, pn.sharded));
+    return B2K_OK;
+}
+
+bool fused_ok(const b2k_ctx* ctx, int k, int sharded, int dtype) {
+    const int C = dtype == B2K_F64 ? 8 : 16;
+    const int nch = (k + C - 1) / C;
+    return !(ctx->nranks > 1 && sharded) && nch <= NS && k <= MAXCH * C;
+}
+
+bool g_use_coop = true;
+
+// modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
+// s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
+// with accumulate, d_res[acc_off + j] += s_j (reorthogonalize!!, :427-431).
+int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res_off, int acc_off) {
+    const int es = ctx->esize;
+    const bool dist = ctx->nranks > 1 && pn.sharded;
+    for (int j = 0; j < k; ++j) {
+        const char* qj = (const char*)pn.base + (size_t)pn.idx[j] * pn.ld * es;
+        const char* qp = j > 0 ? (const char*)pn.base + (size_t)pn.idx[j - 1] * pn.ld * es : nullptr;
+        B2K_TRY(b2k_enqueue_dot(ctx, qj, v.ptr, pn.n, qp, j > 0 ? res_off + j - 1 : -1, res_off + j,
+                                (!dist && acc_off >= 0) ? acc_off + j : -1));
+        if (dist) B2K_TRY(b2k_allreduce(ctx, ctx->d_res + res_off + j, 1, 1));
+    }
+    if (k > 0) {
+        const char* ql = (const char*)pn.base + (size_t)pn.idx[k - 1] * pn.ld * es;
+        B2K_TRY(b2k_enqueue_axpy_dev(ctx, v.ptr, ql, res_off + k - 1, pn.n));
+    }
+    return B2K_OK;
+}
+
+}  // namespace
+
+// called once per context (ctx.cu): opt in to > 48 KB dynamic shared memory
+int32_t b2k_basis_init(b2k_ctx* ctx) {
+#define SETATTR(fn, bytes) \
+    B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+    SETATTR((k_phase<double, false, true>), SMEM_BYTES);
+    SETATTR((k_phase<double, true, true>), SMEM_BYTES);
+    SETATTR((k_phase<double, true, false>), SMEM_BYTES);
+    SETATTR((k_phase<float, false, true>), SMEM_BYTES);
+    SETATTR((k_phase<float, true, true>), SMEM_BYTES);
+    SETATTR((k_phase<float, true, false>), SMEM_BYTES);
+    SETATTR(k_gs_fused<double>, SMEM_BYTES);
+    SETATTR(k_gs_fused<float>, SMEM_BYTES);
+    SETATTR(k_transform<double>, TR_SMEM);
+    SETATTR(k_transform<float>, TR_SMEM);
+#undef SETATTR
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_debug_set_coop(int32_t on) {
+    g_use_coop = on != 0;
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ C ABI ----
+
+extern "C" int32_t b2k_basis_project(b2k_ctx* ctx, const b2k_vec* cols, int32_t k, b2k_vec x,
+                                     double alpha, double beta, double* h_host) {
+    if (!ctx || (k > 0 && !h_host)) return B2K_EINVAL;
+    if (k == 0) return B2K_OK;
+    if (k > B2K_RES_DOUBLES - 8) return b2k_fail(ctx, B2K_EINVAL, "basis_project: k too large");
+    Panel pn;
+    B2K_TRY(make_panel(ctx, cols, k, &pn));
+    VecRef rx;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    if (rx.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "basis_project: x has %lld rows, basis %lld",
+                                      (long long)rx.n, (long long)pn.n);
+    if (ctx->dtype == B2K_F64) B2K_TRY(project_t<double>(ctx, pn, rx, k, 0));
+    else B2K_TRY(project_t<float>(ctx, pn, rx, k, 0));
+    B2K_TRY(b2k_fetch_results(ctx, k, pn.sharded));
+    for (int j = 0; j < k; ++j)
+        h_host[j] = (beta == 0.0) ? alpha * ctx->h_res[j] : beta * h_host[j] + alpha * ctx->h_res[j];
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_basis_unproject(b2k_ctx* ctx, b2k_vec y, const b2k_vec* cols, int32_t k,
+                                       const double* c_host, double alpha, double beta) {
+    if (!ctx || (k > 0 && !c_host)) return B2K_EINVAL;
+    VecRef ry;
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    if (k == 0) {   // orthonormal.jl:162-164
+        if (beta == 1.0) return B2K_OK;
+        if (beta == 0.0) return b2k_vec_zero(ctx, y);
+        return b2k_vec_scale(ctx, y, y, beta);
+    }
+    Panel pn;
+    B2K_TRY(make_panel(ctx, cols, k, &pn));
+    if (ry.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "basis_unproject: y has %lld rows, basis %lld",
+                                      (long long)ry.n, (long long)pn.n);
+    for (int j = 0; j < k; ++j)
+        if (pn.idx[j] == ry.col && ry.space == B2K_VEC_SPACE(cols[j]))
+            return b2k_fail(ctx, B2K_EINVAL, "basis_unproject: y aliases basis vector %d", j);
+    B2K_TRY(b2k_put_coef(ctx, c_host, k, 0));
+    if (ctx->dtype == B2K_F64)
+        return unproject_t<double>(ctx, pn, ry, k, ctx->d_coef, nullptr, alpha, beta, nullptr);
+    return unproject_t<float>(ctx, pn, ry, k, ctx->d_coef, nullptr, alpha, beta, nullptr);
+}
+
+// internal: used by the dense operator (spmv.cu): y = A x / y = A' x through the engine
+int32_t b2k_panel_unproject_dev(b2k_ctx* ctx, void* base, int64_t ld, int64_t n, int32_t k,
+                                const VecRef& y, const void* coef_t) {
+    Panel pn;
+    pn.base = base; pn.ld = ld; pn.n = n; pn.sharded = y.sharded;
+    pn.idx.resize(k);
+    for (int i = 0; i < k; ++i) pn.idx[i] = i;
+    if (ctx->dtype == B2K_F64)
+        return unproject_t<double>(ctx, pn, y, k, nullptr, (const double*)coef_t, 1.0, 0.0, nullptr);
+    return unproject_t<float>(ctx, pn, y, k, nullptr, (const float*)coef_t, 1.0, 0.0, nullptr);
+}
+
+int32_t b2k_panel_project_dev(b2k_ctx* ctx, void* base, int64_t ld, int64_t n, int32_t k,
+                              const VecRef& x, void* out_vec, int32_t sharded) {
+    Panel pn;
+    pn.base = base; pn.ld = ld; pn.n = n; pn.sharded = sharded;
+    pn.idx.resize(k);
+    for (int i = 0; i < k; ++i) pn.idx[i] = i;
+    if (k > B2K_RES_DOUBLES) return b2k_fail(ctx, B2K_ENOTSUP, "dense adjoint: too many columns");
+    if (ctx->dtype == B2K_F64) B2K_TRY(project_t<double>(ctx, pn, x, k, 0));
+    else B2K_TRY(project_t<float>(ctx, pn, x, k, 0));
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res, k, sharded));
+    const int blocks = (k + 127) / 128;
+    if (ctx->dtype == B2K_F64)
+        k_res_to_vec<double><<<blocks, 128, 0, ctx->stream>>>(ctx->d_res, (double*)out_vec, k, 1.0);
+    else
+        k_res_to_vec<float><<<blocks, 128, 0, ctx->stream>>>(ctx->d_res, (float*)out_vec, k, 1.0f);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_basis_orthogonalize(b2k_ctx* ctx, b2k_vec v, const b2k_vec* cols, int32_t k,
+                                           double* h_host, int32_t alg, double eta,
+                                           double* nrm_out, int32_t* passes_out) {
+    if (!ctx || (k > 0 && !h_host)) return B2K_EINVAL;
+    if (alg < B2K_CGS || alg > B2K_MGSIR)
+        return b2k_fail(ctx, B2K_EINVAL, "basis_orthogonalize: unknown orthogonalizer %d", alg);
+    VecRef rv;
+    B2K_TRY(b2k_resolve(ctx, v, &rv));
+    if (passes_out) *passes_out = 0;
+    if (k == 0) {
+        if (nrm_out) return b2k_vec_norm(ctx, v, nrm_out);
+        return B2K_OK;
+    }
+    if (k + 8 > 2048) return b2k_fail(ctx, B2K_ENOTSUP, "basis_orthogonalize: k > 2040");
+    Panel pn;
+    B2K_TRY(make_panel(ctx, cols, k, &pn));
+    if (rv.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "basis_orthogonalize: v has %lld rows, basis %lld",
+                                      (long long)rv.n, (long long)pn.n);
+    for (int j = 0; j < k; ++j)
+        if (pn.idx[j] == rv.col && rv.space == B2K_VEC_SPACE(cols[j]))
+            return b2k_fail(ctx, B2K_EINVAL, "basis_orthogonalize: v aliases basis vector %d", j);
+    const bool f64 = ctx->dtype == B2K_F64;
+    const bool fusable = fused_ok(ctx, k, pn.sharded, ctx->dtype);
+    const double eps = f64 ? 2.220446049250313e-16 : 1.1920929e-07;
+    const int NS_ = 2 * k + 4;   // slot of ||v||^2 results for unfused / MGS paths
+
+    auto cgs_passes = [&](int passes) -> int32_t {   // leaves h in h_res[0..k), norm^2 in h_res[k]
+        if (fusable) {
+            if (f64) B2K_TRY(cgs_fused_t<double>(ctx, pn, rv, k, passes, g_use_coop));
+            else B2K_TRY(cgs_fused_t<float>(ctx, pn, rv, k, passes, g_use_coop));
+            return b2k_fetch_results(ctx, k + 1, 0);
+        }
+        // unfused: pass p writes h_p to d_res[p*k ..], norm to d_res[NS_]
+        for (int ps = 0; ps < passes; ++ps) {
+            if (f64) B2K_TRY(cgs_pass_unfused_t<double>(ctx, pn, rv, k, ps * k, NS_));
+            else B2K_TRY(cgs_pass_unfused_t<float>(ctx, pn, rv, k, ps * k, NS_));
+        }
+        B2K_TRY(b2k_fetch_results(ctx, NS_ + 1, 0));
+        if (passes == 2)
+            for (int j = 0; j < k; ++j) ctx->h_res[j] += ctx->h_res[k + j];
+        ctx->h_res[k] = ctx->h_res[NS_];
+        return B2K_OK;
+    };
+    auto mgs_passes = [&](int passes) -> int32_t {
+        B2K_TRY(mgs_sweep(ctx, pn, rv, k, 0, -1));
+        if (passes == 2) B2K_TRY(mgs_sweep(ctx, pn, rv, k, k, -1));
+        B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rv.ptr, pn.n, nullptr, -1, NS_, -1));
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res + NS_, 1, pn.sharded));
+        B2K_TRY(b2k_fetch_results(ctx, NS_ + 1, 0));
+        if (passes == 2)
+            for (int j = 0; j < k; ++j) ctx->h_res[j] += ctx->h_res[k + j];
+        ctx->h_res[k] = ctx->h_res[NS_];
+        return B2K_OK;
+    };
+
+    int passes = 0;
+    double nrm = 0.0;
+    switch (alg) {
+        case B2K_CGS:
+            B2K_TRY(cgs_passes(1)); passes = 1; break;
+        case B2K_CGS2:
+            B2K_TRY(cgs_passes(2)); passes = 2; break;
+        case B2K_MGS:
+            B2K_TRY(mgs_passes(1)); passes = 1; break;
+        case B2K_MGS2:
+            B2K_TRY(mgs_passes(2)); passes = 2; break;
+        case B2K_CGSIR:
+        case B2K_MGSIR: {
+            // orthonormal.jl:400-412 / 440-452: nold = norm(v); one pass; loop while
+            // eps < nnew < eta*nold
+            double nold;
+            B2K_TRY(b2k_vec_norm(ctx, v, &nold));
+            std::vector<double> hsum(k, 0.0);
+            double nnew = 0.0;
+            for (;;) {
+                if (alg == B2K_CGSIR) B2K_TRY(cgs_passes(1));
+                else B2K_TRY(mgs_passes(1));
+                ++passes;
+                for (int j = 0; j < k; ++j) hsum[j] += ctx->h_res[j];
+                nnew = sqrt(ctx->h_res[k]);
+                if (!(eps < nnew && nnew < eta * nold)) break;
+                nold = nnew;
+            }
+            for (int j = 0; j < k; ++j) h_host[j] = hsum[j];
+            if (nrm_out) *nrm_out = nnew;
+            if (passes_out) *passes_out = passes;
+            return B2K_OK;
+        }
+    }
+    for (int j = 0; j < k; ++j) h_host[j] = ctx->h_res[j];
+    nrm = sqrt(ctx->h_res[k]);
+    if (nrm_out) *nrm_out = nrm;
+    if (passes_out) *passes_out = passes;
+    return B2K_OK;
+}
+
+// expand! + lanczosrecurrence — src/factorizations/lanczos.jl:250-272, 295-376
+extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols,
+                                      int32_t k, b2k_vec r, b2k_vec w, double beta_old,
+                                      int32_t alg, double eta, double* alpha_out,
+                                      double* beta_out) {
+    if (!ctx || !op || !cols || k < 1 || !alpha_out || !beta_out) return B2K_EINVAL;
+    if (alg < B2K_CGS || alg > B2K_MGSIR)
+        return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: unknown orthogonalizer %d", alg);
+    if (cols[k] != r) return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: cols[k] must be r");
+    if (beta_old == 0.0) return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: beta_old == 0");
+    Panel pn;
+    B2K_TRY(make_panel(ctx, cols, k + 1, &pn));   // V after push!: k+1 vectors
+    VecRef rv, rw, vprev;
+    B2K_TRY(b2k_resolve(ctx, r, &rv));
+    B2K_TRY(b2k_resolve(ctx, w, &rw));
+    B2K_TRY(b2k_resolve(ctx, cols[k - 1], &vprev));
+    if (rv.n != pn.n || rw.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "lanczos_expand: length mismatch");
+    for (int j = 0; j <= k; ++j)
+        if (cols[j] == w) return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: w aliases the basis");
+    const bool f64 = ctx->dtype == B2K_F64;
+    const int K1 = k + 1;
+    const double eps = f64 ? 2.220446049250313e-16 : 1.1920929e-07;
+    // d_res slots
+    const int S_H = 0;             // [0..K1) projection coefficients
+    const int S_N = K1;            // ||w||^2
+    const int S_A0 = K1 + 1;       // <v, A v>
+    const int S_X = K1 + 2;        // scratch
+
+    // v = r / beta_old  (the residual's storage becomes the new basis vector, lanczos.jl:257)
+    B2K_TRY(b2k_vec_scale(ctx, r, r, 1.0 / beta_old));
+
+    if (alg == B2K_CGS || alg == B2K_CGS2 || alg == B2K_CGSIR) {
+        // w = A v ; alpha = <v, w>   (one pass)
+        B2K_TRY(b2k_enqueue_apply(ctx, op, rv, rw, 0.0, 1.0, false, &rv, S_A0));
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_A0, 1, pn.sharded));
+        // alpha must reach the host anyway (it is a returned scalar and enters c2)
+        B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+        double alpha = ctx->h_res[S_A0];
+        if (alg == B2K_CGS) {
+            // w = (w - beta v_prev) - alpha v ; beta = ||w||
+            B2K_TRY(b2k_vec_axpy2(ctx, w, cols[k - 1], -beta_old, r, -alpha));
+            B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
+            B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
+            B2K_TRY(b2k_fetch_results(ctx, S_N + 1, 0));
+            *alpha_out = alpha;
+            *beta_out = sqrt(ctx->h_res[S_N]);
+            return B2K_OK;
+        }
+        // CGS2 / CGSIR: three-term prologue fused into the projection sweep, then update+norm
+        double ab2 = alpha * alpha + beta_old * beta_old;
+        double beta = 0.0, nold = 0.0;
+        bool first = true;
+        for (;;) {
+            const bool fusable = fused_ok(ctx, K1, pn.sharded, ctx->dtype);
+            const bool prologue = first;
+            if (alg == B2K_CGSIR && first) {
+                // need beta = ||w'|| before deciding on reorthogonalisation (lanczos.jl:346-349)
+                B2K_TRY(b2k_vec_axpy2(ctx, w, cols[k - 1], -beta_old, r, -alpha));
+                B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
+                B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
+                B2K_TRY(b2k_fetch_results(ctx, S_N + 1, 0));
+                beta = sqrt(ctx->h_res[S_N]);
+                nold = sqrt(beta * beta + ab2);
+                first = false;
+                if (!(eps < beta && beta < eta * nold)) break;
+                nold = beta;
+                continue;
+            }
+            if (fusable) {
+                const int grid = f64 ? grid_for_rows<double>(ctx, pn.n) : grid_for_rows<float>(ctx, pn.n);
+                ColList cl;
+                for (int i = 0; i < K1; ++i) cl.c[i] = pn.idx[i];
+                double* PA = b2k_part_set(ctx, 0);
+                double* PN = b2k_part_set(ctx, 2);
+#define BUILD_AND_LAUNCH(T)                                                                   \
+    {                                                                                         \
+        FusedParams<T> fp;                                                                    \
+        memset(&fp, 0, sizeof(fp));                                                           \
+        PhaseParams<T> a = base_params<T>(pn, K1, rw.ptr, rw.ptr);                            \
+        if (prologue) {                                                                       \
+            a.nvec = 3; a.e1 = (const T*)vprev.ptr; a.e2 = (const T*)rv.ptr;                  \
+            a.c1 = (T)(-beta_old); a.c2 = (T)(-alpha); a.store_x = 1;                         \
+        }                                                                                     \
+        a.part_h = PA;                                                                        \
+        PhaseParams<T> c = base_params<T>(pn, K1, rw.ptr, rw.ptr);                            \
+        c.store_x = 1; c.coef = PA; c.coef_sets = grid; c.coef_stride = B2K_KSTRIDE;          \
+        c.alphac = (T)-1; c.part_n = PN;                                                      \
+        fp.ph[0] = a; fp.kind[0] = 0; fp.ph[1] = c; fp.kind[1] = 2; fp.nph = 2;               \
+        if (g_use_coop) { B2K_TRY(launch_fused<T>(ctx, fp, cl, grid)); }                      \
+        else {                                                                                \
+            B2K_TRY(launch_phase<T>(ctx, fp.ph[0], cl, 0, grid));                             \
+            B2K_TRY(launch_phase<T>(ctx, fp.ph[1], cl, 2, grid));                             \
+        }                                                                                     \
+    }
+                if (f64) BUILD_AND_LAUNCH(double) else BUILD_AND_LAUNCH(float)
+#undef BUILD_AND_LAUNCH
+                B2K_TRY(enqueue_finalize(ctx, PA, nullptr, PN, grid, K1, S_H, S_N));
+                B2K_TRY(b2k_fetch_results(ctx, S_N + 1, 0));
+            } else {
+                if (prologue) B2K_TRY(b2k_vec_axpy2(ctx, w, cols[k - 1], -beta_old, r, -alpha));
+                if (f64) B2K_TRY(cgs_pass_unfused_t<double>(ctx, pn, rw, K1, S_H, S_N));
+                else B2K_TRY(cgs_pass_unfused_t<float>(ctx, pn, rw, K1, S_H, S_N));
+                B2K_TRY(b2k_fetch_results(ctx, S_N + 1, 0));
+            }
+            alpha += ctx->h_res[S_H + k];        // α += s[end]
+            beta = sqrt(ctx->h_res[S_N]);
+            first = false;
+            if (alg == B2K_CGS2) break;
+            if (!(eps < beta && beta < eta * nold)) break;
+            nold = beta;
+        }
+        *alpha_out = alpha;
+        *beta_out = beta;
+        return B2K_OK;
+    }
+
+    // MGS family (lanczos.jl:304-312, 325-338, 357-376): w = A v ; w -= beta v_prev ;
+    // alpha = <v, w> ; w -= alpha v ; [second sweep over all of V]
+    B2K_TRY(b2k_enqueue_apply(ctx, op, rv, rw, 0.0, 1.0, false, nullptr, -1));
+    B2K_TRY(b2k_vec_axpby(ctx, w, cols[k - 1], -beta_old, 1.0));
+    B2K_TRY(b2k_enqueue_dot(ctx, rv.ptr, rw.ptr, pn.n, nullptr, -1, S_A0, -1));
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_A0, 1, pn.sharded));
+    B2K_TRY(b2k_enqueue_axpy_dev(ctx, rw.ptr, rv.ptr, S_A0, pn.n));
+    double alpha = 0.0, beta = 0.0;
+    if (alg == B2K_MGS) {
+        B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
+        B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+        alpha = ctx->h_res[S_A0];
+        beta = sqrt(ctx->h_res[S_N]);
+    } else if (alg == B2K_MGS2) {
+        B2K_TRY(mgs_sweep(ctx, pn, rw, K1, S_H, -1));
+        B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
+        B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+        alpha = ctx->h_res[S_A0] + ctx->h_res[S_H + k];   // α += s (coefficient vs V[end])
+        beta = sqrt(ctx->h_res[S_N]);
+    } else {   // MGSIR
+        B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
+        B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+        alpha = ctx->h_res[S_A0];
+        beta = sqrt(ctx->h_res[S_N]);
+        double nold = sqrt(beta * beta + alpha * alpha + beta_old * beta_old);
+        while (eps < beta && beta < eta * nold) {
+            nold = beta;
+            B2K_TRY(mgs_sweep(ctx, pn, rw, K1, S_H, -1));
+            B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
+            B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
+            B2K_TRY(b2k_fetch_results(ctx, S_N + 1, 0));
+            alpha += ctx->h_res[S_H + k];
+            beta = sqrt(ctx->h_res[S_N]);
+        }
+    }
+    (void)S_X;
+    *alpha_out = alpha;
+    *beta_out = beta;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_t m,
+                                       const double* U_host, int32_t ldu, int32_t keep) {
+    if (!ctx || !cols || !U_host || m < 1 || keep < 1 || keep > m || ldu < m) return B2K_EINVAL;
+    Panel pn;
+    B2K_TRY(make_panel(ctx, cols, m, &pn));
+    const bool f64 = ctx->dtype == B2K_F64;
+    const int C = f64 ? 8 : 16;
+    if ((m + C - 1) / C > NS || m > 256)
+        return b2k_fail(ctx, B2K_ENOTSUP, "basis_transform: m = %d exceeds the resident tile (%d)",
+                        m, NS * C);
+    if ((size_t)m * keep > B2K_COEF_DOUBLES)
+        return b2k_fail(ctx, B2K_ENOTSUP, "basis_transform: U too large");
+    // pack U densely (ldu -> m)
+    std::vector<double> Up((size_t)m * keep);
+    for (int j = 0; j < keep; ++j)
+        for (int i = 0; i < m; ++i) Up[(size_t)j * m + i] = U_host[(size_t)j * ldu + i];
+    B2K_TRY(b2k_put_coef(ctx, Up.data(), m * keep, 0));
+    TransformParams p;
+    p.base = pn.base; p.ld = pn.ld; p.n = pn.n; p.m = m; p.keep = keep; p.ldu = m;
+    p.U = ctx->d_coef;
+    p.u_in_smem = ((size_t)m * keep * ctx->esize <= (size_t)TR_U_BYTES) ? 1 : 0;
+    ColList cl;
+    for (int i = 0; i < m; ++i) cl.c[i] = pn.idx[i];
+    if (f64) {
+        k_transform<double><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+    } else {
+        k_transform<float><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+    }
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_basis_rank1update(b2k_ctx* ctx, const b2k_vec* cols, int32_t k, b2k_vec y,
+                                         const double* x_host, double alpha, double beta) {
+    if (!ctx || (k > 0 && (!cols || !x_host))) return B2K_EINVAL;
+    if (k == 0) return B2K_OK;
+    Panel pn;
+    B2K_TRY(make_panel(ctx, cols, k, &pn));
+    VecRef ry;
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    if (ry.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "basis_rank1update: length mismatch");
+    const int grid = std::max(1, (int)std::min<int64_t>((pn.n + 255) / 256, (int64_t)ctx->num_sms * 8));
+    for (int off = 0; off < k; off += 256) {
+        const int kk = std::min(256, k - off);
+        ColList cl;
+        CoefList cf;
+        for (int i = 0; i < kk; ++i) {
+            cl.c[i] = pn.idx[off + i];
+            cf.c[i] = alpha * x_host[off + i];   // real: conj(x) = x
+        }
+        const int bm = beta == 1.0 ? 1 : (beta == 0.0 ? 0 : 2);
+        if (ctx->dtype == B2K_F64)
+            k_rank1<double><<<grid, 256, 0, ctx->stream>>>((double*)pn.base, pn.ld, pn.n, kk,
+                                                           (const double*)ry.ptr, beta, bm, cl, cf);
+        else
+            k_rank1<float><<<grid, 256, 0, ctx->stream>>>((float*)pn.base, pn.ld, pn.n, kk,
+                                                          (const float*)ry.ptr, (float)beta, bm, cl, cf);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    return B2K_OK;
+}
+
+// rmul!(b, H::Householder) — src/dense/reflector.jl:143-154
+extern "C" int32_t b2k_basis_householder(b2k_ctx* ctx, const b2k_vec* cols, int32_t k,
+                                         const double* v_host, double beta, b2k_vec work) {
+    if (!ctx) return B2K_EINVAL;
+    if (beta == 0.0 || k == 0) return B2K_OK;   // iszero(β) && return b
+    B2K_TRY(b2k_basis_unproject(ctx, work, cols, k, v_host, 1.0, 0.0));
+    return b2k_basis_rank1update(ctx, cols, k, work, v_host, -beta, 1.0);
+}
+
+// ------------------------------------------------------------------ block ops ----
+
+extern "C" int32_t b2k_block_inner(b2k_ctx* ctx, const b2k_vec* X, int32_t p, const b2k_vec* Y,
+                                   int32_t q, double* M_host) {
+    if (!ctx || !X || !Y || !M_host || p < 1 || q < 1) return B2K_EINVAL;
+    if ((int64_t)p * q > B2K_RES_DOUBLES) return b2k_fail(ctx, B2K_ENOTSUP, "block_inner: p*q too large");
+    Panel pn;
+    B2K_TRY(make_panel(ctx, X, p, &pn));
+    for (int j = 0; j < q; ++j) {
+        VecRef ry;
+        B2K_TRY(b2k_resolve(ctx, Y[j], &ry));
+        if (ry.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "block_inner: length mismatch");
+        if (ctx->dtype == B2K_F64) B2K_TRY(project_t<double>(ctx, pn, ry, p, j * p));
+        else B2K_TRY(project_t<float>(ctx, pn, ry, p, j * p));
+    }
+    B2K_TRY(b2k_fetch_results(ctx, p * q, pn.sharded));
+    memcpy(M_host, ctx->h_res, sizeof(double) * p * q);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_block_axpy(b2k_ctx* ctx, const b2k_vec* Y, int32_t q, const b2k_vec* X,
+                                  int32_t p, const double* M_host, int32_t ldm) {
+    if (!ctx || !X || !Y || !M_host || p < 1 || q < 1 || ldm < p) return B2K_EINVAL;
+    for (int j = 0; j < q; ++j)
+        B2K_TRY(b2k_basis_unproject(ctx, Y[j], X, p, M_host + (size_t)j * ldm, -1.0, 1.0));
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_block_reorthogonalize(b2k_ctx* ctx, const b2k_vec* Rb, int32_t p,
+                                             const b2k_vec* V, int32_t k) {
+    if (!ctx || !Rb || p < 1) return B2K_EINVAL;
+    if (k == 0) return B2K_OK;
+    Panel pn;
+    B2K_TRY(make_panel(ctx, V, k, &pn));
+    if (k > B2K_RES_DOUBLES - 8) return b2k_fail(ctx, B2K_ENOTSUP, "block_reorthogonalize: k too large");
+    for (int i = 0; i < p; ++i) {
+        VecRef rv;
+        B2K_TRY(b2k_resolve(ctx, Rb[i], &rv));
+        if (rv.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "block_reorthogonalize: length mismatch");
+        B2K_TRY(mgs_sweep(ctx, pn, rv, k, 0, -1));
+    }
+    return B2K_OK;
+}
+
+// block_qr!(block, tol) — src/factorizations/blocklanczos.jl:312-353
+extern "C" int32_t b2k_block_qr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, double tol,
+                                double* R_host, int32_t* good, int32_t* drift) {
+    if (!ctx || !X || !R_host || !good || !drift || p < 1) return B2K_EINVAL;
+    for (int i = 0; i < p * p; ++i) R_host[i] = 0.0;
+    *drift = 0;
+    double nrm;
+    B2K_TRY(b2k_vec_norm(ctx, X[0], &nrm));   // β = sqrt(real(inner(block[1], block[1])))
+    if (nrm > tol) {
+        R_host[0] = nrm;
+        B2K_TRY(b2k_vec_scale(ctx, X[0], X[0], 1.0 / nrm));
+        good[0] = 1;
+    } else {
+        B2K_TRY(b2k_vec_zero(ctx, X[0]));
+        good[0] = 0;
+    }
+    std::vector<double> h(p);
+    for (int j = 1; j < p; ++j) {
+        double beta;
+        int32_t passes;
+        B2K_TRY(b2k_basis_orthogonalize(ctx, X[j], X, j, h.data(), B2K_MGS, 0.0, &beta, &passes));
+        for (int i = 0; i < j; ++i) R_host[(size_t)j * p + i] = h[i];
+        if (tol < beta && beta < 100 * tol) {   // DGKS reorthogonalisation
+            *drift = 1;
+            B2K_TRY(b2k_basis_orthogonalize(ctx, X[j], X, j, h.data(), B2K_MGS, 0.0, &beta, &passes));
+            for (int i = 0; i < j; ++i) R_host[(size_t)j * p + i] += h[i];
+        }
+        if (beta < tol) {
+            B2K_TRY(b2k_vec_zero(ctx, X[j]));
+            good[j] = 0;
+        } else {
+            R_host[(size_t)j * p + j] = beta;
+            B2K_TRY(b2k_vec_scale(ctx, X[j], X[j], 1.0 / beta));
+            good[j] = 1;
+        }
+    }
+    return B2K_OK;
+}

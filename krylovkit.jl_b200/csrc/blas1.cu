@@ -1,0 +1,500 @@
+// blas1.cu — VectorInterface-level kernels: fill, scale, axpby, axpy2, inner, norm,
+// single-vector orthogonalisation.  All HBM-bound streaming kernels: 128-bit vectorised
+// loads, grid = multiple of the SM count, deterministic two-stage reductions (per-CTA
+// partial -> last CTA sums the partials in CTA order; no floating-point atomics).
+#include "common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr int BT = 256;            // threads per CTA
+constexpr int CTAS_PER_SM = 4;
+
+template <typename T> struct Vec16;
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+template <> struct Vec16<float>  { using type = float4;  static constexpr int N = 4; };
+
+template <typename T> __device__ __forceinline__ void vload(const T* p, T (&v)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void vload<double>(const double* p, double (&v)[2]) {
+    double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void vload<float>(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <typename T> __device__ __forceinline__ void vstore(T* p, const T (&v)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void vstore<double>(double* p, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void vstore<float>(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+inline int grid_for(const b2k_ctx* ctx, int64_t n, int per_thread) {
+    int64_t want = (n + (int64_t)BT * per_thread - 1) / ((int64_t)BT * per_thread);
+    int64_t cap = (int64_t)ctx->num_sms * CTAS_PER_SM;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+// ------------------------------------------------------------------ elementwise ----
+
+template <typename T>
+__global__ void __launch_bounds__(BT) k_fill_splitmix(T* x, int64_t n, uint64_t seed,
+                                                      uint64_t row_offset) {
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < n; i += (int64_t)gridDim.x * BT)
+        x[i] = (T)splitmix_unit(seed, row_offset + (uint64_t)i);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT) k_fill(T* x, int64_t n, T value) {
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < n; i += (int64_t)gridDim.x * BT)
+        x[i] = value;
+}
+
+// y = alpha * x
+template <typename T>
+__global__ void __launch_bounds__(BT) k_scale(T* __restrict__ y, const T* __restrict__ x,
+                                              int64_t n, T alpha) {
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V];
+        vload<T>(x + i * V, a);
+#pragma unroll
+        for (int j = 0; j < V; ++j) a[j] *= alpha;
+        vstore<T>(y + i * V, a);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        int64_t i = nv * V + threadIdx.x;
+        y[i] = alpha * x[i];
+    }
+}
+
+// y = beta*y + alpha*x   (beta == 0 never reads y: hard zero semantics)
+template <typename T, int MODE>   // MODE 0: beta==0, 1: beta==1, 2: general
+__global__ void __launch_bounds__(BT) k_axpby(T* __restrict__ y, const T* __restrict__ x,
+                                              int64_t n, T alpha, T beta) {
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V], b[V];
+        vload<T>(x + i * V, a);
+        if (MODE != 0) vload<T>(y + i * V, b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (MODE == 0) b[j] = alpha * a[j];
+            else if (MODE == 1) b[j] = fma(alpha, a[j], b[j]);
+            else b[j] = fma(alpha, a[j], beta * b[j]);
+        }
+        vstore<T>(y + i * V, b);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        int64_t i = nv * V + threadIdx.x;
+        if (MODE == 0) y[i] = alpha * x[i];
+        else if (MODE == 1) y[i] = fma(alpha, x[i], y[i]);
+        else y[i] = fma(alpha, x[i], beta * y[i]);
+    }
+}
+
+// y = (y + a1*x1) + a2*x2, same rounding sequence as two consecutive add!! calls
+template <typename T>
+__global__ void __launch_bounds__(BT) k_axpy2(T* __restrict__ y, const T* __restrict__ x1, T a1,
+                                              const T* __restrict__ x2, T a2, int64_t n) {
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V], b[V], c[V];
+        vload<T>(y + i * V, c);
+        vload<T>(x1 + i * V, a);
+        vload<T>(x2 + i * V, b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) c[j] = fma(a2, b[j], fma(a1, a[j], c[j]));
+        vstore<T>(y + i * V, c);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        int64_t i = nv * V + threadIdx.x;
+        y[i] = fma(a2, x2[i], fma(a1, x1[i], y[i]));
+    }
+}
+
+// (q1,q2) <- (c*q1 - s*q2, s*q1 + c*q2)   — dense/givens.jl:22-36
+template <typename T>
+__global__ void __launch_bounds__(BT) k_givens(T* __restrict__ q1, T* __restrict__ q2, int64_t n,
+                                               T c, T s) {
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V], b[V], o1[V], o2[V];
+        vload<T>(q1 + i * V, a);
+        vload<T>(q2 + i * V, b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            o1[j] = c * a[j] - s * b[j];
+            o2[j] = s * a[j] + c * b[j];
+        }
+        vstore<T>(q1 + i * V, o1);
+        vstore<T>(q2 + i * V, o2);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        int64_t i = nv * V + threadIdx.x;
+        T a = q1[i], b = q2[i];
+        q1[i] = c * a - s * b;
+        q2[i] = s * a + c * b;
+    }
+}
+
+// ------------------------------------------------------------------ reductions ----
+// out[0] = sum_i x[i]*y[i]; optional fused update: x <- x - s_prev * q_prev BEFORE the dot,
+// with s_prev read from d_res[src] (device scalar of the previous reduction).  That is the
+// pipelined MGS step (orthonormal.jl:417-421): v -= s_{j-1} q_{j-1}; s_j = <q_j, v>.
+// FINAL: 0 = raw sum, 1 = sqrt(sum)
+template <typename T, bool UPDATE, bool NORM>
+__global__ void __launch_bounds__(BT)
+k_dot(const T* __restrict__ q, T* __restrict__ x, int64_t n, const T* __restrict__ qprev,
+      const double* __restrict__ sprev, double* __restrict__ part, unsigned* __restrict__ ticket,
+      double* __restrict__ out, double* __restrict__ accum_into) {
+    __shared__ double red[32];
+    __shared__ bool last;
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    T sp = 0;
+    if (UPDATE) sp = (T)(*sprev);
+    T acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V], b[V];
+        vload<T>(x + i * V, b);
+        if (UPDATE) {
+            T c[V];
+            vload<T>(qprev + i * V, c);
+#pragma unroll
+            for (int j = 0; j < V; ++j) b[j] = fma(-sp, c[j], b[j]);
+            vstore<T>(x + i * V, b);
+        }
+        if (NORM) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc = fma(b[j], b[j], acc);
+        } else {
+            vload<T>(q + i * V, a);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc = fma(a[j], b[j], acc);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        int64_t i = nv * V + threadIdx.x;
+        T b = x[i];
+        if (UPDATE) {
+            b = fma(-sp, qprev[i], b);
+            x[i] = b;
+        }
+        acc = NORM ? fma(b, b, acc) : fma(q[i], b, acc);
+    }
+    double s = block_sum((double)acc, red);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = s;
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double v = 0.0;
+        for (int g = threadIdx.x; g < gridDim.x; g += BT) v += part[g];   // fixed assignment
+        double tot = block_sum(v, red);
+        if (threadIdx.x == 0) {
+            *out = tot;
+            if (accum_into) *accum_into += tot;
+        }
+    }
+}
+
+// final fix-up: x <- x - s*q with s = d_res[src] (tail of the pipelined MGS sweep)
+template <typename T>
+__global__ void __launch_bounds__(BT)
+k_axpy_dev(T* __restrict__ x, const T* __restrict__ q, const double* __restrict__ s, int64_t n) {
+    const T sp = (T)(*s);
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V], b[V];
+        vload<T>(x + i * V, b);
+        vload<T>(q + i * V, a);
+#pragma unroll
+        for (int j = 0; j < V; ++j) b[j] = fma(-sp, a[j], b[j]);
+        vstore<T>(x + i * V, b);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        int64_t i = nv * V + threadIdx.x;
+        x[i] = fma(-sp, q[i], x[i]);
+    }
+}
+
+__global__ void k_sqrt_inplace(double* v, int count) {
+    int i = threadIdx.x;
+    if (i < count) v[i] = sqrt(v[i]);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ internal API ----
+// Enqueue: d_res[slot] = <q, x> (or ||x||^2 if q == nullptr), optionally after the fused
+// update x -= d_res[sprev_slot] * qprev.  If accum_slot >= 0, also d_res[accum_slot] += result.
+// Single-GPU: complete on return of the stream work.  Dist: caller allreduces d_res[slot].
+int32_t b2k_enqueue_dot(b2k_ctx* ctx, const void* q, void* x, int64_t n, const void* qprev,
+                        int sprev_slot, int slot, int accum_slot) {
+    const int grid = grid_for(ctx, n, 8);
+    double* out = ctx->d_res + slot;
+    double* acc = accum_slot >= 0 ? ctx->d_res + accum_slot : nullptr;
+    const double* sp = sprev_slot >= 0 ? ctx->d_res + sprev_slot : nullptr;
+    unsigned* ticket = ctx->d_sync;
+#define LAUNCH(T, UPD, NRM)                                                              \
+    k_dot<T, UPD, NRM><<<grid, BT, 0, ctx->stream>>>((const T*)q, (T*)x, n, (const T*)qprev, \
+                                                     sp, ctx->d_part_s, ticket, out, acc)
+    const bool upd = qprev != nullptr, nrm = q == nullptr;
+    if (ctx->dtype == B2K_F64) {
+        if (upd && nrm) LAUNCH(double, true, true);
+        else if (upd) LAUNCH(double, true, false);
+        else if (nrm) LAUNCH(double, false, true);
+        else LAUNCH(double, false, false);
+    } else {
+        if (upd && nrm) LAUNCH(float, true, true);
+        else if (upd) LAUNCH(float, true, false);
+        else if (nrm) LAUNCH(float, false, true);
+        else LAUNCH(float, false, false);
+    }
+#undef LAUNCH
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+int32_t b2k_enqueue_axpy_dev(b2k_ctx* ctx, void* x, const void* q, int s_slot, int64_t n) {
+    const int grid = grid_for(ctx, n, 8);
+    if (ctx->dtype == B2K_F64)
+        k_axpy_dev<double><<<grid, BT, 0, ctx->stream>>>((double*)x, (const double*)q,
+                                                         ctx->d_res + s_slot, n);
+    else
+        k_axpy_dev<float><<<grid, BT, 0, ctx->stream>>>((float*)x, (const float*)q,
+                                                        ctx->d_res + s_slot, n);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+int32_t b2k_enqueue_sqrt(b2k_ctx* ctx, int slot, int count) {
+    k_sqrt_inplace<<<1, 32, 0, ctx->stream>>>(ctx->d_res + slot, count);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ C ABI ----
+
+extern "C" int32_t b2k_vec_fill_splitmix(b2k_ctx* ctx, b2k_vec v, uint64_t seed) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef r;
+    B2K_TRY(b2k_resolve(ctx, v, &r));
+    if (r.n == 0) return B2K_OK;
+    const int grid = grid_for(ctx, r.n, 4);
+    const uint64_t off = r.sharded ? (uint64_t)ctx->row_offset : 0ull;
+    if (ctx->dtype == B2K_F64)
+        k_fill_splitmix<double><<<grid, BT, 0, ctx->stream>>>((double*)r.ptr, r.n, seed, off);
+    else
+        k_fill_splitmix<float><<<grid, BT, 0, ctx->stream>>>((float*)r.ptr, r.n, seed, off);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_fill(b2k_ctx* ctx, b2k_vec v, double value) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef r;
+    B2K_TRY(b2k_resolve(ctx, v, &r));
+    if (r.n == 0) return B2K_OK;
+    const int grid = grid_for(ctx, r.n, 4);
+    if (ctx->dtype == B2K_F64)
+        k_fill<double><<<grid, BT, 0, ctx->stream>>>((double*)r.ptr, r.n, value);
+    else
+        k_fill<float><<<grid, BT, 0, ctx->stream>>>((float*)r.ptr, r.n, (float)value);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_scale(b2k_ctx* ctx, b2k_vec y, b2k_vec x, double alpha) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef ry, rx;
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    if (ry.n != rx.n) return b2k_fail(ctx, B2K_EDIM, "vec_scale: length mismatch");
+    if (ry.n == 0) return B2K_OK;
+    const int grid = grid_for(ctx, ry.n, 8);
+    if (ctx->dtype == B2K_F64)
+        k_scale<double><<<grid, BT, 0, ctx->stream>>>((double*)ry.ptr, (const double*)rx.ptr,
+                                                      ry.n, alpha);
+    else
+        k_scale<float><<<grid, BT, 0, ctx->stream>>>((float*)ry.ptr, (const float*)rx.ptr, ry.n,
+                                                     (float)alpha);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_axpby(b2k_ctx* ctx, b2k_vec y, b2k_vec x, double alpha, double beta) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef ry, rx;
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    if (ry.n != rx.n) return b2k_fail(ctx, B2K_EDIM, "vec_axpby: length mismatch");
+    if (ry.n == 0) return B2K_OK;
+    if (ry.ptr == rx.ptr) {   // y <- (beta + alpha) * y would change rounding; do it literally
+        return b2k_vec_scale(ctx, y, x, beta + alpha);
+    }
+    const int grid = grid_for(ctx, ry.n, 8);
+#define LAUNCH(T, MODE)                                                                    \
+    k_axpby<T, MODE><<<grid, BT, 0, ctx->stream>>>((T*)ry.ptr, (const T*)rx.ptr, ry.n,     \
+                                                   (T)alpha, (T)beta)
+    if (ctx->dtype == B2K_F64) {
+        if (beta == 0.0) LAUNCH(double, 0);
+        else if (beta == 1.0) LAUNCH(double, 1);
+        else LAUNCH(double, 2);
+    } else {
+        if (beta == 0.0) LAUNCH(float, 0);
+        else if (beta == 1.0) LAUNCH(float, 1);
+        else LAUNCH(float, 2);
+    }
+#undef LAUNCH
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_axpy2(b2k_ctx* ctx, b2k_vec y, b2k_vec x1, double a1, b2k_vec x2,
+                                 double a2) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef ry, r1, r2;
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    B2K_TRY(b2k_resolve(ctx, x1, &r1));
+    B2K_TRY(b2k_resolve(ctx, x2, &r2));
+    if (ry.n != r1.n || ry.n != r2.n) return b2k_fail(ctx, B2K_EDIM, "vec_axpy2: length mismatch");
+    if (ry.ptr == r1.ptr || ry.ptr == r2.ptr)
+        return b2k_fail(ctx, B2K_EINVAL, "vec_axpy2: y must not alias x1/x2");
+    if (ry.n == 0) return B2K_OK;
+    const int grid = grid_for(ctx, ry.n, 8);
+    if (ctx->dtype == B2K_F64)
+        k_axpy2<double><<<grid, BT, 0, ctx->stream>>>((double*)ry.ptr, (const double*)r1.ptr, a1,
+                                                      (const double*)r2.ptr, a2, ry.n);
+    else
+        k_axpy2<float><<<grid, BT, 0, ctx->stream>>>((float*)ry.ptr, (const float*)r1.ptr,
+                                                     (float)a1, (const float*)r2.ptr, (float)a2,
+                                                     ry.n);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_basis_givens(b2k_ctx* ctx, b2k_vec q1, b2k_vec q2, double c, double s) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef r1, r2;
+    B2K_TRY(b2k_resolve(ctx, q1, &r1));
+    B2K_TRY(b2k_resolve(ctx, q2, &r2));
+    if (r1.n != r2.n) return b2k_fail(ctx, B2K_EDIM, "basis_givens: length mismatch");
+    if (r1.ptr == r2.ptr) return b2k_fail(ctx, B2K_EINVAL, "basis_givens: q1 == q2");
+    if (r1.n == 0) return B2K_OK;
+    const int grid = grid_for(ctx, r1.n, 8);
+    if (ctx->dtype == B2K_F64)
+        k_givens<double><<<grid, BT, 0, ctx->stream>>>((double*)r1.ptr, (double*)r2.ptr, r1.n, c, s);
+    else
+        k_givens<float><<<grid, BT, 0, ctx->stream>>>((float*)r1.ptr, (float*)r2.ptr, r1.n,
+                                                      (float)c, (float)s);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_inner(b2k_ctx* ctx, b2k_vec x, b2k_vec y, double* out) {
+    if (!ctx || !out) return B2K_EINVAL;
+    VecRef rx, ry;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    if (rx.n != ry.n) return b2k_fail(ctx, B2K_EDIM, "vec_inner: length mismatch");
+    B2K_TRY(b2k_enqueue_dot(ctx, rx.ptr, ry.ptr, rx.n, nullptr, -1, 0, -1));
+    B2K_TRY(b2k_fetch_results(ctx, 1, rx.sharded));
+    *out = ctx->h_res[0];
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_norm(b2k_ctx* ctx, b2k_vec x, double* out) {
+    if (!ctx || !out) return B2K_EINVAL;
+    VecRef rx;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rx.ptr, rx.n, nullptr, -1, 0, -1));
+    B2K_TRY(b2k_fetch_results(ctx, 1, rx.sharded));
+    *out = sqrt(ctx->h_res[0]);
+    return B2K_OK;
+}
+
+// orthogonalize!!(v, q, alg) against one normalised vector — src/orthonormal.jl:455-489
+extern "C" int32_t b2k_vec_orthogonalize(b2k_ctx* ctx, b2k_vec v, b2k_vec q, int32_t alg,
+                                         double eta, double* s_out, double* nrm_out) {
+    if (!ctx || !s_out) return B2K_EINVAL;
+    VecRef rv, rq;
+    B2K_TRY(b2k_resolve(ctx, v, &rv));
+    B2K_TRY(b2k_resolve(ctx, q, &rq));
+    if (rv.n != rq.n) return b2k_fail(ctx, B2K_EDIM, "vec_orthogonalize: length mismatch");
+    if (rv.ptr == rq.ptr) return b2k_fail(ctx, B2K_EINVAL, "vec_orthogonalize: v == q");
+    const int64_t n = rv.n;
+    const int sh = rv.sharded;
+    const bool dist = ctx->nranks > 1 && sh;
+    auto dot = [&](int slot) -> int32_t {   // d_res[slot] = <q, v>
+        B2K_TRY(b2k_enqueue_dot(ctx, rq.ptr, rv.ptr, n, nullptr, -1, slot, -1));
+        return b2k_allreduce(ctx, ctx->d_res + slot, 1, sh);
+    };
+    auto nrm2 = [&](int slot) -> int32_t {
+        B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rv.ptr, n, nullptr, -1, slot, -1));
+        return b2k_allreduce(ctx, ctx->d_res + slot, 1, sh);
+    };
+    (void)dist;
+    double s = 0.0;
+    if (alg == B2K_CGS || alg == B2K_MGS) {
+        B2K_TRY(dot(0));
+        B2K_TRY(b2k_enqueue_axpy_dev(ctx, rv.ptr, rq.ptr, 0, n));
+        B2K_TRY(nrm2(1));
+        B2K_TRY(b2k_fetch_results(ctx, 2, 0));
+        s = ctx->h_res[0];
+    } else if (alg == B2K_CGS2 || alg == B2K_MGS2) {
+        B2K_TRY(dot(0));
+        B2K_TRY(b2k_enqueue_axpy_dev(ctx, rv.ptr, rq.ptr, 0, n));
+        B2K_TRY(dot(2));
+        B2K_TRY(b2k_enqueue_axpy_dev(ctx, rv.ptr, rq.ptr, 2, n));
+        B2K_TRY(nrm2(1));
+        B2K_TRY(b2k_fetch_results(ctx, 3, 0));
+        s = ctx->h_res[0] + ctx->h_res[2];
+    } else if (alg == B2K_CGSIR || alg == B2K_MGSIR) {
+        B2K_TRY(nrm2(1));
+        B2K_TRY(dot(0));
+        B2K_TRY(b2k_enqueue_axpy_dev(ctx, rv.ptr, rq.ptr, 0, n));
+        B2K_TRY(nrm2(2));
+        B2K_TRY(b2k_fetch_results(ctx, 3, 0));
+        double nold = sqrt(ctx->h_res[1]);
+        s = ctx->h_res[0];
+        double nnew = sqrt(ctx->h_res[2]);
+        const double eps = (ctx->dtype == B2K_F64) ? 2.220446049250313e-16 : 1.1920929e-07;
+        while (eps < nnew && nnew < eta * nold) {
+            nold = nnew;
+            B2K_TRY(dot(0));
+            B2K_TRY(b2k_enqueue_axpy_dev(ctx, rv.ptr, rq.ptr, 0, n));
+            B2K_TRY(nrm2(2));
+            B2K_TRY(b2k_fetch_results(ctx, 3, 0));
+            s += ctx->h_res[0];
+            nnew = sqrt(ctx->h_res[2]);
+        }
+        *s_out = s;
+        if (nrm_out) *nrm_out = nnew;
+        return B2K_OK;
+    } else {
+        return b2k_fail(ctx, B2K_EINVAL, "vec_orthogonalize: unknown orthogonalizer %d", alg);
+    }
+    *s_out = s;
+    if (nrm_out) *nrm_out = sqrt(ctx->h_res[1]);
+    return B2K_OK;
+}

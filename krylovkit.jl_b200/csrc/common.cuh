@@ -1,0 +1,221 @@
+// common.cuh — context, error handling and PTX helpers shared by all translation units
+// of libb200krylov.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/b200krylov.h"
+
+// ----------------------------------------------------------------------------------
+// limits
+// ----------------------------------------------------------------------------------
+constexpr int B2K_MAX_SPACES   = 8;
+constexpr int B2K_RES_DOUBLES  = 8192;     // device/host scalar result buffer
+constexpr int B2K_COEF_DOUBLES = 65536;    // host->device coefficient staging (512 KB)
+constexpr int B2K_MAX_GRID     = 1024;     // upper bound on partial-producing CTAs (basis kernels)
+constexpr int B2K_KSTRIDE      = 256;      // stride (doubles) between per-CTA partial rows
+
+struct B2kSpace {
+    void*   base   = nullptr;   // device pointer, column-major n x ncols, leading dim ld
+    int64_t n      = 0;         // local rows
+    int64_t ld     = 0;         // elements; multiple of 32 (256 B for f64, 128 B for f32)
+    int32_t ncols  = 0;
+    int32_t sharded = 1;        // reductions over this space are summed across ranks
+    std::vector<uint8_t> used;
+};
+
+struct B2kNccl;   // dist.cu
+
+struct b2k_ctx {
+    int32_t device = 0;
+    int32_t dtype  = B2K_F64;
+    int32_t esize  = 8;
+    int32_t num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<B2kSpace> spaces;
+
+    // scratch
+    double*   d_part   = nullptr;   // partial sums: 4 sets x B2K_MAX_GRID x B2K_KSTRIDE doubles
+    double*   d_part_s = nullptr;   // scalar partial sums for BLAS-1 / SpMV dots (1<<20 doubles)
+    double*   d_res    = nullptr;   // reduced results on device
+    double*   h_res    = nullptr;   // pinned
+    double*   d_coef   = nullptr;   // coefficients uploaded from host
+    double*   h_coef   = nullptr;   // pinned staging
+    int32_t*  d_cols   = nullptr;   // column index lists (4 x 4096 ints)
+    int32_t*  h_cols   = nullptr;   // pinned staging
+    unsigned* d_sync   = nullptr;   // [0] ticket, [1] grid barrier counter, ...
+    cudaEvent_t ev_coef = nullptr;  // guards reuse of the pinned staging buffers
+    bool      coef_busy = false;
+
+    // dist
+    int32_t rank = 0, nranks = 1;
+    int64_t n_global = 0, row_offset = 0;
+    B2kNccl* nccl = nullptr;
+
+    unsigned barrier_base = 0;      // value of d_sync[1] before the next cooperative launch
+    int64_t launches = 0;
+    std::string err;
+};
+
+extern std::string g_b2k_create_error;
+
+// ----------------------------------------------------------------------------------
+// error handling
+// ----------------------------------------------------------------------------------
+int32_t b2k_fail(b2k_ctx* ctx, int32_t code, const char* fmt, ...);
+
+#define B2K_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return b2k_fail((ctx), B2K_ECUDA, "%s:%d: %s -> %s", __FILE__, __LINE__,     \
+                            #call, cudaGetErrorString(e__));                             \
+    } while (0)
+
+#define B2K_TRY(call)                                                                    \
+    do {                                                                                 \
+        int32_t s__ = (call);                                                            \
+        if (s__ != B2K_OK) return s__;                                                   \
+    } while (0)
+
+#define B2K_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess)                                                          \
+            return b2k_fail((ctx), B2K_ECUDA, "%s:%d: kernel launch -> %s", __FILE__,    \
+                            __LINE__, cudaGetErrorString(e__));                          \
+    } while (0)
+
+// ----------------------------------------------------------------------------------
+// handle decoding
+// ----------------------------------------------------------------------------------
+struct VecRef {
+    void*   ptr;
+    int64_t n;
+    int64_t ld;
+    int32_t space;
+    int32_t col;
+    int32_t sharded;
+};
+
+int32_t b2k_resolve(b2k_ctx* ctx, b2k_vec v, VecRef* out);
+// all handles must share one space; fills col indices; returns space id in *space
+int32_t b2k_resolve_cols(b2k_ctx* ctx, const b2k_vec* cols, int32_t k, int32_t* space,
+                         std::vector<int32_t>* idx);
+
+// scalar plumbing (ctx.cu)
+// reduce-across-ranks (if sharded & dist) the first `count` doubles of d_res, copy to h_res, sync.
+int32_t b2k_fetch_results(b2k_ctx* ctx, int32_t count, int32_t sharded);
+// allreduce `count` doubles in place on device (no-op on single GPU / non-sharded)
+int32_t b2k_allreduce(b2k_ctx* ctx, double* dptr, int32_t count, int32_t sharded);
+// upload `count` doubles of host coefficients into d_coef + offset (async, pinned staging)
+int32_t b2k_put_coef(b2k_ctx* ctx, const double* host, int32_t count, int32_t offset);
+int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t slot,
+                     int32_t** dptr);
+
+// partial buffers
+static inline double* b2k_part_set(b2k_ctx* ctx, int set) {
+    return ctx->d_part + (size_t)set * B2K_MAX_GRID * B2K_KSTRIDE;
+}
+
+// basis.cu
+int32_t b2k_basis_init(b2k_ctx* ctx);
+
+// dist (dist.cu)
+int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid);
+void    b2k_nccl_destroy(b2k_ctx* ctx);
+int32_t b2k_nccl_allreduce_f64(b2k_ctx* ctx, double* dptr, int32_t count);
+// grouped neighbour exchange; up/dn = peer ranks or -1
+int32_t b2k_nccl_halo_exchange(b2k_ctx* ctx, int up, int dn, const void* send_up, size_t send_up_bytes,
+                               void* recv_dn, size_t recv_dn_bytes, const void* send_dn,
+                               size_t send_dn_bytes, void* recv_up, size_t recv_up_bytes);
+int32_t b2k_nccl_allgather(b2k_ctx* ctx, const void* sendbuf, void* recvbuf, size_t bytes);
+
+// ----------------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (fixed tree); valid result in thread 0.  `red` >= 32 doubles of smem.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (w == 0) {
+        s = (lane < nw) ? red[lane] : 0.0;
+        s = warp_sum(s);
+    }
+    return s;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double splitmix_unit(uint64_t seed, uint64_t i) {
+    return (double)(splitmix64(seed + i) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,353 @@
+// ctx.cu — context, vector spaces (slabs), handle bookkeeping, scalar plumbing.
+#include "common.cuh"
+#include <cstdarg>
+
+std::string g_b2k_create_error;
+
+int32_t b2k_fail(b2k_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_b2k_create_error = buf;
+    return code;
+}
+
+extern "C" int32_t b2k_abi_version(void) { return B2K_ABI_VERSION; }
+
+extern "C" const char* b2k_last_error(const b2k_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_b2k_create_error.c_str();
+}
+
+static int32_t make_space(b2k_ctx* ctx, int64_t n_local, int32_t ncols, int32_t sharded,
+                          int32_t* space_out) {
+    if (n_local < 0 || ncols <= 0 || ncols >= (1 << 20))
+        return b2k_fail(ctx, B2K_EINVAL, "space: invalid n_local=%lld ncols=%d",
+                        (long long)n_local, ncols);
+    if ((int)ctx->spaces.size() >= B2K_MAX_SPACES)
+        return b2k_fail(ctx, B2K_ENOMEM, "too many spaces");
+    B2kSpace s;
+    s.n = n_local;
+    s.ld = ((n_local + 31) / 32) * 32;
+    if (s.ld == 0) s.ld = 32;
+    s.ncols = ncols;
+    s.sharded = sharded;
+    s.used.assign(ncols, 0);
+    size_t bytes = (size_t)s.ld * ncols * ctx->esize;
+    cudaError_t e = cudaMalloc(&s.base, bytes);
+    if (e != cudaSuccess)
+        return b2k_fail(ctx, B2K_ENOMEM, "cudaMalloc(%zu bytes) for slab failed: %s", bytes,
+                        cudaGetErrorString(e));
+    // zero the slab once: the ld-padding rows are read (never written) by the bulk copies
+    B2K_CUDA(ctx, cudaMemsetAsync(s.base, 0, bytes, ctx->stream));
+    ctx->spaces.push_back(std::move(s));
+    *space_out = (int32_t)ctx->spaces.size() - 1;
+    return B2K_OK;
+}
+
+static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
+                                 int32_t ncols, int32_t dtype) {
+    if (!out) return b2k_fail(nullptr, B2K_EINVAL, "ctx_create: out is NULL");
+    *out = nullptr;
+    if (dtype != B2K_F64 && dtype != B2K_F32)
+        return b2k_fail(nullptr, B2K_EINVAL, "ctx_create: unknown dtype %d", dtype);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return b2k_fail(nullptr, B2K_ECUDA,
+                        "ctx_create: no CUDA device available (%s) — this engine has no CPU "
+                        "fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return b2k_fail(nullptr, B2K_EINVAL, "ctx_create: device %d out of range [0,%d)",
+                        device, ndev);
+    b2k_ctx* ctx = new b2k_ctx();
+    ctx->device = device;
+    ctx->dtype = dtype;
+    ctx->esize = (dtype == B2K_F64) ? 8 : 4;
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e2 = (call);                                                          \
+        if (e2 != cudaSuccess) {                                                          \
+            int32_t rc = b2k_fail(nullptr, B2K_ECUDA, "ctx_create: %s -> %s", #call,      \
+                                  cudaGetErrorString(e2));                                \
+            delete ctx;                                                                   \
+            return rc;                                                                    \
+        }                                                                                 \
+    } while (0)
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        fprintf(stderr, "[b200krylov] warning: device %s is sm_%d%d; this library is built for "
+                        "sm_100a only\n", prop.name, prop.major, prop.minor);
+    ctx->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&ctx->d_part, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE));
+    CK(cudaMalloc(&ctx->d_part_s, sizeof(double) * (1 << 20)));
+    CK(cudaMalloc(&ctx->d_res, sizeof(double) * B2K_RES_DOUBLES));
+    CK(cudaHostAlloc(&ctx->h_res, sizeof(double) * B2K_RES_DOUBLES, cudaHostAllocDefault));
+    CK(cudaMalloc(&ctx->d_coef, sizeof(double) * B2K_COEF_DOUBLES));
+    CK(cudaHostAlloc(&ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES, cudaHostAllocDefault));
+    CK(cudaMalloc(&ctx->d_cols, sizeof(int32_t) * 4 * 4096));
+    CK(cudaHostAlloc(&ctx->h_cols, sizeof(int32_t) * 4 * 4096, cudaHostAllocDefault));
+    CK(cudaMalloc(&ctx->d_sync, sizeof(unsigned) * 64));
+    CK(cudaMemsetAsync(ctx->d_sync, 0, sizeof(unsigned) * 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_part, 0, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE,
+                       ctx->stream));
+    CK(cudaEventCreateWithFlags(&ctx->ev_coef, cudaEventDisableTiming));
+#undef CK
+    int32_t sp = 0;
+    int32_t rc = b2k_basis_init(ctx);
+    if (rc == B2K_OK) rc = make_space(ctx, n_local, ncols, 1, &sp);
+    if (rc != B2K_OK) {
+        g_b2k_create_error = ctx->err;
+        b2k_ctx_destroy(ctx);
+        return rc;
+    }
+    ctx->n_global = n_local;
+    ctx->row_offset = 0;
+    *out = ctx;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_ctx_create(b2k_ctx** out, int32_t device, int64_t n_local,
+                                  int32_t ncols, int32_t dtype) {
+    return ctx_create_common(out, device, n_local, ncols, dtype);
+}
+
+extern "C" int32_t b2k_ctx_create_dist(b2k_ctx** out, int32_t device, int64_t n_local,
+                                       int32_t ncols, int32_t dtype, int32_t rank,
+                                       int32_t nranks, const void* nccl_uid, int64_t n_global,
+                                       int64_t row_offset) {
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        return b2k_fail(nullptr, B2K_EINVAL, "ctx_create_dist: bad rank %d / %d", rank, nranks);
+    B2K_TRY(ctx_create_common(out, device, n_local, ncols, dtype));
+    b2k_ctx* ctx = *out;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    ctx->n_global = n_global;
+    ctx->row_offset = row_offset;
+    if (nranks > 1) {
+        int32_t rc = b2k_nccl_init(ctx, nccl_uid);
+        if (rc != B2K_OK) {
+            g_b2k_create_error = ctx->err;
+            b2k_ctx_destroy(ctx);
+            *out = nullptr;
+            return rc;
+        }
+    }
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_ctx_destroy(b2k_ctx* ctx) {
+    if (!ctx) return B2K_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    b2k_nccl_destroy(ctx);
+    for (auto& s : ctx->spaces)
+        if (s.base) cudaFree(s.base);
+    if (ctx->d_part) cudaFree(ctx->d_part);
+    if (ctx->d_part_s) cudaFree(ctx->d_part_s);
+    if (ctx->d_res) cudaFree(ctx->d_res);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->d_coef) cudaFree(ctx->d_coef);
+    if (ctx->h_coef) cudaFreeHost(ctx->h_coef);
+    if (ctx->d_cols) cudaFree(ctx->d_cols);
+    if (ctx->h_cols) cudaFreeHost(ctx->h_cols);
+    if (ctx->d_sync) cudaFree(ctx->d_sync);
+    if (ctx->ev_coef) cudaEventDestroy(ctx->ev_coef);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_space_create(b2k_ctx* ctx, int64_t n_local, int32_t ncols,
+                                    int32_t sharded, int32_t* space_out) {
+    if (!ctx || !space_out) return B2K_EINVAL;
+    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
+    return make_space(ctx, n_local, ncols, sharded, space_out);
+}
+
+extern "C" int32_t b2k_ctx_sync(b2k_ctx* ctx) {
+    if (!ctx) return B2K_EINVAL;
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+extern "C" int64_t b2k_ctx_launch_count(const b2k_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* b2k_ctx_stream(b2k_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------ handles ----
+
+int32_t b2k_resolve(b2k_ctx* ctx, b2k_vec v, VecRef* out) {
+    int32_t sp = B2K_VEC_SPACE(v), col = B2K_VEC_COL(v);
+    if (v < 0 || sp >= (int32_t)ctx->spaces.size())
+        return b2k_fail(ctx, B2K_EINVAL, "invalid vector handle 0x%x (space %d)", v, sp);
+    B2kSpace& s = ctx->spaces[sp];
+    if (col >= s.ncols || !s.used[col])
+        return b2k_fail(ctx, B2K_EINVAL, "vector handle 0x%x: column %d not allocated", v, col);
+    out->ptr = (char*)s.base + (size_t)col * s.ld * ctx->esize;
+    out->n = s.n;
+    out->ld = s.ld;
+    out->space = sp;
+    out->col = col;
+    out->sharded = s.sharded;
+    return B2K_OK;
+}
+
+int32_t b2k_resolve_cols(b2k_ctx* ctx, const b2k_vec* cols, int32_t k, int32_t* space,
+                         std::vector<int32_t>* idx) {
+    if (k < 0 || (k > 0 && !cols)) return b2k_fail(ctx, B2K_EINVAL, "bad column list");
+    idx->resize(k);
+    int32_t sp = -1;
+    for (int32_t j = 0; j < k; ++j) {
+        VecRef r;
+        B2K_TRY(b2k_resolve(ctx, cols[j], &r));
+        if (sp < 0) sp = r.space;
+        else if (sp != r.space)
+            return b2k_fail(ctx, B2K_EDIM, "basis vectors live in different spaces");
+        (*idx)[j] = r.col;
+    }
+    *space = sp;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_alloc(b2k_ctx* ctx, int32_t space, b2k_vec* out) {
+    if (!ctx || !out) return B2K_EINVAL;
+    if (space < 0 || space >= (int32_t)ctx->spaces.size())
+        return b2k_fail(ctx, B2K_EINVAL, "vec_alloc: bad space %d", space);
+    B2kSpace& s = ctx->spaces[space];
+    for (int32_t c = 0; c < s.ncols; ++c)
+        if (!s.used[c]) {
+            s.used[c] = 1;
+            *out = B2K_VEC(space, c);
+            return B2K_OK;
+        }
+    return b2k_fail(ctx, B2K_ENOMEM, "vec_alloc: slab %d has no free column (%d in use)", space,
+                    s.ncols);
+}
+
+extern "C" int32_t b2k_vec_alloc_range(b2k_ctx* ctx, int32_t space, int32_t count,
+                                       b2k_vec* first) {
+    if (!ctx || !first || count <= 0) return B2K_EINVAL;
+    if (space < 0 || space >= (int32_t)ctx->spaces.size())
+        return b2k_fail(ctx, B2K_EINVAL, "vec_alloc_range: bad space %d", space);
+    B2kSpace& s = ctx->spaces[space];
+    int32_t run = 0;
+    for (int32_t c = 0; c < s.ncols; ++c) {
+        run = s.used[c] ? 0 : run + 1;
+        if (run == count) {
+            int32_t c0 = c - count + 1;
+            for (int32_t i = c0; i <= c; ++i) s.used[i] = 1;
+            *first = B2K_VEC(space, c0);
+            return B2K_OK;
+        }
+    }
+    return b2k_fail(ctx, B2K_ENOMEM, "vec_alloc_range: no %d consecutive free columns", count);
+}
+
+extern "C" int32_t b2k_vec_free(b2k_ctx* ctx, b2k_vec v) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef r;
+    B2K_TRY(b2k_resolve(ctx, v, &r));
+    ctx->spaces[r.space].used[r.col] = 0;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_upload(b2k_ctx* ctx, b2k_vec v, const void* host) {
+    if (!ctx || !host) return B2K_EINVAL;
+    VecRef r;
+    B2K_TRY(b2k_resolve(ctx, v, &r));
+    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2K_CUDA(ctx, cudaMemcpyAsync(r.ptr, host, (size_t)r.n * ctx->esize, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_download(b2k_ctx* ctx, b2k_vec v, void* host) {
+    if (!ctx || !host) return B2K_EINVAL;
+    VecRef r;
+    B2K_TRY(b2k_resolve(ctx, v, &r));
+    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2K_CUDA(ctx, cudaMemcpyAsync(host, r.ptr, (size_t)r.n * ctx->esize, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_copy(b2k_ctx* ctx, b2k_vec dst, b2k_vec src) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef d, s;
+    B2K_TRY(b2k_resolve(ctx, dst, &d));
+    B2K_TRY(b2k_resolve(ctx, src, &s));
+    if (d.n != s.n) return b2k_fail(ctx, B2K_EDIM, "vec_copy: length %lld vs %lld",
+                                    (long long)d.n, (long long)s.n);
+    if (d.ptr == s.ptr) return B2K_OK;
+    B2K_CUDA(ctx, cudaMemcpyAsync(d.ptr, s.ptr, (size_t)d.n * ctx->esize,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_vec_zero(b2k_ctx* ctx, b2k_vec v) {
+    if (!ctx) return B2K_EINVAL;
+    VecRef r;
+    B2K_TRY(b2k_resolve(ctx, v, &r));
+    B2K_CUDA(ctx, cudaMemsetAsync(r.ptr, 0, (size_t)r.n * ctx->esize, ctx->stream));
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------ scalar plumbing ----
+
+int32_t b2k_allreduce(b2k_ctx* ctx, double* dptr, int32_t count, int32_t sharded) {
+    if (ctx->nranks > 1 && sharded) return b2k_nccl_allreduce_f64(ctx, dptr, count);
+    return B2K_OK;
+}
+
+int32_t b2k_fetch_results(b2k_ctx* ctx, int32_t count, int32_t sharded) {
+    if (count > B2K_RES_DOUBLES) return b2k_fail(ctx, B2K_EINVAL, "fetch_results: too many");
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res, count, sharded));
+    B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(double) * count,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+static int32_t wait_staging(b2k_ctx* ctx) {
+    if (ctx->coef_busy) {
+        B2K_CUDA(ctx, cudaEventSynchronize(ctx->ev_coef));
+        ctx->coef_busy = false;
+    }
+    return B2K_OK;
+}
+
+int32_t b2k_put_coef(b2k_ctx* ctx, const double* host, int32_t count, int32_t offset) {
+    if (count < 0 || offset < 0 || offset + count > B2K_COEF_DOUBLES)
+        return b2k_fail(ctx, B2K_EINVAL, "put_coef: %d doubles at %d exceeds staging", count,
+                        offset);
+    if (count == 0) return B2K_OK;
+    B2K_TRY(wait_staging(ctx));
+    memcpy(ctx->h_coef + offset, host, sizeof(double) * count);
+    B2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_coef + offset, ctx->h_coef + offset,
+                                  sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
+    B2K_CUDA(ctx, cudaEventRecord(ctx->ev_coef, ctx->stream));
+    ctx->coef_busy = true;
+    return B2K_OK;
+}
+
+int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t slot,
+                     int32_t** dptr) {
+    if (count < 0 || count > 4096 || slot < 0 || slot >= 4)
+        return b2k_fail(ctx, B2K_EINVAL, "put_cols: bad count %d / slot %d", count, slot);
+    *dptr = ctx->d_cols + slot * 4096;
+    if (count == 0) return B2K_OK;
+    B2K_TRY(wait_staging(ctx));
+    memcpy(ctx->h_cols + slot * 4096, host, sizeof(int32_t) * count);
+    B2K_CUDA(ctx, cudaMemcpyAsync(*dptr, ctx->h_cols + slot * 4096, sizeof(int32_t) * count,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    B2K_CUDA(ctx, cudaEventRecord(ctx->ev_coef, ctx->stream));
+    ctx->coef_busy = true;
+    return B2K_OK;
+}

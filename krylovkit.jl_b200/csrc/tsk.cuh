@@ -1,0 +1,347 @@
+// tsk.cuh — the tall-skinny streaming engine.
+//
+// Every basis operation of the Krylov hot path (project!!, unproject!!, the Gram-Schmidt
+// family, basistransform!, block products, and the dense GEMV of the GKL path) is a sweep
+// over an n x k column-major panel Q with n >> k.  All of them are HBM-bound (<= 0.25
+// flop/B in FP64), so the engine is built around one thing: keeping ~200 KB of bulk
+// async copies (TMA, cp.async.bulk -> SASS UBLKCP) in flight per SM without spending
+// registers on it.
+//
+//   * one persistent CTA per SM (grid = min(#SM, #row tiles)), 288 threads:
+//     warps 0-7 = consumers, warp 8 = producer;
+//   * a row tile is R = 256 rows; a ring slot holds R rows x C columns (16 KB:
+//     C = 8 for f64, 16 for f32); NS = 12 slots form the ring, each with a full/empty
+//     mbarrier pair; the producer's lanes issue one 1-D bulk copy per column (2 KB f64),
+//     so arbitrary (non-contiguous) column handle lists cost nothing extra;
+//   * the vector being orthogonalised rides in a separate 3-deep ring ("w slots") that
+//     can also carry the two extra vectors of the Lanczos three-term prologue;
+//   * UPDATE phases map thread <-> row (sequential fma over the columns: the same
+//     association as the reference's chain of add!! calls, orthonormal.jl:146-148);
+//     PROJECT phases map warp <-> column, lane <-> rows (128-bit LDS), accumulators in
+//     registers for the whole sweep, one warp-shuffle reduction per CTA at the end;
+//   * a fused UPDATE+PROJECT phase keeps the whole R x k tile resident in the ring so Q is
+//     read from HBM once for both (this is what makes CGS2 (3k+5)W instead of (4k+6)W);
+//   * reductions are deterministic: per-CTA partials at fixed slots, summed in CTA order
+//     by every consumer of the next phase (or by the finalize kernel).  No FP atomics.
+#pragma once
+#include "common.cuh"
+
+namespace tsk {
+
+template <typename T> struct Cfg;
+template <> struct Cfg<double> {
+    static constexpr int R = 256, C = 8, VEC = 2;
+    using V16 = double2;
+    __device__ static __forceinline__ void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+};
+template <> struct Cfg<float> {
+    static constexpr int R = 256, C = 16, VEC = 4;
+    using V16 = float4;
+    __device__ static __forceinline__ void unpack(const float4& v, float* o) {
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+};
+
+constexpr int NS = 12;         // ring slots
+constexpr int NW = 3;          // w slots
+constexpr int NCONS = 256;     // consumer threads
+constexpr int NTHREADS = 288;  // + producer warp
+constexpr int MAXCH = 16;      // chunks per pass  -> KCAP = MAXCH * C columns per pass
+constexpr int SLOT_BYTES = 16384;
+
+template <typename T> constexpr int kcap() { return MAXCH * Cfg<T>::C; }
+
+// shared memory carve-up (bytes)
+constexpr int OFF_RING = 0;
+constexpr int OFF_WRING = NS * SLOT_BYTES;                  // 196608
+constexpr int WSLOT_MAX = 3 * 256 * 8;                      // 6144
+constexpr int OFF_W1 = OFF_WRING + NW * WSLOT_MAX;          // 215040
+constexpr int OFF_CS = OFF_W1 + 2 * 256 * 8;                // 219136
+constexpr int OFF_RED = OFF_CS + 1024;                      // 220160
+constexpr int OFF_BAR = OFF_RED + 512;                      // 220672
+constexpr int SMEM_BYTES = OFF_BAR + (2 * NS + 2 * NW) * 8; // 220912
+
+struct ColList {
+    int32_t c[256];
+};
+
+template <typename T>
+struct PhaseParams {
+    const T* base;   // panel base (column 0 of the slab / dense matrix)
+    int64_t ld;      // leading dimension (elements)
+    int64_t n;       // rows
+    int32_t k;       // columns in this pass (<= kcap<T>())
+    // the streamed vector
+    const T* x;
+    T* xout;         // may be nullptr
+    const T* e1;     // prologue vectors (nvec == 3): x' = (x + c1*e1) + c2*e2
+    const T* e2;
+    T c1, c2;
+    int32_t nvec;    // 1 or 3
+    int32_t store_x; // write x'' (UPDATE) or x' (prologue write-back) to xout
+    // UPDATE: x'' = betax*x' + sum_j Q[:,j]*cs[j],  cs[j] = alphac * sum_g coef[g*stride+j]
+    const double* coef;
+    const T* coef_t;     // alternative: coefficients stored as a device vector of T
+    int32_t coef_sets;
+    int32_t coef_stride;
+    T alphac, betax;
+    int32_t beta_mode;   // 0: hard zero, 1: one, 2: general
+    // outputs
+    double* part_h;  // [grid][B2K_KSTRIDE] projection partials (PROJECT)
+    double* part_n;  // [grid] partial ||x''||^2 (may be nullptr)
+};
+
+struct Pipe {
+    uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+};
+
+struct SmemView {
+    uint8_t* raw;
+    uint32_t ring, wring, full, empty, wfull, wempty;   // shared-space addresses
+    __device__ explicit SmemView(uint8_t* p) : raw(p) {
+        ring = smem_u32(p + OFF_RING);
+        wring = smem_u32(p + OFF_WRING);
+        full = smem_u32(p + OFF_BAR);
+        empty = full + NS * 8;
+        wfull = empty + NS * 8;
+        wempty = wfull + NW * 8;
+    }
+};
+
+__device__ __forceinline__ void pipe_setup(const SmemView& sm, bool zero_ring) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(sm.full + 8 * i, 1);
+            mbar_init(sm.empty + 8 * i, NCONS / 32);
+        }
+        for (int i = 0; i < NW; ++i) {
+            mbar_init(sm.wfull + 8 * i, 1);
+            mbar_init(sm.wempty + 8 * i, NCONS / 32);
+        }
+        fence_mbar_init();
+    }
+    if (zero_ring) {
+        // the CTA that owns the ragged last tile multiplies stale slot rows by zero:
+        // make sure "stale" can never be a NaN bit pattern left by a previous kernel.
+        uint4* q = reinterpret_cast<uint4*>(sm.raw);
+        for (int i = threadIdx.x; i < OFF_CS / 16; i += blockDim.x) q[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- producer ----
+template <typename T>
+__device__ __forceinline__ void producer_phase(const PhaseParams<T>& p, const ColList& cl,
+                                               const SmemView& sm, Pipe& st) {
+    using CF = Cfg<T>;
+    constexpr int R = CF::R, C = CF::C;
+    const int lane = threadIdx.x & 31;
+    const int nch = (p.k + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        const uint32_t bytes = (uint32_t)((rt * sizeof(T) + 15) & ~(size_t)15);
+        // the vector tile (+ prologue vectors)
+        mbar_wait(sm.wempty + 8 * st.ws, st.wph ^ 1);
+        if (lane == 0) mbar_expect_tx(sm.wfull + 8 * st.ws, bytes * (uint32_t)p.nvec);
+        __syncwarp();
+        if (lane < p.nvec) {
+            const T* src = (lane == 0) ? p.x : (lane == 1 ? p.e1 : p.e2);
+            bulk_g2s(sm.wring + st.ws * (3 * R * (int)sizeof(T)) + lane * R * (int)sizeof(T),
+                     src + r0, bytes, sm.wfull + 8 * st.ws);
+        }
+        if (++st.ws == NW) { st.ws = 0; st.wph ^= 1; }
+        // the panel tile, C columns per slot
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(sm.empty + 8 * st.s, st.ph ^ 1);
+            const int ncol = (p.k - c * C) < C ? (p.k - c * C) : C;
+            if (lane == 0) mbar_expect_tx(sm.full + 8 * st.s, bytes * (uint32_t)ncol);
+            __syncwarp();
+            if (lane < ncol) {
+                const T* src = p.base + (int64_t)cl.c[c * C + lane] * p.ld + r0;
+                bulk_g2s(sm.ring + st.s * SLOT_BYTES + lane * R * (int)sizeof(T), src, bytes,
+                         sm.full + 8 * st.s);
+            }
+            if (++st.s == NS) { st.s = 0; st.ph ^= 1; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- consumers ----
+template <typename T> struct VecOps;
+template <> struct VecOps<double> {
+    __device__ static __forceinline__ void fma_acc(double& acc, const double2& q, const double2& x) {
+        acc = fma(q.x, x.x, acc);
+        acc = fma(q.y, x.y, acc);
+    }
+};
+template <> struct VecOps<float> {
+    __device__ static __forceinline__ void fma_acc(float& acc, const float4& q, const float4& x) {
+        acc = fmaf(q.x, x.x, acc);
+        acc = fmaf(q.y, x.y, acc);
+        acc = fmaf(q.z, x.z, acc);
+        acc = fmaf(q.w, x.w, acc);
+    }
+};
+
+template <typename T, bool UPDATE, bool PROJECT>
+__device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const SmemView& sm,
+                                               Pipe& st) {
+    using CF = Cfg<T>;
+    using V16 = typename CF::V16;
+    constexpr int R = CF::R, C = CF::C, VEC = CF::VEC;
+    constexpr int CPW = C / 8;             // columns per warp per chunk
+    constexpr int NLD = R / (32 * VEC);    // 128-bit loads per column per lane
+    const int tid = threadIdx.x;           // 0..255
+    const int lane = tid & 31, w = tid >> 5;
+    const int nch = (p.k + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    T* cs = reinterpret_cast<T*>(sm.raw + OFF_CS);
+    T* w1 = reinterpret_cast<T*>(sm.raw + OFF_W1);
+    double* red = reinterpret_cast<double*>(sm.raw + OFF_RED);
+
+    if (UPDATE) {
+        // every CTA reduces the previous phase's partials itself, in CTA order
+        for (int j = tid; j < p.k; j += NCONS) {
+            double h;
+            if (p.coef_t) {
+                h = (double)p.coef_t[j];
+            } else {
+                const volatile double* src = p.coef + j;
+                h = 0.0;
+                for (int g = 0; g < p.coef_sets; ++g) h += src[(size_t)g * p.coef_stride];
+            }
+            cs[j] = p.alphac * (T)h;
+        }
+        named_bar_sync(1, NCONS);
+    }
+
+    T acc_h[MAXCH][CPW];
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c)
+#pragma unroll
+        for (int cc = 0; cc < CPW; ++cc) acc_h[c][cc] = (T)0;
+    T nrm = (T)0;
+    int buf = 0;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        mbar_wait(sm.wfull + 8 * st.ws, st.wph);
+        const T* wv = reinterpret_cast<const T*>(sm.raw + OFF_WRING) + st.ws * 3 * R;
+        T xv = wv[tid];
+        if (p.nvec == 3) {
+            xv = fma(p.c1, wv[R + tid], xv);
+            xv = fma(p.c2, wv[2 * R + tid], xv);
+        }
+        if (tid >= rt) xv = (T)0;
+        T acc = xv;
+        const uint32_t s0 = st.s, ph0 = st.ph;
+        if (UPDATE) {
+            acc = (p.beta_mode == 0) ? (T)0 : (p.beta_mode == 1 ? xv : p.betax * xv);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(sm.full + 8 * st.s, st.ph);
+                const T* slot = reinterpret_cast<const T*>(sm.raw + OFF_RING + st.s * SLOT_BYTES);
+                const int ncol = (p.k - c * C) < C ? (p.k - c * C) : C;
+                if (ncol == C) {
+                    T cv[C];
+#pragma unroll
+                    for (int i = 0; i < C / VEC; ++i)
+                        CF::unpack(*reinterpret_cast<const V16*>(cs + c * C + i * VEC), cv + i * VEC);
+#pragma unroll
+                    for (int jj = 0; jj < C; ++jj) acc = fma(slot[jj * R + tid], cv[jj], acc);
+                } else {
+                    for (int jj = 0; jj < ncol; ++jj) acc = fma(slot[jj * R + tid], cs[c * C + jj], acc);
+                }
+                if (!PROJECT) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sm.empty + 8 * st.s);
+                }
+                if (++st.s == NS) { st.s = 0; st.ph ^= 1; }
+            }
+            if (tid >= rt) acc = (T)0;
+        }
+        if (p.store_x && tid < rt) p.xout[r0 + tid] = acc;
+        if (p.part_n) nrm = fma(acc, acc, nrm);
+        if (PROJECT) {
+            T* wb = w1 + buf * R;
+            wb[tid] = acc;
+            named_bar_sync(1, NCONS);
+            V16 xr[NLD];
+#pragma unroll
+            for (int i = 0; i < NLD; ++i)
+                xr[i] = *reinterpret_cast<const V16*>(wb + VEC * lane + 32 * VEC * i);
+            uint32_t ss = UPDATE ? s0 : st.s, pp = UPDATE ? ph0 : st.ph;
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+                if (c < nch) {
+                    if (!UPDATE) mbar_wait(sm.full + 8 * ss, pp);
+                    const T* slot = reinterpret_cast<const T*>(sm.raw + OFF_RING + ss * SLOT_BYTES);
+#pragma unroll
+                    for (int cc = 0; cc < CPW; ++cc) {
+                        const int cj = cc * 8 + w;
+                        if (c * C + cj < p.k) {
+                            const T* colp = slot + cj * R;
+#pragma unroll
+                            for (int i = 0; i < NLD; ++i) {
+                                V16 q = *reinterpret_cast<const V16*>(colp + VEC * lane + 32 * VEC * i);
+                                VecOps<T>::fma_acc(acc_h[c][cc], q, xr[i]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sm.empty + 8 * ss);
+                    if (++ss == NS) { ss = 0; pp ^= 1; }
+                }
+            }
+            if (!UPDATE) { st.s = ss; st.ph = pp; }
+            buf ^= 1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.wempty + 8 * st.ws);
+        if (++st.ws == NW) { st.ws = 0; st.wph ^= 1; }
+    }
+
+    if (PROJECT) {
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+#pragma unroll
+            for (int cc = 0; cc < CPW; ++cc) {
+                const int j = c * C + cc * 8 + w;
+                double v = warp_sum((double)acc_h[c][cc]);   // warp-uniform branch below
+                if (c < nch && j < p.k && lane == 0)
+                    p.part_h[(size_t)blockIdx.x * B2K_KSTRIDE + j] = v;
+            }
+        }
+    }
+    if (p.part_n) {
+        double v = warp_sum((double)nrm);
+        if (lane == 0) red[w] = v;
+        named_bar_sync(1, NCONS);
+        if (tid == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < NCONS / 32; ++i) s += red[i];
+            p.part_n[blockIdx.x] = s;
+        }
+    }
+}
+
+// grid-wide barrier for the cooperative fused kernel.  `target` is the value the
+// monotonically increasing counter reaches when every CTA has arrived.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        while ((int)(*(volatile unsigned*)counter - target) < 0) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+}  // namespace tsk
