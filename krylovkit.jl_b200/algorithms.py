@@ -1,0 +1,124 @@
+"""Algorithm parameter structs and Orthogonalizer tags — mirror of src/algorithms.jl.
+
+Only the contract is mirrored (names, defaults, meaning); the tags select the kernel
+variant in libb200krylov (B2K_CGS ... B2K_MGSIR).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+from . import _lib as L
+
+# verbosity levels — src/KrylovKit.jl:159-162
+SILENT_LEVEL, WARN_LEVEL, STARTSTOP_LEVEL, EACHITERATION_LEVEL = 0, 1, 2, 3
+
+
+# ---- Orthogonalizer hierarchy — src/algorithms.jl:17-80 -----------------------------
+@dataclass(frozen=True)
+class Orthogonalizer:
+    tag: int = -1
+    eta: float = 0.0
+
+    @property
+    def is_reorth2(self) -> bool:      # Union{ClassicalGramSchmidt2, ModifiedGramSchmidt2}
+        return self.tag in (L.CGS2, L.MGS2)
+
+    @property
+    def is_ir(self) -> bool:           # Union{ClassicalGramSchmidtIR, ModifiedGramSchmidtIR}
+        return self.tag in (L.CGSIR, L.MGSIR)
+
+
+@dataclass(frozen=True)
+class ClassicalGramSchmidt(Orthogonalizer):
+    tag: int = L.CGS
+
+
+@dataclass(frozen=True)
+class ModifiedGramSchmidt(Orthogonalizer):
+    tag: int = L.MGS
+
+
+@dataclass(frozen=True)
+class ClassicalGramSchmidt2(Orthogonalizer):
+    tag: int = L.CGS2
+
+
+@dataclass(frozen=True)
+class ModifiedGramSchmidt2(Orthogonalizer):
+    tag: int = L.MGS2
+
+
+@dataclass(frozen=True)
+class ClassicalGramSchmidtIR(Orthogonalizer):
+    tag: int = L.CGSIR
+    eta: float = 1.0 / 2.0 ** 0.5       # algorithms.jl:67
+
+
+@dataclass(frozen=True)
+class ModifiedGramSchmidtIR(Orthogonalizer):
+    tag: int = L.MGSIR
+    eta: float = 1.0 / 2.0 ** 0.5       # algorithms.jl:80
+
+
+cgs, mgs, cgs2, mgs2 = (ClassicalGramSchmidt(), ModifiedGramSchmidt(), ClassicalGramSchmidt2(),
+                        ModifiedGramSchmidt2())
+cgsr, mgsr = ClassicalGramSchmidtIR(), ModifiedGramSchmidtIR()
+
+
+# ---- KrylovDefaults — src/algorithms.jl:556-564 -------------------------------------
+class KrylovDefaults:
+    orth: Orthogonalizer = mgs2
+    krylovdim: int = 30
+    maxiter: int = 100
+    tol: float = 1e-12
+    verbosity: int = WARN_LEVEL
+
+
+# ---- algorithm structs — src/algorithms.jl:110-521 (the ones on the scoped path) ----
+@dataclass(frozen=True)
+class Lanczos:
+    orth: Orthogonalizer = field(default_factory=lambda: KrylovDefaults.orth)
+    krylovdim: int = KrylovDefaults.krylovdim
+    maxiter: int = KrylovDefaults.maxiter
+    tol: float = KrylovDefaults.tol
+    eager: bool = False
+    verbosity: int = KrylovDefaults.verbosity
+
+
+@dataclass(frozen=True)
+class Arnoldi:
+    orth: Orthogonalizer = field(default_factory=lambda: KrylovDefaults.orth)
+    krylovdim: int = KrylovDefaults.krylovdim
+    maxiter: int = KrylovDefaults.maxiter
+    tol: float = KrylovDefaults.tol
+    eager: bool = False
+    verbosity: int = KrylovDefaults.verbosity
+
+
+@dataclass(frozen=True)
+class GKL:
+    orth: Orthogonalizer = field(default_factory=lambda: KrylovDefaults.orth)
+    krylovdim: int = KrylovDefaults.krylovdim
+    maxiter: int = KrylovDefaults.maxiter
+    tol: float = KrylovDefaults.tol
+    eager: bool = False
+    verbosity: int = KrylovDefaults.verbosity
+
+
+@dataclass(frozen=True)
+class GMRES:
+    orth: Orthogonalizer = field(default_factory=lambda: KrylovDefaults.orth)
+    maxiter: int = KrylovDefaults.maxiter
+    krylovdim: int = KrylovDefaults.krylovdim
+    tol: float = KrylovDefaults.tol
+    verbosity: int = KrylovDefaults.verbosity
+
+
+@dataclass
+class ConvergenceInfo:
+    """src/KrylovKit.jl:212-218.  numops = operator applications, numiter = restart cycles."""
+    converged: int
+    residual: object
+    normres: object
+    numiter: int
+    numops: int
