@@ -1,0 +1,373 @@
+"""bench.py — eigsolve(Lanczos) iterations/sec on the 1e7 x 1e7 CSR 5-point Laplacian
+(BASELINE.json configs[1]), Float64, krylovdim = 60, ClassicalGramSchmidt2, 5 restart cycles.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+A "step" is one whole eigsolve job: Lanczos factorization to krylovdim 60, then 4 thick
+restarts (keep 36, re-expand 24) = 156 operator applications (`info.numops`), with the
+convergence tolerance at 0 so the amount of work is fixed.  The metric is operator
+applications per second (KrylovKit's numops/s, SURVEY §5 "iterations/sec").
+
+  value    : inputs (A as CSR, x0) already resident in HBM when the timed region starts,
+             timed with CUDA events on the library's stream, max over ranks.
+  e2e      : the same job through the host-buffer API — kk.eigsolve(A_csr_host, x0_host, ...):
+             context creation, H2D of A and x0 from pinned memory, the solve, D2H of the Ritz
+             vectors into pinned memory, all inside the timed region (wall clock around
+             device-synchronised calls).
+  roofline : the fused Gram-Schmidt sweep (the dominant kernel): algorithmic bytes
+             (2k+3)*8n per launch (SURVEY §8d "one CGS pass", k = basis size incl. the new
+             vector) summed over the launches of the timed region / their summed device time
+             (CUDA events around every launch, on the launching stream), vs the measured HBM
+             peak in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the restated reference path (oracle/krylov_oracle.py,
+             numpy + OpenBLAS on all host cores; no Julia in the image) on a bounded sample
+             of the same workload at full n: initialize + 30 expand! steps (31 operator
+             applications at basis sizes 1..31 — the cheap early part of a cycle, so the
+             CPU figure is optimistic).
+
+N > 1: STRONG scaling — the same 1e7-row problem row-sharded over N ranks (halo exchange
+for the SpMV + NCCL all-reduce of the projection coefficients).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20260923
+HOWMANY = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4000)
+    ap.add_argument("--ny", type=int, default=2500)
+    ap.add_argument("--krylovdim", type=int, default=60)
+    ap.add_argument("--cycles", type=int, default=5)
+    ap.add_argument("--orth", default="cgs2", choices=["cgs2", "mgs2", "cgs", "mgs"])
+    ap.add_argument("--cpu-steps", type=int, default=30, help="expand! steps in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def pinned_array(lib, count, dtype):
+    dt = np.dtype(dtype)
+    p = C.c_void_p()
+    st = lib.b2k_pinned_alloc(count * dt.itemsize, C.byref(p))
+    if st != 0:
+        raise MemoryError("cudaHostAlloc failed")
+    buf = (C.c_byte * (count * dt.itemsize)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dt, count=count), p
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(nx, ny, krylovdim, orth_name, nsteps, A=None):
+    """Restated reference path on the host cores: initialize + nsteps expand! at full n."""
+    from oracle import krylov_oracle as ko
+    orth = {"cgs2": ko.Orth(ko.CGS2), "mgs2": ko.Orth(ko.MGS2), "cgs": ko.Orth(ko.CGS),
+            "mgs": ko.Orth(ko.MGS)}[orth_name]
+    if A is None:
+        A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(SEED, nx * ny)
+    t0 = time.perf_counter()
+    f = ko.lanczos_initialize(A, x0, orth)
+    for _ in range(nsteps):
+        f = ko.lanczos_expand(A, f, orth)
+    dt = time.perf_counter() - t0
+    numops = nsteps + 1
+    return numops / dt, dt, numops
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import krylov_oracle as ko
+    cores = os.cpu_count() or 1
+    A = ko.stencil_matrix(a.nx, a.ny)
+    nsteps = a.cpu_steps
+    for _ in range(min(a.warmup, 1)):
+        cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, min(nsteps, 4), A)
+    t_tot, ops_tot = 0.0, 0
+    for _ in range(a.steps):
+        v, dt, ops = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, nsteps, A)
+        t_tot += dt
+        ops_tot += ops
+    value = ops_tot / t_tot
+    sample = (f"initialize + {nsteps} expand! steps ({nsteps + 1} operator applications, basis sizes 1..{nsteps + 1}) "
+              f"of the full n={a.nx * a.ny} job per step; oracle/krylov_oracle.py, numpy+OpenBLAS, scipy CSR matvec")
+    line = {
+        "impl": "reference", "metric": "eigsolve_lanczos_operator_applications_per_sec", "value": value,
+        "unit": "it/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1000.0 * t_tot / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a):
+    return {"workload": f"eigsolve(Lanczos, :SR, {HOWMANY}) on the {a.nx * a.ny}x{a.nx * a.ny} CSR 5-point "
+                        f"Laplacian ({a.nx}x{a.ny} grid, Dirichlet), Float64, krylovdim={a.krylovdim}, "
+                        f"orth={a.orth}, {a.cycles} restart cycles (tol=0: fixed work)",
+            "n": a.nx * a.ny, "krylovdim": a.krylovdim, "restart_cycles": a.cycles, "orth": a.orth,
+            "l2": "inputs (4.9 GB basis, 0.8 GB matrix) >> 126 MB L2; no explicit flush",
+            "parallelism": f"rows sharded over {a.gpus} GPU(s)" if a.gpus > 1 else "single GPU"}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import krylovkit_jl_b200 as kk
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    dist = None
+    n = a.nx * a.ny
+    orth = {"cgs2": kk.cgs2, "mgs2": kk.mgs2, "cgs": kk.cgs, "mgs": kk.mgs}[a.orth]
+    alg = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=a.cycles, tol=0.0, verbosity=0)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            assert kk._lib.load().b2k_nccl_unique_id(buf) == 0
+            uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        uid_bytes = bytes(uid.cpu().tolist())
+        # shard whole grid lines: rows [y0*nx, y1*nx)
+        y0 = (a.ny * rank) // world
+        y1 = (a.ny * (rank + 1)) // world
+        ctx = kk.B200Context((y1 - y0) * a.nx, a.krylovdim + 8, device=local_rank, rank=rank, nranks=world,
+                             nccl_uid=uid_bytes, n_global=n, row_offset=y0 * a.nx)
+    else:
+        ctx = kk.B200Context(n, a.krylovdim + 8, device=local_rank)
+    lib = ctx.lib
+    op = kk.B200CSR.stencil(ctx, a.nx, a.ny)
+    x0 = ctx.splitmix(SEED)
+
+    def job():
+        return kk.eigsolve(op, x0, HOWMANY, "SR", alg)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        lib.b2k_device_sync()
+
+    for _ in range(a.warmup):
+        vals, vecs, info = job()
+        del vecs
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.b2k_prof_reset(ctx.h)
+    lib.b2k_prof_enable(ctx.h, 1)
+    launches0 = ctx.launches
+    barrier()
+    lib.b2k_timer_start(ctx.h)
+    t0 = time.perf_counter()
+    numops = 0
+    for _ in range(a.steps):
+        vals, vecs, info = job()
+        numops += info.numops
+        del vecs
+    ms = C.c_double()
+    lib.b2k_timer_stop(ctx.h, C.byref(ms))
+    barrier()
+    wall = time.perf_counter() - t0
+    lib.b2k_prof_enable(ctx.h, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    t_dev = ms.value / 1000.0
+    if dist is not None:
+        import torch
+        tt = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+        ll = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ll)
+        launches = int(ll.item())
+    value = numops / t_dev
+
+    # roofline of the dominant kernel (fused Gram-Schmidt sweep) + SpMV beside it
+    def prof(cls):
+        c, m, b = C.c_int64(), C.c_double(), C.c_double()
+        lib.b2k_prof_read(ctx.h, cls, C.byref(c), C.byref(m), C.byref(b))
+        return c.value, m.value, b.value
+    pk, pk_kind = peak_hbm()
+    kern = {}
+    for cls, name in ((1, "gs_fused"), (0, "spmv_csr"), (2, "basis_transform")):
+        c, m, b = prof(cls)
+        if c:
+            kern[name] = {"launches": c, "ms_total": round(m, 3), "avg_ms": round(m / c, 4),
+                          "GBs": round(b / m / 1e6, 1), "frac": round(b / m / 1e6 / pk, 3),
+                          "share_of_step": round(m / (ms.value), 3)}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("gs_fused_bytes_per_launch")
+    gs = kern.get("gs_fused", {})
+    roofline = {"kernel": "k_gs_fused<double> (3-term prologue + project, grid barrier, update + norm)",
+                "bound": "hbm", "achieved": gs.get("GBs"), "peak": pk, "unit": "GB/s",
+                "frac": gs.get("frac"), "peak_kind": pk_kind, "traffic": traffic,
+                "algorithmic_bytes": "(2k+3)*8n per launch, k = basis size incl. the new vector; summed over launches",
+                "avg_launch_ms": gs.get("avg_ms")}
+
+    # ---- end to end through the host-buffer API (rank 0 / single GPU only) ----
+    e2e = None
+    if not a.no_e2e and world == 1:
+        rp, prp = pinned_array(lib, op.n_rows + 1, np.int32)
+        ci, pci = pinned_array(lib, op.nnz, np.int32)
+        va, pva = pinned_array(lib, op.nnz, np.float64)
+        ctx.check(lib.b2k_op_csr_download(ctx.h, op.h, rp.ctypes.data, ci.ctypes.data, va.ctypes.data))
+        xh, pxh = pinned_array(lib, n, np.float64)
+        x0.to_host(xh)
+        outs = [pinned_array(lib, n, np.float64) for _ in range(HOWMANY)]
+        out_arrs = [o[0] for o in outs]
+        h2d = rp.nbytes + ci.nbytes + va.nbytes + xh.nbytes
+        d2h = sum(o.nbytes for o in out_arrs) + 8 * HOWMANY
+
+        def job_e2e():
+            return kk.eigsolve((rp, ci, va), xh, HOWMANY, "SR", alg, out_vectors=out_arrs)
+
+        for _ in range(max(1, min(a.warmup, 2))):
+            job_e2e()
+        lib.b2k_device_sync()
+        t0 = time.perf_counter()
+        ops = 0
+        for _ in range(a.steps):
+            v2, vec2, info2 = job_e2e()
+            ops += info2.numops
+        lib.b2k_device_sync()
+        te = time.perf_counter() - t0
+        assert np.allclose(v2, vals, rtol=1e-12), (v2, vals)
+        e2e = {"value": ops / te, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1000.0 * te / a.steps,
+               "path": "kk.eigsolve(csr_host_arrays, x0_host, ...): ctx create + H2D (pinned) + solve + D2H (pinned)"}
+        for p in (prp, pci, pva, pxh, *[o[1] for o in outs]):
+            lib.b2k_pinned_free(p)
+    elif world > 1:
+        e2e = {"value": None, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "host-buffer path measured at N=1 only"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        A_host = None
+        v, dt, ops = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, a.cpu_steps, A_host)
+        cpu = {"value": v, "unit": "it/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"initialize + {a.cpu_steps} expand! steps ({ops} operator applications, basis sizes "
+                         f"1..{a.cpu_steps + 1}) of the same n={n} job in {dt:.1f} s; oracle/krylov_oracle.py "
+                         "(restated reference, numpy+OpenBLAS all cores, scipy CSR matvec single-threaded like "
+                         "SparseArrays); no Julia in the image"}
+
+    if rank == 0:
+        line = {
+            "metric": "eigsolve_lanczos_operator_applications_per_sec", "value": value, "unit": "it/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * t_dev / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(a),
+            "numops_per_step": numops // a.steps, "wall_s": wall,
+            "ritz_values": [float(v) for v in vals[:HOWMANY]],
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,21 @@ int64_t b2k_ctx_launch_count(const b2k_ctx* ctx);
 /* raw CUDA stream (cudaStream_t) for event timing by the caller */
 void*   b2k_ctx_stream(b2k_ctx* ctx);
 
+/* Instrumentation (not part of the KrylovKit contract): per-kernel-class device timing with
+ * CUDA events on the context stream.  class 0 = CSR SpMV, 1 = fused Gram-Schmidt sweep,
+ * 2 = basis transform, 3 = project, 4 = unproject.  `bytes` = algorithmic bytes
+ * (SURVEY §8d figures) summed over the recorded launches, `ms` their summed duration. */
+int32_t b2k_prof_enable(b2k_ctx* ctx, int32_t on);
+int32_t b2k_prof_reset(b2k_ctx* ctx);
+int32_t b2k_prof_read(b2k_ctx* ctx, int32_t cls, int64_t* count, double* ms, double* bytes);
+/* CUDA-event stopwatch on the context stream (start synchronises the stream first). */
+int32_t b2k_timer_start(b2k_ctx* ctx);
+int32_t b2k_timer_stop(b2k_ctx* ctx, double* ms);
+/* page-locked host memory for fast uploads / downloads, and a whole-device sync */
+int32_t b2k_pinned_alloc(size_t bytes, void** out);
+int32_t b2k_pinned_free(void* p);
+int32_t b2k_device_sync(void);
+
 /* ------------------------------------------------- vectors (VectorInterface) ---- */
 /* zerovector / similar: src/innerproductvec.jl:82-137 is the reference's own list of
  * what a vector type must provide. */

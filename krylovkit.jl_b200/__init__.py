@@ -20,3 +20,9 @@ from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, ort
 from .vectors import B200Context, B200Vec, inner, norm
 
 __all__ = [n for n in dir() if not n.startswith("_")]
+from .eigsolve import eigsolve
+from .linsolve import linsolve
+from .svdsolve import svdsolve
+from . import factorizations
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -53,6 +53,14 @@ _PROTOS = {
     "b2k_ctx_sync": (C.c_int32, [c_ctx]),
     "b2k_ctx_launch_count": (C.c_int64, [c_ctx]),
     "b2k_ctx_stream": (C.c_void_p, [c_ctx]),
+    "b2k_prof_enable": (C.c_int32, [c_ctx, C.c_int32]),
+    "b2k_prof_reset": (C.c_int32, [c_ctx]),
+    "b2k_prof_read": (C.c_int32, [c_ctx, C.c_int32, P(C.c_int64), P(C.c_double), P(C.c_double)]),
+    "b2k_timer_start": (C.c_int32, [c_ctx]),
+    "b2k_timer_stop": (C.c_int32, [c_ctx, P(C.c_double)]),
+    "b2k_pinned_alloc": (C.c_int32, [C.c_size_t, P(C.c_void_p)]),
+    "b2k_pinned_free": (C.c_int32, [C.c_void_p]),
+    "b2k_device_sync": (C.c_int32, []),
     "b2k_vec_alloc": (C.c_int32, [c_ctx, C.c_int32, P(c_vec)]),
     "b2k_vec_alloc_range": (C.c_int32, [c_ctx, C.c_int32, C.c_int32, P(c_vec)]),
     "b2k_vec_free": (C.c_int32, [c_ctx, c_vec]),

@@ -335,7 +335,9 @@ int32_t project_t(b2k_ctx* ctx, const Panel& pn, const VecRef& x, int k, int res
         fill_cols<T>(cl, pn.idx, off, kk);
         PhaseParams<T> p = base_params<T>(pn, kk, x.ptr, nullptr);
         p.part_h = b2k_part_set(ctx, 0);
+        const int pr = b2k_prof_begin(ctx, 3, (kk + 1.0) * sizeof(T) * (double)pn.n);
         B2K_TRY((launch_phase_t<T, false, true>(ctx, p, cl, grid)));
+        b2k_prof_end(ctx, pr);
         B2K_TRY(enqueue_finalize(ctx, b2k_part_set(ctx, 0), nullptr, nullptr, grid, kk,
                                  res_off + off, 0));
     }
@@ -366,7 +368,9 @@ int32_t unproject_t(b2k_ctx* ctx, const Panel& pn, const VecRef& y, int k, const
             p.betax = (T)beta;
         }
         p.part_n = (off + kk >= k) ? part_n : nullptr;
+        const int pr = b2k_prof_begin(ctx, 4, (kk + 2.0) * sizeof(T) * (double)pn.n);
         B2K_TRY((launch_phase_t<T, true, false>(ctx, p, cl, grid)));
+        b2k_prof_end(ctx, pr);
         off += kk;
     } while (off < k);
     return B2K_OK;
@@ -420,11 +424,14 @@ int32_t cgs_fused_t(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int p
         fp.ph[nph] = p; fp.kind[nph] = 2; ++nph;
     }
     fp.nph = nph;
+    const double W = (double)sizeof(T) * (double)pn.n;
+    const int pr = b2k_prof_begin(ctx, 1, (passes == 2 ? (3.0 * k + 5.0) : (2.0 * k + 3.0)) * W);
     if (use_coop) {
         B2K_TRY(launch_fused<T>(ctx, fp, cl, grid));
     } else {
         for (int i = 0; i < nph; ++i) B2K_TRY(launch_phase<T>(ctx, fp.ph[i], cl, fp.kind[i], grid));
     }
+    b2k_prof_end(ctx, pr);
     B2K_TRY(enqueue_finalize(ctx, PA, passes == 2 ? PB : nullptr, PN, grid, k, 0, k));
     return B2K_OK;
 }
@@ -759,11 +766,13 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
         c.store_x = 1; c.coef = PA; c.coef_sets = grid; c.coef_stride = B2K_KSTRIDE;          \
         c.alphac = (T)-1; c.part_n = PN;                                                      \
         fp.ph[0] = a; fp.kind[0] = 0; fp.ph[1] = c; fp.kind[1] = 2; fp.nph = 2;               \
+        const int pr = b2k_prof_begin(ctx, 1, (2.0 * K1 + 3.0) * sizeof(T) * (double)pn.n);   \
         if (g_use_coop) { B2K_TRY(launch_fused<T>(ctx, fp, cl, grid)); }                      \
         else {                                                                                \
             B2K_TRY(launch_phase<T>(ctx, fp.ph[0], cl, 0, grid));                             \
             B2K_TRY(launch_phase<T>(ctx, fp.ph[1], cl, 2, grid));                             \
         }                                                                                     \
+        b2k_prof_end(ctx, pr);                                                                \
     }
                 if (f64) BUILD_AND_LAUNCH(double) else BUILD_AND_LAUNCH(float)
 #undef BUILD_AND_LAUNCH
@@ -854,11 +863,13 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
     p.u_in_smem = ((size_t)m * keep * ctx->esize <= (size_t)TR_U_BYTES) ? 1 : 0;
     ColList cl;
     for (int i = 0; i < m; ++i) cl.c[i] = pn.idx[i];
+    const int pr = b2k_prof_begin(ctx, 2, (double)(m + keep) * ctx->esize * (double)pn.n);
     if (f64) {
         k_transform<double><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
     } else {
         k_transform<float><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
     }
+    b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;
 }

@@ -29,6 +29,18 @@ struct B2kSpace {
 
 struct B2kNccl;   // dist.cu
 
+// optional per-kernel-class timing (CUDA events on the context stream), used by bench.py
+// for the roofline figure: class 0 = CSR SpMV, 1 = fused Gram-Schmidt, 2 = basis transform,
+// 3 = project, 4 = unproject
+constexpr int B2K_PROF_CLASSES = 8;
+struct B2kProfRec { int cls; double bytes; cudaEvent_t e0, e1; };
+struct B2kProf {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t next = 0;
+    std::vector<B2kProfRec> recs;
+};
+
 struct b2k_ctx {
     int32_t device = 0;
     int32_t dtype  = B2K_F64;
@@ -48,6 +60,7 @@ struct b2k_ctx {
     int32_t*  h_cols   = nullptr;   // pinned staging
     unsigned* d_sync   = nullptr;   // [0] ticket, [1] grid barrier counter, ...
     cudaEvent_t ev_coef = nullptr;  // guards reuse of the pinned staging buffers
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // b2k_timer_start/stop
     bool      coef_busy = false;
 
     // dist
@@ -55,6 +68,7 @@ struct b2k_ctx {
     int64_t n_global = 0, row_offset = 0;
     B2kNccl* nccl = nullptr;
 
+    B2kProf prof;
     unsigned barrier_base = 0;      // value of d_sync[1] before the next cooperative launch
     int64_t launches = 0;
     std::string err;
@@ -116,6 +130,10 @@ int32_t b2k_allreduce(b2k_ctx* ctx, double* dptr, int32_t count, int32_t sharded
 int32_t b2k_put_coef(b2k_ctx* ctx, const double* host, int32_t count, int32_t offset);
 int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t slot,
                      int32_t** dptr);
+
+// profiling (ctx.cu): returns a record index (or -1 when profiling is off)
+int  b2k_prof_begin(b2k_ctx* ctx, int cls, double bytes);
+void b2k_prof_end(b2k_ctx* ctx, int idx);
 
 // partial buffers
 static inline double* b2k_part_set(b2k_ctx* ctx, int set) {

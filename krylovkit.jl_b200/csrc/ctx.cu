@@ -158,6 +158,7 @@ extern "C" int32_t b2k_ctx_destroy(b2k_ctx* ctx) {
     if (ctx->h_cols) cudaFreeHost(ctx->h_cols);
     if (ctx->d_sync) cudaFree(ctx->d_sync);
     if (ctx->ev_coef) cudaEventDestroy(ctx->ev_coef);
+    for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B2K_OK;
@@ -349,5 +350,107 @@ int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t s
                                   cudaMemcpyHostToDevice, ctx->stream));
     B2K_CUDA(ctx, cudaEventRecord(ctx->ev_coef, ctx->stream));
     ctx->coef_busy = true;
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ profiling ----
+
+int b2k_prof_begin(b2k_ctx* ctx, int cls, double bytes) {
+    B2kProf& pf = ctx->prof;
+    if (!pf.on) return -1;
+    if (pf.next + 2 > pf.pool.size()) {
+        if (pf.pool.size() >= 65536) return -1;
+        for (int i = 0; i < 512; ++i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            pf.pool.push_back(e);
+        }
+    }
+    B2kProfRec r;
+    r.cls = cls;
+    r.bytes = bytes;
+    r.e0 = pf.pool[pf.next++];
+    r.e1 = pf.pool[pf.next++];
+    cudaEventRecord(r.e0, ctx->stream);
+    pf.recs.push_back(r);
+    return (int)pf.recs.size() - 1;
+}
+
+void b2k_prof_end(b2k_ctx* ctx, int idx) {
+    if (idx < 0) return;
+    cudaEventRecord(ctx->prof.recs[idx].e1, ctx->stream);
+}
+
+extern "C" int32_t b2k_prof_enable(b2k_ctx* ctx, int32_t on) {
+    if (!ctx) return B2K_EINVAL;
+    ctx->prof.on = on != 0;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_prof_reset(b2k_ctx* ctx) {
+    if (!ctx) return B2K_EINVAL;
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof.recs.clear();
+    ctx->prof.next = 0;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_prof_read(b2k_ctx* ctx, int32_t cls, int64_t* count, double* ms,
+                                 double* bytes) {
+    if (!ctx || cls < 0 || cls >= B2K_PROF_CLASSES) return B2K_EINVAL;
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t c = 0;
+    double t = 0.0, b = 0.0;
+    for (const B2kProfRec& r : ctx->prof.recs) {
+        if (r.cls != cls) continue;
+        float m = 0.f;
+        if (cudaEventElapsedTime(&m, r.e0, r.e1) != cudaSuccess) continue;
+        ++c;
+        t += m;
+        b += r.bytes;
+    }
+    if (count) *count = c;
+    if (ms) *ms = t;
+    if (bytes) *bytes = b;
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ host helpers ----
+
+extern "C" int32_t b2k_pinned_alloc(size_t bytes, void** out) {
+    if (!out) return B2K_EINVAL;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return b2k_fail(nullptr, B2K_ENOMEM, "cudaHostAlloc(%zu) -> %s", bytes,
+                                          cudaGetErrorString(e));
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_device_sync(void) {
+    return cudaDeviceSynchronize() == cudaSuccess ? B2K_OK : B2K_ECUDA;
+}
+
+extern "C" int32_t b2k_timer_start(b2k_ctx* ctx) {
+    if (!ctx) return B2K_EINVAL;
+    if (!ctx->ev_t0) {
+        B2K_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
+        B2K_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
+    }
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_timer_stop(b2k_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->ev_t0) return B2K_EINVAL;
+    B2K_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    B2K_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    float f = 0.f;
+    B2K_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+    *ms = f;
     return B2K_OK;
 }

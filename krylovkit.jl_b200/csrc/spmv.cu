@@ -134,12 +134,6 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     }
 }
 
-// y = A' x for CSR (scatter with atomics is non-deterministic; instead one thread per
-// nonzero row accumulates into a zeroed y with ordered per-column passes being too slow —
-// this path is only used by tests / non-symmetric GKL on sparse A, so it uses a simple
-// deterministic two-step: build-free transpose product through sorted atomics is avoided by
-// materialising A' as a second CSR at creation time (see b2k_op_apply_adjoint).
-
 // stencil assembly -------------------------------------------------------------------
 struct StencilDesc {
     int64_t nx, ny, nz;
@@ -244,16 +238,95 @@ void build_rowblocks(const int32_t* rowptr, int64_t n, std::vector<int32_t>* blk
     }
 }
 
-int32_t finish_csr(b2k_ctx* ctx, b2k_op* op, const int32_t* h_rowptr) {
-    std::vector<int32_t> blk;
-    build_rowblocks(h_rowptr, op->n_rows, &blk);
-    op->nblk = (int32_t)blk.size() - 1;
-    B2K_CUDA(ctx, cudaMalloc(&op->rowblk, sizeof(int32_t) * blk.size()));
-    B2K_CUDA(ctx, cudaMemcpyAsync(op->rowblk, blk.data(), sizeof(int32_t) * blk.size(),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    B2K_CUDA(ctx, cudaMalloc(&op->part, sizeof(double) * std::max(1, op->nblk)));
+// longest row and monotonicity of rowptr (device): out[0] = max row length, out[1] = #violations
+__global__ void k_rowptr_stats(const int32_t* __restrict__ rowptr, int64_t n, int* __restrict__ out) {
+    int mx = 0, bad = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = rowptr[i + 1] - rowptr[i];
+        mx = d > mx ? d : mx;
+        bad += d < 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx;
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mx);
+        if (bad) atomicAdd(out + 1, bad);
+    }
+}
+
+// nnz-balanced partition: block b = rows [lower_bound(rowptr, b*T), lower_bound(rowptr, (b+1)*T)).
+// With T = SP_NNZ - maxrow + 1 every block holds <= SP_NNZ nonzeros.
+__global__ void k_rowblocks(const int32_t* __restrict__ rowptr, int64_t n, int T, int nblk,
+                            int32_t* __restrict__ rowblk) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblk) return;
+    if (b == nblk) { rowblk[b] = (int32_t)n; return; }
+    const int64_t target = (int64_t)b * T;
+    int64_t lo = 0, hi = n;           // first r in [0, n] with rowptr[r] >= target
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    rowblk[b] = (int32_t)lo;
+}
+
+int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
+    const int64_t n = op->n_rows;
+    int* d_stats;
+    int h_stats[2] = {0, 0};
+    B2K_CUDA(ctx, cudaMalloc(&d_stats, 2 * sizeof(int)));
+    B2K_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(int), ctx->stream));
+    if (n > 0) {
+        k_rowptr_stats<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(op->rowptr, n, d_stats);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    B2K_CUDA(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
     B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_stats);
+    if (h_stats[1] != 0) return b2k_fail(ctx, B2K_EINVAL, "CSR: rowptr is not non-decreasing");
+    const int maxrow = h_stats[0];
+    if (maxrow <= SP_NNZ / 2) {
+        const int T = SP_NNZ - maxrow + 1;
+        op->nblk = (int32_t)std::max<int64_t>(1, (op->nnz + T - 1) / T);
+        B2K_CUDA(ctx, cudaMalloc(&op->rowblk, sizeof(int32_t) * (op->nblk + 1)));
+        k_rowblocks<<<(op->nblk + 1 + 255) / 256, 256, 0, ctx->stream>>>(op->rowptr, n, T, op->nblk,
+                                                                        op->rowblk);
+        B2K_LAUNCH_CHECK(ctx);
+    } else {
+        // irregular matrix with very long rows: greedy partition on the host
+        std::vector<int32_t> h_rowptr(n + 1), blk;
+        B2K_CUDA(ctx, cudaMemcpyAsync(h_rowptr.data(), op->rowptr, sizeof(int32_t) * (n + 1),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        build_rowblocks(h_rowptr.data(), n, &blk);
+        op->nblk = (int32_t)blk.size() - 1;
+        B2K_CUDA(ctx, cudaMalloc(&op->rowblk, sizeof(int32_t) * blk.size()));
+        B2K_CUDA(ctx, cudaMemcpyAsync(op->rowblk, blk.data(), sizeof(int32_t) * blk.size(),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    B2K_CUDA(ctx, cudaMalloc(&op->part, sizeof(double) * std::max(1, op->nblk)));
     return B2K_OK;
+}
+
+// raw host index arrays (int32/int64, base 0/1) -> device rowptr (int32) / global columns (int64)
+template <typename IT>
+__global__ void k_convert_rowptr(const IT* __restrict__ raw, int base, int32_t* __restrict__ out,
+                                 int64_t count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)((int64_t)raw[i] - base);
+}
+template <typename IT>
+__global__ void k_convert_cols(const IT* __restrict__ raw, int base, int64_t* __restrict__ out,
+                               int64_t count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int64_t)raw[i] - base;
 }
 
 // Halo plan from the global column range of the local rows (dist only).
@@ -338,42 +411,85 @@ void widen(const void* src, int64_t count, int base, std::vector<int64_t>* out) 
 
 // ------------------------------------------------------------------ creation ----
 
-static int32_t create_csr_from_host(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_t n_cols,
-                                    int64_t nnz, const std::vector<int64_t>& rowptr,
-                                    const std::vector<int64_t>& gcol, const void* vals) {
+// Upload raw index arrays and do all conversion / validation / planning on the device:
+// host work is O(1), so a host-buffer eigsolve pays only the PCIe copies.
+static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_t n_cols,
+                              int64_t nnz, const void* rowptr, const void* colidx,
+                              const void* vals, int32_t idx_bytes, int32_t index_base) {
     if (nnz >= (int64_t)1 << 31 || n_rows >= (int64_t)1 << 31)
         return b2k_fail(ctx, B2K_ENOTSUP, "CSR: nnz/rows per GPU must be < 2^31");
     if (n_rows != ctx->spaces[0].n)
         return b2k_fail(ctx, B2K_EDIM, "CSR: %lld local rows but space 0 holds %lld",
                         (long long)n_rows, (long long)ctx->spaces[0].n);
+    const int64_t rp0 = idx_bytes == 8 ? ((const int64_t*)rowptr)[0] : ((const int32_t*)rowptr)[0];
+    const int64_t rpn = idx_bytes == 8 ? ((const int64_t*)rowptr)[n_rows] : ((const int32_t*)rowptr)[n_rows];
+    if (rp0 - index_base != 0 || rpn - index_base != nnz)
+        return b2k_fail(ctx, B2K_EINVAL, "op_create_csr: rowptr does not span [0, nnz]");
+    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
     b2k_op* op = new b2k_op();
     op->kind = 0;
     op->n_rows = n_rows;
     op->n_cols = n_cols;
     op->nnz = nnz;
-    std::vector<int32_t> rp32(n_rows + 1);
-    for (int64_t i = 0; i <= n_rows; ++i) rp32[i] = (int32_t)rowptr[i];
     int64_t* d_gcol = nullptr;
-    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
-    B2K_CUDA(ctx, cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_rows + 1)));
-    B2K_CUDA(ctx, cudaMalloc(&op->colidx, sizeof(int32_t) * std::max<int64_t>(1, nnz)));
-    B2K_CUDA(ctx, cudaMalloc(&op->vals, (size_t)ctx->esize * std::max<int64_t>(1, nnz)));
-    B2K_CUDA(ctx, cudaMalloc(&d_gcol, sizeof(int64_t) * std::max<int64_t>(1, nnz)));
-    B2K_CUDA(ctx, cudaMemcpyAsync(op->rowptr, rp32.data(), sizeof(int32_t) * (n_rows + 1),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    B2K_CUDA(ctx, cudaMemcpyAsync(d_gcol, gcol.data(), sizeof(int64_t) * nnz, cudaMemcpyHostToDevice,
-                                  ctx->stream));
-    B2K_CUDA(ctx, cudaMemcpyAsync(op->vals, vals, (size_t)ctx->esize * nnz, cudaMemcpyHostToDevice,
-                                  ctx->stream));
-    int32_t rc = plan_halo(ctx, op, d_gcol);
+    void* d_raw = nullptr;
+    const int64_t nnz1 = std::max<int64_t>(1, nnz);
+    const size_t raw_bytes = (size_t)idx_bytes * std::max<int64_t>(nnz1, n_rows + 1);
+    int32_t rc = B2K_OK;
+    auto fail = [&](int32_t code) {
+        cudaStreamSynchronize(ctx->stream);
+        if (d_gcol) cudaFree(d_gcol);
+        if (d_raw) cudaFree(d_raw);
+        b2k_op_destroy(ctx, op);
+        return code;
+    };
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(b2k_fail(ctx, B2K_ECUDA, "op_create_csr: %s -> %s", #call,           \
+                                 cudaGetErrorString(e__)));                                  \
+    } while (0)
+    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_rows + 1)));
+    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * nnz1));
+    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * nnz1));
+    CK(cudaMalloc(&d_gcol, sizeof(int64_t) * nnz1));
+    CK(cudaMalloc(&d_raw, raw_bytes));
+    const int g = ctx->num_sms * 8;
+    CK(cudaMemcpyAsync(d_raw, rowptr, (size_t)idx_bytes * (n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (idx_bytes == 8) k_convert_rowptr<int64_t><<<g, 256, 0, ctx->stream>>>((const int64_t*)d_raw, index_base, op->rowptr, n_rows + 1);
+    else k_convert_rowptr<int32_t><<<g, 256, 0, ctx->stream>>>((const int32_t*)d_raw, index_base, op->rowptr, n_rows + 1);
+    ctx->launches++;
+    if (nnz > 0) {
+        CK(cudaMemcpyAsync(d_raw, colidx, (size_t)idx_bytes * nnz, cudaMemcpyHostToDevice, ctx->stream));
+        if (idx_bytes == 8) k_convert_cols<int64_t><<<g, 256, 0, ctx->stream>>>((const int64_t*)d_raw, index_base, d_gcol, nnz);
+        else k_convert_cols<int32_t><<<g, 256, 0, ctx->stream>>>((const int32_t*)d_raw, index_base, d_gcol, nnz);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(op->vals, vals, (size_t)ctx->esize * nnz, cudaMemcpyHostToDevice, ctx->stream));
+        // validate the column range on the device
+        unsigned long long* d_mm;
+        CK(cudaMalloc(&d_mm, 2 * sizeof(unsigned long long)));
+        unsigned long long init[2] = {~0ull, 0ull}, mm[2];
+        CK(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        k_minmax_cols<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(d_gcol, nnz, d_mm, d_mm + 1);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_mm);
+        const int64_t colmax = ctx->nranks > 1 ? ctx->n_global : n_cols;
+        // negative columns wrap to huge unsigned values and are caught by the max test
+        if ((int64_t)mm[1] >= colmax || (int64_t)mm[1] < 0)
+            return fail(b2k_fail(ctx, B2K_EINVAL, "op_create_csr: column index out of range [0, %lld)",
+                                 (long long)colmax));
+    }
+#undef CK
+    rc = plan_halo(ctx, op, d_gcol);
     if (rc == B2K_OK) rc = localize(ctx, op, d_gcol);
-    if (rc == B2K_OK) rc = finish_csr(ctx, op, rp32.data());
+    if (rc == B2K_OK) rc = finish_csr(ctx, op);
+    if (rc != B2K_OK) return fail(rc);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_gcol);
-    if (rc != B2K_OK) {
-        b2k_op_destroy(ctx, op);
-        return rc;
-    }
+    cudaFree(d_raw);
     *out = op;
     return B2K_OK;
 }
@@ -384,22 +500,7 @@ extern "C" int32_t b2k_op_create_csr(b2k_ctx* ctx, b2k_op** out, int64_t n_rows,
     if (!ctx || !out || !rowptr || (nnz > 0 && (!colidx || !vals))) return B2K_EINVAL;
     if ((idx_bytes != 4 && idx_bytes != 8) || (index_base != 0 && index_base != 1))
         return b2k_fail(ctx, B2K_EINVAL, "op_create_csr: idx_bytes must be 4/8, index_base 0/1");
-    std::vector<int64_t> rp, gc;
-    if (idx_bytes == 8) {
-        widen<int64_t>(rowptr, n_rows + 1, index_base, &rp);
-        widen<int64_t>(colidx, nnz, index_base, &gc);
-    } else {
-        widen<int32_t>(rowptr, n_rows + 1, index_base, &rp);
-        widen<int32_t>(colidx, nnz, index_base, &gc);
-    }
-    if (rp[0] != 0 || rp[n_rows] != nnz)
-        return b2k_fail(ctx, B2K_EINVAL, "op_create_csr: rowptr does not span [0, nnz]");
-    const int64_t colmax = ctx->nranks > 1 ? ctx->n_global : n_cols;
-    for (int64_t i = 0; i < nnz; ++i)
-        if (gc[i] < 0 || gc[i] >= colmax)
-            return b2k_fail(ctx, B2K_EINVAL, "op_create_csr: column index out of range at %lld",
-                            (long long)i);
-    return create_csr_from_host(ctx, out, n_rows, n_cols, nnz, rp, gc, vals);
+    return create_csr_raw(ctx, out, n_rows, n_cols, nnz, rowptr, colidx, vals, idx_bytes, index_base);
 }
 
 extern "C" int32_t b2k_op_create_csc(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_t n_cols,
@@ -434,7 +535,7 @@ extern "C" int32_t b2k_op_create_csc(b2k_ctx* ctx, b2k_op** out, int64_t n_rows,
             gc[dst] = c;
             memcpy(vv.data() + es * dst, (const char*)nzval + es * p, es);
         }
-    return create_csr_from_host(ctx, out, n_rows, n_cols, nnz, rp, gc, vv.data());
+    return create_csr_raw(ctx, out, n_rows, n_cols, nnz, rp.data(), gc.data(), vv.data(), 8, 0);
 }
 
 extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx, int64_t ny,
@@ -486,11 +587,11 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
     CK(cudaMalloc(&tmp, tmp_bytes));
     CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, op->rowptr, (int)(n_loc + 1),
                                      ctx->stream));
-    std::vector<int32_t> h_rowptr(n_loc + 1);
-    CK(cudaMemcpyAsync(h_rowptr.data(), op->rowptr, sizeof(int32_t) * (n_loc + 1),
-                       cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t h_nnz = 0;
+    CK(cudaMemcpyAsync(&h_nnz, op->rowptr + n_loc, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    op->nnz = h_rowptr[n_loc];
+    op->nnz = h_nnz;
     CK(cudaMalloc(&op->colidx, sizeof(int32_t) * std::max<int64_t>(1, op->nnz)));
     CK(cudaMalloc(&op->vals, (size_t)ctx->esize * std::max<int64_t>(1, op->nnz)));
     CK(cudaMalloc(&d_gcol, sizeof(int64_t) * std::max<int64_t>(1, op->nnz)));
@@ -506,7 +607,7 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
 #undef CK
     rc = plan_halo(ctx, op, d_gcol);
     if (rc == B2K_OK) rc = localize(ctx, op, d_gcol);
-    if (rc == B2K_OK) rc = finish_csr(ctx, op, h_rowptr.data());
+    if (rc == B2K_OK) rc = finish_csr(ctx, op);
     if (rc != B2K_OK) return fail(rc);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(counts);
@@ -661,6 +762,8 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
         n_loc = 0x7fffffff;
     }
     double* out = dotv ? ctx->d_res + dot_slot : nullptr;
+    const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
+                                              2.0 * ctx->esize * op->n_rows);
 #define LAUNCH(T)                                                                              \
     k_spmv_stream<T><<<op->nblk, SP_BT, 0, ctx->stream>>>(                                     \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
@@ -669,6 +772,7 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
     if (ctx->dtype == B2K_F64) LAUNCH(double);
     else LAUNCH(float);
 #undef LAUNCH
+    b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;
 }

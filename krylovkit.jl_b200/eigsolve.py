@@ -1,0 +1,142 @@
+"""eigsolve with the Lanczos (Krylov-Schur / thick restart) algorithm — mirror of
+src/eigsolve/lanczos.jl and the user-facing entry points of src/eigsolve/eigsolve.jl.
+
+The host keeps the restart / deflation / convergence logic exactly as KrylovKit does; all
+n-length work is delegated to the device through the factorization and basis mirrors.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from .algorithms import ConvergenceInfo, Lanczos, WARN_LEVEL
+from .dense import (eigsort, householder_row, lmul_householder, permuteeig, rmul_householder,
+                    tridiageigh)
+from .factorizations import lanczos as lz
+from .operators import B200CSR, B200Operator
+from .orthonormal import basistransform_
+from .vectors import B200Context, B200Vec
+
+
+def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = None,
+             out_vectors=None, **kwargs):
+    """eigsolve(A, x₀, howmany, which, alg::Lanczos) — src/eigsolve/lanczos.jl:1-155.
+
+    A  : B200Operator / callable on B200Vec (device-resident path), or a scipy sparse
+         matrix / CSR triple on the HOST (then x0 is a host array, the problem is uploaded,
+         solved on the GPU and the vectors are downloaded: the end-to-end path).
+    Returns (values, vectors, ConvergenceInfo).
+    """
+    if alg is None:
+        alg = Lanczos(**kwargs)
+    if not isinstance(x0, B200Vec):
+        return _eigsolve_host(A, x0, howmany, which, alg, out_vectors)
+    return _eigsolve_lanczos(A, x0, howmany, which, alg)
+
+
+def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None):
+    """Host-buffer entry: upload (A, x₀), solve, download.  The slab is sized for the
+    factorization: krylovdim + 1 basis vectors, the residual and work columns."""
+    import scipy.sparse as sp
+    x0 = np.asarray(x0)
+    n = x0.shape[0]
+    dtype = np.float32 if x0.dtype == np.float32 else np.float64
+    ctx = B200Context(n, alg.krylovdim + 8, dtype=dtype)
+    try:
+        if sp.issparse(A):
+            op = B200CSR.from_scipy(ctx, A)
+        elif isinstance(A, tuple) and len(A) == 3:
+            rowptr, colidx, vals = A
+            op = B200CSR.from_csr_arrays(ctx, n, n, rowptr, colidx, vals)   # no host-side copies
+        else:
+            raise TypeError("eigsolve: host-side A must be a scipy sparse matrix or a CSR triple")
+        xv = ctx.from_host(x0)
+        vals, vecs, info = _eigsolve_lanczos(op, xv, howmany, which, alg)
+        # out_vectors: optional preallocated (e.g. pinned) host arrays for the Ritz vectors
+        vecs_h = [v.to_host(out_vectors[i] if out_vectors is not None and i < len(out_vectors) else None)
+                  for i, v in enumerate(vecs)]
+        info.residual = None      # residual vectors stay on the device in the host-buffer path
+        return vals, vecs_h, info
+    finally:
+        ctx.close()
+
+
+def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos):
+    krylovdim, maxiter = alg.krylovdim, alg.maxiter
+    if howmany > krylovdim:
+        raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} eigenvalues")
+    it = lz.LanczosIterator(A, x0, alg.orth)
+    fact = lz.initialize(it)
+    numops, numiter = 1, 1
+    tol = alg.tol
+    HH = np.zeros((krylovdim + 1, krylovdim))
+    converged = 0
+    D = U = f = None
+    while True:
+        beta = fact.normres()
+        K = len(fact)
+        if beta <= tol and K < howmany and alg.verbosity >= WARN_LEVEL:
+            warnings.warn(f"Invariant subspace of dimension {K} (up to requested tolerance `tol = {tol}`), "
+                          f"which is smaller than the number of requested eigenvalues (i.e. `howmany == {howmany}`).")
+        if K == krylovdim or beta <= tol or (alg.eager and K >= howmany):
+            if K == 1:
+                D = np.array([fact.alphas[0]])
+                U = np.ones((1, 1))
+                f = np.array([beta])
+                converged = int(beta <= tol)
+            else:
+                dv, ev = fact.rayleighquotient()
+                D, U = tridiageigh(dv, ev)
+                p = eigsort(which)(D)
+                D, U = permuteeig(D, U, p)
+                f = U[K - 1, :] * beta
+                converged = 0
+                while converged < K and abs(f[converged]) <= tol:
+                    converged += 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            fact = lz.expand_(it, fact)
+            numops += 1
+        else:
+            if numiter == maxiter:
+                break
+            keep = (3 * krylovdim + 2 * converged) // 5
+            # restore Lanczos form in the first keep columns — eigsolve/lanczos.jl:88-105
+            H = HH[: keep + 1, :keep]
+            H[:] = 0
+            for j in range(keep):
+                H[j, j] = D[j]
+                H[keep, j] = f[j]
+            for j in range(keep - 1, -1, -1):
+                h, nu = householder_row(H, j + 1, range(0, j + 1), j)
+                H[j + 1, j] = nu
+                H[j + 1, :j] = 0
+                lmul_householder(h, H)
+                rmul_householder(H, h, slice(0, j + 1))
+                rmul_householder(U, h)
+            for j in range(keep):
+                fact.alphas[j] = H[j, j]
+                fact.betas[j] = H[j + 1, j]
+            B = fact.basis()
+            basistransform_(B, U[:, :keep])
+            r = fact.residual()
+            B[keep] = B[keep].scale_(1 / beta, r)     # B[keep+1] = scale!!(r, 1/β): column reuse
+            fact = lz.shrink_(fact, keep)
+            numiter += 1
+    hm = howmany
+    if converged > howmany:
+        hm = converged
+    elif len(D) < howmany:
+        hm = len(D)
+    values = D[:hm].copy()
+    B = fact.basis()
+    vectors = [B * U[:, i] for i in range(hm)]
+    r = fact.residual()
+    residuals = [r.scale(U[-1, i]) for i in range(hm)]
+    normres = np.abs(f[:hm])
+    if converged < howmany and alg.verbosity >= WARN_LEVEL:
+        warnings.warn(f"Lanczos eigsolve stopped without convergence after {numiter} iterations: "
+                      f"{converged} eigenvalues converged, normres = {normres}, numops = {numops}")
+    return values, vectors, ConvergenceInfo(converged, residuals, normres, numiter, numops)

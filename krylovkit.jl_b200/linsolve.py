@@ -1,0 +1,153 @@
+"""linsolve with restarted GMRES — mirror of src/linsolve/gmres.jl (and the tolerance
+resolution of src/linsolve/linsolve.jl:123-180)."""
+from __future__ import annotations
+
+import math
+import warnings
+
+import numpy as np
+
+from .algorithms import ConvergenceInfo, GMRES, WARN_LEVEL
+from .dense import givens, ldiv_upper
+from .factorizations import arnoldi as ar
+from .operators import B200CSR, apply
+from .orthonormal import rmul_givens_, unproject_
+from .vectors import B200Context, B200Vec
+
+# gmres.jl:112-117 rotates the WHOLE basis with k Givens sweeps only to read column k+1.
+# True = do exactly that (k two-column sweeps); False = obtain the same column as one
+# linear combination with host-accumulated coefficients (rounding differs at the 1e-16 level).
+LITERAL_GIVENS_RESTART = False
+
+
+def linsolve(A, b, x0=None, alg: GMRES | None = None, a0: float = 0.0, a1: float = 1.0,
+             atol: float | None = None, rtol: float | None = None, **kwargs):
+    """linsolve(A, b, x₀, alg::GMRES, a₀, a₁): solve (a₀ + a₁ A) x = b.
+    `tol` of the algorithm is the absolute residual tolerance; pass atol/rtol to get
+    KrylovKit's tol = max(atol, rtol*‖b‖) (linsolve.jl:159-161)."""
+    if alg is None:
+        alg = GMRES(**kwargs)
+    if not isinstance(b, B200Vec):
+        return _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol)
+    if atol is not None or rtol is not None:
+        tol = max(atol or 0.0, (rtol or 0.0) * b.norm())
+        alg = GMRES(orth=alg.orth, maxiter=alg.maxiter, krylovdim=alg.krylovdim, tol=tol,
+                    verbosity=alg.verbosity)
+    if x0 is None:
+        x0 = b.zerovector()
+    return _gmres(A, b, x0, alg, a0, a1)
+
+
+def _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol):
+    import scipy.sparse as sp
+    b = np.asarray(b)
+    n = b.shape[0]
+    ctx = B200Context(n, alg.krylovdim + 10, dtype=np.float32 if b.dtype == np.float32 else np.float64)
+    try:
+        if not sp.issparse(A):
+            raise TypeError("linsolve: host-side A must be a scipy sparse matrix")
+        op = B200CSR.from_scipy(ctx, A)
+        bv = ctx.from_host(b)
+        xv = ctx.from_host(x0) if x0 is not None else None
+        x, info = linsolve(op, bv, xv, alg, a0, a1, atol, rtol)
+        info.residual = info.residual.to_host()
+        return x.to_host(), info
+    finally:
+        ctx.close()
+
+
+def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
+    y0 = apply(operator, x0)
+    r = b.copy()                               # scale(b, one(T))
+    if a0 != 0:
+        r = r.add_(x0, -a0)
+    r = r.add_(y0, -a1)
+    x = x0.copy()                              # scale!!(zerovector(r), x₀, 1)
+    beta = r.norm()
+    maxiter, krylovdim, tol = alg.maxiter, alg.krylovdim, alg.tol
+    if beta < tol:
+        return x, ConvergenceInfo(1, r, beta, 0, 1)
+    y = np.zeros(krylovdim + 1)
+    gs = [None] * krylovdim
+    R = np.zeros((krylovdim, krylovdim))
+    numiter, numops = 0, 1
+    it = ar.ArnoldiIterator(operator, r, alg.orth)
+    fact = ar.initialize(it)
+    numops += 1
+    while True:
+        numiter += 1
+        y[0] = beta
+        k = 1
+        R[0, 0] = a0 + a1 * fact.h(1, 1)
+        c, s, rr = givens(R[0, 0], a1 * fact.normres())
+        gs[0] = (c, s)
+        R[0, 0] = rr
+        y[1] = 0.0
+        y[0], y[1] = c * y[0] + s * y[1], -s * y[0] + c * y[1]
+        beta = abs(y[1])
+        singular = False
+        while R[k - 1, k - 1] != 0 and beta > tol and len(fact) < krylovdim:
+            fact = ar.expand_(it, fact)
+            numops += 1
+            k = len(fact)
+            for i in range(1, k):
+                R[i - 1, k - 1] = a1 * fact.h(i, k)
+            R[k - 1, k - 1] = a0 + a1 * fact.h(k, k)
+            for i in range(k - 1):
+                c, s = gs[i]
+                R[i, k - 1], R[i + 1, k - 1] = (c * R[i, k - 1] + s * R[i + 1, k - 1],
+                                                -s * R[i, k - 1] + c * R[i + 1, k - 1])
+            if math.hypot(R[k - 1, k - 1], a1 * fact.normres()) < tol:
+                if alg.verbosity >= WARN_LEVEL:
+                    warnings.warn(f"GMRES linsolve in iteration {numiter}; step {k}: linear operator is "
+                                  "singular in Krylov subspace")
+                # rotate all the weight into y[k+1] — gmres.jl:84-86
+                y[k] = math.hypot(0.0, y[k - 1])
+                y[k - 1] = 0.0
+                R[k - 1, k - 1] = 0.0
+                singular = True
+            else:
+                c, s, rr = givens(R[k - 1, k - 1], a1 * fact.normres())
+                gs[k - 1] = (c, s)
+                R[k - 1, k - 1] = rr
+                y[k] = 0.0
+                y[k - 1], y[k] = c * y[k - 1] + s * y[k], -s * y[k - 1] + c * y[k]
+            beta = abs(y[k])
+        if R[k - 1, k - 1] == 0 and y[k - 1] == 0:
+            ldiv_upper(R, y, k - 1)
+        else:
+            ldiv_upper(R, y, k)
+        V = fact.basis()
+        # x = add!!(x, V[i], y[i]) for i in 1:k — gmres.jl:105-108: one fused lincomb sweep
+        x = unproject_(x, V, y[:k], 1.0, 1.0, range(k))
+        if beta > tol and numiter < maxiter and not singular:
+            w = fact.residual()
+            V.push(w.scale_(1 / fact.normres()))
+            if LITERAL_GIVENS_RESTART:
+                for i in range(k):
+                    c, s = gs[i]
+                    rmul_givens_(V, i, i + 1, c, -s)          # rmul!(V, gs[i]')
+                r = r.scale_(y[k], V[k])
+            else:
+                # column k+1 of V·G₁ᴴ⋯G_kᴴ as coefficients: e_{k+1} pushed back through the rotations
+                coef = np.zeros(k + 1)
+                coef[k] = 1.0
+                for i in range(k - 1, -1, -1):
+                    c, s = gs[i]
+                    ci, ci1 = coef[i], coef[i + 1]
+                    coef[i], coef[i + 1] = c * ci - s * ci1, s * ci + c * ci1
+                r = unproject_(r, V, coef * y[k], 1.0, 0.0)
+        else:
+            r = r.scale_(1.0, b)
+            r = r.add_(apply(operator, x, a0, a1), -1.0)
+            numops += 1
+            beta = r.norm()
+            if beta < tol:
+                return x, ConvergenceInfo(1, r, beta, numiter, numops)
+        if numiter >= maxiter:
+            if alg.verbosity >= WARN_LEVEL:
+                warnings.warn(f"GMRES linsolve stopped without converging after {numiter} iterations: "
+                              f"normres = {beta}, numops = {numops}")
+            return x, ConvergenceInfo(0, r, beta, numiter, numops)
+        it = ar.ArnoldiIterator(operator, r, alg.orth)
+        fact = ar.initialize_(it, fact)

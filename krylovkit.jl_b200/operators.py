@@ -76,7 +76,7 @@ class B200CSR(B200Operator):
     @classmethod
     def from_csr_arrays(cls, ctx: B200Context, n_rows, n_cols, rowptr, colidx, vals,
                         index_base: int = 0) -> "B200CSR":
-        rp = np.ascontiguousarray(rowptr)
+        rp = np.ascontiguousarray(rowptr)      # no copy when already contiguous (pinned buffers stay pinned)
         ci = np.ascontiguousarray(colidx)
         if rp.dtype != ci.dtype or rp.dtype not in (np.int32, np.int64):
             rp, ci = rp.astype(np.int64), ci.astype(np.int64)

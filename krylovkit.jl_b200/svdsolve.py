@@ -1,0 +1,114 @@
+"""svdsolve with Golub-Kahan-Lanczos bidiagonalisation and thick restart — mirror of
+src/eigsolve/svdsolve.jl:144-314."""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from .algorithms import ConvergenceInfo, GKL, WARN_LEVEL
+from .dense import (bidiagsvd_lower, householder_col, householder_row, lmul_householder,
+                    rmul_householder)
+from .factorizations import gkl
+from .operators import B200Dense
+from .orthonormal import basistransform_, rmul_householder_
+from .vectors import B200Context, B200Vec
+
+
+def svdsolve(A, u0, howmany: int = 1, which: str = "LR", alg: GKL | None = None, **kwargs):
+    """svdsolve(A, x₀, howmany, which, alg::GKL).  u0 lives in the codomain (length m).
+    Host entry: A = numpy m x n array, u0 = numpy vector -> uploaded, solved, downloaded."""
+    if which not in ("LR", "SR"):
+        raise ValueError(f"invalid specification of which singular values to target: which = {which}")
+    if alg is None:
+        alg = GKL(**kwargs)
+    if isinstance(u0, B200Vec):
+        return _svdsolve_gkl(A, u0, howmany, which, alg)
+    A = np.asarray(A)
+    u0 = np.asarray(u0)
+    m, n = A.shape
+    ctx = B200Context(m, alg.krylovdim + 8, dtype=A.dtype if A.dtype == np.float32 else np.float64)
+    try:
+        sv = ctx.add_space(n, alg.krylovdim + 8, sharded=False)
+        op = B200Dense.from_host(ctx, A, sv)
+        S, Uv, Vv, info = _svdsolve_gkl(op, ctx.from_host(u0), howmany, which, alg)
+        info.residual = [r.to_host() for r in info.residual]
+        return S, [u.to_host() for u in Uv], [v.to_host() for v in Vv], info
+    finally:
+        ctx.close()
+
+
+def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
+    krylovdim, maxiter = alg.krylovdim, alg.maxiter
+    if howmany > krylovdim:
+        raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} singular values")
+    numiter = 1
+    it = gkl.GKLIterator(A, u0, alg.orth)
+    fact = gkl.initialize(it)
+    numops = 2
+    tol = alg.tol
+    HH = np.zeros((krylovdim + 1, krylovdim))
+    converged = 0
+    P = S = Q = f = None
+    while True:
+        beta = fact.normres()
+        K = len(fact)
+        if beta <= tol and K < howmany and alg.verbosity >= WARN_LEVEL:
+            warnings.warn(f"Invariant subspace of dimension {K} (up to requested tolerance `tol = {tol}`)")
+        if K == krylovdim or beta <= tol or (alg.eager and K >= howmany):
+            P, S, Q = bidiagsvd_lower(fact.alphas[:K], fact.betas[:K - 1])
+            if which == "SR":
+                P, S, Q = P[:, ::-1].copy(), S[::-1].copy(), Q[::-1, :].copy()
+            f = Q.T[K - 1, :] * beta
+            converged = 0
+            while converged < K and abs(f[converged]) < tol:
+                converged += 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            fact = gkl.expand_(it, fact)
+            numops += 2
+        else:
+            if numiter == maxiter:
+                break
+            keep = (3 * krylovdim + 2 * converged) // 5
+            U, V = fact.basis("U"), fact.basis("V")
+            basistransform_(U, P[:, :keep])
+            basistransform_(V, Q.T[:, :keep])
+            r = fact.residual()
+            U[keep] = U[keep].scale_(1 / fact.normres(), r)       # U[keep+1] = scale!!(r, 1/β)
+            H = HH[: keep + 1, :keep]
+            H[:] = 0
+            for j in range(keep):
+                H[j, j] = S[j]
+                H[keep, j] = f[j]
+            # restore bidiagonal form in the first keep columns — svdsolve.jl:257-268
+            for j in range(keep - 1, -1, -1):
+                h, nu = householder_row(H, j + 1, range(0, j + 1), j)
+                H[j + 1, j] = nu
+                H[j + 1, :j] = 0
+                rmul_householder(H, h, slice(0, j + 1))
+                rmul_householder_(V, h.beta, h.v, h.r)
+                h, nu = householder_col(H, range(0, j + 1), j, j)
+                H[j, j] = nu
+                H[:j, j] = 0
+                lmul_householder(h, H, range(0, j))
+                rmul_householder_(U, h.beta, h.v, h.r)
+            for j in range(keep):
+                fact.alphas[j] = H[j, j]
+                fact.betas[j] = H[j + 1, j]
+            fact = gkl.shrink_(fact, keep)
+            numiter += 1
+    if converged > howmany:
+        howmany = converged
+    values = S[:howmany].copy()
+    U, V = fact.basis("U"), fact.basis("V")
+    left = [U * P[:, i] for i in range(howmany)]
+    right = [V * Q[i, :] for i in range(howmany)]
+    r = fact.residual()
+    residuals = [r.scale(Q[i, -1]) for i in range(howmany)]
+    normres = np.abs(f[:howmany])
+    if converged < howmany and alg.verbosity >= WARN_LEVEL:
+        warnings.warn(f"GKL svdsolve finished without convergence after {numiter} iterations: "
+                      f"{converged} singular values converged, normres = {normres}, numops = {numops}")
+    return values, left, right, ConvergenceInfo(converged, residuals, normres, numiter, numops)

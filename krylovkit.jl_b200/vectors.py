@@ -141,8 +141,12 @@ class B200Vec:
         self.ctx.check(self.ctx.lib.b2k_vec_upload(self.ctx.h, self.handle, a.ctypes.data))
         return self
 
-    def to_host(self) -> np.ndarray:
-        out = np.empty(len(self), dtype=self.ctx.np_dtype)
+    def to_host(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Download into `out` (e.g. a pinned buffer) or a fresh array."""
+        if out is None:
+            out = np.empty(len(self), dtype=self.ctx.np_dtype)
+        elif out.shape != (len(self),) or out.dtype != self.ctx.np_dtype or not out.flags.c_contiguous:
+            raise L.DimensionMismatch("to_host: out has the wrong shape / dtype / layout")
         self.ctx.check(self.ctx.lib.b2k_vec_download(self.ctx.h, self.handle, out.ctypes.data))
         return out
 

@@ -1,0 +1,1023 @@
+"""CPU oracle — a plain numpy/scipy restatement of KrylovKit.jl's Krylov hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under krylovkit.jl_b200/ may import this module; only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do,
+and only as the checker (or the timed CPU baseline), never as the product.
+
+What it restates (operation order follows the cited reference lines; paths relative to
+the KrylovKit.jl v0.10.4 tree):
+  * VectorInterface calls on plain arrays: inner = dot, norm = nrm2, add!! = axpby, scale!!
+  * src/orthonormal.jl:88-150 project!!/unproject!!, :210-229 rank1update!, :291-321
+    basistransform!, :372-489 the six orthogonalize!! variants, :522-527 orthonormalize!!
+  * src/dense/reflector.jl:31-65 Householder, :67-154 lmul!/rmul!, dense/givens.jl:12-36
+  * src/factorizations/lanczos.jl:180-376, arnoldi.jl:135-245, gkl.jl:183-404
+  * src/factorizations/blocklanczos.jl:43-52, 277-284, 312-353 block primitives
+  * src/eigsolve/lanczos.jl:1-155, src/linsolve/gmres.jl:1-151, src/eigsolve/svdsolve.jl:144-314
+  * src/dense/linalg.jl:96-106 ldiv!, :306-333 permuteeig!, packedhessenberg.jl:32-48
+
+Arithmetic that lives outside the reference tree (VectorInterface.jl 0.5/0.6, Julia's
+LinearAlgebra/OpenBLAS, SparseArrays — Project.toml:31-48, no Manifest => versions
+unpinned) is restated by numpy/scipy calls with the same mathematical definition:
+`A @ x` (scipy CSR, single-threaded like SparseArrays' CSC product), np.dot, np.linalg.norm,
+LAPACK dstemr through scipy (the reference calls dstegr, which is dstemr with the same
+MRRR algorithm, dense/linalg.jl:396-458), numpy SVD of the k x k bidiagonal instead of
+LAPACK dbdsqr (values identical, vectors up to sign).
+
+PINNING.  The reference cannot run here (no Julia in the image).  The oracle is pinned
+against the reference's own known-answer fixtures (tests/test_oracle_golden.py):
+the literal 71x71 matrix of issue #143 (test/issues.jl:39-129), eigsolve([1 0;0 1])
+(issues.jl:32-36), the toric-code ground energy -16 (test/eigsolve.jl:471-549) and the
+invariants the reference asserts after every expand!/shrink! (test/factorize.jl:140-158,
+185-203, 285-309).  Bit-level parity with the Julia/OpenBLAS reduction order is
+"parity unpinned": no reference test fixes it.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.linalg import lapack
+
+# orthogonalizer tags (src/algorithms.jl:17-80)
+CGS, MGS, CGS2, MGS2, CGSIR, MGSIR = range(6)
+ETA_DEFAULT = 1.0 / math.sqrt(2.0)
+
+
+@dataclass(frozen=True)
+class Orth:
+    tag: int
+    eta: float = ETA_DEFAULT
+
+
+# ------------------------------------------------------------------ inputs --------------
+
+def splitmix64(z):
+    """counter RNG shared with the device (csrc/common.cuh splitmix64)."""
+    z = np.asarray(z, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def splitmix_vector(seed: int, n: int, offset: int = 0, dtype=np.float64):
+    i = np.arange(n, dtype=np.uint64) + np.uint64(offset) + np.uint64(seed)
+    return ((splitmix64(i) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)).astype(dtype)
+
+
+def stencil_matrix(nx, ny, nz=1, coeffs=(4.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0), dtype=np.float64):
+    """Dirichlet stencil on an nx*ny*nz grid (x fastest): (centre, west, east, south, north, down, up)."""
+    c, w, e, s, n_, d, u = coeffs
+    Ix, Iy, Iz = sp.identity(nx), sp.identity(ny), sp.identity(nz)
+    ex = sp.diags([w * np.ones(max(nx - 1, 0)), e * np.ones(max(nx - 1, 0))], [-1, 1], shape=(nx, nx))
+    ey = sp.diags([s * np.ones(max(ny - 1, 0)), n_ * np.ones(max(ny - 1, 0))], [-1, 1], shape=(ny, ny))
+    A = sp.kron(Iz, sp.kron(Iy, ex)) + sp.kron(Iz, sp.kron(ey, Ix)) + c * sp.identity(nx * ny * nz)
+    if nz > 1:
+        ez = sp.diags([d * np.ones(nz - 1), u * np.ones(nz - 1)], [-1, 1], shape=(nz, nz))
+        A = A + sp.kron(ez, sp.kron(Iy, Ix))
+    A = A.tocsr().astype(dtype)
+    A.sort_indices()
+    return A
+
+
+def laplace_eigenvalues(nx, ny, nz=1):
+    """closed-form spectrum of the Dirichlet 5-/7-point Laplacian."""
+    lx = 2 - 2 * np.cos(np.arange(1, nx + 1) * np.pi / (nx + 1))
+    ly = 2 - 2 * np.cos(np.arange(1, ny + 1) * np.pi / (ny + 1))
+    lam = lx[:, None] + ly[None, :]
+    if nz > 1:
+        lz = 2 - 2 * np.cos(np.arange(1, nz + 1) * np.pi / (nz + 1))
+        lam = lam[:, :, None] + lz[None, None, :]
+    return np.sort(lam.ravel())
+
+
+def dense_splitmix(seed, m, n, dtype=np.float32, row0=0, m_global=None):
+    mg = m if m_global is None else m_global
+    i = np.arange(m, dtype=np.uint64)[:, None] + np.uint64(row0)
+    j = np.arange(n, dtype=np.uint64)[None, :] * np.uint64(mg)
+    z = splitmix64(i + j + np.uint64(seed))
+    return np.asfortranarray(((z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) - 0.5)
+                             .astype(dtype))
+
+
+# ------------------------------------------------------------------ apply (src/apply.jl) --
+
+def apply(op, x, a0=0.0, a1=1.0):
+    """apply.jl:1-11."""
+    y = op @ x if not callable(op) else op(x)
+    if a0 != 0 or a1 != 1:
+        y = a1 * y + a0 * x          # add!!(y, x, α₀, α₁): y = α₁*y + α₀*x
+    return y
+
+
+def apply_normal(op, x):
+    return op[0](x) if isinstance(op, tuple) else (op(x, False) if callable(op) else op @ x)
+
+
+def apply_adjoint(op, x):
+    return op[1](x) if isinstance(op, tuple) else (op(x, True) if callable(op) else op.T @ x)
+
+
+def inner(x, y):
+    return float(np.dot(x, y))
+
+
+def norm(x):
+    return float(np.linalg.norm(x))
+
+
+# ------------------------------------------------------------------ orthonormal.jl --------
+
+def project(y, b, x, alpha=1.0, beta=0.0, r=None):
+    """orthonormal.jl:88-118."""
+    r = range(len(b)) if r is None else r
+    for j, rj in enumerate(r):
+        if beta == 0:
+            y[j] = alpha * inner(b[rj], x)
+        else:
+            y[j] = beta * y[j] + alpha * inner(b[rj], x)
+    return y
+
+
+def unproject(y, b, x, alpha=1.0, beta=0.0, r=None):
+    """orthonormal.jl:132-150 (generic BLAS-1 path)."""
+    r = range(len(b)) if r is None else r
+    if beta == 0:
+        y = y * 0.0                  # hard zero
+    elif beta != 1:
+        y = y * beta
+    for i, ri in enumerate(r):
+        y = y + (alpha * x[i]) * b[ri]
+    return y
+
+
+def rank1update(b, y, x, alpha=1.0, beta=1.0, r=None):
+    """orthonormal.jl:210-229."""
+    r = range(len(b)) if r is None else r
+    for i, ri in enumerate(r):
+        if beta == 1:
+            b[ri] = b[ri] + (alpha * np.conj(x[i])) * y
+        elif beta == 0:
+            b[ri] = (alpha * np.conj(x[i])) * y
+        else:
+            b[ri] = beta * b[ri] + (alpha * np.conj(x[i])) * y
+    return b
+
+
+def basistransform(b, U):
+    """orthonormal.jl:291-321."""
+    m, n = U.shape
+    assert m == len(b)
+    b2 = []
+    for j in range(n):
+        v = b[0] * U[0, j]
+        for i in range(1, m):
+            v = v + b[i] * U[i, j]
+        b2.append(v)
+    for j in range(n):
+        b[j] = b2[j]
+    return b
+
+
+def _cgs_pass(v, b, x):
+    x = project(x, b, v)             # orthonormal.jl:381
+    v = unproject(v, b, x, -1, 1)    # :382
+    return v, x
+
+
+def _mgs_pass(v, b, x, accumulate):
+    for i, q in enumerate(b):        # orthonormal.jl:417-421 / 427-431
+        s = inner(q, v)
+        v = v - s * q
+        if accumulate:
+            x[i] += s
+        else:
+            x[i] = s
+    return v, x
+
+
+def orthogonalize(v, b, x, orth: Orth):
+    """orthogonalize!!(v, b, x, alg) — orthonormal.jl:378-452."""
+    t = orth.tag
+    if t == CGS:
+        return _cgs_pass(v, b, x)
+    if t == CGS2:
+        v, x = _cgs_pass(v, b, x)
+        s = np.empty_like(x)
+        v, s = _cgs_pass(v, b, s)    # reorthogonalize!! :385-393
+        x += s
+        return v, x
+    if t == CGSIR:
+        nold = norm(v)
+        v, x = _cgs_pass(v, b, x)
+        nnew = norm(v)
+        while np.finfo(np.float64).eps < nnew < orth.eta * nold:
+            nold = nnew
+            s = np.empty_like(x)
+            v, s = _cgs_pass(v, b, s)
+            x += s
+            nnew = norm(v)
+        return v, x
+    if t == MGS:
+        return _mgs_pass(v, b, x, False)
+    if t == MGS2:
+        v, x = _mgs_pass(v, b, x, False)
+        return _mgs_pass(v, b, x, True)
+    if t == MGSIR:
+        nold = norm(v)
+        v, x = _mgs_pass(v, b, x, False)
+        nnew = norm(v)
+        while np.finfo(np.float64).eps < nnew < orth.eta * nold:
+            nold = nnew
+            v, x = _mgs_pass(v, b, x, True)
+            nnew = norm(v)
+        return v, x
+    raise ValueError(t)
+
+
+def orthogonalize_vec(v, q, orth: Orth, eps=np.finfo(np.float64).eps):
+    """orthogonalize!!(v, q, alg) against one vector — orthonormal.jl:455-489."""
+    t = orth.tag
+    if t in (CGS, MGS):
+        s = inner(q, v)
+        return v - s * q, s
+    if t in (CGS2, MGS2):
+        s = inner(q, v)
+        v = v - s * q
+        ds = inner(q, v)
+        v = v - ds * q
+        return v, s + ds
+    nold = norm(v)
+    s = inner(q, v)
+    v = v - s * q
+    nnew = norm(v)
+    while eps < nnew < orth.eta * nold:
+        nold = nnew
+        ds = inner(q, v)
+        v = v - ds * q
+        s += ds
+        nnew = norm(v)
+    return v, s
+
+
+def orthonormalize(v, b, x, orth):
+    """orthonormal.jl:522-527."""
+    v, x = orthogonalize(v, b, x, orth)
+    beta = norm(v)
+    return v / beta, beta, x
+
+
+# ------------------------------------------------------------------ dense helpers ---------
+
+def householder_vec(x, i):
+    """_householder!(v, i) — dense/reflector.jl:34-65 (real).  Returns (β, v, ν)."""
+    v = np.array(x, dtype=np.float64)
+    sigma = float(np.sum(v[:i] ** 2) + np.sum(v[i + 1:] ** 2))
+    vi = v[i]
+    nu = math.sqrt(vi * vi + sigma)
+    if sigma == 0 and vi == nu:
+        return 0.0, v, nu
+    if vi < 0:
+        vi = vi - nu
+    else:
+        vi = (-sigma) / (vi + nu)    # ((vi - conj(vi))ν - σ)/(conj(vi)+ν) for real vi
+    v[:i] /= vi
+    v[i + 1:] /= vi
+    v[i] = 1.0
+    beta = -vi / nu
+    return beta, v, nu
+
+
+def householder_lmul(beta, v, r, A):
+    """lmul!(H, A) — reflector.jl:85-106: rows r of A."""
+    if beta == 0:
+        return A
+    r = list(r)
+    for k in range(A.shape[1]):
+        mu = beta * float(np.dot(v, A[r, k]))
+        A[r, k] -= mu * v
+    return A
+
+
+def householder_rmul(A, beta, v, r):
+    """rmul!(A, H) — reflector.jl:107-142: columns r of A (H already adjointed if needed; real)."""
+    if beta == 0:
+        return A
+    r = list(r)
+    w = A[:, r] @ v
+    A[:, r] -= np.outer(w, beta * v)
+    return A
+
+
+def householder_rmul_basis(b, beta, v, r):
+    """rmul!(b::OrthonormalBasis, H) — reflector.jl:143-154."""
+    if beta == 0:
+        return b
+    r = list(r)
+    w = unproject(np.zeros_like(b[r[0]]), b, v, 1, 0, r)
+    return rank1update(b, w, v, -beta, 1, r)
+
+
+def givens(f, g):
+    """LinearAlgebra.givens(f, g, i1, i2) -> (c, s, r) with [c s; -s c][f; g] = [r; 0] (dlartg)."""
+    c, s, r = lapack.dlartg(f, g)
+    return float(c), float(s), float(r)
+
+
+def givens_rmul_basis(b, i1, i2, c, s):
+    """_rmul!(b, G) — dense/givens.jl:31-36."""
+    q1, q2 = b[i1], b[i2]
+    b[i1], b[i2] = c * q1 - s * q2, s * q1 + c * q2
+    return b
+
+
+def tridiageigh(dv, ev):
+    """tridiageigh! -> stegr! (dense/linalg.jl:109-115, 396-458); dstemr here."""
+    n = len(dv)
+    if n == 1:
+        return np.array(dv, dtype=np.float64), np.ones((1, 1))
+    e = np.zeros(n)
+    e[: n - 1] = ev[: n - 1]
+    m, w, z, info = lapack.dstemr(np.array(dv, dtype=np.float64), e, 0, 0.0, 0.0, 1, n, compute_v=1)
+    assert info == 0
+    return w[:n].copy(), z[:, :n].copy()
+
+
+def permuteeig(D, V, p):
+    """permuteeig! — dense/linalg.jl:306-333 (net effect: D[p], V[:, p])."""
+    return D[p].copy(), V[:, p].copy()
+
+
+def eigsort(which):
+    """eigsolve.jl:335-355."""
+    if which == "SR":
+        return lambda d: np.argsort(d, kind="stable")
+    if which == "LR":
+        return lambda d: np.argsort(-d, kind="stable")
+    if which == "LM":
+        return lambda d: np.argsort(-np.abs(d), kind="stable")
+    raise ValueError(which)
+
+
+def ldiv_upper(R, y, k):
+    """ldiv!(UpperTriangular(R), y, 1:k) — dense/linalg.jl:96-106."""
+    for j in range(k - 1, -1, -1):
+        if R[j, j] == 0:
+            raise ZeroDivisionError("singular")
+        yj = y[j] / R[j, j]
+        y[j] = yj
+        y[:j] -= R[:j, j] * yj
+    return y
+
+
+# ------------------------------------------------------------------ Lanczos ---------------
+
+@dataclass
+class LanczosFact:
+    k: int
+    V: list
+    alphas: list
+    betas: list
+    r: np.ndarray
+
+    def normres(self):
+        return self.betas[-1]
+
+
+def lanczos_initialize(A, x0, orth: Orth):
+    """initialize(iter::LanczosIterator) — factorizations/lanczos.jl:180-222."""
+    beta0 = norm(x0)
+    if beta0 == 0:
+        raise ValueError("initial vector should not have norm zero")
+    Ax0 = apply(A, x0)
+    alpha = inner(x0, Ax0) / (beta0 * beta0)
+    v = x0 * (1 / beta0)             # add!!(scale(Ax₀, 0), x₀, 1/β₀)
+    r = Ax0 * (1 / beta0)
+    betaold = norm(r)
+    r = r - alpha * v
+    beta = norm(r)
+    if orth.tag in (CGS2, MGS2):
+        dalpha = inner(v, r)
+        alpha += dalpha
+        r = r - dalpha * v
+        beta = norm(r)
+    elif orth.tag in (CGSIR, MGSIR):
+        while np.finfo(np.float64).eps < beta < orth.eta * betaold:
+            betaold = beta
+            dalpha = inner(v, r)
+            alpha += dalpha
+            r = r - dalpha * v
+            beta = norm(r)
+    return LanczosFact(1, [v], [alpha], [beta], r)
+
+
+def lanczos_recurrence(A, V, beta, orth: Orth):
+    """lanczosrecurrence — factorizations/lanczos.jl:295-376."""
+    t = orth.tag
+    eps = np.finfo(np.float64).eps
+    v = V[-1]
+    w = apply(A, v)
+    if t == CGS:
+        alpha = inner(v, w)
+        w = w - beta * V[-2]
+        w = w - alpha * v
+        return w, alpha, norm(w)
+    if t == MGS:
+        w = w - beta * V[-2]
+        alpha = inner(v, w)
+        w = w - alpha * v
+        return w, alpha, norm(w)
+    if t == CGS2:
+        alpha = inner(v, w)
+        w = w - beta * V[-2]
+        w = w - alpha * v
+        s = np.empty(len(V))
+        w, s = _cgs_pass(w, V, s)
+        alpha += s[-1]
+        return w, alpha, norm(w)
+    if t == MGS2:
+        w = w - beta * V[-2]
+        alpha = inner(v, w)
+        w = w - alpha * v
+        s = alpha
+        for q in V:
+            s = inner(q, w)
+            w = w - s * q
+        alpha += s
+        return w, alpha, norm(w)
+    if t == CGSIR:
+        alpha = inner(v, w)
+        w = w - beta * V[-2]
+        w = w - alpha * v
+        ab2 = alpha * alpha + beta * beta
+        beta = norm(w)
+        nold = math.sqrt(beta * beta + ab2)
+        while eps < beta < orth.eta * nold:
+            nold = beta
+            s = np.empty(len(V))
+            w, s = _cgs_pass(w, V, s)
+            alpha += s[-1]
+            beta = norm(w)
+        return w, alpha, beta
+    if t == MGSIR:
+        w = w - beta * V[-2]
+        alpha = inner(v, w)
+        w = w - alpha * v
+        ab2 = alpha * alpha + beta * beta
+        beta = norm(w)
+        nold = math.sqrt(beta * beta + ab2)
+        while eps < beta < orth.eta * nold:
+            nold = beta
+            s = 0.0
+            for q in V:
+                s = inner(q, w)
+                w = w - s * q
+            alpha += s
+            beta = norm(w)
+        return w, alpha, beta
+    raise ValueError(t)
+
+
+def lanczos_expand(A, f: LanczosFact, orth: Orth):
+    """expand! — factorizations/lanczos.jl:250-272."""
+    betaold = f.normres()
+    f.V.append(f.r * (1 / betaold))
+    r, alpha, beta = lanczos_recurrence(A, f.V, betaold, orth)
+    f.alphas.append(alpha)
+    f.betas.append(beta)
+    f.k += 1
+    f.r = r
+    return f
+
+
+def lanczos_shrink(f: LanczosFact, k):
+    """shrink! — factorizations/lanczos.jl:273-291."""
+    if f.k <= k:
+        return f
+    while len(f.V) > k + 1:
+        f.V.pop()
+    r = f.V.pop()
+    del f.alphas[k:]
+    del f.betas[k:]
+    f.k = k
+    f.r = r * f.normres()
+    return f
+
+
+def eigsolve_lanczos(A, x0, howmany, which, krylovdim=30, maxiter=100, tol=1e-12,
+                     orth: Orth = Orth(MGS2), eager=False, callback=None):
+    """eigsolve(A, x₀, howmany, which, ::Lanczos) — src/eigsolve/lanczos.jl:1-155.
+    Returns (values, vectors, info dict)."""
+    if howmany > krylovdim:
+        raise ValueError("krylov dimension too small")
+    f = lanczos_initialize(A, x0, orth)
+    numops, numiter = 1, 1
+    HH = np.zeros((krylovdim + 1, krylovdim))
+    converged = 0
+    D = U = fvec = None
+    while True:
+        beta = f.normres()
+        K = f.k
+        if K == krylovdim or beta <= tol or (eager and K >= howmany):
+            if K == 1:
+                D = np.array([f.alphas[0]])
+                U = np.ones((1, 1))
+                fvec = np.array([beta])
+                converged = int(beta <= tol)
+            else:
+                D, U = tridiageigh(f.alphas[:K], f.betas[:K - 1])
+                p = eigsort(which)(D)
+                D, U = permuteeig(D, U, p)
+                fvec = U[K - 1, :] * beta
+                converged = 0
+                while converged < K and abs(fvec[converged]) <= tol:
+                    converged += 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            f = lanczos_expand(A, f, orth)
+            numops += 1
+            if callback:
+                callback(f)
+        else:
+            if numiter == maxiter:
+                break
+            keep = (3 * krylovdim + 2 * converged) // 5
+            H = HH[: keep + 1, :keep]
+            H[:] = 0
+            for j in range(keep):
+                H[j, j] = D[j]
+                H[keep, j] = fvec[j]
+            for j in range(keep - 1, -1, -1):        # Julia j = keep:-1:1
+                rr = list(range(0, j + 1))
+                hb, hv, nu = householder_vec(H[j + 1, rr], j)
+                H[j + 1, j] = nu
+                H[j + 1, :j] = 0
+                householder_lmul(hb, hv, rr, H)
+                householder_rmul(H[: j + 1, :], hb, hv, rr)
+                householder_rmul(U, hb, hv, rr)
+            for j in range(keep):
+                f.alphas[j] = H[j, j]
+                f.betas[j] = H[j + 1, j]
+            basistransform(f.V, U[:, :keep])
+            f.V[keep] = f.r * (1 / beta)
+            f = lanczos_shrink(f, keep)
+            numiter += 1
+    hm = howmany
+    if converged > howmany:
+        hm = converged
+    elif len(D) < howmany:
+        hm = len(D)
+    values = D[:hm].copy()
+    vectors = [unproject(np.zeros_like(f.V[0]), f.V, U[:, i]) for i in range(hm)]
+    residuals = [f.r * U[-1, i] for i in range(hm)]
+    normres = np.abs(fvec[:hm])
+    return values, vectors, dict(converged=converged, residual=residuals, normres=normres,
+                                 numiter=numiter, numops=numops, fact=f)
+
+
+# ------------------------------------------------------------------ Arnoldi / GMRES -------
+
+def hidx(i, j):
+    """PackedHessenberg index (1-based i, j) -> 0-based data index — packedhessenberg.jl:32-39."""
+    return ((j * j + j - 2) >> 1) + i - 1
+
+
+@dataclass
+class ArnoldiFact:
+    k: int
+    V: list
+    H: list          # packed Hessenberg incl. trailing β
+    r: np.ndarray
+
+    def normres(self):
+        return abs(self.H[-1])
+
+    def h(self, i, j):
+        return self.H[hidx(i, j)]
+
+
+def arnoldi_initialize(A, x0, orth: Orth):
+    """arnoldi.jl:135-175 (identical to the Lanczos initialisation)."""
+    f = lanczos_initialize(A, x0, orth)
+    return ArnoldiFact(1, f.V, [f.alphas[0], f.betas[0]], f.r)
+
+
+def arnoldi_initialize_inplace(A, x0, f: ArnoldiFact, orth: Orth):
+    """initialize! — arnoldi.jl:176-198."""
+    while len(f.V) > 1:
+        f.V.pop()
+    f.V[0] = x0 * (1 / norm(x0))
+    w = apply(A, f.V[0])
+    r, alpha = orthogonalize_vec(w, f.V[0], orth)
+    f.k = 1
+    f.H = [alpha, norm(r)]
+    f.r = r
+    return f
+
+
+def arnoldi_expand(A, f: ArnoldiFact, orth: Orth):
+    """expand! — arnoldi.jl:199-219; arnoldirecurrence!! :239-245."""
+    f.k += 1
+    k = f.k
+    beta = f.normres()
+    f.V.append(f.r * (1 / beta))
+    w = apply(A, f.V[-1])
+    h = np.empty(k)
+    r, h = orthogonalize(w, f.V, h, orth)
+    f.H.extend(h.tolist())
+    f.H.append(norm(r))
+    f.r = r
+    return f
+
+
+def linsolve_gmres(A, b, x0=None, krylovdim=30, maxiter=100, tol=1e-12, orth: Orth = Orth(MGS2),
+                   a0=0.0, a1=1.0):
+    """linsolve(operator, b, x₀, ::GMRES, a₀, a₁) — src/linsolve/gmres.jl:1-151.
+    tol is the absolute tolerance (linsolve.jl:159-161 resolves max(atol, rtol*‖b‖))."""
+    if x0 is None:
+        x0 = np.zeros_like(b)
+    y0 = apply(A, x0)
+    r = b * 1.0
+    if a0 != 0:
+        r = r - a0 * x0
+    r = r - a1 * y0
+    x = x0 * 1.0
+    beta = norm(r)
+    if beta < tol:
+        return x, dict(converged=1, residual=r, normres=beta, numiter=0, numops=1)
+    y = np.zeros(krylovdim + 1)
+    gs = [None] * krylovdim
+    R = np.zeros((krylovdim, krylovdim))
+    numiter, numops = 0, 1
+    f = arnoldi_initialize(A, r, orth)
+    numops += 1
+    while True:
+        numiter += 1
+        y[0] = beta
+        k = 1
+        R[0, 0] = a0 + a1 * f.h(1, 1)
+        c, s, rr = givens(R[0, 0], a1 * f.normres())
+        gs[0] = (c, s)
+        R[0, 0] = rr
+        y[1] = 0.0
+        y[0], y[1] = c * y[0] + s * y[1], -s * y[0] + c * y[1]
+        beta = abs(y[1])
+        while R[k - 1, k - 1] != 0 and beta > tol and f.k < krylovdim:
+            f = arnoldi_expand(A, f, orth)
+            numops += 1
+            k = f.k
+            for i in range(1, k):
+                R[i - 1, k - 1] = a1 * f.h(i, k)
+            R[k - 1, k - 1] = a0 + a1 * f.h(k, k)
+            for i in range(k - 1):
+                c, s = gs[i]
+                R[i, k - 1], R[i + 1, k - 1] = (c * R[i, k - 1] + s * R[i + 1, k - 1],
+                                                -s * R[i, k - 1] + c * R[i + 1, k - 1])
+            if math.hypot(R[k - 1, k - 1], a1 * f.normres()) < tol:
+                c, s, rr = givens(0.0, y[k - 1])     # givens(zero, y[k], k+1, k): rotate weight into y[k+1]
+                gs[k - 1] = ("swap", c, s)
+                y[k] = rr
+                y[k - 1] = 0.0
+                R[k - 1, k - 1] = 0.0
+            else:
+                c, s, rr = givens(R[k - 1, k - 1], a1 * f.normres())
+                gs[k - 1] = (c, s)
+                R[k - 1, k - 1] = rr
+                y[k] = 0.0
+                y[k - 1], y[k] = c * y[k - 1] + s * y[k], -s * y[k - 1] + c * y[k]
+            beta = abs(y[k])
+        if R[k - 1, k - 1] == 0 and y[k - 1] == 0:
+            ldiv_upper(R, y, k - 1)
+        else:
+            ldiv_upper(R, y, k)
+        for i in range(k):
+            x = x + y[i] * f.V[i]
+        if beta > tol and numiter < maxiter:
+            # residual without a new operator application (gmres.jl:110-117): rotate the
+            # whole basis with the adjoint Givens sequence, take column k+1
+            V = list(f.V) + [f.r * (1 / f.normres())]
+            for i in range(k):
+                g = gs[i]
+                if g[0] == "swap":
+                    raise NotImplementedError("singular branch restart")
+                c, s = g
+                givens_rmul_basis(V, i, i + 1, c, -s)      # rmul!(V, gs[i]')
+            r = V[k] * y[k]
+        else:
+            r = b * 1.0
+            r = r - apply(A, x, a0, a1)
+            numops += 1
+            beta = norm(r)
+            if beta < tol:
+                return x, dict(converged=1, residual=r, normres=beta, numiter=numiter, numops=numops)
+        if numiter >= maxiter:
+            return x, dict(converged=0, residual=r, normres=beta, numiter=numiter, numops=numops)
+        f = arnoldi_initialize_inplace(A, r, f, orth)
+
+
+# ------------------------------------------------------------------ GKL / svdsolve --------
+
+@dataclass
+class GKLFact:
+    k: int
+    U: list
+    V: list
+    alphas: list
+    betas: list
+    r: np.ndarray
+
+    def normres(self):
+        return self.betas[-1]
+
+
+def gkl_initialize(A, u0, orth: Orth):
+    """initialize(iter::GKLIterator) — gkl.jl:183-215."""
+    beta0 = norm(u0)
+    if beta0 == 0:
+        raise ValueError("initial vector should not have norm zero")
+    v0 = apply_adjoint(A, u0)
+    alpha = norm(v0) / beta0
+    Av0 = apply_normal(A, v0)
+    alpha2 = inner(u0, Av0) / beta0 ** 2
+    if not np.isclose(alpha2, alpha * alpha, rtol=math.sqrt(np.finfo(np.asarray(u0).dtype).eps)):
+        raise ValueError("operator and its adjoint are not compatible")
+    T = np.asarray(u0).dtype.type
+    u = u0 * T(1 / beta0)
+    v = v0 * T(1 / (alpha * beta0))
+    r = Av0 * T(1 / (alpha * beta0))
+    r = r - T(alpha) * u
+    beta = norm(r)
+    return GKLFact(1, [u], [v], [alpha], [beta], r)
+
+
+def gkl_recurrence(A, U, V, beta, orth: Orth):
+    """gklrecurrence — gkl.jl:294-404."""
+    t = orth.tag
+    T = U[-1].dtype.type
+    eps = np.finfo(U[-1].dtype).eps
+    u = U[-1]
+    v = apply_adjoint(A, u)
+    v = v - T(beta) * V[-1]
+    if t == MGS2:
+        for q in V:
+            s = inner(q, v)
+            v = v - T(s) * q
+    alpha = norm(v)
+    if t in (CGSIR, MGSIR):
+        nold = math.sqrt(alpha * alpha + beta * beta)
+        while (alpha < orth.eta * nold) if t == CGSIR else (eps < alpha < orth.eta * nold):
+            nold = alpha
+            if t == CGSIR:
+                s = np.empty(len(V))
+                v, s = _cgs_pass(v, V, s)
+            else:
+                for q in V:
+                    s = inner(q, v)
+                    v = v - T(s) * q
+            alpha = norm(v)
+    v = v * T(1 / alpha)
+    r = apply_normal(A, v)
+    r = r - T(alpha) * u
+    if t == CGS2:
+        s = np.empty(len(U))
+        r, s = _cgs_pass(r, U, s)
+    elif t == MGS2:
+        for q in U:
+            s = inner(q, r)
+            r = r - T(s) * q
+    beta = norm(r)
+    if t in (CGSIR, MGSIR):
+        nold = math.sqrt(alpha * alpha + beta * beta)
+        while eps < beta < orth.eta * nold:
+            nold = beta
+            if t == CGSIR:
+                s = np.empty(len(U))
+                r, s = _cgs_pass(r, U, s)
+            else:
+                for q in U:
+                    s = inner(q, r)
+                    r = r - T(s) * q
+            beta = norm(r)
+    return v, r, alpha, beta
+
+
+def gkl_expand(A, f: GKLFact, orth: Orth):
+    """expand! — gkl.jl:246-269."""
+    betaold = f.normres()
+    T = f.r.dtype.type
+    f.U.append(f.r * T(1 / betaold))
+    v, r, alpha, beta = gkl_recurrence(A, f.U, f.V, betaold, orth)
+    f.V.append(v)
+    f.alphas.append(alpha)
+    f.betas.append(beta)
+    f.k += 1
+    f.r = r
+    return f
+
+
+def gkl_shrink(f: GKLFact, k):
+    """shrink! — gkl.jl:270-291."""
+    if f.k <= k:
+        return f
+    while len(f.V) > k + 1:
+        f.U.pop()
+        f.V.pop()
+    f.V.pop()
+    r = f.U.pop()
+    del f.alphas[k:]
+    del f.betas[k:]
+    f.k = k
+    f.r = r * r.dtype.type(f.normres())
+    return f
+
+
+def bidiagsvd_lower(alphas, betas):
+    """bidiagsvd!(Bidiagonal(αs, βs, :L)) -> (P, S, Q) with B = P*Diag(S)*Q (Q = Vt).
+    The reference calls LAPACK bdsqr (dense/linalg.jl:123-130); values identical,
+    vectors up to a common sign per triplet."""
+    K = len(alphas)
+    B = np.diag(np.asarray(alphas, dtype=np.float64))
+    for i in range(K - 1):
+        B[i + 1, i] = betas[i]
+    P, S, Q = np.linalg.svd(B)
+    return P, S, Q
+
+
+def svdsolve_gkl(A, u0, howmany=1, which="LR", krylovdim=30, maxiter=100, tol=1e-12,
+                 orth: Orth = Orth(MGS2), eager=False):
+    """svdsolve(A, x₀, howmany, which, ::GKL) — src/eigsolve/svdsolve.jl:144-314."""
+    if howmany > krylovdim:
+        raise ValueError("krylov dimension too small")
+    numiter = 1
+    f = gkl_initialize(A, u0, orth)
+    numops = 2
+    HH = np.zeros((krylovdim + 1, krylovdim))
+    converged = 0
+    P = S = Q = fvec = None
+    while True:
+        beta = f.normres()
+        K = f.k
+        if K == krylovdim or beta <= tol or (eager and K >= howmany):
+            P, S, Q = bidiagsvd_lower(f.alphas[:K], f.betas[:K - 1])
+            if which == "SR":
+                P = P[:, ::-1].copy()
+                S = S[::-1].copy()
+                Q = Q[::-1, :].copy()
+            elif which != "LR":
+                raise ValueError(which)
+            fvec = Q.T[K - 1, :] * beta          # mul!(f, view(Q', K, :), β)
+            converged = 0
+            while converged < K and abs(fvec[converged]) < tol:
+                converged += 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            f = gkl_expand(A, f, orth)
+            numops += 2
+        else:
+            if numiter == maxiter:
+                break
+            keep = (3 * krylovdim + 2 * converged) // 5
+            T = f.r.dtype.type
+            Pc = P.astype(f.r.dtype)
+            Qc = Q.T.astype(f.r.dtype)
+            basistransform(f.U, Pc[:, :keep])
+            basistransform(f.V, Qc[:, :keep])
+            f.U[keep] = f.r * T(1 / f.normres())
+            H = HH[: keep + 1, :keep]
+            H[:] = 0
+            for j in range(keep):
+                H[j, j] = S[j]
+                H[keep, j] = fvec[j]
+            for j in range(keep - 1, -1, -1):
+                rr = list(range(0, j + 1))
+                hb, hv, nu = householder_vec(H[j + 1, rr], j)
+                H[j + 1, j] = nu
+                H[j + 1, :j] = 0
+                householder_rmul(H[: j + 1, :], hb, hv, rr)
+                householder_rmul_basis(f.V, T(hb), hv.astype(f.r.dtype), rr)
+                hb, hv, nu = householder_vec(H[rr, j], j)
+                H[j, j] = nu
+                H[:j, j] = 0
+                householder_lmul(hb, hv, rr, H[:, :j])
+                householder_rmul_basis(f.U, T(hb), hv.astype(f.r.dtype), rr)
+            for j in range(keep):
+                f.alphas[j] = H[j, j]
+                f.betas[j] = H[j + 1, j]
+            f = gkl_shrink(f, keep)
+            numiter += 1
+    if converged > howmany:
+        howmany = converged
+    values = S[:howmany].copy()
+    dt = f.r.dtype
+    left = [unproject(np.zeros_like(f.U[0]), f.U, P[:, i].astype(dt)) for i in range(howmany)]
+    right = [unproject(np.zeros_like(f.V[0]), f.V, Q[i, :].astype(dt)) for i in range(howmany)]
+    residuals = [f.r * dt.type(Q[i, -1]) for i in range(howmany)]
+    normres = np.abs(fvec[:howmany])
+    return values, left, right, dict(converged=converged, residual=residuals, normres=normres,
+                                     numiter=numiter, numops=numops, fact=f)
+
+
+# ------------------------------------------------------------------ block primitives ------
+
+def block_inner(X, Y):
+    """blocklanczos.jl:43-52."""
+    M = np.empty((len(X), len(Y)))
+    for j in range(len(Y)):
+        for i in range(len(X)):
+            M[i, j] = inner(X[i], Y[j])
+    return M
+
+
+def block_reorthogonalize(R, V):
+    """blocklanczos.jl:277-284."""
+    for i in range(len(R)):
+        for q in V:
+            s = inner(q, R[i])
+            R[i] = R[i] - s * q
+    return R
+
+
+def block_qr(block, tol):
+    """block_qr! — blocklanczos.jl:312-353.  Returns (R[good,:], good_idx, is_drift)."""
+    n = len(block)
+    drift = False
+    idx = [True] * n
+    R = np.zeros((n, n))
+    beta = math.sqrt(inner(block[0], block[0]))
+    if beta > tol:
+        R[0, 0] = beta
+        block[0] = block[0] * (1 / beta)
+    else:
+        block[0] = block[0] * 0.0
+        idx[0] = False
+    for j in range(1, n):
+        for i in range(j):
+            R[i, j] = inner(block[i], block[j])
+            block[j] = block[j] - R[i, j] * block[i]
+        beta = norm(block[j])
+        if tol < beta < 100 * tol:
+            drift = True
+            for i in range(j):
+                d = inner(block[i], block[j])
+                R[i, j] += d
+                block[j] = block[j] - d * block[i]
+            beta = norm(block[j])
+        if beta < tol:
+            block[j] = block[j] * 0.0
+            idx[j] = False
+        else:
+            R[j, j] = beta
+            block[j] = block[j] * (1 / beta)
+    good = [i for i in range(n) if idx[i]]
+    return R[good, :], good, drift
+
+
+# ------------------------------------------------------------------ fixtures --------------
+
+def toric_code_hamiltonian(m, n):
+    """test/eigsolve.jl:471-533: H = Σ X-plaquettes + Σ Z-vertices (last of each dropped)."""
+    N = 2 * m * n
+
+    def li(i, j):       # LinearIndices((m, n))[mod1(i,m), mod1(j,n)], 1-based
+        return ((j - 1) % n) * m + ((i - 1) % m) + 1
+
+    def bottom(i, j):
+        return li(i, j) + m * n
+
+    def right(i, j):
+        return li(i, j)
+
+    xs, zs = [], []
+    for i in range(1, m + 1):        # Julia: for i in 1:m, j in 1:n  (j inner)
+        for j in range(1, n + 1):
+            xs.append((bottom(i, j + 1), right(i, j), bottom(i, j), right(i - 1, j)))
+            zs.append((right(i, j), bottom(i, j), right(i, j - 1), bottom(i + 1, j)))
+    dim = 2 ** N
+    idx = np.arange(dim, dtype=np.int64)
+    rows, cols, vals = [], [], []
+    diag = np.zeros(dim)
+    for s in xs[:-1]:
+        mask = 0
+        for pos in s:                # qubit `pos` (1-based, kron order: pos 1 = most significant)
+            mask ^= 1 << (N - pos)
+        rows.append(idx)
+        cols.append(idx ^ mask)
+        vals.append(np.ones(dim))
+    for s in zs[:-1]:
+        sign = np.ones(dim)
+        for pos in s:
+            sign *= 1 - 2 * ((idx >> (N - pos)) & 1)
+        diag += sign
+    rows.append(idx)
+    cols.append(idx)
+    vals.append(diag)
+    H = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(dim, dim))
+    H.sum_duplicates()
+    H.sort_indices()
+    return H

@@ -1,0 +1,87 @@
+"""CPU checks of the drop-in boundary: the shared library loads without a GPU, exports every
+symbol include/b200krylov.h declares, the ctypes prototypes cover the header, and the
+product path fails loudly (no CPU fallback) when no device is present."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import krylovkit_jl_b200 as kk
+from krylovkit_jl_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200krylov.h")
+
+
+def declared():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2k_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = declared()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in b200krylov.h but not exported"
+    out = subprocess.run(["nm", "-D", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(names) <= exported
+
+
+def test_ctypes_prototypes_cover_header():
+    assert set(declared()) == set(L.EXPORTED)
+
+
+def test_abi_version_and_status_codes():
+    lib = L.load()
+    assert lib.b2k_abi_version() == 1
+    txt = open(HEADER).read()
+    for name, val in (("B2K_EINVAL", L.EINVAL), ("B2K_EDIM", L.EDIM), ("B2K_ECUDA", L.ECUDA),
+                      ("B2K_ENOMEM", L.ENOMEM), ("B2K_ENCCL", L.ENCCL), ("B2K_ENOTSUP", L.ENOTSUP),
+                      ("B2K_CGS2", L.CGS2), ("B2K_MGSIR", L.MGSIR), ("B2K_F32", L.F32)):
+        m = re.search(rf"#define\s+{name}\s+(-?\d+)", txt)
+        assert m and int(m.group(1)) == val
+
+
+def test_no_cpu_fallback_without_device():
+    from conftest import HAVE_GPU
+    if HAVE_GPU:
+        pytest.skip("a GPU is present")
+    with pytest.raises(kk.B200Error, match="no CPU fallback"):
+        kk.B200Context(100, 8)
+    import numpy as np
+    import scipy.sparse as sp
+    with pytest.raises(kk.B200Error):
+        kk.eigsolve(sp.identity(10, format="csr"), np.ones(10), 1, "SR", kk.Lanczos(krylovdim=5))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "krylovkit.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "krylov_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_host_dense_helpers_match_oracle_conventions():
+    """host k x k mirror (krylovkit.jl_b200/dense.py) vs the oracle's restatement."""
+    import numpy as np
+    from krylovkit_jl_b200 import dense
+    from oracle import krylov_oracle as ko
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(7)
+    for i in (0, 3, 6):
+        b1, v1, n1 = dense._householder(x, i)
+        b2, v2, n2 = ko.householder_vec(x, i)
+        assert b1 == b2 and n1 == n2 and np.array_equal(v1, v2)
+    dv, ev = rng.standard_normal(9), rng.standard_normal(8)
+    w1, z1 = dense.tridiageigh(dv, ev)
+    T = np.diag(dv) + np.diag(ev, 1) + np.diag(ev, -1)
+    np.testing.assert_allclose(w1, np.linalg.eigvalsh(T), atol=1e-13)
+    np.testing.assert_allclose(T @ z1, z1 * w1, atol=1e-13)
+    assert dense.hidx(1, 1) == 0 and dense.hidx(2, 1) == 1 and dense.hidx(1, 2) == 2 and dense.hidx(3, 2) == 4
+    assert dense.givens(3.0, 4.0) == ko.givens(3.0, 4.0)

@@ -163,7 +163,7 @@ def test_project_unproject(n, k):
     ctx.close()
 
 
-ALGS = [kk.cgs, kk.mgs, kk.cgs2, kk.mgs2, kk.ClassicalGramSchmidtIR(0.75), kk.ModifiedGramSchmidtIR(0.75)]
+ALGS = [kk.cgs, kk.mgs, kk.cgs2, kk.mgs2, kk.ClassicalGramSchmidtIR(eta=0.75), kk.ModifiedGramSchmidtIR(eta=0.75)]
 
 
 @pytest.mark.parametrize("alg", ALGS, ids=lambda a: type(a).__name__)

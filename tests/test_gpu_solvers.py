@@ -1,0 +1,274 @@
+"""GPU parity of the factorizations and drivers (called through the C-ABI via the host
+mirror) against the CPU oracle on identical (A, x0): per-step Lanczos/Arnoldi/GKL
+coefficients, Ritz values within 1e-10 relative (FP64), residual identities within the
+reference's own tolerances (test/testsetup.jl:14-15)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+import krylovkit_jl_b200 as kk
+from krylovkit_jl_b200 import _lib as L
+from krylovkit_jl_b200.factorizations import arnoldi as ar
+from krylovkit_jl_b200.factorizations import gkl as gk
+from krylovkit_jl_b200.factorizations import lanczos as lz
+from oracle import krylov_oracle as ko
+
+SEED = 20260923
+PAIRS = [(kk.cgs, ko.Orth(ko.CGS)), (kk.mgs, ko.Orth(ko.MGS)), (kk.cgs2, ko.Orth(ko.CGS2)),
+         (kk.mgs2, ko.Orth(ko.MGS2)), (kk.ClassicalGramSchmidtIR(eta=0.75), ko.Orth(ko.CGSIR, 0.75)),
+         (kk.ModifiedGramSchmidtIR(eta=0.75), ko.Orth(ko.MGSIR, 0.75))]
+IDS = ["cgs", "mgs", "cgs2", "mgs2", "cgsr", "mgsr"]
+
+
+def conv_diff(nx, ny):
+    return ko.stencil_matrix(nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0, 0))
+
+
+@pytest.mark.parametrize("pair", PAIRS, ids=IDS)
+@pytest.mark.parametrize("fused", [True, False])
+def test_lanczos_steps_match_oracle(pair, fused):
+    """expand! step by step: alpha_k, beta_k equal the oracle's to <= 1e-12 relative for the
+    reorthogonalised variants; V'V = I, A V = V T + r e' (test/factorize.jl:140-148)."""
+    orth, oorth = pair
+    nx, ny = 61, 43
+    n = nx * ny
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(SEED, n)
+    ctx = kk.B200Context(n, 40)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    it = lz.LanczosIterator(op, ctx.from_host(x0), orth)
+    f = lz.initialize(it)
+    g = ko.lanczos_initialize(A, x0, oorth)
+    steps = 24
+    for _ in range(steps):
+        f = lz.expand_(it, f, fused=fused)
+        g = ko.lanczos_expand(A, g, oorth)
+    tol = 1e-12 if orth.tag not in (L.CGS, L.MGS) else 1e-6
+    np.testing.assert_allclose(f.alphas, g.alphas, rtol=tol, atol=tol)
+    np.testing.assert_allclose(f.betas, g.betas, rtol=tol, atol=tol)
+    V = np.column_stack([v.to_host() for v in f.V])
+    k = f.k
+    T = np.diag(f.alphas) + np.diag(f.betas[:k - 1], 1) + np.diag(f.betas[:k - 1], -1)
+    r = f.r.to_host()
+    if orth.tag not in (L.CGS, L.MGS):
+        assert np.abs(V.T @ V - np.eye(k)).max() < 1e-12
+    E = A @ V - V @ T
+    E[:, -1] -= r
+    assert np.abs(E).max() < 1e-11
+    assert abs(np.linalg.norm(r) - f.normres()) < 1e-12
+    lz.shrink_(f, 10)
+    assert f.k == 10 and len(f.V) == 10
+    ctx.close()
+
+
+@pytest.mark.parametrize("pair", PAIRS, ids=IDS)
+def test_arnoldi_steps_match_oracle(pair):
+    orth, oorth = pair
+    nx, ny = 50, 37
+    n = nx * ny
+    A = conv_diff(nx, ny)
+    x0 = ko.splitmix_vector(SEED, n)
+    ctx = kk.B200Context(n, 40)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    it = ar.ArnoldiIterator(op, ctx.from_host(x0), orth)
+    f = ar.initialize(it)
+    g = ko.arnoldi_initialize(A, x0, oorth)
+    for _ in range(20):
+        f = ar.expand_(it, f)
+        g = ko.arnoldi_expand(A, g, oorth)
+    tol = 1e-12 if orth.tag not in (L.CGS, L.MGS) else 1e-8
+    np.testing.assert_allclose(f.H, g.H, rtol=tol, atol=tol)
+    V = np.column_stack([v.to_host() for v in f.V])
+    H = f.rayleighquotient()
+    E = A @ V - V @ H
+    E[:, -1] -= f.r.to_host()
+    assert np.abs(E).max() < 1e-11
+    ctx.close()
+
+
+@pytest.mark.parametrize("which", ["SR", "LR"])
+@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3], PAIRS[4]], ids=["cgs2", "mgs2", "cgsr"])
+def test_eigsolve_config1_matches_oracle_and_closed_form(pair, which):
+    """BASELINE config 1 (1e4 x 1e4 5-point Laplacian, krylovdim 30, howmany 4): Ritz values
+    within 1e-10 relative of the oracle and of the closed form, residuals within tol."""
+    orth, oorth = pair
+    nx, ny = 125, 80
+    n = nx * ny
+    A = ko.stencil_matrix(nx, ny)
+    lam = ko.laplace_eigenvalues(nx, ny)
+    x0 = ko.splitmix_vector(SEED, n)
+    alg = kk.Lanczos(orth=orth, krylovdim=30, maxiter=300, tol=1e-10, verbosity=0)
+    ctx = kk.B200Context(n, 40)
+    op = kk.B200CSR.stencil(ctx, nx, ny)
+    vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0), 4, which, alg)
+    ovals, ovecs, oinfo = ko.eigsolve_lanczos(A, x0, 4, which, krylovdim=30, maxiter=300, tol=1e-10,
+                                              orth=oorth)
+    assert info.converged >= 4
+    assert info.numiter == oinfo["numiter"] and info.numops == oinfo["numops"]
+    np.testing.assert_allclose(vals[:4], ovals[:4], rtol=1e-10)
+    ref = lam[:4] if which == "SR" else lam[::-1][:4]
+    np.testing.assert_allclose(vals[:4], ref, rtol=1e-10)
+    for i in range(4):
+        v = vecs[i].to_host()
+        assert np.linalg.norm(A @ v - vals[i] * v) < 1e-8
+        assert abs(np.linalg.norm(v) - 1) < 1e-10
+    ctx.close()
+
+
+def test_eigsolve_unconverged_fixed_cycles_matches_oracle():
+    """The benchmark regime: a fixed number of restart cycles far from convergence.  Ritz
+    values and residual norms agree with the oracle at that point."""
+    nx, ny = 300, 200
+    n = nx * ny
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(SEED, n)
+    ctx = kk.B200Context(n, 70)
+    op = kk.B200CSR.stencil(ctx, nx, ny)
+    alg = kk.Lanczos(orth=kk.cgs2, krylovdim=60, maxiter=3, tol=1e-14, verbosity=0)
+    vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0), 4, "SR", alg)
+    ovals, _, oinfo = ko.eigsolve_lanczos(A, x0, 4, "SR", krylovdim=60, maxiter=3, tol=1e-14,
+                                          orth=ko.Orth(ko.CGS2))
+    assert info.numops == oinfo["numops"] == 60 + 2 * 24
+    np.testing.assert_allclose(vals, ovals, rtol=1e-10)
+    np.testing.assert_allclose(info.normres, oinfo["normres"], rtol=1e-6, atol=1e-12)
+    ctx.close()
+
+
+def test_eigsolve_host_buffers_end_to_end():
+    nx, ny = 64, 48
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(3, nx * ny)
+    vals, vecs, info = kk.eigsolve(A, x0, 2, "LR", kk.Lanczos(orth=kk.cgs2, krylovdim=30, tol=1e-10,
+                                                              verbosity=0))
+    lam = ko.laplace_eigenvalues(nx, ny)
+    assert info.converged >= 2
+    np.testing.assert_allclose(vals[:2], lam[::-1][:2], rtol=1e-10)
+    assert isinstance(vecs[0], np.ndarray)
+    assert np.linalg.norm(A @ vecs[0] - vals[0] * vecs[0]) < 1e-8
+
+
+def test_issue143_and_toric_on_gpu():
+    """the reference's known-answer fixtures through the GPU path."""
+    import os
+    A = np.load(os.path.join(os.path.dirname(__file__), "golden", "issue143_matrix.npy"))
+    n = A.shape[0]
+    rng = np.random.default_rng(143)
+    vals, vecs, info = kk.eigsolve(sp.csr_matrix(A), rng.standard_normal(n), n, "SR",
+                                   kk.Lanczos(orth=kk.mgs2, krylovdim=n, maxiter=1, tol=1e-12, verbosity=0))
+    ref = np.linalg.eigvalsh(A)
+    np.testing.assert_allclose(vals, ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max())
+    H = ko.toric_code_hamiltonian(3, 3)
+    x0 = ko.splitmix_vector(7, H.shape[0])
+    vals, vecs, info = kk.eigsolve(-H, x0, 1, "SR", kk.Lanczos(orth=kk.cgs2, krylovdim=30, maxiter=30,
+                                                               tol=1e-8, verbosity=0))
+    assert info.converged >= 1 and abs(vals[0] + 16.0) < 1e-8
+
+
+@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3]], ids=["cgs2", "mgs2"])
+@pytest.mark.parametrize("literal", [False, True])
+def test_gmres_matches_oracle(pair, literal):
+    """config 3 at test size: nonsymmetric convection-diffusion, b = A*1, restarted GMRES."""
+    from krylovkit_jl_b200 import linsolve as ls
+    orth, oorth = pair
+    nx, ny = 80, 50
+    n = nx * ny
+    A = conv_diff(nx, ny)
+    b = A @ np.ones(n)
+    ls.LITERAL_GIVENS_RESTART = literal
+    ctx = kk.B200Context(n, 60)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    alg = kk.GMRES(orth=orth, krylovdim=40, maxiter=5, tol=1e-12, verbosity=0)
+    x, info = kk.linsolve(op, ctx.from_host(b), None, alg)
+    ox, oinfo = ko.linsolve_gmres(A, b, None, krylovdim=40, maxiter=5, tol=1e-12, orth=oorth)
+    ls.LITERAL_GIVENS_RESTART = False
+    assert info.numiter == oinfo["numiter"] and info.numops == oinfo["numops"]
+    xh = x.to_host()
+    # b = A x + residual  (test/linsolve.jl:230)
+    np.testing.assert_allclose(A @ xh + info.residual.to_host(), b, atol=1e-10)
+    np.testing.assert_allclose(info.normres, oinfo["normres"], rtol=1e-6, atol=1e-13)
+    np.testing.assert_allclose(xh, ox, rtol=1e-8, atol=1e-10)
+    # converged solve
+    alg2 = kk.GMRES(orth=orth, krylovdim=40, maxiter=100, tol=1e-10, verbosity=0)
+    x2, info2 = kk.linsolve(op, ctx.from_host(b), None, alg2, 0.5, 1.5)
+    assert info2.converged == 1
+    x2h = x2.to_host()
+    assert np.linalg.norm(0.5 * x2h + 1.5 * (A @ x2h) - b) < 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3], PAIRS[4]], ids=["cgs2", "mgs2", "cgsr"])
+def test_svdsolve_matches_oracle_f64(pair):
+    orth, oorth = pair
+    m, n = 3001, 120
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((m, n))
+    u0 = rng.standard_normal(m)
+    alg = kk.GKL(orth=orth, krylovdim=25, maxiter=100, tol=1e-10, verbosity=0)
+    S, Lv, Rv, info = kk.svdsolve(A, u0, 5, "LR", alg)
+    oS, _, _, oinfo = ko.svdsolve_gkl(A, u0, 5, "LR", krylovdim=25, maxiter=100, tol=1e-10, orth=oorth)
+    ref = np.linalg.svd(A, compute_uv=False)
+    assert info.converged >= 5
+    np.testing.assert_allclose(S[:5], ref[:5], rtol=1e-10)
+    np.testing.assert_allclose(S[:5], oS[:5], rtol=1e-10)
+    U, V = np.column_stack(Lv), np.column_stack(Rv)
+    c = U.shape[1]
+    assert np.abs(U.T @ U - np.eye(c)).max() < 1e-9
+    np.testing.assert_allclose(A.T @ U, V * S[:c], atol=1e-8)
+    Rm = np.column_stack(info.residual)
+    np.testing.assert_allclose(A @ V, U * S[:c] + Rm, atol=1e-8)
+
+
+def test_svdsolve_config4_small_f32():
+    """config 4 at test size: dense tall Float32, 6 triplets, GKL(krylovdim=30, tol=1e-5)."""
+    m, n = 20000, 512
+    A = ko.dense_splitmix(SEED, m, n)
+    u0 = ko.splitmix_vector(SEED + 1, m, dtype=np.float32)
+    alg = kk.GKL(orth=kk.cgs2, krylovdim=30, maxiter=100, tol=1e-5, verbosity=0)
+    ctx = kk.B200Context(m, 40, dtype=np.float32)
+    sv = ctx.add_space(n, 40, sharded=False)
+    op = kk.B200Dense.splitmix(ctx, m, n, SEED, sv)
+    S, Lv, Rv, info = kk.svdsolve(op, ctx.from_host(u0), 6, "LR", alg)
+    ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    assert info.converged >= 6
+    np.testing.assert_allclose(S[:6], ref[:6], rtol=3e-5)
+    u, v = Lv[0].to_host().astype(np.float64), Rv[0].to_host().astype(np.float64)
+    assert np.linalg.norm(A.astype(np.float64) @ v - S[0] * u) < 1e-3 * S[0]
+    ctx.close()
+
+
+def test_block_primitives_gpu():
+    n, p, k = 5003, 5, 12
+    rng = np.random.default_rng(12)
+    ctx = kk.B200Context(n, 40)
+    import ctypes as C
+    from krylovkit_jl_b200.vectors import handles
+    Xh = rng.standard_normal((n, p))
+    Yh = rng.standard_normal((n, p))
+    X = [ctx.from_host(Xh[:, j]) for j in range(p)]
+    Y = [ctx.from_host(Yh[:, j]) for j in range(p)]
+    M = np.zeros((p, p), order="F")
+    ctx.check(ctx.lib.b2k_block_inner(ctx.h, handles(X), p, handles(Y), p,
+                                      M.ctypes.data_as(C.POINTER(C.c_double))))
+    np.testing.assert_allclose(M, Xh.T @ Yh, rtol=1e-12, atol=1e-10)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    V = [ctx.from_host(Q[:, j]) for j in range(k)]
+    ctx.check(ctx.lib.b2k_block_reorthogonalize(ctx.h, handles(X), p, handles(V), k))
+    Xr = np.column_stack([x.to_host() for x in X])
+    assert np.abs(Q.T @ Xr).max() < 1e-11
+    # block_qr with a dependent column
+    Zh = rng.standard_normal((n, p))
+    Zh[:, 3] = 2 * Zh[:, 0] - Zh[:, 1]
+    Z = [ctx.from_host(Zh[:, j]) for j in range(p)]
+    R = np.zeros((p, p), order="F")
+    good = (C.c_int32 * p)()
+    drift = C.c_int32()
+    ctx.check(ctx.lib.b2k_block_qr(ctx.h, handles(Z), p, 1e-8, R.ctypes.data_as(C.POINTER(C.c_double)),
+                                   good, C.byref(drift)))
+    oR, ogood, odrift = ko.block_qr([Zh[:, j].copy() for j in range(p)], 1e-8)
+    assert [i for i in range(p) if good[i]] == ogood == [0, 1, 2, 4]
+    Qz = np.column_stack([Z[i].to_host() for i in ogood])
+    np.testing.assert_allclose(Qz @ R[ogood, :], Zh, atol=1e-8)
+    np.testing.assert_allclose(R[ogood, :], oR, rtol=1e-8, atol=1e-8)
+    ctx.close()

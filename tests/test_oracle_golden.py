@@ -1,0 +1,283 @@
+"""CPU tests that pin the oracle (oracle/krylov_oracle.py) against the reference's own
+known-answer fixtures and against the invariants the reference asserts in its test-suite
+(test/factorize.jl, test/linalg.jl, test/eigsolve.jl, test/linsolve.jl, test/svdsolve.jl,
+test/issues.jl, test/block.jl)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import krylov_oracle as ko
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EPS = np.finfo(np.float64).eps
+TOL = EPS ** (2 / 3)              # tolerance(T) — test/testsetup.jl:14
+ORTHS = {
+    "cgs": ko.Orth(ko.CGS), "mgs": ko.Orth(ko.MGS), "cgs2": ko.Orth(ko.CGS2), "mgs2": ko.Orth(ko.MGS2),
+    "cgsr": ko.Orth(ko.CGSIR, 0.75), "mgsr": ko.Orth(ko.MGSIR, 0.75),      # test/runtests.jl:18-24
+}
+REORTH = ["cgs2", "mgs2", "cgsr", "mgsr"]     # Lanczos/GKL tests skip plain cgs/mgs (factorize.jl:7)
+
+
+def symm(rng, n):
+    A = rng.standard_normal((n, n))
+    return (A + A.T) / 2
+
+
+# ---- known-answer fixtures of the reference ---------------------------------------------
+
+def test_issue143_matrix_spectrum():
+    """test/issues.jl:39-129: the literal 71x71 matrix; a complete Lanczos factorization
+    must reproduce the dense spectrum."""
+    A = np.load(os.path.join(HERE, "golden", "issue143_matrix.npy"))
+    n = A.shape[0]
+    ref = np.linalg.eigvalsh(A)
+    rng = np.random.default_rng(143)
+    D, V, info = ko.eigsolve_lanczos(A, rng.standard_normal(n), n, "SR", krylovdim=n, maxiter=1,
+                                     tol=1e-12, orth=ORTHS["mgs2"])
+    assert len(D) == n
+    np.testing.assert_allclose(D, ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max())
+    U = np.column_stack(V)
+    np.testing.assert_allclose(A @ U, U * D, atol=1e-8 * np.abs(ref).max())
+
+
+def test_issue156_identity():
+    """test/issues.jl:32-36: eigsolve([1 0; 0 1]) -> 1.0."""
+    A = np.eye(2)
+    D, V, info = ko.eigsolve_lanczos(A, np.array([0.3, 0.8]), 1, "LM", krylovdim=2, tol=1e-12)
+    assert info["converged"] >= 1
+    assert np.allclose(D[: info["converged"]], 1.0)
+
+
+def test_toric_code_ground_energy():
+    """test/eigsolve.jl:471-549: -H of the 3x3 toric code has lowest eigenvalue -16."""
+    H = ko.toric_code_hamiltonian(3, 3)
+    assert H.shape == (2 ** 18, 2 ** 18)
+    assert abs(H - H.T).max() == 0
+    x0 = ko.splitmix_vector(7, H.shape[0])
+    D, V, info = ko.eigsolve_lanczos(-H, x0, 1, "SR", krylovdim=30, maxiter=30, tol=1e-8,
+                                     orth=ORTHS["cgs2"])
+    assert info["converged"] >= 1
+    assert abs(D[0] + 16.0) < 1e-8
+
+
+def test_laplacian_closed_form_config1():
+    """BASELINE config 1: eigsolve(Lanczos, :SR, 4) on the 1e4 x 1e4 5-point Laplacian,
+    krylovdim = 30, against the closed-form spectrum.  A non-degenerate
+    125 x 80 grid is used so that the four smallest eigenvalues are simple."""
+    nx, ny = 125, 80
+    A = ko.stencil_matrix(nx, ny)
+    lam = ko.laplace_eigenvalues(nx, ny)
+    x0 = ko.splitmix_vector(20260923, nx * ny)
+    D, V, info = ko.eigsolve_lanczos(A, x0, 4, "SR", krylovdim=30, maxiter=300, tol=1e-10,
+                                     orth=ORTHS["mgs2"])
+    assert info["converged"] >= 4
+    np.testing.assert_allclose(D[:4], lam[:4], rtol=1e-10)
+    for i in range(4):
+        assert np.linalg.norm(A @ V[i] - D[i] * V[i]) < 1e-8
+
+
+# ---- invariants of the reference's tests -------------------------------------------------
+
+@pytest.mark.parametrize("name", list(ORTHS))
+def test_orthonormalize_identities(name):
+    """test/linalg.jl:4-25."""
+    rng = np.random.default_rng(1)
+    n, k = 100, 10
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    b = [Q[:, j].copy() for j in range(k)]
+    a = rng.standard_normal(n)
+    v, beta, x = ko.orthonormalize(a.copy(), b, np.zeros(k), ORTHS[name])
+    assert abs(np.linalg.norm(v) - 1) < 1e-12
+    assert abs(np.hypot(beta, np.linalg.norm(x)) - np.linalg.norm(a)) < 1e-10
+    assert np.abs(Q.T @ v).max() < (1e-8 if name in ("cgs", "mgs") else 1e-12)
+    np.testing.assert_allclose(Q @ x + beta * v, a, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", REORTH)
+def test_lanczos_factorization_invariants(name):
+    """test/factorize.jl:140-158: after every expand!: V'V = I, ‖r‖ = β, A V = V H + r e';
+    again after shrink!."""
+    rng = np.random.default_rng(2)
+    n = 100
+    A = symm(rng, n)
+    f = ko.lanczos_initialize(A, rng.standard_normal(n), ORTHS[name])
+    for _ in range(29):
+        f = ko.lanczos_expand(A, f, ORTHS[name])
+        V = np.column_stack(f.V)
+        k = f.k
+        T = np.diag(f.alphas) + np.diag(f.betas[:k - 1], 1) + np.diag(f.betas[:k - 1], -1)
+        assert np.abs(V.T @ V - np.eye(k)).max() < 1e-12
+        assert abs(np.linalg.norm(f.r) - f.normres()) < 1e-12
+        E = A @ V - V @ T
+        E[:, -1] -= f.r
+        assert np.abs(E).max() < 1e-11
+    f = ko.lanczos_shrink(f, 12)
+    V = np.column_stack(f.V)
+    T = np.diag(f.alphas) + np.diag(f.betas[:11], 1) + np.diag(f.betas[:11], -1)
+    E = A @ V - V @ T
+    E[:, -1] -= f.r
+    assert f.k == 12 and len(f.V) == 12 and np.abs(E).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", list(ORTHS))
+def test_arnoldi_factorization_invariants(name):
+    """test/factorize.jl:185-203."""
+    rng = np.random.default_rng(3)
+    n = 100
+    A = rng.standard_normal((n, n))
+    f = ko.arnoldi_initialize(A, rng.standard_normal(n), ORTHS[name])
+    tol = 1e-9 if name in ("cgs", "mgs") else 1e-11
+    for _ in range(25):
+        f = ko.arnoldi_expand(A, f, ORTHS[name])
+    k = f.k
+    V = np.column_stack(f.V)
+    H = np.zeros((k, k))
+    for j in range(1, k + 1):
+        for i in range(1, min(j + 1, k) + 1):
+            H[i - 1, j - 1] = f.h(i, j)
+    assert np.abs(V.T @ V - np.eye(k)).max() < tol
+    E = A @ V - V @ H
+    E[:, -1] -= f.r
+    assert np.abs(E).max() < tol
+    assert abs(np.linalg.norm(f.r) - f.normres()) < 1e-12
+
+
+@pytest.mark.parametrize("name", REORTH)
+def test_gkl_factorization_invariants(name):
+    """test/factorize.jl:285-309: U'U = I, V'V = I, A V = U B + r e', A'U = V B'."""
+    rng = np.random.default_rng(4)
+    m, n = 120, 80
+    A = rng.standard_normal((m, n))
+    f = ko.gkl_initialize(A, rng.standard_normal(m), ORTHS[name])
+    for _ in range(20):
+        f = ko.gkl_expand(A, f, ORTHS[name])
+    k = f.k
+    U, V = np.column_stack(f.U), np.column_stack(f.V)
+    B = np.diag(f.alphas) + np.diag(f.betas[:k - 1], -1)
+    assert np.abs(U.T @ U - np.eye(k)).max() < 1e-11
+    assert np.abs(V.T @ V - np.eye(k)).max() < 1e-11
+    E = A @ V - U @ B
+    E[:, -1] -= f.r
+    assert np.abs(E).max() < 1e-10
+    assert np.abs(A.T @ U - V @ B.T).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", REORTH)
+@pytest.mark.parametrize("which", ["SR", "LR", "LM"])
+def test_eigsolve_iterative(name, which):
+    """test/eigsolve.jl:84-136: values vs dense eigvals, U'U = I, A U = U D + R."""
+    rng = np.random.default_rng(5)
+    n = 100
+    A = symm(rng, n)
+    ref = np.linalg.eigvalsh(A)
+    order = {"SR": ref, "LR": ref[::-1], "LM": ref[np.argsort(-np.abs(ref))]}[which]
+    D, V, info = ko.eigsolve_lanczos(A, rng.standard_normal(n), 6, which, krylovdim=30, maxiter=50,
+                                     tol=TOL, orth=ORTHS[name])
+    c = info["converged"]
+    assert c >= 6
+    np.testing.assert_allclose(D[:c], order[:c], atol=10 * TOL * np.abs(ref).max())
+    U = np.column_stack(V)
+    assert np.abs(U.T @ U - np.eye(U.shape[1])).max() < 1e-10
+    Rm = np.column_stack(info["residual"])
+    np.testing.assert_allclose(A @ U, U * D[: U.shape[1]] + Rm, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(ORTHS))
+def test_gmres(name):
+    """test/linsolve.jl:119-285: b = A x; restarted: b = A x + residual; shifted operator."""
+    rng = np.random.default_rng(6)
+    n = 100
+    A = rng.standard_normal((n, n)) / np.sqrt(n) + 3 * np.eye(n)
+    b = rng.standard_normal(n)
+    x, info = ko.linsolve_gmres(A, b, krylovdim=n, maxiter=2, tol=1e-12 * np.linalg.norm(b), orth=ORTHS[name])
+    assert info["converged"] == 1
+    np.testing.assert_allclose(A @ x, b, atol=1e-9)
+    x, info = ko.linsolve_gmres(A, b, krylovdim=12, maxiter=3, tol=1e-14, orth=ORTHS[name])
+    np.testing.assert_allclose(A @ x + info["residual"], b, atol=1e-9)
+    x, info = ko.linsolve_gmres(A, b, krylovdim=20, maxiter=50, tol=1e-10, orth=ORTHS[name], a0=0.7, a1=-1.3)
+    assert info["converged"] == 1
+    np.testing.assert_allclose(0.7 * x - 1.3 * (A @ x), b, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", REORTH)
+def test_svdsolve(name):
+    """test/svdsolve.jl:14,60-63,88-98."""
+    rng = np.random.default_rng(7)
+    m, n = 150, 90
+    A = rng.standard_normal((m, n))
+    ref = np.linalg.svd(A, compute_uv=False)
+    S, Lv, Rv, info = ko.svdsolve_gkl(A, rng.standard_normal(m), 5, "LR", krylovdim=25, maxiter=100,
+                                      tol=1e-10, orth=ORTHS[name])
+    assert info["converged"] >= 5
+    c = len(S)
+    np.testing.assert_allclose(S, ref[:c], rtol=1e-9)
+    U, V = np.column_stack(Lv), np.column_stack(Rv)
+    assert np.abs(U.T @ U - np.eye(c)).max() < 1e-9
+    assert np.abs(V.T @ V - np.eye(c)).max() < 1e-9
+    np.testing.assert_allclose(A.T @ U, V * S, atol=1e-8)
+    Rm = np.column_stack(info["residual"])
+    np.testing.assert_allclose(A @ V, U * S + Rm, atol=1e-8)
+
+
+def test_svdsolve_float32():
+    rng = np.random.default_rng(8)
+    m, n = 400, 64
+    A = (rng.random((m, n)) - 0.5).astype(np.float32)
+    ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    S, Lv, Rv, info = ko.svdsolve_gkl(A, rng.random(m).astype(np.float32), 6, "LR", krylovdim=30,
+                                      maxiter=100, tol=1e-5, orth=ORTHS["cgs2"])
+    assert info["converged"] >= 6
+    np.testing.assert_allclose(S[:6], ref[:6], rtol=5e-5)
+
+
+def test_block_primitives():
+    """test/block.jl:74-183."""
+    rng = np.random.default_rng(9)
+    n, p = 200, 6
+    X = [rng.standard_normal(n) for _ in range(p)]
+    Y = [rng.standard_normal(n) for _ in range(p)]
+    np.testing.assert_allclose(ko.block_inner(X, Y), np.column_stack(X).T @ np.column_stack(Y), atol=1e-12)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, 12)))
+    V = [Q[:, j].copy() for j in range(12)]
+    Rb = ko.block_reorthogonalize([x.copy() for x in X], V)
+    assert np.abs(Q.T @ np.column_stack(Rb)).max() < 1e-12
+    X2 = [x.copy() for x in X]
+    X2[3] = 2 * X2[0] - X2[1]                    # rank deficient
+    X0 = np.column_stack(X2)
+    R, good, drift = ko.block_qr(X2, 1e-10)
+    assert good == [0, 1, 2, 4, 5]
+    Qg = np.column_stack([X2[i] for i in good])
+    np.testing.assert_allclose(Qg @ R, X0, atol=1e-9)
+    assert np.abs(Qg.T @ Qg - np.eye(5)).max() < 1e-12
+
+
+def test_householder_givens_basis_equal_dense():
+    """test/linalg.jl:27-44."""
+    rng = np.random.default_rng(10)
+    n, k = 50, 8
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    b = [Q[:, j].copy() for j in range(k)]
+    x = rng.standard_normal(5)
+    beta, v, nu = ko.householder_vec(x, 2)
+    assert nu > 0 and abs(nu - np.linalg.norm(x)) < 1e-14
+    Hm = np.eye(5) - beta * np.outer(v, v)
+    y = Hm @ x
+    assert abs(y[2] - nu) < 1e-13 and np.abs(np.delete(y, 2)).max() < 1e-13
+    r = [1, 2, 3, 5, 6]
+    ko.householder_rmul_basis(b, beta, v, r)
+    Qd = Q.copy()
+    Qd[:, r] = Q[:, r] @ Hm
+    np.testing.assert_allclose(np.column_stack(b), Qd, atol=1e-13)
+    c, s, rr = ko.givens(3.0, 4.0)
+    assert abs(rr - 5.0) < 1e-14 and abs(c * 3 + s * 4 - 5) < 1e-14 and abs(-s * 3 + c * 4) < 1e-14
+
+
+def test_stencil_spectrum_and_splitmix():
+    A = ko.stencil_matrix(7, 5, 3, coeffs=(6.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0))
+    lam = ko.laplace_eigenvalues(7, 5, 3)
+    np.testing.assert_allclose(np.linalg.eigvalsh(A.toarray()), lam, atol=1e-12)
+    x = ko.splitmix_vector(1, 1000)
+    assert 0 <= x.min() and x.max() < 1 and abs(x.mean() - 0.5) < 0.05
+    assert np.array_equal(ko.splitmix_vector(1, 10, offset=5), ko.splitmix_vector(1, 15)[5:])
