@@ -220,10 +220,10 @@ def run_ours(a):
         # shard whole grid lines: rows [y0*nx, y1*nx)
         y0 = (a.ny * rank) // world
         y1 = (a.ny * (rank + 1)) // world
-        ctx = kk.B200Context((y1 - y0) * a.nx, a.krylovdim + 8, device=local_rank, rank=rank, nranks=world,
+        ctx = kk.B200Context((y1 - y0) * a.nx, a.krylovdim + 2 * HOWMANY + 8, device=local_rank, rank=rank, nranks=world,
                              nccl_uid=uid_bytes, n_global=n, row_offset=y0 * a.nx)
     else:
-        ctx = kk.B200Context(n, a.krylovdim + 8, device=local_rank)
+        ctx = kk.B200Context(n, a.krylovdim + 2 * HOWMANY + 8, device=local_rank)
     lib = ctx.lib
     op = kk.B200CSR.stencil(ctx, a.nx, a.ny)
     x0 = ctx.splitmix(SEED)

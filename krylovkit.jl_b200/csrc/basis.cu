@@ -115,17 +115,21 @@ constexpr int TR_OFF_U = NS * SLOT_BYTES;                 // after the ring
 constexpr int TR_U_BYTES = 232448 - TR_OFF_U - 256;       // bytes available for U
 constexpr int TR_OFF_BAR = TR_OFF_U + TR_U_BYTES;
 constexpr int TR_SMEM = TR_OFF_BAR + 2 * NS * 8;
-constexpr int JB = 8;
+constexpr int TJ = 36;   // output columns accumulated in registers per pass over the resident tile
 
-template <typename T>
+// Consumers: thread <-> row, TJ accumulators per thread; U row-major in shared memory
+// (Us[i*pitch + j]), read as broadcast 128-bit loads: 0.5 LDS per FMA, Q read once per pass.
+template <typename T, bool USM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
     using CF = Cfg<T>;
-    constexpr int R = CF::R, C = CF::C;
+    using V16 = typename CF::V16;
+    constexpr int R = CF::R, C = CF::C, VEC = CF::VEC;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t ring = smem_u32(smem);
     const uint32_t full = smem_u32(smem + TR_OFF_BAR), empty = full + NS * 8;
     T* Us = reinterpret_cast<T*>(smem + TR_OFF_U);
+    const int pitch = ((p.keep + VEC - 1) / VEC) * VEC;
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
             mbar_init(full + 8 * i, 1);
@@ -133,10 +137,10 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
         }
         fence_mbar_init();
     }
-    if (p.u_in_smem)
-        for (int i = threadIdx.x; i < p.m * p.keep; i += blockDim.x) {
-            const int r = i % p.m, c = i / p.m;
-            Us[i] = (T)p.U[(size_t)c * p.ldu + r];
+    if (USM)
+        for (int idx = threadIdx.x; idx < p.m * pitch; idx += blockDim.x) {
+            const int i = idx / pitch, j = idx - i * pitch;
+            Us[idx] = (j < p.keep) ? (T)p.U[(size_t)j * p.ldu + i] : (T)0;
         }
     __syncthreads();
     const int nch = (p.m + C - 1) / C;
@@ -165,15 +169,16 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t r0 = tile * R;
             const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
-            const uint32_t s0 = s, ph0 = ph;
-            for (int c = 0; c < nch; ++c) {   // wait for the whole tile
+            const uint32_t s0 = s;
+            for (int c = 0; c < nch; ++c) {   // the whole row tile must be resident
                 mbar_wait(full + 8 * s, ph);
                 if (++s == NS) { s = 0; ph ^= 1; }
             }
-            for (int jb = 0; jb < p.keep; jb += JB) {
-                T acc[JB];
+            for (int jb = 0; jb < p.keep; jb += TJ) {
+                const int nj = (p.keep - jb) < TJ ? (p.keep - jb) : TJ;
+                T acc[TJ];
 #pragma unroll
-                for (int t = 0; t < JB; ++t) acc[t] = (T)0;
+                for (int t = 0; t < TJ; ++t) acc[t] = (T)0;
                 uint32_t ss = s0;
                 for (int c = 0; c < nch; ++c) {
                     const T* slot = reinterpret_cast<const T*>(smem + ss * SLOT_BYTES);
@@ -181,14 +186,21 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
                     for (int jj = 0; jj < ncol; ++jj) {
                         const T q = slot[jj * R + tid];
                         const int i = c * C + jj;
-                        if (p.u_in_smem) {
+                        if (USM) {
+                            const T* urow = Us + i * pitch + jb;
 #pragma unroll
-                            for (int t = 0; t < JB; ++t)
-                                if (jb + t < p.keep) acc[t] = fma(q, Us[(jb + t) * p.m + i], acc[t]);
+                            for (int t = 0; t < TJ; t += VEC) {
+                                if (t < nj) {
+                                    T u[VEC];
+                                    CF::unpack(*reinterpret_cast<const V16*>(urow + t), u);
+#pragma unroll
+                                    for (int e = 0; e < VEC; ++e) acc[t + e] = fma(q, u[e], acc[t + e]);
+                                }
+                            }
                         } else {
 #pragma unroll
-                            for (int t = 0; t < JB; ++t)
-                                if (jb + t < p.keep)
+                            for (int t = 0; t < TJ; ++t)
+                                if (t < nj)
                                     acc[t] = fma(q, (T)__ldg(p.U + (size_t)(jb + t) * p.ldu + i), acc[t]);
                         }
                     }
@@ -196,8 +208,8 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
                 }
                 if (tid < rt) {
 #pragma unroll
-                    for (int t = 0; t < JB; ++t)
-                        if (jb + t < p.keep) base[(int64_t)cl.c[jb + t] * p.ld + r0 + tid] = acc[t];
+                    for (int t = 0; t < TJ; ++t)
+                        if (t < nj) base[(int64_t)cl.c[jb + t] * p.ld + r0 + tid] = acc[t];
                 }
             }
             // release the tile
@@ -207,7 +219,6 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
                 if (lane == 0) mbar_arrive(empty + 8 * ss);
                 if (++ss == NS) ss = 0;
             }
-            (void)ph0;
         }
     }
 }
@@ -496,8 +507,10 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR((k_phase<float, true, false>), SMEM_BYTES);
     SETATTR(k_gs_fused<double>, SMEM_BYTES);
     SETATTR(k_gs_fused<float>, SMEM_BYTES);
-    SETATTR(k_transform<double>, TR_SMEM);
-    SETATTR(k_transform<float>, TR_SMEM);
+    SETATTR((k_transform<double, true>), TR_SMEM);
+    SETATTR((k_transform<double, false>), TR_SMEM);
+    SETATTR((k_transform<float, true>), TR_SMEM);
+    SETATTR((k_transform<float, false>), TR_SMEM);
 #undef SETATTR
     return B2K_OK;
 }
@@ -713,9 +726,14 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
         // w = A v ; alpha = <v, w>   (one pass)
         B2K_TRY(b2k_enqueue_apply(ctx, op, rv, rw, 0.0, 1.0, false, &rv, S_A0));
         B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_A0, 1, pn.sharded));
-        // alpha must reach the host anyway (it is a returned scalar and enters c2)
-        B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
-        double alpha = ctx->h_res[S_A0];
+        // CGS2 on the fused path keeps alpha on the device (the prologue reads it from d_res) so
+        // that the whole step needs ONE host synchronisation; the other variants fetch it now.
+        const bool defer_alpha = (alg == B2K_CGS2) && fused_ok(ctx, K1, pn.sharded, ctx->dtype);
+        double alpha = 0.0;
+        if (!defer_alpha) {
+            B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+            alpha = ctx->h_res[S_A0];
+        }
         if (alg == B2K_CGS) {
             // w = (w - beta v_prev) - alpha v ; beta = ||w||
             B2K_TRY(b2k_vec_axpy2(ctx, w, cols[k - 1], -beta_old, r, -alpha));
@@ -760,6 +778,7 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
         if (prologue) {                                                                       \
             a.nvec = 3; a.e1 = (const T*)vprev.ptr; a.e2 = (const T*)rv.ptr;                  \
             a.c1 = (T)(-beta_old); a.c2 = (T)(-alpha); a.store_x = 1;                         \
+            if (defer_alpha) a.c2_dev = ctx->d_res + S_A0;                                    \
         }                                                                                     \
         a.part_h = PA;                                                                        \
         PhaseParams<T> c = base_params<T>(pn, K1, rw.ptr, rw.ptr);                            \
@@ -777,7 +796,8 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
                 if (f64) BUILD_AND_LAUNCH(double) else BUILD_AND_LAUNCH(float)
 #undef BUILD_AND_LAUNCH
                 B2K_TRY(enqueue_finalize(ctx, PA, nullptr, PN, grid, K1, S_H, S_N));
-                B2K_TRY(b2k_fetch_results(ctx, S_N + 1, 0));
+                B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+                if (defer_alpha) alpha = ctx->h_res[S_A0];
             } else {
                 if (prologue) B2K_TRY(b2k_vec_axpy2(ctx, w, cols[k - 1], -beta_old, r, -alpha));
                 if (f64) B2K_TRY(cgs_pass_unfused_t<double>(ctx, pn, rw, K1, S_H, S_N));
@@ -860,14 +880,20 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
     TransformParams p;
     p.base = pn.base; p.ld = pn.ld; p.n = pn.n; p.m = m; p.keep = keep; p.ldu = m;
     p.U = ctx->d_coef;
-    p.u_in_smem = ((size_t)m * keep * ctx->esize <= (size_t)TR_U_BYTES) ? 1 : 0;
+    {
+        const int vec = f64 ? 2 : 4;
+        const size_t pitch = (size_t)((keep + vec - 1) / vec) * vec;
+        p.u_in_smem = ((size_t)m * pitch * ctx->esize <= (size_t)TR_U_BYTES) ? 1 : 0;
+    }
     ColList cl;
     for (int i = 0; i < m; ++i) cl.c[i] = pn.idx[i];
     const int pr = b2k_prof_begin(ctx, 2, (double)(m + keep) * ctx->esize * (double)pn.n);
     if (f64) {
-        k_transform<double><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        if (p.u_in_smem) k_transform<double, true><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        else k_transform<double, false><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
     } else {
-        k_transform<float><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        if (p.u_in_smem) k_transform<float, true><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        else k_transform<float, false><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
     }
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);

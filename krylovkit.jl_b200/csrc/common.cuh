@@ -140,8 +140,9 @@ static inline double* b2k_part_set(b2k_ctx* ctx, int set) {
     return ctx->d_part + (size_t)set * B2K_MAX_GRID * B2K_KSTRIDE;
 }
 
-// basis.cu
+// basis.cu / spmv.cu
 int32_t b2k_basis_init(b2k_ctx* ctx);
+int32_t b2k_spmv_init(b2k_ctx* ctx);
 
 // dist (dist.cu)
 int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid);

@@ -100,6 +100,7 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
 #undef CK
     int32_t sp = 0;
     int32_t rc = b2k_basis_init(ctx);
+    if (rc == B2K_OK) rc = b2k_spmv_init(ctx);
     if (rc == B2K_OK) rc = make_space(ctx, n_local, ncols, 1, &sp);
     if (rc != B2K_OK) {
         g_b2k_create_error = ctx->err;

@@ -35,6 +35,7 @@ struct b2k_op {
     int32_t* colidx = nullptr;    // local column index; >= n_loc_cols means halo slot
     void*    vals = nullptr;
     int32_t* rowblk = nullptr;    // CTA row-block boundaries
+    int32_t* pblk = nullptr;      // rowptr[rowblk[b]] (first nonzero of each block)
     int32_t  nblk = 0;
     double*  part = nullptr;      // per-CTA dot partials
     // halo plan (dist)
@@ -130,6 +131,190 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             for (int g = tid; g < (int)gridDim.x; g += SP_BT) v2 += pv[g];
             const double tot = block_sum(v2, red);
             if (tid == 0) *out = tot;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Pipelined CSR-stream SpMV (the default): persistent CTAs (2 per SM), a producer warp
+// streams each row block's nonzeros (vals, colidx) and its rowptr segment into a 3-stage
+// shared-memory ring with 1-D TMA bulk copies (UBLKCP) signalled on mbarriers; the 8
+// consumer warps gather x, multiply in place, and sum rows out of shared memory while the
+// next blocks are already in flight.  Same arithmetic (products rounded, summed in CSR
+// order) as k_spmv_stream, which remains as the reference implementation for tests.
+constexpr int SPP_NSTG = 3;
+constexpr int SPP_RMAX = 1024;            // rowptr entries staged per block
+constexpr int SPP_TV = SP_NNZ + 8;        // staged nonzeros (block + alignment slack)
+constexpr int SPP_CONS = 256;
+constexpr int SPP_THREADS = SPP_CONS + 32;
+template <typename T> struct SppLayout {
+    static constexpr int VAL_BYTES = SPP_TV * (int)sizeof(T);
+    static constexpr int COL_BYTES = SPP_TV * 4;
+    static constexpr int RP_BYTES = (SPP_RMAX + 8) * 4;
+    static constexpr int STAGE = VAL_BYTES + COL_BYTES + RP_BYTES;
+    static constexpr int OFF_BAR = SPP_NSTG * STAGE;
+    static constexpr int OFF_RED = OFF_BAR + 2 * SPP_NSTG * 8 + 16;
+    static constexpr int SMEM = OFF_RED + 32 * 8 + 16;
+};
+
+__global__ void k_pblk(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowblk, int count,
+                       int32_t* __restrict__ pblk) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < count) pblk[b] = rowptr[rowblk[b]];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SPP_THREADS, 2)
+k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+            const T* __restrict__ vals, const T* __restrict__ x, const T* __restrict__ halo,
+            int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk,
+            const int32_t* __restrict__ pblk, int nblk, T a0, T a1, int shifted,
+            const T* __restrict__ xs, const T* __restrict__ dotv, double* __restrict__ part,
+            unsigned* __restrict__ ticket, double* __restrict__ out) {
+    using LY = SppLayout<T>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + SPP_NSTG * 8;
+    double* red = reinterpret_cast<double*>(smem + LY::OFF_RED);
+    int* flag = reinterpret_cast<int*>(smem + LY::OFF_RED + 32 * 8);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SPP_NSTG; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, SPP_CONS / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= SPP_CONS) {
+        // ------------------------------ producer warp ------------------------------
+        int tile = blockIdx.x;
+        int d = 0;   // lanes 0..3 hold r0, r1, p0, p1 of the current tile
+        if (tile < nblk && lane < 4) d = (lane < 2) ? rowblk[tile + lane] : pblk[tile + lane - 2];
+        for (; tile < nblk; tile += gridDim.x) {
+            const int r0 = __shfl_sync(0xffffffffu, d, 0), r1 = __shfl_sync(0xffffffffu, d, 1);
+            const int p0 = __shfl_sync(0xffffffffu, d, 2), p1 = __shfl_sync(0xffffffffu, d, 3);
+            const int nt = tile + gridDim.x;      // prefetch the next descriptor before blocking
+            if (nt < nblk && lane < 4) d = (lane < 2) ? rowblk[nt + lane] : pblk[nt + lane - 2];
+            mbar_wait(empty + 8 * s, ph ^ 1);
+            const int nnzb = p1 - p0, nrows = r1 - r0;
+            if (nnzb <= SP_NNZ) {
+                const int p0a = p0 & ~3, cnt = ((p1 + 3) & ~3) - p0a;
+                const int r0a = r0 & ~3;
+                const int rcnt = (nrows <= SPP_RMAX) ? (((r1 + 1 + 3) & ~3) - r0a) : 0;
+                const uint32_t vb = (uint32_t)cnt * (uint32_t)sizeof(T), cb = (uint32_t)cnt * 4u,
+                               rb = (uint32_t)rcnt * 4u;
+                const uint32_t st = smem_u32(smem + s * LY::STAGE);
+                if (lane == 0) mbar_expect_tx(full + 8 * s, vb + cb + rb);
+                __syncwarp();
+                if (lane == 0 && vb) bulk_g2s(st, vals + p0a, vb, full + 8 * s);
+                if (lane == 1 && cb) bulk_g2s(st + LY::VAL_BYTES, colidx + p0a, cb, full + 8 * s);
+                if (lane == 2 && rb) bulk_g2s(st + LY::VAL_BYTES + LY::COL_BYTES, rowptr + r0a, rb, full + 8 * s);
+            } else {
+                if (lane == 0) mbar_arrive(full + 8 * s);   // long row: consumers read global memory
+            }
+            if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+        }
+        return;
+    }
+    // ---------------------------------- consumers ----------------------------------
+    const int tid = threadIdx.x, w = tid >> 5;
+    T dacc = (T)0;
+    int tile = blockIdx.x;
+    int4 dn = make_int4(0, 0, 0, 0);
+    if (tile < nblk) dn = make_int4(rowblk[tile], rowblk[tile + 1], pblk[tile], pblk[tile + 1]);
+    for (; tile < nblk; tile += gridDim.x) {
+        const int r0 = dn.x, r1 = dn.y, p0 = dn.z, p1 = dn.w;
+        const int nt = tile + gridDim.x;
+        if (nt < nblk) dn = make_int4(rowblk[nt], rowblk[nt + 1], pblk[nt], pblk[nt + 1]);
+        const int nnzb = p1 - p0, nrows = r1 - r0;
+        mbar_wait(full + 8 * s, ph);
+        if (nnzb <= SP_NNZ) {
+            T* vs = reinterpret_cast<T*>(smem + s * LY::STAGE);
+            const int32_t* cs = reinterpret_cast<const int32_t*>(smem + s * LY::STAGE + LY::VAL_BYTES);
+            const int32_t* rs = reinterpret_cast<const int32_t*>(smem + s * LY::STAGE + LY::VAL_BYTES + LY::COL_BYTES);
+            const int p0a = p0 & ~3, r0a = r0 & ~3, off = p0 - p0a;
+            constexpr int U = SP_NNZ / SPP_CONS;
+            T xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = tid + u * SPP_CONS;
+                if (i < nnzb) {
+                    const int32_t cc = cs[off + i];
+                    xv[u] = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = tid + u * SPP_CONS;
+                if (i < nnzb) vs[off + i] *= xv[u];
+            }
+            named_bar_sync(1, SPP_CONS);
+            const bool rp_staged = nrows <= SPP_RMAX;
+            for (int r = r0 + tid; r < r1; r += SPP_CONS) {
+                int a, b;
+                if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
+                else { a = rowptr[r]; b = rowptr[r + 1]; }
+                a -= p0a; b -= p0a;
+                T sum = (T)0;
+                for (int p = a; p < b; ++p) sum += vs[p];
+                if (shifted) sum = fma(a0, xs[r], a1 * sum);
+                y[r] = sum;
+                if (dotv) dacc = fma(dotv[r], sum, dacc);
+            }
+        } else {
+            double acc = 0.0;
+            for (int i = tid; i < nnzb; i += SPP_CONS) {
+                const int32_t cc = colidx[p0 + i];
+                const T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+                acc += (double)(vals[p0 + i] * xv);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) red[w] = acc;
+            named_bar_sync(1, SPP_CONS);
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int i = 0; i < SPP_CONS / 32; ++i) tot += red[i];
+                T sum = (T)tot;
+                if (shifted) sum = fma(a0, xs[r0], a1 * sum);
+                y[r0] = sum;
+                if (dotv) dacc = fma(dotv[r0], sum, dacc);
+            }
+            named_bar_sync(1, SPP_CONS);
+        }
+        fence_proxy_async();   // generic-proxy writes to the stage precede its reuse by the TMA unit
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8 * s);
+        if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+    }
+    if (dotv) {
+        double v = warp_sum((double)dacc);
+        if (lane == 0) red[w] = v;
+        named_bar_sync(1, SPP_CONS);
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < SPP_CONS / 32; ++i) tot += red[i];
+            part[blockIdx.x] = tot;
+            __threadfence();
+            const unsigned t = atomicInc(ticket, gridDim.x - 1);
+            *flag = (t == gridDim.x - 1);
+        }
+        named_bar_sync(1, SPP_CONS);
+        if (*flag) {
+            __threadfence();
+            double v2 = 0.0;
+            const volatile double* pv = part;
+            for (int g = tid; g < (int)gridDim.x; g += SPP_CONS) v2 += pv[g];
+            v2 = warp_sum(v2);
+            named_bar_sync(1, SPP_CONS);
+            if (lane == 0) red[w] = v2;
+            named_bar_sync(1, SPP_CONS);
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int i = 0; i < SPP_CONS / 32; ++i) tot += red[i];
+                *out = tot;
+            }
         }
     }
 }
@@ -309,6 +494,9 @@ int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
                                       cudaMemcpyHostToDevice, ctx->stream));
         B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    B2K_CUDA(ctx, cudaMalloc(&op->pblk, sizeof(int32_t) * (op->nblk + 1)));
+    k_pblk<<<(op->nblk + 1 + 255) / 256, 256, 0, ctx->stream>>>(op->rowptr, op->rowblk, op->nblk + 1, op->pblk);
+    B2K_LAUNCH_CHECK(ctx);
     B2K_CUDA(ctx, cudaMalloc(&op->part, sizeof(double) * std::max(1, op->nblk)));
     return B2K_OK;
 }
@@ -450,9 +638,9 @@ static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_
             return fail(b2k_fail(ctx, B2K_ECUDA, "op_create_csr: %s -> %s", #call,           \
                                  cudaGetErrorString(e__)));                                  \
     } while (0)
-    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_rows + 1)));
-    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * nnz1));
-    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * nnz1));
+    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_rows + 1 + 8)));
+    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * (nnz1 + 8)));
+    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * (nnz1 + 8)));
     CK(cudaMalloc(&d_gcol, sizeof(int64_t) * nnz1));
     CK(cudaMalloc(&d_raw, raw_bytes));
     const int g = ctx->num_sms * 8;
@@ -577,7 +765,7 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
                                  cudaGetErrorString(e__)));                                  \
     } while (0)
     CK(cudaMalloc(&counts, sizeof(int32_t) * (n_loc + 1)));
-    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_loc + 1)));
+    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_loc + 1 + 8)));
     const unsigned blocks = (unsigned)((n_loc + 1 + 255) / 256);
     k_stencil_count<<<blocks, 256, 0, ctx->stream>>>(d, counts);
     ctx->launches++;
@@ -592,8 +780,8 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     op->nnz = h_nnz;
-    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * std::max<int64_t>(1, op->nnz)));
-    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * std::max<int64_t>(1, op->nnz)));
+    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * (std::max<int64_t>(1, op->nnz) + 8)));
+    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * (std::max<int64_t>(1, op->nnz) + 8)));
     CK(cudaMalloc(&d_gcol, sizeof(int64_t) * std::max<int64_t>(1, op->nnz)));
     if (n_loc > 0) {
         if (ctx->dtype == B2K_F64)
@@ -679,6 +867,7 @@ extern "C" int32_t b2k_op_destroy(b2k_ctx* ctx, b2k_op* op) {
     if (op->colidx) cudaFree(op->colidx);
     if (op->vals) cudaFree(op->vals);
     if (op->rowblk) cudaFree(op->rowblk);
+    if (op->pblk) cudaFree(op->pblk);
     if (op->part) cudaFree(op->part);
     if (op->halo) cudaFree(op->halo);
     if (op->xall) cudaFree(op->xall);
@@ -715,6 +904,22 @@ extern "C" int32_t b2k_op_csr_download(b2k_ctx* ctx, const b2k_op* op, int32_t* 
 }
 
 // ------------------------------------------------------------------ apply ----
+
+static bool g_spmv_pipe = true;
+
+extern "C" int32_t b2k_debug_set_spmv_pipe(int32_t on) {
+    g_spmv_pipe = on != 0;
+    return B2K_OK;
+}
+
+// opt in to > 48 KB dynamic shared memory for the pipelined SpMV (called per context)
+int32_t b2k_spmv_init(b2k_ctx* ctx) {
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmv_pipe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<double>::SMEM));
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmv_pipe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<float>::SMEM));
+    return B2K_OK;
+}
 
 int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
                           double a0, double a1, bool shifted, const VecRef* dotv, int dot_slot) {
@@ -764,14 +969,26 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
     double* out = dotv ? ctx->d_res + dot_slot : nullptr;
     const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
                                               2.0 * ctx->esize * op->n_rows);
+    if (g_spmv_pipe) {
+        const int grid = std::min(op->nblk, 2 * ctx->num_sms);
+#define LAUNCH(T)                                                                              \
+    k_spmv_pipe<T><<<grid, SPP_THREADS, SppLayout<T>::SMEM, ctx->stream>>>(                    \
+        op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
+        (T*)y.ptr, op->rowblk, op->pblk, op->nblk, (T)a0, (T)a1, shifted ? 1 : 0,              \
+        (const T*)x.ptr, dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out)
+        if (ctx->dtype == B2K_F64) LAUNCH(double);
+        else LAUNCH(float);
+#undef LAUNCH
+    } else {
 #define LAUNCH(T)                                                                              \
     k_spmv_stream<T><<<op->nblk, SP_BT, 0, ctx->stream>>>(                                     \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
         (T*)y.ptr, op->rowblk, (T)a0, (T)a1, shifted ? 1 : 0, (const T*)x.ptr,                 \
         dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out)
-    if (ctx->dtype == B2K_F64) LAUNCH(double);
-    else LAUNCH(float);
+        if (ctx->dtype == B2K_F64) LAUNCH(double);
+        else LAUNCH(float);
 #undef LAUNCH
+    }
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;

@@ -77,6 +77,7 @@ struct PhaseParams {
     const T* e1;     // prologue vectors (nvec == 3): x' = (x + c1*e1) + c2*e2
     const T* e2;
     T c1, c2;
+    const double* c2_dev;   // if set: c2 = -(*c2_dev), a device scalar produced by the previous kernel
     int32_t nvec;    // 1 or 3
     int32_t store_x; // write x'' (UPDATE) or x' (prologue write-back) to xout
     // UPDATE: x'' = betax*x' + sum_j Q[:,j]*cs[j],  cs[j] = alphac * sum_g coef[g*stride+j]
@@ -225,6 +226,8 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
         for (int cc = 0; cc < CPW; ++cc) acc_h[c][cc] = (T)0;
     T nrm = (T)0;
     int buf = 0;
+    T c2 = p.c2;
+    if (p.c2_dev) c2 = (T)(-(*reinterpret_cast<const volatile double*>(p.c2_dev)));
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * R;
@@ -234,7 +237,7 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
         T xv = wv[tid];
         if (p.nvec == 3) {
             xv = fma(p.c1, wv[R + tid], xv);
-            xv = fma(p.c2, wv[2 * R + tid], xv);
+            xv = fma(c2, wv[2 * R + tid], xv);
         }
         if (tid >= rt) xv = (T)0;
         T acc = xv;

@@ -42,7 +42,7 @@ def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None):
     x0 = np.asarray(x0)
     n = x0.shape[0]
     dtype = np.float32 if x0.dtype == np.float32 else np.float64
-    ctx = B200Context(n, alg.krylovdim + 8, dtype=dtype)
+    ctx = B200Context(n, alg.krylovdim + 2 * howmany + 8, dtype=dtype)
     try:
         if sp.issparse(A):
             op = B200CSR.from_scipy(ctx, A)
@@ -52,17 +52,21 @@ def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None):
         else:
             raise TypeError("eigsolve: host-side A must be a scipy sparse matrix or a CSR triple")
         xv = ctx.from_host(x0)
-        vals, vecs, info = _eigsolve_lanczos(op, xv, howmany, which, alg)
-        # out_vectors: optional preallocated (e.g. pinned) host arrays for the Ritz vectors
-        vecs_h = [v.to_host(out_vectors[i] if out_vectors is not None and i < len(out_vectors) else None)
-                  for i, v in enumerate(vecs)]
-        info.residual = None      # residual vectors stay on the device in the host-buffer path
+        vecs_h = []
+
+        def sink(i, v):
+            # out_vectors: optional preallocated (e.g. pinned) host arrays for the Ritz vectors;
+            # each Ritz vector is downloaded and its slab column released before the next one
+            vecs_h.append(v.to_host(out_vectors[i] if out_vectors is not None and i < len(out_vectors)
+                                    else None))
+
+        vals, _, info = _eigsolve_lanczos(op, xv, howmany, which, alg, sink)
         return vals, vecs_h, info
     finally:
         ctx.close()
 
 
-def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos):
+def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, sink=None):
     krylovdim, maxiter = alg.krylovdim, alg.maxiter
     if howmany > krylovdim:
         raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} eigenvalues")
@@ -132,9 +136,16 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos):
         hm = len(D)
     values = D[:hm].copy()
     B = fact.basis()
-    vectors = [B * U[:, i] for i in range(hm)]
-    r = fact.residual()
-    residuals = [r.scale(U[-1, i]) for i in range(hm)]
+    if sink is None:
+        vectors = [B * U[:, i] for i in range(hm)]
+        r = fact.residual()
+        residuals = [r.scale(U[-1, i]) for i in range(hm)]
+    else:       # host-buffer path: stream the Ritz vectors out one at a time
+        vectors, residuals = None, None
+        for i in range(hm):
+            v = B * U[:, i]
+            sink(i, v)
+            v.free()
     normres = np.abs(f[:hm])
     if converged < howmany and alg.verbosity >= WARN_LEVEL:
         warnings.warn(f"Lanczos eigsolve stopped without convergence after {numiter} iterations: "

@@ -27,9 +27,9 @@ def svdsolve(A, u0, howmany: int = 1, which: str = "LR", alg: GKL | None = None,
     A = np.asarray(A)
     u0 = np.asarray(u0)
     m, n = A.shape
-    ctx = B200Context(m, alg.krylovdim + 8, dtype=A.dtype if A.dtype == np.float32 else np.float64)
+    ctx = B200Context(m, alg.krylovdim + 2 * howmany + 8, dtype=A.dtype if A.dtype == np.float32 else np.float64)
     try:
-        sv = ctx.add_space(n, alg.krylovdim + 8, sharded=False)
+        sv = ctx.add_space(n, alg.krylovdim + howmany + 8, sharded=False)
         op = B200Dense.from_host(ctx, A, sv)
         S, Uv, Vv, info = _svdsolve_gkl(op, ctx.from_host(u0), howmany, which, alg)
         info.residual = [r.to_host() for r in info.residual]

@@ -70,8 +70,15 @@ def test_splitmix_matches_host():
     ctx.close()
 
 
-@pytest.mark.parametrize("nx,ny", [(100, 100), (125, 80), (1, 7), (2048, 3), (37, 1)])
-def test_spmv_stencil_and_csr(nx, ny):
+@pytest.fixture(params=[1, 0], ids=["pipe", "stream"])
+def spmv_kernel(request):
+    L.load().b2k_debug_set_spmv_pipe(request.param)
+    yield request.param
+    L.load().b2k_debug_set_spmv_pipe(1)
+
+
+@pytest.mark.parametrize("nx,ny", [(100, 100), (125, 80), (1, 7), (2048, 3), (37, 1), (1000, 700)])
+def test_spmv_stencil_and_csr(nx, ny, spmv_kernel):
     n = nx * ny
     A = laplace2d(nx, ny)
     ctx = kk.B200Context(n, 8)
@@ -99,12 +106,14 @@ def test_spmv_stencil_and_csr(nx, ny):
     ctx.close()
 
 
-def test_spmv_irregular_rows_and_csc():
+def test_spmv_irregular_rows_and_csc(spmv_kernel):
     rng = np.random.default_rng(5)
     n = 3000
     A = sp.random(n, n, density=0.002, random_state=7, format="lil")
     A[17, :] = rng.standard_normal(n)          # one long row (> 2048 nnz)
     A[100:140, :] = 0                            # empty rows
+    A[2000:, :] = 0                              # a long run of empty rows (> rowptr staging)
+    A[2500, 3] = 1.5
     A = A.tocsr()
     A.sort_indices()
     ctx = kk.B200Context(n, 6)

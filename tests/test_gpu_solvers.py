@@ -100,7 +100,7 @@ def test_eigsolve_config1_matches_oracle_and_closed_form(pair, which):
     lam = ko.laplace_eigenvalues(nx, ny)
     x0 = ko.splitmix_vector(SEED, n)
     alg = kk.Lanczos(orth=orth, krylovdim=30, maxiter=300, tol=1e-10, verbosity=0)
-    ctx = kk.B200Context(n, 40)
+    ctx = kk.B200Context(n, 48)
     op = kk.B200CSR.stencil(ctx, nx, ny)
     vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0), 4, which, alg)
     ovals, ovecs, oinfo = ko.eigsolve_lanczos(A, x0, 4, which, krylovdim=30, maxiter=300, tol=1e-10,
@@ -124,7 +124,7 @@ def test_eigsolve_unconverged_fixed_cycles_matches_oracle():
     n = nx * ny
     A = ko.stencil_matrix(nx, ny)
     x0 = ko.splitmix_vector(SEED, n)
-    ctx = kk.B200Context(n, 70)
+    ctx = kk.B200Context(n, 80)
     op = kk.B200CSR.stencil(ctx, nx, ny)
     alg = kk.Lanczos(orth=kk.cgs2, krylovdim=60, maxiter=3, tol=1e-14, verbosity=0)
     vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0), 4, "SR", alg)
@@ -226,8 +226,8 @@ def test_svdsolve_config4_small_f32():
     A = ko.dense_splitmix(SEED, m, n)
     u0 = ko.splitmix_vector(SEED + 1, m, dtype=np.float32)
     alg = kk.GKL(orth=kk.cgs2, krylovdim=30, maxiter=100, tol=1e-5, verbosity=0)
-    ctx = kk.B200Context(m, 40, dtype=np.float32)
-    sv = ctx.add_space(n, 40, sharded=False)
+    ctx = kk.B200Context(m, 56, dtype=np.float32)
+    sv = ctx.add_space(n, 48, sharded=False)
     op = kk.B200Dense.splitmix(ctx, m, n, SEED, sv)
     S, Lv, Rv, info = kk.svdsolve(op, ctx.from_host(u0), 6, "LR", alg)
     ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
