@@ -61,10 +61,16 @@ def lmul_householder(H: Householder, A, cols=None):
     """lmul!(H, A[, cols]) — dense/reflector.jl:85-106."""
     if H.beta == 0:
         return A
-    cols = range(A.shape[1]) if cols is None else cols
-    for k in cols:
-        mu = H.beta * float(np.dot(H.v, A[H.r, k]))
-        A[H.r, k] -= mu * H.v
+    cols = slice(None) if cols is None else (slice(cols.start, cols.stop) if isinstance(cols, range) else cols)
+    r = H.r
+    if r == list(range(r[0], r[0] + len(r))):      # contiguous index range -> views, no gather
+        sub = A[r[0]:r[0] + len(r), cols]
+        mu = H.beta * (H.v @ sub)                  # one μ per column (reflector.jl:93-99)
+        sub -= np.outer(H.v, mu)
+    else:
+        sub = A[np.ix_(r, np.arange(A.shape[1])[cols])]
+        mu = H.beta * (H.v @ sub)
+        A[np.ix_(r, np.arange(A.shape[1])[cols])] = sub - np.outer(H.v, mu)
     return A
 
 
