@@ -115,12 +115,13 @@ constexpr int TR_OFF_U = NS * SLOT_BYTES;                 // after the ring
 constexpr int TR_U_BYTES = 232448 - TR_OFF_U - 256;       // bytes available for U
 constexpr int TR_OFF_BAR = TR_OFF_U + TR_U_BYTES;
 constexpr int TR_SMEM = TR_OFF_BAR + 2 * NS * 8;
-constexpr int TJ = 36;   // output columns accumulated in registers per pass over the resident tile
+constexpr int TJ = 36;
+constexpr int TR_THREADS = NCONS + 32;   // 8 consumer warps + ONE producer warp (compute-bound kernel)   // output columns accumulated in registers per pass over the resident tile
 
 // Consumers: thread <-> row, TJ accumulators per thread; U row-major in shared memory
 // (Us[i*pitch + j]), read as broadcast 128-bit loads: 0.5 LDS per FMA, Q read once per pass.
 template <typename T, bool USM>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(TR_THREADS, 1)
 k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
     using CF = Cfg<T>;
     using V16 = typename CF::V16;
@@ -174,43 +175,59 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
                 mbar_wait(full + 8 * s, ph);
                 if (++s == NS) { s = 0; ph ^= 1; }
             }
-            for (int jb = 0; jb < p.keep; jb += TJ) {
-                const int nj = (p.keep - jb) < TJ ? (p.keep - jb) : TJ;
-                T acc[TJ];
+            // thread -> two rows (rp, rp + R/2) x one half of the TJ outputs of this pass: each
+            // U value fetched from shared memory feeds two FMAs (22 instead of 38 smem
+            // wavefronts per basis vector and warp)
+            constexpr int TJT = (sizeof(T) == 8) ? TJ : 40;   // outputs per pass; TJT/2 % VEC == 0
+            constexpr int TH = TJT / 2;
+            static_assert(TH % VEC == 0, "half-pass width must keep the 128-bit U loads aligned");
+            const int half = tid >> 7, rp = tid & 127;
+            for (int jb = 0; jb < p.keep; jb += TJT) {
+                const int nj = (p.keep - jb) < TJT ? (p.keep - jb) : TJT;
+                const int njh = nj - half * TH;          // valid outputs of my half (may be <= 0)
+                T acc0[TH], acc1[TH];
 #pragma unroll
-                for (int t = 0; t < TJ; ++t) acc[t] = (T)0;
+                for (int t = 0; t < TH; ++t) { acc0[t] = (T)0; acc1[t] = (T)0; }
                 uint32_t ss = s0;
                 for (int c = 0; c < nch; ++c) {
                     const T* slot = reinterpret_cast<const T*>(smem + ss * SLOT_BYTES);
                     const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
                     for (int jj = 0; jj < ncol; ++jj) {
-                        const T q = slot[jj * R + tid];
+                        const T q0 = slot[jj * R + rp], q1 = slot[jj * R + rp + R / 2];
                         const int i = c * C + jj;
                         if (USM) {
-                            const T* urow = Us + i * pitch + jb;
+                            const T* urow = Us + i * pitch + jb + half * TH;
 #pragma unroll
-                            for (int t = 0; t < TJ; t += VEC) {
-                                if (t < nj) {
+                            for (int t = 0; t < TH; t += VEC) {
+                                if (t < njh) {
                                     T u[VEC];
                                     CF::unpack(*reinterpret_cast<const V16*>(urow + t), u);
 #pragma unroll
-                                    for (int e = 0; e < VEC; ++e) acc[t + e] = fma(q, u[e], acc[t + e]);
+                                    for (int e = 0; e < VEC; ++e) {
+                                        acc0[t + e] = fma(q0, u[e], acc0[t + e]);
+                                        acc1[t + e] = fma(q1, u[e], acc1[t + e]);
+                                    }
                                 }
                             }
                         } else {
 #pragma unroll
-                            for (int t = 0; t < TJ; ++t)
-                                if (t < nj)
-                                    acc[t] = fma(q, (T)__ldg(p.U + (size_t)(jb + t) * p.ldu + i), acc[t]);
+                            for (int t = 0; t < TH; ++t)
+                                if (t < njh) {
+                                    const T u = (T)__ldg(p.U + (size_t)(jb + half * TH + t) * p.ldu + i);
+                                    acc0[t] = fma(q0, u, acc0[t]);
+                                    acc1[t] = fma(q1, u, acc1[t]);
+                                }
                         }
                     }
                     if (++ss == NS) ss = 0;
                 }
-                if (tid < rt) {
 #pragma unroll
-                    for (int t = 0; t < TJ; ++t)
-                        if (t < nj) base[(int64_t)cl.c[jb + t] * p.ld + r0 + tid] = acc[t];
-                }
+                for (int t = 0; t < TH; ++t)
+                    if (t < njh) {
+                        T* col = base + (int64_t)cl.c[jb + half * TH + t] * p.ld + r0;
+                        if (rp < rt) col[rp] = acc0[t];
+                        if (rp + R / 2 < rt) col[rp + R / 2] = acc1[t];
+                    }
             }
             // release the tile
             uint32_t ss = s0;
@@ -889,11 +906,11 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
     for (int i = 0; i < m; ++i) cl.c[i] = pn.idx[i];
     const int pr = b2k_prof_begin(ctx, 2, (double)(m + keep) * ctx->esize * (double)pn.n);
     if (f64) {
-        if (p.u_in_smem) k_transform<double, true><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
-        else k_transform<double, false><<<grid_for_rows<double>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        if (p.u_in_smem) k_transform<double, true><<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        else k_transform<double, false><<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
     } else {
-        if (p.u_in_smem) k_transform<float, true><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
-        else k_transform<float, false><<<grid_for_rows<float>(ctx, pn.n), NTHREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        if (p.u_in_smem) k_transform<float, true><<<grid_for_rows<float>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
+        else k_transform<float, false><<<grid_for_rows<float>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
     }
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);

@@ -7,8 +7,8 @@
 // async copies (TMA, cp.async.bulk -> SASS UBLKCP) in flight per SM without spending
 // registers on it.
 //
-//   * one persistent CTA per SM (grid = min(#SM, #row tiles)), 288 threads:
-//     warps 0-7 = consumers, warp 8 = producer;
+//   * one persistent CTA per SM (grid = min(#SM, #row tiles)), 384 threads:
+//     warps 0-7 = consumers, warps 8-11 = producers (chunk g -> producer g % 4);
 //   * a row tile is R = 256 rows; a ring slot holds R rows x C columns (16 KB:
 //     C = 8 for f64, 16 for f32); NS = 12 slots form the ring, each with a full/empty
 //     mbarrier pair; the producer's lanes issue one 1-D bulk copy per column (2 KB f64),
@@ -45,9 +45,12 @@ template <> struct Cfg<float> {
 constexpr int NS = 12;         // ring slots
 constexpr int NW = 3;          // w slots
 constexpr int NCONS = 256;     // consumer threads
-constexpr int NTHREADS = 288;  // + producer warp
+constexpr int NPROD = 4;        // producer warps: the TMA issue rate of ONE warp (~110 cycles per
+                               // 2 KB bulk copy) caps a CTA at ~19 B/clk, i.e. 5.4 TB/s chip-wide (ncu, r01)
+constexpr int NTHREADS = NCONS + 32 * NPROD;
 constexpr int MAXCH = 16;      // chunks per pass  -> KCAP = MAXCH * C columns per pass
 constexpr int SLOT_BYTES = 16384;
+static_assert(NS % NPROD == 0, "a ring slot must always be refilled by the same producer warp");
 
 template <typename T> constexpr int kcap() { return MAXCH * Cfg<T>::C; }
 
@@ -94,6 +97,7 @@ struct PhaseParams {
 
 struct Pipe {
     uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+    uint32_t g = 0;   // running chunk counter (producers: chunk g belongs to producer warp g % NPROD)
 };
 
 struct SmemView {
@@ -138,33 +142,40 @@ __device__ __forceinline__ void producer_phase(const PhaseParams<T>& p, const Co
     using CF = Cfg<T>;
     constexpr int R = CF::R, C = CF::C;
     const int lane = threadIdx.x & 31;
+    const uint32_t me = (threadIdx.x - NCONS) >> 5;     // producer warp index
     const int nch = (p.k + C - 1) / C;
     const int64_t ntiles = (p.n + R - 1) / R;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * R;
         const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
         const uint32_t bytes = (uint32_t)((rt * sizeof(T) + 15) & ~(size_t)15);
-        // the vector tile (+ prologue vectors)
-        mbar_wait(sm.wempty + 8 * st.ws, st.wph ^ 1);
-        if (lane == 0) mbar_expect_tx(sm.wfull + 8 * st.ws, bytes * (uint32_t)p.nvec);
-        __syncwarp();
-        if (lane < p.nvec) {
-            const T* src = (lane == 0) ? p.x : (lane == 1 ? p.e1 : p.e2);
-            bulk_g2s(sm.wring + st.ws * (3 * R * (int)sizeof(T)) + lane * R * (int)sizeof(T),
-                     src + r0, bytes, sm.wfull + 8 * st.ws);
+        // the vector tile (+ prologue vectors): producer warp 0
+        if (me == 0) {
+            mbar_wait(sm.wempty + 8 * st.ws, st.wph ^ 1);
+            if (lane == 0) mbar_expect_tx(sm.wfull + 8 * st.ws, bytes * (uint32_t)p.nvec);
+            __syncwarp();
+            if (lane < p.nvec) {
+                const T* src = (lane == 0) ? p.x : (lane == 1 ? p.e1 : p.e2);
+                bulk_g2s(sm.wring + st.ws * (3 * R * (int)sizeof(T)) + lane * R * (int)sizeof(T),
+                         src + r0, bytes, sm.wfull + 8 * st.ws);
+            }
         }
         if (++st.ws == NW) { st.ws = 0; st.wph ^= 1; }
-        // the panel tile, C columns per slot
+        // the panel tile, C columns per slot; chunk g is issued by producer warp g % NPROD
+        // (NS % NPROD == 0, so a slot is always refilled by the same warp)
         for (int c = 0; c < nch; ++c) {
-            mbar_wait(sm.empty + 8 * st.s, st.ph ^ 1);
-            const int ncol = (p.k - c * C) < C ? (p.k - c * C) : C;
-            if (lane == 0) mbar_expect_tx(sm.full + 8 * st.s, bytes * (uint32_t)ncol);
-            __syncwarp();
-            if (lane < ncol) {
-                const T* src = p.base + (int64_t)cl.c[c * C + lane] * p.ld + r0;
-                bulk_g2s(sm.ring + st.s * SLOT_BYTES + lane * R * (int)sizeof(T), src, bytes,
-                         sm.full + 8 * st.s);
+            if ((st.g % NPROD) == me) {
+                mbar_wait(sm.empty + 8 * st.s, st.ph ^ 1);
+                const int ncol = (p.k - c * C) < C ? (p.k - c * C) : C;
+                if (lane == 0) mbar_expect_tx(sm.full + 8 * st.s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol) {
+                    const T* src = p.base + (int64_t)cl.c[c * C + lane] * p.ld + r0;
+                    bulk_g2s(sm.ring + st.s * SLOT_BYTES + lane * R * (int)sizeof(T), src, bytes,
+                             sm.full + 8 * st.s);
+                }
             }
+            ++st.g;
             if (++st.s == NS) { st.s = 0; st.ph ^= 1; }
         }
     }
