@@ -106,6 +106,9 @@ int32_t b2k_timer_stop(b2k_ctx* ctx, double* ms);
 int32_t b2k_pinned_alloc(size_t bytes, void** out);
 int32_t b2k_pinned_free(void* p);
 int32_t b2k_device_sync(void);
+/* Device memory is drawn from the CUDA stream-ordered pool and kept for reuse (context and
+ * operator creation become O(us) after first use); this returns the cached memory. */
+int32_t b2k_cache_release(void);
 
 /* ------------------------------------------------- vectors (VectorInterface) ---- */
 /* zerovector / similar: src/innerproductvec.jl:82-137 is the reference's own list of

@@ -61,6 +61,7 @@ _PROTOS = {
     "b2k_pinned_alloc": (C.c_int32, [C.c_size_t, P(C.c_void_p)]),
     "b2k_pinned_free": (C.c_int32, [C.c_void_p]),
     "b2k_device_sync": (C.c_int32, []),
+    "b2k_cache_release": (C.c_int32, []),
     "b2k_vec_alloc": (C.c_int32, [c_ctx, C.c_int32, P(c_vec)]),
     "b2k_vec_alloc_range": (C.c_int32, [c_ctx, C.c_int32, C.c_int32, P(c_vec)]),
     "b2k_vec_free": (C.c_int32, [c_ctx, c_vec]),

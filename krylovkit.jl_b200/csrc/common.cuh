@@ -48,6 +48,7 @@ struct b2k_ctx {
     int32_t num_sms = 0;
     cudaStream_t stream = nullptr;
     std::vector<B2kSpace> spaces;
+    std::vector<b2k_op*> ops;   // operators created on this context (destroyed with it)
 
     // scratch
     double*   d_part   = nullptr;   // partial sums: 4 sets x B2K_MAX_GRID x B2K_KSTRIDE doubles
@@ -131,6 +132,18 @@ int32_t b2k_put_coef(b2k_ctx* ctx, const double* host, int32_t count, int32_t of
 int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t slot,
                      int32_t** dptr);
 
+// Device memory comes from the CUDA stream-ordered pool with an unbounded release
+// threshold: cudaMalloc/cudaFree of multi-GB slabs cost 30-600 ms per solve in the
+// host-buffer path (tools/e2e_breakdown.py); the pool makes context/operator
+// creation and destruction O(microseconds) after the first use.
+cudaError_t b2k_dmalloc(void** p, size_t bytes, cudaStream_t stream);
+cudaError_t b2k_dfree(void* p, cudaStream_t stream);
+#define B2K_DMALLOC(p, bytes) b2k_dmalloc((void**)(p), (bytes), ctx->stream)
+#define B2K_DFREE(p) b2k_dfree((p), ctx->stream)
+// small cache of page-locked host scratch buffers (cudaHostAlloc is ~1 ms per call)
+cudaError_t b2k_hmalloc(void** p, size_t bytes);
+void b2k_hfree(void* p, size_t bytes);
+
 // profiling (ctx.cu): returns a record index (or -1 when profiling is off)
 int  b2k_prof_begin(b2k_ctx* ctx, int cls, double bytes);
 void b2k_prof_end(b2k_ctx* ctx, int idx);
@@ -139,6 +152,9 @@ void b2k_prof_end(b2k_ctx* ctx, int idx);
 static inline double* b2k_part_set(b2k_ctx* ctx, int set) {
     return ctx->d_part + (size_t)set * B2K_MAX_GRID * B2K_KSTRIDE;
 }
+
+// spmv.cu: free the device arrays of an operator (called by b2k_op_destroy / b2k_ctx_destroy)
+void b2k_op_release(b2k_ctx* ctx, b2k_op* op);
 
 // basis.cu / spmv.cu
 int32_t b2k_basis_init(b2k_ctx* ctx);

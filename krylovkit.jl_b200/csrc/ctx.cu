@@ -4,6 +4,77 @@
 
 std::string g_b2k_create_error;
 
+// ------------------------------------------------------------------ memory ----
+#include <mutex>
+static std::mutex g_mem_mutex;
+static bool g_pool_configured[64] = {false};
+struct HostBlock { void* p; size_t bytes; };
+static std::vector<HostBlock> g_host_cache;
+
+cudaError_t b2k_dmalloc(void** p, size_t bytes, cudaStream_t stream) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mutex);
+        if (dev < 64 && !g_pool_configured[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            g_pool_configured[dev] = true;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, stream);
+    if (e != cudaSuccess) {   // return cached blocks to the driver and retry once
+        cudaGetLastError();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        e = cudaMallocAsync(p, bytes ? bytes : 1, stream);
+    }
+    return e;
+}
+
+cudaError_t b2k_dfree(void* p, cudaStream_t stream) {
+    if (!p) return cudaSuccess;
+    return cudaFreeAsync(p, stream);
+}
+
+cudaError_t b2k_hmalloc(void** p, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mutex);
+        for (size_t i = 0; i < g_host_cache.size(); ++i)
+            if (g_host_cache[i].bytes == bytes) {
+                *p = g_host_cache[i].p;
+                g_host_cache.erase(g_host_cache.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+}
+
+void b2k_hfree(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mem_mutex);
+    if (g_host_cache.size() < 64) g_host_cache.push_back({p, bytes});
+    else cudaFreeHost(p);
+}
+
+extern "C" int32_t b2k_cache_release(void) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    cudaDeviceSynchronize();
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    std::lock_guard<std::mutex> lk(g_mem_mutex);
+    for (auto& b : g_host_cache) cudaFreeHost(b.p);
+    g_host_cache.clear();
+    return B2K_OK;
+}
+
 int32_t b2k_fail(b2k_ctx* ctx, int32_t code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -36,9 +107,9 @@ static int32_t make_space(b2k_ctx* ctx, int64_t n_local, int32_t ncols, int32_t 
     s.sharded = sharded;
     s.used.assign(ncols, 0);
     size_t bytes = (size_t)s.ld * ncols * ctx->esize;
-    cudaError_t e = cudaMalloc(&s.base, bytes);
+    cudaError_t e = B2K_DMALLOC(&s.base, bytes);
     if (e != cudaSuccess)
-        return b2k_fail(ctx, B2K_ENOMEM, "cudaMalloc(%zu bytes) for slab failed: %s", bytes,
+        return b2k_fail(ctx, B2K_ENOMEM, "B2K_DMALLOC(%zu bytes) for slab failed: %s", bytes,
                         cudaGetErrorString(e));
     // zero the slab once: the ld-padding rows are read (never written) by the bulk copies
     B2K_CUDA(ctx, cudaMemsetAsync(s.base, 0, bytes, ctx->stream));
@@ -84,15 +155,15 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
                         "sm_100a only\n", prop.name, prop.major, prop.minor);
     ctx->num_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&ctx->d_part, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE));
-    CK(cudaMalloc(&ctx->d_part_s, sizeof(double) * (1 << 20)));
-    CK(cudaMalloc(&ctx->d_res, sizeof(double) * B2K_RES_DOUBLES));
-    CK(cudaHostAlloc(&ctx->h_res, sizeof(double) * B2K_RES_DOUBLES, cudaHostAllocDefault));
-    CK(cudaMalloc(&ctx->d_coef, sizeof(double) * B2K_COEF_DOUBLES));
-    CK(cudaHostAlloc(&ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES, cudaHostAllocDefault));
-    CK(cudaMalloc(&ctx->d_cols, sizeof(int32_t) * 4 * 4096));
-    CK(cudaHostAlloc(&ctx->h_cols, sizeof(int32_t) * 4 * 4096, cudaHostAllocDefault));
-    CK(cudaMalloc(&ctx->d_sync, sizeof(unsigned) * 64));
+    CK(B2K_DMALLOC(&ctx->d_part, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE));
+    CK(B2K_DMALLOC(&ctx->d_part_s, sizeof(double) * (1 << 20)));
+    CK(B2K_DMALLOC(&ctx->d_res, sizeof(double) * B2K_RES_DOUBLES));
+    CK(b2k_hmalloc((void**)&ctx->h_res, sizeof(double) * B2K_RES_DOUBLES));
+    CK(B2K_DMALLOC(&ctx->d_coef, sizeof(double) * B2K_COEF_DOUBLES));
+    CK(b2k_hmalloc((void**)&ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES));
+    CK(B2K_DMALLOC(&ctx->d_cols, sizeof(int32_t) * 4 * 4096));
+    CK(b2k_hmalloc((void**)&ctx->h_cols, sizeof(int32_t) * 4 * 4096));
+    CK(B2K_DMALLOC(&ctx->d_sync, sizeof(unsigned) * 64));
     CK(cudaMemsetAsync(ctx->d_sync, 0, sizeof(unsigned) * 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_part, 0, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE,
                        ctx->stream));
@@ -146,21 +217,28 @@ extern "C" int32_t b2k_ctx_destroy(b2k_ctx* ctx) {
     if (!ctx) return B2K_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (b2k_op* op : ctx->ops) b2k_op_release(ctx, op);
+    ctx->ops.clear();
     b2k_nccl_destroy(ctx);
     for (auto& s : ctx->spaces)
-        if (s.base) cudaFree(s.base);
-    if (ctx->d_part) cudaFree(ctx->d_part);
-    if (ctx->d_part_s) cudaFree(ctx->d_part_s);
-    if (ctx->d_res) cudaFree(ctx->d_res);
-    if (ctx->h_res) cudaFreeHost(ctx->h_res);
-    if (ctx->d_coef) cudaFree(ctx->d_coef);
-    if (ctx->h_coef) cudaFreeHost(ctx->h_coef);
-    if (ctx->d_cols) cudaFree(ctx->d_cols);
-    if (ctx->h_cols) cudaFreeHost(ctx->h_cols);
-    if (ctx->d_sync) cudaFree(ctx->d_sync);
+        if (s.base) B2K_DFREE(s.base);
+    if (ctx->d_part) B2K_DFREE(ctx->d_part);
+    if (ctx->d_part_s) B2K_DFREE(ctx->d_part_s);
+    if (ctx->d_res) B2K_DFREE(ctx->d_res);
+    b2k_hfree(ctx->h_res, sizeof(double) * B2K_RES_DOUBLES);
+    if (ctx->d_coef) B2K_DFREE(ctx->d_coef);
+    b2k_hfree(ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES);
+    if (ctx->d_cols) B2K_DFREE(ctx->d_cols);
+    b2k_hfree(ctx->h_cols, sizeof(int32_t) * 4 * 4096);
+    if (ctx->d_sync) B2K_DFREE(ctx->d_sync);
     if (ctx->ev_coef) cudaEventDestroy(ctx->ev_coef);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
     delete ctx;
     return B2K_OK;
 }

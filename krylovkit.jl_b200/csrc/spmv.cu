@@ -463,7 +463,7 @@ int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
     const int64_t n = op->n_rows;
     int* d_stats;
     int h_stats[2] = {0, 0};
-    B2K_CUDA(ctx, cudaMalloc(&d_stats, 2 * sizeof(int)));
+    B2K_CUDA(ctx, B2K_DMALLOC(&d_stats, 2 * sizeof(int)));
     B2K_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(int), ctx->stream));
     if (n > 0) {
         k_rowptr_stats<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(op->rowptr, n, d_stats);
@@ -471,13 +471,13 @@ int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
     }
     B2K_CUDA(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
     B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_stats);
+    B2K_DFREE(d_stats);
     if (h_stats[1] != 0) return b2k_fail(ctx, B2K_EINVAL, "CSR: rowptr is not non-decreasing");
     const int maxrow = h_stats[0];
     if (maxrow <= SP_NNZ / 2) {
         const int T = SP_NNZ - maxrow + 1;
         op->nblk = (int32_t)std::max<int64_t>(1, (op->nnz + T - 1) / T);
-        B2K_CUDA(ctx, cudaMalloc(&op->rowblk, sizeof(int32_t) * (op->nblk + 1)));
+        B2K_CUDA(ctx, B2K_DMALLOC(&op->rowblk, sizeof(int32_t) * (op->nblk + 1)));
         k_rowblocks<<<(op->nblk + 1 + 255) / 256, 256, 0, ctx->stream>>>(op->rowptr, n, T, op->nblk,
                                                                         op->rowblk);
         B2K_LAUNCH_CHECK(ctx);
@@ -489,15 +489,15 @@ int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
         B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         build_rowblocks(h_rowptr.data(), n, &blk);
         op->nblk = (int32_t)blk.size() - 1;
-        B2K_CUDA(ctx, cudaMalloc(&op->rowblk, sizeof(int32_t) * blk.size()));
+        B2K_CUDA(ctx, B2K_DMALLOC(&op->rowblk, sizeof(int32_t) * blk.size()));
         B2K_CUDA(ctx, cudaMemcpyAsync(op->rowblk, blk.data(), sizeof(int32_t) * blk.size(),
                                       cudaMemcpyHostToDevice, ctx->stream));
         B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    B2K_CUDA(ctx, cudaMalloc(&op->pblk, sizeof(int32_t) * (op->nblk + 1)));
+    B2K_CUDA(ctx, B2K_DMALLOC(&op->pblk, sizeof(int32_t) * (op->nblk + 1)));
     k_pblk<<<(op->nblk + 1 + 255) / 256, 256, 0, ctx->stream>>>(op->rowptr, op->rowblk, op->nblk + 1, op->pblk);
     B2K_LAUNCH_CHECK(ctx);
-    B2K_CUDA(ctx, cudaMalloc(&op->part, sizeof(double) * std::max(1, op->nblk)));
+    B2K_CUDA(ctx, B2K_DMALLOC(&op->part, sizeof(double) * std::max(1, op->nblk)));
     return B2K_OK;
 }
 
@@ -524,7 +524,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
     op->gather_all = 0;
     if (ctx->nranks == 1) return B2K_OK;
     unsigned long long* d_mm;
-    B2K_CUDA(ctx, cudaMalloc(&d_mm, 2 * sizeof(unsigned long long)));
+    B2K_CUDA(ctx, B2K_DMALLOC(&d_mm, 2 * sizeof(unsigned long long)));
     unsigned long long init[2] = {~0ull, 0ull};
     B2K_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     if (op->nnz > 0) {
@@ -534,7 +534,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
     unsigned long long mm[2];
     B2K_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
     B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_mm);
+    B2K_DFREE(d_mm);
     const int64_t col0 = ctx->row_offset, n_loc = op->n_loc_cols;
     int64_t lo = 0, hi = 0;
     if (op->nnz > 0) {
@@ -544,7 +544,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
     // exchange (halo_lo, halo_hi, n_loc) with all ranks: 3 int64 each, through a double buffer
     const int R = ctx->nranks;
     double* d_x;
-    B2K_CUDA(ctx, cudaMalloc(&d_x, sizeof(double) * 3 * R));
+    B2K_CUDA(ctx, B2K_DMALLOC(&d_x, sizeof(double) * 3 * R));
     double mine[3] = {(double)lo, (double)hi, (double)n_loc};
     B2K_CUDA(ctx, cudaMemcpyAsync(d_x + 3 * ctx->rank, mine, sizeof(mine), cudaMemcpyHostToDevice,
                                   ctx->stream));
@@ -553,7 +553,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
     B2K_CUDA(ctx, cudaMemcpyAsync(all.data(), d_x, sizeof(double) * 3 * R, cudaMemcpyDeviceToHost,
                                   ctx->stream));
     B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_x);
+    B2K_DFREE(d_x);
     bool neighbour_ok = true;
     for (int r = 0; r < R; ++r) {
         const int64_t l = (int64_t)all[3 * r], h = (int64_t)all[3 * r + 1];
@@ -565,7 +565,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
         op->halo_hi = hi;
         op->send_hi = ctx->rank + 1 < R ? (int64_t)all[3 * (ctx->rank + 1)] : 0;      // rank+1's halo_lo
         op->send_lo = ctx->rank > 0 ? (int64_t)all[3 * (ctx->rank - 1) + 1] : 0;      // rank-1's halo_hi
-        if (lo + hi > 0) B2K_CUDA(ctx, cudaMalloc(&op->halo, (size_t)(lo + hi) * ctx->esize));
+        if (lo + hi > 0) B2K_CUDA(ctx, B2K_DMALLOC(&op->halo, (size_t)(lo + hi) * ctx->esize));
     } else {
         for (int r = 0; r < R; ++r)
             if ((int64_t)all[3 * r + 2] != n_loc)
@@ -573,7 +573,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
                                 "operator couples non-adjacent row shards and shards are unequal: "
                                 "allgather fallback needs equal n_local");
         op->gather_all = 1;
-        B2K_CUDA(ctx, cudaMalloc(&op->xall, (size_t)n_loc * R * ctx->esize));
+        B2K_CUDA(ctx, B2K_DMALLOC(&op->xall, (size_t)n_loc * R * ctx->esize));
     }
     return B2K_OK;
 }
@@ -626,8 +626,8 @@ static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_
     int32_t rc = B2K_OK;
     auto fail = [&](int32_t code) {
         cudaStreamSynchronize(ctx->stream);
-        if (d_gcol) cudaFree(d_gcol);
-        if (d_raw) cudaFree(d_raw);
+        if (d_gcol) B2K_DFREE(d_gcol);
+        if (d_raw) B2K_DFREE(d_raw);
         b2k_op_destroy(ctx, op);
         return code;
     };
@@ -638,11 +638,11 @@ static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_
             return fail(b2k_fail(ctx, B2K_ECUDA, "op_create_csr: %s -> %s", #call,           \
                                  cudaGetErrorString(e__)));                                  \
     } while (0)
-    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_rows + 1 + 8)));
-    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * (nnz1 + 8)));
-    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * (nnz1 + 8)));
-    CK(cudaMalloc(&d_gcol, sizeof(int64_t) * nnz1));
-    CK(cudaMalloc(&d_raw, raw_bytes));
+    CK(B2K_DMALLOC(&op->rowptr, sizeof(int32_t) * (n_rows + 1 + 8)));
+    CK(B2K_DMALLOC(&op->colidx, sizeof(int32_t) * (nnz1 + 8)));
+    CK(B2K_DMALLOC(&op->vals, (size_t)ctx->esize * (nnz1 + 8)));
+    CK(B2K_DMALLOC(&d_gcol, sizeof(int64_t) * nnz1));
+    CK(B2K_DMALLOC(&d_raw, raw_bytes));
     const int g = ctx->num_sms * 8;
     CK(cudaMemcpyAsync(d_raw, rowptr, (size_t)idx_bytes * (n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (idx_bytes == 8) k_convert_rowptr<int64_t><<<g, 256, 0, ctx->stream>>>((const int64_t*)d_raw, index_base, op->rowptr, n_rows + 1);
@@ -656,14 +656,14 @@ static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_
         CK(cudaMemcpyAsync(op->vals, vals, (size_t)ctx->esize * nnz, cudaMemcpyHostToDevice, ctx->stream));
         // validate the column range on the device
         unsigned long long* d_mm;
-        CK(cudaMalloc(&d_mm, 2 * sizeof(unsigned long long)));
+        CK(B2K_DMALLOC(&d_mm, 2 * sizeof(unsigned long long)));
         unsigned long long init[2] = {~0ull, 0ull}, mm[2];
         CK(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
         k_minmax_cols<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(d_gcol, nnz, d_mm, d_mm + 1);
         ctx->launches++;
         CK(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_mm);
+        B2K_DFREE(d_mm);
         const int64_t colmax = ctx->nranks > 1 ? ctx->n_global : n_cols;
         // negative columns wrap to huge unsigned values and are caught by the max test
         if ((int64_t)mm[1] >= colmax || (int64_t)mm[1] < 0)
@@ -676,8 +676,9 @@ static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_
     if (rc == B2K_OK) rc = finish_csr(ctx, op);
     if (rc != B2K_OK) return fail(rc);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_gcol);
-    cudaFree(d_raw);
+    B2K_DFREE(d_gcol);
+    B2K_DFREE(d_raw);
+    ctx->ops.push_back(op);
     *out = op;
     return B2K_OK;
 }
@@ -751,9 +752,9 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
     void* tmp = nullptr;
     int32_t rc = B2K_OK;
     auto fail = [&](int32_t code) {
-        if (counts) cudaFree(counts);
-        if (d_gcol) cudaFree(d_gcol);
-        if (tmp) cudaFree(tmp);
+        if (counts) B2K_DFREE(counts);
+        if (d_gcol) B2K_DFREE(d_gcol);
+        if (tmp) B2K_DFREE(tmp);
         b2k_op_destroy(ctx, op);
         return code;
     };
@@ -764,15 +765,15 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
             return fail(b2k_fail(ctx, B2K_ECUDA, "stencil: %s -> %s", #call,                 \
                                  cudaGetErrorString(e__)));                                  \
     } while (0)
-    CK(cudaMalloc(&counts, sizeof(int32_t) * (n_loc + 1)));
-    CK(cudaMalloc(&op->rowptr, sizeof(int32_t) * (n_loc + 1 + 8)));
+    CK(B2K_DMALLOC(&counts, sizeof(int32_t) * (n_loc + 1)));
+    CK(B2K_DMALLOC(&op->rowptr, sizeof(int32_t) * (n_loc + 1 + 8)));
     const unsigned blocks = (unsigned)((n_loc + 1 + 255) / 256);
     k_stencil_count<<<blocks, 256, 0, ctx->stream>>>(d, counts);
     ctx->launches++;
     size_t tmp_bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, op->rowptr, (int)(n_loc + 1),
                                      ctx->stream));
-    CK(cudaMalloc(&tmp, tmp_bytes));
+    CK(B2K_DMALLOC(&tmp, tmp_bytes));
     CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, op->rowptr, (int)(n_loc + 1),
                                      ctx->stream));
     int32_t h_nnz = 0;
@@ -780,9 +781,9 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     op->nnz = h_nnz;
-    CK(cudaMalloc(&op->colidx, sizeof(int32_t) * (std::max<int64_t>(1, op->nnz) + 8)));
-    CK(cudaMalloc(&op->vals, (size_t)ctx->esize * (std::max<int64_t>(1, op->nnz) + 8)));
-    CK(cudaMalloc(&d_gcol, sizeof(int64_t) * std::max<int64_t>(1, op->nnz)));
+    CK(B2K_DMALLOC(&op->colidx, sizeof(int32_t) * (std::max<int64_t>(1, op->nnz) + 8)));
+    CK(B2K_DMALLOC(&op->vals, (size_t)ctx->esize * (std::max<int64_t>(1, op->nnz) + 8)));
+    CK(B2K_DMALLOC(&d_gcol, sizeof(int64_t) * std::max<int64_t>(1, op->nnz)));
     if (n_loc > 0) {
         if (ctx->dtype == B2K_F64)
             k_stencil_fill<double><<<blocks, 256, 0, ctx->stream>>>(d, op->rowptr, d_gcol,
@@ -798,9 +799,10 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
     if (rc == B2K_OK) rc = finish_csr(ctx, op);
     if (rc != B2K_OK) return fail(rc);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(counts);
-    cudaFree(d_gcol);
-    cudaFree(tmp);
+    B2K_DFREE(counts);
+    B2K_DFREE(d_gcol);
+    B2K_DFREE(tmp);
+    ctx->ops.push_back(op);
     *out = op;
     return B2K_OK;
 }
@@ -818,13 +820,14 @@ static int32_t alloc_dense(b2k_ctx* ctx, b2k_op** out, int64_t m_local, int64_t 
     op->nnz = m_local * n;
     op->ld = ((m_local + 31) / 32) * 32;
     const size_t bytes = (size_t)op->ld * n * ctx->esize;
-    cudaError_t e = cudaMalloc(&op->A, bytes);
+    cudaError_t e = B2K_DMALLOC(&op->A, bytes);
     if (e != cudaSuccess) {
         delete op;
-        return b2k_fail(ctx, B2K_ENOMEM, "dense: cudaMalloc(%zu) failed: %s", bytes,
+        return b2k_fail(ctx, B2K_ENOMEM, "dense: B2K_DMALLOC(%zu) failed: %s", bytes,
                         cudaGetErrorString(e));
     }
     cudaMemsetAsync(op->A, 0, bytes, ctx->stream);
+    ctx->ops.push_back(op);
     *out = op;
     return B2K_OK;
 }
@@ -857,22 +860,24 @@ extern "C" int32_t b2k_op_create_dense_splitmix(b2k_ctx* ctx, b2k_op** out, int6
     return B2K_OK;
 }
 
+void b2k_op_release(b2k_ctx* ctx, b2k_op* op) {
+    cudaStream_t st = ctx ? ctx->stream : nullptr;
+    void* ptrs[] = {op->rowptr, op->colidx, op->vals, op->rowblk, op->pblk, op->part, op->halo, op->xall, op->A};
+    for (void* p : ptrs) b2k_dfree(p, st);     // stream-ordered: pending kernels finish first
+    delete op;
+}
+
 extern "C" int32_t b2k_op_destroy(b2k_ctx* ctx, b2k_op* op) {
     if (!op) return B2K_OK;
     if (ctx) {
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i < ctx->ops.size(); ++i)
+            if (ctx->ops[i] == op) {
+                ctx->ops.erase(ctx->ops.begin() + i);
+                break;
+            }
     }
-    if (op->rowptr) cudaFree(op->rowptr);
-    if (op->colidx) cudaFree(op->colidx);
-    if (op->vals) cudaFree(op->vals);
-    if (op->rowblk) cudaFree(op->rowblk);
-    if (op->pblk) cudaFree(op->pblk);
-    if (op->part) cudaFree(op->part);
-    if (op->halo) cudaFree(op->halo);
-    if (op->xall) cudaFree(op->xall);
-    if (op->A) cudaFree(op->A);
-    delete op;
+    b2k_op_release(ctx, op);
     return B2K_OK;
 }
 
