@@ -210,18 +210,11 @@ def run_ours(a):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf = C.create_string_buffer(128)
-            assert kk._lib.load().b2k_nccl_unique_id(buf) == 0
-            uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        uid_bytes = bytes(uid.cpu().tolist())
-        # shard whole grid lines: rows [y0*nx, y1*nx)
-        y0 = (a.ny * rank) // world
-        y1 = (a.ny * (rank + 1)) // world
-        ctx = kk.B200Context((y1 - y0) * a.nx, a.krylovdim + 2 * HOWMANY + 8, device=local_rank, rank=rank, nranks=world,
-                             nccl_uid=uid_bytes, n_global=n, row_offset=y0 * a.nx)
+        from krylovkit_jl_b200 import sharding
+        uid_bytes = sharding.broadcast_nccl_uid(dist, kk._lib.load(), torch.device("cuda", local_rank))
+        shard = sharding.shard_grid_lines(a.nx, a.ny, rank, world)      # whole grid lines per rank
+        ctx = kk.B200Context(shard.n_local, a.krylovdim + 2 * HOWMANY + 8, device=local_rank, rank=rank,
+                             nranks=world, nccl_uid=uid_bytes, n_global=n, row_offset=shard.row_offset)
     else:
         ctx = kk.B200Context(n, a.krylovdim + 2 * HOWMANY + 8, device=local_rank)
     lib = ctx.lib
@@ -285,14 +278,17 @@ def run_ours(a):
             kern[name] = {"launches": c, "ms_total": round(m, 3), "avg_ms": round(m / c, 4),
                           "GBs": round(b / m / 1e6, 1), "frac": round(b / m / 1e6 / pk, 3),
                           "share_of_step": round(m / (ms.value), 3)}
-    traffic = None
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("gs_fused_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("gs_fused_bytes_per_launch")
+        traffic_note = (f"dram__bytes_read+write of one ncu --set full capture ({tj.get('captured_launch')}); "
+                        f"algorithmic bytes of that launch {tj.get('algorithmic_bytes_same_launch')}")
     gs = kern.get("gs_fused", {})
     roofline = {"kernel": "k_gs_fused<double> (3-term prologue + project, grid barrier, update + norm)",
                 "bound": "hbm", "achieved": gs.get("GBs"), "peak": pk, "unit": "GB/s",
-                "frac": gs.get("frac"), "peak_kind": pk_kind, "traffic": traffic,
+                "frac": gs.get("frac"), "peak_kind": pk_kind, "traffic": traffic, "traffic_note": traffic_note,
                 "algorithmic_bytes": "(2k+3)*8n per launch, k = basis size incl. the new vector; summed over launches",
                 "avg_launch_ms": gs.get("avg_ms")}
 

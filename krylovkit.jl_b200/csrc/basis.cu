@@ -71,22 +71,28 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
 __global__ void k_finalize(const double* __restrict__ A, const double* __restrict__ B,
                            const double* __restrict__ N, int G, int stride, int k,
                            double* __restrict__ res, int off, int noff) {
+    // sums run in CTA order (deterministic); the loads are batched 8 at a time so the chain is
+    // bound by the adds, not by G dependent memory round trips
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < k) {
+    auto colsum = [&](const double* P, int st) {
         double a = 0.0;
-        for (int g = 0; g < G; ++g) a += A[(size_t)g * stride + j];
-        if (B) {
-            double b = 0.0;
-            for (int g = 0; g < G; ++g) b += B[(size_t)g * stride + j];
-            a += b;
+        int g = 0;
+        for (; g + 8 <= G; g += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = P[(size_t)(g + u) * st];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a += t[u];
         }
+        for (; g < G; ++g) a += P[(size_t)g * st];
+        return a;
+    };
+    if (j < k) {
+        double a = colsum(A + j, stride);
+        if (B) a += colsum(B + j, stride);
         res[off + j] = a;
     }
-    if (N && j == 0) {
-        double s = 0.0;
-        for (int g = 0; g < G; ++g) s += N[g];
-        res[noff] = s;
-    }
+    if (N && j == k) res[noff] = colsum(N, 1);
 }
 
 // out[j] = (T) res[j]  (dense adjoint: projection coefficients become a device vector)
@@ -300,7 +306,7 @@ int32_t launch_fused(b2k_ctx* ctx, FusedParams<T>& fp, const ColList& cl, int gr
 int32_t enqueue_finalize(b2k_ctx* ctx, const double* A, const double* B, const double* N, int G,
                          int k, int off, int noff) {
     const int threads = 128;
-    const int blocks = std::max(1, (k + threads - 1) / threads);
+    const int blocks = std::max(1, (k + 1 + threads - 1) / threads);   // thread k sums the norm partials
     k_finalize<<<blocks, threads, 0, ctx->stream>>>(A, B, N, G, B2K_KSTRIDE, k, ctx->d_res, off, noff);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;

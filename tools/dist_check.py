@@ -1,0 +1,77 @@
+"""Run under torchrun (one rank per GPU): row-sharded eigsolve / primitives vs the CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29611 tools/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import krylovkit_jl_b200 as kk  # noqa: E402
+from krylovkit_jl_b200 import sharding  # noqa: E402
+from oracle import krylov_oracle as ko  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    uid = sharding.broadcast_nccl_uid(dist, kk._lib.load(), torch.device("cuda", local))
+    nx, ny = 200, 151
+    n = nx * ny
+    shard = sharding.shard_grid_lines(nx, ny, rank, world)
+    ctx = kk.B200Context(shard.n_local, 64, device=local, rank=rank, nranks=world, nccl_uid=uid,
+                         n_global=n, row_offset=shard.row_offset)
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(20260923, n)
+    sl = slice(shard.row_offset, shard.row_offset + shard.n_local)
+    # 1. device-side start vector is the global splitmix sequence
+    xd = ctx.splitmix(20260923)
+    assert np.array_equal(xd.to_host(), x0[sl])
+    # 2. sharded SpMV (halo exchange) for the stencil and for an uploaded CSR with global columns
+    ref = A @ x0
+    op = kk.B200CSR.stencil(ctx, nx, ny)
+    y = kk.apply(op, xd)
+    assert np.allclose(y.to_host(), ref[sl], rtol=1e-14, atol=1e-14)
+    Aloc = A[sl].tocsr()
+    op2 = kk.B200CSR.from_csr_arrays(ctx, shard.n_local, n, Aloc.indptr.astype(np.int64),
+                                     Aloc.indices.astype(np.int64), Aloc.data)
+    y2 = kk.apply(op2, xd)
+    assert np.array_equal(y2.to_host(), y.to_host())
+    # 3. global reductions
+    assert abs(xd.inner(y) - x0 @ ref) < 1e-9 * abs(x0 @ ref)
+    assert abs(xd.norm() - np.linalg.norm(x0)) < 1e-12 * np.linalg.norm(x0)
+    # 4. eigsolve, converged and fixed-cycle, vs the serial oracle
+    for orth, oorth in ((kk.cgs2, ko.Orth(ko.CGS2)), (kk.mgs2, ko.Orth(ko.MGS2))):
+        alg = kk.Lanczos(orth=orth, krylovdim=30, maxiter=200, tol=1e-10, verbosity=0)
+        vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0[sl]), 3, "SR", alg)
+        ovals, ovecs, oinfo = ko.eigsolve_lanczos(A, x0, 3, "SR", krylovdim=30, maxiter=200, tol=1e-10,
+                                                  orth=oorth)
+        assert info.converged >= 3 and info.numops == oinfo["numops"], (info.numops, oinfo["numops"])
+        assert np.allclose(vals[:3], ovals[:3], rtol=1e-10)
+        lam = ko.laplace_eigenvalues(nx, ny)
+        assert np.allclose(vals[:3], lam[:3], rtol=1e-10)
+        # gather one Ritz vector and check the residual globally
+        vloc = torch.from_numpy(vecs[0].to_host()).cuda()
+        parts = [torch.zeros(sharding.shard_grid_lines(nx, ny, r, world).n_local, dtype=torch.float64,
+                             device="cuda") for r in range(world)]
+        dist.all_gather(parts, vloc)
+        v = torch.cat(parts).cpu().numpy()
+        assert np.linalg.norm(A @ v - vals[0] * v) < 1e-8
+        del vecs
+    if rank == 0:
+        print(f"dist_check ok on {world} ranks: Ritz values {vals[:3]}")
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
