@@ -751,7 +751,8 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
         B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_A0, 1, pn.sharded));
         // CGS2 on the fused path keeps alpha on the device (the prologue reads it from d_res) so
         // that the whole step needs ONE host synchronisation; the other variants fetch it now.
-        const bool defer_alpha = (alg == B2K_CGS2) && fused_ok(ctx, K1, pn.sharded, ctx->dtype);
+        const bool one_pass = K1 <= (f64 ? kcap<double>() : kcap<float>());
+        const bool defer_alpha = (alg == B2K_CGS2) && one_pass;
         double alpha = 0.0;
         if (!defer_alpha) {
             B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
@@ -819,6 +820,40 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
                 if (f64) BUILD_AND_LAUNCH(double) else BUILD_AND_LAUNCH(float)
 #undef BUILD_AND_LAUNCH
                 B2K_TRY(enqueue_finalize(ctx, PA, nullptr, PN, grid, K1, S_H, S_N));
+                B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+                if (defer_alpha) alpha = ctx->h_res[S_A0];
+            } else if (one_pass) {
+                // row-sharded (or > resident-tile) variant of the same two sweeps: one launch per
+                // sweep, the all-reduce of the coefficients sits where the grid barrier was
+                const int grid = f64 ? grid_for_rows<double>(ctx, pn.n) : grid_for_rows<float>(ctx, pn.n);
+                ColList cl;
+                for (int i = 0; i < K1; ++i) cl.c[i] = pn.idx[i];
+                double* PA = b2k_part_set(ctx, 0);
+                double* PN = b2k_part_set(ctx, 2);
+#define SPLIT_SWEEPS(T)                                                                       \
+    {                                                                                         \
+        PhaseParams<T> a = base_params<T>(pn, K1, rw.ptr, rw.ptr);                            \
+        if (prologue) {                                                                       \
+            a.nvec = 3; a.e1 = (const T*)vprev.ptr; a.e2 = (const T*)rv.ptr;                  \
+            a.c1 = (T)(-beta_old); a.c2 = (T)(-alpha); a.store_x = 1;                         \
+            if (defer_alpha) a.c2_dev = ctx->d_res + S_A0;                                    \
+        }                                                                                     \
+        a.part_h = PA;                                                                        \
+        const int pr = b2k_prof_begin(ctx, 1, (2.0 * K1 + 3.0) * sizeof(T) * (double)pn.n);   \
+        B2K_TRY(launch_phase<T>(ctx, a, cl, 0, grid));                                        \
+        B2K_TRY(enqueue_finalize(ctx, PA, nullptr, nullptr, grid, K1, S_H, S_N));             \
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_H, K1, pn.sharded));                        \
+        PhaseParams<T> c = base_params<T>(pn, K1, rw.ptr, rw.ptr);                            \
+        c.store_x = 1; c.coef = ctx->d_res + S_H; c.coef_sets = 1; c.coef_stride = 0;         \
+        c.alphac = (T)-1; c.part_n = PN;                                                      \
+        B2K_TRY(launch_phase<T>(ctx, c, cl, 2, grid));                                        \
+        b2k_prof_end(ctx, pr);                                                                \
+    }
+                if (f64) SPLIT_SWEEPS(double) else SPLIT_SWEEPS(float)
+#undef SPLIT_SWEEPS
+                k_finalize<<<1, 32, 0, ctx->stream>>>(PN, nullptr, PN, grid, B2K_KSTRIDE, 0, ctx->d_res, 0, S_N);
+                B2K_LAUNCH_CHECK(ctx);
+                B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
                 B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
                 if (defer_alpha) alpha = ctx->h_res[S_A0];
             } else {

@@ -24,7 +24,7 @@ int32_t b2k_panel_project_dev(b2k_ctx* ctx, void* base, int64_t ld, int64_t n, i
                               const VecRef& x, void* out_vec, int32_t sharded);
 
 constexpr int SP_BT = 256;
-constexpr int SP_NNZ = 2048;      // nonzeros per CTA tile
+constexpr int SP_NNZ = 1536;      // nonzeros per CTA tile
 constexpr int SP_ROWS = 2048;     // max rows per CTA tile (empty rows)
 
 struct b2k_op {
@@ -165,7 +165,7 @@ __global__ void k_pblk(const int32_t* __restrict__ rowptr, const int32_t* __rest
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SPP_THREADS, 2)
+__global__ void __launch_bounds__(SPP_THREADS, 3)
 k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
             const T* __restrict__ vals, const T* __restrict__ x, const T* __restrict__ halo,
             int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk,
@@ -253,15 +253,18 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             named_bar_sync(1, SPP_CONS);
             const bool rp_staged = nrows <= SPP_RMAX;
             for (int r = r0 + tid; r < r1; r += SPP_CONS) {
+                // issue the (optional) per-row global loads first so they overlap the row sum
+                const T dv = dotv ? __ldg(dotv + r) : (T)0;
+                const T xsr = shifted ? __ldg(xs + r) : (T)0;
                 int a, b;
                 if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
                 else { a = rowptr[r]; b = rowptr[r + 1]; }
                 a -= p0a; b -= p0a;
                 T sum = (T)0;
                 for (int p = a; p < b; ++p) sum += vs[p];
-                if (shifted) sum = fma(a0, xs[r], a1 * sum);
+                if (shifted) sum = fma(a0, xsr, a1 * sum);
                 y[r] = sum;
-                if (dotv) dacc = fma(dotv[r], sum, dacc);
+                dacc = fma(dv, sum, dacc);
             }
         } else {
             double acc = 0.0;
@@ -975,7 +978,7 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
     const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
                                               2.0 * ctx->esize * op->n_rows);
     if (g_spmv_pipe) {
-        const int grid = std::min(op->nblk, 2 * ctx->num_sms);
+        const int grid = std::min(op->nblk, 3 * ctx->num_sms);
 #define LAUNCH(T)                                                                              \
     k_spmv_pipe<T><<<grid, SPP_THREADS, SppLayout<T>::SMEM, ctx->stream>>>(                    \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
