@@ -11,9 +11,64 @@ static bool g_pool_configured[64] = {false};
 struct HostBlock { void* p; size_t bytes; };
 static std::vector<HostBlock> g_host_cache;
 
+// Large blocks (slabs, CSR arrays) are kept in an exact-size free list: repeated solves of the
+// same shape — the host-buffer eigsolve path — then never touch the driver allocator.  (The
+// stream-ordered pool alone splits a freed 6 GB slab to serve 400 MB requests and has to map
+// fresh memory for the next slab: sporadic 100-300 ms stalls, tools/e2e_breakdown.py.)
+// Reuse across streams is made safe by an event recorded at free time.
+#include <unordered_map>
+#include <cstdlib>
+constexpr size_t B2K_BIG_BYTES = (size_t)32 << 20;
+struct BigBlock { void* p; size_t bytes; int dev; cudaEvent_t ev; };
+static std::vector<BigBlock> g_big_free;
+static std::unordered_map<void*, size_t> g_big_live;
+static size_t g_big_cached = 0;
+
+static size_t big_cap_bytes() {
+    static size_t cap = 0;
+    if (!cap) {
+        const char* e = getenv("B2K_CACHE_GB");
+        cap = (size_t)(e ? atof(e) : 48.0) << 30;
+    }
+    return cap;
+}
+
+static void big_evict_locked(size_t keep_bytes) {
+    while (!g_big_free.empty() && g_big_cached > keep_bytes) {
+        BigBlock blk = g_big_free.front();
+        g_big_free.erase(g_big_free.begin());
+        cudaEventSynchronize(blk.ev);
+        cudaEventDestroy(blk.ev);
+        cudaFree(blk.p);
+        g_big_cached -= blk.bytes;
+    }
+}
+
 cudaError_t b2k_dmalloc(void** p, size_t bytes, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
+    if (bytes >= B2K_BIG_BYTES) {
+        std::lock_guard<std::mutex> lk(g_mem_mutex);
+        for (size_t i = 0; i < g_big_free.size(); ++i)
+            if (g_big_free[i].bytes == bytes && g_big_free[i].dev == dev) {
+                BigBlock blk = g_big_free[i];
+                g_big_free.erase(g_big_free.begin() + i);
+                g_big_cached -= bytes;
+                cudaStreamWaitEvent(stream, blk.ev, 0);
+                cudaEventDestroy(blk.ev);
+                g_big_live[blk.p] = bytes;
+                *p = blk.p;
+                return cudaSuccess;
+            }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) {       // give cached blocks back to the driver and retry
+            cudaGetLastError();
+            big_evict_locked(0);
+            e = cudaMalloc(p, bytes);
+        }
+        if (e == cudaSuccess) g_big_live[*p] = bytes;
+        return e;
+    }
     {
         std::lock_guard<std::mutex> lk(g_mem_mutex);
         if (dev < 64 && !g_pool_configured[dev]) {
@@ -25,21 +80,28 @@ cudaError_t b2k_dmalloc(void** p, size_t bytes, cudaStream_t stream) {
             g_pool_configured[dev] = true;
         }
     }
-    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, stream);
-    if (e != cudaSuccess) {   // return cached blocks to the driver and retry once
-        cudaGetLastError();
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            cudaDeviceSynchronize();
-            cudaMemPoolTrimTo(pool, 0);
-        }
-        e = cudaMallocAsync(p, bytes ? bytes : 1, stream);
-    }
-    return e;
+    return cudaMallocAsync(p, bytes ? bytes : 1, stream);
 }
 
 cudaError_t b2k_dfree(void* p, cudaStream_t stream) {
     if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mutex);
+        auto it = g_big_live.find(p);
+        if (it != g_big_live.end()) {
+            BigBlock blk;
+            blk.p = p;
+            blk.bytes = it->second;
+            cudaGetDevice(&blk.dev);
+            g_big_live.erase(it);
+            cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming);
+            cudaEventRecord(blk.ev, stream);
+            g_big_free.push_back(blk);
+            g_big_cached += blk.bytes;
+            big_evict_locked(big_cap_bytes());
+            return cudaSuccess;
+        }
+    }
     return cudaFreeAsync(p, stream);
 }
 
@@ -70,6 +132,7 @@ extern "C" int32_t b2k_cache_release(void) {
     cudaDeviceSynchronize();
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     std::lock_guard<std::mutex> lk(g_mem_mutex);
+    big_evict_locked(0);
     for (auto& b : g_host_cache) cudaFreeHost(b.p);
     g_host_cache.clear();
     return B2K_OK;
