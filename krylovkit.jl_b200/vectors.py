@@ -101,6 +101,11 @@ class B200Context:
         self.check(self.lib.b2k_vec_zero(self.h, v.handle))
         return v
 
+    def full(self, value: float, space: int = 0) -> "B200Vec":
+        v = self.empty(space)
+        self.check(self.lib.b2k_vec_fill(self.h, v.handle, float(value)))
+        return v
+
     def from_host(self, x, space: int = 0) -> "B200Vec":
         v = self.empty(space)
         v.upload(x)

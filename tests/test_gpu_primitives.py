@@ -237,33 +237,48 @@ def test_orthogonalize_single_vector():
     ctx.close()
 
 
-@pytest.mark.parametrize("n,m,keep", [(70001, 30, 18), (5000, 60, 36), (300, 61, 61), (1000, 3, 1)])
-def test_basistransform(n, m, keep):
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,keep", [(70001, 30, 18), (5000, 60, 36), (300, 61, 61), (1000, 3, 1),
+                                      (512, 30, 18), (100003, 90, 75)])
+def test_basistransform(n, m, keep, dtype):
     rng = np.random.default_rng(n)
-    ctx = kk.B200Context(n, m + 4)
-    Q, b = _basis(ctx, n, m, rng)
+    ctx = kk.B200Context(n, m + 4, dtype=dtype)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    Q = Q.astype(dtype)
+    vecs = ctx.empty_range(m)
+    for j, v in enumerate(vecs):
+        v.upload(Q[:, j])
+    b = kk.OrthonormalBasis(vecs)
     U, _ = np.linalg.qr(rng.standard_normal((m, m)))
     kk.basistransform_(b, U[:, :keep])
-    ref = Q @ U[:, :keep]
+    ref = Q.astype(np.float64) @ U[:, :keep]
+    tol = 1e-12 if dtype == np.float64 else 2e-6
     for j in range(keep):
-        np.testing.assert_allclose(b[j].to_host(), ref[:, j], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(b[j].to_host(), ref[:, j], rtol=tol, atol=tol)
     for j in range(keep, m):        # untouched
         np.testing.assert_array_equal(b[j].to_host(), Q[:, j])
     ctx.close()
 
 
-def test_givens_householder_rank1():
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_givens_householder_rank1(dtype):
     """test/linalg.jl:27-44: Givens / Householder on a basis equal the dense result."""
     n, k = 4001, 10
     rng = np.random.default_rng(2)
-    ctx = kk.B200Context(n, k + 6)
-    Q, b = _basis(ctx, n, k, rng)
+    ctx = kk.B200Context(n, k + 6, dtype=dtype)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    Q = Q.astype(dtype).astype(np.float64)
+    vecs = ctx.empty_range(k)
+    for j, v in enumerate(vecs):
+        v.upload(Q[:, j])
+    b = kk.OrthonormalBasis(vecs)
+    f32 = dtype == np.float32
     c, s = np.cos(0.3), np.sin(0.3)
     kk.rmul_givens_(b, 2, 5, c, s)
     Q2 = Q.copy()
     Q2[:, 2], Q2[:, 5] = c * Q[:, 2] - s * Q[:, 5], s * Q[:, 2] + c * Q[:, 5]
     for j in range(k):
-        np.testing.assert_allclose(b[j].to_host(), Q2[:, j], rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(b[j].to_host(), Q2[:, j], rtol=1e-14 if not f32 else 1e-6, atol=1e-15 if not f32 else 1e-7)
     # Householder on columns r
     r = [1, 2, 3, 4, 7]
     vv = rng.standard_normal(len(r))
@@ -274,14 +289,14 @@ def test_givens_householder_rank1():
     w = Q2[:, r] @ vv
     Q3[:, r] -= beta * np.outer(w, vv)
     for j in range(k):
-        np.testing.assert_allclose(b[j].to_host(), Q3[:, j], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(b[j].to_host(), Q3[:, j], rtol=1e-13 if not f32 else 1e-5, atol=1e-14 if not f32 else 1e-6)
     # rank-1 update with beta != 1
     y = ctx.from_host(rng.standard_normal(n))
     xh = rng.standard_normal(k)
     kk.rank1update_(b, y, xh, 0.5, 2.0)
     Q4 = 2.0 * Q3 + 0.5 * np.outer(y.to_host(), xh)
     for j in range(k):
-        np.testing.assert_allclose(b[j].to_host(), Q4[:, j], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(b[j].to_host(), Q4[:, j], rtol=1e-13 if not f32 else 1e-5, atol=1e-14 if not f32 else 1e-5)
     ctx.close()
 
 
@@ -313,4 +328,32 @@ def test_errors_map_to_exceptions():
         a.inner(b2)
     with pytest.raises(kk.B200Error):
         [ctx.empty() for _ in range(10)]
+    ctx.close()
+
+
+@pytest.mark.parametrize("alg", ALGS, ids=lambda a: type(a).__name__)
+@pytest.mark.parametrize("n,k", [(100003, 30), (2_000_128, 12)])
+def test_orthogonalize_float32_multi_tile(alg, n, k):
+    """Float32 path of the fused / pipelined Gram-Schmidt kernels with many row tiles per CTA
+    (config 4's vector length), against a float64 numpy restatement."""
+    rng = np.random.default_rng(n + k)
+    ctx = kk.B200Context(n, k + 6, dtype=np.float32)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    Q = Q.astype(np.float32)
+    vecs = ctx.empty_range(k)
+    for j, v in enumerate(vecs):
+        v.upload(Q[:, j])
+    b = kk.OrthonormalBasis(vecs)
+    vh = rng.standard_normal(n).astype(np.float32)
+    v = ctx.from_host(vh)
+    v, x = kk.orthogonalize_(v, b, alg)
+    nrm = kk.orthogonalize_.last_norm
+    out = v.to_host().astype(np.float64)
+    Q64, v64 = Q.astype(np.float64), vh.astype(np.float64)
+    scale = np.linalg.norm(v64)
+    tol = 3e-6 if alg.tag not in (L.CGS, L.MGS) else 3e-5
+    np.testing.assert_allclose(x, Q64.T @ v64, atol=tol * scale)
+    assert np.abs(Q64.T @ out).max() < tol * scale
+    assert abs(nrm - np.linalg.norm(out)) < 1e-5 * scale
+    assert np.isfinite(out).all()
     ctx.close()
