@@ -38,6 +38,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 import scipy.sparse as sp
+from scipy.linalg import blas as _blas
 from scipy.linalg import lapack
 
 # orthogonalizer tags (src/algorithms.jl:17-80)
@@ -126,6 +127,17 @@ def inner(x, y):
     return float(np.dot(x, y))
 
 
+def _axpy(y, a, x):
+    """y <- y + a*x IN PLACE through BLAS axpy (what VectorInterface.add!! lowers to for Arrays:
+    LinearAlgebra.axpy!).  y must be an array this module owns (fresh result of apply / copy)."""
+    if y.dtype == np.float64 and x.dtype == np.float64 and y.flags.c_contiguous and x.flags.c_contiguous:
+        return _blas.daxpy(x, y, a=float(a))
+    if y.dtype == np.float32 and x.dtype == np.float32 and y.flags.c_contiguous and x.flags.c_contiguous:
+        return _blas.saxpy(x, y, a=float(a))
+    y += y.dtype.type(a) * x
+    return y
+
+
 def norm(x):
     return float(np.linalg.norm(x))
 
@@ -147,11 +159,13 @@ def unproject(y, b, x, alpha=1.0, beta=0.0, r=None):
     """orthonormal.jl:132-150 (generic BLAS-1 path)."""
     r = range(len(b)) if r is None else r
     if beta == 0:
-        y = y * 0.0                  # hard zero
+        y = np.zeros_like(y)         # hard zero
     elif beta != 1:
         y = y * beta
+    else:
+        y = y.copy()                 # the oracle's callers keep their input; one copy, then in-place axpys
     for i, ri in enumerate(r):
-        y = y + (alpha * x[i]) * b[ri]
+        y = _axpy(y, alpha * x[i], b[ri])
     return y
 
 
@@ -190,9 +204,10 @@ def _cgs_pass(v, b, x):
 
 
 def _mgs_pass(v, b, x, accumulate):
+    v = v.copy()
     for i, q in enumerate(b):        # orthonormal.jl:417-421 / 427-431
         s = inner(q, v)
-        v = v - s * q
+        v = _axpy(v, -s, q)
         if accumulate:
             x[i] += s
         else:
@@ -433,20 +448,20 @@ def lanczos_recurrence(A, V, beta, orth: Orth):
         return w, alpha, norm(w)
     if t == CGS2:
         alpha = inner(v, w)
-        w = w - beta * V[-2]
-        w = w - alpha * v
+        w = _axpy(w, -beta, V[-2])   # w is the fresh result of apply: mutate in place like add!!
+        w = _axpy(w, -alpha, v)
         s = np.empty(len(V))
         w, s = _cgs_pass(w, V, s)
         alpha += s[-1]
         return w, alpha, norm(w)
     if t == MGS2:
-        w = w - beta * V[-2]
+        w = _axpy(w, -beta, V[-2])
         alpha = inner(v, w)
-        w = w - alpha * v
+        w = _axpy(w, -alpha, v)
         s = alpha
         for q in V:
             s = inner(q, w)
-            w = w - s * q
+            w = _axpy(w, -s, q)
         alpha += s
         return w, alpha, norm(w)
     if t == CGSIR:
