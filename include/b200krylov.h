@@ -212,6 +212,15 @@ int32_t b2k_vec_orthogonalize(b2k_ctx* ctx, b2k_vec v, b2k_vec q, int32_t alg, d
 int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, int32_t k,
                            b2k_vec r, b2k_vec w, double beta_old, int32_t alg, double eta,
                            double* alpha_out, double* beta_out);
+/* Up to `nsteps` consecutive expand! steps — the inner loop of src/eigsolve/lanczos.jl:33-78
+ * while K < krylovdim and beta > tol — without returning to the caller in between.  `cols` has
+ * capacity k + nsteps + 1: on entry the k basis handles followed by the residual handle; new
+ * residual columns are allocated from the slab.  On return cols[0 .. k + *steps_done) is the basis,
+ * *r_out the residual; alphas_out/betas_out hold one entry per step.  Stops early once beta <= tol. */
+int32_t b2k_lanczos_expand_many(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k,
+                                int32_t nsteps, double beta_old, double tol, int32_t alg, double eta,
+                                double* alphas_out, double* betas_out, int32_t* steps_done,
+                                b2k_vec* r_out);
 /* basistransform!(b, U): b[j] <- sum_i b[i]*U[i,j], j < keep — src/orthonormal.jl:291-354.
  * U is host column-major m x keep (ldu).  In place on cols[0..keep) (row-tile resident). */
 int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_t m,
@@ -226,6 +235,13 @@ int32_t b2k_basis_givens(b2k_ctx* ctx, b2k_vec q1, b2k_vec q2, double c, double 
  * w = sum_i b[cols[i]]*v[i]; b[cols[i]] -= beta*w*conj(v[i]).  `work` is a scratch vector. */
 int32_t b2k_basis_householder(b2k_ctx* ctx, const b2k_vec* cols, int32_t k,
                               const double* v_host, double beta, b2k_vec work);
+
+/* Host-only helper (no device work): restore tridiagonal form after a thick restart —
+ * src/eigsolve/lanczos.jl:88-105 with the Householder conventions of dense/reflector.jl.
+ * D: sorted Ritz values, f: residual weights, U: K x K column-major (updated in place by the
+ * reflectors); alphas/betas get the new T entries.  In Julia this loop stays in Julia. */
+int32_t b2k_host_lanczos_restart(int32_t K, int32_t keep, const double* D, const double* f,
+                                 double* U, int32_t ldu, double* alphas, double* betas);
 
 /* ------------------------------------------------------- block (BlockLanczos) ---- */
 /* block_inner(X, Y): M[i,j] = <X[i], Y[j]> — src/factorizations/blocklanczos.jl:43-52.

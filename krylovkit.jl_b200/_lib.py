@@ -101,6 +101,9 @@ _PROTOS = {
                                           P(C.c_double)]),
     "b2k_lanczos_expand": (C.c_int32, [c_ctx, c_op, P(c_vec), C.c_int32, c_vec, c_vec, C.c_double,
                                        C.c_int32, C.c_double, P(C.c_double), P(C.c_double)]),
+    "b2k_lanczos_expand_many": (C.c_int32, [c_ctx, c_op, P(c_vec), C.c_int32, C.c_int32, C.c_double,
+                                            C.c_double, C.c_int32, C.c_double, P(C.c_double),
+                                            P(C.c_double), P(C.c_int32), P(c_vec)]),
     "b2k_basis_transform": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, P(C.c_double), C.c_int32,
                                         C.c_int32]),
     "b2k_basis_rank1update": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, c_vec, P(C.c_double),
@@ -108,6 +111,8 @@ _PROTOS = {
     "b2k_basis_givens": (C.c_int32, [c_ctx, c_vec, c_vec, C.c_double, C.c_double]),
     "b2k_basis_householder": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, P(C.c_double), C.c_double,
                                           c_vec]),
+    "b2k_host_lanczos_restart": (C.c_int32, [C.c_int32, C.c_int32, P(C.c_double), P(C.c_double),
+                                             P(C.c_double), C.c_int32, P(C.c_double), P(C.c_double)]),
     "b2k_block_inner": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, P(c_vec), C.c_int32, P(C.c_double)]),
     "b2k_block_axpy": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, P(c_vec), C.c_int32, P(C.c_double),
                                    C.c_int32]),

@@ -918,6 +918,42 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
     return B2K_OK;
 }
 
+// The inner loop of eigsolve (src/eigsolve/lanczos.jl:33-78 while K < krylovdim and beta > tol):
+// consecutive expand! steps without returning to the caller.  One host synchronisation per
+// step remains (the reference checks beta after every step), but the per-step host work is
+// C++ instead of interpreter time.
+extern "C" int32_t b2k_lanczos_expand_many(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k,
+                                           int32_t nsteps, double beta_old, double tol, int32_t alg,
+                                           double eta, double* alphas_out, double* betas_out,
+                                           int32_t* steps_done, b2k_vec* r_out) {
+    if (!ctx || !op || !cols || k < 1 || nsteps < 0 || !alphas_out || !betas_out || !steps_done || !r_out)
+        return B2K_EINVAL;
+    *steps_done = 0;
+    b2k_vec r = cols[k];
+    *r_out = r;
+    double beta = beta_old;
+    for (int32_t i = 0; i < nsteps; ++i) {
+        b2k_vec w;
+        B2K_TRY(b2k_vec_alloc(ctx, B2K_VEC_SPACE(r), &w));
+        double a = 0.0, b = 0.0;
+        int32_t rc = b2k_lanczos_expand(ctx, op, cols, k, r, w, beta, alg, eta, &a, &b);
+        if (rc != B2K_OK) {
+            b2k_vec_free(ctx, w);
+            return rc;
+        }
+        alphas_out[i] = a;
+        betas_out[i] = b;
+        ++k;                 // cols[k-1] == old r is now the newest basis vector
+        cols[k] = w;         // the new residual
+        r = w;
+        beta = b;
+        *steps_done = i + 1;
+        *r_out = r;
+        if (beta <= tol) break;
+    }
+    return B2K_OK;
+}
+
 extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_t m,
                                        const double* U_host, int32_t ldu, int32_t keep) {
     if (!ctx || !cols || !U_host || m < 1 || keep < 1 || keep > m || ldu < m) return B2K_EINVAL;

@@ -164,6 +164,9 @@ int32_t b2k_spmv_init(b2k_ctx* ctx);
 int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid);
 void    b2k_nccl_destroy(b2k_ctx* ctx);
 int32_t b2k_nccl_allreduce_f64(b2k_ctx* ctx, double* dptr, int32_t count);
+// NVLink peer-memory all-reduce of a small vector (dist.cu); b2k_peer_ok says whether it is usable
+bool    b2k_peer_ok(const b2k_ctx* ctx);
+int32_t b2k_peer_allreduce(b2k_ctx* ctx, double* dptr, int32_t count);
 // grouped neighbour exchange; up/dn = peer ranks or -1
 int32_t b2k_nccl_halo_exchange(b2k_ctx* ctx, int up, int dn, const void* send_up, size_t send_up_bytes,
                                void* recv_dn, size_t recv_dn_bytes, const void* send_dn,

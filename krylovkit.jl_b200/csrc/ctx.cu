@@ -445,7 +445,10 @@ extern "C" int32_t b2k_vec_zero(b2k_ctx* ctx, b2k_vec v) {
 // ------------------------------------------------------------ scalar plumbing ----
 
 int32_t b2k_allreduce(b2k_ctx* ctx, double* dptr, int32_t count, int32_t sharded) {
-    if (ctx->nranks > 1 && sharded) return b2k_nccl_allreduce_f64(ctx, dptr, count);
+    if (ctx->nranks > 1 && sharded) {
+        if (b2k_peer_ok(ctx) && count <= 1016) return b2k_peer_allreduce(ctx, dptr, count);
+        return b2k_nccl_allreduce_f64(ctx, dptr, count);
+    }
     return B2K_OK;
 }
 

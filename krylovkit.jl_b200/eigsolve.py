@@ -6,9 +6,12 @@ n-length work is delegated to the device through the factorization and basis mir
 """
 from __future__ import annotations
 
+import ctypes as C
 import warnings
 
 import numpy as np
+
+from . import _lib as L
 
 from .algorithms import ConvergenceInfo, Lanczos, WARN_LEVEL
 from .dense import (eigsort, householder_row, lmul_householder, permuteeig, rmul_householder,
@@ -33,6 +36,28 @@ def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = N
     if not isinstance(x0, B200Vec):
         return _eigsolve_host(A, x0, howmany, which, alg, out_vectors)
     return _eigsolve_lanczos(A, x0, howmany, which, alg)
+
+
+USE_NATIVE_RESTART = True      # b2k_host_lanczos_restart (C++) instead of the numpy loop below
+
+
+def restart_lanczos_form(HH, D, f, U, keep, alphas, betas):
+    """eigsolve/lanczos.jl:88-105 in numpy (reference implementation of the native helper)."""
+    H = HH[: keep + 1, :keep]
+    H[:] = 0
+    for j in range(keep):
+        H[j, j] = D[j]
+        H[keep, j] = f[j]
+    for j in range(keep - 1, -1, -1):
+        h, nu = householder_row(H, j + 1, range(0, j + 1), j)
+        H[j + 1, j] = nu
+        H[j + 1, :j] = 0
+        lmul_householder(h, H)
+        rmul_householder(H, h, slice(0, j + 1))
+        rmul_householder(U, h)
+    for j in range(keep):
+        alphas[j] = H[j, j]
+        betas[j] = H[j + 1, j]
 
 
 def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None):
@@ -101,28 +126,28 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
             if converged >= howmany or beta <= tol:
                 break
         if K < krylovdim:
-            fact = lz.expand_(it, fact)
-            numops += 1
+            if alg.eager:
+                fact = lz.expand_(it, fact)
+                numops += 1
+            else:
+                # nothing happens between expansions until K == krylovdim or β <= tol
+                # (eigsolve/lanczos.jl:45,77-79): run them back to back
+                numops += lz.expand_many_(it, fact, krylovdim - K, tol)
         else:
             if numiter == maxiter:
                 break
             keep = (3 * krylovdim + 2 * converged) // 5
             # restore Lanczos form in the first keep columns — eigsolve/lanczos.jl:88-105
-            H = HH[: keep + 1, :keep]
-            H[:] = 0
-            for j in range(keep):
-                H[j, j] = D[j]
-                H[keep, j] = f[j]
-            for j in range(keep - 1, -1, -1):
-                h, nu = householder_row(H, j + 1, range(0, j + 1), j)
-                H[j + 1, j] = nu
-                H[j + 1, :j] = 0
-                lmul_householder(h, H)
-                rmul_householder(H, h, slice(0, j + 1))
-                rmul_householder(U, h)
-            for j in range(keep):
-                fact.alphas[j] = H[j, j]
-                fact.betas[j] = H[j + 1, j]
+            if USE_NATIVE_RESTART:
+                U = np.asfortranarray(U)
+                Dc, fc = np.ascontiguousarray(D, dtype=np.float64), np.ascontiguousarray(f, dtype=np.float64)
+                na, nb = np.empty(keep), np.empty(keep)
+                dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+                L.check(L.load().b2k_host_lanczos_restart(K, keep, dp(Dc), dp(fc), dp(U), U.shape[0], dp(na), dp(nb)))
+                fact.alphas[:keep] = na.tolist()
+                fact.betas[:keep] = nb.tolist()
+            else:
+                restart_lanczos_form(HH, D, f, U, keep, fact.alphas, fact.betas)
             B = fact.basis()
             basistransform_(B, U[:, :keep])
             r = fact.residual()

@@ -196,6 +196,44 @@ def expand_(it: LanczosIterator, state: LanczosFactorization, fused: bool | None
     return state
 
 
+def expand_many_(it: LanczosIterator, state: LanczosFactorization, nsteps: int, tol: float) -> int:
+    """Up to `nsteps` consecutive expand! steps in one C-ABI call (b2k_lanczos_expand_many); stops
+    early once normres <= tol.  Returns the number of steps done.  Falls back to a loop of
+    expand_ for operators that are not device CSR matrices."""
+    if nsteps <= 0:
+        return 0
+    if not (USE_FUSED_EXPAND and isinstance(it.operator, B200CSR) and it.keepvecs):
+        done = 0
+        for _ in range(nsteps):
+            expand_(it, state)
+            done += 1
+            if state.normres() <= tol:
+                break
+        return done
+    V, r = state.V, state.r
+    ctx = r.ctx
+    k = len(V)
+    cols = (L.c_vec * (k + nsteps + 1))()
+    for i, v in enumerate(V.basis):
+        cols[i] = v.handle
+    cols[k] = r.handle
+    al = (C.c_double * nsteps)()
+    be = (C.c_double * nsteps)()
+    done, rout = C.c_int32(), L.c_vec()
+    ctx.check(ctx.lib.b2k_lanczos_expand_many(ctx.h, it.operator.h, cols, k, nsteps, state.normres(), tol,
+                                              it.orth.tag, it.orth.eta, al, be, C.byref(done), C.byref(rout)))
+    d = done.value
+    if d > 0:
+        V.push(r)                                   # the old residual became basis vector k+1
+        for i in range(1, d):
+            V.push(B200Vec(ctx, cols[k + i]))       # columns allocated by the library
+        state.r = B200Vec(ctx, rout.value)
+        state.alphas.extend(al[:d])
+        state.betas.extend(be[:d])
+        state.k += d
+    return d
+
+
 def shrink_(state: LanczosFactorization, k: int):
     """shrink!(state, k) — lanczos.jl:273-291."""
     if state.k != len(state.V):
