@@ -246,6 +246,150 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
     }
 }
 
+// FP64 tensor-core variant of the restart GEMM (double, U resident in shared memory):
+// mma.sync.aligned.m8n8k4.f64 (DMMA).  Warp w owns rows [32w, 32w+32) of the resident tile as
+// four 8-row blocks; outputs are produced 40 columns (five 8-column blocks) per pass; the k loop
+// walks the basis vectors 4 at a time.  Per k-step a warp loads 4 A fragments + 5 B fragments
+// (9 LDS.64) for 20 DMMAs = 5120 FMAs: shared-memory traffic per FMA drops 5x vs the FMA kernel,
+// which was bound by the broadcast loads of U (ncu r01: L1/smem 65 %, FP64 pipe 30 %).
+// Column pitch in the ring is R+8 doubles (== 64 mod 128 bytes) so the four columns of an A
+// fragment hit two disjoint bank halves: 2 wavefronts per LDS.64, the minimum.
+constexpr int TD_PITCH = 256 + 8;                         // doubles per staged column
+constexpr int TD_SLOT = 8 * TD_PITCH * 8;                 // 16896 bytes per ring slot
+constexpr int TD_OFF_U = NS * TD_SLOT;                    // 202752
+constexpr int TD_U_BYTES = 232448 - TD_OFF_U - 256;       // 29440
+constexpr int TD_OFF_BAR = TD_OFF_U + TD_U_BYTES;
+constexpr int TD_SMEM = TD_OFF_BAR + 2 * NS * 8;
+constexpr int TD_NCB = 5;                                 // 8-column output blocks per pass
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+k_transform_dmma(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
+    constexpr int R = 256, C = 8;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full = smem_u32(smem + TD_OFF_BAR), empty = full + NS * 8;
+    double* Us = reinterpret_cast<double*>(smem + TD_OFF_U);
+    const int pitch = ((p.keep + 7) / 8) * 8;             // zero-padded to whole 8-column blocks
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, NCONS / 32);
+        }
+        fence_mbar_init();
+    }
+    for (int idx = threadIdx.x; idx < p.m * pitch; idx += blockDim.x) {
+        const int i = idx / pitch, j = idx - i * pitch;
+        Us[idx] = (j < p.keep) ? p.U[(size_t)j * p.ldu + i] : 0.0;
+    }
+    __syncthreads();
+    const int nch = (p.m + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    double* base = reinterpret_cast<double*>(p.base);
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= NCONS) {
+        const int lane = threadIdx.x & 31;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(empty + 8 * s, ph ^ 1);
+                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+                if (lane == 0) mbar_expect_tx(full + 8 * s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(ring + s * TD_SLOT + lane * TD_PITCH * 8,
+                             base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes, full + 8 * s);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        const bool streaming = p.keep <= 8 * TD_NCB;   // one pass: consume and release chunks as they land
+        const uint32_t s0 = s;
+        if (!streaming) {
+            for (int c = 0; c < nch; ++c) {   // several passes: the whole row tile must be resident
+                mbar_wait(full + 8 * s, ph);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+        for (int jb = 0; jb < p.keep; jb += 8 * TD_NCB) {
+            const int ncb = ((p.keep - jb + 7) / 8) < TD_NCB ? ((p.keep - jb + 7) / 8) : TD_NCB;
+            double acc[4][TD_NCB][2];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int cb = 0; cb < TD_NCB; ++cb) { acc[rb][cb][0] = 0.0; acc[rb][cb][1] = 0.0; }
+            uint32_t ss = s0;
+            for (int c = 0; c < nch; ++c) {
+                if (streaming) {
+                    mbar_wait(full + 8 * s, ph);
+                    ss = s;
+                }
+                const double* slot = reinterpret_cast<const double*>(smem + ss * TD_SLOT);
+                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const int k0 = ks * 4;
+                    if (k0 < ncol) {
+                        const bool kv = (k0 + t) < ncol;          // tail of the last chunk: zero operands
+                        double a[4], b[TD_NCB];
+#pragma unroll
+                        for (int rb = 0; rb < 4; ++rb) {
+                            const int row = 32 * w + 8 * rb + g;
+                            // rows >= rt hold stale (possibly non-finite) data: zero them
+                            a[rb] = (kv && row < rt) ? slot[(k0 + t) * TD_PITCH + row] : 0.0;
+                        }
+                        const double* urow = Us + (size_t)(c * C + k0 + t) * pitch + jb + g;
+#pragma unroll
+                        for (int cb = 0; cb < TD_NCB; ++cb) b[cb] = (kv && cb < ncb) ? urow[cb * 8] : 0.0;
+#pragma unroll
+                        for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                            for (int cb = 0; cb < TD_NCB; ++cb)
+                                if (cb < ncb) dmma884(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
+                    }
+                }
+                if (streaming) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + 8 * s);
+                    if (++s == NS) { s = 0; ph ^= 1; }
+                } else if (++ss == NS) ss = 0;
+            }
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                const int row = 32 * w + 8 * rb + g;
+#pragma unroll
+                for (int cb = 0; cb < TD_NCB; ++cb) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = jb + cb * 8 + 2 * t + e;
+                        if (cb < ncb && col < p.keep && row < rt)
+                            base[(int64_t)cl.c[col] * p.ld + r0 + row] = acc[rb][cb][e];
+                    }
+                }
+            }
+        }
+        if (streaming) continue;
+        uint32_t ss = s0;
+        __syncwarp();
+        for (int c = 0; c < nch; ++c) {
+            if (lane == 0) mbar_arrive(empty + 8 * ss);
+            if (++ss == NS) ss = 0;
+        }
+    }
+}
+
 // rank1update!: b[cols[i]] = beta*b[cols[i]] + (alpha*conj(x[i])) * y   — orthonormal.jl:219-227
 struct CoefList {
     double c[256];
@@ -495,6 +639,7 @@ bool fused_ok(const b2k_ctx* ctx, int k, int sharded, int dtype) {
 }
 
 bool g_use_coop = true;
+bool g_use_dmma = true;
 
 // modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
 // s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
@@ -530,11 +675,17 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR((k_phase<float, true, false>), SMEM_BYTES);
     SETATTR(k_gs_fused<double>, SMEM_BYTES);
     SETATTR(k_gs_fused<float>, SMEM_BYTES);
+    SETATTR(k_transform_dmma, TD_SMEM);
     SETATTR((k_transform<double, true>), TR_SMEM);
     SETATTR((k_transform<double, false>), TR_SMEM);
     SETATTR((k_transform<float, true>), TR_SMEM);
     SETATTR((k_transform<float, false>), TR_SMEM);
 #undef SETATTR
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_debug_set_dmma(int32_t on) {
+    g_use_dmma = on != 0;
     return B2K_OK;
 }
 
@@ -982,7 +1133,10 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
     ColList cl;
     for (int i = 0; i < m; ++i) cl.c[i] = pn.idx[i];
     const int pr = b2k_prof_begin(ctx, 2, (double)(m + keep) * ctx->esize * (double)pn.n);
-    if (f64) {
+    const bool dmma_ok = f64 && g_use_dmma && (size_t)m * (((keep + 7) / 8) * 8) * 8 <= (size_t)TD_U_BYTES;
+    if (dmma_ok) {
+        k_transform_dmma<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
+    } else if (f64) {
         if (p.u_in_smem) k_transform<double, true><<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
         else k_transform<double, false><<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
     } else {
