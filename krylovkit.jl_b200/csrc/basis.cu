@@ -644,9 +644,33 @@ bool g_use_dmma = true;
 // modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
 // s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
 // with accumulate, d_res[acc_off + j] += s_j (reorthogonalize!!, :427-431).
+// While a modified Gram-Schmidt sweep runs, the vector being orthogonalised is re-read and
+// re-written once per basis vector (4W per column).  If it fits the persisting-L2 carve-out
+// (n*8 <= ~94 MB of the 126 MB L2) it is pinned there for the duration of the sweep, so HBM
+// only sees the two basis columns of each pass.
+void mgs_pin_vector(b2k_ctx* ctx, const VecRef& v, bool on) {
+    if (ctx->l2_persist_bytes == 0) return;
+    const size_t bytes = (size_t)v.n * ctx->esize;
+    if (bytes > ctx->l2_persist_bytes || bytes > ctx->l2_window_max) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = v.ptr;
+    attr.accessPolicyWindow.num_bytes = on ? bytes : 0;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (!on) cudaCtxResetPersistingL2Cache();
+}
+
 int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res_off, int acc_off) {
     const int es = ctx->esize;
     const bool dist = ctx->nranks > 1 && pn.sharded;
+    struct Pin {
+        b2k_ctx* c; const VecRef& v; bool on;
+        Pin(b2k_ctx* c_, const VecRef& v_, bool on_) : c(c_), v(v_), on(on_) { if (on) mgs_pin_vector(c, v, true); }
+        ~Pin() { if (on) mgs_pin_vector(c, v, false); }
+    } pin(ctx, v, k >= 4);
     for (int j = 0; j < k; ++j) {
         const char* qj = (const char*)pn.base + (size_t)pn.idx[j] * pn.ld * es;
         const char* qp = j > 0 ? (const char*)pn.base + (size_t)pn.idx[j - 1] * pn.ld * es : nullptr;

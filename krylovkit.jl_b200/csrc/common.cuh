@@ -46,6 +46,8 @@ struct b2k_ctx {
     int32_t dtype  = B2K_F64;
     int32_t esize  = 8;
     int32_t num_sms = 0;
+    size_t  l2_persist_bytes = 0;   // persisting-L2 carve-out (0 = unavailable)
+    size_t  l2_window_max = 0;      // max access-policy window
     cudaStream_t stream = nullptr;
     std::vector<B2kSpace> spaces;
     std::vector<b2k_op*> ops;   // operators created on this context (destroyed with it)

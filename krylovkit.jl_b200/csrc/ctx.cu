@@ -217,6 +217,13 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
         fprintf(stderr, "[b200krylov] warning: device %s is sm_%d%d; this library is built for "
                         "sm_100a only\n", prop.name, prop.major, prop.minor);
     ctx->num_sms = prop.multiProcessorCount;
+    if (prop.persistingL2CacheMaxSize > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+        ctx->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+        ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    } else {
+        cudaGetLastError();
+    }
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(B2K_DMALLOC(&ctx->d_part, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE));
     CK(B2K_DMALLOC(&ctx->d_part_s, sizeof(double) * (1 << 20)));
