@@ -292,42 +292,68 @@ def run_ours(a):
                 "algorithmic_bytes": "(2k+3)*8n per launch, k = basis size incl. the new vector; summed over launches",
                 "avg_launch_ms": gs.get("avg_ms")}
 
-    # ---- end to end through the host-buffer API (rank 0 / single GPU only) ----
+    # ---- end to end through the host-buffer API: every rank uploads ITS rows of A (CSR with global
+    # column indices) and its slice of x0 from pinned memory, solves, downloads its slice of the vectors
     e2e = None
-    if not a.no_e2e and world == 1:
-        rp, prp = pinned_array(lib, op.n_rows + 1, np.int32)
+    if not a.no_e2e:
+        n_loc = op.n_rows
+        rp, prp = pinned_array(lib, n_loc + 1, np.int32)
         ci, pci = pinned_array(lib, op.nnz, np.int32)
         va, pva = pinned_array(lib, op.nnz, np.float64)
         ctx.check(lib.b2k_op_csr_download(ctx.h, op.h, rp.ctypes.data, ci.ctypes.data, va.ctypes.data))
-        xh, pxh = pinned_array(lib, n, np.float64)
+        shard, uid2 = None, None
+        if world > 1:
+            # the device stores localised columns ([local | lo halo | hi halo]); undo that to get
+            # the global indices a user would hand over (5-point stencil: one grid line of halo)
+            from krylovkit_jl_b200 import sharding
+            shard = sharding.shard_grid_lines(a.nx, a.ny, rank, world)
+            lo = a.nx if rank > 0 else 0
+            loc = ci.astype(np.int64)
+            glob = np.where(loc < n_loc, loc + shard.row_offset,
+                            np.where(loc < n_loc + lo, loc - n_loc + shard.row_offset - lo,
+                                     loc - n_loc - lo + shard.row_offset + n_loc))
+            ci[:] = glob.astype(np.int32)
+            import torch
+            uid2 = sharding.broadcast_nccl_uid(dist, lib, torch.device("cuda", local_rank))
+        xh, pxh = pinned_array(lib, n_loc, np.float64)
         x0.to_host(xh)
-        outs = [pinned_array(lib, n, np.float64) for _ in range(HOWMANY)]
+        # the resident context is no longer needed: closing it returns its slab to the library's
+        # block cache and (N > 1) its NCCL communicator to the per-process cache, so the per-call
+        # contexts of the host-buffer path reuse both instead of paying for new ones
+        ctx.close()
+        outs = [pinned_array(lib, n_loc, np.float64) for _ in range(HOWMANY)]
         out_arrs = [o[0] for o in outs]
         h2d = rp.nbytes + ci.nbytes + va.nbytes + xh.nbytes
         d2h = sum(o.nbytes for o in out_arrs) + 8 * HOWMANY
 
         def job_e2e():
-            return kk.eigsolve((rp, ci, va), xh, HOWMANY, "SR", alg, out_vectors=out_arrs)
+            return kk.eigsolve((rp, ci, va), xh, HOWMANY, "SR", alg, out_vectors=out_arrs, shard=shard,
+                               nccl_uid=uid2, device=local_rank)
 
         for _ in range(max(1, min(a.warmup, 2))):
             job_e2e()
-        lib.b2k_device_sync()
+        barrier()
         t0 = time.perf_counter()
         ops = 0
         for _ in range(a.steps):
             v2, vec2, info2 = job_e2e()
             ops += info2.numops
-        lib.b2k_device_sync()
+        barrier()
         te = time.perf_counter() - t0
-        assert np.allclose(v2, vals, rtol=1e-12), (v2, vals)
+        assert np.allclose(v2, vals, rtol=1e-10), (v2, vals)
+        if dist is not None:
+            import torch
+            tt = torch.tensor([te, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+            tmax = tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt)
+            te, h2d, d2h = float(tmax[0].item()), float(tt[1].item()), float(tt[2].item())
         e2e = {"value": ops / te, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1000.0 * te / a.steps,
-               "path": "kk.eigsolve(csr_host_arrays, x0_host, ...): ctx create + H2D (pinned) + solve + D2H (pinned)"}
+               "path": "kk.eigsolve(csr_host_arrays, x0_host, ...) on every rank: ctx create + H2D (pinned) + solve "
+                       "+ D2H (pinned); wall clock, max over ranks; bytes summed over ranks"}
         for p in (prp, pci, pva, pxh, *[o[1] for o in outs]):
             lib.b2k_pinned_free(p)
-    elif world > 1:
-        e2e = {"value": None, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "host-buffer path measured at N=1 only"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -351,10 +377,10 @@ def run_ours(a):
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
 
 
 def main():

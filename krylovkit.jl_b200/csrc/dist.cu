@@ -187,7 +187,20 @@ int32_t b2k_peer_allreduce(b2k_ctx* ctx, double* dptr, int32_t count) {
     return B2K_OK;
 }
 
+// One NCCL communicator per process (rank, nranks, device) is kept alive and shared by
+// consecutive contexts: ncclCommInitRank costs 50-200 ms, which would dominate a host-buffer
+// solve that creates a context per call.  A cached communicator ignores the new unique id.
+static B2kNccl* g_comm_cache = nullptr;
+static int g_comm_rank = -1, g_comm_nranks = -1, g_comm_device = -1;
+static bool g_comm_in_use = false;
+
 int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid) {
+    if (g_comm_cache && !g_comm_in_use && g_comm_rank == ctx->rank && g_comm_nranks == ctx->nranks &&
+        g_comm_device == ctx->device) {
+        ctx->nccl = g_comm_cache;
+        g_comm_in_use = true;
+        return B2K_OK;
+    }
     if (!uid) return b2k_fail(ctx, B2K_EINVAL, "ctx_create_dist: nccl_uid is NULL");
     B2kNccl* n = new B2kNccl();
     int32_t rc = load_nccl(ctx, n);
@@ -200,11 +213,23 @@ int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid) {
     ctx->nccl = n;
     NCCL_CK(ctx, n, n->CommInitRank(&n->comm, ctx->nranks, id, ctx->rank));
     peer_setup(ctx, n);
+    if (!g_comm_cache) {
+        g_comm_cache = n;
+        g_comm_rank = ctx->rank;
+        g_comm_nranks = ctx->nranks;
+        g_comm_device = ctx->device;
+        g_comm_in_use = true;
+    }
     return B2K_OK;
 }
 
 void b2k_nccl_destroy(b2k_ctx* ctx) {
     if (!ctx->nccl) return;
+    if (ctx->nccl == g_comm_cache) {     // stays alive for the next context of this process
+        g_comm_in_use = false;
+        ctx->nccl = nullptr;
+        return;
+    }
     if (ctx->nccl->peer_ok)
         for (int p = 0; p < ctx->nranks; ++p)
             if (p != ctx->rank) cudaIpcCloseMemHandle(ctx->nccl->peer.ptr[p]);

@@ -23,7 +23,7 @@ from .vectors import B200Context, B200Vec
 
 
 def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = None,
-             out_vectors=None, **kwargs):
+             out_vectors=None, shard=None, nccl_uid: bytes | None = None, device: int = 0, **kwargs):
     """eigsolve(A, x₀, howmany, which, alg::Lanczos) — src/eigsolve/lanczos.jl:1-155.
 
     A  : B200Operator / callable on B200Vec (device-resident path), or a scipy sparse
@@ -34,7 +34,7 @@ def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = N
     if alg is None:
         alg = Lanczos(**kwargs)
     if not isinstance(x0, B200Vec):
-        return _eigsolve_host(A, x0, howmany, which, alg, out_vectors)
+        return _eigsolve_host(A, x0, howmany, which, alg, out_vectors, shard, nccl_uid, device)
     return _eigsolve_lanczos(A, x0, howmany, which, alg)
 
 
@@ -60,20 +60,29 @@ def restart_lanczos_form(HH, D, f, U, keep, alphas, betas):
         betas[j] = H[j + 1, j]
 
 
-def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None):
+def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None, shard=None, nccl_uid=None, device=0):
     """Host-buffer entry: upload (A, x₀), solve, download.  The slab is sized for the
-    factorization: krylovdim + 1 basis vectors, the residual and work columns."""
+    factorization: krylovdim + 1 basis vectors, the residual and work columns.
+    Row-sharded form (one process per GPU): `shard` = sharding.RowShard of this rank, A = the
+    local rows as a CSR triple with GLOBAL column indices, x0 = the local slice."""
     import scipy.sparse as sp
     x0 = np.asarray(x0)
     n = x0.shape[0]
     dtype = np.float32 if x0.dtype == np.float32 else np.float64
-    ctx = B200Context(n, alg.krylovdim + 2 * howmany + 8, dtype=dtype)
+    if shard is not None and shard.world > 1:
+        ctx = B200Context(n, alg.krylovdim + 2 * howmany + 8, dtype=dtype, device=device, rank=shard.rank,
+                          nranks=shard.world, nccl_uid=nccl_uid, n_global=shard.n_global,
+                          row_offset=shard.row_offset)
+        ncols_global = shard.n_global
+    else:
+        ctx = B200Context(n, alg.krylovdim + 2 * howmany + 8, dtype=dtype, device=device)
+        ncols_global = n
     try:
         if sp.issparse(A):
             op = B200CSR.from_scipy(ctx, A)
         elif isinstance(A, tuple) and len(A) == 3:
             rowptr, colidx, vals = A
-            op = B200CSR.from_csr_arrays(ctx, n, n, rowptr, colidx, vals)   # no host-side copies
+            op = B200CSR.from_csr_arrays(ctx, n, ncols_global, rowptr, colidx, vals)   # no host-side copies
         else:
             raise TypeError("eigsolve: host-side A must be a scipy sparse matrix or a CSR triple")
         xv = ctx.from_host(x0)
