@@ -103,11 +103,6 @@ __global__ void k_res_to_vec(const double* __restrict__ res, T* __restrict__ out
     if (j < k) out[j] = alpha * (T)res[j];
 }
 
-// Lanczos tail: res[0] = alpha0 + s[k-1]  (lanczos.jl:321 `α += s[end]`)
-__global__ void k_lanczos_alpha(double* res, int alpha_slot, int s_last_slot, int out_slot) {
-    if (threadIdx.x == 0) res[out_slot] = res[alpha_slot] + res[s_last_slot];
-}
-
 // basistransform!: cols[0..keep) <- Q[:, cols[0..m)] * U, in place, tile resident in the ring
 struct TransformParams {
     void* base;
@@ -558,14 +553,6 @@ int32_t unproject_t(b2k_ctx* ctx, const Panel& pn, const VecRef& y, int k, const
 // Gram-Schmidt drivers (device side: everything stays enqueued; results land in d_res)
 // d_res layout for orthogonalize: [0..k) h, [k] ||v||^2
 // ------------------------------------------------------------------------------------
-struct GsPlan {
-    bool prologue = false;      // Lanczos three-term prologue in the first phase
-    const void* e1 = nullptr;
-    const void* e2 = nullptr;
-    double c1 = 0, c2 = 0;
-    int c2_slot = -1;           // if >= 0: c2 = -d_res[c2_slot] is not known on host -> unsupported here
-};
-
 // One classical Gram-Schmidt pass set.  passes = 1 (CGS) or 2 (CGS2).  Results:
 // d_res[0..k) = h (sum over passes), d_res[k] = ||v_out||^2.  Single-GPU fused path.
 template <typename T>
@@ -915,7 +902,6 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
     const int S_H = 0;             // [0..K1) projection coefficients
     const int S_N = K1;            // ||w||^2
     const int S_A0 = K1 + 1;       // <v, A v>
-    const int S_X = K1 + 2;        // scratch
 
     // v = r / beta_old  (the residual's storage becomes the new basis vector, lanczos.jl:257)
     B2K_TRY(b2k_vec_scale(ctx, r, r, 1.0 / beta_old));
@@ -1087,7 +1073,6 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
             beta = sqrt(ctx->h_res[S_N]);
         }
     }
-    (void)S_X;
     *alpha_out = alpha;
     *beta_out = beta;
     return B2K_OK;

@@ -237,11 +237,6 @@ k_axpy_dev(T* __restrict__ x, const T* __restrict__ q, const double* __restrict_
     }
 }
 
-__global__ void k_sqrt_inplace(double* v, int count) {
-    int i = threadIdx.x;
-    if (i < count) v[i] = sqrt(v[i]);
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------ internal API ----
@@ -283,12 +278,6 @@ int32_t b2k_enqueue_axpy_dev(b2k_ctx* ctx, void* x, const void* q, int s_slot, i
     else
         k_axpy_dev<float><<<grid, BT, 0, ctx->stream>>>((float*)x, (const float*)q,
                                                         ctx->d_res + s_slot, n);
-    B2K_LAUNCH_CHECK(ctx);
-    return B2K_OK;
-}
-
-int32_t b2k_enqueue_sqrt(b2k_ctx* ctx, int slot, int count) {
-    k_sqrt_inplace<<<1, 32, 0, ctx->stream>>>(ctx->d_res + slot, count);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;
 }

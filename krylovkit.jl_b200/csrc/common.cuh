@@ -59,8 +59,6 @@ struct b2k_ctx {
     double*   h_res    = nullptr;   // pinned
     double*   d_coef   = nullptr;   // coefficients uploaded from host
     double*   h_coef   = nullptr;   // pinned staging
-    int32_t*  d_cols   = nullptr;   // column index lists (4 x 4096 ints)
-    int32_t*  h_cols   = nullptr;   // pinned staging
     unsigned* d_sync   = nullptr;   // [0] ticket, [1] grid barrier counter, ...
     cudaEvent_t ev_coef = nullptr;  // guards reuse of the pinned staging buffers
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // b2k_timer_start/stop
@@ -131,8 +129,6 @@ int32_t b2k_fetch_results(b2k_ctx* ctx, int32_t count, int32_t sharded);
 int32_t b2k_allreduce(b2k_ctx* ctx, double* dptr, int32_t count, int32_t sharded);
 // upload `count` doubles of host coefficients into d_coef + offset (async, pinned staging)
 int32_t b2k_put_coef(b2k_ctx* ctx, const double* host, int32_t count, int32_t offset);
-int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t slot,
-                     int32_t** dptr);
 
 // Device memory comes from the CUDA stream-ordered pool with an unbounded release
 // threshold: cudaMalloc/cudaFree of multi-GB slabs cost 30-600 ms per solve in the

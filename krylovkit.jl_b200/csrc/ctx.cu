@@ -231,8 +231,6 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
     CK(b2k_hmalloc((void**)&ctx->h_res, sizeof(double) * B2K_RES_DOUBLES));
     CK(B2K_DMALLOC(&ctx->d_coef, sizeof(double) * B2K_COEF_DOUBLES));
     CK(b2k_hmalloc((void**)&ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES));
-    CK(B2K_DMALLOC(&ctx->d_cols, sizeof(int32_t) * 4 * 4096));
-    CK(b2k_hmalloc((void**)&ctx->h_cols, sizeof(int32_t) * 4 * 4096));
     CK(B2K_DMALLOC(&ctx->d_sync, sizeof(unsigned) * 64));
     CK(cudaMemsetAsync(ctx->d_sync, 0, sizeof(unsigned) * 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_part, 0, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE,
@@ -298,8 +296,6 @@ extern "C" int32_t b2k_ctx_destroy(b2k_ctx* ctx) {
     b2k_hfree(ctx->h_res, sizeof(double) * B2K_RES_DOUBLES);
     if (ctx->d_coef) B2K_DFREE(ctx->d_coef);
     b2k_hfree(ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES);
-    if (ctx->d_cols) B2K_DFREE(ctx->d_cols);
-    b2k_hfree(ctx->h_cols, sizeof(int32_t) * 4 * 4096);
     if (ctx->d_sync) B2K_DFREE(ctx->d_sync);
     if (ctx->ev_coef) cudaEventDestroy(ctx->ev_coef);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -485,21 +481,6 @@ int32_t b2k_put_coef(b2k_ctx* ctx, const double* host, int32_t count, int32_t of
     memcpy(ctx->h_coef + offset, host, sizeof(double) * count);
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_coef + offset, ctx->h_coef + offset,
                                   sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
-    B2K_CUDA(ctx, cudaEventRecord(ctx->ev_coef, ctx->stream));
-    ctx->coef_busy = true;
-    return B2K_OK;
-}
-
-int32_t b2k_put_cols(b2k_ctx* ctx, const int32_t* host, int32_t count, int32_t slot,
-                     int32_t** dptr) {
-    if (count < 0 || count > 4096 || slot < 0 || slot >= 4)
-        return b2k_fail(ctx, B2K_EINVAL, "put_cols: bad count %d / slot %d", count, slot);
-    *dptr = ctx->d_cols + slot * 4096;
-    if (count == 0) return B2K_OK;
-    B2K_TRY(wait_staging(ctx));
-    memcpy(ctx->h_cols + slot * 4096, host, sizeof(int32_t) * count);
-    B2K_CUDA(ctx, cudaMemcpyAsync(*dptr, ctx->h_cols + slot * 4096, sizeof(int32_t) * count,
-                                  cudaMemcpyHostToDevice, ctx->stream));
     B2K_CUDA(ctx, cudaEventRecord(ctx->ev_coef, ctx->stream));
     ctx->coef_busy = true;
     return B2K_OK;
