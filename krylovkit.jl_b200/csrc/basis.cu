@@ -68,31 +68,24 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
 }
 
 // res[off + j] = sum_g A[g*stride + j] (+ sum_g B[g*stride + j]);  res[noff] = sum_g N[g]
-__global__ void k_finalize(const double* __restrict__ A, const double* __restrict__ B,
-                           const double* __restrict__ N, int G, int stride, int k,
-                           double* __restrict__ res, int off, int noff) {
-    // sums run in CTA order (deterministic); the loads are batched 8 at a time so the chain is
-    // bound by the adds, not by G dependent memory round trips
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    auto colsum = [&](const double* P, int st) {
-        double a = 0.0;
-        int g = 0;
-        for (; g + 8 <= G; g += 8) {
-            double t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = P[(size_t)(g + u) * st];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a += t[u];
-        }
-        for (; g < G; ++g) a += P[(size_t)g * st];
-        return a;
-    };
-    if (j < k) {
-        double a = colsum(A + j, stride);
-        if (B) a += colsum(B + j, stride);
-        res[off + j] = a;
+__global__ void __launch_bounds__(NCONS)
+k_finalize(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ N, int G,
+           int stride, int k, double* __restrict__ res, int off, int noff) {
+    // one block of NCONS threads; same lane layout and summation order as the UPDATE phases
+    const int tid = threadIdx.x;
+    if (k > 0) {
+        const int L = coef_lanes(k);
+        const int j = tid / L, l = tid % L;
+        const bool valid = j < k;
+        double a = coef_colsum(A, G, stride, j, l, L, valid);
+        if (B) a += coef_colsum(B, G, stride, j, l, L, valid);
+        if (valid && l == 0) res[off + j] = a;
     }
-    if (N && j == k) res[noff] = colsum(N, 1);
+    if (N && tid < 32) {
+        double a = (tid < 16) ? partial_lane_sum(N, G, 1, tid, 16) : 0.0;
+        for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (tid == 0) res[noff] = a;
+    }
 }
 
 // out[j] = (T) res[j]  (dense adjoint: projection coefficients become a device vector)
@@ -444,9 +437,8 @@ int32_t launch_fused(b2k_ctx* ctx, FusedParams<T>& fp, const ColList& cl, int gr
 
 int32_t enqueue_finalize(b2k_ctx* ctx, const double* A, const double* B, const double* N, int G,
                          int k, int off, int noff) {
-    const int threads = 128;
-    const int blocks = std::max(1, (k + 1 + threads - 1) / threads);   // thread k sums the norm partials
-    k_finalize<<<blocks, threads, 0, ctx->stream>>>(A, B, N, G, B2K_KSTRIDE, k, ctx->d_res, off, noff);
+    if (k > NCONS) return b2k_fail(ctx, B2K_ENOTSUP, "finalize: more than %d coefficients per pass", NCONS);
+    k_finalize<<<1, NCONS, 0, ctx->stream>>>(A, B, N, G, B2K_KSTRIDE, k, ctx->d_res, off, noff);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;
 }
@@ -612,7 +604,7 @@ int32_t cgs_pass_unfused_t(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k
                            b2k_part_set(ctx, 2)));
     const int grid = grid_for_rows<T>(ctx, pn.n);
     // norm partials -> d_res[nslot]
-    k_finalize<<<1, 32, 0, ctx->stream>>>(b2k_part_set(ctx, 2), nullptr, b2k_part_set(ctx, 2), grid,
+    k_finalize<<<1, NCONS, 0, ctx->stream>>>(b2k_part_set(ctx, 2), nullptr, b2k_part_set(ctx, 2), grid,
                                           B2K_KSTRIDE, 0, ctx->d_res, 0, nslot);
     B2K_LAUNCH_CHECK(ctx);
     B2K_TRY(b2k_allreduce(ctx, ctx->d_res + nslot, 1, pn.sharded));
@@ -1012,7 +1004,7 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
     }
                 if (f64) SPLIT_SWEEPS(double) else SPLIT_SWEEPS(float)
 #undef SPLIT_SWEEPS
-                k_finalize<<<1, 32, 0, ctx->stream>>>(PN, nullptr, PN, grid, B2K_KSTRIDE, 0, ctx->d_res, 0, S_N);
+                k_finalize<<<1, NCONS, 0, ctx->stream>>>(PN, nullptr, PN, grid, B2K_KSTRIDE, 0, ctx->d_res, 0, S_N);
                 B2K_LAUNCH_CHECK(ctx);
                 B2K_TRY(b2k_allreduce(ctx, ctx->d_res + S_N, 1, pn.sharded));
                 B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));

@@ -135,6 +135,36 @@ __device__ __forceinline__ void pipe_setup(const SmemView& sm, bool zero_ring) {
     __syncthreads();
 }
 
+// ---------------------------------------------------------------- partial sums ----
+// Deterministic sum over G per-CTA partials of one coefficient, shared by the UPDATE phases and
+// by k_finalize so that the coefficient APPLIED to the vector and the one REPORTED to the host
+// are the same bits.  L = coef_lanes(k) lanes (a power of two, L*k <= 256) share a column: lane
+// l adds the partials g = l, l+L, ... in order (loads batched 4 deep), then a fixed xor tree
+// combines the lanes.  One memory round trip instead of G dependent ones.
+__device__ __forceinline__ int coef_lanes(int k) {
+    int L = 16;
+    while (L > 1 && L * k > NCONS) L >>= 1;
+    return L;
+}
+__device__ __forceinline__ double partial_lane_sum(const double* P, int G, int stride, int l, int L) {
+    double a = 0.0;
+    int g = l;
+    for (; g + 3 * L < G; g += 4 * L) {
+        const double t0 = __ldcg(P + (size_t)g * stride), t1 = __ldcg(P + (size_t)(g + L) * stride);
+        const double t2 = __ldcg(P + (size_t)(g + 2 * L) * stride), t3 = __ldcg(P + (size_t)(g + 3 * L) * stride);
+        a += t0; a += t1; a += t2; a += t3;
+    }
+    for (; g < G; g += L) a += __ldcg(P + (size_t)g * stride);
+    return a;
+}
+// all 32 lanes of the warp must call this (inactive columns pass valid = false)
+__device__ __forceinline__ double coef_colsum(const double* P, int G, int stride, int j, int l, int L,
+                                              bool valid) {
+    double a = valid ? partial_lane_sum(P + j, G, stride, l, L) : 0.0;
+    for (int o = L >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
+
 // ---------------------------------------------------------------- producer ----
 template <typename T>
 __device__ __forceinline__ void producer_phase(const PhaseParams<T>& p, const ColList& cl,
@@ -215,17 +245,15 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
     double* red = reinterpret_cast<double*>(sm.raw + OFF_RED);
 
     if (UPDATE) {
-        // every CTA reduces the previous phase's partials itself, in CTA order
-        for (int j = tid; j < p.k; j += NCONS) {
-            double h;
-            if (p.coef_t) {
-                h = (double)p.coef_t[j];
-            } else {
-                const volatile double* src = p.coef + j;
-                h = 0.0;
-                for (int g = 0; g < p.coef_sets; ++g) h += src[(size_t)g * p.coef_stride];
-            }
-            cs[j] = p.alphac * (T)h;
+        // every CTA reduces the previous phase's partials itself (fixed order, see coef_colsum)
+        if (p.coef_t) {
+            for (int j = tid; j < p.k; j += NCONS) cs[j] = p.alphac * p.coef_t[j];
+        } else {
+            const int L = coef_lanes(p.k);
+            const int j = tid / L, l = tid % L;
+            const bool valid = j < p.k;
+            const double h = coef_colsum(p.coef, p.coef_sets, p.coef_stride, j, l, L, valid);
+            if (valid && l == 0) cs[j] = p.alphac * (T)h;
         }
         named_bar_sync(1, NCONS);
     }
