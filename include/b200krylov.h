@@ -180,6 +180,12 @@ int32_t b2k_op_apply_adjoint(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec 
 int32_t b2k_op_apply_dot(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec y, b2k_vec v,
                          double* dot);
 
+/* One conjugate-gradient iteration (src/linsolve/cg.jl:62-67) with one host round trip:
+ * p <- beta*p + r; q <- (a0 + a1*A) p fused with <p,q>; alpha = rho/<p,q> (on the device);
+ * x += alpha*p; r -= alpha*q; returns <p,q> and ||r||.  beta = 0 is the first iteration (p = r). */
+int32_t b2k_cg_step(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec p, b2k_vec q,
+                    double a0, double a1, double beta, double rho, double* pq_out, double* normr_out);
+
 /* ---------------------------------------------- basis (OrthonormalBasis) ---- */
 /* project!!(y, b, x, alpha, beta, r): h[j] = beta*h[j] + alpha*<b[cols[j]], x>
  * — src/orthonormal.jl:88-118.  h is a HOST vector (orthonormal.jl:374, arnoldi.jl:212). */

@@ -10,7 +10,7 @@ B200Context does, and fails loudly without one (no CPU fallback).
 """
 from . import _lib
 from ._lib import B200Error, DimensionMismatch, LibraryMissing
-from .algorithms import (Arnoldi, ClassicalGramSchmidt, ClassicalGramSchmidt2,
+from .algorithms import (Arnoldi, CG, ClassicalGramSchmidt, ClassicalGramSchmidt2,
                          ClassicalGramSchmidtIR, ConvergenceInfo, GKL, GMRES, KrylovDefaults,
                          Lanczos, ModifiedGramSchmidt, ModifiedGramSchmidt2,
                          ModifiedGramSchmidtIR, Orthogonalizer, cgs, cgs2, cgsr, mgs, mgs2, mgsr)

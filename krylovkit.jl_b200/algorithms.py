@@ -114,6 +114,14 @@ class GMRES:
     verbosity: int = KrylovDefaults.verbosity
 
 
+@dataclass(frozen=True)
+class CG:
+    """src/algorithms.jl:344-355."""
+    maxiter: int = KrylovDefaults.maxiter
+    tol: float = KrylovDefaults.tol
+    verbosity: int = KrylovDefaults.verbosity
+
+
 @dataclass
 class ConvergenceInfo:
     """src/KrylovKit.jl:212-218.  numops = operator applications, numiter = restart cycles."""

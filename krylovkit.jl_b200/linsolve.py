@@ -7,7 +7,7 @@ import warnings
 
 import numpy as np
 
-from .algorithms import ConvergenceInfo, GMRES, WARN_LEVEL
+from .algorithms import CG, ConvergenceInfo, GMRES, WARN_LEVEL
 from .dense import givens, ldiv_upper
 from .factorizations import arnoldi as ar
 from .operators import B200CSR, apply
@@ -27,6 +27,12 @@ def linsolve(A, b, x0=None, alg: GMRES | None = None, a0: float = 0.0, a1: float
     KrylovKit's tol = max(atol, rtol*‖b‖) (linsolve.jl:159-161)."""
     if alg is None:
         alg = GMRES(**kwargs)
+    if isinstance(alg, CG):
+        if not isinstance(b, B200Vec):
+            raise TypeError("linsolve(CG): pass device vectors (B200Vec)")
+        if atol is not None or rtol is not None:
+            alg = CG(maxiter=alg.maxiter, tol=max(atol or 0.0, (rtol or 0.0) * b.norm()), verbosity=alg.verbosity)
+        return _cg(A, b, x0 if x0 is not None else b.zerovector(), alg, a0, a1)
     if not isinstance(b, B200Vec):
         return _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol)
     if atol is not None or rtol is not None:
@@ -151,3 +157,63 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
             return x, ConvergenceInfo(0, r, beta, numiter, numops)
         it = ar.ArnoldiIterator(operator, r, alg.orth)
         fact = ar.initialize_(it, fact)
+
+
+USE_FUSED_CG = True      # b2k_cg_step (one host round trip per iteration) for device CSR operators
+
+
+def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
+    """linsolve(operator, b, x₀, alg::CG, a₀, a₁) — src/linsolve/cg.jl:1-103 (SURVEY §8f-2)."""
+    import ctypes as C
+    y0 = apply(operator, x0)
+    r = b.copy()
+    if a0 != 0:
+        r = r.add_(x0, -a0)
+    r = r.add_(y0, -a1)
+    x = x0.copy()
+    normr = r.norm()
+    maxiter, tol = alg.maxiter, alg.tol
+    numops, numiter = 1, 0
+    if normr < tol:
+        return x, ConvergenceInfo(1, r, normr, numiter, numops)
+    ctx = b.ctx
+    fused = USE_FUSED_CG and isinstance(operator, B200CSR)
+    rho = normr ** 2
+    p = r.zerovector()
+    q = r.zerovector() if fused else None
+    beta = 0.0           # first iteration: p = r  (cg.jl:35)
+    first = True
+    while True:
+        if fused:
+            pq, nr = C.c_double(), C.c_double()
+            ctx.check(ctx.lib.b2k_cg_step(ctx.h, operator.h, x.handle, r.handle, p.handle, q.handle, a0, a1,
+                                          beta, rho, C.byref(pq), C.byref(nr)))
+            normr = nr.value
+        else:
+            p = p.scale_(1.0, r) if first else p.add_(r, 1.0, beta)      # cg.jl:35 / :63
+            q = apply(operator, p, a0, a1)
+            alpha = rho / p.inner(q)
+            x = x.add_(p, alpha)
+            r = r.add_(q, -alpha)
+            normr = r.norm()
+        if not first and normr < tol:
+            # recompute to account for buildup of floating point errors — cg.jl:69-73
+            r = r.scale_(1.0, b)
+            r = r.add_(apply(operator, x, a0, a1), -1.0)
+            normr = r.norm()
+            rho = normr ** 2
+            beta = 0.0
+        else:
+            rhoold = rho
+            rho = normr ** 2
+            beta = rho / rhoold
+        first = False
+        numops += 1
+        numiter += 1
+        if normr < tol:
+            return x, ConvergenceInfo(1, r, normr, numiter, numops)
+        if numiter >= maxiter:
+            if alg.verbosity >= WARN_LEVEL:
+                warnings.warn(f"CG linsolve stopped without converging after {numiter} iterations: "
+                              f"normres = {normr}, numops = {numops}")
+            return x, ConvergenceInfo(0, r, normr, numiter, numops)

@@ -735,6 +735,58 @@ def linsolve_gmres(A, b, x0=None, krylovdim=30, maxiter=100, tol=1e-12, orth: Or
         f = arnoldi_initialize_inplace(A, r, f, orth)
 
 
+def linsolve_cg(A, b, x0=None, maxiter=100, tol=1e-12, a0=0.0, a1=1.0):
+    """linsolve(operator, b, x₀, ::CG, a₀, a₁) — src/linsolve/cg.jl:1-103."""
+    if x0 is None:
+        x0 = np.zeros_like(b)
+    y0 = apply(A, x0)
+    r = b * 1.0
+    if a0 != 0:
+        r = r - a0 * x0
+    r = r - a1 * y0
+    x = x0 * 1.0
+    normr = norm(r)
+    numops, numiter = 1, 0
+    if normr < tol:
+        return x, dict(converged=1, residual=r, normres=normr, numiter=numiter, numops=numops)
+    rho = normr ** 2
+    p = r * 1.0
+    q = apply(A, p, a0, a1)
+    alpha = rho / inner(p, q)
+    x = x + alpha * p
+    r = r - alpha * q
+    normr = norm(r)
+    rhoold = rho
+    rho = normr ** 2
+    beta = rho / rhoold
+    numops += 1
+    numiter += 1
+    if normr < tol:
+        return x, dict(converged=1, residual=r, normres=normr, numiter=numiter, numops=numops)
+    while True:
+        p = beta * p + r
+        q = apply(A, p, a0, a1)
+        alpha = rho / inner(p, q)
+        x = x + alpha * p
+        r = r - alpha * q
+        normr = norm(r)
+        if normr < tol:
+            r = b - apply(A, x, a0, a1)
+            normr = norm(r)
+            rho = normr ** 2
+            beta = 0.0
+        else:
+            rhoold = rho
+            rho = normr ** 2
+            beta = rho / rhoold
+        numops += 1
+        numiter += 1
+        if normr < tol:
+            return x, dict(converged=1, residual=r, normres=normr, numiter=numiter, numops=numops)
+        if numiter >= maxiter:
+            return x, dict(converged=0, residual=r, normres=normr, numiter=numiter, numops=numops)
+
+
 # ------------------------------------------------------------------ GKL / svdsolve --------
 
 @dataclass

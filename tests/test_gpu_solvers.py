@@ -272,3 +272,37 @@ def test_block_primitives_gpu():
     np.testing.assert_allclose(Qz @ R[ogood, :], Zh, atol=1e-8)
     np.testing.assert_allclose(R[ogood, :], oR, rtol=1e-8, atol=1e-8)
     ctx.close()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_cg_matches_oracle(fused):
+    """conjugate gradients (src/linsolve/cg.jl) — fused one-sync step and the literal
+    VectorInterface mirror against the oracle: same iteration count, same solution."""
+    import importlib
+    ls = importlib.import_module("krylovkit_jl_b200.linsolve")
+    nx, ny = 70, 45
+    n = nx * ny
+    A = ko.stencil_matrix(nx, ny)
+    b = A @ np.ones(n)
+    ls.USE_FUSED_CG = fused
+    ctx = kk.B200Context(n, 16)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    for (a0, a1) in ((0.0, 1.0), (0.3, 1.5)):
+        alg = kk.CG(maxiter=1000, tol=1e-10, verbosity=0)
+        x, info = kk.linsolve(op, ctx.from_host(b), None, alg, a0, a1)
+        ox, oinfo = ko.linsolve_cg(A, b, None, maxiter=1000, tol=1e-10, a0=a0, a1=a1)
+        assert info.converged == 1 and oinfo["converged"] == 1
+        assert abs(info.numiter - oinfo["numiter"]) <= 1 and info.numops == info.numiter + 1
+        xh = x.to_host()
+        np.testing.assert_allclose(xh, ox, rtol=1e-8, atol=1e-9)
+        assert np.linalg.norm(a0 * xh + a1 * (A @ xh) - b) < 1e-8
+        np.testing.assert_allclose(info.residual.to_host(), b - (a0 * xh + a1 * (A @ xh)), atol=1e-9)
+    # non-converged, fixed iterations: residual identity b - A x = r
+    alg = kk.CG(maxiter=7, tol=1e-14, verbosity=0)
+    x, info = kk.linsolve(op, ctx.from_host(b), None, alg)
+    ox, oinfo = ko.linsolve_cg(A, b, None, maxiter=7, tol=1e-14)
+    assert info.converged == 0 and info.numiter == 7
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(info.normres, oinfo["normres"], rtol=1e-9)
+    ls.USE_FUSED_CG = True
+    ctx.close()

@@ -281,3 +281,21 @@ def test_stencil_spectrum_and_splitmix():
     x = ko.splitmix_vector(1, 1000)
     assert 0 <= x.min() and x.max() < 1 and abs(x.mean() - 0.5) < 0.05
     assert np.array_equal(ko.splitmix_vector(1, 10, offset=5), ko.splitmix_vector(1, 15)[5:])
+
+
+def test_cg_oracle():
+    """test/linsolve.jl:1-117 (CG): b = A x for SPD A, shifted operator, numops = numiter + 1."""
+    rng = np.random.default_rng(11)
+    n = 100
+    B = rng.standard_normal((n, n))
+    A = B @ B.T / n + np.eye(n)
+    b = rng.standard_normal(n)
+    x, info = ko.linsolve_cg(A, b, maxiter=10 * n, tol=1e-12 * np.linalg.norm(b))
+    assert info["converged"] == 1 and info["numops"] == info["numiter"] + 1
+    np.testing.assert_allclose(A @ x, b, atol=1e-9)
+    x, info = ko.linsolve_cg(A, b, maxiter=10 * n, tol=1e-10, a0=0.4, a1=1.7)
+    assert info["converged"] == 1
+    np.testing.assert_allclose(0.4 * x + 1.7 * (A @ x), b, atol=1e-8)
+    x, info = ko.linsolve_cg(A, b, maxiter=3, tol=1e-14)
+    assert info["converged"] == 0 and info["numiter"] == 3
+    np.testing.assert_allclose(b - A @ x, info["residual"], atol=1e-10)
