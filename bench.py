@@ -160,8 +160,13 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     A = ko.stencil_matrix(a.nx, a.ny)
     nsteps = a.cpu_steps
-    for _ in range(min(a.warmup, 1)):
-        cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, min(nsteps, 4), A)
+    # one short untimed sample (also the warm-up): sizes the per-step sample so that the whole
+    # --steps K run stays within ~4 minutes whatever K the driver passes (the cost of an expand!
+    # step grows with the basis size, hence the factor 2.5)
+    _, dt_w, ops_w = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, 4, A)
+    budget_s = 220.0
+    est = 2.5 * dt_w / ops_w
+    nsteps = int(max(5, min(nsteps, budget_s / max(1, a.steps) / est)))
     t_tot, ops_tot = 0.0, 0
     for _ in range(a.steps):
         v, dt, ops = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, nsteps, A)

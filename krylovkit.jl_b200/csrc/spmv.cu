@@ -5,7 +5,7 @@
 // CSR SpMV design ("CSR-stream"): the matrices of the configs have ~5-7 nonzeros per
 // row, so a warp-per-row kernel would idle most lanes and a thread-per-row kernel reads
 // vals/colidx with a 40-56 B stride.  Instead a CTA owns a run of consecutive rows whose
-// nonzeros fit a 2048-entry shared-memory tile: the nonzero stream (vals, colidx) is read
+// nonzeros fit a 1536-entry shared-memory tile: the nonzero stream (vals, colidx) is read
 // fully coalesced, multiplied with the gathered x (L1/L2-served: the band structure keeps
 // the working set of x tiny), parked in shared memory, then each thread sums the products
 // of its row(s) in CSR order.  Products are rounded before summation and summed in
@@ -137,7 +137,7 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 
 
 // ---------------------------------------------------------------------------------------
-// Pipelined CSR-stream SpMV (the default): persistent CTAs (2 per SM), a producer warp
+// Pipelined CSR-stream SpMV (the default): persistent CTAs (3 per SM), a producer warp
 // streams each row block's nonzeros (vals, colidx) and its rowptr segment into a 3-stage
 // shared-memory ring with 1-D TMA bulk copies (UBLKCP) signalled on mbarriers; the 8
 // consumer warps gather x, multiply in place, and sum rows out of shared memory while the

@@ -306,3 +306,31 @@ def test_cg_matches_oracle(fused):
     np.testing.assert_allclose(info.normres, oinfo["normres"], rtol=1e-9)
     ls.USE_FUSED_CG = True
     ctx.close()
+
+
+def test_invariant_subspace_early_exit():
+    """eigsolve/lanczos.jl:38-44, 45: beta <= tol stops the expansion loop early (also inside
+    b2k_lanczos_expand_many) and reports the exact eigenvalues of the invariant subspace."""
+    n = 3000
+    d = np.repeat([1.0, 2.5, 7.0], n // 3)
+    A = sp.diags(d).tocsr()
+    x0 = ko.splitmix_vector(5, n) + 0.5
+    alg = kk.Lanczos(orth=kk.cgs2, krylovdim=20, maxiter=5, tol=1e-9, verbosity=0)
+    ctx = kk.B200Context(n, 40)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0), 3, "SR", alg)
+    ovals, _, oinfo = ko.eigsolve_lanczos(A, x0, 3, "SR", krylovdim=20, maxiter=5, tol=1e-9, orth=ko.Orth(ko.CGS2))
+    assert info.numops == oinfo["numops"] == 3          # the Krylov space is exhausted after 3 vectors
+    assert info.converged == 3
+    np.testing.assert_allclose(vals, [1.0, 2.5, 7.0], rtol=1e-12)
+    np.testing.assert_allclose(vals, ovals, rtol=1e-12)
+    ctx.close()
+
+
+def test_zero_start_vector_raises():
+    """lanczos.jl:184: ArgumentError("initial vector should not have norm zero")."""
+    ctx = kk.B200Context(100, 16)
+    op = kk.B200CSR.stencil(ctx, 10, 10)
+    with pytest.raises(ValueError):
+        kk.eigsolve(op, ctx.zeros(), 1, "SR", kk.Lanczos(krylovdim=5, verbosity=0))
+    ctx.close()
