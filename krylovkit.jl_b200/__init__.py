@@ -10,9 +10,9 @@ B200Context does, and fails loudly without one (no CPU fallback).
 """
 from . import _lib
 from ._lib import B200Error, DimensionMismatch, LibraryMissing
-from .algorithms import (Arnoldi, CG, ClassicalGramSchmidt, ClassicalGramSchmidt2,
+from .algorithms import (Arnoldi, BiCGStab, CG, ClassicalGramSchmidt, ClassicalGramSchmidt2,
                          ClassicalGramSchmidtIR, ConvergenceInfo, GKL, GMRES, KrylovDefaults,
-                         Lanczos, ModifiedGramSchmidt, ModifiedGramSchmidt2,
+                         Lanczos, LSMR, ModifiedGramSchmidt, ModifiedGramSchmidt2,
                          ModifiedGramSchmidtIR, Orthogonalizer, cgs, cgs2, cgsr, mgs, mgs2, mgsr)
 from .operators import B200CSR, B200Dense, B200Operator, apply, apply_adjoint, apply_normal
 from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, orthonormalize_,
@@ -22,6 +22,7 @@ from .vectors import B200Context, B200Vec, inner, norm
 __all__ = [n for n in dir() if not n.startswith("_")]
 from .eigsolve import eigsolve
 from .linsolve import linsolve
+from .lssolve import lssolve
 from .svdsolve import svdsolve
 from . import factorizations
 

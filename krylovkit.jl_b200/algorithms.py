@@ -122,6 +122,25 @@ class CG:
     verbosity: int = KrylovDefaults.verbosity
 
 
+@dataclass(frozen=True)
+class BiCGStab:
+    """src/algorithms.jl:457-481."""
+    maxiter: int = KrylovDefaults.maxiter
+    tol: float = KrylovDefaults.tol
+    verbosity: int = KrylovDefaults.verbosity
+
+
+@dataclass(frozen=True)
+class LSMR:
+    """src/algorithms.jl:483-521.  `krylovdim` = how many recent right vectors the next one is
+    reorthogonalised against; the default orthogonalizer is plain MGS (:517)."""
+    orth: Orthogonalizer = mgs
+    maxiter: int = KrylovDefaults.maxiter
+    krylovdim: int = KrylovDefaults.krylovdim
+    tol: float = KrylovDefaults.tol
+    verbosity: int = KrylovDefaults.verbosity
+
+
 @dataclass
 class ConvergenceInfo:
     """src/KrylovKit.jl:212-218.  numops = operator applications, numiter = restart cycles."""

@@ -7,7 +7,7 @@ import warnings
 
 import numpy as np
 
-from .algorithms import CG, ConvergenceInfo, GMRES, WARN_LEVEL
+from .algorithms import BiCGStab, CG, ConvergenceInfo, GMRES, WARN_LEVEL
 from .dense import givens, ldiv_upper
 from .factorizations import arnoldi as ar
 from .operators import B200CSR, apply
@@ -33,6 +33,13 @@ def linsolve(A, b, x0=None, alg: GMRES | None = None, a0: float = 0.0, a1: float
         if atol is not None or rtol is not None:
             alg = CG(maxiter=alg.maxiter, tol=max(atol or 0.0, (rtol or 0.0) * b.norm()), verbosity=alg.verbosity)
         return _cg(A, b, x0 if x0 is not None else b.zerovector(), alg, a0, a1)
+    if isinstance(alg, BiCGStab):
+        if not isinstance(b, B200Vec):
+            raise TypeError("linsolve(BiCGStab): pass device vectors (B200Vec)")
+        if atol is not None or rtol is not None:
+            alg = BiCGStab(maxiter=alg.maxiter, tol=max(atol or 0.0, (rtol or 0.0) * b.norm()),
+                           verbosity=alg.verbosity)
+        return _bicgstab(A, b, x0 if x0 is not None else b.zerovector(), alg, a0, a1)
     if not isinstance(b, B200Vec):
         return _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol)
     if atol is not None or rtol is not None:
@@ -215,5 +222,80 @@ def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
         if numiter >= maxiter:
             if alg.verbosity >= WARN_LEVEL:
                 warnings.warn(f"CG linsolve stopped without converging after {numiter} iterations: "
+                              f"normres = {normr}, numops = {numops}")
+            return x, ConvergenceInfo(0, r, normr, numiter, numops)
+
+
+def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: float):
+    """linsolve(operator, b, x₀, alg::BiCGStab, a₀, a₁) — src/linsolve/bicgstab.jl:1-203
+    (SURVEY §8f-2).  Real arithmetic only (the library has no complex dtype).  The reference
+    spells its first iteration out ahead of the loop; here one loop serves both, `p is None`
+    marking the first pass, including its quirk that `maxiter` is only looked at from the
+    second iteration on."""
+    y0 = apply(operator, x0)
+    r = b.copy()
+    if a0 != 0:
+        r = r.add_(x0, -a0)
+    r = r.add_(y0, -a1)
+    del y0
+    x = x0.copy()
+    normr = r.norm()
+    maxiter, tol = alg.maxiter, alg.tol
+    numops, numiter = 1, 0
+    if normr < tol:
+        return x, ConvergenceInfo(1, r, normr, numiter, numops)
+    r_shadow = r.copy()
+    rho = alpha = omega = 1.0
+    p = v = None
+    s, xhalf = r.zerovector(), x.zerovector()
+    while True:
+        numiter += 1
+        rhoold, rho = rho, r_shadow.inner(r)
+        if p is None:
+            if rho == 0.0:                       # `ρ ≈ 0.0` (bicgstab.jl:36): the method breaks down
+                if alg.verbosity >= WARN_LEVEL:
+                    warnings.warn("BiCGStab linsolve errored after 1 iteration: rho = 0")
+                return x, ConvergenceInfo(0, r, normr, numiter, numops)
+            p = r.copy()
+        else:
+            beta = (rho / rhoold) * (alpha / omega)
+            p = p.add_(v, -omega)
+            p = p.add_(r, 1.0, beta)
+        v = apply(operator, p, a0, a1)
+        numops += 1
+        sigma = r_shadow.inner(v)
+        alpha = rho / sigma
+        s = s.scale_(1.0, r)
+        s = s.add_(v, -alpha)                    # half step residual
+        xhalf = xhalf.scale_(1.0, x)
+        xhalf = xhalf.add_(p, alpha)             # half step iterate
+        normr = s.norm()
+        if normr < tol:
+            # replace the recurrence residual by the actual one before trusting it
+            s = s.scale_(1.0, b)
+            s = s.add_(apply(operator, xhalf, a0, a1), -1.0)
+            numops += 1
+            normr_act = s.norm()
+            if normr_act < tol:
+                return xhalf, ConvergenceInfo(1, s, normr_act, numiter, numops)
+        t = apply(operator, s, a0, a1)
+        numops += 1
+        omega = t.inner(s) / t.inner(t)
+        x = x.scale_(1.0, xhalf)
+        x = x.add_(s, omega)                     # full step iterate
+        r = r.scale_(1.0, s)
+        r = r.add_(t, -omega)                    # full step residual
+        del t
+        normr = r.norm()
+        if normr < tol:
+            r = r.scale_(1.0, b)
+            r = r.add_(apply(operator, x, a0, a1), -1.0)
+            numops += 1
+            normr_act = r.norm()
+            if normr_act < tol:
+                return x, ConvergenceInfo(1, r, normr_act, numiter, numops)
+        if numiter > 1 and numiter >= maxiter:
+            if alg.verbosity >= WARN_LEVEL:
+                warnings.warn(f"BiCGStab linsolve stopped without converging after {numiter} iterations: "
                               f"normres = {normr}, numops = {numops}")
             return x, ConvergenceInfo(0, r, normr, numiter, numops)

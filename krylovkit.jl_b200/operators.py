@@ -33,6 +33,11 @@ class B200Operator:
     def free(self):
         self._fin()
 
+    def with_spaces(self, space_in: int, space_out: int):
+        """Rectangular operators: name the vector spaces of x and y in y = A x."""
+        self.space_in, self.space_out = space_in, space_out
+        return self
+
     # y = A x into an existing vector (y must not alias x)
     def apply_into(self, y: B200Vec, x: B200Vec) -> B200Vec:
         self.ctx.check(self.ctx.lib.b2k_op_apply(self.ctx.h, self.h, x.handle, y.handle))
@@ -153,7 +158,7 @@ def apply(op, x: B200Vec, a0: float = 0.0, a1: float = 1.0) -> B200Vec:
     """apply(operator, x[, α₀, α₁]) — src/apply.jl:1-11.  `op` is a B200Operator or any
     callable x -> y on B200Vec (the abstract-linear-map contract)."""
     if isinstance(op, B200Operator):
-        y = x.ctx.empty(op.space_out if isinstance(op, B200Dense) else x.space)
+        y = x.ctx.empty(op.space_out if (isinstance(op, B200Dense) or op.n_rows != op.n_cols) else x.space)
         if a0 != 0.0 or a1 != 1.0:
             x.ctx.check(x.ctx.lib.b2k_op_apply_shifted(x.ctx.h, op.h, x.handle, y.handle,
                                                        float(a0), float(a1)))

@@ -787,6 +787,143 @@ def linsolve_cg(A, b, x0=None, maxiter=100, tol=1e-12, a0=0.0, a1=1.0):
             return x, dict(converged=0, residual=r, normres=normr, numiter=numiter, numops=numops)
 
 
+def linsolve_bicgstab(A, b, x0=None, maxiter=100, tol=1e-12, a0=0.0, a1=1.0):
+    """linsolve(operator, b, x₀, ::BiCGStab, a₀, a₁) — src/linsolve/bicgstab.jl:1-203.
+    The reference unrolls the first iteration (:32-93) ahead of its `while true` (:95-201);
+    the two bodies differ only in how p is formed, so one loop with a flag restates both."""
+    if x0 is None:
+        x0 = np.zeros_like(b)
+    info = lambda c, res, nr, it, ops: dict(converged=c, residual=res, normres=nr, numiter=it, numops=ops)
+    y0 = apply(A, x0)
+    r = b * 1.0                                        # :8-10
+    if a0 != 0:
+        r = r - a0 * x0
+    r = r - a1 * y0
+    x = x0 * 1.0
+    normr = norm(r)
+    numops, numiter = 1, 0
+    if normr < tol:                                    # :22
+        return x, info(1, r, normr, numiter, numops)
+    r_shadow = r * 1.0                                 # :32
+    rho = alpha = omega = 1.0
+    p = v = None
+    while True:
+        numiter += 1
+        rhoold, rho = rho, inner(r_shadow, r)          # :33 / :97-98
+        if p is None:
+            if rho == 0.0:                             # `ρ ≈ 0.0` with default tolerances is ρ == 0 (:36)
+                return x, info(0, r, normr, numiter, numops)
+            p = r * 1.0                                # :44
+        else:
+            beta = (rho / rhoold) * (alpha / omega)    # :99
+            p = p - omega * v                          # :101-102
+            p = beta * p + r
+        v = apply(A, p, a0, a1)                        # :45 / :104
+        numops += 1
+        sigma = inner(r_shadow, v)
+        alpha = rho / sigma
+        s = r - alpha * v                              # half step residual
+        xhalf = x + alpha * p                          # half step iterate
+        normr = norm(s)
+        if normr < tol:                                # :60-72 / :118-135 — check the ACTUAL residual
+            s = b - apply(A, xhalf, a0, a1)            # s is overwritten whether or not it passes
+            numops += 1
+            normr_act = norm(s)
+            if normr_act < tol:
+                return xhalf, info(1, s, normr_act, numiter, numops)
+        t = apply(A, s, a0, a1)                        # :75 / :141
+        numops += 1
+        omega = inner(t, s) / inner(t, t)
+        x = xhalf + omega * s                          # full step
+        r = s - omega * t
+        normr = norm(r)
+        if normr < tol:                                # :87-100 / :153-169
+            r = b - apply(A, x, a0, a1)                # r is overwritten whether or not it passes
+            numops += 1
+            normr_act = norm(r)
+            if normr_act < tol:
+                return x, info(1, r, normr_act, numiter, numops)
+        if numiter > 1 and numiter >= maxiter:         # :170 — inside the while loop only
+            return x, info(0, r, normr, numiter, numops)
+
+
+def lssolve_lsmr(A, b, maxiter=100, krylovdim=30, tol=1e-12, orth: "Orth | None" = None, lam=0.0):
+    """lssolve(operator, b, ::LSMR, λ) — src/lssolve/lsmr.jl:1-162.  Minimises
+    ‖b − A x‖² + λ²‖x‖² by Golub-Kahan bidiagonalisation with two layers of plane rotations; the last
+    `krylovdim` right vectors are kept in a ring (slot order, not age, defines the sweep order) and v
+    is reorthogonalised against them (:75-88).  info.normres = |ζ̄| estimates ‖Aᴴ r − λ² x‖."""
+    if orth is None:
+        orth = Orth(MGS)                               # algorithms.jl:517
+    info = lambda c, res, nr, it, ops: dict(converged=c, residual=res, normres=nr, numiter=it, numops=ops)
+    u = b * 1.0
+    v = apply_adjoint(A, b) * 1.0
+    beta = norm(u)
+    u = u / beta
+    v = v / beta
+    alpha = norm(v)
+    v = v / alpha
+    V = [v]
+    K = krylovdim
+    Vv = np.zeros(K)
+    alphabar, zetabar = alpha, alpha * beta
+    rho, theta, rhobar, cbar, sbar = 1.0, 0.0, 1.0, 1.0, 0.0
+    abszetabar = abs(zetabar)
+    x = np.zeros_like(v)
+    h = v * 1.0
+    hbar = np.zeros_like(v)
+    r = u * beta
+    Ah = np.zeros_like(u)
+    Ahbar = np.zeros_like(u)
+    numiter, numops = 0, 1
+    if abszetabar < tol:
+        return x, info(1, r, abszetabar, numiter, numops)
+    while True:
+        numiter += 1
+        Av = apply_normal(A, v)
+        numops += 1
+        Ah = Av - (theta / rho) * Ah                   # :64  Ah ← Av − θ/ρ·Ah
+        u = Av - alpha * u                             # :67  (Av is consumed)
+        beta = norm(u)
+        if beta > tol:
+            u = u / beta
+            v = apply_adjoint(A, u) - beta * v         # :72
+            numops += 1
+            if K > 1:
+                v, _ = orthogonalize(v, V, Vv[:min(K, numiter)], orth)
+            alpha = norm(v)
+            if alpha > tol:
+                v = v / alpha
+                if numiter < K:
+                    V.append(v)
+                else:
+                    V[numiter % K] = v                 # mod1(numiter + 1, K), 1-based
+        alphahat = math.hypot(alphabar, lam)           # rotation P̂ (regularisation)
+        rhoold = rho
+        rho = math.hypot(alphahat, beta)               # rotation P: B → R
+        c, s_ = alphahat / rho, beta / rho
+        theta = s_ * alpha
+        alphabar = c * alpha
+        rhobarold = rhobar                             # rotation P̄: Rᵀ → R̄
+        thetabar = sbar * rho
+        cbarrho = cbar * rho
+        rhobar = math.hypot(cbarrho, theta)
+        cbar = cbarrho / rhobar
+        sbar = theta / rhobar
+        zeta = cbar * zetabar
+        zetabar = -sbar * zetabar
+        g = -thetabar * rho / (rhoold * rhobarold)
+        hbar = h + g * hbar
+        Ahbar = Ah + g * Ahbar
+        x = x + (zeta / (rho * rhobar)) * hbar
+        r = r - (zeta / (rho * rhobar)) * Ahbar
+        h = v - (theta / rho) * h
+        abszetabar = abs(zetabar)
+        if abszetabar <= tol:
+            return x, info(1, r, abszetabar, numiter, numops)
+        if numiter >= maxiter:
+            return x, info(0, r, abszetabar, numiter, numops)
+
+
 # ------------------------------------------------------------------ GKL / svdsolve --------
 
 @dataclass

@@ -308,6 +308,113 @@ def test_cg_matches_oracle(fused):
     ctx.close()
 
 
+def test_bicgstab_matches_oracle_and_reference_properties():
+    """BiCGStab (src/linsolve/bicgstab.jl) on a nonsymmetric sparse operator — the
+    properties test/linsolve.jl:287-403 checks (converged, b = (a0 + a1 A) x, warm restart costs one
+    operator application, non-converged run satisfies b = A x + r) plus step-for-step agreement
+    with the oracle."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    # convection-diffusion-like: 1-D Laplacian + skew part, diagonally dominant
+    A = (sp.diags([-1.3, 2.6, -0.7], [-1, 0, 1], shape=(n, n)) +
+         sp.random(n, n, density=2e-3, random_state=3) * 0.05).tocsr()
+    b = rng.random(n)
+    tol = 1e-12 * np.linalg.norm(b)
+    ctx = kk.B200Context(n, 20)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    for (a0, a1) in ((0.0, 1.0), (1.4, 0.6)):
+        alg = kk.BiCGStab(maxiter=4 * n, tol=tol, verbosity=0)
+        x, info = kk.linsolve(op, ctx.from_host(b), None, alg, a0, a1)
+        ox, oinfo = ko.linsolve_bicgstab(A, b, None, maxiter=4 * n, tol=tol, a0=a0, a1=a1)
+        assert info.converged == 1 and oinfo["converged"] == 1
+        assert abs(info.numiter - oinfo["numiter"]) <= 1
+        xh = x.to_host()
+        np.testing.assert_allclose(xh, ox, rtol=1e-8, atol=1e-10)
+        assert np.linalg.norm(a0 * xh + a1 * (A @ xh) - b) < 10 * tol
+        np.testing.assert_allclose(info.residual.to_host(), b - (a0 * xh + a1 * (A @ xh)), atol=1e-11)
+        # restart from the solution: one application, immediately converged (linsolve.jl:328-332)
+        x2, info2 = kk.linsolve(op, ctx.from_host(b), x, alg, a0, a1)
+        assert info2.numops == 1 and info2.converged == 1
+    # fixed, too small iteration budget: identical iterates and the residual identity (:360-366)
+    alg = kk.BiCGStab(maxiter=3, tol=1e-300, verbosity=0)
+    x, info = kk.linsolve(op, ctx.from_host(b), None, alg)
+    ox, oinfo = ko.linsolve_bicgstab(A, b, None, maxiter=3, tol=1e-300)
+    assert info.converged == 0 and info.numiter == 3 == oinfo["numiter"] and info.numops == oinfo["numops"]
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(A @ x.to_host() + info.residual.to_host(), b, atol=1e-12)
+    # maxiter is first consulted in the second iteration (bicgstab.jl:170 sits inside the loop)
+    x, info = kk.linsolve(op, ctx.from_host(b), None, kk.BiCGStab(maxiter=1, tol=1e-300, verbosity=0))
+    assert info.numiter == 2
+    # f32
+    ctx32 = kk.B200Context(n, 20, dtype=np.float32)
+    op32 = kk.B200CSR.from_scipy(ctx32, A.astype(np.float32))
+    b32 = b.astype(np.float32)
+    x, info = kk.linsolve(op32, ctx32.from_host(b32), None,
+                          kk.BiCGStab(maxiter=4 * n, tol=1e-5 * float(np.linalg.norm(b32)), verbosity=0))
+    assert info.converged == 1
+    assert np.linalg.norm(A @ x.to_host().astype(np.float64) - b) < 1e-4 * np.linalg.norm(b)
+    ctx32.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("orth", ["mgs", "cgs2", "mgsr"])
+def test_lsmr_matches_oracle_and_reference_properties(orth):
+    """LSMR (src/lssolve/lsmr.jl) — test/lssolve.jl's assertions through the device
+    path (dense operator with two vector spaces, and a rectangular sparse (A, Aᵀ) pair), and
+    iterate-for-iterate agreement with the oracle including the sliding reorthogonalisation ring."""
+    o = getattr(kk, orth)
+    oo = ko.Orth(o.tag, o.eta) if o.is_ir else ko.Orth(o.tag)
+    rng = np.random.default_rng(21)
+    n, N = 10, 100
+    A = rng.random((2 * n, n))
+    U, S, Vt = np.linalg.svd(A, full_matrices=False)
+    invS = 1 / S
+    S[-1] = 0
+    invS[-1] = 0
+    A = U @ np.diag(S) @ Vt
+    b = rng.random(2 * n)
+    tol = 10 * n * np.finfo(float).eps
+    # host entry, no reorthogonalisation, three iterations
+    x, info = kk.lssolve(A, b, kk.LSMR(orth=o, maxiter=3, krylovdim=1, verbosity=0))
+    ox, oinfo = ko.lssolve_lsmr(A, b, maxiter=3, krylovdim=1, orth=oo)
+    r = b - A @ x
+    np.testing.assert_allclose(info.residual, r, atol=1e-13)
+    np.testing.assert_allclose(info.normres, np.linalg.norm(A.T @ r), rtol=1e-8)
+    assert info.converged == 0 and info.numops == oinfo["numops"] == 7
+    np.testing.assert_allclose(x, ox, rtol=1e-11, atol=1e-14)
+    # full reorthogonalisation: minimum-norm solution within n iterations
+    alg = kk.LSMR(orth=o, maxiter=n, tol=tol, krylovdim=n, verbosity=0)
+    x, info = kk.lssolve(A, b, alg)
+    assert info.converged > 0
+    assert abs(Vt[-1] @ x) < tol
+    np.testing.assert_allclose(x, Vt.T @ np.diag(invS) @ U.T @ b, rtol=1e-8)
+    lam = 0.37
+    x, info = kk.lssolve(A, b, alg, lam)
+    assert info.converged > 0
+    np.testing.assert_allclose(A.T @ (b - A @ x), lam ** 2 * x, atol=2 * tol)
+    # large problem, ring of 5 (exercises slot replacement), against the oracle
+    A = rng.random((2 * N, N)) - 0.5
+    b = rng.random(2 * N) - 0.5
+    tol = 10 * N * np.finfo(float).eps
+    x, info = kk.lssolve(A, b, kk.LSMR(orth=o, maxiter=N, tol=tol, krylovdim=5, verbosity=0))
+    ox, oinfo = ko.lssolve_lsmr(A, b, maxiter=N, tol=tol, krylovdim=5, orth=oo)
+    assert info.converged > 0 and abs(info.numiter - oinfo["numiter"]) <= 2
+    assert np.linalg.norm(A.T @ (b - A @ x)) < 5 * tol
+    np.testing.assert_allclose(x, ox, rtol=1e-8, atol=1e-11)
+    x12, info12 = kk.lssolve(A, b, kk.LSMR(orth=o, maxiter=12, tol=0.0, krylovdim=5, verbosity=0))
+    ox12, oinfo12 = ko.lssolve_lsmr(A, b, maxiter=12, tol=0.0, krylovdim=5, orth=oo)
+    np.testing.assert_allclose(x12, ox12, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(info12.normres, oinfo12["normres"], rtol=1e-8)
+    # sparse rectangular operator as an (A, Aᵀ) pair
+    As = sp.random(3000, 800, density=0.01, random_state=4).tocsr() + sp.eye(3000, 800).tocsr()
+    bs = rng.random(3000)
+    tol = 1e-10
+    x, info = kk.lssolve(As, bs, kk.LSMR(orth=o, maxiter=400, tol=tol, krylovdim=8, verbosity=0))
+    assert info.converged > 0
+    assert np.linalg.norm(As.T @ (bs - As @ x)) < 50 * tol
+    np.testing.assert_allclose(info.residual, bs - As @ x, atol=1e-10)
+
+
 def test_invariant_subspace_early_exit():
     """eigsolve/lanczos.jl:38-44, 45: beta <= tol stops the expansion loop early (also inside
     b2k_lanczos_expand_many) and reports the exact eigenvalues of the invariant subspace."""

@@ -299,3 +299,79 @@ def test_cg_oracle():
     x, info = ko.linsolve_cg(A, b, maxiter=3, tol=1e-14)
     assert info["converged"] == 0 and info["numiter"] == 3
     np.testing.assert_allclose(b - A @ x, info["residual"], atol=1e-10)
+
+
+def test_bicgstab_oracle():
+    """test/linsolve.jl:287-403 (BiCGStab), real scalar types: the small problem
+    A = I - 0.9 B/ρ(B) (converged, b ≈ A x, restart from x costs one operator application,
+    shifted operator), the large problem with maxiter = 2 (b ≈ (α₀ + α₁A) x + residual) and its
+    continuation to convergence."""
+    rng = np.random.default_rng(5)
+    n, N = 10, 100
+    B = rng.random((n, n)) - 0.5
+    A = np.eye(n) - 0.9 * B / np.max(np.abs(np.linalg.eigvals(B)))
+    b = rng.random(n)
+    tol = 1e-12 * np.linalg.norm(b)
+    x, info = ko.linsolve_bicgstab(A, b, maxiter=4 * n, tol=tol)
+    assert info["converged"] > 0
+    np.testing.assert_allclose(A @ x, b, rtol=1e-9)
+    _, info2 = ko.linsolve_bicgstab(A, b, x, maxiter=4 * n, tol=tol)
+    assert info2["numops"] == 1
+    a0, a1 = rng.random() + 1, rng.random()
+    x, info = ko.linsolve_bicgstab(A, b, maxiter=4 * n, tol=tol, a0=a0, a1=a1)
+    assert info["converged"] > 0
+    np.testing.assert_allclose(a0 * x + a1 * (A @ x), b, rtol=1e-9)
+
+    A = rng.random((N, N)) - 0.5
+    b = rng.random(N)
+    a0, a1 = np.max(np.abs(np.linalg.eigvals(A))), -0.9 * rng.random()
+    tol = 1e-12 * np.linalg.norm(b)
+    x, info = ko.linsolve_bicgstab(A, b, maxiter=2, tol=tol, a0=a0, a1=a1)
+    np.testing.assert_allclose(a0 * x + a1 * (A @ x) + info["residual"], b, rtol=1e-10)
+    assert info["converged"] == 0 and info["numiter"] == 2
+    x, info = ko.linsolve_bicgstab(A, b, x, maxiter=10 * N, tol=tol, a0=a0, a1=a1)
+    assert info["converged"] > 0
+    np.testing.assert_allclose(a0 * x + a1 * (A @ x), b, rtol=1e-9)
+    # agrees with a direct solve
+    np.testing.assert_allclose(x, np.linalg.solve(a0 * np.eye(N) + a1 * A, b), rtol=1e-8)
+    # breakdown: r_shadow ⟂ r cannot happen at the first step (ρ = ‖r‖²) unless r = 0, which
+    # returns before the loop with numops = 1
+    x, info = ko.linsolve_bicgstab(np.eye(3), np.zeros(3), maxiter=5, tol=1e-12)
+    assert info["converged"] == 1 and info["numops"] == 1 and info["numiter"] == 0
+
+
+def test_lsmr_oracle():
+    """test/lssolve.jl (LSMR), real scalar types: rank-deficient 2n×n problem — three iterations
+    without reorthogonalisation leave residual = b − A x and normres = ‖Aᵀ r‖; with krylovdim = n it
+    converges within n iterations to the minimum-norm solution V S⁺ Uᵀ b; with λ the regularised normal
+    equations hold; the 2N×N problem with a ring of 5 vectors converges."""
+    rng = np.random.default_rng(9)
+    n, N = 10, 100
+    A = rng.random((2 * n, n))
+    U, S, Vt = np.linalg.svd(A, full_matrices=False)
+    invS = 1 / S
+    S[-1] = 0
+    invS[-1] = 0
+    A = U @ np.diag(S) @ Vt
+    b = rng.random(2 * n)
+    tol = 10 * n * np.finfo(float).eps
+    x, info = ko.lssolve_lsmr(A, b, maxiter=3, krylovdim=1)
+    r = b - A @ x
+    np.testing.assert_allclose(info["residual"], r, rtol=1e-10)
+    np.testing.assert_allclose(info["normres"], np.linalg.norm(A.T @ r), rtol=1e-8)
+    assert info["converged"] == 0 and info["numops"] == 1 + 2 * 3
+    x, info = ko.lssolve_lsmr(A, b, maxiter=n, tol=tol, krylovdim=n)
+    assert info["converged"] > 0
+    assert abs(Vt[-1] @ x) < tol
+    np.testing.assert_allclose(x, Vt.T @ np.diag(invS) @ U.T @ b, rtol=1e-8)
+    lam = rng.random()
+    x, info = ko.lssolve_lsmr(A, b, maxiter=n, tol=tol, krylovdim=n, lam=lam)
+    assert info["converged"] > 0
+    np.testing.assert_allclose(A.T @ (b - A @ x), lam ** 2 * x, atol=2 * tol)
+    A = rng.random((2 * N, N)) - 0.5
+    b = rng.random(2 * N) - 0.5
+    tol = 10 * N * np.finfo(float).eps
+    x, info = ko.lssolve_lsmr(A, b, maxiter=N, tol=tol, krylovdim=5)
+    assert info["converged"] > 0
+    assert np.linalg.norm(A.T @ (b - A @ x)) < 5 * tol
+    np.testing.assert_allclose(x, np.linalg.lstsq(A, b, rcond=None)[0], rtol=1e-8)
