@@ -10,7 +10,7 @@ B200Context does, and fails loudly without one (no CPU fallback).
 """
 from . import _lib
 from ._lib import B200Error, DimensionMismatch, LibraryMissing
-from .algorithms import (Arnoldi, BiCGStab, CG, ClassicalGramSchmidt, ClassicalGramSchmidt2,
+from .algorithms import (Arnoldi, BiCGStab, BlockLanczos, CG, ClassicalGramSchmidt, ClassicalGramSchmidt2,
                          ClassicalGramSchmidtIR, ConvergenceInfo, GKL, GMRES, KrylovDefaults,
                          Lanczos, LSMR, ModifiedGramSchmidt, ModifiedGramSchmidt2,
                          ModifiedGramSchmidtIR, Orthogonalizer, cgs, cgs2, cgsr, mgs, mgs2, mgsr)
@@ -25,5 +25,6 @@ from .linsolve import linsolve
 from .lssolve import lssolve
 from .svdsolve import svdsolve
 from . import factorizations
+from .factorizations.blocklanczos import Block
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -86,6 +86,19 @@ class Lanczos:
 
 
 @dataclass(frozen=True)
+class BlockLanczos:
+    """src/algorithms.jl:152-171.  krylovdim defaults to KrylovDefaults.blockkrylovdim = 100;
+    `qr_tol` is the rank tolerance of block_qr!."""
+    orth: Orthogonalizer = field(default_factory=lambda: KrylovDefaults.orth)
+    krylovdim: int = 100
+    maxiter: int = KrylovDefaults.maxiter
+    tol: float = KrylovDefaults.tol
+    qr_tol: float = KrylovDefaults.tol
+    eager: bool = False
+    verbosity: int = KrylovDefaults.verbosity
+
+
+@dataclass(frozen=True)
 class Arnoldi:
     orth: Orthogonalizer = field(default_factory=lambda: KrylovDefaults.orth)
     krylovdim: int = KrylovDefaults.krylovdim

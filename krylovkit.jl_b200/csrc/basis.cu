@@ -234,6 +234,57 @@ k_transform(const __grid_constant__ TransformParams p, const __grid_constant__ C
     }
 }
 
+// basistransform! for bases wider than the resident ring (NS*C < m <= 256; the BlockLanczos default
+// krylovdim = 100 lands here).  Still one pass over the basis and in place: a TB_ROWS-row tile of all m
+// columns is staged in shared memory with plain coalesced loads, every thread then owns one row and
+// TB_J outputs per sweep, reading U (L1-resident, warp-uniform address) straight from global memory.
+// Sums run over i in increasing order with fma, like k_transform.
+constexpr int TB_ROWS = 64;
+constexpr int TB_THREADS = 256;
+constexpr int TB_J = 8;                                   // outputs per thread and sweep
+constexpr int TB_GROUPS = TB_THREADS / TB_ROWS;           // 4 output groups -> 32 outputs per sweep
+constexpr int TB_SMEM_MAX = TB_ROWS * 256 * 8;            // 128 KB at m = 256, f64
+
+template <typename T>
+__global__ void __launch_bounds__(TB_THREADS)
+k_transform_big(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    T* Qs = reinterpret_cast<T*>(smem);                   // Qs[i * TB_ROWS + r]
+    T* base = reinterpret_cast<T*>(p.base);
+    const int64_t ntiles = (p.n + TB_ROWS - 1) / TB_ROWS;
+    const int r = threadIdx.x % TB_ROWS, g = threadIdx.x / TB_ROWS;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * TB_ROWS;
+        for (int idx = threadIdx.x; idx < p.m * TB_ROWS; idx += TB_THREADS) {
+            const int i = idx / TB_ROWS, rr = idx - i * TB_ROWS;
+            Qs[idx] = (r0 + rr < p.n) ? base[(int64_t)cl.c[i] * p.ld + r0 + rr] : (T)0;
+        }
+        __syncthreads();
+        for (int jb = g * TB_J; jb < p.keep; jb += TB_GROUPS * TB_J) {
+            const double* ucol[TB_J];
+#pragma unroll
+            for (int t = 0; t < TB_J; ++t) {
+                const int j = (jb + t < p.keep) ? (jb + t) : (p.keep - 1);   // clamp: no branch in the i loop
+                ucol[t] = p.U + (size_t)j * p.ldu;
+            }
+            T acc[TB_J];
+#pragma unroll
+            for (int t = 0; t < TB_J; ++t) acc[t] = (T)0;
+            for (int i = 0; i < p.m; ++i) {
+                const T q = Qs[i * TB_ROWS + r];
+#pragma unroll
+                for (int t = 0; t < TB_J; ++t) acc[t] = fma(q, (T)__ldg(ucol[t] + i), acc[t]);
+            }
+            if (r0 + r < p.n) {
+#pragma unroll
+                for (int t = 0; t < TB_J; ++t)
+                    if (jb + t < p.keep) base[(int64_t)cl.c[jb + t] * p.ld + r0 + r] = acc[t];
+            }
+        }
+        __syncthreads();                                  // tile fully consumed before it is overwritten
+    }
+}
+
 // FP64 tensor-core variant of the restart GEMM (double, U resident in shared memory):
 // mma.sync.aligned.m8n8k4.f64 (DMMA).  Warp w owns rows [32w, 32w+32) of the resident tile as
 // four 8-row blocks; outputs are produced 40 columns (five 8-column blocks) per pass; the k loop
@@ -683,6 +734,8 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR((k_transform<double, false>), TR_SMEM);
     SETATTR((k_transform<float, true>), TR_SMEM);
     SETATTR((k_transform<float, false>), TR_SMEM);
+    SETATTR(k_transform_big<double>, TB_SMEM_MAX);
+    SETATTR(k_transform_big<float>, TB_SMEM_MAX);
 #undef SETATTR
     return B2K_OK;
 }
@@ -1113,9 +1166,9 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
     B2K_TRY(make_panel(ctx, cols, m, &pn));
     const bool f64 = ctx->dtype == B2K_F64;
     const int C = f64 ? 8 : 16;
-    if ((m + C - 1) / C > NS || m > 256)
-        return b2k_fail(ctx, B2K_ENOTSUP, "basis_transform: m = %d exceeds the resident tile (%d)",
-                        m, NS * C);
+    if (m > 256)
+        return b2k_fail(ctx, B2K_ENOTSUP, "basis_transform: m = %d exceeds the supported basis width (256)", m);
+    const bool wide = (m + C - 1) / C > NS;       // does not fit the resident ring: staged-tile kernel
     if ((size_t)m * keep > B2K_COEF_DOUBLES)
         return b2k_fail(ctx, B2K_ENOTSUP, "basis_transform: U too large");
     // pack U densely (ldu -> m)
@@ -1135,7 +1188,14 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
     for (int i = 0; i < m; ++i) cl.c[i] = pn.idx[i];
     const int pr = b2k_prof_begin(ctx, 2, (double)(m + keep) * ctx->esize * (double)pn.n);
     const bool dmma_ok = f64 && g_use_dmma && (size_t)m * (((keep + 7) / 8) * 8) * 8 <= (size_t)TD_U_BYTES;
-    if (dmma_ok) {
+    if (wide) {
+        const int64_t ntiles = (pn.n + TB_ROWS - 1) / TB_ROWS;
+        const size_t smem = (size_t)TB_ROWS * m * ctx->esize;
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(200 * 1024) / smem));
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm);
+        if (f64) k_transform_big<double><<<grid, TB_THREADS, smem, ctx->stream>>>(p, cl);
+        else k_transform_big<float><<<grid, TB_THREADS, smem, ctx->stream>>>(p, cl);
+    } else if (dmma_ok) {
         k_transform_dmma<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
     } else if (f64) {
         if (p.u_in_smem) k_transform<double, true><<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl);

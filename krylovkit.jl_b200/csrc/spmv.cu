@@ -609,7 +609,12 @@ static int32_t create_csr_raw(b2k_ctx* ctx, b2k_op** out, int64_t n_rows, int64_
                               const void* vals, int32_t idx_bytes, int32_t index_base) {
     if (nnz >= (int64_t)1 << 31 || n_rows >= (int64_t)1 << 31)
         return b2k_fail(ctx, B2K_ENOTSUP, "CSR: nnz/rows per GPU must be < 2^31");
-    if (n_rows != ctx->spaces[0].n)
+    // rows must be the length of a vector space of this context: space 0 in general, any space for a
+    // rectangular operator on a single GPU (the (A, A') pair of lssolve / svdsolve)
+    bool rows_ok = n_rows == ctx->spaces[0].n;
+    if (!rows_ok && ctx->nranks == 1)
+        for (const auto& sp : ctx->spaces) rows_ok = rows_ok || sp.n == n_rows;
+    if (!rows_ok)
         return b2k_fail(ctx, B2K_EDIM, "CSR: %lld local rows but space 0 holds %lld",
                         (long long)n_rows, (long long)ctx->spaces[0].n);
     const int64_t rp0 = idx_bytes == 8 ? ((const int64_t*)rowptr)[0] : ((const int32_t*)rowptr)[0];

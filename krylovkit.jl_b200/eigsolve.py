@@ -13,12 +13,13 @@ import numpy as np
 
 from . import _lib as L
 
-from .algorithms import ConvergenceInfo, Lanczos, WARN_LEVEL
+from .algorithms import BlockLanczos, ConvergenceInfo, Lanczos, WARN_LEVEL
 from .dense import (eigsort, householder_row, lmul_householder, permuteeig, rmul_householder,
                     tridiageigh)
+from .factorizations import blocklanczos as blz
 from .factorizations import lanczos as lz
 from .operators import B200CSR, B200Operator
-from .orthonormal import basistransform_
+from .orthonormal import OrthonormalBasis, basistransform_
 from .vectors import B200Context, B200Vec
 
 
@@ -32,7 +33,11 @@ def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = N
     Returns (values, vectors, ConvergenceInfo).
     """
     if alg is None:
-        alg = Lanczos(**kwargs)
+        alg = BlockLanczos(**kwargs) if isinstance(x0, blz.Block) else Lanczos(**kwargs)
+    if isinstance(alg, BlockLanczos):
+        if isinstance(x0, (list, tuple)):
+            x0 = blz.Block(x0)
+        return _eigsolve_blocklanczos(A, x0, howmany, which, alg)
     if not isinstance(x0, B200Vec):
         return _eigsolve_host(A, x0, howmany, which, alg, out_vectors, shard, nccl_uid, device)
     return _eigsolve_lanczos(A, x0, howmany, which, alg)
@@ -185,3 +190,88 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
         warnings.warn(f"Lanczos eigsolve stopped without convergence after {numiter} iterations: "
                       f"{converged} eigenvalues converged, normres = {normres}, numops = {numops}")
     return values, vectors, ConvergenceInfo(converged, residuals, normres, numiter, numops)
+
+
+def _eigsolve_blocklanczos(A, x0: "blz.Block", howmany: int, which: str, alg: BlockLanczos):
+    """eigsolve(A, x₀::Block, howmany, which, alg::BlockLanczos) — src/eigsolve/blocklanczos.jl:1-144
+    (SURVEY §8f-3).  Resolves degenerate eigenvalues up to the block size; thick restart as in the
+    Lanczos driver, with `bs` Householder-restored rows instead of one."""
+    maxiter, krylovdim = alg.maxiter, alg.krylovdim
+    if howmany > krylovdim:
+        raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} eigenvalues")
+    tol = alg.tol
+    bs = len(x0)
+    it = blz.BlockLanczosIterator(A, x0, krylovdim + bs, alg.orth, alg.qr_tol)
+    fact = blz.initialize(it)
+    if alg.verbosity >= WARN_LEVEL and blz.warn_nonhermitian(fact.H[:fact.k, :fact.k]):
+        warnings.warn("ignoring the antihermitian part of the block triangular matrix: "
+                      "operator might not be hermitian?")
+    numops, numiter, converged = bs + 1, 1, 0
+    D = U = normresiduals = None
+    while True:
+        K = len(fact)
+        beta = fact.normres()
+        if beta < tol and K < howmany and alg.verbosity >= WARN_LEVEL:
+            warnings.warn(f"Invariant subspace of dimension {K} (up to requested tolerance `tol = {tol}`), "
+                          f"which is smaller than the number of requested eigenvalues (i.e. `howmany == {howmany}`).")
+        if K >= krylovdim or beta <= tol or (alg.eager and K >= howmany):
+            BTD = fact.H[:K, :K]
+            D, U = np.linalg.eigh((BTD + BTD.T) / 2)           # eigen(Hermitian(BTD))
+            D, U = permuteeig(D, U, eigsort(which)(D))
+            bs_R = fact.R_size
+            r = fact.residual()
+            UU = U[K - bs_R:K, :]
+            RR = blz.block_inner(r, r)
+            normresiduals = np.sqrt(np.maximum(np.einsum("ik,ij,jk->k", UU, RR, UU), 0.0))
+            converged = 0
+            while converged < K and normresiduals[converged] <= tol:
+                converged += 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            blz.expand_(it, fact)
+            numops += fact.R_size
+        else:
+            if numiter >= maxiter:
+                break
+            keep = max((3 * krylovdim + 2 * converged) // (5 * bs), 1) * bs
+            H = np.zeros((keep + bs, keep))
+            for j in range(keep):
+                H[j, j] = D[j]
+                H[keep:, j] = U[K - bs:K, j]
+            for j in range(keep - 1, -1, -1):
+                h, nu = householder_row(H, j + bs, range(0, j + 1), j)
+                H[j + bs, j] = nu
+                H[j + bs, :j] = 0
+                lmul_householder(h, H)
+                rmul_householder(H, h, slice(0, j + bs))
+                rmul_householder(U, h)
+            fact.H[:] = 0
+            Hk = H[:keep, :keep]
+            fact.H[:keep, :keep] = (Hk + Hk.T) / 2             # exactly symmetric
+            B = fact.basis()
+            basistransform_(B, U[:, :keep])
+            R_new = OrthonormalBasis(fact.R.vec[:bs_R])
+            basistransform_(R_new, H[keep + bs - bs_R:keep + bs, keep - bs_R:keep])
+            fact.R.vec[:bs_R] = R_new.basis[:bs_R]
+            while len(B) > keep:
+                B.pop().free()
+            fact.k = keep
+            numiter += 1
+    hm = howmany
+    if converged > howmany:
+        hm = converged
+    elif len(D) < howmany:
+        hm = len(D)
+    values = D[:hm].copy()
+    V = fact.basis()
+    vectors = [V * U[:, i] for i in range(hm)]
+    bs_R, K = fact.R_size, len(fact)
+    U2 = U[K - bs_R:K, :hm]
+    Rb = OrthonormalBasis(fact.R.vec[:bs_R])
+    residuals = [Rb * U2[:, i] for i in range(hm)]
+    normresiduals = normresiduals[:hm]
+    if converged < howmany and alg.verbosity >= WARN_LEVEL:
+        warnings.warn(f"BlockLanczos eigsolve stopped without full convergence after {numiter} iterations: "
+                      f"{converged} eigenvalues converged, normres = {normresiduals}, numops = {numops}")
+    return values, vectors, ConvergenceInfo(converged, residuals, normresiduals, numiter, numops)

@@ -1182,6 +1182,158 @@ def block_qr(block, tol):
     return R[good, :], good, drift
 
 
+# ------------------------------------------------------------------ block Lanczos ---------
+
+@dataclass
+class BlockLanczosFact:
+    """BlockLanczosFactorization — blocklanczos.jl:82-94.  A V = V H + R Bᵀ, B = [0; I]."""
+    k: int
+    V: list
+    H: np.ndarray
+    R: list
+    R_size: int
+    norm_R: float
+
+
+def _block_norm(R):
+    return math.sqrt(sum(inner(x, x) for x in R))
+
+
+def blocklanczos_initialize(A, X0, maxdim, qr_tol):
+    """initialize(::BlockLanczosIterator) — blocklanczos.jl:159-190."""
+    if _block_norm(X0) == 0:
+        raise ValueError("initial vector should not have norm zero")
+    X1 = [x * 1.0 for x in X0]
+    _, good, _ = block_qr(X1, qr_tol)
+    X1 = [X1[i] for i in good]
+    V = list(X1)
+    bs = len(X1)
+    AX = [apply(A, x) for x in X1]
+    M = block_inner(X1, AX)
+    H = np.zeros((maxdim, maxdim))
+    H[:bs, :bs] = M
+    for j in range(bs):
+        for i in range(bs):
+            AX[j] = AX[j] - M[i, j] * X1[i]
+    return BlockLanczosFact(bs, V, H, AX, bs, _block_norm(AX))
+
+
+def blocklanczos_recurrence(A, V, B):
+    """block_lanczosrecurrence(…, ::ModifiedGramSchmidt2) — blocklanczos.jl:232-251."""
+    bs, bs_prev = B.shape
+    k = len(V)
+    X = V[k - bs:k]
+    AX = [apply(A, x) for x in X]
+    M = block_inner(X, AX)
+    Xprev = V[k - bs_prev - bs:k - bs]
+    for j in range(bs):
+        for i in range(bs):
+            AX[j] = AX[j] - M[i, j] * X[i]
+        for i in range(len(Xprev)):
+            AX[j] = AX[j] - B[j, i] * Xprev[i]
+    block_reorthogonalize(AX, V)
+    return AX, M
+
+
+def blocklanczos_expand(A, f: BlockLanczosFact, qr_tol):
+    """expand!(::BlockLanczosIterator, state) — blocklanczos.jl:192-230."""
+    k = f.k
+    R = f.R[:f.R_size]
+    bs = len(R)
+    Rcopy = [x * 1.0 for x in R]
+    B, good, drift = block_qr(R, qr_tol)
+    if drift:
+        block_reorthogonalize(R, f.V)
+        _, good, drift = block_qr(R, qr_tol)
+        B = block_inner([R[i] for i in good], Rcopy)
+    bs_next = len(good)
+    f.V.extend(R[i] for i in good)
+    f.H[k:k + bs_next, k - bs:k] = B[:bs_next, :bs]
+    f.H[k - bs:k, k:k + bs_next] = B[:bs_next, :bs].T
+    Rnext, M = blocklanczos_recurrence(A, f.V, B)
+    f.H[k:k + bs_next, k:k + bs_next] = M[:bs_next, :bs_next]
+    f.R[:bs_next] = Rnext
+    f.norm_R = _block_norm(Rnext)
+    f.k += bs_next
+    f.R_size = bs_next
+    return f
+
+
+def eigsolve_blocklanczos(A, X0, howmany, which, krylovdim=100, maxiter=100, tol=1e-12, qr_tol=1e-12,
+                          eager=False):
+    """eigsolve(A, x₀::Block, howmany, which, ::BlockLanczos) — eigsolve/blocklanczos.jl:1-144."""
+    if howmany > krylovdim:
+        raise ValueError("krylov dimension too small")
+    bs = len(X0)
+    f = blocklanczos_initialize(A, X0, krylovdim + bs, qr_tol)
+    numops, numiter, converged = bs + 1, 1, 0
+    D = U = normres = None
+    while True:
+        K, beta = f.k, f.norm_R
+        if K >= krylovdim or beta <= tol or (eager and K >= howmany):
+            BTD = f.H[:K, :K]
+            D, U = np.linalg.eigh((BTD + BTD.T) / 2)
+            D, U = permuteeig(D, U, eigsort(which)(D))
+            bs_R = f.R_size
+            r = f.R[:bs_R]
+            UU = U[K - bs_R:K, :]
+            RR = block_inner(r, r)
+            normres = np.sqrt(np.maximum(np.einsum("ik,ij,jk->k", UU, RR, UU), 0.0))
+            converged = 0
+            while converged < K and normres[converged] <= tol:
+                converged += 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            blocklanczos_expand(A, f, qr_tol)
+            numops += f.R_size
+        else:
+            if numiter >= maxiter:
+                break
+            keep = max((3 * krylovdim + 2 * converged) // (5 * bs), 1) * bs
+            H = np.zeros((keep + bs, keep))
+            for j in range(keep):
+                H[j, j] = D[j]
+                H[keep:, j] = U[K - bs:K, j]
+            for j in range(keep - 1, -1, -1):                 # Julia j = keep:-1:1
+                rr = list(range(j + 1))
+                row = j + bs                                  # Julia row j + bs
+                hb, hv, nu = householder_vec(H[row, rr], j)
+                H[row, j] = nu
+                H[row, :j] = 0
+                householder_lmul(hb, hv, rr, H)
+                householder_rmul(H[:row, :], hb, hv, rr)
+                householder_rmul(U, hb, hv, rr)
+            f.H[:] = 0
+            Hk = H[:keep, :keep]
+            f.H[:keep, :keep] = (Hk + Hk.T) / 2
+            basistransform(f.V, U[:, :keep])
+            view_H = H[keep + bs - bs_R:keep + bs, keep - bs_R:keep]
+            Rnew = list(f.R[:bs_R])
+            basistransform(Rnew, view_H)
+            f.R[:bs_R] = Rnew[:bs_R]
+            del f.V[keep:]
+            f.k = keep
+            numiter += 1
+    hm = howmany
+    if converged > howmany:
+        hm = converged
+    elif len(D) < howmany:
+        hm = len(D)
+    values = D[:hm].copy()
+    vectors = [unproject(np.zeros_like(f.V[0]), f.V, U[:, i]) for i in range(hm)]
+    bs_R, K = f.R_size, f.k
+    U2 = U[K - bs_R:K, :hm]
+    residuals = []
+    for i in range(hm):
+        res = np.zeros_like(f.R[0])
+        for j in range(bs_R):
+            res = res + U2[j, i] * f.R[j]
+        residuals.append(res)
+    return values, vectors, dict(converged=converged, residual=residuals, normres=normres[:hm],
+                                 numiter=numiter, numops=numops, fact=f)
+
+
 # ------------------------------------------------------------------ fixtures --------------
 
 def toric_code_hamiltonian(m, n):

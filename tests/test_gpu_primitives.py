@@ -239,7 +239,9 @@ def test_orthogonalize_single_vector():
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n,m,keep", [(70001, 30, 18), (5000, 60, 36), (300, 61, 61), (1000, 3, 1),
-                                      (512, 30, 18), (100003, 90, 75)])
+                                      (512, 30, 18), (100003, 90, 75),
+                                      # wider than the resident ring (96 f64 / 192 f32 columns): staged-tile kernel
+                                      (20011, 100, 64), (3000, 130, 130), (777, 256, 40), (5000, 200, 199)])
 def test_basistransform(n, m, keep, dtype):
     rng = np.random.default_rng(n)
     ctx = kk.B200Context(n, m + 4, dtype=dtype)

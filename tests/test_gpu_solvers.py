@@ -415,6 +415,131 @@ def test_lsmr_matches_oracle_and_reference_properties(orth):
     np.testing.assert_allclose(info.residual, bs - As @ x, atol=1e-10)
 
 
+def _mat_with_eigrepetition(rng, N, mult):
+    """test/testsetup.jl:46-58: symmetric matrix with repeated extremal eigenvalues."""
+    Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    D = np.sort(rng.standard_normal(N))
+    i = 0
+    while mult >= 2 and i + mult <= N // 2:
+        D[i:i + mult] = D[i]
+        D[N - i - mult:N - i] = D[N - i - 1]
+        i += mult
+        mult -= 1
+    A = Q @ np.diag(D) @ Q.T
+    return (A + A.T) / 2
+
+
+def _dense_sym_op(ctx, A):
+    return kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A))
+
+
+def test_blocklanczos_reference_properties():
+    """SURVEY §8f-3 / test/eigsolve.jl:552-770 through the device path: full spectrum from both ends
+    with repeated eigenvalues, orthonormal Ritz vectors, A v = λ v, agreement with the oracle, the
+    single-vector block reproducing Lanczos (same numiter, numops + 1), and the restart improving
+    accuracy."""
+    rng = np.random.default_rng(17)
+    n, N = 10, 100
+    tol = 1e-12
+    # --- full
+    A = _mat_with_eigrepetition(rng, n, 2)
+    X0 = [rng.random(n) for _ in range(2)]
+    ev = np.linalg.eigvalsh(A)
+    ctx = kk.B200Context(n, 64)
+    op = _dense_sym_op(ctx, A)
+    n1 = n // 2
+    n2 = n - n1
+    blk = lambda: kk.Block([ctx.from_host(x) for x in X0])
+    D1, V1, info1 = kk.eigsolve(op, blk(), n1, "SR", kk.BlockLanczos(krylovdim=n, maxiter=1, tol=tol, verbosity=0))
+    D2, V2, info2 = kk.eigsolve(op, blk(), n2, "LR", kk.BlockLanczos(krylovdim=2 * n, maxiter=4, tol=tol, verbosity=0))
+    np.testing.assert_allclose(np.concatenate([D1[:n1], D2[:n2][::-1]]), ev, rtol=1e-9, atol=1e-11)
+    for D, V in ((D1, V1), (D2, V2)):
+        Uh = np.column_stack([v.to_host() for v in V])
+        np.testing.assert_allclose(Uh.T @ Uh, np.eye(Uh.shape[1]), atol=1e-9)
+        np.testing.assert_allclose(A @ Uh, Uh * D, atol=1e-9)
+    oD1, _, oinfo1 = ko.eigsolve_blocklanczos(A, X0, n1, "SR", krylovdim=n, maxiter=1, tol=tol)
+    np.testing.assert_allclose(D1, oD1, rtol=1e-9, atol=1e-11)
+    assert info1.numops == oinfo1["numops"] and info1.converged == oinfo1["converged"]
+    with pytest.raises(ValueError):
+        kk.eigsolve(op, blk(), n + 1, "SR", kk.BlockLanczos(krylovdim=n, verbosity=0))
+    ctx.close()
+    # --- iterative, eager, block of 4 with multiplicity 4
+    A = _mat_with_eigrepetition(rng, N, 4)
+    X0 = [rng.random(N) for _ in range(4)]
+    ev = np.linalg.eigvalsh(A)
+    ctx = kk.B200Context(N, 140)
+    op = _dense_sym_op(ctx, A)
+    blk = lambda: kk.Block([ctx.from_host(x) for x in X0])
+    alg = kk.BlockLanczos(krylovdim=N, maxiter=10, tol=tol, eager=True, verbosity=0)
+    D1, V1, info1 = kk.eigsolve(op, blk(), n, "SR", alg)
+    D2, V2, info2 = kk.eigsolve(op, blk(), n, "LR", alg)
+    l1, l2 = info1.converged, info2.converged
+    assert l1 >= n and l2 >= n
+    np.testing.assert_allclose(D1[:l1], ev[:l1], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(D2[:l2], ev[::-1][:l2], rtol=1e-9, atol=1e-10)
+    U1 = np.column_stack([v.to_host() for v in V1])
+    np.testing.assert_allclose(U1.T @ U1, np.eye(U1.shape[1]), atol=1e-9)
+    R1 = np.column_stack([r.to_host() for r in info1.residual])
+    np.testing.assert_allclose(A @ U1, U1 * D1 + R1, atol=1e-9)
+    # --- shrink makes it better (:741-770)
+    A = _mat_with_eigrepetition(rng, N, 5)
+    X0 = [rng.random(N) for _ in range(5)]
+    v0 = np.linalg.eigvalsh(A)[:n]
+    op = _dense_sym_op(ctx, A)
+    va, _, _ = kk.eigsolve(op, blk5 := kk.Block([ctx.from_host(x) for x in X0]), n, "SR",
+                           kk.BlockLanczos(krylovdim=3 * n // 2, maxiter=1, tol=1e-12, verbosity=0))
+    vb, _, infob = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), n, "SR",
+                               kk.BlockLanczos(krylovdim=3 * n // 2, maxiter=2, tol=1e-12, verbosity=0))
+    assert np.linalg.norm(vb[:n // 2] - v0[:n // 2]) < np.linalg.norm(va[:n // 2] - v0[:n // 2])
+    ovb, _, oinfob = ko.eigsolve_blocklanczos(A, X0, n, "SR", krylovdim=3 * n // 2, maxiter=2, tol=1e-12)
+    np.testing.assert_allclose(vb, ovb, rtol=1e-8, atol=1e-9)
+    assert infob.numops == oinfob["numops"] and infob.numiter == oinfob["numiter"] == 2
+    del blk5
+    ctx.close()
+    # --- block size 1 reproduces Lanczos (:685-712)
+    A = rng.random((2 * N, 2 * N)) - 0.5
+    A = (A + A.T) / 2
+    x0 = rng.random(2 * N)
+    ctx = kk.B200Context(2 * N, 80)
+    op = _dense_sym_op(ctx, A)
+    e1, _, j1 = kk.eigsolve(op, ctx.from_host(x0), n, "SR",
+                            kk.Lanczos(krylovdim=2 * n, maxiter=10, tol=tol, verbosity=0))
+    e2, _, j2 = kk.eigsolve(op, kk.Block([ctx.from_host(x0)]), n, "SR",
+                            kk.BlockLanczos(krylovdim=2 * n, maxiter=10, tol=tol, verbosity=0))
+    assert j1.converged == j2.converged and j1.numiter == j2.numiter and j1.numops + 1 == j2.numops
+    np.testing.assert_allclose(j1.normres, j2.normres[:len(j1.normres)], atol=1e-9)
+    np.testing.assert_allclose(e1[:j1.converged], e2[:j2.converged], rtol=1e-9, atol=1e-11)
+    ctx.close()
+
+
+def test_blocklanczos_toric_code_degenerate_ground_space():
+    """test/eigsolve.jl:471-549: −H of the 3×3 toric code (2^18 states) has a four-fold degenerate
+    lowest eigenvalue −16, which a block of 5 resolves in one sweep (krylovdim 100, no restart); a
+    second run with krylovdim 60 and restarts exercises the wide (K > 96 columns not needed) and the
+    thick-restart path at scale."""
+    H = ko.toric_code_hamiltonian(3, 3)
+    M = H.shape[0]
+    rng = np.random.default_rng(1)
+    X0 = [rng.random(M) for _ in range(5)]
+    ctx = kk.B200Context(M, 120)
+    op = kk.B200CSR.from_scipy(ctx, (-H).tocsr())
+    alg = kk.BlockLanczos(tol=1e-6, maxiter=1, verbosity=0)
+    D, U, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 10, "SR", alg)
+    assert np.sum(np.abs(D[:10] + 16.0) < 2.0 - 1e-6) == 4
+    assert np.sum(np.abs(D[:10] + 16.0) < 1e-6) == 4
+    # map input: any callable on device vectors
+    D, U, info = kk.eigsolve(lambda x: op(x), kk.Block([ctx.from_host(x) for x in X0]), 10, "SR", alg)
+    assert np.sum(np.abs(D[:10] + 16.0) < 1e-6) == 4
+    del U
+    alg = kk.BlockLanczos(tol=1e-8, krylovdim=40, maxiter=30, verbosity=0)
+    D, U, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 4, "SR", alg)
+    assert info.converged >= 4 and info.numiter > 1
+    np.testing.assert_allclose(D[:4], -16.0, atol=1e-7)
+    G = np.column_stack([u.to_host() for u in U[:4]])
+    np.testing.assert_allclose(G.T @ G, np.eye(4), atol=1e-7)
+    ctx.close()
+
+
 def test_invariant_subspace_early_exit():
     """eigsolve/lanczos.jl:38-44, 45: beta <= tol stops the expansion loop early (also inside
     b2k_lanczos_expand_many) and reports the exact eigenvalues of the invariant subspace."""

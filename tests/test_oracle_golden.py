@@ -375,3 +375,75 @@ def test_lsmr_oracle():
     assert info["converged"] > 0
     assert np.linalg.norm(A.T @ (b - A @ x)) < 5 * tol
     np.testing.assert_allclose(x, np.linalg.lstsq(A, b, rcond=None)[0], rtol=1e-8)
+
+
+def _mat_with_eigrepetition(rng, N, mult):
+    """test/testsetup.jl:46-58."""
+    Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    D = np.sort(rng.standard_normal(N))
+    i = 0
+    while mult >= 2 and i + mult <= N // 2:
+        D[i:i + mult] = D[i]
+        D[N - i - mult:N - i] = D[N - i - 1]
+        i += mult
+        mult -= 1
+    A = Q @ np.diag(D) @ Q.T
+    return (A + A.T) / 2
+
+
+def test_blocklanczos_oracle():
+    """The reference's own BlockLanczos assertions (test/eigsolve.jl:552-770) on the restatement:
+    both ends of a spectrum with repeated eigenvalues, orthonormal eigenvectors, block size 1 =
+    Lanczos (same convergence count and restarts, one extra operator application, same residual
+    norms), and a restart improving on a single sweep."""
+    rng = np.random.default_rng(3)
+    n, N, tol = 10, 100, 1e-12
+    A = _mat_with_eigrepetition(rng, n, 2)
+    X0 = [rng.random(n) for _ in range(2)]
+    n1 = n // 2
+    n2 = n - n1
+    ev = np.linalg.eigvalsh(A)
+    D1, V1, _ = ko.eigsolve_blocklanczos(A, X0, n1, "SR", krylovdim=n, maxiter=1, tol=tol)
+    D2, V2, _ = ko.eigsolve_blocklanczos(A, X0, n2, "LR", krylovdim=2 * n, maxiter=4, tol=tol)
+    np.testing.assert_allclose(np.concatenate([D1[:n1], D2[:n2][::-1]]), ev, rtol=1e-9, atol=1e-11)
+    U1 = np.array(V1).T
+    np.testing.assert_allclose(U1.T @ U1, np.eye(U1.shape[1]), atol=1e-10)
+    np.testing.assert_allclose(A @ U1, U1 * D1, atol=1e-10)
+
+    A = _mat_with_eigrepetition(rng, N, 4)
+    X0 = [rng.random(N) for _ in range(4)]
+    ev = np.linalg.eigvalsh(A)
+    D1, _, i1 = ko.eigsolve_blocklanczos(A, X0, n, "SR", krylovdim=N, maxiter=10, tol=tol, eager=True)
+    D2, _, i2 = ko.eigsolve_blocklanczos(A, X0, n, "LR", krylovdim=N, maxiter=10, tol=tol, eager=True)
+    l1, l2 = i1["converged"], i2["converged"]
+    assert l1 >= n and l2 >= n
+    np.testing.assert_allclose(D1[:l1], ev[:l1], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(D2[:l2], ev[::-1][:l2], rtol=1e-9, atol=1e-10)
+
+    A = rng.random((2 * N, 2 * N)) - 0.5
+    A = (A + A.T) / 2
+    x0 = rng.random(2 * N)
+    e1, _, j1 = ko.eigsolve_lanczos(A, x0, n, "SR", krylovdim=2 * n, maxiter=10, tol=tol, orth=ko.Orth(ko.MGS2))
+    e2, _, j2 = ko.eigsolve_blocklanczos(A, [x0], n, "SR", krylovdim=2 * n, maxiter=10, tol=tol)
+    assert j1["converged"] == j2["converged"] and j1["numiter"] == j2["numiter"]
+    assert j1["numops"] + 1 == j2["numops"]
+    m = len(j1["normres"])
+    np.testing.assert_allclose(j1["normres"], j2["normres"][:m], atol=1e-11)
+    np.testing.assert_allclose(e1[:j1["converged"]], e2[:j2["converged"]], rtol=1e-10)
+
+    A = _mat_with_eigrepetition(rng, N, 5)
+    X0 = [rng.random(N) for _ in range(5)]
+    v0 = np.linalg.eigvalsh(A)[:n]
+    va, _, _ = ko.eigsolve_blocklanczos(A, X0, n, "SR", krylovdim=3 * n // 2, maxiter=1, tol=1e-12)
+    vb, _, _ = ko.eigsolve_blocklanczos(A, X0, n, "SR", krylovdim=3 * n // 2, maxiter=2, tol=1e-12)
+    assert np.linalg.norm(vb[:n // 2] - v0[:n // 2]) < np.linalg.norm(va[:n // 2] - v0[:n // 2])
+
+
+def test_blocklanczos_toric_oracle():
+    """test/eigsolve.jl:534-548: a block of 5 finds the four-fold degenerate −16 of the 3×3 toric code."""
+    H = ko.toric_code_hamiltonian(3, 3)
+    rng = np.random.default_rng(2)
+    X0 = [rng.random(H.shape[0]) for _ in range(5)]
+    D, _, info = ko.eigsolve_blocklanczos((-H).tocsr(), X0, 10, "SR", krylovdim=100, maxiter=1, tol=1e-6)
+    assert np.sum(np.abs(D[:10] + 16.0) < 2.0 - 1e-6) == 4
+    assert np.sum(np.abs(D[:10] + 16.0) < 1e-6) == 4
