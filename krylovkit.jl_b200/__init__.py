@@ -22,6 +22,7 @@ from .vectors import B200Context, B200Vec, inner, norm
 __all__ = [n for n in dir() if not n.startswith("_")]
 from .eigsolve import eigsolve
 from .linsolve import linsolve
+from .schursolve import ComplexVec, schursolve
 from .lssolve import lssolve
 from .svdsolve import svdsolve
 from . import factorizations

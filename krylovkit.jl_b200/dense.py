@@ -146,3 +146,108 @@ def ldiv_upper(R, y, k):
 def hidx(i: int, j: int) -> int:
     """PackedHessenberg (1-based i <= j+1) -> 0-based index into data — packedhessenberg.jl:32-39."""
     return ((j * j + j - 2) >> 1) + i - 1
+
+
+# ---- real Schur machinery for the Arnoldi drivers — dense/linalg.jl:150-393 ----------------------
+
+def schur2eigvals(T: np.ndarray) -> np.ndarray:
+    """schur2eigvals(T::Real) — dense/linalg.jl:166-189.  The first row of a 2×2 block carries +Im."""
+    n = T.shape[0]
+    D = np.zeros(n, dtype=np.complex128)
+    i = 0
+    while i < n:
+        if i < n - 1 and T[i + 1, i] != 0:
+            halftr = (T[i, i] + T[i + 1, i + 1]) / 2
+            diff = (T[i, i] - T[i + 1, i + 1]) / 2
+            im = math.sqrt(-(diff * diff + T[i, i + 1] * T[i + 1, i]))
+            D[i], D[i + 1] = complex(halftr, im), complex(halftr, -im)
+            i += 2
+        else:
+            D[i] = T[i, i]
+            i += 1
+    return D
+
+
+def hschur(H: np.ndarray):
+    """hschur!(H, Z) — dense/linalg.jl:152-154: real Schur form H = Z T Zᵀ (LAPACK, through scipy)."""
+    from scipy.linalg import schur
+    T, Z = schur(np.asarray(H, dtype=np.float64), output="real")
+    return T, Z, schur2eigvals(T)
+
+
+def eigsort_complex(which: str):
+    """eigsort for complex Ritz values — eigsolve/eigsolve.jl:335-355; stable like sortperm."""
+    keys = {"LM": lambda v: -np.abs(v), "LR": lambda v: -v.real, "SR": lambda v: v.real,
+            "LI": lambda v: -v.imag, "SI": lambda v: v.imag}
+    if which not in keys:
+        raise ValueError(f"invalid specification of which eigenvalues to target: which = {which}")
+    return lambda vals: np.argsort(keys[which](np.asarray(vals)), kind="stable")
+
+
+def permuteschur(T: np.ndarray, Q: np.ndarray, order):
+    """permuteschur!(T, Q, order) — dense/linalg.jl:356-386: reorder the diagonal blocks of a real
+    Schur form with LAPACK trexc; a 2×2 block moves as a unit and may not be split."""
+    T = np.asfortranarray(T, dtype=np.float64)
+    Q = np.asfortranarray(Q, dtype=np.float64)
+    n = T.shape[0]
+    p = [int(v) + 1 for v in order]                      # trexc counts from one
+    i = 0
+    while i < len(p):
+        ifirst = p[i]
+        width = 1 if (ifirst == n or T[ifirst, ifirst - 1] == 0) else 2
+        if width == 2 and (i + 1 >= len(p) or p[i + 1] != ifirst + 1):
+            raise ValueError("cannot split 2x2 blocks when permuting schur decomposition")
+        T, Q, info = lapack.dtrexc(T, Q, ifirst, i + 1)
+        if info != 0:
+            raise RuntimeError(f"dtrexc failed: info = {info}")
+        for k in range(i + width, len(p)):
+            if p[k] < p[i]:
+                p[k] += width
+        i += width
+    return T, Q, schur2eigvals(T)
+
+
+def schur2eigvecs(T: np.ndarray) -> np.ndarray:
+    """schur2eigvecs(T::Real) — dense/linalg.jl:223-246: unit-norm complex eigenvectors of a real
+    quasi-triangular T, column i belonging to schur2eigvals(T)[i].  The reference calls LAPACK trevc;
+    here T is rotated to complex triangular form (rsf2csf) and back-substituted."""
+    from scipy.linalg import rsf2csf
+    n = T.shape[0]
+    Tc, Zc = rsf2csf(np.asarray(T, dtype=np.float64), np.eye(n))
+    smin = np.finfo(np.float64).eps * max(float(np.abs(Tc).max()), 1.0)
+    X = np.zeros((n, n), dtype=np.complex128)
+    for k in range(n):
+        lam = Tc[k, k]
+        X[k, k] = 1.0
+        for i in range(k - 1, -1, -1):
+            den = Tc[i, i] - lam
+            if abs(den) < smin:
+                den = smin
+            X[i, k] = -(Tc[i, i + 1:k + 1] @ X[i + 1:k + 1, k]) / den
+    W = Zc @ X
+    W /= np.linalg.norm(W, axis=0)
+    V = np.empty_like(W)
+    i = 0
+    while i < n:
+        if i < n - 1 and T[i + 1, i] != 0:
+            k = i if Tc[i, i].imag > 0 else i + 1          # whichever slot holds the +Im eigenvalue
+            V[:, i] = W[:, k]
+            V[:, i + 1] = np.conj(W[:, k])
+            i += 2
+        else:
+            V[:, i] = W[:, i]
+            i += 1
+    return V
+
+
+def restore_arnoldi_form(U: np.ndarray, H: np.ndarray, f: np.ndarray, keep: int):
+    """_restorearnoldiform!(U, H, f, keep) — eigsolve/arnoldi.jl:468-481: Householder sweep that turns
+    the truncated Krylov-Schur relation back into Arnoldi (Hessenberg) form."""
+    H[keep, :keep] = f[:keep]
+    for j in range(keep - 1, -1, -1):
+        h, nu = householder_row(H, j + 1, range(0, j + 1), j)
+        H[j + 1, j] = nu
+        H[j + 1, :j] = 0
+        lmul_householder(h, H)
+        rmul_householder(H, h, slice(0, j + 1))
+        rmul_householder(U, h)

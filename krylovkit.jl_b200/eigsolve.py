@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib as L
 
-from .algorithms import BlockLanczos, ConvergenceInfo, Lanczos, WARN_LEVEL
+from .algorithms import Arnoldi, BlockLanczos, ConvergenceInfo, Lanczos, WARN_LEVEL
 from .dense import (eigsort, householder_row, lmul_householder, permuteeig, rmul_householder,
                     tridiageigh)
 from .factorizations import blocklanczos as blz
@@ -38,6 +38,11 @@ def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = N
         if isinstance(x0, (list, tuple)):
             x0 = blz.Block(x0)
         return _eigsolve_blocklanczos(A, x0, howmany, which, alg)
+    if isinstance(alg, Arnoldi):
+        if not isinstance(x0, B200Vec):
+            raise TypeError("eigsolve(Arnoldi): pass a device start vector (B200Vec)")
+        from .schursolve import eigsolve_arnoldi
+        return eigsolve_arnoldi(A, x0, howmany, which, alg)
     if not isinstance(x0, B200Vec):
         return _eigsolve_host(A, x0, howmany, which, alg, out_vectors, shard, nccl_uid, device)
     return _eigsolve_lanczos(A, x0, howmany, which, alg)

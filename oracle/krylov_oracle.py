@@ -650,6 +650,232 @@ def arnoldi_expand(A, f: ArnoldiFact, orth: Orth):
     return f
 
 
+def arnoldi_shrink(f: ArnoldiFact, k):
+    """shrink! — factorizations/arnoldi.jl:220-236."""
+    if f.k <= k:
+        return f
+    while len(f.V) > k + 1:
+        f.V.pop()
+    r = f.V.pop()
+    del f.H[(k * k + 3 * k) >> 1:]
+    f.k = k
+    f.r = r * f.normres()
+    return f
+
+
+def arnoldi_rayleighquotient(f: ArnoldiFact):
+    k = f.k
+    Hm = np.zeros((k, k))
+    for j in range(1, k + 1):
+        for i in range(1, min(j + 1, k) + 1):
+            Hm[i - 1, j - 1] = f.H[hidx(i, j)]
+    return Hm
+
+
+def schur2eigvals(T):
+    """schur2eigvals(T::Real) — dense/linalg.jl:166-189: complex eigenvalues from the 1×1 / 2×2 diagonal
+    blocks of a real quasi-triangular matrix; the first row of a 2×2 block carries +Im."""
+    n = T.shape[0]
+    D = np.zeros(n, dtype=np.complex128)
+    for i in range(n):
+        if i < n - 1 and T[i + 1, i] != 0:
+            halftr = (T[i, i] + T[i + 1, i + 1]) / 2
+            diff = (T[i, i] - T[i + 1, i + 1]) / 2
+            d = diff * diff + T[i, i + 1] * T[i + 1, i]
+            D[i] = halftr + 1j * math.sqrt(-d)
+        elif i > 0 and T[i, i - 1] != 0:
+            halftr = (T[i, i] + T[i - 1, i - 1]) / 2
+            diff = -(T[i, i] - T[i - 1, i - 1]) / 2
+            d = diff * diff + T[i, i - 1] * T[i - 1, i]
+            D[i] = halftr - 1j * math.sqrt(-d)
+        else:
+            D[i] = T[i, i]
+    return D
+
+
+def hschur(H):
+    """hschur!(H, Z) — dense/linalg.jl:152-154 (LAPACK hseqr): real Schur form H = Z T Zᵀ."""
+    from scipy.linalg import schur
+    T, Z = schur(H, output="real")
+    return T, Z, schur2eigvals(T)
+
+
+def eigsort_complex(which):
+    """eigsort — eigsolve/eigsolve.jl:335-355 for complex values: stable permutation."""
+    key = {"LM": lambda v: -np.abs(v), "LR": lambda v: -v.real, "SR": lambda v: v.real,
+           "LI": lambda v: -v.imag, "SI": lambda v: v.imag}[which]
+    return lambda vals: np.argsort(key(np.asarray(vals)), kind="stable")
+
+
+def permuteschur(T, Q, order):
+    """permuteschur!(T, Q, order) for real T — dense/linalg.jl:356-386: bring the diagonal blocks into
+    the given order with LAPACK trexc, never splitting a 2×2 block."""
+    T = np.asfortranarray(T, dtype=np.float64)
+    Q = np.asfortranarray(Q, dtype=np.float64)
+    n = T.shape[0]
+    p = [int(v) + 1 for v in order]                      # 1-based like the reference
+    i = 0
+    while i < len(p):
+        ifirst, ilast = p[i], i + 1
+        single = ifirst == n or T[ifirst, ifirst - 1] == 0     # T[ifirst+1, ifirst] in 1-based terms
+        if not single and (i + 1 >= len(p) or p[i + 1] != ifirst + 1):
+            raise ValueError("cannot split 2x2 blocks when permuting schur decomposition")
+        T, Q, info = lapack.dtrexc(T, Q, ifirst, ilast)
+        if info != 0:
+            raise RuntimeError(f"trexc failed: info = {info}")
+        step = 1 if single else 2
+        for k in range(i + step, len(p)):
+            if p[k] < p[i]:
+                p[k] += step
+        i += step
+    return T, Q, schur2eigvals(T)
+
+
+def schur2eigvecs(T):
+    """schur2eigvecs(T::Real) — dense/linalg.jl:223-246 (LAPACK trevc + normalisation): unit-norm complex
+    eigenvectors of a real quasi-triangular matrix, column i ↔ schur2eigvals(T)[i]; the two columns of a
+    2×2 block are complex conjugates.  Restated as a back substitution per diagonal block."""
+    n = T.shape[0]
+    vals = schur2eigvals(T)
+    V = np.zeros((n, n), dtype=np.complex128)
+    i = 0
+    while i < n:
+        two = i < n - 1 and T[i + 1, i] != 0
+        lam = vals[i]
+        x = np.zeros(n, dtype=np.complex128)
+        if two:
+            x[i], x[i + 1] = T[i, i + 1], lam - T[i, i]          # null vector of the 2×2 block minus λ
+            top = i
+            rhs = -(T[:top, i:i + 2] @ x[i:i + 2])
+        else:
+            x[i] = 1.0
+            top = i
+            rhs = -T[:top, i].astype(np.complex128)
+        if top > 0:
+            Lm = T[:top, :top] - lam * np.eye(top)
+            smin = np.finfo(float).eps * max(np.abs(T).max(), 1.0)
+            for d in range(top):                               # trevc-style perturbation of tiny pivots
+                if abs(Lm[d, d]) < smin and not (d < top - 1 and T[d + 1, d] != 0) \
+                        and not (d > 0 and T[d, d - 1] != 0):
+                    Lm[d, d] = smin
+            x[:top] = np.linalg.solve(Lm, rhs)
+        x /= np.linalg.norm(x)
+        V[:, i] = x
+        if two:
+            V[:, i + 1] = np.conj(x)
+            i += 2
+        else:
+            i += 1
+    return V
+
+
+def restore_arnoldi_form(U, H, f, keep):
+    """_restorearnoldiform!(U, H, f, keep) — eigsolve/arnoldi.jl:468-481."""
+    for j in range(keep):
+        H[keep, j] = f[j]
+    for j in range(keep - 1, -1, -1):
+        rr = list(range(j + 1))
+        hb, hv, nu = householder_vec(H[j + 1, rr], j)
+        H[j + 1, j] = nu
+        H[j + 1, :j] = 0
+        householder_lmul(hb, hv, rr, H)
+        householder_rmul(H[: j + 1, :], hb, hv, rr)
+        householder_rmul(U, hb, hv, rr)
+
+
+def _schursolve(A, x0, howmany, which, krylovdim, maxiter, tol, orth, eager):
+    """_schursolve — eigsolve/arnoldi.jl:351-452 (Krylov-Schur restarts in real arithmetic)."""
+    if howmany > krylovdim:
+        raise ValueError("krylov dimension too small")
+    numiter = 1
+    f = arnoldi_initialize(A, x0, orth)
+    numops = 1
+    converged = 0
+    T = U = fv = None
+    while True:
+        beta = f.normres()
+        K = f.k
+        if K == krylovdim or beta <= tol or (eager and K >= howmany):
+            H = arnoldi_rayleighquotient(f)
+            T, U, values = hschur(H)
+            p = eigsort_complex(which)(values)
+            T, U, values = permuteschur(T, U, p)
+            fv = U[K - 1, :] * beta
+            converged = 0
+            while converged < K and abs(fv[converged]) <= tol:
+                converged += 1
+            if 0 < converged < K and T[converged, converged - 1] != 0:
+                converged -= 1
+            if converged >= howmany or beta <= tol:
+                break
+        if K < krylovdim:
+            f = arnoldi_expand(A, f, orth)
+            numops += 1
+        else:
+            if numiter == maxiter:
+                break
+            keep = (3 * krylovdim + 2 * converged) // 5
+            H = np.array(T)
+            if H[keep, keep - 1] != 0:                 # in the middle of a 2×2 block
+                if keep > 1:
+                    keep -= 1
+                else:
+                    keep += 1
+                    if krylovdim == 2:
+                        break
+            restore_arnoldi_form(U, H, fv, keep)
+            # copy H back into packed Hessenberg storage (only the first keep columns survive the shrink)
+            for j in range(1, K + 1):
+                for i in range(1, min(j + 1, K) + 1):
+                    f.H[hidx(i, j)] = H[i - 1, j - 1]
+            basistransform(f.V, U[:, :keep])
+            f.V[keep] = f.r * (1 / beta)
+            f = arnoldi_shrink(f, keep)
+            numiter += 1
+    return T, U, f, converged, numiter, numops
+
+
+def _schur_howmany(T, f, howmany, converged):
+    hm = howmany
+    if howmany < f.k and T[howmany, howmany - 1] != 0:
+        hm += 1
+    elif T.shape[0] < howmany:
+        hm = T.shape[0]
+    if converged > howmany:
+        hm = converged
+    return hm
+
+
+def schursolve_arnoldi(A, x0, howmany, which, krylovdim=30, maxiter=100, tol=1e-12,
+                       orth: Orth = Orth(MGS2), eager=False):
+    """schursolve(A, x₀, howmany, which, ::Arnoldi) — eigsolve/arnoldi.jl:110-145."""
+    T, U, f, converged, numiter, numops = _schursolve(A, x0, howmany, which, krylovdim, maxiter, tol, orth, eager)
+    hm = _schur_howmany(T, f, howmany, converged)
+    TT = T[:hm, :hm]
+    values = schur2eigvals(TT)
+    vectors = [unproject(np.zeros_like(f.V[0]), f.V, U[:, i]) for i in range(hm)]
+    residuals = [f.r * U[-1, i] for i in range(hm)]
+    normres = np.array([f.normres() * abs(U[-1, i]) for i in range(hm)])
+    return TT, vectors, values, dict(converged=converged, residual=residuals, normres=normres,
+                                     numiter=numiter, numops=numops)
+
+
+def eigsolve_arnoldi(A, x0, howmany, which, krylovdim=30, maxiter=100, tol=1e-12,
+                     orth: Orth = Orth(MGS2), eager=False):
+    """eigsolve(A, x₀, howmany, which, ::Arnoldi) — eigsolve/arnoldi.jl:147-184.  Complex eigenvectors."""
+    T, U, f, converged, numiter, numops = _schursolve(A, x0, howmany, which, krylovdim, maxiter, tol, orth, eager)
+    hm = _schur_howmany(T, f, howmany, converged)
+    TT = T[:hm, :hm]
+    values = schur2eigvals(TT)
+    Vc = U[:, :hm] @ schur2eigvecs(TT)
+    Bm = np.column_stack(f.V)
+    vectors = [Bm @ Vc[:, i] for i in range(hm)]
+    residuals = [f.r * Vc[-1, i] for i in range(hm)]
+    normres = np.array([f.normres() * abs(Vc[-1, i]) for i in range(hm)])
+    return values, vectors, dict(converged=converged, residual=residuals, normres=normres,
+                                 numiter=numiter, numops=numops)
+
+
 def linsolve_gmres(A, b, x0=None, krylovdim=30, maxiter=100, tol=1e-12, orth: Orth = Orth(MGS2),
                    a0=0.0, a1=1.0):
     """linsolve(operator, b, x₀, ::GMRES, a₀, a₁) — src/linsolve/gmres.jl:1-151.

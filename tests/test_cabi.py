@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 import krylovkit_jl_b200 as kk
@@ -130,3 +131,44 @@ def test_native_restart_helper_matches_numpy_mirror_and_oracle():
             assert (be >= 0).all()
             assert np.abs(Ux[:, :keep].T @ Ux[:, :keep] - np.eye(keep)).max() < 1e-12
     assert L.load().b2k_host_lanczos_restart(5, 0, None, None, None, 5, None, None) == L.EINVAL
+
+
+def test_real_schur_helpers_match_oracle():
+    """Host-side real Schur machinery of the Arnoldi drivers (dense/linalg.jl:150-393): the product's
+    helpers (trexc reordering; rsf2csf back-substitution for the eigenvectors) against the oracle's
+    (same reordering; quasi-triangular solves) and against the defining identities."""
+    import importlib
+    from oracle import krylov_oracle as ko
+    d = importlib.import_module("krylovkit_jl_b200.dense")
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 5, 12, 30):
+        A = rng.standard_normal((n, n))
+        T, Z, vals = d.hschur(A)
+        np.testing.assert_allclose(np.sort_complex(vals), np.sort_complex(np.linalg.eigvals(A)), atol=1e-10)
+        for which in ("LM", "LR", "SR"):
+            p = d.eigsort_complex(which)(vals)
+            T2, Z2, v2 = d.permuteschur(T, Z, p)
+            np.testing.assert_allclose(Z2 @ T2 @ Z2.T, A, atol=1e-10)
+            np.testing.assert_allclose(np.tril(T2, -2), 0, atol=0)
+            key = {"LM": -np.abs(v2), "LR": -v2.real, "SR": v2.real}[which]
+            assert np.all(np.diff(key) >= -1e-12)
+            V = d.schur2eigvecs(T2)
+            np.testing.assert_allclose(T2 @ V, V * v2, atol=1e-9)
+            np.testing.assert_allclose(np.linalg.norm(V, axis=0), 1.0, rtol=1e-12)
+            Vo = ko.schur2eigvecs(T2)
+            np.testing.assert_allclose(np.abs(np.sum(np.conj(V) * Vo, axis=0)), 1.0, rtol=1e-8)
+            oT, oZ, ov = ko.permuteschur(T, Z, p)
+            np.testing.assert_allclose(ov, v2, atol=1e-12)
+    # restore_arnoldi_form: A V U = V U H + v f' stays a Krylov relation in Hessenberg form
+    K, keep = 9, 5
+    H = np.triu(rng.standard_normal((K, K)))
+    U = np.linalg.qr(rng.standard_normal((K, K)))[0]
+    f = rng.standard_normal(K)
+    H1, U1 = H.copy(), U.copy()
+    d.restore_arnoldi_form(U1, H1, f, keep)
+    H2, U2 = H.copy(), U.copy()
+    ko.restore_arnoldi_form(U2, H2, f, keep)
+    np.testing.assert_allclose(H1[:keep + 1, :keep], H2[:keep + 1, :keep], atol=1e-12)
+    np.testing.assert_allclose(U1[:, :keep], U2[:, :keep], atol=1e-12)
+    np.testing.assert_allclose(np.tril(H1[:keep + 1, :keep], -2), 0, atol=1e-14)
+    np.testing.assert_allclose(U1.T @ U1, np.eye(K), atol=1e-12)

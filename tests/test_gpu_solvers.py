@@ -445,7 +445,7 @@ def test_blocklanczos_reference_properties():
     A = _mat_with_eigrepetition(rng, n, 2)
     X0 = [rng.random(n) for _ in range(2)]
     ev = np.linalg.eigvalsh(A)
-    ctx = kk.B200Context(n, 64)
+    ctx = kk.B200Context(n, 128)
     op = _dense_sym_op(ctx, A)
     n1 = n // 2
     n2 = n - n1
@@ -467,7 +467,7 @@ def test_blocklanczos_reference_properties():
     A = _mat_with_eigrepetition(rng, N, 4)
     X0 = [rng.random(N) for _ in range(4)]
     ev = np.linalg.eigvalsh(A)
-    ctx = kk.B200Context(N, 140)
+    ctx = kk.B200Context(N, 800)
     op = _dense_sym_op(ctx, A)
     blk = lambda: kk.Block([ctx.from_host(x) for x in X0])
     alg = kk.BlockLanczos(krylovdim=N, maxiter=10, tol=tol, eager=True, verbosity=0)
@@ -486,7 +486,7 @@ def test_blocklanczos_reference_properties():
     X0 = [rng.random(N) for _ in range(5)]
     v0 = np.linalg.eigvalsh(A)[:n]
     op = _dense_sym_op(ctx, A)
-    va, _, _ = kk.eigsolve(op, blk5 := kk.Block([ctx.from_host(x) for x in X0]), n, "SR",
+    va, _, _ = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), n, "SR",
                            kk.BlockLanczos(krylovdim=3 * n // 2, maxiter=1, tol=1e-12, verbosity=0))
     vb, _, infob = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), n, "SR",
                                kk.BlockLanczos(krylovdim=3 * n // 2, maxiter=2, tol=1e-12, verbosity=0))
@@ -494,13 +494,12 @@ def test_blocklanczos_reference_properties():
     ovb, _, oinfob = ko.eigsolve_blocklanczos(A, X0, n, "SR", krylovdim=3 * n // 2, maxiter=2, tol=1e-12)
     np.testing.assert_allclose(vb, ovb, rtol=1e-8, atol=1e-9)
     assert infob.numops == oinfob["numops"] and infob.numiter == oinfob["numiter"] == 2
-    del blk5
     ctx.close()
     # --- block size 1 reproduces Lanczos (:685-712)
     A = rng.random((2 * N, 2 * N)) - 0.5
     A = (A + A.T) / 2
     x0 = rng.random(2 * N)
-    ctx = kk.B200Context(2 * N, 80)
+    ctx = kk.B200Context(2 * N, 200)
     op = _dense_sym_op(ctx, A)
     e1, _, j1 = kk.eigsolve(op, ctx.from_host(x0), n, "SR",
                             kk.Lanczos(krylovdim=2 * n, maxiter=10, tol=tol, verbosity=0))
@@ -521,7 +520,7 @@ def test_blocklanczos_toric_code_degenerate_ground_space():
     M = H.shape[0]
     rng = np.random.default_rng(1)
     X0 = [rng.random(M) for _ in range(5)]
-    ctx = kk.B200Context(M, 120)
+    ctx = kk.B200Context(M, 190)
     op = kk.B200CSR.from_scipy(ctx, (-H).tocsr())
     alg = kk.BlockLanczos(tol=1e-6, maxiter=1, verbosity=0)
     D, U, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 10, "SR", alg)
@@ -537,6 +536,67 @@ def test_blocklanczos_toric_code_degenerate_ground_space():
     np.testing.assert_allclose(D[:4], -16.0, atol=1e-7)
     G = np.column_stack([u.to_host() for u in U[:4]])
     np.testing.assert_allclose(G.T @ G, np.eye(4), atol=1e-7)
+    ctx.close()
+
+
+@pytest.mark.parametrize("orth", ["cgs2", "mgs2", "cgsr", "mgsr"])
+def test_arnoldi_eigsolve_and_schursolve(orth):
+    """SURVEY §8f-4 / test/eigsolve.jl:138-300 through the device path: non-symmetric real operator,
+    complex Ritz pairs returned as (re, im) device vectors; SR half + LR half = eigvals(A), A V = V D,
+    orthonormal Schur vectors with A Q = Q T; restarted runs agree with the oracle's values."""
+    o = getattr(kk, orth)
+    oo = ko.Orth(o.tag, o.eta) if o.is_ir else ko.Orth(o.tag)
+    rng = np.random.default_rng(31)
+    n, N, tol = 10, 100, 1e-12
+    A = rng.random((n, n)) - 0.5
+    v = rng.random(n)
+    n1 = n // 2
+    n2 = n - n1
+    ctx = kk.B200Context(n, 120)
+    op = kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A))
+    D1, V1, i1 = kk.eigsolve(op, ctx.from_host(v), n1, "SR", kk.Arnoldi(orth=o, krylovdim=n, maxiter=1, tol=tol, verbosity=0))
+    D2, V2, i2 = kk.eigsolve(op, ctx.from_host(v), n2, "LR", kk.Arnoldi(orth=o, krylovdim=2 * n, maxiter=1, tol=tol, verbosity=0))
+    def srt(D):
+        D = np.asarray(D)
+        D = D[np.argsort(-D.imag, kind="stable")]
+        return D[np.argsort(D.real, kind="stable")]
+    D2s = srt(D2)
+    np.testing.assert_allclose(np.concatenate([D1[:n1], D2s[len(D2s) - n2:]]), srt(np.linalg.eigvals(A)),
+                               rtol=1e-9, atol=1e-11)
+    for D, V in ((D1, V1), (D2, V2)):
+        Uh = np.column_stack([x.to_host() for x in V])
+        np.testing.assert_allclose(A @ Uh, Uh * D, atol=1e-9)
+    oD1, _, oi1 = ko.eigsolve_arnoldi(A, v, n1, "SR", krylovdim=n, maxiter=1, tol=tol, orth=oo)
+    np.testing.assert_allclose(D1, oD1, rtol=1e-9, atol=1e-11)
+    assert i1.numops == oi1["numops"] and i1.converged == oi1["converged"]
+    T, Q, vals, info = kk.schursolve(op, ctx.from_host(v), n1, "SR", kk.Arnoldi(orth=o, krylovdim=n, maxiter=1, tol=tol, verbosity=0))
+    Qh = np.column_stack([q.to_host() for q in Q])
+    np.testing.assert_allclose(Qh.T @ Qh, np.eye(Qh.shape[1]), atol=1e-10)
+    np.testing.assert_allclose(A @ Qh, Qh @ T, atol=1e-9)
+    np.testing.assert_allclose(vals, D1[:len(vals)], rtol=1e-9, atol=1e-11)
+    ctx.close()
+    # restarts
+    A = rng.random((N, N)) - 0.5
+    v = rng.random(N)
+    ctx = kk.B200Context(N, 200)
+    op = kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A))
+    Dfull = np.linalg.eigvals(A)
+    Dfull = Dfull[np.argsort(-Dfull.imag, kind="stable")]
+    for which, key in (("SR", lambda d: d.real), ("LR", lambda d: -d.real), ("LM", lambda d: -np.abs(d))):
+        alg = kk.Arnoldi(orth=o, krylovdim=3 * n, maxiter=20, tol=tol, eager=True, verbosity=0)
+        Dw, Vw, iw = kk.eigsolve(op, ctx.from_host(v), n, which, alg)
+        l = iw.converged
+        assert l > 0 and iw.numiter > 1
+        want = Dfull[np.argsort(key(Dfull), kind="stable")][:l]
+        if which == "LM":
+            np.testing.assert_allclose(np.abs(Dw[:l]), np.abs(want), rtol=1e-8)
+        else:
+            np.testing.assert_allclose(Dw[:l], want, rtol=1e-8, atol=1e-10)
+        Uw = np.column_stack([x.to_host() for x in Vw])
+        Rw = np.column_stack([x.to_host() for x in iw.residual])
+        np.testing.assert_allclose(A @ Uw, Uw * Dw + Rw, atol=1e-9)
+        np.testing.assert_allclose(iw.normres, np.linalg.norm(Rw, axis=0), rtol=1e-6, atol=1e-13)
+        del Vw, iw
     ctx.close()
 
 

@@ -447,3 +447,53 @@ def test_blocklanczos_toric_oracle():
     D, _, info = ko.eigsolve_blocklanczos((-H).tocsr(), X0, 10, "SR", krylovdim=100, maxiter=1, tol=1e-6)
     assert np.sum(np.abs(D[:10] + 16.0) < 2.0 - 1e-6) == 4
     assert np.sum(np.abs(D[:10] + 16.0) < 1e-6) == 4
+
+
+def _sort_real_then_imag(D):
+    """sort(sort(D; by = imag, rev = true); alg = MergeSort, by = real) — test/eigsolve.jl:209."""
+    D = np.asarray(D)
+    D = D[np.argsort(-D.imag, kind="stable")]
+    return D[np.argsort(D.real, kind="stable")]
+
+
+@pytest.mark.parametrize("orth", [ko.Orth(ko.CGS2), ko.Orth(ko.MGS2), ko.Orth(ko.CGSIR, 0.75), ko.Orth(ko.MGSIR, 0.75)])
+def test_arnoldi_eigsolve_oracle(orth):
+    """test/eigsolve.jl:138-300 (Arnoldi, real scalar type): SR half + LR half reproduce eigvals(A),
+    A V = V D for the complex eigenvectors, partial Schur relation for schursolve; iterative runs with
+    restarts converge to the extremal eigenvalues and satisfy A V = V D + R."""
+    rng = np.random.default_rng(7)
+    n, N, tol = 10, 100, 1e-12
+    A = rng.random((n, n)) - 0.5
+    v = rng.random(n)
+    n1 = n // 2
+    n2 = n - n1
+    D1, V1, i1 = ko.eigsolve_arnoldi(A, v, n1, "SR", krylovdim=n, maxiter=1, tol=tol, orth=orth)
+    D2, V2, i2 = ko.eigsolve_arnoldi(A, v, n2, "LR", krylovdim=2 * n, maxiter=1, tol=tol, orth=orth)
+    D = _sort_real_then_imag(np.linalg.eigvals(A))
+    D2s = _sort_real_then_imag(D2)
+    np.testing.assert_allclose(np.concatenate([D1[:n1], D2s[len(D2s) - n2:]]), D, rtol=1e-9, atol=1e-11)
+    U1, U2 = np.column_stack(V1), np.column_stack(V2)
+    np.testing.assert_allclose(A @ U1, U1 * D1, atol=1e-9)
+    np.testing.assert_allclose(A @ U2, U2 * D2, atol=1e-9)
+    T, Vs, vals, info = ko.schursolve_arnoldi(A, v, n1, "SR", krylovdim=n, maxiter=1, tol=tol, orth=orth)
+    Q = np.column_stack(Vs)
+    np.testing.assert_allclose(Q.T @ Q, np.eye(Q.shape[1]), atol=1e-10)
+    np.testing.assert_allclose(A @ Q, Q @ T, atol=1e-9)
+    with pytest.raises(ValueError):
+        ko.eigsolve_arnoldi(A, v, n + 1, "LM", krylovdim=n, maxiter=1, tol=tol, orth=orth)
+
+    A = rng.random((N, N)) - 0.5
+    v = rng.random(N)
+    Dfull = np.linalg.eigvals(A)
+    Dfull = Dfull[np.argsort(-Dfull.imag, kind="stable")]
+    for which, key in (("SR", lambda d: d.real), ("LR", lambda d: -d.real), ("LM", lambda d: -np.abs(d))):
+        Dw, Vw, iw = ko.eigsolve_arnoldi(A, v, n, which, krylovdim=3 * n, maxiter=20, tol=tol, orth=orth, eager=True)
+        l = iw["converged"]
+        assert l > 0 and iw["numiter"] > 1
+        want = Dfull[np.argsort(key(Dfull), kind="stable")][:l]
+        if which == "LM":
+            np.testing.assert_allclose(np.abs(Dw[:l]), np.abs(want), rtol=1e-8)
+        else:
+            np.testing.assert_allclose(Dw[:l], want, rtol=1e-8, atol=1e-10)
+        Uw, Rw = np.column_stack(Vw), np.column_stack(iw["residual"])
+        np.testing.assert_allclose(A @ Uw, Uw * Dw + Rw, atol=1e-9)
