@@ -24,6 +24,7 @@ from .eigsolve import eigsolve
 from .linsolve import linsolve
 from .schursolve import ComplexVec, schursolve
 from .lssolve import lssolve
+from .expintegrator import expintegrator, exponentiate
 from .svdsolve import svdsolve
 from . import factorizations
 from .factorizations.blocklanczos import Block

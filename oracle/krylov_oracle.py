@@ -1150,6 +1150,150 @@ def lssolve_lsmr(A, b, maxiter=100, krylovdim=30, tol=1e-12, orth: "Orth | None"
             return x, info(0, r, abszetabar, numiter, numops)
 
 
+# ------------------------------------------------------------------ expintegrator ---------
+
+def lanczos_initialize_inplace(A, x0, f: LanczosFact, orth: Orth):
+    """initialize!(iter, state) — factorizations/lanczos.jl:223-249."""
+    while len(f.V) > 1:
+        f.V.pop()
+    f.V[0] = x0 * (1 / norm(x0))
+    w = apply(A, f.V[0])
+    r, alpha = orthogonalize_vec(w, f.V[0], orth)
+    f.k = 1
+    f.alphas[:] = [alpha]
+    f.betas[:] = [norm(r)]
+    f.r = r
+    return f
+
+
+def expintegrator(A, t, u, method="lanczos", orth: Orth = Orth(MGS2), krylovdim=30, maxiter=100, tol=1e-12,
+                  eager=False):
+    """expintegrator(A, t, u::Tuple, alg) — matrixfun/expintegrator.jl:101-323, real t.
+    y(t) = ϕ₀(tA) u₀ + t ϕ₁(tA) u₁ + … + tᵖ ϕₚ(tA) uₚ, the solution of y' = A y + Σ_j t^j/j! u_{j+1},
+    by adaptive Krylov time stepping (Niesen & Wright).  `tol` is the error per unit time."""
+    from scipy.linalg import expm
+    u = tuple(u)
+    if len(u) == 1:
+        u = (u[0], np.zeros_like(u[0]))
+    p = len(u) - 1
+    lanczos = method == "lanczos"
+    u0 = u[0]
+    Au0 = apply(A, u0)
+    numops = 1
+    w0 = u0 * 1.0
+    K = krylovdim
+    eta = tol
+    totalerr = 0.0
+    sgn = float(np.sign(t))
+    tau = abs(t)
+    if math.isfinite(tau):
+        dtau, dtaumin, maxerr = tau, tau / maxiter, tau * eta
+    else:
+        dtau, dtaumin, maxerr = 1.0, 0.0, eta
+    delta, gamma = 1.2, 0.8
+    tau0 = 0.0
+    w = [None] * (p + 1)
+    w[0] = w0
+    w[1] = Au0 * 1.0
+
+    def fill_w(first_apply_done):
+        nonlocal numops
+        for j in range(1, p + 1):
+            if j > 1 or not first_apply_done:
+                w[j] = apply(A, w[j - 1])
+                numops += 1
+            lfac = 1
+            for l in range(0, p - j + 1):
+                w[j] = w[j] + ((sgn * tau0) ** l / lfac) * u[j + l]
+                lfac *= l + 1
+
+    fill_w(True)
+    beta = norm(w[p])
+    if beta < eta and p == 1:
+        return w0, dict(converged=1, residual=None, normres=beta, numiter=0, numops=numops)
+    if lanczos:
+        f = lanczos_initialize(A, w[p], orth)
+        rq = lambda: (np.diag(f.alphas) + np.diag(f.betas[:f.k - 1], 1) + np.diag(f.betas[:f.k - 1], -1))
+        init_inplace = lambda x: lanczos_initialize_inplace(A, x, f, orth)
+        expand = lambda: lanczos_expand(A, f, orth)
+    else:
+        f = arnoldi_initialize(A, w[p], orth)
+        rq = lambda: arnoldi_rayleighquotient(f)
+        init_inplace = lambda x: arnoldi_initialize_inplace(A, x, f, orth)
+        expand = lambda: arnoldi_expand(A, f, orth)
+    numops += 1
+    numiter = 1
+
+    def small_exp(K, dt):
+        H = np.zeros((K + p + 1, K + p + 1))
+        H[:K, :K] = rq() * (sgn * dt)
+        H[0, K] = 1
+        for i in range(1, p + 1):
+            H[K + i - 1, K + i] = 1
+        return expm(H)
+
+    def take_step(K, dt, expH):
+        nonlocal w0
+        jfac = 1
+        for j in range(1, p):
+            w0 = w0 + ((sgn * dt) ** j / jfac) * w[j]
+            jfac *= j + 1
+        wp = unproject(np.zeros_like(w[p]), f.V, expH[:K, K + p - 1])
+        wp = wp + expH[K - 1, K + p] * f.r
+        w[p] = wp
+        w0 = w0 + (beta * (sgn * dt) ** p) * wp
+        w[0] = w0
+
+    while True:
+        K = f.k
+        if K == krylovdim:
+            if numiter < maxiter:
+                dtau = min(dtau, tau - tau0)
+                if math.isfinite(tau):
+                    dtaumin = (tau - tau0) / (maxiter - numiter + 1)
+            else:
+                dtau = tau - tau0
+            expH = small_exp(K, dtau)
+            eps_ = abs(dtau ** p * beta * f.normres() * expH[K - 1, K + p])
+            omega = eps_ / (dtau * eta)
+            q = K / 2
+            while numiter < maxiter and omega >= 1 and dtau > dtaumin:
+                eps_prev, dtau_prev = eps_, dtau
+                dtau = max(dtau * (gamma / omega) ** (1 / (q + 1)), dtaumin)
+                expH = small_exp(K, dtau)
+                eps_ = abs(dtau ** p * beta * f.normres() * expH[K - 1, K + p])
+                omega = eps_ / (dtau * eta)
+                q = max(0.0, math.log(eps_ / eps_prev) / math.log(dtau / dtau_prev) - 1)
+            tau0 = tau0 + dtau if numiter < maxiter else tau
+            totalerr += eps_
+            take_step(K, dtau, expH)
+            if omega < gamma:
+                dtau *= (gamma / omega) ** (1 / (q + 1))
+        elif f.normres() <= (tau - tau0) * eta or eager:
+            dt = tau - tau0
+            expH = small_exp(K, dt)
+            eps_ = abs(dt ** p * beta * f.normres() * expH[K - 1, K + p])
+            omega = eps_ / (dt * eta)
+            if omega < 1:
+                totalerr += eps_
+                take_step(K, dt, expH)
+                tau0 = tau
+        if tau0 >= tau:
+            return w0, dict(converged=int(totalerr <= maxerr), residual=None, normres=totalerr,
+                            numiter=numiter, numops=numops)
+        if K < krylovdim:
+            expand()
+            numops += 1
+        else:
+            fill_w(False)
+            beta = norm(w[p])
+            if beta < eta and p == 1:
+                return w0, dict(converged=1, residual=None, normres=beta, numiter=numiter, numops=numops)
+            init_inplace(w[p])
+            numops += 1
+            numiter += 1
+
+
 # ------------------------------------------------------------------ GKL / svdsolve --------
 
 @dataclass

@@ -600,6 +600,82 @@ def test_arnoldi_eigsolve_and_schursolve(orth):
     ctx.close()
 
 
+def _phi(A, v, p):
+    """ϕ_p(A) v through the augmented-matrix exponential — test/expintegrator.jl:1-13."""
+    from scipy.linalg import expm
+    m = A.shape[0]
+    if p == 0:
+        return expm(A) @ v
+    Ap = np.zeros((m + p, m + p))
+    Ap[:m, :m] = A
+    Ap[:m, m] = v
+    for k in range(1, p):
+        Ap[m + k - 1, m + k] = 1
+    return expm(Ap)[:m, -1]
+
+
+@pytest.mark.parametrize("method", ["lanczos", "arnoldi"])
+def test_exponentiate_and_expintegrator(method):
+    """SURVEY §8f-4 / test/expintegrator.jl:15-190 (real time steps): exponentiate reproduces exp(A)
+    column by column; expintegrator reproduces Σ_j t^j ϕ_j(tA) u_j for p = 1..5 in the full-space and in
+    the restarted (krylovdim ≪ N, eager) regime; loose tolerance gives proportionally loose answers;
+    the device result follows the oracle step for step."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(41)
+    n, N = 10, 100
+    Alg = kk.Lanczos if method == "lanczos" else kk.Arnoldi
+    for orth in ("cgs2", "mgs2", "cgsr", "mgsr"):
+        o = getattr(kk, orth)
+        A = rng.random((n, n)) - 0.5
+        if method == "lanczos":
+            A = (A + A.T) / 2
+        ctx = kk.B200Context(n, 80)
+        op = kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A))
+        alg = Alg(orth=o, krylovdim=n, maxiter=2, tol=1e-12, verbosity=0)
+        W = np.zeros((n, n))
+        for k in range(n):
+            w, info = kk.exponentiate(op, 1.0, ctx.from_host(np.eye(n)[:, k]), alg)
+            W[:, k] = w.to_host()
+        np.testing.assert_allclose(W, expm(A), rtol=1e-9, atol=1e-11)
+        for t in (rng.random(), -rng.random()):
+            for p in range(1, 6):
+                u = tuple(rng.random(n) for _ in range(p + 1))
+                w, info = kk.expintegrator(op, t, tuple(ctx.from_host(x) for x in u), alg)
+                w2 = expm(t * A) @ u[0]
+                for j in range(1, p + 1):
+                    w2 = w2 + t ** j * _phi(t * A, u[j], j)
+                assert info.converged > 0
+                np.testing.assert_allclose(w.to_host(), w2, rtol=1e-9, atol=1e-11)
+        with pytest.raises(TypeError):
+            kk.exponentiate(op, 1j, ctx.from_host(np.eye(n)[:, 0]), alg)
+        ctx.close()
+    A = 0.5 * (rng.random((N, N)) - 0.5)
+    if method == "lanczos":
+        A = (A + A.T) / 2
+    ctx = kk.B200Context(N, 80)
+    op = kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A))
+    restarts = 0
+    for t in (0.9 + rng.random(), -0.9 - rng.random()):
+        for p in range(1, 6):
+            u = tuple(rng.random(N) for _ in range(p + 1))
+            alg = Alg(krylovdim=n, maxiter=100, tol=1e-12, eager=True, verbosity=0)
+            w, info = kk.expintegrator(op, t, tuple(ctx.from_host(x) for x in u), alg)
+            ow, oinfo = ko.expintegrator(A, t, u, method, ko.Orth(ko.MGS2), krylovdim=n, maxiter=100, tol=1e-12, eager=True)
+            w2 = expm(t * A) @ u[0]
+            for j in range(1, p + 1):
+                w2 = w2 + t ** j * _phi(t * A, u[j], j)
+            assert info.converged > 0
+            np.testing.assert_allclose(w.to_host(), w2, rtol=1e-8, atol=1e-10)
+            np.testing.assert_allclose(w.to_host(), ow, rtol=1e-8, atol=1e-10)
+            assert info.numiter == oinfo["numiter"] and info.numops == oinfo["numops"]
+            restarts += info.numiter - 1
+            alg = Alg(krylovdim=n, maxiter=100, tol=1e-3, eager=True, verbosity=0)
+            w, info = kk.expintegrator(op, t, tuple(ctx.from_host(x) for x in u), alg)
+            np.testing.assert_allclose(w.to_host(), w2, atol=1e-2 * abs(t))
+    assert restarts > 0
+    ctx.close()
+
+
 def test_invariant_subspace_early_exit():
     """eigsolve/lanczos.jl:38-44, 45: beta <= tol stops the expansion loop early (also inside
     b2k_lanczos_expand_many) and reports the exact eigenvalues of the invariant subspace."""

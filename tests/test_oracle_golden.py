@@ -497,3 +497,59 @@ def test_arnoldi_eigsolve_oracle(orth):
             np.testing.assert_allclose(Dw[:l], want, rtol=1e-8, atol=1e-10)
         Uw, Rw = np.column_stack(Vw), np.column_stack(iw["residual"])
         np.testing.assert_allclose(A @ Uw, Uw * Dw + Rw, atol=1e-9)
+
+
+def _phi(A, v, p):
+    """test/expintegrator.jl:1-13."""
+    from scipy.linalg import expm
+    m = A.shape[0]
+    if p == 0:
+        return expm(A) @ v
+    Ap = np.zeros((m + p, m + p))
+    Ap[:m, :m] = A
+    Ap[:m, m] = v
+    for k in range(1, p):
+        Ap[m + k - 1, m + k] = 1
+    return expm(Ap)[:m, -1]
+
+
+@pytest.mark.parametrize("method", ["lanczos", "arnoldi"])
+def test_expintegrator_oracle(method):
+    """test/expintegrator.jl:15-190, real t: exponentiate = exp(A) column by column; expintegrator =
+    Σ_j t^j ϕ_j(tA) u_j for p = 1..5, full-space and restarted; tol = 1e-3 stays within 1e-2|t|."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(13)
+    n, N = 10, 100
+    for orth in (ko.Orth(ko.CGS2), ko.Orth(ko.MGS2), ko.Orth(ko.CGSIR, 0.75), ko.Orth(ko.MGSIR, 0.75)):
+        A = rng.random((n, n)) - 0.5
+        if method == "lanczos":
+            A = (A + A.T) / 2
+        W = np.column_stack([ko.expintegrator(A, 1.0, (np.eye(n)[:, k],), method, orth, krylovdim=n, maxiter=2,
+                                              tol=1e-12)[0] for k in range(n)])
+        np.testing.assert_allclose(W, expm(A), rtol=1e-9, atol=1e-11)
+        for t in (rng.random(), -rng.random()):
+            for p in range(1, 6):
+                u = tuple(rng.random(n) for _ in range(p + 1))
+                w, info = ko.expintegrator(A, t, u, method, orth, krylovdim=n, maxiter=2, tol=1e-12)
+                w2 = expm(t * A) @ u[0]
+                for j in range(1, p + 1):
+                    w2 = w2 + t ** j * _phi(t * A, u[j], j)
+                assert info["converged"] > 0
+                np.testing.assert_allclose(w, w2, rtol=1e-9, atol=1e-11)
+    A = 0.5 * (rng.random((N, N)) - 0.5)
+    if method == "lanczos":
+        A = (A + A.T) / 2
+    restarts = 0
+    for t in (0.9 + rng.random(), -0.9 - rng.random()):
+        for p in range(1, 6):
+            u = tuple(rng.random(N) for _ in range(p + 1))
+            w, info = ko.expintegrator(A, t, u, method, ko.Orth(ko.MGS2), krylovdim=n, maxiter=100, tol=1e-12, eager=True)
+            w2 = expm(t * A) @ u[0]
+            for j in range(1, p + 1):
+                w2 = w2 + t ** j * _phi(t * A, u[j], j)
+            assert info["converged"] > 0
+            np.testing.assert_allclose(w, w2, rtol=1e-8, atol=1e-10)
+            restarts += info["numiter"] - 1
+            w, info = ko.expintegrator(A, t, u, method, ko.Orth(ko.MGS2), krylovdim=n, maxiter=100, tol=1e-3, eager=True)
+            np.testing.assert_allclose(w, w2, atol=1e-2 * abs(t))
+    assert restarts > 0
