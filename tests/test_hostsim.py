@@ -1,0 +1,117 @@
+"""Host-side driver logic without a GPU: the bodies of the GPU parity tests, run against
+tests/hostsim.py (a numpy stand-in for the C-ABI, test infrastructure only).  What this covers is
+everything ABOVE the C-ABI — restart bookkeeping, Schur reordering, block bookkeeping, step-size
+control, handle lifetimes and slab column budgets; the kernels themselves are covered by `-m gpu`."""
+import numpy as np
+import pytest
+
+import krylovkit_jl_b200 as kk
+from krylovkit_jl_b200 import _lib as L
+from oracle import krylov_oracle as ko
+
+import hostsim
+import test_gpu_solvers as G
+
+
+@pytest.fixture()
+def sim():
+    with hostsim.installed() as lib:
+        yield lib
+    assert not isinstance(L._lib, hostsim.HostSimLib)
+
+
+def test_simulator_is_not_the_product(sim):
+    """The stand-in lives under tests/ only and the package cannot reach it."""
+    import os
+    pkg = os.path.dirname(os.path.abspath(kk._lib.__file__))
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "hostsim" not in src and "from oracle" not in src and "import oracle" not in src
+
+
+def test_vector_interface_and_errors(sim):
+    ctx = kk.B200Context(50, 6)
+    x = ctx.from_host(np.arange(50.0))
+    y = x.copy().scale_(2.0)
+    assert y.inner(x) == pytest.approx(2 * np.sum(np.arange(50.0) ** 2))
+    y = y.add_(x, -2.0)
+    assert y.norm() == 0.0
+    vs = [ctx.empty() for _ in range(4)]
+    with pytest.raises(L.B200Error):                      # slab exhausted -> loud failure, no silent growth
+        ctx.empty()
+    del vs
+    ctx.empty()
+    ctx.close()
+
+
+def test_bicgstab(sim):
+    G.test_bicgstab_matches_oracle_and_reference_properties()
+
+
+@pytest.mark.parametrize("orth", ["mgs", "cgs2", "mgsr"])
+def test_lsmr(sim, orth):
+    G.test_lsmr_matches_oracle_and_reference_properties(orth)
+
+
+def test_blocklanczos(sim):
+    G.test_blocklanczos_reference_properties()
+
+
+@pytest.mark.parametrize("orth", ["cgs2", "mgs2", "cgsr", "mgsr"])
+def test_arnoldi_eigsolve_and_schursolve(sim, orth):
+    G.test_arnoldi_eigsolve_and_schursolve(orth)
+
+
+@pytest.mark.parametrize("method", ["lanczos", "arnoldi"])
+def test_exponentiate_and_expintegrator(sim, method):
+    G.test_exponentiate_and_expintegrator(method)
+
+
+def test_cg_literal_path(sim):
+    G.test_cg_matches_oracle(False)
+
+
+def test_lanczos_eigsolve_with_restarts(sim):
+    """eigsolve(::Lanczos) host loop incl. the native restart helper, vs the oracle."""
+    nx, ny = 40, 25
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(7, nx * ny)
+    ctx = kk.B200Context(nx * ny, 40)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    alg = kk.Lanczos(orth=kk.cgs2, krylovdim=20, maxiter=60, tol=1e-10, verbosity=0)
+    D, V, info = kk.eigsolve(op, ctx.from_host(x0), 3, "SR", alg)
+    oD, _, oinfo = ko.eigsolve_lanczos(A, x0, 3, "SR", krylovdim=20, maxiter=60, tol=1e-10, orth=ko.Orth(ko.CGS2))
+    assert info.converged >= 3 and info.numiter > 1
+    np.testing.assert_allclose(D[:3], oD[:3], rtol=1e-10)
+    np.testing.assert_allclose(D[:3], ko.laplace_eigenvalues(nx, ny)[:3], rtol=1e-9)
+    assert info.numiter == oinfo["numiter"] and info.numops == oinfo["numops"]
+    for lam, v in zip(D[:3], V[:3]):
+        vh = v.to_host()
+        assert np.linalg.norm(A @ vh - lam * vh) < 1e-8
+    ctx.close()
+
+
+@pytest.mark.parametrize("pair", G.PAIRS, ids=G.IDS)
+def test_lanczos_and_arnoldi_steps(sim, pair):
+    G.test_lanczos_steps_match_oracle(pair, False)
+    G.test_arnoldi_steps_match_oracle(pair)
+
+
+@pytest.mark.parametrize("pair", [G.PAIRS[2], G.PAIRS[3]], ids=["cgs2", "mgs2"])
+@pytest.mark.parametrize("literal", [False, True])
+def test_gmres(sim, pair, literal):
+    G.test_gmres_matches_oracle(pair, literal)
+
+
+@pytest.mark.parametrize("pair", [G.PAIRS[2], G.PAIRS[3], G.PAIRS[4]], ids=["cgs2", "mgs2", "cgsr"])
+def test_svdsolve(sim, pair):
+    G.test_svdsolve_matches_oracle_f64(pair)
+
+
+def test_misc_drivers(sim):
+    G.test_eigsolve_unconverged_fixed_cycles_matches_oracle()
+    G.test_block_primitives_gpu()
+    G.test_invariant_subspace_early_exit()
+    G.test_zero_start_vector_raises()
