@@ -520,16 +520,19 @@ def test_blocklanczos_toric_code_degenerate_ground_space():
     M = H.shape[0]
     rng = np.random.default_rng(1)
     X0 = [rng.random(M) for _ in range(5)]
-    ctx = kk.B200Context(M, 190)
+    # every converged Ritz pair is returned (here ~80 of the 100), each with its residual vector
+    ctx = kk.B200Context(M, 480)
     op = kk.B200CSR.from_scipy(ctx, (-H).tocsr())
     alg = kk.BlockLanczos(tol=1e-6, maxiter=1, verbosity=0)
     D, U, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 10, "SR", alg)
     assert np.sum(np.abs(D[:10] + 16.0) < 2.0 - 1e-6) == 4
     assert np.sum(np.abs(D[:10] + 16.0) < 1e-6) == 4
+    assert len(U) == max(10, info.converged) and len(info.residual) == len(U)
+    del U, info
     # map input: any callable on device vectors
     D, U, info = kk.eigsolve(lambda x: op(x), kk.Block([ctx.from_host(x) for x in X0]), 10, "SR", alg)
     assert np.sum(np.abs(D[:10] + 16.0) < 1e-6) == 4
-    del U
+    del U, info
     alg = kk.BlockLanczos(tol=1e-8, krylovdim=40, maxiter=30, verbosity=0)
     D, U, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 4, "SR", alg)
     assert info.converged >= 4 and info.numiter > 1

@@ -115,3 +115,7 @@ def test_misc_drivers(sim):
     G.test_block_primitives_gpu()
     G.test_invariant_subspace_early_exit()
     G.test_zero_start_vector_raises()
+
+
+def test_blocklanczos_toric(sim):
+    G.test_blocklanczos_toric_code_degenerate_ground_space()
