@@ -405,6 +405,10 @@ def test_lsmr_matches_oracle_and_reference_properties(orth):
     ox12, oinfo12 = ko.lssolve_lsmr(A, b, maxiter=12, tol=0.0, krylovdim=5, orth=oo)
     np.testing.assert_allclose(x12, ox12, rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(info12.normres, oinfo12["normres"], rtol=1e-8)
+    # issue #133 (test/issues.jl:21-29): literal fixture
+    x, info = kk.lssolve(np.eye(2), np.array([1.0, 0.0]), kk.LSMR(orth=o, verbosity=0))
+    assert np.array_equal(x, [1.0, 0.0])
+    assert info.converged == 1 and info.numiter == 1 and info.numops == 2 and info.normres == 0.0
     # sparse rectangular operator as an (A, Aᵀ) pair
     As = sp.random(3000, 800, density=0.01, random_state=4).tocsr() + sp.eye(3000, 800).tocsr()
     bs = rng.random(3000)

@@ -553,3 +553,10 @@ def test_expintegrator_oracle(method):
             w, info = ko.expintegrator(A, t, u, method, ko.Orth(ko.MGS2), krylovdim=n, maxiter=100, tol=1e-3, eager=True)
             np.testing.assert_allclose(w, w2, atol=1e-2 * abs(t))
     assert restarts > 0
+
+
+def test_issue133_lssolve_identity_fixture():
+    """test/issues.jl:21-29 (issue #133), a literal known-answer fixture for LSMR."""
+    x, info = ko.lssolve_lsmr(np.eye(2), np.array([1.0, 0.0]))
+    assert np.array_equal(x, [1.0, 0.0])
+    assert info["converged"] == 1 and info["numiter"] == 1 and info["numops"] == 2 and info["normres"] == 0.0
