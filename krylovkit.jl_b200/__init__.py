@@ -20,8 +20,8 @@ from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, ort
 from .vectors import B200Context, B200Vec, inner, norm
 
 __all__ = [n for n in dir() if not n.startswith("_")]
-from .eigsolve import eigsolve
-from .linsolve import linsolve
+from .eigsolve import eigselector, eigsolve
+from .linsolve import linselector, linsolve
 from .schursolve import ComplexVec, schursolve
 from .lssolve import lssolve
 from .expintegrator import expintegrator, exponentiate

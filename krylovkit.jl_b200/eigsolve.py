@@ -33,19 +33,88 @@ def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = N
     Returns (values, vectors, ConvergenceInfo).
     """
     if alg is None:
-        alg = BlockLanczos(**kwargs) if isinstance(x0, blz.Block) else Lanczos(**kwargs)
+        alg = eigselector(A, block=isinstance(x0, blz.Block), **kwargs)
+    elif kwargs:
+        raise TypeError(f"eigsolve: keyword arguments {sorted(kwargs)} only apply when no algorithm is passed")
+    checkwhich(which, alg)
     if isinstance(alg, BlockLanczos):
         if isinstance(x0, (list, tuple)):
             x0 = blz.Block(x0)
         return _eigsolve_blocklanczos(A, x0, howmany, which, alg)
     if isinstance(alg, Arnoldi):
-        if not isinstance(x0, B200Vec):
-            raise TypeError("eigsolve(Arnoldi): pass a device start vector (B200Vec)")
         from .schursolve import eigsolve_arnoldi
+        if not isinstance(x0, B200Vec):
+            return _eigsolve_arnoldi_host(A, x0, howmany, which, alg, device)
         return eigsolve_arnoldi(A, x0, howmany, which, alg)
     if not isinstance(x0, B200Vec):
         return _eigsolve_host(A, x0, howmany, which, alg, out_vectors, shard, nccl_uid, device)
     return _eigsolve_lanczos(A, x0, howmany, which, alg)
+
+
+def _host_issymmetric(A) -> bool:
+    """LinearAlgebra.issymmetric for the host matrix types the front end accepts."""
+    import scipy.sparse as sp
+    if sp.issparse(A):
+        return A.shape[0] == A.shape[1] and (abs(A - A.T)).nnz == 0
+    if isinstance(A, np.ndarray) and A.ndim == 2:
+        return A.shape[0] == A.shape[1] and bool(np.array_equal(A, A.T))
+    return False
+
+
+def eigselector(A, block: bool = False, issymmetric: bool | None = None, ishermitian: bool | None = None,
+                krylovdim: int | None = None, maxiter: int | None = None, tol: float | None = None,
+                qr_tol: float | None = None, orth=None, eager: bool = False, verbosity: int | None = None):
+    """eigselector — src/eigsolve/eigsolve.jl:238-321: Lanczos for symmetric problems, Arnoldi otherwise,
+    BlockLanczos for a Block start.  Symmetry is detected for host matrices (the AbstractMatrix method);
+    device operators and callables default to `issymmetric = false` like a Julia function does."""
+    from .algorithms import KrylovDefaults
+    if issymmetric is None:
+        issymmetric = _host_issymmetric(A)
+    if ishermitian is None:
+        ishermitian = issymmetric                      # real scalars only
+    kw = dict(maxiter=KrylovDefaults.maxiter if maxiter is None else maxiter,
+              tol=KrylovDefaults.tol if tol is None else tol,
+              orth=KrylovDefaults.orth if orth is None else orth, eager=eager,
+              verbosity=KrylovDefaults.verbosity if verbosity is None else verbosity)
+    if block:
+        if not (issymmetric or ishermitian):
+            raise ValueError("BlockLanczos requires a symmetric or hermitian linear map. A BlockArnoldi method "
+                             "has not yet been implemented")
+        return BlockLanczos(krylovdim=100 if krylovdim is None else krylovdim,
+                            qr_tol=KrylovDefaults.tol if qr_tol is None else qr_tol, **kw)
+    kd = KrylovDefaults.krylovdim if krylovdim is None else krylovdim
+    if issymmetric or ishermitian:
+        return Lanczos(krylovdim=kd, **kw)
+    return Arnoldi(krylovdim=kd, **kw)
+
+
+def checkwhich(which: str, alg) -> None:
+    """eigsolve.jl:210-222, 323-324: selector validity for the chosen algorithm (real arithmetic)."""
+    if which not in ("LM", "LR", "SR", "LI", "SI"):
+        raise ValueError(f"Unknown eigenvalue selector: which = {which}")
+    if which in ("LI", "SI"):
+        if isinstance(alg, (Lanczos, BlockLanczos)):
+            raise ValueError(f"Eigenvalue selector which = {which} invalid: real eigenvalues expected with "
+                             "Lanczos and BlockLanczos algorithms")
+        raise ValueError(f"Eigenvalue selector which = {which} invalid because it does not treat `λ` and "
+                         "`conj(λ)` equally: that needs complex arithmetic, which this real-only engine lacks")
+
+
+def _eigsolve_arnoldi_host(A, x0, howmany, which, alg, device=0):
+    """Host-buffer entry for the Arnoldi driver: upload, solve, download (complex numpy vectors)."""
+    import scipy.sparse as sp
+    from .schursolve import eigsolve_arnoldi
+    x0 = np.asarray(x0)
+    if not sp.issparse(A):
+        raise TypeError("eigsolve: host-side A must be a scipy sparse matrix")
+    n = x0.shape[0]
+    dtype = np.float32 if x0.dtype == np.float32 else np.float64
+    ctx = B200Context(n, alg.krylovdim + 12, dtype=dtype, device=device)
+    try:
+        op = B200CSR.from_scipy(ctx, A)
+        return eigsolve_arnoldi(op, ctx.from_host(x0), howmany, which, alg, to_host=True)
+    finally:
+        ctx.close()
 
 
 USE_NATIVE_RESTART = True      # b2k_host_lanczos_restart (C++) instead of the numpy loop below

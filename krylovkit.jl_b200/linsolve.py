@@ -26,7 +26,12 @@ def linsolve(A, b, x0=None, alg: GMRES | None = None, a0: float = 0.0, a1: float
     `tol` of the algorithm is the absolute residual tolerance; pass atol/rtol to get
     KrylovKit's tol = max(atol, rtol*‖b‖) (linsolve.jl:159-161)."""
     if alg is None:
-        alg = GMRES(**kwargs)
+        alg = linselector(A, b, atol=atol, rtol=rtol, **kwargs)
+        atol = rtol = None                              # already folded into alg.tol
+    elif kwargs:
+        raise TypeError(f"linsolve: keyword arguments {sorted(kwargs)} only apply when no algorithm is passed")
+    if isinstance(alg, (CG, BiCGStab)) and not isinstance(b, B200Vec):
+        return _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol)
     if isinstance(alg, CG):
         if not isinstance(b, B200Vec):
             raise TypeError("linsolve(CG): pass device vectors (B200Vec)")
@@ -51,11 +56,35 @@ def linsolve(A, b, x0=None, alg: GMRES | None = None, a0: float = 0.0, a1: float
     return _gmres(A, b, x0, alg, a0, a1)
 
 
+def linselector(A, b, issymmetric: bool | None = None, ishermitian: bool | None = None,
+                isposdef: bool = False, krylovdim: int | None = None, maxiter: int | None = None,
+                rtol: float | None = None, atol: float | None = None, tol: float | None = None, orth=None,
+                verbosity: int | None = None):
+    """linselector — src/linsolve/linsolve.jl:123-180: CG for symmetric positive definite problems (the
+    caller asserts `isposdef`; the reference only tests it for an AbstractMatrix), GMRES otherwise;
+    tol = max(atol, rtol·‖b‖) with both defaulting to KrylovDefaults.tol."""
+    from .algorithms import KrylovDefaults
+    from .eigsolve import _host_issymmetric
+    if issymmetric is None:
+        issymmetric = _host_issymmetric(A)
+    if ishermitian is None:
+        ishermitian = issymmetric
+    kd = KrylovDefaults.krylovdim if krylovdim is None else krylovdim
+    mi = KrylovDefaults.maxiter if maxiter is None else maxiter
+    vb = KrylovDefaults.verbosity if verbosity is None else verbosity
+    if tol is None:
+        nb = b.norm() if isinstance(b, B200Vec) else float(np.linalg.norm(np.asarray(b, dtype=np.float64)))
+        tol = max(KrylovDefaults.tol if atol is None else atol, (KrylovDefaults.tol if rtol is None else rtol) * nb)
+    if (issymmetric or ishermitian) and isposdef:
+        return CG(maxiter=kd * mi, tol=tol, verbosity=vb)
+    return GMRES(krylovdim=kd, maxiter=mi, tol=tol, orth=KrylovDefaults.orth if orth is None else orth, verbosity=vb)
+
+
 def _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol):
     import scipy.sparse as sp
     b = np.asarray(b)
     n = b.shape[0]
-    ctx = B200Context(n, alg.krylovdim + 10, dtype=np.float32 if b.dtype == np.float32 else np.float64)
+    ctx = B200Context(n, getattr(alg, "krylovdim", 0) + 12, dtype=np.float32 if b.dtype == np.float32 else np.float64)
     try:
         if not sp.issparse(A):
             raise TypeError("linsolve: host-side A must be a scipy sparse matrix")

@@ -122,8 +122,10 @@ def schursolve(A, x0: B200Vec, howmany: int, which: str, alg: Arnoldi):
     return TT, vectors, values, ConvergenceInfo(converged, residuals, normres, numiter, numops)
 
 
-def eigsolve_arnoldi(A, x0: B200Vec, howmany: int, which: str, alg: Arnoldi):
-    """eigsolve(A, x₀, howmany, which, alg::Arnoldi) — arnoldi.jl:147-184."""
+def eigsolve_arnoldi(A, x0: B200Vec, howmany: int, which: str, alg: Arnoldi, to_host: bool = False):
+    """eigsolve(A, x₀, howmany, which, alg::Arnoldi) — arnoldi.jl:147-184.  `to_host` streams every Ritz
+    vector / residual out as a complex numpy array as soon as it is formed (host-buffer entry: the number
+    of converged pairs, hence of returned vectors, is not known when the slab is sized)."""
     T, U, fact, converged, numiter, numops = _schursolve(A, x0, howmany, which, alg)
     hm = _howmany_actual(T, fact, howmany, converged)
     TT = np.array(T[:hm, :hm])
@@ -134,8 +136,12 @@ def eigsolve_arnoldi(A, x0: B200Vec, howmany: int, which: str, alg: Arnoldi):
     vectors, residuals = [], []
     for i in range(hm):
         vre, vim = np.ascontiguousarray(V[:, i].real), np.ascontiguousarray(V[:, i].imag)
-        vectors.append(ComplexVec(B * vre, B * vim))
-        residuals.append(ComplexVec(r.scale(float(vre[-1])), r.scale(float(vim[-1]))))
+        vec = ComplexVec(B * vre, B * vim)
+        vectors.append(vec.to_host() if to_host else vec)
+        del vec
+        res = ComplexVec(r.scale(float(vre[-1])), r.scale(float(vim[-1])))
+        residuals.append(res.to_host() if to_host else res)
+        del res
     normres = np.array([fact.normres() * abs(V[-1, i]) for i in range(hm)])
     _warn(alg, "eigsolve", converged, howmany, numiter, normres, numops)
     return values, vectors, ConvergenceInfo(converged, residuals, normres, numiter, numops)

@@ -119,3 +119,47 @@ def test_misc_drivers(sim):
 
 def test_blocklanczos_toric(sim):
     G.test_blocklanczos_toric_code_degenerate_ground_space()
+
+
+def test_keyword_front_ends_select_like_the_reference(sim):
+    """eigselector / linselector (eigsolve.jl:238-321, linsolve.jl:123-180) and the `which` checks
+    (eigsolve.jl:210-222)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n = 60
+    S = ko.stencil_matrix(10, 6)
+    Nn = (S + sp.diags([0.3], [1], shape=(n, n))).tocsr()
+    assert isinstance(kk.eigselector(S), kk.Lanczos) and isinstance(kk.eigselector(Nn), kk.Arnoldi)
+    assert isinstance(kk.eigselector(lambda x: x), kk.Arnoldi)            # a function: not assumed symmetric
+    assert isinstance(kk.eigselector(lambda x: x, issymmetric=True), kk.Lanczos)
+    assert kk.eigselector(S, block=True).krylovdim == 100
+    with pytest.raises(ValueError):
+        kk.eigselector(Nn, block=True)
+    x0 = rng.random(n)
+    vals, vecs, info = kk.eigsolve(S, x0, 2, "SR", krylovdim=30, tol=1e-10)
+    np.testing.assert_allclose(vals[:2], ko.laplace_eigenvalues(10, 6)[:2], rtol=1e-9)
+    vals, vecs, info = kk.eigsolve(Nn, x0, 2, "LR", krylovdim=n, tol=1e-10)    # -> Arnoldi, host buffers
+    want = np.linalg.eigvals(Nn.toarray())
+    want = want[np.argsort(-want.real, kind="stable")]
+    np.testing.assert_allclose(np.sort(vals[:2].real), np.sort(want[:2].real), rtol=1e-8)
+    for lam, v in zip(vals, vecs):
+        assert np.linalg.norm(Nn @ v - lam * v) < 1e-7
+    with pytest.raises(ValueError):
+        kk.eigsolve(S, x0, 1, "LI", krylovdim=20)
+    with pytest.raises(ValueError):
+        kk.eigsolve(Nn, x0, 1, "SI", krylovdim=20)
+    with pytest.raises(ValueError):
+        kk.eigsolve(S, x0, 1, "XX", krylovdim=20)
+    with pytest.raises(TypeError):
+        kk.eigsolve(S, x0, 1, "SR", kk.Lanczos(), krylovdim=20)
+    b = rng.random(n)
+    alg = kk.linselector(S, b, isposdef=True, krylovdim=10, maxiter=7)
+    assert isinstance(alg, kk.CG) and alg.maxiter == 70
+    assert alg.tol == pytest.approx(max(1e-12, 1e-12 * np.linalg.norm(b)))
+    assert isinstance(kk.linselector(S, b), kk.GMRES) and isinstance(kk.linselector(Nn, b, isposdef=True), kk.GMRES)
+    x, info = kk.linsolve(S, b, isposdef=True, rtol=1e-10)
+    assert info.converged == 1 and np.linalg.norm(S @ x - b) < 1e-9 * np.linalg.norm(b) * 10
+    x, info = kk.linsolve(Nn, b, krylovdim=20, rtol=1e-10)
+    assert info.converged == 1 and np.linalg.norm(Nn @ x - b) < 1e-8
+    x, info = kk.linsolve(Nn, b, None, kk.BiCGStab(maxiter=500, tol=1e-10, verbosity=0))
+    assert info.converged == 1 and np.linalg.norm(Nn @ x - b) < 1e-9
