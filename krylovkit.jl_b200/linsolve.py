@@ -255,6 +255,20 @@ def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
             return x, ConvergenceInfo(0, r, normr, numiter, numops)
 
 
+USE_FUSED_APPLY_DOT = True   # BiCGStab: take ⟨r̃, A p⟩ and ⟨A s, s⟩ from the SpMV epilogue (b2k_op_apply_dot)
+
+
+def _apply_and_dot(operator, x: B200Vec, a0: float, a1: float, v: B200Vec):
+    """(y, ⟨v, y⟩) with y = apply(operator, x, a₀, a₁).  For an unshifted device CSR operator the inner
+    product rides on the SpMV pass (one sweep and one host round trip less); otherwise the two literal
+    VectorInterface calls."""
+    if USE_FUSED_APPLY_DOT and isinstance(operator, B200CSR) and a0 == 0.0 and a1 == 1.0:
+        y = x.ctx.empty(x.space)
+        return y, operator.apply_dot_into(y, x, v)
+    y = apply(operator, x, a0, a1)
+    return y, v.inner(y)
+
+
 def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: float):
     """linsolve(operator, b, x₀, alg::BiCGStab, a₀, a₁) — src/linsolve/bicgstab.jl:1-203
     (SURVEY §8f-2).  Real arithmetic only (the library has no complex dtype).  The reference
@@ -290,9 +304,8 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
             beta = (rho / rhoold) * (alpha / omega)
             p = p.add_(v, -omega)
             p = p.add_(r, 1.0, beta)
-        v = apply(operator, p, a0, a1)
+        v, sigma = _apply_and_dot(operator, p, a0, a1, r_shadow)      # v = (a₀ + a₁A) p, σ = ⟨r̃, v⟩
         numops += 1
-        sigma = r_shadow.inner(v)
         alpha = rho / sigma
         s = s.scale_(1.0, r)
         s = s.add_(v, -alpha)                    # half step residual
@@ -307,9 +320,9 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
             normr_act = s.norm()
             if normr_act < tol:
                 return xhalf, ConvergenceInfo(1, s, normr_act, numiter, numops)
-        t = apply(operator, s, a0, a1)
+        t, ts = _apply_and_dot(operator, s, a0, a1, s)                # t = (a₀ + a₁A) s, ⟨t, s⟩
         numops += 1
-        omega = t.inner(s) / t.inner(t)
+        omega = ts / t.inner(t)
         x = x.scale_(1.0, xhalf)
         x = x.add_(s, omega)                     # full step iterate
         r = r.scale_(1.0, s)

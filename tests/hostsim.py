@@ -131,6 +131,19 @@ class HostSimLib:
     def b2k_ctx_stream(self, h):
         return None
 
+    def b2k_device_sync(self):
+        return L.OK
+
+    def b2k_timer_start(self, h):
+        import time
+        self._c(h).t0 = time.perf_counter()
+        return L.OK
+
+    def b2k_timer_stop(self, h, ms):
+        import time
+        _set(ms, (time.perf_counter() - self._c(h).t0) * 1e3)
+        return L.OK
+
     # ---- vectors ------------------------------------------------------------------------------
     def b2k_vec_alloc(self, h, space, out):
         return self.b2k_vec_alloc_range(h, space, 1, out)

@@ -241,6 +241,70 @@ def cg():
     return out
 
 
+def widened(nx=4000, ny=2500, lnx=2000, lny=2000):
+    """SURVEY §8f rows at the 1e7 scale (1 GPU): BiCGStab and GMRES on the convection-diffusion operator,
+    LSMR on a tall sparse least-squares problem, BlockLanczos (p = 4) and Arnoldi eigsolve on the
+    Laplacian / convection-diffusion operator, exponentiate (imaginary-time step) on the Laplacian."""
+    n = nx * ny
+    out = {}
+    ctx = kk.B200Context(n, 64)
+    W = 8.0 * n
+    lap = kk.B200CSR.stencil(ctx, nx, ny)
+    cd = kk.B200CSR.stencil(ctx, nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0))
+    ones = ctx.full(1.0)
+    spmv_bytes = lap.nnz * 12 + 4 * (n + 1) + 2 * W
+    # BiCGStab, 100 iterations (2 operator applications each)
+    b = kk.apply(cd, ones)
+    alg = kk.BiCGStab(maxiter=100, tol=1e-300, verbosity=0)
+    (x, info), t_dev, _ = timed(lambda: kk.linsolve(cd, b, None, alg), ctx)
+    chk = kk.apply(cd, x).add_(info.residual, 1.0).add_(b, -1.0)
+    out["bicgstab"] = {"numiter": info.numiter, "numops": info.numops, "s": t_dev, "ops_per_s": info.numops / t_dev,
+                       "normres": float(info.normres), "||A x + r - b||/||b||": chk.norm() / b.norm(),
+                       "algorithmic_GBs (2 SpMV + 28W per iteration)": (2 * spmv_bytes + 28 * W) * info.numiter / t_dev / 1e9}
+    del x, info, chk
+    # Arnoldi eigsolve, 3 restart cycles at krylovdim 30
+    x0 = ctx.splitmix(SEED)
+    alg = kk.Arnoldi(orth=kk.cgs2, krylovdim=30, maxiter=3, tol=0.0, verbosity=0)
+    (vals, vecs, info), t_dev, _ = timed(lambda: kk.eigsolve(cd, x0, 2, "LR", alg), ctx)
+    out["arnoldi_eigsolve"] = {"numops": info.numops, "numiter": info.numiter, "s": t_dev, "it_per_s": info.numops / t_dev,
+                               "ritz": [[float(v.real), float(v.imag)] for v in vals[:2]],
+                               "normres": [float(v) for v in info.normres[:2]]}
+    del vecs, info
+    # BlockLanczos, block of 4, krylovdim 32, 3 restart cycles
+    X0 = kk.Block([ctx.splitmix(SEED + i) for i in range(4)])
+    alg = kk.BlockLanczos(krylovdim=32, maxiter=3, tol=0.0, verbosity=0)
+    (vals, vecs, info), t_dev, _ = timed(lambda: kk.eigsolve(lap, X0, 4, "SR", alg), ctx)
+    out["blocklanczos_p4"] = {"numops": info.numops, "numiter": info.numiter, "s": t_dev, "it_per_s": info.numops / t_dev,
+                              "ritz": [float(v) for v in vals[:4]], "normres": [float(v) for v in info.normres[:4]]}
+    del vecs, info, X0
+    # exponentiate: w = exp(-0.5 A) x0 with Lanczos, krylovdim 30
+    alg = kk.Lanczos(orth=kk.cgs2, krylovdim=30, maxiter=10, tol=1e-10, verbosity=0)
+    (w, info), t_dev, _ = timed(lambda: kk.exponentiate(lap, -0.5, x0, alg), ctx)
+    out["exponentiate"] = {"numops": info.numops, "numiter": info.numiter, "converged": info.converged, "s": t_dev,
+                           "it_per_s": info.numops / t_dev, "err_estimate": float(info.normres),
+                           "||w||/||x0||": w.norm() / x0.norm()}
+    del w, info
+    ctx.close()
+    # LSMR: min ||b - A x|| for an 8e6 x 4e6 sparse A = [L; I] (Laplacian stacked on the identity), 50 iterations
+    import scipy.sparse as sp
+    n = lnx * lny
+    m = 2 * n
+    ctx = kk.B200Context(m, 12)
+    sv = ctx.add_space(n, 24, sharded=False)
+    from oracle import krylov_oracle as ko          # operator construction only (host-side test matrix)
+    Lh = ko.stencil_matrix(lnx, lny)
+    Ah = sp.vstack([Lh, sp.identity(n, format="csr")]).tocsr()
+    A = kk.B200CSR.from_scipy(ctx, Ah).with_spaces(sv, 0)
+    At = kk.B200CSR.from_scipy(ctx, Ah.T.tocsr()).with_spaces(0, sv)
+    bb = ctx.splitmix(SEED)
+    alg = kk.LSMR(maxiter=50, krylovdim=8, tol=0.0, verbosity=0)
+    (x, info), t_dev, _ = timed(lambda: kk.lssolve((A, At), bb, alg), ctx)
+    out["lsmr"] = {"numiter": info.numiter, "numops": info.numops, "s": t_dev, "ops_per_s": info.numops / t_dev,
+                   "normres": float(info.normres)}
+    ctx.close()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]
     res = {}
