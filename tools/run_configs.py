@@ -253,15 +253,17 @@ def widened(nx=4000, ny=2500, lnx=2000, lny=2000):
     cd = kk.B200CSR.stencil(ctx, nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0))
     ones = ctx.full(1.0)
     spmv_bytes = lap.nnz * 12 + 4 * (n + 1) + 2 * W
-    # BiCGStab, 100 iterations (2 operator applications each)
-    b = kk.apply(cd, ones)
-    alg = kk.BiCGStab(maxiter=100, tol=1e-300, verbosity=0)
-    (x, info), t_dev, _ = timed(lambda: kk.linsolve(cd, b, None, alg), ctx)
-    chk = kk.apply(cd, x).add_(info.residual, 1.0).add_(b, -1.0)
+    # BiCGStab, 40 iterations (2 operator applications each) on the strictly diagonally dominant variant
+    # (centre 5): unpreconditioned BiCGStab stagnates on the centre-4 operator, in the oracle as well
+    cd5 = kk.B200CSR.stencil(ctx, nx, ny, 1, (5.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0))
+    b = ctx.splitmix(SEED + 1)
+    alg = kk.BiCGStab(maxiter=40, tol=1e-300, verbosity=0)
+    (x, info), t_dev, _ = timed(lambda: kk.linsolve(cd5, b, None, alg), ctx)
+    chk = kk.apply(cd5, x).add_(b, -1.0)
     out["bicgstab"] = {"numiter": info.numiter, "numops": info.numops, "s": t_dev, "ops_per_s": info.numops / t_dev,
-                       "normres": float(info.normres), "||A x + r - b||/||b||": chk.norm() / b.norm(),
+                       "normres": float(info.normres), "||A x - b||/||b||": chk.norm() / b.norm(),
                        "algorithmic_GBs (2 SpMV + 28W per iteration)": (2 * spmv_bytes + 28 * W) * info.numiter / t_dev / 1e9}
-    del x, info, chk
+    del x, info, chk, cd5
     # Arnoldi eigsolve, 3 restart cycles at krylovdim 30
     x0 = ctx.splitmix(SEED)
     alg = kk.Arnoldi(orth=kk.cgs2, krylovdim=30, maxiter=3, tol=0.0, verbosity=0)
