@@ -186,6 +186,20 @@ int32_t b2k_op_apply_dot(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec y, b
 int32_t b2k_cg_step(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec p, b2k_vec q,
                     double a0, double a1, double beta, double rho, double* pq_out, double* normr_out);
 
+/* One BiCGStab iteration (src/linsolve/bicgstab.jl:95-171) as two calls, one host round trip
+ * each, with the half-step convergence test (:118) between them on the host as in the reference.
+ * half (:97-116): p <- r + beta*(p - omega*v) [first != 0: p <- r]; v <- (a0 + a1*A) p with
+ *   sigma = <rs, v> taken from the SpMV pass; alpha = rho/sigma (on the device); s <- r - alpha*v; ||s||.
+ * full (:139-150, :98): t <- (a0 + a1*A) s with <t,s> from the SpMV pass; <t,t>; omega = <t,s>/<t,t> (on the
+ *   device); x <- x + alpha*p + omega*s; r <- s - omega*t; ||r|| and the next rho = <rs, r>.
+ * Every elementwise update uses the rounding sequence of the add!! calls it replaces. */
+int32_t b2k_bicgstab_half(b2k_ctx* ctx, const b2k_op* op, b2k_vec rs, b2k_vec r, b2k_vec p, b2k_vec v,
+                          b2k_vec s, double a0, double a1, double beta, double omega, double rho,
+                          int32_t first, double* sigma_out, double* norms_out);
+int32_t b2k_bicgstab_full(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec rs, b2k_vec p,
+                          b2k_vec s, b2k_vec t, double a0, double a1, double alpha, double* omega_out,
+                          double* normr_out, double* rho_out);
+
 /* ---------------------------------------------- basis (OrthonormalBasis) ---- */
 /* project!!(y, b, x, alpha, beta, r): h[j] = beta*h[j] + alpha*<b[cols[j]], x>
  * — src/orthonormal.jl:88-118.  h is a HOST vector (orthonormal.jl:374, arnoldi.jl:212). */

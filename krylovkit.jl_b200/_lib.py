@@ -93,6 +93,11 @@ _PROTOS = {
     "b2k_op_apply_dot": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, P(C.c_double)]),
     "b2k_cg_step": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, C.c_double, C.c_double, C.c_double,
                                 C.c_double, P(C.c_double), P(C.c_double)]),
+    "b2k_bicgstab_half": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, c_vec, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, C.c_int32, P(C.c_double),
+                                      P(C.c_double)]),
+    "b2k_bicgstab_full": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, c_vec, c_vec, C.c_double,
+                                      C.c_double, C.c_double, P(C.c_double), P(C.c_double), P(C.c_double)]),
     "b2k_basis_project": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, c_vec, C.c_double, C.c_double,
                                       P(C.c_double)]),
     "b2k_basis_unproject": (C.c_int32, [c_ctx, c_vec, P(c_vec), C.c_int32, P(C.c_double), C.c_double,

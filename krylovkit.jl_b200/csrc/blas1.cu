@@ -291,6 +291,142 @@ k_cg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* 
     }
 }
 
+// ---- BiCGStab (src/linsolve/bicgstab.jl) elementwise stages: each is one sweep, sums are formed with the
+// same fma pairing as the literal add!! sequence they replace ----
+
+// p <- r + beta*(p - omega*v)   (bicgstab.jl:101-102: p = add!!(p, v, -ω); p = add!!(p, r, 1, β))
+template <typename T>
+__global__ void __launch_bounds__(BT)
+k_bicg_p(T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ v, int64_t n, T beta, T omega) {
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T pv[V], rv[V], vv[V];
+        vload<T>(p + i * V, pv);
+        vload<T>(r + i * V, rv);
+        vload<T>(v + i * V, vv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const T tmp = fma(-omega, vv[j], pv[j]);          // add!!(p, v, -ω)       (k_axpby MODE 1)
+            pv[j] = fma((T)1, rv[j], beta * tmp);             // add!!(p, r, 1, β)     (k_axpby MODE 2)
+        }
+        vstore<T>(p + i * V, pv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        const int64_t i = nv * V + threadIdx.x;
+        const T tmp = fma(-omega, v[i], p[i]);
+        p[i] = fma((T)1, r[i], beta * tmp);
+    }
+}
+
+// two-stage deterministic finish shared by the kernels below: per-CTA partials, last CTA adds them in
+// CTA order; NRED independent sums (part is NRED x gridDim.x)
+template <int NRED>
+__device__ __forceinline__ void finish_sums(const double (&blk)[NRED], double* __restrict__ part,
+                                            unsigned* __restrict__ ticket, double* __restrict__ out,
+                                            double* red, bool* last) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) part[(size_t)k * gridDim.x + blockIdx.x] = blk[k];
+        __threadfence();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        *last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*last) {
+        __threadfence();
+        const volatile double* pv = part;
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) {
+            double v = 0.0;
+            for (int g = threadIdx.x; g < (int)gridDim.x; g += BT) v += pv[(size_t)k * gridDim.x + g];
+            const double tot = block_sum(v, red);
+            if (threadIdx.x == 0) out[k] = tot;
+        }
+    }
+}
+
+// s <- r - alpha*v with alpha = rho / *sigma (device scalar); out[0] = ||s||^2   (bicgstab.jl:109-116)
+template <typename T>
+__global__ void __launch_bounds__(BT)
+k_bicg_s(T* __restrict__ s, const T* __restrict__ r, const T* __restrict__ v, int64_t n, double rho,
+         const double* __restrict__ sigma, double* __restrict__ part, unsigned* __restrict__ ticket,
+         double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool last;
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    const T alpha = (T)(rho / *sigma);
+    T acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T rv[V], vv[V];
+        vload<T>(r + i * V, rv);
+        vload<T>(v + i * V, vv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            rv[j] = fma(-alpha, vv[j], rv[j]);
+            acc = fma(rv[j], rv[j], acc);
+        }
+        vstore<T>(s + i * V, rv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        const int64_t i = nv * V + threadIdx.x;
+        const T sv = fma(-alpha, v[i], r[i]);
+        s[i] = sv;
+        acc = fma(sv, sv, acc);
+    }
+    const double blk[1] = {block_sum((double)acc, red)};
+    finish_sums<1>(blk, part, ticket, out, red, &last);
+}
+
+// x <- (x + alpha*p) + omega*s ; r <- s - omega*t with omega = *ts / *tt (device scalars);
+// out[0] = ||r||^2, out[1] = <rs, r>   (bicgstab.jl:143-150 and the next iteration's rho, :98)
+template <typename T>
+__global__ void __launch_bounds__(BT)
+k_bicg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ rs, const T* __restrict__ p,
+          const T* __restrict__ s, const T* __restrict__ t, int64_t n, T alpha, const double* __restrict__ ts,
+          const double* __restrict__ tt, double* __restrict__ part, unsigned* __restrict__ ticket,
+          double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool last;
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    const T omega = (T)(*ts / *tt);
+    T a1 = 0, a2 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T xv[V], pv[V], sv[V], tv[V], qv[V];
+        vload<T>(x + i * V, xv);
+        vload<T>(p + i * V, pv);
+        vload<T>(s + i * V, sv);
+        vload<T>(t + i * V, tv);
+        vload<T>(rs + i * V, qv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            xv[j] = fma(omega, sv[j], fma(alpha, pv[j], xv[j]));
+            tv[j] = fma(-omega, tv[j], sv[j]);
+            a1 = fma(tv[j], tv[j], a1);
+            a2 = fma(qv[j], tv[j], a2);
+        }
+        vstore<T>(x + i * V, xv);
+        vstore<T>(r + i * V, tv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        const int64_t i = nv * V + threadIdx.x;
+        x[i] = fma(omega, s[i], fma(alpha, p[i], x[i]));
+        const T rr = fma(-omega, t[i], s[i]);
+        r[i] = rr;
+        a1 = fma(rr, rr, a1);
+        a2 = fma(rs[i], rr, a2);
+    }
+    double blk[2];
+    blk[0] = block_sum((double)a1, red);
+    blk[1] = block_sum((double)a2, red);
+    finish_sums<2>(blk, part, ticket, out, red, &last);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ internal API ----
@@ -577,5 +713,96 @@ extern "C" int32_t b2k_cg_step(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_ve
     B2K_TRY(b2k_fetch_results(ctx, 2, 0));
     *pq_out = ctx->h_res[0];
     *normr_out = sqrt(ctx->h_res[1]);
+    return B2K_OK;
+}
+
+
+// BiCGStab iteration in two calls with one host round trip each — src/linsolve/bicgstab.jl:97-117 and
+// :139-150.  The half-step convergence test (:118) sits between them, on the host, as in the reference.
+//   half: p <- r + beta*(p - omega*v)  [first != 0: p <- r];  v <- (a0 + a1 A) p with sigma = <rs, v> taken
+//         from the SpMV pass;  alpha = rho/sigma on the device;  s <- r - alpha*v with ||s||.
+//   full: t <- (a0 + a1 A) s with <t, s> from the SpMV pass;  <t, t>;  omega = <t,s>/<t,t> on the device;
+//         x <- x + alpha*p + omega*s;  r <- s - omega*t with ||r|| and the next rho = <rs, r>.
+extern "C" int32_t b2k_bicgstab_half(b2k_ctx* ctx, const b2k_op* op, b2k_vec rs, b2k_vec r, b2k_vec p, b2k_vec v,
+                                     b2k_vec s, double a0, double a1, double beta, double omega, double rho,
+                                     int32_t first, double* sigma_out, double* norms_out) {
+    if (!ctx || !op || !sigma_out || !norms_out) return B2K_EINVAL;
+    VecRef rrs, rr, rp, rv, rsv;
+    B2K_TRY(b2k_resolve(ctx, rs, &rrs));
+    B2K_TRY(b2k_resolve(ctx, r, &rr));
+    B2K_TRY(b2k_resolve(ctx, p, &rp));
+    B2K_TRY(b2k_resolve(ctx, v, &rv));
+    B2K_TRY(b2k_resolve(ctx, s, &rsv));
+    const int64_t n = rr.n;
+    if (rrs.n != n || rp.n != n || rv.n != n || rsv.n != n)
+        return b2k_fail(ctx, B2K_EDIM, "bicgstab_half: length mismatch");
+    const int grid = grid_for(ctx, n, 8);
+    if (first) {
+        B2K_TRY(b2k_vec_copy(ctx, p, r));
+    } else if (ctx->dtype == B2K_F64) {
+        k_bicg_p<double><<<grid, BT, 0, ctx->stream>>>((double*)rp.ptr, (const double*)rr.ptr,
+                                                       (const double*)rv.ptr, n, beta, omega);
+        B2K_LAUNCH_CHECK(ctx);
+    } else {
+        k_bicg_p<float><<<grid, BT, 0, ctx->stream>>>((float*)rp.ptr, (const float*)rr.ptr, (const float*)rv.ptr,
+                                                      n, (float)beta, (float)omega);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    const bool shifted = (a0 != 0.0) || (a1 != 1.0);
+    B2K_TRY(b2k_enqueue_apply(ctx, op, rp, rv, a0, a1, shifted, &rrs, 0));      // d_res[0] = sigma
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res, 1, rr.sharded));
+    if (ctx->dtype == B2K_F64)
+        k_bicg_s<double><<<grid, BT, 0, ctx->stream>>>((double*)rsv.ptr, (const double*)rr.ptr,
+                                                       (const double*)rv.ptr, n, rho, ctx->d_res, ctx->d_part_s,
+                                                       ctx->d_sync, ctx->d_res + 1);
+    else
+        k_bicg_s<float><<<grid, BT, 0, ctx->stream>>>((float*)rsv.ptr, (const float*)rr.ptr, (const float*)rv.ptr,
+                                                      n, rho, ctx->d_res, ctx->d_part_s, ctx->d_sync,
+                                                      ctx->d_res + 1);
+    B2K_LAUNCH_CHECK(ctx);
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res + 1, 1, rr.sharded));
+    B2K_TRY(b2k_fetch_results(ctx, 2, 0));
+    *sigma_out = ctx->h_res[0];
+    *norms_out = sqrt(ctx->h_res[1]);
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_bicgstab_full(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec rs, b2k_vec p,
+                                     b2k_vec s, b2k_vec t, double a0, double a1, double alpha,
+                                     double* omega_out, double* normr_out, double* rho_out) {
+    if (!ctx || !op || !omega_out || !normr_out || !rho_out) return B2K_EINVAL;
+    VecRef rx, rr, rrs, rp, rsv, rt;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    B2K_TRY(b2k_resolve(ctx, r, &rr));
+    B2K_TRY(b2k_resolve(ctx, rs, &rrs));
+    B2K_TRY(b2k_resolve(ctx, p, &rp));
+    B2K_TRY(b2k_resolve(ctx, s, &rsv));
+    B2K_TRY(b2k_resolve(ctx, t, &rt));
+    const int64_t n = rr.n;
+    if (rx.n != n || rrs.n != n || rp.n != n || rsv.n != n || rt.n != n)
+        return b2k_fail(ctx, B2K_EDIM, "bicgstab_full: length mismatch");
+    const bool shifted = (a0 != 0.0) || (a1 != 1.0);
+    B2K_TRY(b2k_enqueue_apply(ctx, op, rsv, rt, a0, a1, shifted, &rsv, 0));     // d_res[0] = <s, t>
+    B2K_TRY(b2k_enqueue_dot(ctx, rt.ptr, rt.ptr, n, nullptr, -1, 1, -1));       // d_res[1] = <t, t>
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res, 2, rr.sharded));
+    const int grid = grid_for(ctx, n, 8);
+    if (ctx->dtype == B2K_F64)
+        k_bicg_xr<double><<<grid, BT, 0, ctx->stream>>>((double*)rx.ptr, (double*)rr.ptr, (const double*)rrs.ptr,
+                                                        (const double*)rp.ptr, (const double*)rsv.ptr,
+                                                        (const double*)rt.ptr, n, alpha, ctx->d_res,
+                                                        ctx->d_res + 1, ctx->d_part_s, ctx->d_sync,
+                                                        ctx->d_res + 2);
+    else
+        k_bicg_xr<float><<<grid, BT, 0, ctx->stream>>>((float*)rx.ptr, (float*)rr.ptr, (const float*)rrs.ptr,
+                                                       (const float*)rp.ptr, (const float*)rsv.ptr,
+                                                       (const float*)rt.ptr, n, (float)alpha, ctx->d_res,
+                                                       ctx->d_res + 1, ctx->d_part_s, ctx->d_sync,
+                                                       ctx->d_res + 2);
+    B2K_LAUNCH_CHECK(ctx);
+    B2K_TRY(b2k_allreduce(ctx, ctx->d_res + 2, 2, rr.sharded));
+    B2K_TRY(b2k_fetch_results(ctx, 4, 0));
+    *omega_out = ctx->h_res[0] / ctx->h_res[1];
+    *normr_out = sqrt(ctx->h_res[2]);
+    *rho_out = ctx->h_res[3];
     return B2K_OK;
 }

@@ -269,12 +269,18 @@ def _apply_and_dot(operator, x: B200Vec, a0: float, a1: float, v: B200Vec):
     return y, v.inner(y)
 
 
+USE_FUSED_BICGSTAB = True    # b2k_bicgstab_half / _full (two host round trips per iteration) for device CSR operators
+
+
 def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: float):
     """linsolve(operator, b, x₀, alg::BiCGStab, a₀, a₁) — src/linsolve/bicgstab.jl:1-203
     (SURVEY §8f-2).  Real arithmetic only (the library has no complex dtype).  The reference
     spells its first iteration out ahead of the loop; here one loop serves both, `p is None`
     marking the first pass, including its quirk that `maxiter` is only looked at from the
-    second iteration on."""
+    second iteration on.  For a device CSR operator every iteration is two fused C-ABI calls
+    (b2k_bicgstab_half / _full: 17 vector sweeps + 2 SpMV instead of 28 + 2, two host round trips
+    instead of six); any other operator runs the literal VectorInterface sequence."""
+    import ctypes as C
     y0 = apply(operator, x0)
     r = b.copy()
     if a0 != 0:
@@ -287,52 +293,84 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
     numops, numiter = 1, 0
     if normr < tol:
         return x, ConvergenceInfo(1, r, normr, numiter, numops)
+    ctx = b.ctx
+    fused = USE_FUSED_BICGSTAB and isinstance(operator, B200CSR)
     r_shadow = r.copy()
     rho = alpha = omega = 1.0
+    rho_next = None                              # ⟨r̃, r⟩ delivered by the previous fused full step
     p = v = None
     s, xhalf = r.zerovector(), x.zerovector()
+    t = r.zerovector() if fused else None
     while True:
         numiter += 1
-        rhoold, rho = rho, r_shadow.inner(r)
-        if p is None:
+        rhoold, rho = rho, (r_shadow.inner(r) if rho_next is None else rho_next)
+        rho_next = None
+        first = p is None
+        if first:
             if rho == 0.0:                       # `ρ ≈ 0.0` (bicgstab.jl:36): the method breaks down
                 if alg.verbosity >= WARN_LEVEL:
                     warnings.warn("BiCGStab linsolve errored after 1 iteration: rho = 0")
                 return x, ConvergenceInfo(0, r, normr, numiter, numops)
-            p = r.copy()
+            beta = 0.0
         else:
             beta = (rho / rhoold) * (alpha / omega)
-            p = p.add_(v, -omega)
-            p = p.add_(r, 1.0, beta)
-        v, sigma = _apply_and_dot(operator, p, a0, a1, r_shadow)      # v = (a₀ + a₁A) p, σ = ⟨r̃, v⟩
-        numops += 1
-        alpha = rho / sigma
-        s = s.scale_(1.0, r)
-        s = s.add_(v, -alpha)                    # half step residual
-        xhalf = xhalf.scale_(1.0, x)
-        xhalf = xhalf.add_(p, alpha)             # half step iterate
-        normr = s.norm()
+        if fused:
+            if first:
+                p, v = r.zerovector(), r.zerovector()
+            sg, ns = C.c_double(), C.c_double()
+            ctx.check(ctx.lib.b2k_bicgstab_half(ctx.h, operator.h, r_shadow.handle, r.handle, p.handle, v.handle,
+                                                s.handle, a0, a1, beta, omega, rho, int(first),
+                                                C.byref(sg), C.byref(ns)))
+            numops += 1
+            alpha = rho / sg.value
+            normr = ns.value
+        else:
+            if first:
+                p = r.copy()
+            else:
+                p = p.add_(v, -omega)
+                p = p.add_(r, 1.0, beta)
+            v, sigma = _apply_and_dot(operator, p, a0, a1, r_shadow)      # v = (a₀ + a₁A) p, σ = ⟨r̃, v⟩
+            numops += 1
+            alpha = rho / sigma
+            s = s.scale_(1.0, r)
+            s = s.add_(v, -alpha)                # half step residual
+            xhalf = xhalf.scale_(1.0, x)
+            xhalf = xhalf.add_(p, alpha)         # half step iterate
+            normr = s.norm()
         if normr < tol:
             # replace the recurrence residual by the actual one before trusting it
+            if fused:
+                xhalf = xhalf.scale_(1.0, x)
+                xhalf = xhalf.add_(p, alpha)
             s = s.scale_(1.0, b)
             s = s.add_(apply(operator, xhalf, a0, a1), -1.0)
             numops += 1
             normr_act = s.norm()
             if normr_act < tol:
                 return xhalf, ConvergenceInfo(1, s, normr_act, numiter, numops)
-        t, ts = _apply_and_dot(operator, s, a0, a1, s)                # t = (a₀ + a₁A) s, ⟨t, s⟩
-        numops += 1
-        omega = ts / t.inner(t)
-        x = x.scale_(1.0, xhalf)
-        x = x.add_(s, omega)                     # full step iterate
-        r = r.scale_(1.0, s)
-        r = r.add_(t, -omega)                    # full step residual
-        del t
-        normr = r.norm()
+        if fused:
+            om, nr, rn = C.c_double(), C.c_double(), C.c_double()
+            ctx.check(ctx.lib.b2k_bicgstab_full(ctx.h, operator.h, x.handle, r.handle, r_shadow.handle, p.handle,
+                                                s.handle, t.handle, a0, a1, alpha, C.byref(om), C.byref(nr),
+                                                C.byref(rn)))
+            numops += 1
+            omega, normr, rho_next = om.value, nr.value, rn.value
+        else:
+            t, ts = _apply_and_dot(operator, s, a0, a1, s)                # t = (a₀ + a₁A) s, ⟨t, s⟩
+            numops += 1
+            omega = ts / t.inner(t)
+            x = x.scale_(1.0, xhalf)
+            x = x.add_(s, omega)                     # full step iterate
+            r = r.scale_(1.0, s)
+            r = r.add_(t, -omega)                    # full step residual
+            del t
+            normr = r.norm()
         if normr < tol:
             r = r.scale_(1.0, b)
             r = r.add_(apply(operator, x, a0, a1), -1.0)
             numops += 1
+            rho_next = None                      # r changed: ⟨r̃, r⟩ has to be taken again
             normr_act = r.norm()
             if normr_act < tol:
                 return x, ConvergenceInfo(1, r, normr_act, numiter, numops)

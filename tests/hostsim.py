@@ -6,7 +6,7 @@ It is never importable from the package, ships nothing, and measures nothing: th
 loads the CUDA library or raises.  `install()` swaps the object `_lib.load()` returns for the
 duration of a test; semantics follow include/b200krylov.h entry by entry, the arithmetic is the
 oracle's (tests may use the oracle).  The fused entry points (b2k_lanczos_expand[_many],
-b2k_cg_step) are deliberately absent: under the simulator the drivers run their literal
+b2k_cg_step, b2k_bicgstab_half/_full) are deliberately absent: under the simulator the drivers run their literal
 VectorInterface paths.
 """
 from __future__ import annotations
@@ -464,12 +464,13 @@ class installed:
         import importlib
         self.lz = importlib.import_module("krylovkit_jl_b200.factorizations.lanczos")
         self.ls = importlib.import_module("krylovkit_jl_b200.linsolve")
-        self.saved = (L._lib, self.lz.USE_FUSED_EXPAND, self.ls.USE_FUSED_CG)
+        self.saved = (L._lib, self.lz.USE_FUSED_EXPAND, self.ls.USE_FUSED_CG, self.ls.USE_FUSED_BICGSTAB)
         L._lib = HostSimLib()
         self.lz.USE_FUSED_EXPAND = False
         self.ls.USE_FUSED_CG = False
+        self.ls.USE_FUSED_BICGSTAB = False
         return L._lib
 
     def __exit__(self, *exc):
-        L._lib, self.lz.USE_FUSED_EXPAND, self.ls.USE_FUSED_CG = self.saved
+        L._lib, self.lz.USE_FUSED_EXPAND, self.ls.USE_FUSED_CG, self.ls.USE_FUSED_BICGSTAB = self.saved
         return False

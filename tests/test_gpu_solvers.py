@@ -308,11 +308,17 @@ def test_cg_matches_oracle(fused):
     ctx.close()
 
 
-def test_bicgstab_matches_oracle_and_reference_properties():
-    """BiCGStab (src/linsolve/bicgstab.jl) on a nonsymmetric sparse operator — the
+@pytest.mark.parametrize("fused", [True, False])
+def test_bicgstab_matches_oracle_and_reference_properties(fused):
+    """BiCGStab (src/linsolve/bicgstab.jl) on a nonsymmetric sparse operator, through the
+    fused two-call step (b2k_bicgstab_half/_full) and through the literal VectorInterface sequence — the
     properties test/linsolve.jl:287-403 checks (converged, b = (a0 + a1 A) x, warm restart costs one
     operator application, non-converged run satisfies b = A x + r) plus step-for-step agreement
     with the oracle."""
+    import importlib
+    ls = importlib.import_module("krylovkit_jl_b200.linsolve")
+    saved = ls.USE_FUSED_BICGSTAB
+    ls.USE_FUSED_BICGSTAB = fused
     rng = np.random.default_rng(11)
     n = 4000
     # convection-diffusion-like: 1-D Laplacian + skew part, diagonally dominant
@@ -355,6 +361,7 @@ def test_bicgstab_matches_oracle_and_reference_properties():
     assert np.linalg.norm(A @ x.to_host().astype(np.float64) - b) < 1e-4 * np.linalg.norm(b)
     ctx32.close()
     ctx.close()
+    ls.USE_FUSED_BICGSTAB = saved
 
 
 @pytest.mark.parametrize("orth", ["mgs", "cgs2", "mgsr"])

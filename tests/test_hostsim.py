@@ -47,7 +47,7 @@ def test_vector_interface_and_errors(sim):
 
 
 def test_bicgstab(sim):
-    G.test_bicgstab_matches_oracle_and_reference_properties()
+    G.test_bicgstab_matches_oracle_and_reference_properties(False)
 
 
 @pytest.mark.parametrize("orth", ["mgs", "cgs2", "mgsr"])
