@@ -6,6 +6,8 @@
 import os
 import sys
 
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "8")   # small oracle problems: a 128-thread pool only adds latency
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -66,6 +68,53 @@ def main():
         v = torch.cat(parts).cpu().numpy()
         assert np.linalg.norm(A @ v - vals[0] * v) < 1e-8
         del vecs
+    # 5. widened drivers on the sharded context: every scalar they see is all-reduced inside
+    #    the library, so the host logic is rank-replicated; results = the serial oracle's
+    def gather(vec):
+        loc = torch.from_numpy(vec.to_host()).cuda()
+        parts = [torch.zeros(sharding.shard_grid_lines(nx, ny, r, world).n_local, dtype=torch.float64,
+                             device="cuda") for r in range(world)]
+        dist.all_gather(parts, loc)
+        return torch.cat(parts).cpu().numpy()
+
+    import importlib
+    ls = importlib.import_module("krylovkit_jl_b200.linsolve")
+    cdc = (5.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0)
+    Acd = ko.stencil_matrix(nx, ny, 1, cdc)
+    opcd = kk.B200CSR.stencil(ctx, nx, ny, 1, cdc)
+    bh = ko.splitmix_vector(7, n)
+    ox, oinfo = ko.linsolve_bicgstab(Acd, bh, maxiter=200, tol=1e-10)
+    for fused in (True, False):
+        ls.USE_FUSED_BICGSTAB = fused
+        x, info = kk.linsolve(opcd, ctx.from_host(bh[sl]), None, kk.BiCGStab(maxiter=200, tol=1e-10, verbosity=0))
+        assert info.converged == 1 and abs(info.numiter - oinfo["numiter"]) <= 1, (info.numiter, oinfo["numiter"])
+        xg = gather(x)
+        assert np.linalg.norm(Acd @ xg - bh) < 1e-9 and np.allclose(xg, ox, rtol=1e-7, atol=1e-9)
+    ls.USE_FUSED_BICGSTAB = True
+    spd = (5.0, -1.0, -1.0, -1.0, -1.0, 0.0, 0.0)
+    Aspd, opspd = ko.stencil_matrix(nx, ny, 1, spd), kk.B200CSR.stencil(ctx, nx, ny, 1, spd)
+    x, info = kk.linsolve(opspd, ctx.from_host(bh[sl]), None, kk.CG(maxiter=500, tol=1e-9, verbosity=0))
+    ox, oinfo = ko.linsolve_cg(Aspd, bh, maxiter=500, tol=1e-9)
+    assert info.converged == 1 and abs(info.numiter - oinfo["numiter"]) <= 1
+    assert np.linalg.norm(Aspd @ gather(x) - bh) < 1e-8
+    # fixed number of restart cycles (tol = 0): same Krylov spaces as the serial oracle, same Ritz values
+    alg = kk.Arnoldi(orth=kk.cgs2, krylovdim=30, maxiter=4, tol=0.0, verbosity=0)
+    vals, vecs, info = kk.eigsolve(opcd, ctx.from_host(x0[sl]), 2, "LR", alg)
+    ovals, _, oinfo = ko.eigsolve_arnoldi(Acd, x0, 2, "LR", krylovdim=30, maxiter=4, tol=0.0, orth=ko.Orth(ko.CGS2))
+    assert info.numops == oinfo["numops"] and np.allclose(vals[:2], ovals[:2], rtol=1e-7), (vals[:2], ovals[:2])
+    vg = gather(vecs[0].re) + 1j * gather(vecs[0].im)
+    rg = gather(info.residual[0].re) + 1j * gather(info.residual[0].im)
+    assert np.linalg.norm(Acd @ vg - vals[0] * vg - rg) < 1e-9
+    del vecs, info
+    X0 = [ko.splitmix_vector(100 + i, n) for i in range(3)]
+    alg = kk.BlockLanczos(krylovdim=30, maxiter=4, tol=0.0, verbosity=0)
+    vals, vecs, info = kk.eigsolve(op, kk.Block([ctx.from_host(x[sl]) for x in X0]), 3, "SR", alg)
+    ovals, _, oinfo = ko.eigsolve_blocklanczos(A, X0, 3, "SR", krylovdim=30, maxiter=4, tol=0.0)
+    assert info.numops == oinfo["numops"] and np.allclose(vals[:3], ovals[:3], rtol=1e-7), (vals[:3], ovals[:3])
+    del vecs, info
+    w, info = kk.exponentiate(op, -0.3, ctx.from_host(x0[sl]), kk.Lanczos(orth=kk.cgs2, krylovdim=25, tol=1e-10, verbosity=0))
+    ow, _ = ko.expintegrator(A, -0.3, (x0,), "lanczos", ko.Orth(ko.CGS2), krylovdim=25, tol=1e-10)
+    assert info.converged == 1 and np.allclose(gather(w), ow, rtol=1e-9, atol=1e-11)
     if rank == 0:
         print(f"dist_check ok on {world} ranks: Ritz values {vals[:3]}")
     dist.barrier()
