@@ -22,7 +22,7 @@ from .vectors import B200Context, B200Vec, inner, norm
 __all__ = [n for n in dir() if not n.startswith("_")]
 from .eigsolve import eigselector, eigsolve
 from .linsolve import linselector, linsolve
-from .schursolve import ComplexVec, schursolve
+from .schursolve import ComplexVec, realeigsolve, schursolve
 from .lssolve import lssolve
 from .expintegrator import expintegrator, exponentiate
 from .svdsolve import svdsolve

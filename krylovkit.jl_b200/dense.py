@@ -251,3 +251,25 @@ def restore_arnoldi_form(U: np.ndarray, H: np.ndarray, f: np.ndarray, keep: int)
         lmul_householder(h, H)
         rmul_householder(H, h, slice(0, j + 1))
         rmul_householder(U, h)
+
+
+def schur2realeigvecs(T: np.ndarray) -> np.ndarray:
+    """schur2realeigvecs — dense/linalg.jl:247-257: real eigenvectors of an upper triangular T
+    (LAPACK trevc in the reference; scipy's triangular solver here), unit 2-norm columns."""
+    from scipy.linalg import solve_triangular
+    T = np.asarray(T, dtype=np.float64)
+    n = T.shape[0]
+    if np.any(np.diag(T, -1) != 0):
+        raise ValueError("T must be upper triangular")
+    smin = np.finfo(np.float64).eps * max(float(np.abs(T).max()), 1.0)
+    V = np.zeros((n, n))
+    for k in range(n):
+        V[k, k] = 1.0
+        if k > 0:
+            M = T[:k, :k] - T[k, k] * np.eye(k)
+            d = np.diag(M).copy()
+            d[np.abs(d) < smin] = smin                  # trevc-style perturbation of (near-)repeated values
+            M[np.diag_indices(k)] = d
+            V[:k, k] = solve_triangular(M, -T[:k, k], lower=False)
+        V[:, k] /= np.linalg.norm(V[:, k])
+    return V

@@ -14,7 +14,7 @@ import numpy as np
 
 from .algorithms import Arnoldi, ConvergenceInfo, WARN_LEVEL
 from .dense import (eigsort_complex, hidx, hschur, permuteschur, restore_arnoldi_form, schur2eigvals,
-                    schur2eigvecs)
+                    schur2eigvecs, schur2realeigvecs)
 from .factorizations import arnoldi as ar
 from .orthonormal import basistransform_
 from .vectors import B200Vec
@@ -144,6 +144,45 @@ def eigsolve_arnoldi(A, x0: B200Vec, howmany: int, which: str, alg: Arnoldi, to_
         del res
     normres = np.array([fact.normres() * abs(V[-1, i]) for i in range(hm)])
     _warn(alg, "eigsolve", converged, howmany, numiter, normres, numops)
+    return values, vectors, ConvergenceInfo(converged, residuals, normres, numiter, numops)
+
+
+def realeigsolve(A, x0: B200Vec, howmany: int, which: str, alg: Arnoldi):
+    """realeigsolve(A, x₀, howmany, which, alg::Arnoldi) — arnoldi.jl:293-349: for operators whose
+    spectrum is known to be real.  2×2 Schur blocks among the requested values are flattened with a
+    warning (the imaginary parts are dropped); eigenvalues and eigenvectors come back real."""
+    import math
+    T, U, fact, converged, numiter, numops = _schursolve(A, x0, howmany, which, alg)
+    T = np.array(T)
+    K = len(fact)
+    i = 0
+    while i < howmany:
+        i += 1
+        if i < K:
+            if abs(T[i, i - 1]) > alg.tol and alg.verbosity >= WARN_LEVEL:
+                impart = math.sqrt(max(-T[i, i - 1] * T[i - 1, i], 0.0))
+                warnings.warn(f"2 x 2 Schur block at position {i} and {i + 1} detected, complex eigenvalues with "
+                              f"imaginary part {impart} will be ignored by setting T[i+1,i] = {T[i, i - 1]} to zero.")
+            T[i, i - 1] = 0
+    while i < converged:
+        i += 1
+        if i < K:
+            if abs(T[i, i - 1]) <= alg.tol:
+                T[i, i - 1] = 0
+            else:
+                i -= 1
+                break
+    hm = min(i, T.shape[0])
+    converged = min(converged, hm)
+    TT = T[:hm, :hm]
+    values = np.diag(TT).copy()
+    V = U[:, :hm] @ schur2realeigvecs(TT)
+    B = fact.basis()
+    r = fact.residual()
+    vectors = [B * np.ascontiguousarray(V[:, j]) for j in range(hm)]
+    residuals = [r.scale(float(V[-1, j])) for j in range(hm)]
+    normres = np.array([fact.normres() * abs(V[-1, j]) for j in range(hm)])
+    _warn(alg, "realeigsolve", converged, hm, numiter, normres, numops)
     return values, vectors, ConvergenceInfo(converged, residuals, normres, numiter, numops)
 
 

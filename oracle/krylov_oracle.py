@@ -876,6 +876,60 @@ def eigsolve_arnoldi(A, x0, howmany, which, krylovdim=30, maxiter=100, tol=1e-12
                                  numiter=numiter, numops=numops)
 
 
+def schur2realeigvecs(T):
+    """schur2realeigvecs — dense/linalg.jl:247-257: eigenvectors of an upper TRIANGULAR real matrix
+    (back substitution), unit 2-norm columns."""
+    n = T.shape[0]
+    if np.any(np.diag(T, -1) != 0):
+        raise ValueError("T must be upper triangular")
+    V = np.zeros((n, n))
+    smin = np.finfo(float).eps * max(np.abs(T).max(), 1.0)
+    for k in range(n):
+        V[k, k] = 1.0
+        for i in range(k - 1, -1, -1):
+            den = T[i, i] - T[k, k]
+            if abs(den) < smin:
+                den = smin
+            V[i, k] = -(T[i, i + 1:k + 1] @ V[i + 1:k + 1, k]) / den
+        V[:, k] /= np.linalg.norm(V[:, k])
+    return V
+
+
+def realeigsolve_arnoldi(A, x0, howmany, which, krylovdim=30, maxiter=100, tol=1e-12,
+                         orth: Orth = Orth(MGS2), eager=False):
+    """realeigsolve(A, x₀, howmany, which, ::Arnoldi) — eigsolve/arnoldi.jl:293-349: the caller asserts a
+    real spectrum; 2×2 Schur blocks among the requested values are flattened (their imaginary parts
+    dropped), real eigenvalues and real eigenvectors are returned."""
+    T, U, f, converged, numiter, numops = _schursolve(A, x0, howmany, which, krylovdim, maxiter, tol, orth, eager)
+    T = np.array(T)
+    ignored = []
+    i = 0
+    while i < howmany:
+        i += 1
+        if i < f.k:
+            if abs(T[i, i - 1]) > tol:
+                ignored.append(math.sqrt(max(-T[i, i - 1] * T[i - 1, i], 0.0)))
+            T[i, i - 1] = 0
+    while i < converged:
+        i += 1
+        if i < f.k:
+            if abs(T[i, i - 1]) <= tol:
+                T[i, i - 1] = 0
+            else:
+                i -= 1
+                break
+    hm = min(i, T.shape[0])
+    converged = min(converged, hm)
+    TT = T[:hm, :hm]
+    values = np.diag(TT).copy()
+    Vr = U[:, :hm] @ schur2realeigvecs(TT)
+    vectors = [unproject(np.zeros_like(f.V[0]), f.V, Vr[:, j]) for j in range(hm)]
+    residuals = [f.r * Vr[-1, j] for j in range(hm)]
+    normres = np.array([f.normres() * abs(Vr[-1, j]) for j in range(hm)])
+    return values, vectors, dict(converged=converged, residual=residuals, normres=normres, numiter=numiter,
+                                 numops=numops, ignored_imag=ignored)
+
+
 def linsolve_gmres(A, b, x0=None, krylovdim=30, maxiter=100, tol=1e-12, orth: Orth = Orth(MGS2),
                    a0=0.0, a1=1.0):
     """linsolve(operator, b, x₀, ::GMRES, a₀, a₁) — src/linsolve/gmres.jl:1-151.

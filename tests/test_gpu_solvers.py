@@ -614,6 +614,40 @@ def test_arnoldi_eigsolve_and_schursolve(orth):
     ctx.close()
 
 
+def test_realeigsolve():
+    """test/eigsolve.jl:330-440 through the device path: real spectrum in, real eigenpairs out; a complex
+    pair among the requested values is flattened with a warning."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(5)
+    n, N = 10, 100
+    V = expm(rng.standard_normal((N, N)) / 10)
+    D = rng.standard_normal(N)
+    A = V @ np.diag(D) @ np.linalg.inv(V)
+    v = rng.random(N)
+    ctx = kk.B200Context(N, 120)
+    op = kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A))
+    alg = kk.Arnoldi(krylovdim=3 * n, maxiter=20, tol=1e-12, eager=True, verbosity=0)
+    for which, want in (("SR", np.sort(D)), ("LR", np.sort(D)[::-1]), ("LM", D[np.argsort(-np.abs(D))])):
+        D1, V1, i1 = kk.realeigsolve(op, ctx.from_host(v), n, which, alg)
+        oD1, _, oi1 = ko.realeigsolve_arnoldi(A, v, n, which, krylovdim=3 * n, maxiter=20, tol=1e-12, eager=True)
+        l = i1.converged
+        assert l > 0 and D1.dtype == np.float64
+        np.testing.assert_allclose(D1[:l], want[:l], rtol=1e-8, atol=1e-10)
+        m = min(l, oi1["converged"])
+        np.testing.assert_allclose(D1[:m], oD1[:m], rtol=1e-8, atol=1e-10)
+        U1 = np.column_stack([x.to_host() for x in V1])
+        R1 = np.column_stack([x.to_host() for x in i1.residual])
+        np.testing.assert_allclose(A @ U1, U1 * D1 + R1, atol=1e-9)
+        del V1, i1
+    ctx.close()
+    ctx = kk.B200Context(2, 16)
+    op = kk.B200CSR.from_scipy(ctx, sp.csr_matrix(np.array([[1.0, -1.0], [1.0, 1.0]])))
+    with pytest.warns(UserWarning, match="2 x 2 Schur block"):
+        D1, _, _ = kk.realeigsolve(op, ctx.from_host(np.array([1.0, 0.3])), 1, "LM", kk.Arnoldi(tol=1e-8, verbosity=1))
+    np.testing.assert_allclose(D1, 1.0)
+    ctx.close()
+
+
 def _phi(A, v, p):
     """ϕ_p(A) v through the augmented-matrix exponential — test/expintegrator.jl:1-13."""
     from scipy.linalg import expm

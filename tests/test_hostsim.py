@@ -163,3 +163,7 @@ def test_keyword_front_ends_select_like_the_reference(sim):
     assert info.converged == 1 and np.linalg.norm(Nn @ x - b) < 1e-8
     x, info = kk.linsolve(Nn, b, None, kk.BiCGStab(maxiter=500, tol=1e-10, verbosity=0))
     assert info.converged == 1 and np.linalg.norm(Nn @ x - b) < 1e-9
+
+
+def test_realeigsolve(sim):
+    G.test_realeigsolve()

@@ -560,3 +560,26 @@ def test_issue133_lssolve_identity_fixture():
     x, info = ko.lssolve_lsmr(np.eye(2), np.array([1.0, 0.0]))
     assert np.array_equal(x, [1.0, 0.0])
     assert info["converged"] == 1 and info["numiter"] == 1 and info["numops"] == 2 and info["normres"] == 0.0
+
+
+def test_realeigsolve_oracle():
+    """test/eigsolve.jl:330-440: A = V D V⁻¹ with real spectrum — real eigenvalues in the requested order,
+    real eigenvectors with A U = U D + R; a genuinely complex pair is flattened and reported."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(5)
+    n, N = 10, 100
+    V = expm(rng.standard_normal((N, N)) / 10)
+    D = rng.standard_normal(N)
+    A = V @ np.diag(D) @ np.linalg.inv(V)
+    v = rng.random(N)
+    for which, want in (("SR", np.sort(D)), ("LR", np.sort(D)[::-1]), ("LM", D[np.argsort(-np.abs(D))])):
+        D1, V1, i1 = ko.realeigsolve_arnoldi(A, v, n, which, krylovdim=3 * n, maxiter=20, tol=1e-12, eager=True)
+        l = i1["converged"]
+        assert l > 0 and D1.dtype == np.float64 and not i1["ignored_imag"]
+        np.testing.assert_allclose(D1[:l], want[:l], rtol=1e-8, atol=1e-10)
+        U1, R1 = np.column_stack(V1), np.column_stack(i1["residual"])
+        assert U1.dtype == np.float64
+        np.testing.assert_allclose(A @ U1, U1 * D1 + R1, atol=1e-9)
+    D1, _, i1 = ko.realeigsolve_arnoldi(np.array([[1.0, -1.0], [1.0, 1.0]]), np.array([1.0, 0.3]), 1, "LM", tol=1e-8)
+    np.testing.assert_allclose(D1, 1.0)
+    np.testing.assert_allclose(i1["ignored_imag"], [1.0])
