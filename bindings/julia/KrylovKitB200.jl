@@ -1,0 +1,254 @@
+# KrylovKitB200.jl — the reference-side binding of libb200krylov.so (include/b200krylov.h).
+#
+# STATUS: written against KrylovKit.jl v0.10.4 / VectorInterface.jl 0.5 signatures, NOT RUN: there is no
+# Julia in the build image.  The Python package krylovkit.jl_b200/ binds the same C-ABI entry points in
+# the same pairing and is what the test-suite exercises (INTEGRATION.md §6).  Everything below is a
+# one-to-one `ccall`; no numerical code lives here.
+#
+# Usage:
+#     using KrylovKit, KrylovKitB200
+#     ctx = B200Ctx(size(A, 1), 40)                  # n rows, 40 slab columns (≈ krylovdim + 10)
+#     op  = B200CSR(ctx, A)                          # A::SparseMatrixCSC{Float64,Int64}
+#     x0  = B200Vec(ctx, rand(size(A, 1)))
+#     vals, vecs, info = eigsolve(op, x0, 4, :SR, Lanczos(; orth = ClassicalGramSchmidt2()))
+module KrylovKitB200
+
+using KrylovKit, VectorInterface, LinearAlgebra, SparseArrays
+import KrylovKit: OrthonormalBasis, Orthogonalizer, apply, apply_normal, apply_adjoint
+import KrylovKit: project!!, unproject!!, rank1update!, basistransform!, orthogonalize!!
+import KrylovKit: ClassicalGramSchmidt, ModifiedGramSchmidt, ClassicalGramSchmidt2, ModifiedGramSchmidt2,
+    ClassicalGramSchmidtIR, ModifiedGramSchmidtIR
+
+export B200Ctx, B200Vec, B200CSR, B200Dense
+
+const lib = get(ENV, "B200KRYLOV_LIB", "libb200krylov.so")
+
+# ---- status codes -> exceptions (include/b200krylov.h: B2K_OK … B2K_ENOTSUP) -------------------------
+function check(ctxh::Ptr{Cvoid}, st::Cint)
+    st == 0 && return nothing
+    msg = unsafe_string(ccall((:b2k_last_error, lib), Cstring, (Ptr{Cvoid},), ctxh))
+    st == -1 && throw(ArgumentError(msg))            # B2K_EINVAL
+    st == -2 && throw(DimensionMismatch(msg))        # B2K_EDIM   (orthonormal.jl:93,140,158-161)
+    error("b200krylov [$st]: $msg")                   # CUDA / memory / NCCL / not supported
+end
+
+# ---- context -------------------------------------------------------------------------------------------
+mutable struct B200Ctx
+    h::Ptr{Cvoid}
+    n::Int
+    T::DataType
+end
+function B200Ctx(n::Integer, ncols::Integer; T::Type{<:Union{Float64, Float32}} = Float64, device::Integer = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:b2k_ctx_create, lib), Cint, (Ref{Ptr{Cvoid}}, Cint, Int64, Cint, Cint),
+                        h, device, n, ncols, T === Float64 ? 0 : 1))
+    ctx = B200Ctx(h[], n, T)
+    finalizer(c -> ccall((:b2k_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), ctx)
+    return ctx
+end
+# one process per GPU: uid = 128 bytes from b2k_nccl_unique_id on rank 0, broadcast by MPI / Distributed
+function B200Ctx(nlocal::Integer, ncols::Integer, rank::Integer, nranks::Integer, uid::Vector{UInt8},
+                 nglobal::Integer, rowoffset::Integer; T = Float64, device::Integer = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:b2k_ctx_create_dist, lib), Cint,
+                        (Ref{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Cint, Cint, Ptr{UInt8}, Int64, Int64),
+                        h, device, nlocal, ncols, T === Float64 ? 0 : 1, rank, nranks, uid, nglobal, rowoffset))
+    ctx = B200Ctx(h[], nlocal, T)
+    finalizer(c -> ccall((:b2k_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), ctx)
+    return ctx
+end
+
+# ---- vectors: one slab column each ----------------------------------------------------------------------
+mutable struct B200Vec{T}
+    ctx::B200Ctx
+    handle::Int32
+end
+function B200Vec(ctx::B200Ctx; space::Integer = 0)
+    v = Ref{Int32}(0)
+    check(ctx.h, ccall((:b2k_vec_alloc, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Int32}), ctx.h, space, v))
+    x = B200Vec{ctx.T}(ctx, v[])
+    finalizer(y -> ccall((:b2k_vec_free, lib), Cint, (Ptr{Cvoid}, Int32), y.ctx.h, y.handle), x)
+    return x
+end
+function B200Vec(ctx::B200Ctx, host::Vector{T}) where {T}
+    T === ctx.T || throw(ArgumentError("host data must be $(ctx.T)"))
+    x = B200Vec(ctx)
+    check(ctx.h, ccall((:b2k_vec_upload, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{T}), ctx.h, x.handle, host))
+    return x
+end
+function Base.Array(x::B200Vec{T}) where {T}
+    out = Vector{T}(undef, x.ctx.n)
+    check(x.ctx.h, ccall((:b2k_vec_download, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{T}), x.ctx.h, x.handle, out))
+    return out
+end
+space(x::B200Vec) = Int(x.handle >> 20)
+_copy(x::B200Vec) = (y = B200Vec(x.ctx; space = space(x));
+    check(x.ctx.h, ccall((:b2k_vec_copy, lib), Cint, (Ptr{Cvoid}, Int32, Int32), x.ctx.h, y.handle, x.handle)); y)
+
+# ---- VectorInterface: the complete list KrylovKit uses (src/innerproductvec.jl:82-137) ------------------
+VectorInterface.scalartype(::Type{B200Vec{T}}) where {T} = T
+
+function VectorInterface.zerovector(x::B200Vec, ::Type{S} = scalartype(x)) where {S <: Number}
+    S === scalartype(x) || throw(ArgumentError("B200Vec is real $(scalartype(x)) only"))
+    y = B200Vec(x.ctx; space = space(x))
+    return zerovector!(y)
+end
+function VectorInterface.zerovector!(x::B200Vec)
+    check(x.ctx.h, ccall((:b2k_vec_zero, lib), Cint, (Ptr{Cvoid}, Int32), x.ctx.h, x.handle))
+    return x
+end
+VectorInterface.zerovector!!(x::B200Vec) = zerovector!(x)
+
+function VectorInterface.scale!(y::B200Vec, x::B200Vec, α::Number)      # y ← α x   (lanczos.jl:257, arnoldi.jl:209)
+    check(y.ctx.h, ccall((:b2k_vec_scale, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Float64),
+                         y.ctx.h, y.handle, x.handle, Float64(α)))
+    return y
+end
+VectorInterface.scale!(x::B200Vec, α::Number) = scale!(x, x, α)
+VectorInterface.scale!!(x::B200Vec, α::Number) = scale!(x, x, α)
+VectorInterface.scale!!(y::B200Vec, x::B200Vec, α::Number) = scale!(y, x, α)
+VectorInterface.scale(x::B200Vec, α::Number) = scale!(B200Vec(x.ctx; space = space(x)), x, α)
+
+function VectorInterface.add!(y::B200Vec, x::B200Vec, α::Number = 1, β::Number = 1)   # y ← β y + α x
+    check(y.ctx.h, ccall((:b2k_vec_axpby, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Float64, Float64),
+                         y.ctx.h, y.handle, x.handle, Float64(α), Float64(β)))
+    return y
+end
+VectorInterface.add!!(y::B200Vec, x::B200Vec, α::Number = 1, β::Number = 1) = add!(y, x, α, β)
+VectorInterface.add(y::B200Vec, x::B200Vec, α::Number = 1, β::Number = 1) = add!(_copy(y), x, α, β)
+
+function VectorInterface.inner(x::B200Vec, y::B200Vec)
+    o = Ref{Float64}(0)
+    check(x.ctx.h, ccall((:b2k_vec_inner, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{Float64}),
+                         x.ctx.h, x.handle, y.handle, o))
+    return o[]
+end
+function LinearAlgebra.norm(x::B200Vec)
+    o = Ref{Float64}(0)
+    check(x.ctx.h, ccall((:b2k_vec_norm, lib), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), x.ctx.h, x.handle, o))
+    return o[]
+end
+
+# ---- operators (src/apply.jl) -----------------------------------------------------------------------------
+mutable struct B200CSR{T}
+    ctx::B200Ctx
+    h::Ptr{Cvoid}
+end
+function B200CSR(ctx::B200Ctx, A::SparseMatrixCSC{T, Int64}) where {T}      # colptr / rowval / nzval as stored
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.h, ccall((:b2k_op_create_csc, lib), Cint,
+                       (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{T}, Cint, Cint),
+                       ctx.h, h, size(A, 1), size(A, 2), nnz(A), A.colptr, A.rowval, A.nzval, 8, 1))
+    return B200CSR{T}(ctx, h[])          # the context owns the operator's device memory
+end
+mutable struct B200Dense{T}
+    ctx::B200Ctx
+    h::Ptr{Cvoid}
+    space_in::Int                         # x of y = A x lives here (length n); y in space 0 (length m)
+end
+function B200Dense(ctx::B200Ctx, A::Matrix{T}, space_in::Integer) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.h, ccall((:b2k_op_create_dense, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{T}, Int64),
+                       ctx.h, h, size(A, 1), size(A, 2), A, stride(A, 2)))
+    return B200Dense{T}(ctx, h[], space_in)
+end
+
+function apply(A::B200CSR, x::B200Vec)                                          # apply.jl:1 — a NEW vector
+    y = B200Vec(x.ctx; space = space(x))
+    check(x.ctx.h, ccall((:b2k_op_apply, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32), x.ctx.h, A.h, x.handle, y.handle))
+    return y
+end
+function apply(A::B200CSR, x::B200Vec, α₀::Number, α₁::Number)                   # apply.jl:4-11
+    y = B200Vec(x.ctx; space = space(x))
+    check(x.ctx.h, ccall((:b2k_op_apply_shifted, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Float64, Float64),
+                         x.ctx.h, A.h, x.handle, y.handle, Float64(α₀), Float64(α₁)))
+    return y
+end
+function apply_normal(A::B200Dense, x::B200Vec)                                  # apply.jl:14
+    y = B200Vec(x.ctx; space = 0)
+    check(x.ctx.h, ccall((:b2k_op_apply, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32), x.ctx.h, A.h, x.handle, y.handle))
+    return y
+end
+function apply_adjoint(A::B200Dense, x::B200Vec)                                 # apply.jl:15
+    y = B200Vec(x.ctx; space = A.space_in)
+    check(x.ctx.h, ccall((:b2k_op_apply_adjoint, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32), x.ctx.h, A.h, x.handle, y.handle))
+    return y
+end
+apply(A::B200Dense, x::B200Vec) = apply_normal(A, x)
+
+# ---- basis fast path: what `Array` gets via _use_multithreaded_array_kernel (orthonormal.jl:66-73) --------
+const B200Basis = OrthonormalBasis{<:B200Vec}
+_cols(b::B200Basis, r) = Int32[b[i].handle for i in r]
+_ctx(b::B200Basis) = b[1].ctx
+
+function project!!(y::AbstractVector, b::B200Basis, x::B200Vec, α::Number = true, β::Number = false,
+                   r = Base.OneTo(length(b)))                                    # orthonormal.jl:88-118
+    length(y) == length(r) || throw(DimensionMismatch())
+    h = β == 0 ? Vector{Float64}(undef, length(r)) : Vector{Float64}(y)
+    check(x.ctx.h, ccall((:b2k_basis_project, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Int32, Float64, Float64, Ptr{Float64}),
+                         x.ctx.h, _cols(b, r), length(r), x.handle, Float64(α), Float64(β), h))
+    y .= h
+    return y
+end
+function unproject!!(y::B200Vec, b::B200Basis, x::AbstractVector, α::Number = true, β::Number = false,
+                     r = Base.OneTo(length(b)))                                  # orthonormal.jl:132-196
+    length(x) == length(r) || throw(DimensionMismatch())
+    check(y.ctx.h, ccall((:b2k_basis_unproject, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Cint, Ptr{Float64}, Float64, Float64),
+                         y.ctx.h, y.handle, _cols(b, r), length(r), Vector{Float64}(x), Float64(α), Float64(β)))
+    return y
+end
+function rank1update!(b::B200Basis, y::B200Vec, x::AbstractVector, α::Number = true, β::Number = true,
+                      r = Base.OneTo(length(b)))                                 # orthonormal.jl:210-275
+    check(y.ctx.h, ccall((:b2k_basis_rank1update, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Int32, Ptr{Float64}, Float64, Float64),
+                         y.ctx.h, _cols(b, r), length(r), y.handle, Vector{Float64}(x), Float64(α), Float64(β)))
+    return b
+end
+function basistransform!(b::B200Basis, U::AbstractMatrix)                         # orthonormal.jl:291-354, in place
+    m, keep = size(U)
+    m == length(b) || throw(DimensionMismatch())
+    Ud = Matrix{Float64}(U)
+    check(_ctx(b).h, ccall((:b2k_basis_transform, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, Cint),
+                           _ctx(b).h, _cols(b, 1:m), m, Ud, m, keep))
+    return b
+end
+
+_tag(::ClassicalGramSchmidt) = (0, 0.0);   _tag(::ModifiedGramSchmidt) = (1, 0.0)
+_tag(::ClassicalGramSchmidt2) = (2, 0.0);  _tag(::ModifiedGramSchmidt2) = (3, 0.0)
+_tag(a::ClassicalGramSchmidtIR) = (4, Float64(a.η));  _tag(a::ModifiedGramSchmidtIR) = (5, Float64(a.η))
+
+function orthogonalize!!(v::B200Vec, b::B200Basis, x::AbstractVector, alg::Orthogonalizer)   # orthonormal.jl:378-452
+    k = length(b)
+    tag, η = _tag(alg)
+    h = Vector{Float64}(undef, k); nrm = Ref{Float64}(0); passes = Ref{Cint}(0)
+    check(v.ctx.h, ccall((:b2k_basis_orthogonalize, lib), Cint,
+                         (Ptr{Cvoid}, Int32, Ptr{Int32}, Cint, Ptr{Float64}, Cint, Float64, Ref{Float64}, Ref{Cint}),
+                         v.ctx.h, v.handle, _cols(b, 1:k), k, h, tag, η, nrm, passes))
+    x[1:k] .= h
+    return (v, x)
+end
+function orthogonalize!!(v::B200Vec, q::B200Vec, alg::Orthogonalizer)             # orthonormal.jl:455-489
+    tag, η = _tag(alg)
+    s = Ref{Float64}(0); nrm = Ref{Float64}(0)
+    check(v.ctx.h, ccall((:b2k_vec_orthogonalize, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Cint, Float64, Ref{Float64}, Ref{Float64}),
+                         v.ctx.h, v.handle, q.handle, tag, η, s, nrm))
+    return (v, s[])
+end
+
+function LinearAlgebra.rmul!(b::B200Basis, G::LinearAlgebra.Givens)               # dense/givens.jl:12-36
+    check(_ctx(b).h, ccall((:b2k_basis_givens, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Float64, Float64),
+                           _ctx(b).h, b[G.i1].handle, b[G.i2].handle, Float64(G.c), Float64(G.s)))
+    return b
+end
+function LinearAlgebra.rmul!(b::B200Basis, H::KrylovKit.Householder)              # dense/reflector.jl:143-154
+    work = B200Vec(_ctx(b); space = space(b[1]))
+    check(_ctx(b).h, ccall((:b2k_basis_householder, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Float64, Int32),
+                           _ctx(b).h, _cols(b, H.r), length(H.r), Vector{Float64}(H.v), Float64(H.β), work.handle))
+    return b
+end
+
+# Optional fused steps (DESIGN.md §3): specialise KrylovKit.expand!(::LanczosIterator{<:B200CSR}, state) on
+# b2k_lanczos_expand, the inner loop of eigsolve(::Lanczos) on b2k_lanczos_expand_many, linsolve(::CG) on
+# b2k_cg_step and linsolve(::BiCGStab) on b2k_bicgstab_half/_full — same pairing as
+# krylovkit.jl_b200/factorizations/lanczos.py::expand_/expand_many_ and linsolve.py::_cg/_bicgstab.
+
+end # module
