@@ -1,0 +1,162 @@
+"""TEST / BASELINE INFRASTRUCTURE ONLY — plugs the OpenMP kernels of oracle/csrc/kernels.c into the
+oracle's primitives so that the CPU baseline runs multi-threaded like KrylovKit's own `Array` fast path
+(src/orthonormal.jl:66-73, 151-196, 322-354) instead of at numpy / scipy single-thread speed.
+
+    with native.patched():                       # swaps ko.apply / inner / norm / _axpy / project /
+        ko.eigsolve_lanczos(A, x0, ...)          # unproject / basistransform for float64 data
+
+The drivers (restart logic, convergence tests, Householder bookkeeping) remain the numpy oracle's; only the
+n-length loops change.  Only tests/, bench.py's CPU legs and __graft_entry__ import this module.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import krylov_oracle as ko
+from .csrc import build as _build
+
+_lib = None
+_P = C.POINTER
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(_build.build())
+        dp, ip32, ip64 = _P(C.c_double), _P(C.c_int32), _P(C.c_int64)
+        pp = _P(dp)
+        lib.nat_num_threads.restype = C.c_int
+        lib.nat_spmv_csr_f64.argtypes = [C.c_int64, ip64, ip32, dp, dp, dp]
+        lib.nat_dot_f64.restype = C.c_double
+        lib.nat_dot_f64.argtypes = [C.c_int64, dp, dp]
+        lib.nat_axpy_f64.argtypes = [C.c_int64, C.c_double, dp, dp]
+        lib.nat_scale_f64.argtypes = [C.c_int64, C.c_double, dp, dp]
+        lib.nat_project_f64.argtypes = [C.c_int64, C.c_int32, pp, dp, C.c_double, C.c_double, dp]
+        lib.nat_unproject_f64.argtypes = [C.c_int64, C.c_int32, pp, dp, C.c_double, C.c_double, dp]
+        lib.nat_basistransform_f64.argtypes = [C.c_int64, C.c_int32, C.c_int32, pp, dp, pp]
+        for f in ("nat_spmv_csr_f64", "nat_axpy_f64", "nat_scale_f64", "nat_project_f64", "nat_unproject_f64",
+                  "nat_basistransform_f64"):
+            getattr(lib, f).restype = None
+        _lib = lib
+    return _lib
+
+
+def num_threads() -> int:
+    return int(load().nat_num_threads())
+
+
+def _d(a):
+    return a.ctypes.data_as(_P(C.c_double))
+
+
+def _ok(*arrs) -> bool:
+    return all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.ndim == 1
+               for a in arrs)
+
+
+def _ptrs(vecs):
+    arr = (_P(C.c_double) * len(vecs))()
+    for i, v in enumerate(vecs):
+        arr[i] = _d(v)
+    return arr
+
+
+class CSR:
+    """CSR operator with the index arrays converted once (int64 rowptr, int32 colidx)."""
+
+    def __init__(self, A):
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        self.shape = A.shape
+        self.rowptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        self.colidx = np.ascontiguousarray(A.indices, dtype=np.int32)
+        self.vals = np.ascontiguousarray(A.data, dtype=np.float64)
+        self.scipy = A
+
+    def __matmul__(self, x):
+        if not _ok(x):
+            return self.scipy @ x
+        y = np.empty(self.shape[0])
+        load().nat_spmv_csr_f64(self.shape[0], self.rowptr.ctypes.data_as(_P(C.c_int64)),
+                                self.colidx.ctypes.data_as(_P(C.c_int32)), _d(self.vals), _d(x), _d(y))
+        return y
+
+
+def inner(x, y):
+    if _ok(x, y):
+        return float(load().nat_dot_f64(len(x), _d(x), _d(y)))
+    return _orig["inner"](x, y)
+
+
+def norm(x):
+    if _ok(x):
+        return float(np.sqrt(load().nat_dot_f64(len(x), _d(x), _d(x))))
+    return _orig["norm"](x)
+
+
+def _axpy(y, a, x):
+    if _ok(x, y):
+        load().nat_axpy_f64(len(y), float(a), _d(x), _d(y))
+        return y
+    return _orig["_axpy"](y, a, x)
+
+
+def project(y, b, x, alpha=1.0, beta=0.0, r=None):
+    vecs = list(b) if r is None else [b[i] for i in r]
+    if vecs and _ok(x, *vecs) and isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous:
+        load().nat_project_f64(len(x), len(vecs), _ptrs(vecs), _d(x), float(alpha), float(beta), _d(y))
+        return y
+    return _orig["project"](y, b, x, alpha, beta, r)
+
+
+def unproject(y, b, x, alpha=1.0, beta=0.0, r=None):
+    vecs = list(b) if r is None else [b[i] for i in r]
+    if vecs and _ok(y, *vecs):
+        out = np.empty_like(y) if beta == 0 else y.copy()      # the oracle's callers keep their input
+        c = np.ascontiguousarray(x, dtype=np.float64)
+        load().nat_unproject_f64(len(out), len(vecs), _ptrs(vecs), _d(c), float(alpha), float(beta), _d(out))
+        return out
+    return _orig["unproject"](y, b, x, alpha, beta, r)
+
+
+def basistransform(b, U):
+    m, keep = U.shape
+    if m == len(b) and _ok(*b[:m]):
+        Uc = np.asfortranarray(U, dtype=np.float64)
+        out = [np.empty_like(b[0]) for _ in range(keep)]
+        load().nat_basistransform_f64(len(b[0]), m, keep, _ptrs(b[:m]), Uc.ctypes.data_as(_P(C.c_double)), _ptrs(out))
+        for j in range(keep):
+            b[j] = out[j]
+        return b
+    return _orig["basistransform"](b, U)
+
+
+_NAMES = ("inner", "norm", "_axpy", "project", "unproject", "basistransform")
+_orig = {name: getattr(ko, name) for name in _NAMES}
+
+
+@contextlib.contextmanager
+def patched():
+    """Route the oracle's n-length primitives through the OpenMP kernels (float64 data; anything else
+    falls through to numpy).  Wrap sparse operators in `native.CSR` to get the threaded matvec too."""
+    load()
+    for name in _NAMES:
+        setattr(ko, name, globals()[name])
+    try:
+        yield
+    finally:
+        for name in _NAMES:
+            setattr(ko, name, _orig[name])
+
+
+def available() -> bool:
+    try:
+        load()
+        return True
+    except (OSError, FileNotFoundError, Exception):      # no gcc / no OpenMP runtime: numpy oracle only
+        return False

@@ -583,3 +583,49 @@ def test_realeigsolve_oracle():
     D1, _, i1 = ko.realeigsolve_arnoldi(np.array([[1.0, -1.0], [1.0, 1.0]]), np.array([1.0, 0.3]), 1, "LM", tol=1e-8)
     np.testing.assert_allclose(D1, 1.0)
     np.testing.assert_allclose(i1["ignored_imag"], [1.0])
+
+
+def test_native_cpu_kernels_match_numpy_oracle():
+    """oracle/csrc/kernels.c (the multi-threaded CPU baseline's n-length loops) against the numpy primitives
+    they replace, then through the whole eigsolve driver: same numops, Ritz values to 1e-11."""
+    from oracle import native
+    if not native.available():
+        pytest.skip("no gcc / OpenMP runtime")
+    rng = np.random.default_rng(4)
+    n, k = 211 * 237, 7
+    x, y = rng.random(n), rng.random(n)
+    B = [rng.random(n) for _ in range(k)]
+    c = rng.standard_normal(k)
+    h0, h1 = rng.random(k), None
+    A = ko.stencil_matrix(211, 237)
+    U = np.linalg.qr(rng.standard_normal((k, k)))[0][:, :4]
+    want = dict(inner=ko.inner(x, y), norm=ko.norm(x), proj=ko.project(h0.copy(), B, x, 0.7, 0.3),
+                unproj=ko.unproject(y, B, c, -1.0, 1.0), unproj0=ko.unproject(y, B, c, 2.0, 0.0),
+                bt=ko.basistransform([b.copy() for b in B], U)[:4], mv=A @ x)
+    with native.patched():
+        assert ko.inner is native.inner
+        np.testing.assert_allclose(ko.inner(x, y), want["inner"], rtol=1e-13)
+        np.testing.assert_allclose(ko.norm(x), want["norm"], rtol=1e-13)
+        np.testing.assert_allclose(ko.project(h0.copy(), B, x, 0.7, 0.3), want["proj"], rtol=1e-12)
+        y_in = y.copy()
+        np.testing.assert_allclose(ko.unproject(y, B, c, -1.0, 1.0), want["unproj"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(y, y_in)                       # callers keep their input
+        np.testing.assert_allclose(ko.unproject(y, B, c, 2.0, 0.0), want["unproj0"], rtol=1e-12, atol=1e-12)
+        got = ko.basistransform([b.copy() for b in B], U)[:4]
+        for g, w in zip(got, want["bt"]):
+            np.testing.assert_allclose(g, w, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(native.CSR(A) @ x, want["mv"], rtol=1e-13)
+        z = y.copy()
+        ko._axpy(z, 0.25, x)
+        np.testing.assert_allclose(z, y + 0.25 * x, rtol=1e-15)
+        # float32 data falls through to numpy
+        assert isinstance(ko.inner(x.astype(np.float32), y.astype(np.float32)), float)
+    assert ko.inner is not native.inner
+    nx, ny = 120, 90
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(3, nx * ny)
+    D0, _, i0 = ko.eigsolve_lanczos(A, x0, 3, "SR", krylovdim=16, maxiter=6, tol=0.0, orth=ko.Orth(ko.CGS2))
+    with native.patched():
+        D1, _, i1 = ko.eigsolve_lanczos(native.CSR(A), x0, 3, "SR", krylovdim=16, maxiter=6, tol=0.0, orth=ko.Orth(ko.CGS2))
+    assert i0["numops"] == i1["numops"] and i0["converged"] == i1["converged"]
+    np.testing.assert_allclose(D1, D0, rtol=1e-11)
