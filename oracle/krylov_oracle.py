@@ -155,14 +155,21 @@ def project(y, b, x, alpha=1.0, beta=0.0, r=None):
     return y
 
 
-def unproject(y, b, x, alpha=1.0, beta=0.0, r=None):
-    """orthonormal.jl:132-150 (generic BLAS-1 path)."""
+def scale_(x, a):
+    """scale!!(x, a) IN PLACE — for arrays the caller owns (lanczos.jl:257 `scale!!(r, 1/β)`)."""
+    x *= x.dtype.type(a)
+    return x
+
+
+def unproject(y, b, x, alpha=1.0, beta=0.0, r=None, inplace=False):
+    """orthonormal.jl:132-150 (generic BLAS-1 path).  `inplace` (beta == 1 only): update y itself, as the
+    reference's unproject!! does — for callers that own y; by default the input is left untouched."""
     r = range(len(b)) if r is None else r
     if beta == 0:
         y = np.zeros_like(y)         # hard zero
     elif beta != 1:
         y = y * beta
-    else:
+    elif not inplace:
         y = y.copy()                 # the oracle's callers keep their input; one copy, then in-place axpys
     for i, ri in enumerate(r):
         y = _axpy(y, alpha * x[i], b[ri])
@@ -197,9 +204,9 @@ def basistransform(b, U):
     return b
 
 
-def _cgs_pass(v, b, x):
+def _cgs_pass(v, b, x, own=False):
     x = project(x, b, v)             # orthonormal.jl:381
-    v = unproject(v, b, x, -1, 1)    # :382
+    v = unproject(v, b, x, -1, 1, inplace=own)    # :382
     return v, x
 
 
@@ -451,7 +458,7 @@ def lanczos_recurrence(A, V, beta, orth: Orth):
         w = _axpy(w, -beta, V[-2])   # w is the fresh result of apply: mutate in place like add!!
         w = _axpy(w, -alpha, v)
         s = np.empty(len(V))
-        w, s = _cgs_pass(w, V, s)
+        w, s = _cgs_pass(w, V, s, own=True)
         alpha += s[-1]
         return w, alpha, norm(w)
     if t == MGS2:
@@ -500,7 +507,7 @@ def lanczos_recurrence(A, V, beta, orth: Orth):
 def lanczos_expand(A, f: LanczosFact, orth: Orth):
     """expand! — factorizations/lanczos.jl:250-272."""
     betaold = f.normres()
-    f.V.append(f.r * (1 / betaold))
+    f.V.append(scale_(f.r, 1 / betaold))       # the residual's storage becomes the new basis vector (:257)
     r, alpha, beta = lanczos_recurrence(A, f.V, betaold, orth)
     f.alphas.append(alpha)
     f.betas.append(beta)

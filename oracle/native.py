@@ -114,14 +114,26 @@ def project(y, b, x, alpha=1.0, beta=0.0, r=None):
     return _orig["project"](y, b, x, alpha, beta, r)
 
 
-def unproject(y, b, x, alpha=1.0, beta=0.0, r=None):
+def scale_(x, a):
+    if _ok(x):
+        load().nat_scale_f64(len(x), float(a), _d(x), _d(x))
+        return x
+    return _orig["scale_"](x, a)
+
+
+def unproject(y, b, x, alpha=1.0, beta=0.0, r=None, inplace=False):
     vecs = list(b) if r is None else [b[i] for i in r]
     if vecs and _ok(y, *vecs):
-        out = np.empty_like(y) if beta == 0 else y.copy()      # the oracle's callers keep their input
+        if beta == 0:
+            out = np.empty_like(y)
+        elif inplace and beta == 1:
+            out = y                                             # the caller owns y (unproject!! semantics)
+        else:
+            out = y.copy()                                      # the oracle's callers keep their input
         c = np.ascontiguousarray(x, dtype=np.float64)
         load().nat_unproject_f64(len(out), len(vecs), _ptrs(vecs), _d(c), float(alpha), float(beta), _d(out))
         return out
-    return _orig["unproject"](y, b, x, alpha, beta, r)
+    return _orig["unproject"](y, b, x, alpha, beta, r, inplace)
 
 
 def basistransform(b, U):
@@ -136,7 +148,7 @@ def basistransform(b, U):
     return _orig["basistransform"](b, U)
 
 
-_NAMES = ("inner", "norm", "_axpy", "project", "unproject", "basistransform")
+_NAMES = ("inner", "norm", "_axpy", "scale_", "project", "unproject", "basistransform")
 _orig = {name: getattr(ko, name) for name in _NAMES}
 
 
