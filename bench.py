@@ -37,6 +37,10 @@ import argparse
 import ctypes as C
 import json
 import os
+
+# libgomp reads this once, when it is first loaded (torch loads it): idle OpenMP workers of the CPU baseline
+# must sleep, not spin, on hosts whose logical CPUs are shared
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 import subprocess
 import sys
 import threading
@@ -151,9 +155,22 @@ def _cpu_backend():
 
 
 def _cpu_operator(nx, ny, native):
+    """Host operator; with the OpenMP backend also settles the thread count by a short calibration
+    (nproc threads are not always the fastest choice on a shared box) and logs the host's CPU limits."""
     from oracle import krylov_oracle as ko
     A = ko.stencil_matrix(nx, ny)
-    return native.CSR(A) if native is not None else A
+    if native is None:
+        return A
+    An = native.CSR(A)
+    log = lambda m: print(m, file=sys.stderr, flush=True)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/proc/loadavg"):
+        try:
+            log(f"host: {path} = {open(path).read().strip()}")
+        except OSError:
+            pass
+    t = native.calibrate(An, ko.splitmix_vector(SEED, nx * ny), verbose=log)
+    log(f"host: using {t} OpenMP threads of {os.cpu_count()} logical CPUs")
+    return An
 
 
 def cpu_sample(nx, ny, krylovdim, orth_name, nsteps, A=None):

@@ -21,6 +21,14 @@
 
 #define RED_BLOCK 16384   /* rows per partial sum */
 
+void nat_set_num_threads(int t) {
+#ifdef _OPENMP
+    if (t >= 1) omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
+
 int nat_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -27,10 +27,13 @@ _P = C.POINTER
 def load():
     global _lib
     if _lib is None:
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")     # only effective if libgomp is not loaded yet
         lib = C.CDLL(_build.build())
         dp, ip32, ip64 = _P(C.c_double), _P(C.c_int32), _P(C.c_int64)
         pp = _P(dp)
         lib.nat_num_threads.restype = C.c_int
+        lib.nat_set_num_threads.argtypes = [C.c_int]
+        lib.nat_set_num_threads.restype = None
         lib.nat_spmv_csr_f64.argtypes = [C.c_int64, ip64, ip32, dp, dp, dp]
         lib.nat_dot_f64.restype = C.c_double
         lib.nat_dot_f64.argtypes = [C.c_int64, dp, dp]
@@ -48,6 +51,38 @@ def load():
 
 def num_threads() -> int:
     return int(load().nat_num_threads())
+
+
+def set_num_threads(t: int) -> None:
+    load().nat_set_num_threads(int(t))
+
+
+def calibrate(A: "CSR", x: np.ndarray, k: int = 8, verbose=None) -> int:
+    """Pick the OpenMP thread count that is actually fastest on this host for one representative step
+    (fresh-output matvec + project + in-place unproject + dot at the real n): on shared / quota-limited
+    boxes `nproc` threads can be far slower than fewer.  Leaves the winner installed and returns it."""
+    import time
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({t for t in (ncpu, ncpu // 2, ncpu // 4, ncpu // 8, 16, 8, 4) if 1 <= t <= ncpu}, reverse=True)
+    basis = [x * (1.0 + 0.01 * j) for j in range(k)]
+    h = np.zeros(k)
+    best_t, best = cands[0], float("inf")
+    for t in cands:
+        set_num_threads(t)
+        dt = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            w = A @ x
+            project(h, basis, w)
+            w = unproject(w, basis, h, -1.0, 1.0, inplace=True)
+            inner(w, x)
+            dt = min(dt, time.perf_counter() - t0)
+        if verbose:
+            verbose(f"native.calibrate: {t} threads -> {dt * 1e3:.1f} ms per step sample")
+        if dt < best:
+            best_t, best = t, dt
+    set_num_threads(best_t)
+    return best_t
 
 
 def _d(a):
