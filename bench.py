@@ -173,6 +173,18 @@ def _cpu_operator(nx, ny, native):
     return An
 
 
+def _cpu_host_note():
+    """'N threads; cgroup CPU quota Q of M logical CPUs' — what the CPU legs really had."""
+    note = f"{os.cpu_count()} logical CPUs"
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            note += f", cgroup CPU quota {float(q) / float(per):g}"
+    except (OSError, ValueError):
+        pass
+    return note
+
+
 def cpu_sample(nx, ny, krylovdim, orth_name, nsteps, A=None):
     """Restated reference path on the host cores: initialize + nsteps expand! at full n."""
     from oracle import krylov_oracle as ko
@@ -212,6 +224,9 @@ def run_reference(a):
         return
     native, _, cores, backend = _cpu_backend()
     A = _cpu_operator(a.nx, a.ny, native)
+    if native is not None:
+        cores = native.num_threads()                 # the calibrated thread count
+    backend += f" with {cores} threads ({_cpu_host_note()})"
     # one short untimed sample (also the warm-up) sizes the work so that the whole --steps K run stays within
     # ~4 minutes whatever K the driver passes: the full job if it fits, else a bounded number of expand! steps
     # (the cost of a step grows with the basis size: the job averages ~3x the cost of the first four steps)
@@ -424,8 +439,12 @@ def run_ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        _, _, cores, backend = _cpu_backend()
-        v, dt, ops = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, a.cpu_steps, None)
+        native, _, cores, backend = _cpu_backend()
+        A_host = _cpu_operator(a.nx, a.ny, native)
+        if native is not None:
+            cores = native.num_threads()             # the calibrated thread count
+        backend += f" with {cores} threads ({_cpu_host_note()})"
+        v, dt, ops = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, a.cpu_steps, A_host)
         cpu = {"value": v, "unit": "it/s", "cores": cores, "kind": "port",
                "sample": f"initialize + {a.cpu_steps} expand! steps ({ops} operator applications, basis sizes "
                          f"1..{a.cpu_steps + 1}) of the same n={n} job in {dt:.1f} s; oracle/krylov_oracle.py "
