@@ -1,6 +1,11 @@
 import os
 import sys
 
+# The oracle makes thousands of small BLAS-1 calls; OpenBLAS' default of one spinning thread per logical
+# CPU makes each of them cost milliseconds on shared / quota-limited hosts.  Must be set before numpy loads.
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "4")
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
