@@ -629,3 +629,46 @@ def test_native_cpu_kernels_match_numpy_oracle():
         D1, _, i1 = ko.eigsolve_lanczos(native.CSR(A), x0, 3, "SR", krylovdim=16, maxiter=6, tol=0.0, orth=ko.Orth(ko.CGS2))
     assert i0["numops"] == i1["numops"] and i0["converged"] == i1["converged"]
     np.testing.assert_allclose(D1, D0, rtol=1e-11)
+
+
+def test_oracle_agrees_with_scipys_independent_implementations():
+    """Pins from implementations that share no code with the oracle (or with KrylovKit): SciPy's LSMR
+    (Fong & Saunders' own algorithm) iterate-for-iterate incl. the ‖Aᵀr‖ estimate, its BiCGStab
+    iterate-for-iterate, expm_multiply (Al-Mohy & Higham) for exponentiate, ARPACK for the extremal
+    eigenvalues and singular values."""
+    import scipy.sparse.linalg as spl
+    rng = np.random.default_rng(0)
+    A = sp.random(300, 120, density=0.05, random_state=1).tocsr() + sp.eye(300, 120).tocsr()
+    b = rng.random(300)
+    for k in (3, 10, 25):
+        x, info = ko.lssolve_lsmr(A.toarray(), b, maxiter=k, krylovdim=1, tol=0.0)
+        ref = spl.lsmr(A, b, atol=0, btol=0, conlim=0, maxiter=k)
+        np.testing.assert_allclose(x, ref[0], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(info["normres"], ref[4], rtol=1e-9)            # ‖Aᵀ r‖ estimate
+    x, _ = ko.lssolve_lsmr(A.toarray(), b, maxiter=15, krylovdim=1, tol=0.0, lam=0.3)
+    np.testing.assert_allclose(x, spl.lsmr(A, b, damp=0.3, atol=0, btol=0, conlim=0, maxiter=15)[0], rtol=1e-5, atol=1e-8)
+
+    N = sp.diags([-1.3, 2.6, -0.7], [-1, 0, 1], shape=(400, 400)).tocsr()
+    bb = rng.random(400)
+    x, _ = ko.linsolve_bicgstab(N, bb, maxiter=8, tol=1e-300)
+    try:
+        xs, _ = spl.bicgstab(N, bb, rtol=0, atol=0, maxiter=8)
+    except TypeError:                                                              # older SciPy keyword
+        xs, _ = spl.bicgstab(N, bb, tol=0, atol=0, maxiter=8)
+    np.testing.assert_allclose(x, xs, rtol=1e-12, atol=1e-14)
+
+    S = ko.stencil_matrix(30, 20).tocsr()
+    v = rng.random(600)
+    w, info = ko.expintegrator(S, -0.7, (v,), "lanczos", ko.Orth(ko.MGS2), krylovdim=30, tol=1e-12)
+    assert info["converged"] == 1
+    np.testing.assert_allclose(w, spl.expm_multiply(-0.7 * S, v), rtol=1e-11, atol=1e-13)
+    C = (S + sp.diags([0.4], [1], shape=S.shape)).tocsr()                          # non-symmetric: Arnoldi
+    w, info = ko.expintegrator(C, 0.35, (v,), "arnoldi", ko.Orth(ko.MGS2), krylovdim=30, tol=1e-12)
+    np.testing.assert_allclose(w, spl.expm_multiply(0.35 * C, v), rtol=1e-10, atol=1e-12)
+
+    vals, _, info = ko.eigsolve_lanczos(S, v, 3, "SR", krylovdim=30, maxiter=200, tol=1e-11, orth=ko.Orth(ko.MGS2))
+    assert info["converged"] >= 3
+    np.testing.assert_allclose(vals[:3], np.sort(spl.eigsh(S, k=3, which="SA", tol=1e-12)[0]), rtol=1e-9)
+    D = rng.standard_normal((90, 40))
+    sv, _, _, info = ko.svdsolve_gkl(D, rng.random(90), 3, "LR", krylovdim=20, maxiter=200, tol=1e-11, orth=ko.Orth(ko.MGS2))
+    np.testing.assert_allclose(sv[:3], np.sort(spl.svds(D, k=3, tol=1e-12)[1])[::-1], rtol=1e-9)
