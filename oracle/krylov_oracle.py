@@ -14,6 +14,11 @@ the KrylovKit.jl v0.10.4 tree):
   * src/factorizations/blocklanczos.jl:43-52, 277-284, 312-353 block primitives
   * src/eigsolve/lanczos.jl:1-155, src/linsolve/gmres.jl:1-151, src/eigsolve/svdsolve.jl:144-314
   * src/dense/linalg.jl:96-106 ldiv!, :306-333 permuteeig!, packedhessenberg.jl:32-48
+  * widened rows: src/linsolve/cg.jl, bicgstab.jl, src/lssolve/lsmr.jl, src/factorizations/blocklanczos.jl
+    + src/eigsolve/blocklanczos.jl, src/eigsolve/arnoldi.jl (schursolve / eigsolve / realeigsolve) with
+    src/dense/linalg.jl:150-393 (real Schur helpers), src/matrixfun/expintegrator.jl:101-323
+  The n-length loops also exist in C/OpenMP (oracle/csrc/kernels.c, plugged in by oracle/native.py) for
+  the timed CPU baseline; they are checked against the numpy primitives here.
 
 Arithmetic that lives outside the reference tree (VectorInterface.jl 0.5/0.6, Julia's
 LinearAlgebra/OpenBLAS, SparseArrays — Project.toml:31-48, no Manifest => versions
@@ -28,8 +33,11 @@ against the reference's own known-answer fixtures (tests/test_oracle_golden.py):
 the literal 71x71 matrix of issue #143 (test/issues.jl:39-129), eigsolve([1 0;0 1])
 (issues.jl:32-36), the toric-code ground energy -16 (test/eigsolve.jl:471-549) and the
 invariants the reference asserts after every expand!/shrink! (test/factorize.jl:140-158,
-185-203, 285-309).  Bit-level parity with the Julia/OpenBLAS reduction order is
-"parity unpinned": no reference test fixes it.
+185-203, 285-309), lssolve(I(2), [1, 0]) of issue #133 (issues.jl:21-29), and — for every widened
+solver — the assertions of the reference's own test file for it (test/linsolve.jl, lssolve.jl,
+eigsolve.jl, expintegrator.jl), run on the oracle.  Independent implementations agree too: SciPy's LSMR
+and BiCGStab iterate for iterate, expm_multiply, ARPACK.  Bit-level parity with the Julia/OpenBLAS
+reduction order is "parity unpinned": no reference test fixes it.
 """
 from __future__ import annotations
 
