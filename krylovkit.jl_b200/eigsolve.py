@@ -23,7 +23,7 @@ from .orthonormal import OrthonormalBasis, basistransform_
 from .vectors import B200Context, B200Vec
 
 
-def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = None,
+def eigsolve(A, x0=None, howmany: int = 1, which: str = "LM", alg: Lanczos | None = None,
              out_vectors=None, shard=None, nccl_uid: bytes | None = None, device: int = 0, **kwargs):
     """eigsolve(A, x₀, howmany, which, alg::Lanczos) — src/eigsolve/lanczos.jl:1-155.
 
@@ -32,6 +32,11 @@ def eigsolve(A, x0, howmany: int = 1, which: str = "LM", alg: Lanczos | None = N
          solved on the GPU and the vectors are downloaded: the end-to-end path).
     Returns (values, vectors, ConvergenceInfo).
     """
+    if x0 is None:
+        # eigsolve(A::AbstractMatrix, howmany, which; kwargs...) — eigsolve.jl:195-201: random start vector
+        if not hasattr(A, "shape"):
+            raise TypeError("eigsolve: a start vector is required unless A is a host matrix")
+        x0 = np.random.default_rng().random(A.shape[0])
     if alg is None:
         alg = eigselector(A, block=isinstance(x0, blz.Block), **kwargs)
     elif kwargs:

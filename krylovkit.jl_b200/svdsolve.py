@@ -15,13 +15,18 @@ from .orthonormal import basistransform_, rmul_householder_
 from .vectors import B200Context, B200Vec
 
 
-def svdsolve(A, u0, howmany: int = 1, which: str = "LR", alg: GKL | None = None, **kwargs):
+def svdsolve(A, u0=None, howmany: int = 1, which: str = "LR", alg: GKL | None = None, **kwargs):
     """svdsolve(A, x₀, howmany, which, alg::GKL).  u0 lives in the codomain (length m).
     Host entry: A = numpy m x n array, u0 = numpy vector -> uploaded, solved, downloaded."""
     if which not in ("LR", "SR"):
         raise ValueError(f"invalid specification of which singular values to target: which = {which}")
     if alg is None:
         alg = GKL(**kwargs)
+    if u0 is None:
+        # svdsolve(A::AbstractMatrix, howmany, which; kwargs...) — svdsolve.jl:123-129: random start vector
+        if not hasattr(A, "shape"):
+            raise TypeError("svdsolve: a start vector is required unless A is a host matrix")
+        u0 = np.random.default_rng().random(np.asarray(A).shape[0]).astype(np.asarray(A).dtype if np.asarray(A).dtype == np.float32 else np.float64)
     if isinstance(u0, B200Vec):
         return _svdsolve_gkl(A, u0, howmany, which, alg)
     A = np.asarray(A)
