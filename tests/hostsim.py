@@ -63,12 +63,55 @@ class _Space:
 
 
 class _Ctx:
-    def __init__(self, n, ncols, dtype):
+    def __init__(self, n, ncols, dtype, dist=None):
         self.dtype = np.float64 if dtype == L.F64 else np.float32
         self.ctype = C.c_double if dtype == L.F64 else C.c_float
         self.spaces = [_Space(n, ncols)]
+        self.sharded = [True]
         self.err = b""
         self.launches = 0
+        self.dist = dist            # None, or dict(rank, nranks, n_global, row_offset): rows sharded over ranks
+
+    def allsum(self, v, sharded=True):
+        """The library's all-reduce of scalars / coefficient vectors (NCCL there, gloo here)."""
+        a = np.atleast_1d(np.asarray(v, dtype=np.float64)).copy()
+        if self.dist is not None and sharded:
+            import torch
+            import torch.distributed as tdist
+            t = torch.from_numpy(a)
+            tdist.all_reduce(t)
+            a = t.numpy()
+        return a
+
+    def gather_rows(self, x):
+        """x over all ranks, in rank order (what the halo exchange provides to the local rows)."""
+        if self.dist is None:
+            return x
+        import torch.distributed as tdist
+        parts = [None] * self.dist["nranks"]
+        tdist.all_gather_object(parts, np.asarray(x))
+        return np.concatenate(parts)
+
+
+class _global_reductions:
+    """While active, the oracle's inner / norm see GLOBAL sums — so that its orthogonalisation and block
+    routines, run on the local rows by every rank, behave like the library's sharded kernels."""
+
+    def __init__(self, ctx: _Ctx, sharded=True):
+        self.ctx, self.on = ctx, ctx.dist is not None and sharded
+
+    def __enter__(self):
+        if self.on:
+            self.saved = (ko.inner, ko.norm)
+            ctx = self.ctx
+            ko.inner = lambda x, y: float(ctx.allsum(np.dot(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)))[0])
+            ko.norm = lambda x: float(np.sqrt(ctx.allsum(np.dot(np.asarray(x, dtype=np.float64), np.asarray(x, dtype=np.float64)))[0]))
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            ko.inner, ko.norm = self.saved
+        return False
 
 
 class HostSimLib:
@@ -94,6 +137,9 @@ class HostSimLib:
         v = int(v)
         ctx.spaces[v >> 20].cols[v & 0xFFFFF][:] = arr
 
+    def _sh(self, ctx, v):
+        return ctx.sharded[int(v) >> 20]
+
     def _cols(self, ctx, cols, k):
         return [self._vec(ctx, c) for c in list(cols)[:k]]
 
@@ -112,6 +158,16 @@ class HostSimLib:
         _set(out, self.next_id)
         return L.OK
 
+    def b2k_nccl_unique_id(self, buf):
+        return L.OK
+
+    def b2k_ctx_create_dist(self, out, device, n_local, ncols, dtype, rank, nranks, uid, n_global, row_offset):
+        self.next_id += 1
+        self.ctxs[self.next_id] = _Ctx(n_local, ncols, dtype, dict(rank=int(rank), nranks=int(nranks),
+                                                                   n_global=int(n_global), row_offset=int(row_offset)))
+        _set(out, self.next_id)
+        return L.OK
+
     def b2k_ctx_destroy(self, h):
         self.ctxs.pop(_key(h), None)
         return L.OK
@@ -119,6 +175,7 @@ class HostSimLib:
     def b2k_space_create(self, h, n_local, ncols, sharded, out):
         ctx = self._c(h)
         ctx.spaces.append(_Space(n_local, ncols))
+        ctx.sharded.append(bool(sharded))
         _set(out, len(ctx.spaces) - 1)
         return L.OK
 
@@ -192,7 +249,8 @@ class HostSimLib:
 
     def b2k_vec_fill_splitmix(self, h, v, seed):
         ctx = self._c(h)
-        self._setvec(ctx, v, ko.splitmix_vector(int(seed), len(self._vec(ctx, v))))
+        off = ctx.dist["row_offset"] if (ctx.dist and self._sh(ctx, v)) else 0
+        self._setvec(ctx, v, ko.splitmix_vector(int(seed), len(self._vec(ctx, v)), offset=off))
         return L.OK
 
     def b2k_vec_inner(self, h, x, y, out):
@@ -200,11 +258,13 @@ class HostSimLib:
         a, b = self._vec(ctx, x), self._vec(ctx, y)
         if len(a) != len(b):
             return self._fail(ctx, L.EDIM, "inner: length mismatch")
-        _set(out, float(np.dot(a.astype(np.float64), b.astype(np.float64))))
+        _set(out, float(ctx.allsum(np.dot(a.astype(np.float64), b.astype(np.float64)), self._sh(ctx, x))[0]))
         return L.OK
 
     def b2k_vec_norm(self, h, x, out):
-        _set(out, float(np.linalg.norm(self._vec(self._c(h), x).astype(np.float64))))
+        ctx = self._c(h)
+        a = self._vec(ctx, x).astype(np.float64)
+        _set(out, float(np.sqrt(ctx.allsum(np.dot(a, a), self._sh(ctx, x))[0])))
         return L.OK
 
     def b2k_vec_axpby(self, h, y, x, alpha, beta):
@@ -240,6 +300,8 @@ class HostSimLib:
         va = np.array(_view(vals, nnz, ctx.ctype))
         if not any(s.n == n_rows for s in ctx.spaces):
             return self._fail(ctx, L.EDIM, f"CSR: {n_rows} local rows but space 0 holds {ctx.spaces[0].n}")
+        if ctx.dist is not None:                      # local rows, GLOBAL column indices
+            n_cols = ctx.dist["n_global"]
         return self._newop(out, sp.csr_matrix((va, ci, rp), shape=(n_rows, n_cols)))
 
     def b2k_op_create_csc(self, h, out, n_rows, n_cols, nnz, colptr, rowval, nzval, idx_bytes, index_base):
@@ -252,7 +314,11 @@ class HostSimLib:
 
     def b2k_op_create_stencil(self, h, out, nx, ny, nz, c):
         ctx = self._c(h)
-        return self._newop(out, ko.stencil_matrix(nx, ny, nz, tuple(float(c[i]) for i in range(7)), dtype=ctx.dtype))
+        A = ko.stencil_matrix(nx, ny, nz, tuple(float(c[i]) for i in range(7)), dtype=ctx.dtype)
+        if ctx.dist is not None:                      # this rank's rows of the global operator
+            r0 = ctx.dist["row_offset"]
+            A = A[r0:r0 + ctx.spaces[0].n].tocsr()
+        return self._newop(out, A)
 
     def b2k_op_create_dense(self, h, out, m, n, host, ld):
         ctx = self._c(h)
@@ -287,6 +353,16 @@ class HostSimLib:
         A = self.ops[_key(op)]
         xv, yv = self._vec(ctx, x), self._vec(ctx, y)
         M = A.T if adjoint else A
+        if ctx.dist is not None:
+            if not sp.issparse(A) or adjoint:
+                return self._fail(ctx, L.ENOTSUP, "hostsim: only sharded CSR operators are simulated")
+            xg = ctx.gather_rows(xv)                  # stands for the halo exchange
+            if M.shape[1] != len(xg) or M.shape[0] != len(yv):
+                return self._fail(ctx, L.EDIM, "apply: shard / operator mismatch")
+            ctx.launches += 1
+            r = M @ xg
+            self._setvec(ctx, y, a1 * r + a0 * xv if (a0 != 0 or a1 != 1) else r)
+            return L.OK
         if M.shape[1] != len(xv) or M.shape[0] != len(yv):
             return self._fail(ctx, L.EDIM, f"apply: x has {len(xv)} entries, operator wants {M.shape[1]}")
         ctx.launches += 1
@@ -310,7 +386,8 @@ class HostSimLib:
         ctx = self._c(h)
         st = self._apply(ctx, op, x, y)
         if st == L.OK:
-            _set(out, float(np.dot(self._vec(ctx, v).astype(np.float64), self._vec(ctx, y).astype(np.float64))))
+            d = np.dot(self._vec(ctx, v).astype(np.float64), self._vec(ctx, y).astype(np.float64))
+            _set(out, float(ctx.allsum(d, self._sh(ctx, y))[0]))
         return st
 
     # ---- basis ----------------------------------------------------------------------------------
@@ -318,10 +395,14 @@ class HostSimLib:
         ctx = self._c(h)
         hv = _view(hptr, k, C.c_double)
         xv = self._vec(ctx, x).astype(np.float64)
+        dots = np.zeros(k)
         for j, q in enumerate(self._cols(ctx, cols, k)):
             if len(q) != len(xv):
                 return self._fail(ctx, L.EDIM, "project: length mismatch")
-            hv[j] = (beta * hv[j] if beta != 0 else 0.0) + alpha * float(np.dot(q.astype(np.float64), xv))
+            dots[j] = float(np.dot(q.astype(np.float64), xv))
+        dots = ctx.allsum(dots, self._sh(ctx, x))
+        for j in range(k):
+            hv[j] = (beta * hv[j] if beta != 0 else 0.0) + alpha * dots[j]
         ctx.launches += 1
         return L.OK
 
@@ -343,10 +424,12 @@ class HostSimLib:
         hv = _view(hptr, k, C.c_double)
         b = [q.astype(np.float64) for q in self._cols(ctx, cols, k)]
         x = np.zeros(k)
-        w, x = ko.orthogonalize(self._vec(ctx, v).astype(np.float64), b, x, ko.Orth(int(alg), float(eta)))
+        with _global_reductions(ctx, self._sh(ctx, v)):
+            w, x = ko.orthogonalize(self._vec(ctx, v).astype(np.float64), b, x, ko.Orth(int(alg), float(eta)))
+            nw = ko.norm(w)
         self._setvec(ctx, v, w)
         hv[:] = x
-        _set(nrm, float(np.linalg.norm(w)))
+        _set(nrm, float(nw))
         if passes is not None:
             _set(passes, 1)
         ctx.launches += 1
@@ -354,11 +437,13 @@ class HostSimLib:
 
     def b2k_vec_orthogonalize(self, h, v, q, alg, eta, s, nrm):
         ctx = self._c(h)
-        w, sv = ko.orthogonalize_vec(self._vec(ctx, v).astype(np.float64), self._vec(ctx, q).astype(np.float64),
-                                     ko.Orth(int(alg), float(eta)), eps=float(np.finfo(ctx.dtype).eps))
+        with _global_reductions(ctx, self._sh(ctx, v)):
+            w, sv = ko.orthogonalize_vec(self._vec(ctx, v).astype(np.float64), self._vec(ctx, q).astype(np.float64),
+                                         ko.Orth(int(alg), float(eta)), eps=float(np.finfo(ctx.dtype).eps))
+            nw = ko.norm(w)
         self._setvec(ctx, v, w)
         _set(s, float(sv))
-        _set(nrm, float(np.linalg.norm(w)))
+        _set(nrm, float(nw))
         return L.OK
 
     def b2k_basis_transform(self, h, cols, m, U, ldu, keep):
@@ -406,7 +491,8 @@ class HostSimLib:
         ctx = self._c(h)
         Mv = _view(M, p * q, C.c_double)
         Xs, Ys = self._cols(ctx, X, p), self._cols(ctx, Y, q)
-        Mv[:] = ko.block_inner([x.astype(np.float64) for x in Xs], [y.astype(np.float64) for y in Ys]).T.reshape(-1)
+        with _global_reductions(ctx, self._sh(ctx, list(X)[0])):
+            Mv[:] = ko.block_inner([x.astype(np.float64) for x in Xs], [y.astype(np.float64) for y in Ys]).T.reshape(-1)
         return L.OK
 
     def b2k_block_axpy(self, h, Y, q, X, p, M, ldm):
@@ -424,7 +510,8 @@ class HostSimLib:
         ctx = self._c(h)
         Vs = [v.astype(np.float64) for v in self._cols(ctx, V, k)]
         Rs = [self._vec(ctx, c).astype(np.float64) for c in list(R)[:p]]
-        ko.block_reorthogonalize(Rs, Vs)
+        with _global_reductions(ctx, self._sh(ctx, list(R)[0])):
+            ko.block_reorthogonalize(Rs, Vs)
         for c, r in zip(list(R)[:p], Rs):
             self._setvec(ctx, c, r)
         return L.OK
@@ -432,7 +519,8 @@ class HostSimLib:
     def b2k_block_qr(self, h, X, p, tol, Rh, good, drift):
         ctx = self._c(h)
         blk = [self._vec(ctx, c).astype(np.float64) for c in list(X)[:p]]
-        Rg, gidx, dr = ko.block_qr(blk, tol)
+        with _global_reductions(ctx, self._sh(ctx, list(X)[0])):
+            Rg, gidx, dr = ko.block_qr(blk, tol)
         Rfull = np.zeros((p, p))
         for row, gi in enumerate(gidx):
             Rfull[gi, :] = Rg[row, :]
