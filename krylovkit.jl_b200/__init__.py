@@ -20,6 +20,7 @@ from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, ort
 from .vectors import B200Context, B200Vec, inner, norm
 
 __all__ = [n for n in dir() if not n.startswith("_")]
+from .dense import EigSorter
 from .eigsolve import eigselector, eigsolve
 from .linsolve import linselector, linsolve
 from .schursolve import ComplexVec, realeigsolve, schursolve

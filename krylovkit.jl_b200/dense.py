@@ -116,8 +116,25 @@ def bidiagsvd_lower(alphas, betas):
     return np.linalg.svd(B)
 
 
-def eigsort(which: str):
+class EigSorter:
+    """EigSorter(by; rev = false) — src/eigsolve/eigsolve.jl:181-192: eigenvalues λ that come first (last
+    if `rev`) when sorted by `by(λ)`.  `by` maps a numpy array of eigenvalues to real keys."""
+
+    def __init__(self, by, rev: bool = False):
+        self.by, self.rev = by, bool(rev)
+
+    def permutation(self, vals):
+        keys = np.asarray(self.by(np.asarray(vals)), dtype=np.float64)
+        return np.argsort(-keys if self.rev else keys, kind="stable")      # stable like sortperm
+
+    def __repr__(self):
+        return f"EigSorter({getattr(self.by, '__name__', self.by)!r}, rev={self.rev})"
+
+
+def eigsort(which):
     """eigsort — src/eigsolve/eigsolve.jl:335-355 (real spectra)."""
+    if isinstance(which, EigSorter):
+        return which.permutation
     if which == "SR":
         return lambda d: np.argsort(d, kind="stable")
     if which == "LR":
@@ -177,6 +194,8 @@ def hschur(H: np.ndarray):
 
 def eigsort_complex(which: str):
     """eigsort for complex Ritz values — eigsolve/eigsolve.jl:335-355; stable like sortperm."""
+    if isinstance(which, EigSorter):
+        return which.permutation
     keys = {"LM": lambda v: -np.abs(v), "LR": lambda v: -v.real, "SR": lambda v: v.real,
             "LI": lambda v: -v.imag, "SI": lambda v: v.imag}
     if which not in keys:

@@ -95,6 +95,13 @@ def eigselector(A, block: bool = False, issymmetric: bool | None = None, ishermi
 
 def checkwhich(which: str, alg) -> None:
     """eigsolve.jl:210-222, 323-324: selector validity for the chosen algorithm (real arithmetic)."""
+    from .dense import EigSorter
+    if isinstance(which, EigSorter):
+        if not isinstance(alg, (Lanczos, BlockLanczos)):
+            probe = which.by(np.array([1j, -1j]))
+            if probe[0] != probe[1]:                  # eigsolve.jl:216-221
+                raise ValueError("Eigenvalue selector invalid because it does not treat `λ` and `conj(λ)` equally")
+        return
     if which not in ("LM", "LR", "SR", "LI", "SI"):
         raise ValueError(f"Unknown eigenvalue selector: which = {which}")
     if which in ("LI", "SI"):

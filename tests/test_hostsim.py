@@ -179,3 +179,31 @@ def test_matrix_only_front_ends_draw_a_random_start(sim):
     np.testing.assert_allclose(sv[:2], np.linalg.svd(D, compute_uv=False)[:2], rtol=1e-8)
     with pytest.raises(TypeError):
         kk.eigsolve(lambda x: x, None, 1, "SR")
+
+
+def test_eigsorter_selects_interior_targets(sim):
+    """EigSorter(by; rev) — eigsolve.jl:181-192: e.g. the eigenvalues closest to a shift (full-space run)."""
+    n = 24
+    rng = np.random.default_rng(8)
+    d = np.sort(rng.standard_normal(n))
+    A = sp_diags(d)
+    ctx = kk.B200Context(n, 240)           # every converged pair comes back with its residual vector
+    op = kk.B200CSR.from_scipy(ctx, A)
+    target = 0.1
+    sorter = kk.EigSorter(lambda lam: np.abs(lam - target))
+    vals, vecs, info = kk.eigsolve(op, ctx.from_host(rng.random(n)), 3, sorter,
+                                   kk.Lanczos(krylovdim=n, maxiter=1, tol=1e-10, verbosity=0))
+    want = d[np.argsort(np.abs(d - target))][:3]
+    np.testing.assert_allclose(vals[:3], want, rtol=1e-8, atol=1e-10)
+    vals, _, _ = kk.eigsolve(op, ctx.from_host(rng.random(n)), 2, kk.EigSorter(lambda lam: np.real(lam), rev=True),
+                             kk.Arnoldi(krylovdim=n, maxiter=1, tol=1e-10, verbosity=0))
+    np.testing.assert_allclose(np.real(vals[:2]), d[::-1][:2], rtol=1e-8)
+    with pytest.raises(ValueError):
+        kk.eigsolve(op, ctx.from_host(rng.random(n)), 1, kk.EigSorter(lambda lam: np.imag(lam)),
+                    kk.Arnoldi(krylovdim=n, maxiter=1, verbosity=0))
+    ctx.close()
+
+
+def sp_diags(d):
+    import scipy.sparse as sp
+    return sp.diags(d).tocsr()
