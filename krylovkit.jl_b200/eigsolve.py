@@ -18,7 +18,7 @@ from .dense import (eigsort, householder_row, lmul_householder, permuteeig, rmul
                     tridiageigh)
 from .factorizations import blocklanczos as blz
 from .factorizations import lanczos as lz
-from .operators import B200CSR, B200Operator
+from .operators import B200CSR
 from .orthonormal import OrthonormalBasis, basistransform_
 from .vectors import B200Context, B200Vec
 

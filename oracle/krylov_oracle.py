@@ -42,7 +42,7 @@ reduction order is "parity unpinned": no reference test fixes it.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import scipy.sparse as sp

@@ -11,7 +11,6 @@ pytestmark = pytest.mark.gpu
 import krylovkit_jl_b200 as kk
 from krylovkit_jl_b200 import _lib as L
 from krylovkit_jl_b200.factorizations import arnoldi as ar
-from krylovkit_jl_b200.factorizations import gkl as gk
 from krylovkit_jl_b200.factorizations import lanczos as lz
 from oracle import krylov_oracle as ko
 

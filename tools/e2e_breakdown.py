@@ -1,5 +1,4 @@
 """Wall-clock breakdown of the host-buffer eigsolve path (context create / uploads / solve / downloads)."""
-import ctypes as C
 import os
 import sys
 import time
