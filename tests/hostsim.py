@@ -6,8 +6,9 @@ It is never importable from the package, ships nothing, and measures nothing: th
 loads the CUDA library or raises.  `install()` swaps the object `_lib.load()` returns for the
 duration of a test; semantics follow include/b200krylov.h entry by entry, the arithmetic is the
 oracle's (tests may use the oracle).  The fused entry points (b2k_lanczos_expand[_many],
-b2k_cg_step, b2k_bicgstab_half/_full) are deliberately absent: under the simulator the drivers run their literal
-VectorInterface paths.
+b2k_cg_step, b2k_bicgstab_half/_full) are simulated as well; `installed(fused=False)` switches the
+drivers to their literal VectorInterface paths, `installed(fused=True)` exercises the fused branches'
+host-side bookkeeping (handle accounting of expand_many, the two-call BiCGStab flow).
 """
 from __future__ import annotations
 
@@ -482,6 +483,113 @@ class HostSimLib:
             self._setvec(ctx, c, self._vec(ctx, c) - (beta * vv[i]) * w)
         return L.OK
 
+    # ---- fused steps: same arithmetic as the literal sequences, one call -------------------------------
+    class _OpView:
+        """The operator as the oracle's `apply` sees it: local rows times the gathered vector."""
+
+        def __init__(self, ctx, A):
+            self.ctx, self.A = ctx, A
+
+        def __matmul__(self, x):
+            return self.A @ self.ctx.gather_rows(x)
+
+    def b2k_lanczos_expand(self, h, op, cols, k, r, w, beta_old, alg, eta, alpha_out, beta_out):
+        ctx = self._c(h)
+        cl = list(cols)[:k + 1]
+        if int(cl[k]) != int(r):
+            return self._fail(ctx, L.EINVAL, "lanczos_expand: cols[k] must be r")
+        if beta_old == 0.0:
+            return self._fail(ctx, L.EINVAL, "lanczos_expand: beta_old == 0")
+        self._setvec(ctx, r, self._vec(ctx, r) * (1.0 / beta_old))      # lanczos.jl:257
+        V = [self._vec(ctx, c).astype(np.float64) for c in cl]
+        with _global_reductions(ctx, self._sh(ctx, r)):
+            wn, alpha, beta = ko.lanczos_recurrence(self._OpView(ctx, self.ops[_key(op)]), V, float(beta_old),
+                                                    ko.Orth(int(alg), float(eta)))
+        self._setvec(ctx, w, wn)
+        _set(alpha_out, float(alpha))
+        _set(beta_out, float(beta))
+        ctx.launches += 3
+        return L.OK
+
+    def b2k_lanczos_expand_many(self, h, op, cols, k, nsteps, beta_old, tol, alg, eta, alphas, betas, done, r_out):
+        ctx = self._c(h)
+        r = int(cols[k])
+        _set(done, 0)
+        _set(r_out, r)
+        beta = float(beta_old)
+        for i in range(nsteps):
+            wref = C.c_int32()
+            st = self.b2k_vec_alloc(h, r >> 20, wref)
+            if st != L.OK:
+                return st
+            a, b = C.c_double(), C.c_double()
+            st = self.b2k_lanczos_expand(h, op, cols, k, r, wref.value, beta, alg, eta, a, b)
+            if st != L.OK:
+                self.b2k_vec_free(h, wref.value)
+                return st
+            alphas[i], betas[i] = a.value, b.value
+            k += 1
+            cols[k] = wref.value
+            r, beta = wref.value, b.value
+            _set(done, i + 1)
+            _set(r_out, r)
+            if beta <= tol:
+                break
+        return L.OK
+
+    def _shifted(self, ctx, op, x, a0, a1):
+        y = self.ops[_key(op)] @ ctx.gather_rows(x)
+        return a1 * y + a0 * x if (a0 != 0 or a1 != 1) else y
+
+    def b2k_cg_step(self, h, op, x, r, p, q, a0, a1, beta, rho, pq_out, normr_out):
+        ctx = self._c(h)
+        sh = self._sh(ctx, r)
+        rv = self._vec(ctx, r).astype(np.float64)
+        pv = beta * self._vec(ctx, p) + rv if beta != 0 else rv.copy()
+        qv = self._shifted(ctx, op, pv, a0, a1)
+        pq = float(ctx.allsum(np.dot(pv, qv), sh)[0])
+        alpha = rho / pq
+        self._setvec(ctx, p, pv)
+        self._setvec(ctx, q, qv)
+        self._setvec(ctx, x, self._vec(ctx, x) + alpha * pv)
+        rn = rv - alpha * qv
+        self._setvec(ctx, r, rn)
+        _set(pq_out, pq)
+        _set(normr_out, float(np.sqrt(ctx.allsum(np.dot(rn, rn), sh)[0])))
+        return L.OK
+
+    def b2k_bicgstab_half(self, h, op, rs, r, p, v, s, a0, a1, beta, omega, rho, first, sigma_out, norms_out):
+        ctx = self._c(h)
+        sh = self._sh(ctx, r)
+        rv = self._vec(ctx, r).astype(np.float64)
+        pv = rv.copy() if first else rv + beta * (self._vec(ctx, p) - omega * self._vec(ctx, v))
+        vv = self._shifted(ctx, op, pv, a0, a1)
+        sigma = float(ctx.allsum(np.dot(self._vec(ctx, rs).astype(np.float64), vv), sh)[0])
+        sv = rv - (rho / sigma) * vv
+        self._setvec(ctx, p, pv)
+        self._setvec(ctx, v, vv)
+        self._setvec(ctx, s, sv)
+        _set(sigma_out, sigma)
+        _set(norms_out, float(np.sqrt(ctx.allsum(np.dot(sv, sv), sh)[0])))
+        return L.OK
+
+    def b2k_bicgstab_full(self, h, op, x, r, rs, p, s, t, a0, a1, alpha, omega_out, normr_out, rho_out):
+        ctx = self._c(h)
+        sh = self._sh(ctx, r)
+        sv = self._vec(ctx, s).astype(np.float64)
+        tv = self._shifted(ctx, op, sv, a0, a1)
+        ts, tt = ctx.allsum([np.dot(tv, sv), np.dot(tv, tv)], sh)
+        omega = ts / tt
+        self._setvec(ctx, t, tv)
+        self._setvec(ctx, x, (self._vec(ctx, x) + alpha * self._vec(ctx, p)) + omega * sv)
+        rn = sv - omega * tv
+        self._setvec(ctx, r, rn)
+        nr, rho = ctx.allsum([np.dot(rn, rn), np.dot(self._vec(ctx, rs).astype(np.float64), rn)], sh)
+        _set(omega_out, float(omega))
+        _set(normr_out, float(np.sqrt(nr)))
+        _set(rho_out, float(rho))
+        return L.OK
+
     def b2k_host_lanczos_restart(self, *args):
         # host-only helper: the real library runs it without a GPU
         return _real_lib().b2k_host_lanczos_restart(*args)
@@ -546,7 +654,12 @@ def _real_lib():
 
 
 class installed:
-    """Context manager: route `_lib.load()` to a fresh simulator and switch the fused entry points off."""
+    """Context manager: route `_lib.load()` to a fresh simulator.  `fused=False` (default) also switches the
+    fused entry points off, so the drivers run their literal VectorInterface sequences; `fused=True` leaves
+    the product's defaults (b2k_lanczos_expand[_many], b2k_cg_step, b2k_bicgstab_half/_full)."""
+
+    def __init__(self, fused: bool = False):
+        self.fused = fused
 
     def __enter__(self):
         import importlib
@@ -554,9 +667,10 @@ class installed:
         self.ls = importlib.import_module("krylovkit_jl_b200.linsolve")
         self.saved = (L._lib, self.lz.USE_FUSED_EXPAND, self.ls.USE_FUSED_CG, self.ls.USE_FUSED_BICGSTAB)
         L._lib = HostSimLib()
-        self.lz.USE_FUSED_EXPAND = False
-        self.ls.USE_FUSED_CG = False
-        self.ls.USE_FUSED_BICGSTAB = False
+        if not self.fused:
+            self.lz.USE_FUSED_EXPAND = False
+            self.ls.USE_FUSED_CG = False
+            self.ls.USE_FUSED_BICGSTAB = False
         return L._lib
 
     def __exit__(self, *exc):

@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, fused):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "2")
@@ -37,7 +37,7 @@ def _worker(rank, world, port, out):
         return np.concatenate(parts)
 
     report = {}
-    with hostsim.installed():
+    with hostsim.installed(fused=fused):
         ctx = kk.B200Context(shard.n_local, 160, rank=rank, nranks=world, nccl_uid=bytes(128), n_global=n,
                              row_offset=shard.row_offset)
         A = ko.stencil_matrix(nx, ny)
@@ -111,10 +111,14 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_all_drivers_row_sharded_on_two_ranks(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["literal", "fused-steps"])
+def test_all_drivers_row_sharded_on_two_ranks(tmp_path, fused):
     import torch.multiprocessing as mp
     from oracle import krylov_oracle as ko
     out = str(tmp_path / "vals.npy")
-    port = 31500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 31500 + (os.getpid() % 2000) + (1 if fused else 0)
+    mp.spawn(_worker, args=(2, port, out, fused), nprocs=2, join=True)
     np.testing.assert_allclose(np.load(out), ko.laplace_eigenvalues(30, 22)[:2], rtol=1e-9)

@@ -207,3 +207,42 @@ def test_eigsorter_selects_interior_targets(sim):
 def sp_diags(d):
     import scipy.sparse as sp
     return sp.diags(d).tocsr()
+
+
+@pytest.fixture()
+def simf():
+    """The simulator with the product's fused entry points left ON."""
+    with hostsim.installed(fused=True) as lib:
+        yield lib
+
+
+def test_fused_branches_bookkeeping(simf):
+    """Host-side bookkeeping of the fused branches — handle accounting of expand_/expand_many_ (library-
+    allocated residual columns adopted by Python), the one-call CG step, the two-call BiCGStab flow with
+    its half-step exit — against the oracle, exactly as the GPU tests run them."""
+    for pair in (G.PAIRS[2], G.PAIRS[3], G.PAIRS[4], G.PAIRS[0]):
+        G.test_lanczos_steps_match_oracle(pair, True)
+    G.test_cg_matches_oracle(True)
+    G.test_bicgstab_matches_oracle_and_reference_properties(True)
+    G.test_eigsolve_unconverged_fixed_cycles_matches_oracle()
+    G.test_invariant_subspace_early_exit()
+
+
+def test_fused_eigsolve_with_restarts(simf):
+    nx, ny = 40, 25
+    A = ko.stencil_matrix(nx, ny)
+    x0 = ko.splitmix_vector(7, nx * ny)
+    ctx = kk.B200Context(nx * ny, 40)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    for orth, oorth in ((kk.cgs2, ko.Orth(ko.CGS2)), (kk.mgs2, ko.Orth(ko.MGS2))):
+        alg = kk.Lanczos(orth=orth, krylovdim=20, maxiter=60, tol=1e-10, verbosity=0)
+        live0 = len(ctx.lib.ctxs[ctx.h.value].spaces[0].cols)
+        D, V, info = kk.eigsolve(op, ctx.from_host(x0), 3, "SR", alg)
+        oD, _, oinfo = ko.eigsolve_lanczos(A, x0, 3, "SR", krylovdim=20, maxiter=60, tol=1e-10, orth=oorth)
+        assert info.numiter == oinfo["numiter"] and info.numops == oinfo["numops"] and info.numiter > 1
+        np.testing.assert_allclose(D[:3], oD[:3], rtol=1e-10)
+        n_out = len(V) + len(info.residual)
+        del V, info
+        # every column the library allocated inside expand_many was adopted and released again
+        assert len(ctx.lib.ctxs[ctx.h.value].spaces[0].cols) == live0, "leaked slab columns"
+    ctx.close()
