@@ -84,7 +84,7 @@ def _linsolve_host(A, b, x0, alg, a0, a1, atol, rtol):
     import scipy.sparse as sp
     b = np.asarray(b)
     n = b.shape[0]
-    ctx = B200Context(n, getattr(alg, "krylovdim", 0) + 12, dtype=np.float32 if b.dtype == np.float32 else np.float64)
+    ctx = B200Context(n, getattr(alg, "krylovdim", 0) + 16, dtype=np.float32 if b.dtype == np.float32 else np.float64)
     try:
         if not sp.issparse(A):
             raise TypeError("linsolve: host-side A must be a scipy sparse matrix")
