@@ -243,12 +243,12 @@ def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
             rhoold = rho
             rho = normr ** 2
             beta = rho / rhoold
-        first = False
+        was_first, first = first, False
         numops += 1
         numiter += 1
         if normr < tol:
             return x, ConvergenceInfo(1, r, normr, numiter, numops)
-        if numiter >= maxiter:
+        if not was_first and numiter >= maxiter:     # cg.jl:35-60: the first iteration never looks at maxiter
             if alg.verbosity >= WARN_LEVEL:
                 warnings.warn(f"CG linsolve stopped without converging after {numiter} iterations: "
                               f"normres = {normr}, numops = {numops}")

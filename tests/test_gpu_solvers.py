@@ -303,6 +303,11 @@ def test_cg_matches_oracle(fused):
     assert info.converged == 0 and info.numiter == 7
     np.testing.assert_allclose(x.to_host(), ox, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(info.normres, oinfo["normres"], rtol=1e-9)
+    # the first iteration never looks at maxiter (cg.jl:35-60): maxiter = 1 still does two
+    x, info = kk.linsolve(op, ctx.from_host(b), None, kk.CG(maxiter=1, tol=1e-300, verbosity=0))
+    ox, oinfo = ko.linsolve_cg(A, b, None, maxiter=1, tol=1e-300)
+    assert info.numiter == oinfo["numiter"] == 2 and info.numops == oinfo["numops"] == 3
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-10, atol=1e-12)
     ls.USE_FUSED_CG = True
     ctx.close()
 

@@ -1,0 +1,148 @@
+"""Randomised agreement of the product's host drivers (run on tests/hostsim.py, literal and fused modes
+alternating) with the oracle: same numops / numiter / converged counts and the same results on small random
+problems that hit the rare branches — invariant subspaces, eager exits, restarts with tiny Krylov dimensions,
+2×2 Schur blocks at the truncation point, rank-deficient start blocks, half-step exits, maxiter quirks.
+(A 1000-seed run of this generator is what found the CG `maxiter = 1` discrepancy fixed in round 1.)"""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import hostsim
+import krylovkit_jl_b200 as kk
+from oracle import krylov_oracle as ko
+
+ORTHS = [("cgs", ko.CGS), ("mgs", ko.MGS), ("cgs2", ko.CGS2), ("mgs2", ko.MGS2), ("cgsr", ko.CGSIR), ("mgsr", ko.MGSIR)]
+
+
+def _orth_pair(rng):
+    name, tag = ORTHS[int(rng.integers(0, 6))]
+    o = getattr(kk, name)
+    return name, o, (ko.Orth(tag, o.eta) if o.is_ir else ko.Orth(tag))
+
+
+def _sym(B):
+    return (B + B.T) / 2
+
+
+def _counts(info, oinfo, fields=("numops", "numiter", "converged")):
+    for f in fields:
+        assert getattr(info, f) == oinfo[f], (f, getattr(info, f), oinfo[f])
+
+
+def _lanczos(rng, seed, ctx, n):
+    name, o, ov = _orth_pair(rng)
+    d = np.repeat(rng.standard_normal(int(rng.integers(2, 6))), 20)[:n]      # few distinct values: invariant subspaces
+    if len(d) < n:
+        d = np.concatenate([d, rng.standard_normal(n - len(d))])
+    A = sp.diags(d).tocsr() if seed % 4 < 2 else sp.csr_matrix(_sym(rng.standard_normal((n, n))))
+    x0 = rng.random(n)
+    kd = int(rng.integers(2, min(n, 20) + 1))
+    hm = int(rng.integers(1, kd + 1))
+    which = ["SR", "LR", "LM"][int(rng.integers(0, 3))]
+    alg = kk.Lanczos(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 8)), tol=1e-9, eager=bool(rng.integers(0, 2)), verbosity=0)
+    D, _, info = kk.eigsolve(kk.B200CSR.from_scipy(ctx, A), ctx.from_host(x0), hm, which, alg)
+    oD, _, oinfo = ko.eigsolve_lanczos(A, x0, hm, which, krylovdim=kd, maxiter=alg.maxiter, tol=1e-9, orth=ov, eager=alg.eager)
+    _counts(info, oinfo)
+    if name not in ("cgs", "mgs"):            # without reorthogonalisation ghost values are rounding-chaotic
+        assert len(D) == len(oD)
+        np.testing.assert_allclose(D, oD, rtol=1e-7, atol=1e-9)
+
+
+def _arnoldi(rng, seed, ctx, n):
+    _, o, ov = _orth_pair(rng)
+    A = sp.csr_matrix(rng.random((n, n)) - 0.5)
+    x0 = rng.random(n)
+    kd = int(rng.integers(3, min(n, 16) + 1))
+    hm = int(rng.integers(1, min(kd, 4) + 1))
+    which = ["SR", "LR", "LM"][int(rng.integers(0, 3))]
+    alg = kk.Arnoldi(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 6)), tol=1e-9, eager=bool(rng.integers(0, 2)), verbosity=0)
+    D, _, info = kk.eigsolve(kk.B200CSR.from_scipy(ctx, A), ctx.from_host(x0), hm, which, alg)
+    oD, _, oinfo = ko.eigsolve_arnoldi(A, x0, hm, which, krylovdim=kd, maxiter=alg.maxiter, tol=1e-9, orth=ov, eager=alg.eager)
+    _counts(info, oinfo)
+    assert len(D) == len(oD)
+    np.testing.assert_allclose(D, oD, rtol=1e-6, atol=1e-8)
+
+
+def _gmres(rng, seed, ctx, n):
+    _, o, ov = _orth_pair(rng)
+    A = sp.csr_matrix(np.eye(n) * 3 + 0.5 * (rng.random((n, n)) - 0.5))
+    b = rng.random(n)
+    kd = int(rng.integers(2, 12))
+    alg = kk.GMRES(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 6)), tol=1e-10, verbosity=0)
+    a0, a1 = (0.0, 1.0) if seed % 3 else (0.7, 1.3)
+    x, info = kk.linsolve(kk.B200CSR.from_scipy(ctx, A), ctx.from_host(b), None, alg, a0, a1)
+    ox, oinfo = ko.linsolve_gmres(A, b, krylovdim=kd, maxiter=alg.maxiter, tol=1e-10, orth=ov, a0=a0, a1=a1)
+    _counts(info, oinfo, ("numops", "converged"))
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-7, atol=1e-9)
+
+
+def _short_recurrences(rng, seed, ctx, n):
+    A = sp.csr_matrix(np.eye(n) * 4 + 0.8 * (rng.random((n, n)) - 0.5))
+    b = rng.random(n)
+    mi = int(rng.integers(1, 30))
+    tol = 10.0 ** (-int(rng.integers(3, 12)))
+    x, info = kk.linsolve(kk.B200CSR.from_scipy(ctx, A), ctx.from_host(b), None, kk.BiCGStab(maxiter=mi, tol=tol, verbosity=0))
+    ox, oinfo = ko.linsolve_bicgstab(A, b, maxiter=mi, tol=tol)
+    _counts(info, oinfo)
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-6, atol=1e-9)
+    S = sp.csr_matrix(A @ A.T)
+    x, info = kk.linsolve(kk.B200CSR.from_scipy(ctx, S), ctx.from_host(b), None, kk.CG(maxiter=mi, tol=tol, verbosity=0))
+    ox, oinfo = ko.linsolve_cg(S, b, maxiter=mi, tol=tol)
+    _counts(info, oinfo)
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-6, atol=1e-9)
+
+
+def _blocklanczos(rng, seed, ctx, n):
+    A = sp.csr_matrix(_sym(rng.standard_normal((n, n))))
+    p = int(rng.integers(1, 4))
+    X0 = [rng.random(n) for _ in range(p)]
+    if p > 1 and seed % 8 == 4:
+        X0[1] = 2 * X0[0]                     # linearly dependent start block: block_qr! drops a column
+    kd = int(rng.integers(p + 1, min(n, 18) + 1))
+    hm = int(rng.integers(1, kd + 1))
+    alg = kk.BlockLanczos(krylovdim=kd, maxiter=int(rng.integers(1, 5)), tol=1e-9, qr_tol=1e-10,
+                          eager=bool(rng.integers(0, 2)), verbosity=0)
+    D, _, info = kk.eigsolve(kk.B200CSR.from_scipy(ctx, A), kk.Block([ctx.from_host(x) for x in X0]), hm, "SR", alg)
+    oD, _, oinfo = ko.eigsolve_blocklanczos(A, [x.copy() for x in X0], hm, "SR", krylovdim=kd, maxiter=alg.maxiter,
+                                            tol=1e-9, qr_tol=1e-10, eager=alg.eager)
+    _counts(info, oinfo)
+    assert len(D) == len(oD)
+    np.testing.assert_allclose(D, oD, rtol=1e-6, atol=1e-8)
+
+
+def _lsmr_and_expintegrator(rng, seed, ctx, n):
+    _, o, ov = _orth_pair(rng)
+    m = n + int(rng.integers(0, 20))
+    A = rng.standard_normal((m, n))
+    b = rng.random(m)
+    K, mi = int(rng.integers(1, 8)), int(rng.integers(1, 25))
+    lam = float(rng.random() * (seed % 2))
+    x, info = kk.lssolve(A, b, kk.LSMR(orth=o, maxiter=mi, krylovdim=K, tol=1e-10, verbosity=0), lam)
+    ox, oinfo = ko.lssolve_lsmr(A, b, maxiter=mi, krylovdim=K, tol=1e-10, orth=ov, lam=lam)
+    _counts(info, oinfo, ("numiter", "converged"))
+    np.testing.assert_allclose(x, ox, rtol=1e-6, atol=1e-9)
+    S = sp.csr_matrix(_sym(rng.standard_normal((n, n))) / 2)
+    t = float(rng.standard_normal())
+    u = tuple(rng.random(n) for _ in range(int(rng.integers(0, 4)) + 1))
+    kd, eager = 3 + seed % 9, bool(seed % 2)
+    w, info = kk.expintegrator(kk.B200CSR.from_scipy(ctx, S), t, tuple(ctx.from_host(z) for z in u),
+                               kk.Lanczos(orth=kk.mgs2, krylovdim=kd, maxiter=50, tol=1e-10, eager=eager, verbosity=0))
+    ow, oinfo = ko.expintegrator(S, t, u, "lanczos", ko.Orth(ko.MGS2), krylovdim=kd, maxiter=50, tol=1e-10, eager=eager)
+    _counts(info, oinfo)
+    np.testing.assert_allclose(w.to_host(), ow, rtol=1e-7, atol=1e-10)
+
+
+KINDS = [_lanczos, _arnoldi, _gmres, _short_recurrences, _blocklanczos, _lsmr_and_expintegrator]
+
+
+@pytest.mark.parametrize("seed", range(96))
+def test_driver_agrees_with_oracle(seed):
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(seed)
+    with hostsim.installed(fused=bool(seed % 2)):
+        n = int(rng.integers(6, 60))
+        ctx = kk.B200Context(n, 600)
+        KINDS[seed % 6](rng, seed, ctx, n)
+        ctx.close()
