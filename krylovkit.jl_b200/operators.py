@@ -29,6 +29,7 @@ class B200Operator:
         self.n_rows, self.n_cols, self.nnz = nr.value, nc.value, nnz.value
         self.space_in = 0     # space of x in y = A x
         self.space_out = 0
+        self._explicit_spaces = False
 
     def free(self):
         self._fin()
@@ -36,6 +37,7 @@ class B200Operator:
     def with_spaces(self, space_in: int, space_out: int):
         """Rectangular operators: name the vector spaces of x and y in y = A x."""
         self.space_in, self.space_out = space_in, space_out
+        self._explicit_spaces = True
         return self
 
     # y = A x into an existing vector (y must not alias x)
@@ -158,7 +160,10 @@ def apply(op, x: B200Vec, a0: float = 0.0, a1: float = 1.0) -> B200Vec:
     """apply(operator, x[, α₀, α₁]) — src/apply.jl:1-11.  `op` is a B200Operator or any
     callable x -> y on B200Vec (the abstract-linear-map contract)."""
     if isinstance(op, B200Operator):
-        y = x.ctx.empty(op.space_out if (isinstance(op, B200Dense) or op.n_rows != op.n_cols) else x.space)
+        # the result lives in the operator's output space when it has one of its own (dense operators, CSR
+        # operators given spaces explicitly — also square ones, e.g. the (A, Aᵀ) pair of lssolve), else next to x
+        own_space = isinstance(op, B200Dense) or op._explicit_spaces or op.n_rows != op.n_cols
+        y = x.ctx.empty(op.space_out if own_space else x.space)
         if a0 != 0.0 or a1 != 1.0:
             x.ctx.check(x.ctx.lib.b2k_op_apply_shifted(x.ctx.h, op.h, x.handle, y.handle,
                                                        float(a0), float(a1)))

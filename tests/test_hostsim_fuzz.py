@@ -117,7 +117,7 @@ def _lsmr_and_expintegrator(rng, seed, ctx, n):
     m = n + int(rng.integers(0, 20))
     A = rng.standard_normal((m, n))
     b = rng.random(m)
-    K, mi = int(rng.integers(1, 8)), int(rng.integers(1, 25))
+    K, mi = int(rng.integers(1, 8)), int(rng.integers(1, 9))   # few iterations: see _lsmr_sparse_pair
     lam = float(rng.random() * (seed % 2))
     x, info = kk.lssolve(A, b, kk.LSMR(orth=o, maxiter=mi, krylovdim=K, tol=1e-10, verbosity=0), lam)
     ox, oinfo = ko.lssolve_lsmr(A, b, maxiter=mi, krylovdim=K, tol=1e-10, orth=ov, lam=lam)
@@ -134,15 +134,95 @@ def _lsmr_and_expintegrator(rng, seed, ctx, n):
     np.testing.assert_allclose(w.to_host(), ow, rtol=1e-7, atol=1e-10)
 
 
-KINDS = [_lanczos, _arnoldi, _gmres, _short_recurrences, _blocklanczos, _lsmr_and_expintegrator]
+def _svdsolve(rng, seed, ctx, n):
+    name, o, ov = _orth_pair(rng)
+    m = n + int(rng.integers(0, 12))
+    A = rng.standard_normal((m, n))
+    u0 = rng.random(m)
+    kd = int(rng.integers(2, min(n, 12) + 1))
+    hm = int(rng.integers(1, kd + 1))
+    which = ["LR", "SR"][int(rng.integers(0, 2))]
+    alg = kk.GKL(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 6)), tol=1e-9, eager=bool(rng.integers(0, 2)), verbosity=0)
+    S, _, _, info = kk.svdsolve(A, u0, hm, which, alg)                 # host entry: dense operator, two spaces
+    oS, _, _, oinfo = ko.svdsolve_gkl(A, u0, hm, which, krylovdim=kd, maxiter=alg.maxiter, tol=1e-9, orth=ov, eager=alg.eager)
+    _counts(info, oinfo)
+    if name not in ("cgs", "mgs"):
+        assert len(S) == len(oS)
+        np.testing.assert_allclose(S, oS, rtol=1e-6, atol=1e-8)
 
 
-@pytest.mark.parametrize("seed", range(96))
+def _schur_and_realeig(rng, seed, ctx, n):
+    name, o, ov = _orth_pair(rng)
+    A = rng.random((n, n)) - 0.5
+    x0 = rng.random(n)
+    kd = int(rng.integers(3, min(n, 14) + 1))
+    hm = int(rng.integers(1, min(kd, 4) + 1))
+    which = ["SR", "LR", "LM"][int(rng.integers(0, 3))]
+    alg = kk.Arnoldi(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 6)), tol=1e-9, eager=bool(rng.integers(0, 2)), verbosity=0)
+    kw = dict(krylovdim=kd, maxiter=alg.maxiter, tol=1e-9, orth=ov, eager=alg.eager)
+    T, Q, vals, info = kk.schursolve(kk.B200CSR.from_scipy(ctx, sp.csr_matrix(A)), ctx.from_host(x0), hm, which, alg)
+    oT, _, ovals, oinfo = ko.schursolve_arnoldi(A, x0, hm, which, **kw)
+    _counts(info, oinfo, ("numops", "converged"))
+    assert T.shape == oT.shape
+    np.testing.assert_allclose(vals, ovals, rtol=1e-6, atol=1e-8)
+    Qh = np.column_stack([q.to_host() for q in Q])
+    R = np.column_stack([r.to_host() for r in info.residual])
+    np.testing.assert_allclose(A @ Qh, Qh @ T + R, atol=1e-8)          # partial Schur relation with residuals
+    del Q, info
+    As = _sym(A) + np.diag(np.arange(n)) * 0.1                         # real spectrum
+    D, _, info = kk.realeigsolve(kk.B200CSR.from_scipy(ctx, sp.csr_matrix(As)), ctx.from_host(x0), hm, which, alg)
+    oD, _, oinfo = ko.realeigsolve_arnoldi(As, x0, hm, which, **kw)
+    _counts(info, oinfo, ("numops", "converged"))
+    assert len(D) == len(oD)
+    if name not in ("cgs", "mgs"):
+        np.testing.assert_allclose(D, oD, rtol=1e-6, atol=1e-8)
+
+
+def _gmres_warm_start(rng, seed, ctx, n):
+    import importlib
+    ls = importlib.import_module("krylovkit_jl_b200.linsolve")
+    _, o, ov = _orth_pair(rng)
+    A = sp.csr_matrix(np.eye(n) * 3 + 0.5 * (rng.random((n, n)) - 0.5))
+    b, xs = rng.random(n), rng.random(n)
+    kd = int(rng.integers(2, 10))
+    alg = kk.GMRES(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 5)), tol=1e-10, verbosity=0)
+    ls.LITERAL_GIVENS_RESTART = seed % 4 == 2          # gmres.jl:112-117 done literally (k two-column sweeps)
+    try:
+        x, info = kk.linsolve(kk.B200CSR.from_scipy(ctx, A), ctx.from_host(b), ctx.from_host(xs), alg)
+    finally:
+        ls.LITERAL_GIVENS_RESTART = False
+    ox, oinfo = ko.linsolve_gmres(A, b, xs, krylovdim=kd, maxiter=alg.maxiter, tol=1e-10, orth=ov)
+    _counts(info, oinfo, ("numops", "converged"))
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(info.residual.to_host(), b - A @ x.to_host(), atol=1e-7)
+
+
+def _lsmr_sparse_pair(rng, seed, ctx, n):
+    """Host entry with a sparse matrix: the (A, Aᵀ) CSR pair in two vector spaces — also when A is square
+    (the output space must come from the operator, not from x).  Few iterations: without a long
+    reorthogonalisation window LSMR amplifies rounding differences exponentially (SciPy's does, too)."""
+    _, o, ov = _orth_pair(rng)
+    m = n if seed % 3 == 0 else n + int(rng.integers(1, 15))
+    A = (sp.random(m, n, density=0.3, random_state=seed) + sp.eye(m, n)).tocsr()
+    b = rng.random(m)
+    K, mi = int(rng.integers(1, 6)), int(rng.integers(1, 7))
+    x, info = kk.lssolve(A, b, kk.LSMR(orth=o, maxiter=mi, krylovdim=K, tol=1e-10, verbosity=0))
+    ox, oinfo = ko.lssolve_lsmr(A.toarray(), b, maxiter=mi, krylovdim=K, tol=1e-10, orth=ov)
+    _counts(info, oinfo, ("numiter", "converged"))
+    np.testing.assert_allclose(x, ox, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(info.residual, b - A @ x, atol=1e-8)
+
+
+KINDS = [_lanczos, _arnoldi, _gmres, _short_recurrences, _blocklanczos, _lsmr_and_expintegrator,
+         _svdsolve, _schur_and_realeig, _gmres_warm_start, _lsmr_sparse_pair]
+
+
+@pytest.mark.parametrize("seed", range(160))
 def test_driver_agrees_with_oracle(seed):
     warnings.simplefilter("ignore")
     rng = np.random.default_rng(seed)
     with hostsim.installed(fused=bool(seed % 2)):
         n = int(rng.integers(6, 60))
         ctx = kk.B200Context(n, 600)
-        KINDS[seed % 6](rng, seed, ctx, n)
+        KINDS[seed % len(KINDS)](rng, seed, ctx, n)
         ctx.close()
