@@ -32,9 +32,11 @@ def svdsolve(A, u0=None, howmany: int = 1, which: str = "LR", alg: GKL | None = 
     A = np.asarray(A)
     u0 = np.asarray(u0)
     m, n = A.shape
-    ctx = B200Context(m, alg.krylovdim + 2 * howmany + 8, dtype=A.dtype if A.dtype == np.float32 else np.float64)
+    # every converged triple comes back (up to krylovdim of them): U, the left vectors and their residuals
+    # live in space 0, V and the right vectors in the short space
+    ctx = B200Context(m, 3 * alg.krylovdim + 12, dtype=A.dtype if A.dtype == np.float32 else np.float64)
     try:
-        sv = ctx.add_space(n, alg.krylovdim + howmany + 8, sharded=False)
+        sv = ctx.add_space(n, 2 * alg.krylovdim + 10, sharded=False)
         op = B200Dense.from_host(ctx, A, sv)
         S, Uv, Vv, info = _svdsolve_gkl(op, ctx.from_host(u0), howmany, which, alg)
         info.residual = [r.to_host() for r in info.residual]

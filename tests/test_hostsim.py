@@ -169,13 +169,17 @@ def test_realeigsolve(sim):
     G.test_realeigsolve()
 
 
-def test_matrix_only_front_ends_draw_a_random_start(sim):
+@pytest.mark.parametrize("seed", [0, 40, 114, 149])        # 40 / 114 / 149: all 20 triplets converge at once
+def test_matrix_only_front_ends_draw_a_random_start(sim, seed, monkeypatch):
     """eigsolve(A, howmany, which; …) / svdsolve(A, howmany, which; …) — eigsolve.jl:195-201, svdsolve.jl:123-129."""
+    rng0 = np.random.default_rng
+    monkeypatch.setattr(np.random, "default_rng", lambda *a: rng0(seed))      # deterministic "random" start
     S = ko.stencil_matrix(12, 9)
     vals, vecs, info = kk.eigsolve(S, None, 2, "SR", krylovdim=40, tol=1e-9)
     np.testing.assert_allclose(vals[:2], ko.laplace_eigenvalues(12, 9)[:2], rtol=1e-8)
-    D = np.random.default_rng(2).standard_normal((50, 20))
+    D = rng0(2).standard_normal((50, 20))
     sv, U, V, info = kk.svdsolve(D, None, 2, "LR", krylovdim=20, tol=1e-10)
+    assert len(U) == len(V) == max(2, info.converged)
     np.testing.assert_allclose(sv[:2], np.linalg.svd(D, compute_uv=False)[:2], rtol=1e-8)
     with pytest.raises(TypeError):
         kk.eigsolve(lambda x: x, None, 1, "SR")
