@@ -17,7 +17,7 @@ from .algorithms import (Arnoldi, BiCGStab, BlockLanczos, CG, ClassicalGramSchmi
 from .operators import B200CSR, B200Dense, B200Operator, apply, apply_adjoint, apply_normal
 from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, orthonormalize_,
                           project_, rank1update_, rmul_givens_, rmul_householder_, unproject_)
-from .vectors import B200Context, B200Vec, inner, norm
+from .vectors import B200Context, B200Vec, cache_release, inner, norm
 
 __all__ = [n for n in dir() if not n.startswith("_")]
 from .dense import EigSorter

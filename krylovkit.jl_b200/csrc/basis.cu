@@ -689,8 +689,10 @@ void mgs_pin_vector(b2k_ctx* ctx, const VecRef& v, bool on) {
     attr.accessPolicyWindow.hitRatio = 1.0f;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    // turning the window off is enough: lines left in the persisting carve-out are replaced by the next
+    // pinned vector.  (cudaCtxResetPersistingL2Cache() would be a process-wide side effect inside a
+    // library call.)
     cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-    if (!on) cudaCtxResetPersistingL2Cache();
 }
 
 int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res_off, int acc_off) {

@@ -28,7 +28,7 @@ static size_t big_cap_bytes() {
     static size_t cap = 0;
     if (!cap) {
         const char* e = getenv("B2K_CACHE_GB");
-        cap = (size_t)(e ? atof(e) : 48.0) << 30;
+        cap = (size_t)((e ? atof(e) : 16.0) * (double)((size_t)1 << 30));
     }
     return cap;
 }

@@ -944,9 +944,11 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
                             (long long)op->n_rows);
         return b2k_panel_unproject_dev(ctx, op->A, op->ld, op->n_rows, (int32_t)op->n_cols, y, x.ptr);
     }
-    if (x.n != op->n_loc_cols && !(ctx->nranks == 1 && x.n == op->n_cols))
+    // one GPU: x must span all columns (a rectangular operator takes x from the matching space);
+    // row-sharded: x is the local slice and the halo plan supplies the rest
+    if (ctx->nranks == 1 ? x.n != op->n_cols : x.n != op->n_loc_cols)
         return b2k_fail(ctx, B2K_EDIM, "apply: x has %lld entries, operator wants %lld",
-                        (long long)x.n, (long long)op->n_cols);
+                        (long long)x.n, (long long)(ctx->nranks == 1 ? op->n_cols : op->n_loc_cols));
     if (y.n != op->n_rows)
         return b2k_fail(ctx, B2K_EDIM, "apply: y has %lld entries, operator has %lld rows",
                         (long long)y.n, (long long)op->n_rows);

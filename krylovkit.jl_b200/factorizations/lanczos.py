@@ -220,8 +220,11 @@ def expand_many_(it: LanczosIterator, state: LanczosFactorization, nsteps: int, 
     al = (C.c_double * nsteps)()
     be = (C.c_double * nsteps)()
     done, rout = C.c_int32(), L.c_vec()
-    ctx.check(ctx.lib.b2k_lanczos_expand_many(ctx.h, it.operator.h, cols, k, nsteps, state.normres(), tol,
-                                              it.orth.tag, it.orth.eta, al, be, C.byref(done), C.byref(rout)))
+    status = ctx.lib.b2k_lanczos_expand_many(ctx.h, it.operator.h, cols, k, nsteps, state.normres(), tol,
+                                             it.orth.tag, it.orth.eta, al, be, C.byref(done), C.byref(rout))
+    # commit the completed steps BEFORE raising: the library has already turned the residual into a basis
+    # vector and allocated columns for them, so the factorization must stay consistent for a caller that
+    # catches the error (e.g. a slab that ran out of columns at step i > 0)
     d = done.value
     if d > 0:
         V.push(r)                                   # the old residual became basis vector k+1
@@ -231,6 +234,7 @@ def expand_many_(it: LanczosIterator, state: LanczosFactorization, nsteps: int, 
         state.alphas.extend(al[:d])
         state.betas.extend(be[:d])
         state.k += d
+    ctx.check(status)
     return d
 
 

@@ -127,7 +127,6 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
         y[1] = 0.0
         y[0], y[1] = c * y[0] + s * y[1], -s * y[0] + c * y[1]
         beta = abs(y[1])
-        singular = False
         while R[k - 1, k - 1] != 0 and beta > tol and len(fact) < krylovdim:
             fact = ar.expand_(it, fact)
             numops += 1
@@ -143,11 +142,12 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
                 if alg.verbosity >= WARN_LEVEL:
                     warnings.warn(f"GMRES linsolve in iteration {numiter}; step {k}: linear operator is "
                                   "singular in Krylov subspace")
-                # rotate all the weight into y[k+1] — gmres.jl:84-86
-                y[k] = math.hypot(0.0, y[k - 1])
+                # rotate all the weight into y[k+1] — gmres.jl:84-86: gs[k] = Givens(k+1, k, c, s)
+                c, s, rr = givens(0.0, y[k - 1])
+                gs[k - 1] = ("swap", c, s)
+                y[k] = rr
                 y[k - 1] = 0.0
                 R[k - 1, k - 1] = 0.0
-                singular = True
             else:
                 c, s, rr = givens(R[k - 1, k - 1], a1 * fact.normres())
                 gs[k - 1] = (c, s)
@@ -162,11 +162,14 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
         V = fact.basis()
         # x = add!!(x, V[i], y[i]) for i in 1:k — gmres.jl:105-108: one fused lincomb sweep
         x = unproject_(x, V, y[:k], 1.0, 1.0, range(k))
-        if beta > tol and numiter < maxiter and not singular:
+        if beta > tol and numiter < maxiter:
             w = fact.residual()
             V.push(w.scale_(1 / fact.normres()))
             if LITERAL_GIVENS_RESTART:
                 for i in range(k):
+                    if gs[i][0] == "swap":                    # singular branch: Givens(k+1, k, c, s)
+                        rmul_givens_(V, i + 1, i, gs[i][1], -gs[i][2])
+                        continue
                     c, s = gs[i]
                     rmul_givens_(V, i, i + 1, c, -s)          # rmul!(V, gs[i]')
                 r = r.scale_(y[k], V[k])
@@ -175,6 +178,11 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
                 coef = np.zeros(k + 1)
                 coef[k] = 1.0
                 for i in range(k - 1, -1, -1):
+                    if gs[i][0] == "swap":                    # rotation acting on (i1, i2) = (i+1, i)
+                        _, c, s = gs[i]
+                        ci1, ci = coef[i + 1], coef[i]
+                        coef[i + 1], coef[i] = c * ci1 - s * ci, s * ci1 + c * ci
+                        continue
                     c, s = gs[i]
                     ci, ci1 = coef[i], coef[i + 1]
                     coef[i], coef[i + 1] = c * ci - s * ci1, s * ci + c * ci1

@@ -2,10 +2,12 @@
 src/eigsolve/svdsolve.jl:144-314."""
 from __future__ import annotations
 
+import math
 import warnings
 
 import numpy as np
 
+from ._lib import B200Error
 from .algorithms import ConvergenceInfo, GKL, WARN_LEVEL
 from .dense import (bidiagsvd_lower, householder_col, householder_row, lmul_householder,
                     rmul_householder)
@@ -45,6 +47,27 @@ def svdsolve(A, u0=None, howmany: int = 1, which: str = "LR", alg: GKL | None = 
         ctx.close()
 
 
+def _diverged(fact, alg, what: str) -> B200Error:
+    return B200Error(
+        f"GKL bidiagonalisation diverged at step {len(fact)} ({what}; alpha = {fact.alphas[-1]:.3g}, "
+        f"beta = {fact.betas[-1]:.3g}): orthogonality of the Krylov bases was lost with orth = {alg.orth}. "
+        "With ClassicalGramSchmidt2 the recurrence reorthogonalises the long side only (gkl.jl:308-323), which is "
+        "not enough in Float32 on clustered singular values; use an iterative-refinement orthogonalizer "
+        "(ClassicalGramSchmidtIR / ModifiedGramSchmidtIR, as the reference's own Float32 tests do, "
+        "test/runtests.jl:18) or ModifiedGramSchmidt2.")
+
+
+def _check_finite(fact, alg) -> None:
+    """The reference would carry Inf/NaN coefficients into LAPACK (bdsqr) and fail there; fail here, early
+    and with the cause, as soon as a coefficient stops being finite or exceeds any possible ||A||."""
+    a, b = fact.alphas[-1], fact.betas[-1]
+    big = 1.0 / np.finfo(np.float32).eps * max(1.0, abs(fact.alphas[0]))      # >> sigma_max ~ alpha_1
+    if not (math.isfinite(a) and math.isfinite(b)):
+        raise _diverged(fact, alg, "non-finite coefficient")
+    if abs(a) > big or abs(b) > big:
+        raise _diverged(fact, alg, "coefficient far above any singular value of A")
+
+
 def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
     krylovdim, maxiter = alg.krylovdim, alg.maxiter
     if howmany > krylovdim:
@@ -63,7 +86,10 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
         if beta <= tol and K < howmany and alg.verbosity >= WARN_LEVEL:
             warnings.warn(f"Invariant subspace of dimension {K} (up to requested tolerance `tol = {tol}`)")
         if K == krylovdim or beta <= tol or (alg.eager and K >= howmany):
-            P, S, Q = bidiagsvd_lower(fact.alphas[:K], fact.betas[:K - 1])
+            try:
+                P, S, Q = bidiagsvd_lower(fact.alphas[:K], fact.betas[:K - 1])
+            except np.linalg.LinAlgError as e:       # LAPACK gives up on a bidiagonal that has blown up
+                raise _diverged(fact, alg, f"SVD of the {K}x{K} bidiagonal failed: {e}") from e
             if which == "SR":
                 P, S, Q = P[:, ::-1].copy(), S[::-1].copy(), Q[::-1, :].copy()
             f = Q.T[K - 1, :] * beta
@@ -75,6 +101,7 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
         if K < krylovdim:
             fact = gkl.expand_(it, fact)
             numops += 2
+            _check_finite(fact, alg)
         else:
             if numiter == maxiter:
                 break

@@ -220,6 +220,13 @@ def _destroy_ctx(lib, ctx_h, alive):
         lib.b2k_ctx_destroy(ctx_h)
 
 
+def cache_release() -> None:
+    """Give the library's cached device / pinned blocks back to the driver (b2k_cache_release).  Freed slabs
+    and CSR arrays (>= 32 MB) are kept for reuse by the next context of the same shape, up to B2K_CACHE_GB
+    (default 16 GB); call this when other CUDA libraries in the process need the memory."""
+    L.check(L.load().b2k_cache_release())
+
+
 # free functions in VectorInterface style -------------------------------------------------
 def inner(v: B200Vec, w: B200Vec) -> float:
     return v.inner(w)

@@ -1013,8 +1013,9 @@ def linsolve_gmres(A, b, x0=None, krylovdim=30, maxiter=100, tol=1e-12, orth: Or
             V = list(f.V) + [f.r * (1 / f.normres())]
             for i in range(k):
                 g = gs[i]
-                if g[0] == "swap":
-                    raise NotImplementedError("singular branch restart")
+                if g[0] == "swap":                         # Givens(k+1, k, c, s) of the singular branch, gmres.jl:84
+                    givens_rmul_basis(V, i + 1, i, g[1], -g[2])
+                    continue
                 c, s = g
                 givens_rmul_basis(V, i, i + 1, c, -s)      # rmul!(V, gs[i]')
             r = V[k] * y[k]

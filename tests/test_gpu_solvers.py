@@ -197,6 +197,38 @@ def test_gmres_matches_oracle(pair, literal):
     ctx.close()
 
 
+@pytest.mark.parametrize("literal", [False, True])
+def test_gmres_singular_in_krylov_subspace_branch(literal):
+    """gmres.jl:79-86: when hypot(R[k,k], α₁·normres) < tol the weight is rotated into y[k+1] with
+    Givens(k+1, k, ...) and the cheap restart (:110-117) still runs.  Same numops / x / residual as the oracle."""
+    import scipy.sparse as sp
+    from krylovkit_jl_b200 import linsolve as ls
+    n = 40
+    A = sp.lil_matrix((n, n))
+    A[1, 0] = 1.0
+    A[2, 1] = 1e-6                      # A e2 = 1e-6 e3: R[2,2] = 0 and normres = 1e-6 < tol at step 2
+    for i in range(3, n):
+        A[i, i] = 1.0 + 0.01 * i
+    A = A.tocsr()
+    b = np.zeros(n)
+    b[0] = 1.0
+    ls.LITERAL_GIVENS_RESTART = literal
+    try:
+        ctx = kk.B200Context(n, 24)
+        op = kk.B200CSR.from_scipy(ctx, A)
+        alg = kk.GMRES(orth=kk.mgs2, krylovdim=6, maxiter=3, tol=1e-3, verbosity=0)
+        x, info = kk.linsolve(op, ctx.from_host(b), None, alg)
+        ox, oinfo = ko.linsolve_gmres(A, b, None, krylovdim=6, maxiter=3, tol=1e-3, orth=ko.Orth(ko.MGS2))
+    finally:
+        ls.LITERAL_GIVENS_RESTART = False
+    assert info.numiter == oinfo["numiter"] and info.numops == oinfo["numops"]
+    assert info.converged == oinfo["converged"]
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(info.residual.to_host(), oinfo["residual"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(info.normres, oinfo["normres"], rtol=1e-9, atol=1e-14)
+    ctx.close()
+
+
 @pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3], PAIRS[4]], ids=["cgs2", "mgs2", "cgsr"])
 def test_svdsolve_matches_oracle_f64(pair):
     orth, oorth = pair

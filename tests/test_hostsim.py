@@ -105,6 +105,11 @@ def test_gmres(sim, pair, literal):
     G.test_gmres_matches_oracle(pair, literal)
 
 
+@pytest.mark.parametrize("literal", [False, True])
+def test_gmres_singular_branch(sim, literal):
+    G.test_gmres_singular_in_krylov_subspace_branch(literal)
+
+
 @pytest.mark.parametrize("pair", [G.PAIRS[2], G.PAIRS[3], G.PAIRS[4]], ids=["cgs2", "mgs2", "cgsr"])
 def test_svdsolve(sim, pair):
     G.test_svdsolve_matches_oracle_f64(pair)
