@@ -236,7 +236,16 @@ int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, 
  * while K < krylovdim and beta > tol — without returning to the caller in between.  `cols` has
  * capacity k + nsteps + 1: on entry the k basis handles followed by the residual handle; new
  * residual columns are allocated from the slab.  On return cols[0 .. k + *steps_done) is the basis,
- * *r_out the residual; alphas_out/betas_out hold one entry per step.  Stops early once beta <= tol. */
+ * *r_out the residual; alphas_out/betas_out hold one entry per step.  Stops early once beta <= tol.
+ *
+ * HANDLES: the d = *steps_done new basis vectors are cols[k .. k + d).  cols[k] may or may not be the residual
+ * handle that was passed in: with ClassicalGramSchmidt2 on a square CSR operator the steps are chained on the
+ * device (SpMV with the normalisation r/beta fused into its gather + ONE cooperative Gram-Schmidt launch per
+ * step, scalars kept in device records, a single host synchronisation per call) and the normalised vector is
+ * written to a column of its own; the library then RELEASES the residual handle passed in (the caller must
+ * not free it again).  If cols[k] still equals it on return the caller keeps owning it.  Steps enqueued
+ * behind a beta <= tol are skipped on the device, so the returned factorization is the one of the
+ * step-by-step loop bit for bit.  A non-zero status can come with *steps_done > 0: those steps are valid. */
 int32_t b2k_lanczos_expand_many(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k,
                                 int32_t nsteps, double beta_old, double tol, int32_t alg, double eta,
                                 double* alphas_out, double* betas_out, int32_t* steps_done,

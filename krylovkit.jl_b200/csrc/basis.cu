@@ -42,12 +42,19 @@ struct FusedParams {
     int32_t nph;
     unsigned* barrier;
     unsigned barrier_base;   // counter value before this launch
+    const int* stop;         // device flag: when set, the launch does nothing (see FinalizeParams)
+    FinalizeParams fin;      // optional in-kernel finalisation by the last CTA
 };
 
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ ColList cl) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (fp.stop && *reinterpret_cast<const volatile int*>(fp.stop)) {   // uniform over the grid
+        // keep the monotone barrier counter in step with the host's bookkeeping (launch_fused)
+        if (threadIdx.x == 0 && fp.nph > 1) atomicAdd(fp.barrier, (unsigned)(fp.nph - 1));
+        return;
+    }
     SmemView sm(smem);
     const int64_t n = fp.ph[0].n;
     const int64_t ntiles = (n + Cfg<T>::R - 1) / Cfg<T>::R;
@@ -65,27 +72,41 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
         }
         if (i + 1 < fp.nph) grid_barrier(fp.barrier, fp.barrier_base + (unsigned)(i + 1) * gridDim.x);
     }
+    if (fp.fin.enabled && !prod) {
+        // the last CTA to finish (ticket) reduces the per-CTA partials and publishes the step's scalars
+        double* sh = reinterpret_cast<double*>(smem + OFF_RED);
+        int* flag = reinterpret_cast<int*>(smem + OFF_RED + 256);
+        __threadfence();
+        named_bar_sync(1, NCONS);
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicInc(fp.fin.ticket, gridDim.x - 1);
+            *flag = (t == gridDim.x - 1);
+        }
+        named_bar_sync(1, NCONS);
+        if (*flag) {
+            __threadfence();
+            finalize_block(fp.fin, threadIdx.x, sh);
+        }
+    }
 }
 
-// res[off + j] = sum_g A[g*stride + j] (+ sum_g B[g*stride + j]);  res[noff] = sum_g N[g]
+// one block of NCONS threads: the stand-alone form of finalize_block
 __global__ void __launch_bounds__(NCONS)
 k_finalize(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ N, int G,
            int stride, int k, double* __restrict__ res, int off, int noff) {
-    // one block of NCONS threads; same lane layout and summation order as the UPDATE phases
-    const int tid = threadIdx.x;
-    if (k > 0) {
-        const int L = coef_lanes(k);
-        const int j = tid / L, l = tid % L;
-        const bool valid = j < k;
-        double a = coef_colsum(A, G, stride, j, l, L, valid);
-        if (B) a += coef_colsum(B, G, stride, j, l, L, valid);
-        if (valid && l == 0) res[off + j] = a;
-    }
-    if (N && tid < 32) {
-        double a = (tid < 16) ? partial_lane_sum(N, G, 1, tid, 16) : 0.0;
-        for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (tid == 0) res[noff] = a;
-    }
+    __shared__ double sh[2];
+    FinalizeParams f;
+    f.A = A; f.B = B; f.N = N; f.G = G; f.stride = stride; f.k = k; f.res = res; f.off = off; f.noff = noff;
+    f.rec = nullptr; f.alpha_col = -1; f.tol = 0.0; f.stop = nullptr; f.ticket = nullptr; f.enabled = 1;
+    finalize_block(f, threadIdx.x, sh);
+}
+
+// rec[2] = beta, rec[3] = 1/beta (start of a batch of device-chained Lanczos steps); *stop = 0
+__global__ void k_lanczos_seed(double* rec, double beta, int* stop) {
+    rec[2] = beta;
+    rec[3] = 1.0 / beta;
+    rec[4] = beta * beta;
+    *stop = 0;
 }
 
 // out[j] = (T) res[j]  (dense adjoint: projection coefficients become a device vector)
@@ -1129,6 +1150,158 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
 // consecutive expand! steps without returning to the caller.  One host synchronisation per
 // step remains (the reference checks beta after every step), but the per-step host work is
 // C++ instead of interpreter time.
+// ---------------------------------------------------------------------------------------
+// Device-chained Lanczos steps (ClassicalGramSchmidt2, lanczos.jl:250-272 + 313-324), TWO launches per step
+// and no host round trip between steps:
+//   1. SpMV with the normalisation fused into the gather: reads the residual r (unnormalised), the scalar
+//      1/β from the previous step's device record, writes v = r·(1/β) into a column of its own (it becomes the
+//      new basis vector; r's column is recycled by a later step), w = A v, and α₀ = <v, w> into this step's record;
+//   2. the cooperative Gram-Schmidt kernel: prologue w − β v₋ − α₀ v with β, α₀ read from the records, projection
+//      on all of V, grid barrier, update + ||w||², and the last CTA finalises the step's record {α, β, 1/β}.
+// The reference looks at β after every step (eigsolve/lanczos.jl:45: `while K < krylovdim && β > tol`), so do
+// the kernels: a record with β <= tol raises a device flag and everything enqueued behind it does nothing.  The
+// host reads all records with ONE synchronisation at the end of the batch and commits the steps up to the
+// first β <= tol — same α, β, V, r as stepping one at a time, bit for bit (same kernels, same operand bits).
+bool g_use_chain = true;
+
+bool chain_ok(const b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, int32_t k, int32_t nsteps, int32_t alg,
+              double beta_old) {
+    if (!g_use_chain || !g_use_coop || alg != B2K_CGS2 || nsteps < 1 || nsteps > B2K_MAX_CHAIN) return false;
+    int64_t op_rows = 0, op_cols = 0;
+    int32_t op_kind = -1;
+    if (b2k_op_info(op, &op_rows, &op_cols, nullptr, &op_kind) != B2K_OK) return false;
+    if (ctx->nranks > 1 || op_kind != 0 || beta_old == 0.0 || !(beta_old == beta_old)) return false;
+    const int32_t sp = B2K_VEC_SPACE(cols[k]);
+    if (sp < 0 || sp >= (int32_t)ctx->spaces.size()) return false;
+    const B2kSpace& s = ctx->spaces[sp];
+    if (op_rows != s.n || op_cols != s.n) return false;
+    return fused_ok(ctx, k + nsteps, s.sharded, ctx->dtype);
+}
+
+template <typename T>
+int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, const VecRef& vprev,
+                      const VecRef& rv, double* rec_prev, double* rec, double tol) {
+    const int grid = grid_for_rows<T>(ctx, pn.n);
+    ColList cl;
+    for (int i = 0; i < K1; ++i) cl.c[i] = pn.idx[i];
+    double* PA = b2k_part_set(ctx, 0);
+    double* PN = b2k_part_set(ctx, 2);
+    FusedParams<T> fp;
+    memset(&fp, 0, sizeof(fp));
+    PhaseParams<T> a = base_params<T>(pn, K1, rw.ptr, rw.ptr);
+    a.nvec = 3; a.e1 = (const T*)vprev.ptr; a.e2 = (const T*)rv.ptr; a.store_x = 1;
+    a.c1_dev = rec_prev + 2;          // beta of the previous step
+    a.c2_dev = rec + 0;               // <v, A v> of this step
+    a.part_h = PA;
+    PhaseParams<T> c = base_params<T>(pn, K1, rw.ptr, rw.ptr);
+    c.store_x = 1; c.coef = PA; c.coef_sets = grid; c.coef_stride = B2K_KSTRIDE;
+    c.alphac = (T)-1; c.part_n = PN;
+    fp.ph[0] = a; fp.kind[0] = 0; fp.ph[1] = c; fp.kind[1] = 2; fp.nph = 2;
+    fp.stop = reinterpret_cast<const int*>(ctx->d_sync + B2K_SYNC_STOP);
+    fp.fin.A = PA; fp.fin.B = nullptr; fp.fin.N = PN; fp.fin.G = grid; fp.fin.stride = B2K_KSTRIDE;
+    fp.fin.k = K1; fp.fin.res = nullptr; fp.fin.off = 0; fp.fin.noff = 0; fp.fin.rec = rec;
+    fp.fin.alpha_col = K1 - 1; fp.fin.tol = tol;
+    fp.fin.stop = reinterpret_cast<int*>(ctx->d_sync + B2K_SYNC_STOP);
+    fp.fin.ticket = ctx->d_sync + B2K_SYNC_GSFIN; fp.fin.enabled = 1;
+    const int pr = b2k_prof_begin(ctx, 1, (2.0 * K1 + 3.0) * sizeof(T) * (double)pn.n);
+    B2K_TRY(launch_fused<T>(ctx, fp, cl, grid));
+    b2k_prof_end(ctx, pr);
+    return B2K_OK;
+}
+
+int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, int32_t nsteps,
+                      double beta_old, double tol, double* alphas_out, double* betas_out,
+                      int32_t* steps_done, b2k_vec* r_out) {
+    const bool f64 = ctx->dtype == B2K_F64;
+    const int32_t space = B2K_VEC_SPACE(cols[k]);
+    double* rec0 = ctx->d_steps;
+    int* d_stop = reinterpret_cast<int*>(ctx->d_sync + B2K_SYNC_STOP);
+    {   // every handle must be live before anything is enqueued
+        VecRef t;
+        for (int i = 0; i <= k; ++i) B2K_TRY(b2k_resolve(ctx, cols[i], &t));
+    }
+    k_lanczos_seed<<<1, 1, 0, ctx->stream>>>(rec0, beta_old, d_stop);
+    B2K_LAUNCH_CHECK(ctx);
+    std::vector<b2k_vec> touched, Vh, Wh;
+    touched.push_back(cols[k]);
+    int32_t enq = 0, rc = B2K_OK;
+    for (int32_t i = 0; i < nsteps; ++i) {
+        const int32_t K = k + i;                 // basis size before this step's push!
+        const b2k_vec R = cols[K];
+        b2k_vec V = -1, W = -1;
+        rc = b2k_vec_alloc(ctx, space, &V);
+        if (rc != B2K_OK) break;
+        rc = b2k_vec_alloc(ctx, space, &W);
+        if (rc != B2K_OK) { b2k_vec_free(ctx, V); break; }
+        touched.push_back(V);
+        touched.push_back(W);
+        VecRef rR, rV, rW, vprev;
+        rc = b2k_resolve(ctx, R, &rR);
+        if (rc == B2K_OK) rc = b2k_resolve(ctx, V, &rV);
+        if (rc == B2K_OK) rc = b2k_resolve(ctx, W, &rW);
+        if (rc == B2K_OK) rc = b2k_resolve(ctx, cols[K - 1], &vprev);
+        if (rc != B2K_OK) break;
+        double* rec_prev = rec0 + (size_t)B2K_REC * i;
+        double* rec = rec0 + (size_t)B2K_REC * (i + 1);
+        SpmvFuse fz;
+        fz.xscale = rec_prev + 3;
+        fz.vout = rV.ptr;
+        fz.stop = d_stop;
+        fz.dot_self = 1;
+        rc = b2k_enqueue_apply_fused(ctx, op, rR, rW, 0.0, 1.0, false, nullptr, rec + 0, &fz);
+        if (rc != B2K_OK) break;
+        cols[K] = V;                             // the normalised residual is the new basis vector ...
+        Panel pn;
+        rc = make_panel(ctx, cols, K + 1, &pn);
+        if (rc != B2K_OK) break;
+        rc = f64 ? chain_step_gs<double>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol)
+                 : chain_step_gs<float>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol);
+        if (rc != B2K_OK) break;
+        cols[K + 1] = W;                         // ... and w the new residual
+        Vh.push_back(V);
+        Wh.push_back(W);
+        // r's column has been consumed; later steps may reuse it (stream order keeps that safe)
+        ctx->spaces[space].used[B2K_VEC_COL(R)] = 0;
+        ++enq;
+    }
+    int32_t d = 0;
+    if (enq > 0) {
+        cudaError_t e = cudaMemcpyAsync(ctx->h_res, rec0 + B2K_REC, sizeof(double) * B2K_REC * enq,
+                                        cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess)
+            return b2k_fail(ctx, B2K_ECUDA, "lanczos_expand_many: %s", cudaGetErrorString(e));
+        d = enq;
+        for (int32_t i = 0; i < enq; ++i) {
+            alphas_out[i] = ctx->h_res[(size_t)B2K_REC * i + 1];
+            betas_out[i] = ctx->h_res[(size_t)B2K_REC * i + 2];
+            if (betas_out[i] <= tol) { d = i + 1; break; }
+        }
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    // column bookkeeping: everything this batch touched is free again, except the d new basis vectors and
+    // the residual that follows them (steps behind a breakdown were skipped on the device)
+    B2kSpace& sp = ctx->spaces[space];
+    for (b2k_vec h : touched) sp.used[B2K_VEC_COL(h)] = 0;
+    if (d > 0) {
+        for (int32_t i = 0; i < d; ++i) cols[k + i] = Vh[i];     // (skipped steps overwrote cols[k + d ..])
+        cols[k + d] = Wh[d - 1];
+        for (int32_t i = 0; i <= d; ++i) sp.used[B2K_VEC_COL(cols[k + i])] = 1;
+    } else {
+        sp.used[B2K_VEC_COL(touched[0])] = 1;    // nothing ran: r is still r
+        cols[k] = touched[0];
+    }
+    *steps_done = d;
+    *r_out = cols[k + d];
+    return rc;
+}
+
+extern "C" int32_t b2k_debug_set_chain(int32_t on) {
+    g_use_chain = on != 0;
+    return B2K_OK;
+}
+
 extern "C" int32_t b2k_lanczos_expand_many(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k,
                                            int32_t nsteps, double beta_old, double tol, int32_t alg,
                                            double eta, double* alphas_out, double* betas_out,
@@ -1138,6 +1311,8 @@ extern "C" int32_t b2k_lanczos_expand_many(b2k_ctx* ctx, const b2k_op* op, b2k_v
     *steps_done = 0;
     b2k_vec r = cols[k];
     *r_out = r;
+    if (chain_ok(ctx, op, cols, k, nsteps, alg, beta_old))
+        return lanczos_chain(ctx, op, cols, k, nsteps, beta_old, tol, alphas_out, betas_out, steps_done, r_out);
     double beta = beta_old;
     for (int32_t i = 0; i < nsteps; ++i) {
         b2k_vec w;

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(BT) k_scale(T* __restrict__ y, const T* __rest
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T a[V];
         vload<T>(x + i * V, a);
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(BT) k_axpby(T* __restrict__ y, const T* __rest
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T a[V], b[V];
         vload<T>(x + i * V, a);
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(BT) k_axpy2(T* __restrict__ y, const T* __rest
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T a[V], b[V], c[V];
         vload<T>(y + i * V, c);
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(BT) k_givens(T* __restrict__ q1, T* __restrict
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T a[V], b[V], o1[V], o2[V];
         vload<T>(q1 + i * V, a);
@@ -167,6 +171,7 @@ k_dot(const T* __restrict__ q, T* __restrict__ x, int64_t n, const T* __restrict
     T sp = 0;
     if (UPDATE) sp = (T)(*sprev);
     T acc = 0;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T a[V], b[V];
         vload<T>(x + i * V, b);
@@ -223,6 +228,7 @@ k_axpy_dev(T* __restrict__ x, const T* __restrict__ q, const double* __restrict_
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T a[V], b[V];
         vload<T>(x + i * V, b);
@@ -251,6 +257,7 @@ k_cg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* 
     const int64_t stride = (int64_t)gridDim.x * BT;
     const T alpha = (T)(rho / *pq);
     T acc = 0;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T xv[V], rv[V], pv[V], qv[V];
         vload<T>(x + i * V, xv);
@@ -301,6 +308,7 @@ k_bicg_p(T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ v, in
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T pv[V], rv[V], vv[V];
         vload<T>(p + i * V, pv);
@@ -360,6 +368,7 @@ k_bicg_s(T* __restrict__ s, const T* __restrict__ r, const T* __restrict__ v, in
     const int64_t stride = (int64_t)gridDim.x * BT;
     const T alpha = (T)(rho / *sigma);
     T acc = 0;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T rv[V], vv[V];
         vload<T>(r + i * V, rv);
@@ -396,6 +405,7 @@ k_bicg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ rs, const 
     const int64_t stride = (int64_t)gridDim.x * BT;
     const T omega = (T)(*ts / *tt);
     T a1 = 0, a2 = 0;
+    _Pragma("unroll 4")
     for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
         T xv[V], pv[V], sv[V], tv[V], qv[V];
         vload<T>(x + i * V, xv);

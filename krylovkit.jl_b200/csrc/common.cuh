@@ -17,6 +17,12 @@ constexpr int B2K_RES_DOUBLES  = 8192;     // device/host scalar result buffer
 constexpr int B2K_COEF_DOUBLES = 65536;    // host->device coefficient staging (512 KB)
 constexpr int B2K_MAX_GRID     = 1024;     // upper bound on partial-producing CTAs (basis kernels)
 constexpr int B2K_KSTRIDE      = 256;      // stride (doubles) between per-CTA partial rows
+constexpr int B2K_MAX_CHAIN    = 512;      // Lanczos steps enqueued back to back without a host round trip
+constexpr int B2K_REC          = 8;        // doubles per step record (tsk.cuh FinalizeParams)
+// d_sync slots: [0] ticket of the BLAS-1 / SpMV reductions, [1] grid-barrier counter, [2] ticket of the
+// in-kernel Gram-Schmidt finalisation, [4] breakdown flag of a chained Lanczos batch
+constexpr int B2K_SYNC_GSFIN   = 2;
+constexpr int B2K_SYNC_STOP    = 4;
 
 struct B2kSpace {
     void*   base   = nullptr;   // device pointer, column-major n x ncols, leading dim ld
@@ -59,7 +65,8 @@ struct b2k_ctx {
     double*   h_res    = nullptr;   // pinned
     double*   d_coef   = nullptr;   // coefficients uploaded from host
     double*   h_coef   = nullptr;   // pinned staging
-    unsigned* d_sync   = nullptr;   // [0] ticket, [1] grid barrier counter, ...
+    unsigned* d_sync   = nullptr;   // [0] ticket, [1] grid barrier counter, ... (B2K_SYNC_*)
+    double*   d_steps  = nullptr;   // (B2K_MAX_CHAIN + 1) step records of B2K_REC doubles
     cudaEvent_t ev_coef = nullptr;  // guards reuse of the pinned staging buffers
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // b2k_timer_start/stop
     bool      coef_busy = false;
@@ -153,6 +160,27 @@ static inline double* b2k_part_set(b2k_ctx* ctx, int set) {
 
 // spmv.cu: free the device arrays of an operator (called by b2k_op_destroy / b2k_ctx_destroy)
 void b2k_op_release(b2k_ctx* ctx, b2k_op* op);
+
+// Optional fusions of the Lanczos step into the SpMV (basis.cu, b2k_lanczos_expand_many):
+//   xscale   : device scalar; the operand is x*(*xscale) — the normalisation v = r/β of lanczos.jl:257 applied
+//              while gathering (each gathered entry is rounded exactly like the separate scale!! pass);
+//   vout     : the normalised operand is also written out (row r writes x[r]*(*xscale)): it becomes the new
+//              basis vector, in a column of its own because other CTAs still gather the unscaled x;
+//   dot_self : the fused dot product is <x*(*xscale), y> (no separate read of the normalised vector);
+//   stop     : device flag; when set the launch does nothing (a breakdown was detected by an earlier step of
+//              a batch that was enqueued without waiting for the host).
+struct SpmvFuse {
+    const double* xscale;
+    void* vout;
+    const int* stop;
+    int dot_self;
+};
+
+int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
+                          double a0, double a1, bool shifted, const VecRef* dotv, int dot_slot);
+int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
+                                double a0, double a1, bool shifted, const VecRef* dotv, double* dot_out,
+                                const SpmvFuse* fz);
 
 // basis.cu / spmv.cu
 int32_t b2k_basis_init(b2k_ctx* ctx);

@@ -58,10 +58,15 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
               const T* __restrict__ vals, const T* __restrict__ x, const T* __restrict__ halo,
               int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk, T a0, T a1,
               int shifted, const T* __restrict__ xs, const T* __restrict__ dotv,
-              double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out) {
+              double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out,
+              const SpmvFuse fz) {
     __shared__ T prod[SP_NNZ];
     __shared__ double red[32];
     __shared__ bool last;
+    if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
+    const bool scaled = fz.xscale != nullptr;
+    const T sc = scaled ? (T)(*fz.xscale) : (T)1;
+    T* const vout = reinterpret_cast<T*>(fz.vout);
     const int tid = threadIdx.x;
     const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
     const int p0 = rowptr[r0], p1 = rowptr[r1];
@@ -85,7 +90,8 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             const int i = tid + u * SP_BT;
             if (i < nnzb) {
                 const int32_t cc = c[u];
-                const T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+                T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+                if (scaled) xv *= sc;
                 prod[i] = v[u] * xv;
             }
         }
@@ -97,14 +103,21 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             for (int p = a; p < b; ++p) s += prod[p];
             if (shifted) s = fma(a0, xs[r], a1 * s);
             y[r] = s;
-            if (dotv) dacc = fma(dotv[r], s, dacc);
+            T dv = (T)0;
+            if (vout || fz.dot_self) {
+                dv = __ldg(x + r) * sc;                 // the normalised x_r (square operator, local row r)
+                if (vout) vout[r] = dv;
+            }
+            if (dotv && !fz.dot_self) dv = dotv[r];
+            if (dotv || fz.dot_self) dacc = fma(dv, s, dacc);
         }
     } else {
         // long row: the CTA owns exactly one row
         double acc = 0.0;
         for (int i = tid; i < nnzb; i += SP_BT) {
             const int32_t cc = colidx[p0 + i];
-            const T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+            T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+            if (scaled) xv *= sc;
             acc += (double)(vals[p0 + i] * xv);
         }
         const double tot = block_sum(acc, red);
@@ -112,10 +125,16 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             T s = (T)tot;
             if (shifted) s = fma(a0, xs[r0], a1 * s);
             y[r0] = s;
-            if (dotv) dacc = dotv[r0] * s;
+            T dv = (T)0;
+            if (vout || fz.dot_self) {
+                dv = __ldg(x + r0) * sc;
+                if (vout) vout[r0] = dv;
+            }
+            if (dotv && !fz.dot_self) dv = dotv[r0];
+            if (dotv || fz.dot_self) dacc = dv * s;
         }
     }
-    if (dotv) {
+    if (dotv || fz.dot_self) {
         const double s = block_sum((double)dacc, red);
         if (tid == 0) {
             part[blockIdx.x] = s;
@@ -171,9 +190,10 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk,
             const int32_t* __restrict__ pblk, int nblk, T a0, T a1, int shifted,
             const T* __restrict__ xs, const T* __restrict__ dotv, double* __restrict__ part,
-            unsigned* __restrict__ ticket, double* __restrict__ out) {
+            unsigned* __restrict__ ticket, double* __restrict__ out, const SpmvFuse fz) {
     using LY = SppLayout<T>;
     extern __shared__ __align__(128) uint8_t smem[];
+    if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
     const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + SPP_NSTG * 8;
     double* red = reinterpret_cast<double*>(smem + LY::OFF_RED);
     int* flag = reinterpret_cast<int*>(smem + LY::OFF_RED + 32 * 8);
@@ -220,6 +240,11 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     }
     // ---------------------------------- consumers ----------------------------------
     const int tid = threadIdx.x, w = tid >> 5;
+    const bool scaled = fz.xscale != nullptr;
+    const T sc = scaled ? (T)(*fz.xscale) : (T)1;
+    T* const vout = reinterpret_cast<T*>(fz.vout);
+    const bool self = (vout != nullptr) || fz.dot_self;
+    const bool want_dot = (dotv != nullptr) || fz.dot_self;
     T dacc = (T)0;
     int tile = blockIdx.x;
     int4 dn = make_int4(0, 0, 0, 0);
@@ -245,6 +270,10 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                     xv[u] = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
                 }
             }
+            if (scaled) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] *= sc;      // v_j = r_j * (1/β), rounded like scale!!
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = tid + u * SPP_CONS;
@@ -254,7 +283,8 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const bool rp_staged = nrows <= SPP_RMAX;
             for (int r = r0 + tid; r < r1; r += SPP_CONS) {
                 // issue the (optional) per-row global loads first so they overlap the row sum
-                const T dv = dotv ? __ldg(dotv + r) : (T)0;
+                T dv = (dotv && !fz.dot_self) ? __ldg(dotv + r) : (T)0;
+                const T xself = self ? __ldg(x + r) : (T)0;
                 const T xsr = shifted ? __ldg(xs + r) : (T)0;
                 int a, b;
                 if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
@@ -264,13 +294,19 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 for (int p = a; p < b; ++p) sum += vs[p];
                 if (shifted) sum = fma(a0, xsr, a1 * sum);
                 y[r] = sum;
+                if (self) {
+                    const T vn = xself * sc;
+                    if (vout) vout[r] = vn;
+                    if (fz.dot_self) dv = vn;
+                }
                 dacc = fma(dv, sum, dacc);
             }
         } else {
             double acc = 0.0;
             for (int i = tid; i < nnzb; i += SPP_CONS) {
                 const int32_t cc = colidx[p0 + i];
-                const T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+                T xv = (cc < n_loc) ? __ldg(x + cc) : __ldg(halo + (cc - n_loc));
+                if (scaled) xv *= sc;
                 acc += (double)(vals[p0 + i] * xv);
             }
             acc = warp_sum(acc);
@@ -282,7 +318,13 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 T sum = (T)tot;
                 if (shifted) sum = fma(a0, xs[r0], a1 * sum);
                 y[r0] = sum;
-                if (dotv) dacc = fma(dotv[r0], sum, dacc);
+                T dv = (dotv && !fz.dot_self) ? dotv[r0] : (T)0;
+                if (self) {
+                    const T vn = __ldg(x + r0) * sc;
+                    if (vout) vout[r0] = vn;
+                    if (fz.dot_self) dv = vn;
+                }
+                if (want_dot) dacc = fma(dv, sum, dacc);
             }
             named_bar_sync(1, SPP_CONS);
         }
@@ -291,7 +333,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
         if (lane == 0) mbar_arrive(empty + 8 * s);
         if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
     }
-    if (dotv) {
+    if (want_dot) {
         double v = warp_sum((double)dacc);
         if (lane == 0) red[w] = v;
         named_bar_sync(1, SPP_CONS);
@@ -936,6 +978,21 @@ int32_t b2k_spmv_init(b2k_ctx* ctx) {
 
 int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
                           double a0, double a1, bool shifted, const VecRef* dotv, int dot_slot) {
+    return b2k_enqueue_apply_fused(ctx, op, x, y, a0, a1, shifted, dotv,
+                                   dotv ? ctx->d_res + dot_slot : nullptr, nullptr);
+}
+
+// fz (optional): normalise-on-gather / write the normalised operand / dot with it / skip flag — see SpmvFuse.
+int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
+                                double a0, double a1, bool shifted, const VecRef* dotv, double* dot_out,
+                                const SpmvFuse* fzp) {
+    SpmvFuse fz;
+    memset(&fz, 0, sizeof(fz));
+    if (fzp) fz = *fzp;
+    if (fzp && op->kind != 0) return b2k_fail(ctx, B2K_ENOTSUP, "fused apply: CSR operators only");
+    if ((fz.vout || fz.dot_self) && (op->n_rows != x.n))
+        return b2k_fail(ctx, B2K_EDIM, "fused apply: needs a square operator (row r <-> x[r])");
+    if (fz.dot_self && !dot_out) return b2k_fail(ctx, B2K_EINVAL, "fused apply: dot_self without an output slot");
     if (op->kind == 1) {
         if (shifted || dotv) return b2k_fail(ctx, B2K_ENOTSUP, "dense apply: no shift/dot fusion");
         if (x.n != op->n_cols || y.n != op->n_rows)
@@ -981,7 +1038,7 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
     } else if (x.n == op->n_cols) {
         n_loc = 0x7fffffff;
     }
-    double* out = dotv ? ctx->d_res + dot_slot : nullptr;
+    double* out = (dotv || fz.dot_self) ? dot_out : nullptr;
     const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
                                               2.0 * ctx->esize * op->n_rows);
     if (g_spmv_pipe) {
@@ -990,7 +1047,7 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
     k_spmv_pipe<T><<<grid, SPP_THREADS, SppLayout<T>::SMEM, ctx->stream>>>(                    \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
         (T*)y.ptr, op->rowblk, op->pblk, op->nblk, (T)a0, (T)a1, shifted ? 1 : 0,              \
-        (const T*)x.ptr, dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out)
+        (const T*)x.ptr, dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz)
         if (ctx->dtype == B2K_F64) LAUNCH(double);
         else LAUNCH(float);
 #undef LAUNCH
@@ -999,7 +1056,7 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
     k_spmv_stream<T><<<op->nblk, SP_BT, 0, ctx->stream>>>(                                     \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
         (T*)y.ptr, op->rowblk, (T)a0, (T)a1, shifted ? 1 : 0, (const T*)x.ptr,                 \
-        dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out)
+        dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz)
         if (ctx->dtype == B2K_F64) LAUNCH(double);
         else LAUNCH(float);
 #undef LAUNCH

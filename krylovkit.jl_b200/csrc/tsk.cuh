@@ -80,6 +80,7 @@ struct PhaseParams {
     const T* e1;     // prologue vectors (nvec == 3): x' = (x + c1*e1) + c2*e2
     const T* e2;
     T c1, c2;
+    const double* c1_dev;   // if set: c1 = -(*c1_dev)  (beta of the previous step, kept on the device)
     const double* c2_dev;   // if set: c2 = -(*c2_dev), a device scalar produced by the previous kernel
     int32_t nvec;    // 1 or 3
     int32_t store_x; // write x'' (UPDATE) or x' (prologue write-back) to xout
@@ -265,7 +266,8 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
         for (int cc = 0; cc < CPW; ++cc) acc_h[c][cc] = (T)0;
     T nrm = (T)0;
     int buf = 0;
-    T c2 = p.c2;
+    T c1 = p.c1, c2 = p.c2;
+    if (p.c1_dev) c1 = (T)(-(*reinterpret_cast<const volatile double*>(p.c1_dev)));
     if (p.c2_dev) c2 = (T)(-(*reinterpret_cast<const volatile double*>(p.c2_dev)));
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -275,7 +277,7 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
         const T* wv = reinterpret_cast<const T*>(sm.raw + OFF_WRING) + st.ws * 3 * R;
         T xv = wv[tid];
         if (p.nvec == 3) {
-            xv = fma(p.c1, wv[R + tid], xv);
+            xv = fma(c1, wv[R + tid], xv);
             xv = fma(c2, wv[2 * R + tid], xv);
         }
         if (tid >= rt) xv = (T)0;
@@ -367,6 +369,66 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
 #pragma unroll
             for (int i = 0; i < NCONS / 32; ++i) s += red[i];
             p.part_n[blockIdx.x] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- finalize ----
+// res[off + j] = sum_g A[g*stride + j] (+ sum_g B[g*stride + j]);  res[noff] = sum_g N[g] — executed by NCONS
+// threads, same lane layout and summation order as the UPDATE phases (coef_colsum), so the coefficient REPORTED
+// equals the one APPLIED bit for bit.  Used by k_finalize (one launch) and, when a Gram-Schmidt launch carries a
+// FinalizeParams, by the last CTA of that launch itself (ticket): no extra launch, and the Lanczos scalars of
+// the step land in a device record the NEXT step's kernels read — the host never has to be in the loop:
+//   rec[0] = <v, A v> (written by the SpMV)      rec[1] = alpha = rec[0] + h[alpha_col]   (lanczos.jl:321)
+//   rec[2] = beta = sqrt(||w||^2)                 rec[3] = 1/beta                           rec[4] = ||w||^2
+// and *stop = 1 if beta <= tol (the steps already enqueued behind this one then do nothing).
+struct FinalizeParams {
+    const double* A;
+    const double* B;
+    const double* N;
+    int G, stride, k;
+    double* res;        // may be nullptr
+    int off, noff;
+    double* rec;        // may be nullptr
+    int alpha_col;
+    double tol;
+    int* stop;
+    unsigned* ticket;
+    int enabled;
+};
+
+// `sh` : >= 2 doubles of shared memory; `barrier_id` : named barrier the NCONS calling threads may use
+__device__ __forceinline__ void finalize_block(const FinalizeParams& f, int tid, double* sh) {
+    double hval = 0.0;
+    if (f.k > 0) {
+        const int L = coef_lanes(f.k);
+        const int j = tid / L, l = tid % L;
+        const bool valid = j < f.k;
+        double a = coef_colsum(f.A, f.G, f.stride, j, l, L, valid);
+        if (f.B) a += coef_colsum(f.B, f.G, f.stride, j, l, L, valid);
+        if (valid && l == 0) {
+            if (f.res) f.res[f.off + j] = a;
+            if (j == f.alpha_col) hval = a;
+        }
+        if (f.rec && valid && l == 0 && j == f.alpha_col) sh[0] = hval;
+    }
+    double n2 = 0.0;
+    if (f.N && tid < 32) {
+        double a = (tid < 16) ? partial_lane_sum(f.N, f.G, 1, tid, 16) : 0.0;
+        for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        n2 = a;
+        if (tid == 0 && f.res) f.res[f.noff] = a;
+    }
+    if (f.rec) {
+        named_bar_sync(1, NCONS);
+        if (tid == 0) {
+            const double alpha = f.rec[0] + sh[0];
+            const double beta = sqrt(n2);
+            f.rec[1] = alpha;
+            f.rec[2] = beta;
+            f.rec[3] = 1.0 / beta;
+            f.rec[4] = n2;
+            if (f.stop && beta <= f.tol) *f.stop = 1;
         }
     }
 }

@@ -227,9 +227,17 @@ def expand_many_(it: LanczosIterator, state: LanczosFactorization, nsteps: int, 
     # catches the error (e.g. a slab that ran out of columns at step i > 0)
     d = done.value
     if d > 0:
-        V.push(r)                                   # the old residual became basis vector k+1
-        for i in range(1, d):
-            V.push(B200Vec(ctx, cols[k + i]))       # columns allocated by the library
+        # the library returns the d new basis vectors in cols[k : k + d] and the residual in r_out.  On the
+        # literal path the old residual's column IS the first of them (lanczos.jl:257); on the device-chained
+        # path the normalised vector was written to a column of its own and r's column has been recycled.
+        new = [int(cols[k + i]) for i in range(d)]
+        if new[0] == r.handle:
+            V.push(r)
+        else:
+            r.disown()                              # released (and possibly reused) inside the library
+            V.push(B200Vec(ctx, new[0]))
+        for h in new[1:]:
+            V.push(B200Vec(ctx, h))                 # columns allocated by the library
         state.r = B200Vec(ctx, rout.value)
         state.alphas.extend(al[:d])
         state.betas.extend(be[:d])

@@ -139,6 +139,10 @@ class B200Vec:
     def free(self):
         self._fin()
 
+    def disown(self):
+        """Forget the column without releasing it: the library has taken it back (b2k_lanczos_expand_many)."""
+        self._fin.detach()
+
     def upload(self, x):
         a = np.ascontiguousarray(x, dtype=self.ctx.np_dtype)
         if a.shape != (len(self),):

@@ -121,6 +121,11 @@ class HostSimLib:
         self.ops: dict[int, object] = {}
         self.next_id = 1000
         self.err = b""
+        self.chain = True          # b2k_lanczos_expand_many follows the device-chained handle contract (CGS2)
+
+    def b2k_debug_set_chain(self, on):
+        self.chain = bool(on)
+        return L.OK
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _fail(self, ctx, code, msg):
@@ -528,6 +533,16 @@ class HostSimLib:
                 self.b2k_vec_free(h, wref.value)
                 return st
             alphas[i], betas[i] = a.value, b.value
+            if self.chain and alg == L.CGS2:
+                # the device-chained contract: the normalised vector lives in a column of its own and the old
+                # residual's column goes back to the slab (it may be handed out again right away)
+                vref = C.c_int32()
+                st = self.b2k_vec_alloc(h, r >> 20, vref)
+                if st != L.OK:
+                    return st
+                self.b2k_vec_copy(h, vref.value, r)
+                self.b2k_vec_free(h, r)
+                cols[k] = vref.value
             k += 1
             cols[k] = wref.value
             r, beta = wref.value, b.value

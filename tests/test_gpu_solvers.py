@@ -786,3 +786,58 @@ def test_zero_start_vector_raises():
     with pytest.raises(ValueError):
         kk.eigsolve(op, ctx.zeros(), 1, "SR", kk.Lanczos(krylovdim=5, verbosity=0))
     ctx.close()
+
+
+def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None):
+    """initialize + one b2k_lanczos_expand_many batch; returns (alphas, betas, V (host), r (host), free columns)."""
+    lib = L.load()
+    lib.b2k_debug_set_chain(1 if chain else 0)
+    try:
+        n = nx * ny
+        ctx = kk.B200Context(n, steps + 8)
+        if diag is None:
+            op = kk.B200CSR.stencil(ctx, nx, ny)
+            x0 = ctx.from_host(ko.splitmix_vector(SEED, n))
+        else:
+            op = kk.B200CSR.from_scipy(ctx, sp.diags(diag).tocsr())
+            x0 = ctx.from_host(ko.splitmix_vector(5, n) + 0.5)
+        it = lz.LanczosIterator(op, x0, kk.cgs2)
+        f = lz.initialize(it)
+        done = lz.expand_many_(it, f, steps, tol)
+        out = (done, np.array(f.alphas), np.array(f.betas), np.column_stack([v.to_host() for v in f.V]),
+               f.r.to_host())
+        del f, it, x0
+        import gc
+        gc.collect()
+        # every slab column is free again: nothing leaked by the batch's internal column recycling
+        spare = [ctx.empty() for _ in range(steps + 8)]
+        del spare
+        ctx.close()
+        return out
+    finally:
+        lib.b2k_debug_set_chain(1)
+
+
+def test_chained_lanczos_batch_is_bit_identical_to_stepping():
+    """b2k_lanczos_expand_many with the device-chained steps (normalisation fused into the SpMV gather, scalars
+    kept in device records, in-kernel finalisation, no host round trip) gives the same bits as one synchronous
+    b2k_lanczos_expand per step: same kernels' arithmetic, same operand bits (lanczos.jl:250-272, 313-324)."""
+    d1, a1, b1, V1, r1 = _expand_many_run(True)
+    d0, a0, b0, V0, r0 = _expand_many_run(False)
+    assert d1 == d0 == 30
+    assert np.array_equal(a1, a0) and np.array_equal(b1, b0)
+    assert np.array_equal(V1, V0) and np.array_equal(r1, r0)
+    assert np.abs(V1.T @ V1 - np.eye(V1.shape[1])).max() < 1e-12
+
+
+def test_chained_lanczos_batch_stops_at_breakdown_on_the_device():
+    """beta <= tol in the middle of a batch (eigsolve/lanczos.jl:45): the kernels enqueued behind that step do
+    nothing, the factorization is the one of the synchronous loop and the residual is intact."""
+    n = 3000
+    d = np.repeat([1.0, 2.5, 7.0, 11.0], n // 4)
+    res = [_expand_many_run(c, nx=n, ny=1, steps=12, tol=1e-9, diag=d) for c in (True, False)]
+    (d1, a1, b1, V1, r1), (d0, a0, b0, V0, r0) = res
+    assert d1 == d0 == 3                        # 4 distinct eigenvalues: the Krylov space is exhausted at K = 4
+    assert np.array_equal(a1, a0) and np.array_equal(b1, b0)
+    assert np.array_equal(V1, V0) and np.array_equal(r1, r0)
+    assert b1[-1] <= 1e-9

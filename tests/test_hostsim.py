@@ -237,6 +237,13 @@ def test_fused_branches_bookkeeping(simf):
     G.test_invariant_subspace_early_exit()
 
 
+def test_chained_batch_bookkeeping(simf):
+    """handle accounting of the device-chained b2k_lanczos_expand_many contract (new column per basis vector,
+    the old residual's column recycled, breakdown in the middle of a batch) without a GPU"""
+    G.test_chained_lanczos_batch_is_bit_identical_to_stepping()
+    G.test_chained_lanczos_batch_stops_at_breakdown_on_the_device()
+
+
 def test_fused_eigsolve_with_restarts(simf):
     nx, ny = 40, 25
     A = ko.stencil_matrix(nx, ny)
