@@ -70,6 +70,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=30, help="expand! steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra", default="c3,c4,c5",
+                    help="other BASELINE.json configs measured after the headline (records under 'other_configs'); "
+                         "'' = none")
     return ap.parse_args()
 
 
@@ -215,10 +218,44 @@ def cpu_full_job(a, A):
         vals, vecs, info = ko.eigsolve_lanczos(A, x0, HOWMANY, "SR", krylovdim=a.krylovdim, maxiter=a.cycles,
                                                tol=0.0, orth=orth)
         dt = time.perf_counter() - t0
-    return info["numops"] / dt, dt, info["numops"]
+    return info["numops"] / dt, dt, info["numops"], vals
+
+
+def golden_case(a):
+    """The oracle's committed full-size results for this workload (tests/golden/fullsize.json, written by
+    tests/golden/make_fullsize_golden.py) or None when the command line asks for another workload."""
+    p = os.path.join(ROOT, "tests", "golden", "fullsize.json")
+    if not os.path.exists(p):
+        return None
+    g = json.load(open(p))
+    for name in ("c2", "c2_mgs2", "c2_1e6"):
+        c = g.get(name)
+        if c and c["grid"] == [a.nx, a.ny, 1] and c["krylovdim"] == a.krylovdim and c["orth"] == a.orth \
+                and str(a.cycles) in c["after_cycles"]:
+            return {"name": f"tests/golden/fullsize.json:{name}:after_cycles[{a.cycles}]", **c["after_cycles"][str(a.cycles)]}
+    return None
+
+
+def check_parity(a, vals, numops, what):
+    """Ritz values of this run vs the oracle's on the same (A, x0): <= 1e-10 relative (north_star), numops equal."""
+    g = golden_case(a)
+    if g is None:
+        return {"checked": False, "why": "no committed oracle result for this workload"}
+    ref = np.array(g["ritz"])
+    rel = float(np.max(np.abs(np.array(vals[:len(ref)]) - ref) / np.abs(ref)))
+    ok = rel <= 1e-10 and int(numops) == int(g["numops"])
+    out = {"checked": True, "against": g["name"] + " (oracle/krylov_oracle.py at full size)", "max_rel_diff_ritz": rel,
+           "tolerance": 1e-10, "numops": int(numops), "numops_oracle": int(g["numops"]), "ok": bool(ok)}
+    if not ok:
+        raise AssertionError(f"{what}: parity with the oracle lost: {out}; ritz = {list(vals[:len(ref)])}, oracle = {list(ref)}")
+    return out
 
 
 def run_reference(a):
+    """The reference arm runs the SAME job as the GPU arm — the whole eigsolve (krylovdim expansion + restart
+    cycles, `numops` operator applications) — through the restated reference on the host cores.  The number of
+    timed jobs is capped (a whole job costs ~10-20 s of the box's CPU quota) independently of --steps, and is
+    reported as steps_timed; the Ritz values of the last job are printed so both arms can be compared."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -227,37 +264,33 @@ def run_reference(a):
     if native is not None:
         cores = native.num_threads()                 # the calibrated thread count
     backend += f" with {cores} threads ({_cpu_host_note()})"
-    # one short untimed sample (also the warm-up) sizes the work so that the whole --steps K run stays within
-    # ~4 minutes whatever K the driver passes: the full job if it fits, else a bounded number of expand! steps
+    # one short untimed sample (also the warm-up) sizes the run: whole jobs only, as many as fit ~200 s
     # (the cost of a step grows with the basis size: the job averages ~3x the cost of the first four steps)
     _, dt_w, ops_w = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, 4, A)
-    budget_s = 220.0
+    budget_s = 200.0
     per_op = dt_w / ops_w
     job_ops = a.krylovdim + (a.cycles - 1) * (a.krylovdim - (3 * a.krylovdim) // 5)
-    full = 3.0 * per_op * job_ops * max(1, a.steps) <= budget_s
-    t_tot, ops_tot = 0.0, 0
-    if full:
-        for _ in range(a.steps):
-            v, dt, ops = cpu_full_job(a, A)
-            t_tot += dt
-            ops_tot += ops
-        sample = (f"the whole job per step ({ops_tot // max(1, a.steps)} operator applications, {a.cycles} restart cycles) "
-                  f"through oracle/krylov_oracle.py eigsolve_lanczos; n-length loops: {backend}")
-    else:
-        nsteps = int(max(5, min(a.cpu_steps, budget_s / max(1, a.steps) / (2.5 * per_op))))
-        for _ in range(a.steps):
-            v, dt, ops = cpu_sample(a.nx, a.ny, a.krylovdim, a.orth, nsteps, A)
-            t_tot += dt
-            ops_tot += ops
-        sample = (f"initialize + {nsteps} expand! steps ({nsteps + 1} operator applications, basis sizes 1..{nsteps + 1}) "
-                  f"of the full n={a.nx * a.ny} job per step; oracle/krylov_oracle.py; n-length loops: {backend}")
+    est_job = 3.0 * per_op * job_ops
+    jobs = int(max(1, min(a.steps, budget_s // max(est_job, 1e-9))))
+    t_tot, ops_tot, vals = 0.0, 0, None
+    for _ in range(jobs):
+        v, dt, ops, vals = cpu_full_job(a, A)
+        t_tot += dt
+        ops_tot += ops
+        if t_tot > budget_s:
+            jobs = _ + 1
+            break
+    sample = (f"the WHOLE job, {jobs} time(s) ({ops_tot // jobs} operator applications per job, {a.cycles} restart "
+              f"cycles) through oracle/krylov_oracle.py eigsolve_lanczos; n-length loops: {backend}")
     value = ops_tot / t_tot
+    parity = check_parity(a, vals, ops_tot // jobs, "reference arm (oracle on this host)")
     line = {
         "impl": "reference", "metric": "eigsolve_lanczos_operator_applications_per_sec", "value": value,
-        "unit": "it/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1000.0 * t_tot / a.steps, "higher_is_better": True, "scaling": "strong",
+        "unit": "it/s", "n_gpus": a.gpus, "steps": a.steps, "steps_timed": jobs, "warmup": a.warmup,
+        "ms_per_step": 1000.0 * t_tot / jobs, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a),
+        "config": workload_config(a), "numops_per_step": ops_tot // jobs,
+        "ritz_values": [float(x) for x in vals[:HOWMANY]], "parity": parity,
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -293,7 +326,7 @@ def run_ours(a):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from krylovkit_jl_b200 import sharding
-        uid_bytes = sharding.broadcast_nccl_uid(dist, kk._lib.load(), torch.device("cuda", local_rank))
+        uid_bytes = sharding.broadcast_nccl_uid(dist, kk._lib.load())
         shard = sharding.shard_grid_lines(a.nx, a.ny, rank, world)      # whole grid lines per rank
         ctx = kk.B200Context(shard.n_local, a.krylovdim + 2 * HOWMANY + 8, device=local_rank, rank=rank,
                              nranks=world, nccl_uid=uid_bytes, n_global=n, row_offset=shard.row_offset)
@@ -346,6 +379,7 @@ def run_ours(a):
         dist.all_reduce(ll)
         launches = int(ll.item())
     value = numops / t_dev
+    parity = check_parity(a, vals, numops // a.steps, "device-resident path")     # every rank: values are replicated
 
     # roofline of the dominant kernel (fused Gram-Schmidt sweep) + SpMV beside it
     def prof(cls):
@@ -396,7 +430,7 @@ def run_ours(a):
                                      loc - n_loc - lo + shard.row_offset + n_loc))
             ci[:] = glob.astype(np.int32)
             import torch
-            uid2 = sharding.broadcast_nccl_uid(dist, lib, torch.device("cuda", local_rank))
+            uid2 = sharding.broadcast_nccl_uid(dist, lib)
         xh, pxh = pinned_array(lib, n_loc, np.float64)
         x0.to_host(xh)
         # the resident context is no longer needed: closing it returns its slab to the library's
@@ -423,6 +457,7 @@ def run_ours(a):
         barrier()
         te = time.perf_counter() - t0
         assert np.allclose(v2, vals, rtol=1e-10), (v2, vals)
+        parity_e2e = check_parity(a, v2, ops // a.steps, "host-buffer (e2e) path")
         if dist is not None:
             import torch
             tt = torch.tensor([te, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
@@ -433,7 +468,10 @@ def run_ours(a):
         e2e = {"value": ops / te, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1000.0 * te / a.steps,
                "path": "kk.eigsolve(csr_host_arrays, x0_host, ...) on every rank: ctx create + H2D (pinned) + solve "
-                       "+ D2H (pinned); wall clock, max over ranks; bytes summed over ranks"}
+                       "+ D2H (pinned); wall clock, max over ranks; bytes summed over ranks.  Steady state: the "
+                       "library's block cache (slab, CSR arrays) and the per-process NCCL communicator are warm "
+                       "from the previous call, so cudaMalloc / ncclCommInitRank of a first call are not in it",
+               "parity": parity_e2e}
         for p in (prp, pci, pva, pxh, *[o[1] for o in outs]):
             lib.b2k_pinned_free(p)
 
@@ -450,6 +488,15 @@ def run_ours(a):
                          f"1..{a.cpu_steps + 1}) of the same n={n} job in {dt:.1f} s; oracle/krylov_oracle.py "
                          f"(restated reference; n-length loops: {backend}); no Julia in the image"}
 
+    extras = None
+    if a.extra:
+        if not a.no_e2e:
+            pass                                   # the resident context was closed before the e2e leg
+        else:
+            ctx.close()
+        lib.b2k_cache_release()                    # config 5 needs 31 GB on one GPU: start from a clean allocator
+        extras = other_configs(kk, a, rank, world, local_rank, dist)
+
     if rank == 0:
         line = {
             "metric": "eigsolve_lanczos_operator_applications_per_sec", "value": value, "unit": "it/s",
@@ -457,8 +504,8 @@ def run_ours(a):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(a),
             "numops_per_step": numops // a.steps, "wall_s": wall,
-            "ritz_values": [float(v) for v in vals[:HOWMANY]],
-            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
+            "ritz_values": [float(v) for v in vals[:HOWMANY]], "parity": parity,
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "other_configs": extras,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -466,6 +513,139 @@ def run_ours(a):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------- other configs
+def other_configs(kk, a, rank, world, local_rank, dist):
+    """BASELINE.json configs[2..4] on the same box, after the headline measurement: one warm-up + one timed job
+    each (CUDA events on the library stream, max over ranks), with the parity evidence that exists at full size:
+    the oracle's committed results (tests/golden/fullsize.json) for config 3, residual identities evaluated on the
+    device for config 4, the closed-form lower bound + cross-N agreement for config 5."""
+    from krylovkit_jl_b200 import sharding
+    lib = kk._lib.load()
+    want = [w for w in a.extra.split(",") if w]
+    gold = {}
+    gp = os.path.join(ROOT, "tests", "golden", "fullsize.json")
+    if os.path.exists(gp):
+        gold = json.load(open(gp))
+    out = {}
+
+    def make_ctx(n_lines, line, ncols, dtype=np.float64):
+        n = n_lines * line
+        if world == 1:
+            return kk.B200Context(n, ncols, dtype=dtype, device=local_rank), n
+        import torch
+        u = sharding.broadcast_nccl_uid(dist, lib)
+        sh = sharding.shard_grid_lines(line, n_lines, rank, world)
+        return kk.B200Context(sh.n_local, ncols, dtype=dtype, device=local_rank, rank=rank, nranks=world, nccl_uid=u,
+                              n_global=n, row_offset=sh.row_offset), n
+
+    def timed(ctx, fn):
+        fn()
+        lib.b2k_device_sync()
+        if dist is not None:
+            dist.barrier()
+        lib.b2k_timer_start(ctx.h)
+        res = fn()
+        ms = C.c_double()
+        lib.b2k_timer_stop(ctx.h, C.byref(ms))
+        t = ms.value / 1000.0
+        if dist is not None:
+            import torch
+            tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return res, t
+
+    if "c3" in want:
+        nx, ny, kd = 4000, 2500, 40
+        ctx, n = make_ctx(ny, nx, kd + 16)
+        op = kk.B200CSR.stencil(ctx, nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0))
+        ones = ctx.full(1.0)
+        b = kk.apply(op, ones)
+        rec = {"workload": f"linsolve(GMRES, krylovdim={kd}) on the {n}x{n} convection-diffusion CSR (5-point, "
+                           "nonsymmetric), b = A*1, x0 = 0, 5 restart cycles (tol -> 0: fixed work)"}
+        for name, orth, gname in (("cgs2", kk.cgs2, "c3"), ("mgs2_reference_default", kk.mgs2, None)):
+            alg = kk.GMRES(orth=orth, krylovdim=kd, maxiter=5, tol=1e-300, verbosity=0)
+            (x, info), t = timed(ctx, lambda: kk.linsolve(op, b, None, alg))
+            chk = kk.apply(op, x)
+            chk.add_(info.residual, 1.0).add_(b, -1.0)          # b = A x + r  (test/linsolve.jl:230)
+            r = {"numops": info.numops, "numiter": info.numiter, "ms": 1000 * t, "value": info.numops / t,
+                 "unit": "it/s", "normres": float(info.normres), "||A x + r - b||/||b||": chk.norm() / b.norm()}
+            g = gold.get(gname, {}).get("after_cycles", {}).get("5") if gname else None
+            if g:
+                rel = abs(info.normres - g["normres"]) / g["normres"]
+                xn = x.norm()
+                r["parity"] = {"against": f"tests/golden/fullsize.json:{gname}:after_cycles[5] (oracle at full size)",
+                               "numops_oracle": g["numops"], "normres_rel_diff": rel,
+                               "x_norm_rel_diff": abs(xn - g["x_norm"]) / g["x_norm"],
+                               "ok": bool(info.numops == g["numops"] and rel <= 1e-8 and abs(xn - g["x_norm"]) <= 1e-10 * g["x_norm"])}
+                if not r["parity"]["ok"]:
+                    raise AssertionError(f"config 3: parity with the oracle lost: {r}")
+            rec[name] = r
+            del x, info, chk
+        out["c3"] = rec
+        ctx.close()
+
+    if "c4" in want and world == 1:
+        m, nn, kd = 2_000_000, 512, 30
+        ctx = kk.B200Context(m, kd + 24, dtype=np.float32, device=local_rank)
+        sv = ctx.add_space(nn, kd + 24, sharded=False)
+        op = kk.B200Dense.splitmix(ctx, m, nn, SEED, sv)
+        u0 = ctx.splitmix(SEED + 1)
+        rec = {"workload": f"svdsolve(GKL, krylovdim={kd}, tol=1e-5) on the dense {m}x{nn} Float32 matrix (splitmix "
+                           "entries in (-0.5, 0.5)), 6 triplets :LR",
+               "note": "with ClassicalGramSchmidt2 the Float32 recurrence loses orthogonality on this clustered spectrum "
+                       "(in the CPU oracle too) and the driver raises B200Error; reported with the reference's default "
+                       "orthogonalizer and with the iterative-refinement one its Float32 tests use (test/runtests.jl:18)"}
+        for name, orth in (("mgs2_reference_default", kk.mgs2), ("cgsr_eta0.75", kk.ClassicalGramSchmidtIR(eta=0.75)),
+                           ("cgs2", kk.cgs2)):
+            alg = kk.GKL(orth=orth, krylovdim=kd, maxiter=100, tol=1e-5, verbosity=0)
+            try:
+                (S, Lv, Rv, info), t = timed(ctx, lambda: kk.svdsolve(op, u0, 6, "LR", alg))
+            except kk.B200Error as e:
+                rec[name] = {"raised": "B200Error: " + str(e)[:160]}
+                continue
+            res = []
+            for i in range(3):                                  # A v = s u + r, A' u = s v on the device
+                w = kk.apply_normal(op, Rv[i])
+                w.add_(Lv[i], -float(S[i]))
+                z = kk.apply_adjoint(op, Lv[i])
+                z.add_(Rv[i], -float(S[i]))
+                res.append([float(w.norm() / S[i]), float(z.norm() / S[i])])
+            rec[name] = {"numops": info.numops, "numiter": info.numiter, "converged": info.converged, "ms": 1000 * t,
+                         "value": info.numops / t, "unit": "it/s", "sigma": [float(v) for v in S[:6]],
+                         "rel_residuals(Av-su, A'u-sv)": res}
+            del Lv, Rv, info
+        out["c4"] = rec
+        ctx.close()
+
+    if "c5" in want:
+        nx, ny, nz, kd = 625, 500, 256, 30
+        ctx, n = make_ctx(nz, nx * ny, kd + 14)
+        op = kk.B200CSR.stencil(ctx, nx, ny, nz, (6.0, -1, -1, -1, -1, -1, -1))
+        x0 = ctx.splitmix(SEED)
+        alg = kk.Lanczos(orth=kk.cgs2, krylovdim=kd, maxiter=3, tol=0.0, verbosity=0)
+        (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, 4, "SR", alg))
+        del vecs
+        lam_min = 6.0 - 2.0 * (np.cos(np.pi / (nx + 1)) + np.cos(np.pi / (ny + 1)) + np.cos(np.pi / (nz + 1)))
+        rec = {"workload": f"eigsolve(Lanczos, :SR, 4) on the {n}x{n} 7-point Laplacian ({nx}x{ny}x{nz}), Float64, "
+                           f"krylovdim={kd}, orth=cgs2, 3 restart cycles, rows sharded by z-planes over {world} GPU(s)",
+               "numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
+               "ritz": [float(v) for v in vals[:4]], "closed_form_lambda_min": float(lam_min),
+               "ritz_above_lambda_min": bool(vals[0] >= lam_min * (1 - 1e-12))}
+        g = gold.get("c5", {}).get("after_cycles", {}).get("3")
+        if g:
+            ref = np.array(g["ritz"])
+            rel = float(np.max(np.abs(np.array(vals[:4]) - ref) / np.abs(ref)))
+            rec["parity"] = {"against": "tests/golden/fullsize.json:c5:after_cycles[3] (oracle at full size)",
+                             "max_rel_diff_ritz": rel, "numops_oracle": g["numops"],
+                             "ok": bool(rel <= 1e-10 and info.numops == g["numops"])}
+            if not rec["parity"]["ok"]:
+                raise AssertionError(f"config 5: parity with the oracle lost: {rec}")
+        out["c5"] = rec
+        ctx.close()
+    return out
 
 
 def main():

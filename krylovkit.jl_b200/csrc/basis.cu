@@ -44,7 +44,44 @@ struct FusedParams {
     unsigned barrier_base;   // counter value before this launch
     const int* stop;         // device flag: when set, the launch does nothing (see FinalizeParams)
     FinalizeParams fin;      // optional in-kernel finalisation by the last CTA
+    PeerStep ps;             // row-sharded contexts: cross-GPU exchanges of this launch (ps.on == 0: one GPU)
 };
+
+// Phase boundary of a row-sharded launch.  The local grid barrier and the cross-GPU sum of the projection
+// coefficients are one step: the last CTA of this rank to arrive reduces the rank's per-CTA partials (same
+// fixed order as on one GPU) and stores them into EVERY rank's window; every CTA of every rank then waits, in
+// its own window, for the nranks contributions — which also proves that all local CTAs have arrived.  One
+// NVLink store latency instead of a kernel boundary + ncclAllReduce + a kernel boundary.
+template <typename T>
+__device__ __forceinline__ void peer_boundary(const FusedParams<T>& fp, int i, uint8_t* smem) {
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    int* flag = reinterpret_cast<int*>(smem + OFF_RED + 256);
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(fp.barrier, 1u);
+        *flag = (old == fp.barrier_base + (unsigned)(i + 1) * gridDim.x - 1u);
+    }
+    __syncthreads();
+    const PeerDev& pd = fp.ps.pd;
+    const unsigned long long seq = fp.ps.seq_coef[i];
+    const int tid = threadIdx.x;
+    if (*flag && tid < NCONS) {
+        __threadfence();
+        const int k = fp.ph[i].k;
+        const int L = coef_lanes(k);
+        const int j = tid / L, l = tid % L;
+        const bool valid = j < k;
+        const double a = coef_colsum(fp.ph[i].part_h, gridDim.x, B2K_KSTRIDE, j, l, L, valid);
+        if (valid && l == 0)
+            for (int p = 0; p < pd.nranks; ++p) peer_slot(pd, p, PEER_CH_COEF, seq, pd.rank)[j] = a;
+        __threadfence_system();
+        named_bar_sync(1, NCONS);
+        if (tid < pd.nranks) st_release_sys_u64(peer_flag(pd, tid, PEER_CH_COEF, seq, pd.rank), seq);
+    }
+    peer_wait(pd, PEER_CH_COEF, seq, tid);
+    __syncthreads();
+}
 
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -62,6 +99,10 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
     pipe_setup(sm, ragged);
     Pipe st;
     const bool prod = threadIdx.x >= NCONS;
+    if (fp.ps.on && fp.ps.seq_alpha) {       // <v, A v>: every rank's partial must be in my window
+        peer_wait(fp.ps.pd, PEER_CH_ALPHA, fp.ps.seq_alpha, threadIdx.x);
+        __syncthreads();
+    }
     for (int i = 0; i < fp.nph; ++i) {
         if (prod) {
             producer_phase<T>(fp.ph[i], cl, sm, st);
@@ -70,13 +111,17 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
             else if (fp.kind[i] == 1) consumer_phase<T, true, true>(fp.ph[i], sm, st);
             else consumer_phase<T, true, false>(fp.ph[i], sm, st);
         }
-        if (i + 1 < fp.nph) grid_barrier(fp.barrier, fp.barrier_base + (unsigned)(i + 1) * gridDim.x);
+        if (i + 1 < fp.nph) {
+            if (fp.ps.on) peer_boundary<T>(fp, i, smem);
+            else grid_barrier(fp.barrier, fp.barrier_base + (unsigned)(i + 1) * gridDim.x);
+        }
     }
     if (fp.fin.enabled && !prod) {
         // the last CTA to finish (ticket) reduces the per-CTA partials and publishes the step's scalars
         double* sh = reinterpret_cast<double*>(smem + OFF_RED);
         int* flag = reinterpret_cast<int*>(smem + OFF_RED + 256);
-        __threadfence();
+        if (fp.ps.on) __threadfence_system();      // halo rows stored into the neighbours' windows
+        else __threadfence();
         named_bar_sync(1, NCONS);
         if (threadIdx.x == 0) {
             const unsigned t = atomicInc(fp.fin.ticket, gridDim.x - 1);
@@ -85,7 +130,7 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
         named_bar_sync(1, NCONS);
         if (*flag) {
             __threadfence();
-            finalize_block(fp.fin, threadIdx.x, sh);
+            finalize_block(fp.fin, threadIdx.x, sh, fp.ps.on ? &fp.ps : nullptr);
         }
     }
 }
@@ -98,6 +143,7 @@ k_finalize(const double* __restrict__ A, const double* __restrict__ B, const dou
     FinalizeParams f;
     f.A = A; f.B = B; f.N = N; f.G = G; f.stride = stride; f.k = k; f.res = res; f.off = off; f.noff = noff;
     f.rec = nullptr; f.alpha_col = -1; f.tol = 0.0; f.stop = nullptr; f.ticket = nullptr; f.enabled = 1;
+    f.peer = 0; f.G_local = G;
     finalize_block(f, threadIdx.x, sh);
 }
 
@@ -1170,17 +1216,24 @@ bool chain_ok(const b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, int32_t
     int64_t op_rows = 0, op_cols = 0;
     int32_t op_kind = -1;
     if (b2k_op_info(op, &op_rows, &op_cols, nullptr, &op_kind) != B2K_OK) return false;
-    if (ctx->nranks > 1 || op_kind != 0 || beta_old == 0.0 || !(beta_old == beta_old)) return false;
+    if (op_kind != 0 || beta_old == 0.0 || !(beta_old == beta_old)) return false;
     const int32_t sp = B2K_VEC_SPACE(cols[k]);
     if (sp < 0 || sp >= (int32_t)ctx->spaces.size()) return false;
     const B2kSpace& s = ctx->spaces[sp];
-    if (op_rows != s.n || op_cols != s.n) return false;
-    return fused_ok(ctx, k + nsteps, s.sharded, ctx->dtype);
+    if (ctx->nranks > 1) {
+        // row-sharded: every exchange of the step goes through the NVLink peer window (no NCCL, no extra launch)
+        if (!s.sharded || !b2k_peer_ok(ctx) || !b2k_op_has_peer_halo(op) || op_rows != s.n) return false;
+    } else if (op_rows != s.n || op_cols != s.n) {
+        return false;
+    }
+    const int C = ctx->dtype == B2K_F64 ? 8 : 16;
+    const int K1 = k + nsteps;
+    return (K1 + C - 1) / C <= NS && K1 <= MAXCH * C && K1 <= PEER_SLOT;
 }
 
 template <typename T>
 int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, const VecRef& vprev,
-                      const VecRef& rv, double* rec_prev, double* rec, double tol) {
+                      const VecRef& rv, double* rec_prev, double* rec, double tol, const PeerStep* psp) {
     const int grid = grid_for_rows<T>(ctx, pn.n);
     ColList cl;
     for (int i = 0; i < K1; ++i) cl.c[i] = pn.idx[i];
@@ -1203,6 +1256,31 @@ int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, c
     fp.fin.alpha_col = K1 - 1; fp.fin.tol = tol;
     fp.fin.stop = reinterpret_cast<int*>(ctx->d_sync + B2K_SYNC_STOP);
     fp.fin.ticket = ctx->d_sync + B2K_SYNC_GSFIN; fp.fin.enabled = 1;
+    fp.fin.peer = 0; fp.fin.G_local = grid;
+    if (psp && psp->on) {
+        const PeerStep& ps = *psp;
+        fp.ps = ps;
+        char* win = b2k_peer_local(ctx);
+        auto slot = [&](int ch, unsigned long long seq) {
+            return reinterpret_cast<double*>(win + PEER_OFF_SLOTS) + (size_t)((ch * 2 + (int)(seq & 1ull)) * PEER_MAXR) * PEER_SLOT;
+        };
+        // <v, A v>: the per-rank partials the SpMV published (rank order)
+        fp.ph[0].c2_dev = slot(PEER_CH_ALPHA, ps.seq_alpha);
+        fp.ph[0].c2_sets = ps.pd.nranks;
+        fp.ph[0].c2_stride = PEER_SLOT;
+        // projection coefficients: the per-rank sums in my window instead of the per-CTA partials
+        fp.ph[1].coef = slot(PEER_CH_COEF, ps.seq_coef[0]);
+        fp.ph[1].coef_sets = ps.pd.nranks;
+        fp.ph[1].coef_stride = PEER_SLOT;
+        fp.fin.A = fp.ph[1].coef; fp.fin.G = ps.pd.nranks; fp.fin.stride = PEER_SLOT; fp.fin.peer = 1;
+        // rows the neighbours need for their next SpMV leave with the final store
+        if (ps.seq_halo) {
+            fp.ph[1].send_lo = ps.send_lo;
+            fp.ph[1].send_hi = ps.send_hi;
+            fp.ph[1].halo_dn = ps.send_lo ? reinterpret_cast<T*>(ps.pd.win[ps.pd.rank - 1] + ps.dn_off) : nullptr;
+            fp.ph[1].halo_up = ps.send_hi ? reinterpret_cast<T*>(ps.pd.win[ps.pd.rank + 1] + ps.up_off) : nullptr;
+        }
+    }
     const int pr = b2k_prof_begin(ctx, 1, (2.0 * K1 + 3.0) * sizeof(T) * (double)pn.n);
     B2K_TRY(launch_fused<T>(ctx, fp, cl, grid));
     b2k_prof_end(ctx, pr);
@@ -1225,6 +1303,8 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
     std::vector<b2k_vec> touched, Vh, Wh;
     touched.push_back(cols[k]);
     int32_t enq = 0, rc = B2K_OK;
+    const bool dist = ctx->nranks > 1;
+    unsigned long long halo_seq = 0;
     for (int32_t i = 0; i < nsteps; ++i) {
         const int32_t K = k + i;                 // basis size before this step's push!
         const b2k_vec R = cols[K];
@@ -1244,18 +1324,33 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
         double* rec_prev = rec0 + (size_t)B2K_REC * i;
         double* rec = rec0 + (size_t)B2K_REC * (i + 1);
         SpmvFuse fz;
+        memset(&fz, 0, sizeof(fz));
         fz.xscale = rec_prev + 3;
         fz.vout = rV.ptr;
         fz.stop = d_stop;
         fz.dot_self = 1;
+        PeerStep ps;
+        memset(&ps, 0, sizeof(ps));
+        if (dist) {
+            ps.on = 1;
+            ps.pd = *b2k_peer_dev(ctx);
+            ps.seq_alpha = b2k_peer_next_seq(ctx, PEER_CH_ALPHA);
+            ps.seq_coef[0] = b2k_peer_next_seq(ctx, PEER_CH_COEF);
+            ps.seq_norm = b2k_peer_next_seq(ctx, PEER_CH_NORM);
+            fz.seq_alpha = ps.seq_alpha;
+            fz.seq_halo = halo_seq;                    // 0 on the first step: the apply pushes r's boundary rows
+            halo_seq = b2k_peer_next_seq(ctx, 4);      // this step's Gram-Schmidt launch pushes w's
+            rc = b2k_op_peer_halo(ctx, op, halo_seq, &ps);
+            if (rc != B2K_OK) break;
+        }
         rc = b2k_enqueue_apply_fused(ctx, op, rR, rW, 0.0, 1.0, false, nullptr, rec + 0, &fz);
         if (rc != B2K_OK) break;
         cols[K] = V;                             // the normalised residual is the new basis vector ...
         Panel pn;
         rc = make_panel(ctx, cols, K + 1, &pn);
         if (rc != B2K_OK) break;
-        rc = f64 ? chain_step_gs<double>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol)
-                 : chain_step_gs<float>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol);
+        rc = f64 ? chain_step_gs<double>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol, &ps)
+                 : chain_step_gs<float>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol, &ps);
         if (rc != B2K_OK) break;
         cols[K + 1] = W;                         // ... and w the new residual
         Vh.push_back(V);

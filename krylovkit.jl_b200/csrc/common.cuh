@@ -23,6 +23,7 @@ constexpr int B2K_REC          = 8;        // doubles per step record (tsk.cuh F
 // in-kernel Gram-Schmidt finalisation, [4] breakdown flag of a chained Lanczos batch
 constexpr int B2K_SYNC_GSFIN   = 2;
 constexpr int B2K_SYNC_STOP    = 4;
+constexpr int B2K_SYNC_HALO    = 5;        // ticket of k_halo_push
 
 struct B2kSpace {
     void*   base   = nullptr;   // device pointer, column-major n x ncols, leading dim ld
@@ -174,6 +175,10 @@ struct SpmvFuse {
     void* vout;
     const int* stop;
     int dot_self;
+    // row-sharded contexts with the peer window: sequence number under which <x, y> is published to all ranks
+    // (0: not published), and the halo sequence number a previous kernel has already pushed this operand's
+    // boundary rows under (0: the apply pushes them itself)
+    unsigned long long seq_alpha, seq_halo;
 };
 
 int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
@@ -186,13 +191,63 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
 int32_t b2k_basis_init(b2k_ctx* ctx);
 int32_t b2k_spmv_init(b2k_ctx* ctx);
 
-// dist (dist.cu)
+// ----------------------------------------------------------------------------------
+// NVLink peer window (dist.cu).  Every rank owns one cudaMalloc'ed window that all other ranks of the node
+// map through CUDA IPC.  It carries the latency-bound exchanges of the Krylov step without NCCL and without
+// extra launches: a rank WRITES its contribution into every peer's window (one-way stores over NVLink, then a
+// release flag), and READS only its own window (local polling), so a reduction costs one NVLink write latency.
+//   channel 0: <v, A v> partial of the SpMV          channel 1: projection coefficients of a Gram-Schmidt sweep
+//   channel 2: ||w||^2 partial                        channel 3: generic small-vector all-reduce
+// Slots and flags are double-buffered by the parity of the operation's sequence number (a rank can be at most
+// one operation ahead of a peer on a channel, because the next operation needs that peer's contribution).
+// The rest of the window is a heap for the receive side of halo exchanges (operators allocate from it).
+// ----------------------------------------------------------------------------------
+constexpr int    PEER_MAXR  = 16;
+constexpr int    PEER_SLOT  = 1024;                      // doubles per (channel, parity, source rank)
+constexpr int    PEER_NCH   = 4;
+constexpr int    PEER_CH_ALPHA = 0, PEER_CH_COEF = 1, PEER_CH_NORM = 2, PEER_CH_GEN = 3;
+constexpr size_t PEER_OFF_FLAGS  = 0;                    // u64 [NCH][2][MAXR], then halo flags u64 [2][2]
+constexpr size_t PEER_OFF_HFLAGS = 8 * (size_t)(PEER_NCH * 2 * PEER_MAXR);
+constexpr size_t PEER_OFF_SLOTS  = 4096;
+constexpr size_t PEER_OFF_HEAP   = PEER_OFF_SLOTS + 8 * (size_t)(PEER_NCH * 2 * PEER_MAXR) * PEER_SLOT;
+
+struct PeerDev {
+    char* win[PEER_MAXR];      // win[p] = rank p's window as mapped in THIS process (win[rank] = own)
+    int rank, nranks;
+};
+// what one kernel launch needs to know about the exchanges it takes part in (all seq == 0: single GPU)
+struct PeerStep {
+    PeerDev pd;
+    unsigned long long seq_alpha;   // GS kernel: wait for / SpMV: publish <v, A v>
+    unsigned long long seq_coef[2]; // GS kernel: phase boundaries
+    unsigned long long seq_norm;    // GS kernel: finaliser
+    unsigned long long seq_halo;    // GS kernel: halo rows pushed by the update phase / SpMV: wait before gathering
+    // halo push (update phase of the GS kernel, or k_halo_push): my first send_lo rows go to rank-1's window at
+    // dn_off, my last send_hi rows to rank+1's window at up_off (byte offsets from the window base)
+    long long send_lo, send_hi;
+    size_t dn_off, up_off;
+    int wait_lo, wait_hi;           // SpMV: my lo / hi halo is filled by rank-1 / rank+1
+    int on;
+};
+
+int32_t b2k_op_peer_halo(const b2k_ctx* ctx, const b2k_op* op, unsigned long long seq, PeerStep* ps);
+bool    b2k_op_has_peer_halo(const b2k_op* op);
+
 int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid);
 void    b2k_nccl_destroy(b2k_ctx* ctx);
 int32_t b2k_nccl_allreduce_f64(b2k_ctx* ctx, double* dptr, int32_t count);
 // NVLink peer-memory all-reduce of a small vector (dist.cu); b2k_peer_ok says whether it is usable
 bool    b2k_peer_ok(const b2k_ctx* ctx);
+bool    b2k_has_nccl(const b2k_ctx* ctx);
 int32_t b2k_peer_allreduce(b2k_ctx* ctx, double* dptr, int32_t count);
+// device view of the windows + host-side sequence counters (identical on every rank: SPMD call order)
+const PeerDev* b2k_peer_dev(const b2k_ctx* ctx);
+unsigned long long b2k_peer_next_seq(b2k_ctx* ctx, int channel);      // channel 4 = halo
+// symmetric allocation from the window heap (same offset on every rank); returns SIZE_MAX if it does not fit
+size_t  b2k_peer_heap_alloc(b2k_ctx* ctx, size_t bytes);
+char*   b2k_peer_local(const b2k_ctx* ctx);
+// host-side all-gather of small blobs over the node-local rendezvous (no NCCL needed)
+int32_t b2k_host_allgather(b2k_ctx* ctx, const void* mine, size_t bytes, void* all);
 // grouped neighbour exchange; up/dn = peer ranks or -1
 int32_t b2k_nccl_halo_exchange(b2k_ctx* ctx, int up, int dn, const void* send_up, size_t send_up_bytes,
                                void* recv_dn, size_t recv_dn_bytes, const void* send_dn,
@@ -203,6 +258,54 @@ int32_t b2k_nccl_allgather(b2k_ctx* ctx, const void* sendbuf, void* recvbuf, siz
 // device helpers
 // ----------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double* peer_slot(const PeerDev& pd, int dst, int ch, unsigned long long seq, int src) {
+    return reinterpret_cast<double*>(pd.win[dst] + PEER_OFF_SLOTS) +
+           (size_t)((ch * 2 + (int)(seq & 1ull)) * PEER_MAXR + src) * PEER_SLOT;
+}
+__device__ __forceinline__ unsigned long long* peer_flag(const PeerDev& pd, int dst, int ch, unsigned long long seq,
+                                                         int src) {
+    return reinterpret_cast<unsigned long long*>(pd.win[dst] + PEER_OFF_FLAGS) +
+           ((ch * 2 + (int)(seq & 1ull)) * PEER_MAXR + src);
+}
+// halo flags of a window: [parity][0 = written by rank-1 (my lo halo), 1 = written by rank+1 (my hi halo)]
+__device__ __forceinline__ unsigned long long* peer_hflag(const PeerDev& pd, int dst, unsigned long long seq, int side) {
+    return reinterpret_cast<unsigned long long*>(pd.win[dst] + PEER_OFF_HFLAGS) + ((int)(seq & 1ull) * 2 + side);
+}
+// one thread per rank waits until that rank's contribution `seq` has landed in MY window (local polling);
+// the caller synchronises its threads afterwards
+__device__ __forceinline__ void peer_wait(const PeerDev& pd, int ch, unsigned long long seq, int tid) {
+    if (tid < pd.nranks) {
+        const unsigned long long* f = peer_flag(pd, pd.rank, ch, seq, tid);
+        while (ld_acquire_sys_u64(f) < seq) {
+        }
+    }
+}
+// single-thread publication of ONE double to every rank (SpMV dot epilogue, norm partial)
+__device__ __forceinline__ void peer_publish1(const PeerDev& pd, int ch, unsigned long long seq, double v) {
+    for (int p = 0; p < pd.nranks; ++p) peer_slot(pd, p, ch, seq, pd.rank)[0] = v;
+    __threadfence_system();
+    for (int p = 0; p < pd.nranks; ++p) st_release_sys_u64(peer_flag(pd, p, ch, seq, pd.rank), seq);
+}
+// rank-ordered sum of the `nranks` contributions to element j (identical bits on every rank)
+__device__ __forceinline__ double peer_sum1(const PeerDev& pd, int ch, unsigned long long seq, int j) {
+    double a = 0.0;
+    for (int p = 0; p < pd.nranks; ++p) a += ld_volatile_f64(peer_slot(pd, pd.rank, ch, seq, p) + j);
+    return a;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

@@ -1,6 +1,7 @@
 // ctx.cu — context, vector spaces (slabs), handle bookkeeping, scalar plumbing.
 #include "common.cuh"
 #include <cstdarg>
+#include <algorithm>
 
 std::string g_b2k_create_error;
 
@@ -452,7 +453,12 @@ extern "C" int32_t b2k_vec_zero(b2k_ctx* ctx, b2k_vec v) {
 
 int32_t b2k_allreduce(b2k_ctx* ctx, double* dptr, int32_t count, int32_t sharded) {
     if (ctx->nranks > 1 && sharded) {
-        if (b2k_peer_ok(ctx) && count <= 1016) return b2k_peer_allreduce(ctx, dptr, count);
+        if (b2k_peer_ok(ctx) && count <= PEER_SLOT) return b2k_peer_allreduce(ctx, dptr, count);
+        if (b2k_peer_ok(ctx) && !b2k_has_nccl(ctx)) {          // peer-only transport: in slot-sized pieces
+            for (int32_t off = 0; off < count; off += PEER_SLOT)
+                B2K_TRY(b2k_peer_allreduce(ctx, dptr + off, std::min<int32_t>(PEER_SLOT, count - off)));
+            return B2K_OK;
+        }
         return b2k_nccl_allreduce_f64(ctx, dptr, count);
     }
     return B2K_OK;

@@ -1,4 +1,5 @@
-// dist.cu — NCCL plumbing for row-sharded contexts (one process per GPU).
+// dist.cu — transports of row-sharded contexts (one process per GPU): the NVLink peer window (CUDA IPC, the
+// default for every latency-bound exchange of the Krylov step) and NCCL (bootstrap-free fallback, bulk gathers).
 // NCCL is resolved at run time with dlopen so that (a) the library has no link-time NCCL
 // dependency and loads on machines without it, and (b) inside a PyTorch process we bind to
 // the very libnccl.so.2 torch already loaded instead of a second copy.
@@ -6,7 +7,12 @@
 // nearest-neighbour halo exchange for the SpMV.
 #include "common.cuh"
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdlib>
+#include <ctime>
 #include <vector>
 
 // minimal NCCL ABI (stable since 2.x)
@@ -17,26 +23,32 @@ enum { ncclSuccess_ = 0 };
 enum { ncclInt8_ = 0, ncclChar_ = 0, ncclFloat64_ = 8 };
 enum { ncclSum_ = 0 };
 
-// Small-vector all-reduce over NVLink peer memory (CUDA IPC): every rank publishes its k
-// coefficients + a sequence flag in its own buffer, reads the peers' buffers directly over
-// NVLink and sums them in rank order (deterministic, identical on all ranks).  One ~5 us
-// kernel instead of a ~20-25 us NCCL call for the three latency-bound reductions of a
-// Lanczos step.  Falls back to NCCL if IPC mapping is unavailable.
-constexpr int PEER_STRIDE = 1024;                 // doubles per slot
-constexpr int PEER_MAXK = PEER_STRIDE - 8;
-constexpr int PEER_MAXR = 16;
-struct PeerArgs {
-    double* ptr[PEER_MAXR];     // ptr[p] = rank p's buffer (2 slots + 2 flags), mapped into this process
-    int rank, nranks;
+// Node-local rendezvous: a POSIX shared-memory segment named after the job's 128-byte unique id.  It carries
+// the CUDA IPC handles (and other small blobs, b2k_host_allgather) between the ranks of one node, so the peer
+// window can be set up without NCCL — and with it, two ranks can share ONE GPU (NCCL refuses that), which is
+// how the sharded path is tested on a single-GPU box.
+constexpr size_t RV_BLOB = 4096;
+struct RvShm {
+    unsigned long long arrive;
+    unsigned long long pad[7];
+    unsigned char data[2][PEER_MAXR][RV_BLOB];
+};
+struct Rendezvous {
+    RvShm* shm = nullptr;
+    char name[64] = {0};
+    unsigned long long round = 0;
+    int rank = 0, nranks = 1;
 };
 
 struct B2kNccl {
     void* lib = nullptr;
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;          // nullptr: NCCL not in use (B2K_NO_NCCL=1 or libnccl missing)
+    Rendezvous rv;
     bool peer_ok = false;
-    double* peer_local = nullptr;
-    PeerArgs peer;
-    unsigned long long peer_seq = 0;
+    char* win_local = nullptr;          // my window (cudaMalloc)
+    size_t win_bytes = 0, heap_used = 0;
+    PeerDev pd;
+    unsigned long long seq[5] = {0, 0, 0, 0, 0};   // channels 0..3 + halo
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -91,98 +103,150 @@ extern "C" int32_t b2k_nccl_unique_id(void* uid128) {
     return B2K_OK;
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
+// ------------------------------------------------------------------ rendezvous ----
+static int32_t rv_open(b2k_ctx* ctx, Rendezvous* rv, const void* uid128, int rank, int nranks) {
+    unsigned long long h = 1469598103934665603ull;                 // FNV-1a of the unique id
+    const unsigned char* u = (const unsigned char*)uid128;
+    for (int i = 0; i < 128; ++i) { h ^= u[i]; h *= 1099511628211ull; }
+    snprintf(rv->name, sizeof(rv->name), "/b2k_%016llx_%d", h, nranks);
+    const int fd = shm_open(rv->name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return b2k_fail(ctx, B2K_ENCCL, "rendezvous: shm_open(%s) failed", rv->name);
+    if (ftruncate(fd, sizeof(RvShm)) != 0) {                       // new pages are zero-filled
+        close(fd);
+        return b2k_fail(ctx, B2K_ENCCL, "rendezvous: ftruncate failed");
+    }
+    void* p = mmap(nullptr, sizeof(RvShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return b2k_fail(ctx, B2K_ENCCL, "rendezvous: mmap failed");
+    rv->shm = (RvShm*)p;
+    rv->rank = rank;
+    rv->nranks = nranks;
+    rv->round = 0;
+    return B2K_OK;
 }
 
+static void rv_close(Rendezvous* rv) {
+    if (!rv->shm) return;
+    munmap(rv->shm, sizeof(RvShm));
+    rv->shm = nullptr;
+}
+
+// all[p*bytes ..] = rank p's blob.  A rank cannot be more than one round ahead of a peer (the next round
+// needs that peer's arrival), so two data buffers are enough.
+static int32_t rv_allgather(b2k_ctx* ctx, Rendezvous* rv, const void* mine, size_t bytes, void* all) {
+    if (!rv->shm) return b2k_fail(ctx, B2K_ENCCL, "rendezvous not open");
+    if (bytes > RV_BLOB) return b2k_fail(ctx, B2K_EINVAL, "rendezvous: blob too large");
+    const unsigned long long r = ++rv->round;
+    const int buf = (int)(r & 1ull);
+    memcpy(rv->shm->data[buf][rv->rank], mine, bytes);
+    __atomic_fetch_add(&rv->shm->arrive, 1ull, __ATOMIC_SEQ_CST);
+    const unsigned long long target = r * (unsigned long long)rv->nranks;
+    const time_t t0 = time(nullptr);
+    while (__atomic_load_n(&rv->shm->arrive, __ATOMIC_SEQ_CST) < target) {
+        usleep(50);
+        if (time(nullptr) - t0 > 120)
+            return b2k_fail(ctx, B2K_ENCCL, "rendezvous: timed out waiting for %d ranks (round %llu)", rv->nranks, r);
+    }
+    for (int p = 0; p < rv->nranks; ++p) memcpy((char*)all + (size_t)p * bytes, rv->shm->data[buf][p], bytes);
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ peer window ----
+// generic small-vector all-reduce (channel 3): publish, wait, sum in rank order (same bits on every rank)
 __global__ void __launch_bounds__(256)
-k_peer_allreduce(const __grid_constant__ PeerArgs a, double* __restrict__ inout, int count,
+k_peer_allreduce(const __grid_constant__ PeerDev pd, double* __restrict__ inout, int count,
                  unsigned long long seq) {
-    const int slot = (int)(seq & 1ull);
-    double* mine = a.ptr[a.rank] + (size_t)slot * PEER_STRIDE;
-    unsigned long long* myflag = reinterpret_cast<unsigned long long*>(a.ptr[a.rank] + 2 * PEER_STRIDE) + slot;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) mine[i] = inout[i];
+    for (int idx = threadIdx.x; idx < count * pd.nranks; idx += blockDim.x) {
+        const int p = idx / count, j = idx - p * count;
+        peer_slot(pd, p, PEER_CH_GEN, seq, pd.rank)[j] = inout[j];
+    }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(myflag, seq);
-    if (threadIdx.x < a.nranks && threadIdx.x != a.rank) {
-        const unsigned long long* pf =
-            reinterpret_cast<const unsigned long long*>(a.ptr[threadIdx.x] + 2 * PEER_STRIDE) + slot;
-        while (ld_acquire_sys(pf) < seq) {
-        }
-    }
+    if ((int)threadIdx.x < pd.nranks)
+        st_release_sys_u64(peer_flag(pd, threadIdx.x, PEER_CH_GEN, seq, pd.rank), seq);
+    peer_wait(pd, PEER_CH_GEN, seq, threadIdx.x);
     __syncthreads();
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        double acc = 0.0;
-        for (int p = 0; p < a.nranks; ++p)     // rank order: every rank computes the same bits
-            acc += ld_volatile_f64(a.ptr[p] + (size_t)slot * PEER_STRIDE + i);
-        inout[i] = acc;
-    }
+    for (int j = threadIdx.x; j < count; j += blockDim.x) inout[j] = peer_sum1(pd, PEER_CH_GEN, seq, j);
+}
+
+static size_t window_bytes() {
+    const char* e = getenv("B2K_PEER_WINDOW_MB");
+    const double mb = e ? atof(e) : 48.0;
+    return PEER_OFF_HEAP + (size_t)(mb * 1048576.0);
 }
 
 static void peer_setup(b2k_ctx* ctx, B2kNccl* n) {
-    // NOTE: every rank runs the same collectives below, whatever its local outcome.
+    // NOTE: every rank runs the same rendezvous rounds below, whatever its local outcome.
     n->peer_ok = false;
-    // opt-in (B2K_PEER=1): validated on 2 GPUs in r01 (bit-identical to the NCCL path, no speed-up
-    // at N=2); NCCL stays the default until it is measured at 8 GPUs.
-    const char* on = getenv("B2K_PEER");
-    if (!(on && on[0] == '1') || ctx->nranks > PEER_MAXR) return;   // same decision on every rank
+    const char* off = getenv("B2K_PEER");
+    if ((off && off[0] == '0') || ctx->nranks > PEER_MAXR || !n->rv.shm) return;   // same decision on every rank
     const int R = ctx->nranks;
-    const size_t bytes = sizeof(double) * (2 * PEER_STRIDE + 16);
+    n->win_bytes = window_bytes();
     int good = 1;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
-    if (cudaMalloc(&n->peer_local, bytes) != cudaSuccess) { cudaGetLastError(); n->peer_local = nullptr; good = 0; }
-    if (good) cudaMemset(n->peer_local, 0, bytes);
-    if (good && cudaIpcGetMemHandle(&mine, n->peer_local) != cudaSuccess) { cudaGetLastError(); good = 0; }
-    char* d_h = nullptr;
-    std::vector<cudaIpcMemHandle_t> all(R);
-    if (cudaMalloc(&d_h, sizeof(mine) * R + sizeof(double)) != cudaSuccess) return;   // cannot even talk
-    cudaMemcpy(d_h + sizeof(mine) * ctx->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
-    if (n->AllGather(d_h + sizeof(mine) * ctx->rank, d_h, sizeof(mine), ncclChar_, n->comm, ctx->stream) != ncclSuccess_) good = 0;
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemcpy(all.data(), d_h, sizeof(mine) * R, cudaMemcpyDeviceToHost);
+    if (cudaMalloc(&n->win_local, n->win_bytes) != cudaSuccess) { cudaGetLastError(); n->win_local = nullptr; good = 0; }
+    if (good && cudaMemset(n->win_local, 0, n->win_bytes) != cudaSuccess) { cudaGetLastError(); good = 0; }
+    if (good && cudaIpcGetMemHandle(&mine, n->win_local) != cudaSuccess) { cudaGetLastError(); good = 0; }
+    cudaDeviceSynchronize();
+    struct Blob { cudaIpcMemHandle_t h; int good; int pid; } me, all[PEER_MAXR];
+    memset(&me, 0, sizeof(me));
+    me.h = mine; me.good = good; me.pid = (int)getpid();
+    if (rv_allgather(ctx, &n->rv, &me, sizeof(me), all) != B2K_OK) return;
+    for (int p = 0; p < R; ++p) good = good && all[p].good;
+    memset(&n->pd, 0, sizeof(n->pd));
     for (int p = 0; p < R && good; ++p) {
-        if (p == ctx->rank) { n->peer.ptr[p] = n->peer_local; continue; }
+        if (p == ctx->rank) { n->pd.win[p] = n->win_local; continue; }
         void* q = nullptr;
-        if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        if (cudaIpcOpenMemHandle(&q, all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             cudaGetLastError();
             good = 0;
             break;
         }
-        n->peer.ptr[p] = (double*)q;
+        n->pd.win[p] = (char*)q;
     }
     // every rank must agree (and have finished mapping) before the first use
-    double* d_flag = reinterpret_cast<double*>(d_h + sizeof(mine) * R);
-    double hv = good ? 0.0 : 1.0;
-    cudaMemcpy(d_flag, &hv, sizeof(double), cudaMemcpyHostToDevice);
-    n->AllReduce(d_flag, d_flag, 1, ncclFloat64_, ncclSum_, n->comm, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemcpy(&hv, d_flag, sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(d_h);
-    n->peer.rank = ctx->rank;
-    n->peer.nranks = R;
-    n->peer_ok = (hv == 0.0);
-    n->peer_seq = 0;
+    int mygood = good, allgood[PEER_MAXR];
+    if (rv_allgather(ctx, &n->rv, &mygood, sizeof(int), allgood) != B2K_OK) return;
+    for (int p = 0; p < R; ++p) good = good && allgood[p];
+    n->pd.rank = ctx->rank;
+    n->pd.nranks = R;
+    n->peer_ok = good != 0;
+    n->heap_used = 0;
+    for (int c = 0; c < 5; ++c) n->seq[c] = 0;
+    if (!n->peer_ok && n->win_local) {
+        for (int p = 0; p < R; ++p)
+            if (p != ctx->rank && n->pd.win[p]) cudaIpcCloseMemHandle(n->pd.win[p]);
+        cudaFree(n->win_local);
+        n->win_local = nullptr;
+    }
 }
 
 bool b2k_peer_ok(const b2k_ctx* ctx) { return ctx->nccl && ctx->nccl->peer_ok; }
+bool b2k_has_nccl(const b2k_ctx* ctx) { return ctx->nccl && ctx->nccl->comm != nullptr; }
+const PeerDev* b2k_peer_dev(const b2k_ctx* ctx) { return &ctx->nccl->pd; }
+char* b2k_peer_local(const b2k_ctx* ctx) { return ctx->nccl->win_local; }
+unsigned long long b2k_peer_next_seq(b2k_ctx* ctx, int channel) { return ++ctx->nccl->seq[channel]; }
+
+size_t b2k_peer_heap_alloc(b2k_ctx* ctx, size_t bytes) {
+    B2kNccl* n = ctx->nccl;
+    if (!n || !n->peer_ok) return SIZE_MAX;
+    const size_t off = PEER_OFF_HEAP + ((n->heap_used + 255) & ~(size_t)255);
+    if (off + bytes > n->win_bytes) return SIZE_MAX;
+    n->heap_used = off + bytes - PEER_OFF_HEAP;
+    return off;
+}
+
+int32_t b2k_host_allgather(b2k_ctx* ctx, const void* mine, size_t bytes, void* all) {
+    if (!ctx->nccl) return b2k_fail(ctx, B2K_ENCCL, "host allgather on a context without a rendezvous");
+    return rv_allgather(ctx, &ctx->nccl->rv, mine, bytes, all);
+}
 
 int32_t b2k_peer_allreduce(b2k_ctx* ctx, double* dptr, int32_t count) {
     B2kNccl* n = ctx->nccl;
-    if (!n || !n->peer_ok || count > PEER_MAXK) return b2k_fail(ctx, B2K_ENCCL, "peer all-reduce unavailable");
-    ++n->peer_seq;
-    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(n->peer, dptr, count, n->peer_seq);
+    if (!n || !n->peer_ok || count > PEER_SLOT) return b2k_fail(ctx, B2K_ENCCL, "peer all-reduce unavailable");
+    const unsigned long long seq = ++n->seq[PEER_CH_GEN];
+    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(n->pd, dptr, count, seq);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;
 }
@@ -203,16 +267,35 @@ int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid) {
     }
     if (!uid) return b2k_fail(ctx, B2K_EINVAL, "ctx_create_dist: nccl_uid is NULL");
     B2kNccl* n = new B2kNccl();
-    int32_t rc = load_nccl(ctx, n);
-    if (rc != B2K_OK) {
-        delete n;
-        return rc;
-    }
-    ncclUniqueId id;
-    memcpy(&id, uid, sizeof(id));
     ctx->nccl = n;
-    NCCL_CK(ctx, n, n->CommInitRank(&n->comm, ctx->nranks, id, ctx->rank));
+    // B2K_NO_NCCL=1: peer windows only (the uid is then just a 128-byte job-unique token).  That is the mode
+    // in which several ranks may share one GPU.
+    const char* nonccl = getenv("B2K_NO_NCCL");
+    const bool want_nccl = !(nonccl && nonccl[0] == '1');
+    int32_t rc = rv_open(ctx, &n->rv, uid, ctx->rank, ctx->nranks);
+    if (rc != B2K_OK) { ctx->nccl = nullptr; delete n; return rc; }
+    {   // one round proves that every rank has mapped the segment; its name can then go away (the mapping
+        // stays valid), so nothing is left behind in /dev/shm even though the object is cached for the process
+        int pids[PEER_MAXR], me = (int)getpid();
+        rc = rv_allgather(ctx, &n->rv, &me, sizeof(int), pids);
+        shm_unlink(n->rv.name);
+        if (rc != B2K_OK) { rv_close(&n->rv); ctx->nccl = nullptr; delete n; return rc; }
+    }
+    if (want_nccl) {
+        rc = load_nccl(ctx, n);
+        if (rc != B2K_OK) { rv_close(&n->rv); ctx->nccl = nullptr; delete n; return rc; }
+        ncclUniqueId id;
+        memcpy(&id, uid, sizeof(id));
+        NCCL_CK(ctx, n, n->CommInitRank(&n->comm, ctx->nranks, id, ctx->rank));
+    }
     peer_setup(ctx, n);
+    if (!n->peer_ok && !n->comm) {
+        rv_close(&n->rv);
+        ctx->nccl = nullptr;
+        delete n;
+        return b2k_fail(ctx, B2K_ENCCL, "no transport: NCCL disabled (B2K_NO_NCCL=1) and the NVLink peer window "
+                                        "could not be mapped on every rank");
+    }
     if (!g_comm_cache) {
         g_comm_cache = n;
         g_comm_rank = ctx->rank;
@@ -225,6 +308,7 @@ int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid) {
 
 void b2k_nccl_destroy(b2k_ctx* ctx) {
     if (!ctx->nccl) return;
+    ctx->nccl->heap_used = 0;            // operators (the heap's only users) die with their context
     if (ctx->nccl == g_comm_cache) {     // stays alive for the next context of this process
         g_comm_in_use = false;
         ctx->nccl = nullptr;
@@ -232,8 +316,9 @@ void b2k_nccl_destroy(b2k_ctx* ctx) {
     }
     if (ctx->nccl->peer_ok)
         for (int p = 0; p < ctx->nranks; ++p)
-            if (p != ctx->rank) cudaIpcCloseMemHandle(ctx->nccl->peer.ptr[p]);
-    if (ctx->nccl->peer_local) cudaFree(ctx->nccl->peer_local);
+            if (p != ctx->rank) cudaIpcCloseMemHandle(ctx->nccl->pd.win[p]);
+    if (ctx->nccl->win_local) cudaFree(ctx->nccl->win_local);
+    rv_close(&ctx->nccl->rv);
     if (ctx->nccl->comm) ctx->nccl->CommDestroy(ctx->nccl->comm);
     delete ctx->nccl;
     ctx->nccl = nullptr;
@@ -241,14 +326,14 @@ void b2k_nccl_destroy(b2k_ctx* ctx) {
 
 int32_t b2k_nccl_allreduce_f64(b2k_ctx* ctx, double* dptr, int32_t count) {
     B2kNccl* n = ctx->nccl;
-    if (!n) return b2k_fail(ctx, B2K_ENCCL, "allreduce on a context without a communicator");
+    if (!n || !n->comm) return b2k_fail(ctx, B2K_ENCCL, "allreduce on a context without a communicator");
     NCCL_CK(ctx, n, n->AllReduce(dptr, dptr, (size_t)count, ncclFloat64_, ncclSum_, n->comm, ctx->stream));
     return B2K_OK;
 }
 
 int32_t b2k_nccl_allgather(b2k_ctx* ctx, const void* sendbuf, void* recvbuf, size_t bytes) {
     B2kNccl* n = ctx->nccl;
-    if (!n) return b2k_fail(ctx, B2K_ENCCL, "allgather on a context without a communicator");
+    if (!n || !n->comm) return b2k_fail(ctx, B2K_ENCCL, "allgather on a context without a communicator");
     NCCL_CK(ctx, n, n->AllGather(sendbuf, recvbuf, bytes, ncclChar_, n->comm, ctx->stream));
     return B2K_OK;
 }
@@ -257,7 +342,7 @@ int32_t b2k_nccl_halo_exchange(b2k_ctx* ctx, int up, int dn, const void* send_up
                                void* recv_dn, size_t recv_dn_bytes, const void* send_dn,
                                size_t send_dn_bytes, void* recv_up, size_t recv_up_bytes) {
     B2kNccl* n = ctx->nccl;
-    if (!n) return b2k_fail(ctx, B2K_ENCCL, "halo exchange on a context without a communicator");
+    if (!n || !n->comm) return b2k_fail(ctx, B2K_ENCCL, "halo exchange on a context without a communicator");
     NCCL_CK(ctx, n, n->GroupStart());
     if (up >= 0 && send_up_bytes) NCCL_CK(ctx, n, n->Send(send_up, send_up_bytes, ncclChar_, up, n->comm, ctx->stream));
     if (dn >= 0 && recv_dn_bytes) NCCL_CK(ctx, n, n->Recv(recv_dn, recv_dn_bytes, ncclChar_, dn, n->comm, ctx->stream));

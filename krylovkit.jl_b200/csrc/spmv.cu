@@ -43,6 +43,9 @@ struct b2k_op {
     int64_t  halo_lo = 0, halo_hi = 0;         // entries needed from rank-1 / rank+1
     int64_t  send_lo = 0, send_hi = 0;         // entries rank-1 / rank+1 need from me
     void*    halo = nullptr;      // [halo_lo | halo_hi] receive buffer
+    int32_t  peer_halo = 0;       // receive buffers live in the NVLink peer window (symmetric heap offset)
+    size_t   halo_off = 0, halo_region = 0;    // window offset of [parity 0 | parity 1], bytes per parity
+    int64_t  dn_lo = 0;           // rank-1's halo_lo: my head rows land behind its lo entries
     int32_t  gather_all = 0;      // fallback: allgather the whole x
     void*    xall = nullptr;
     // dense (device, column-major m x n, leading dim ld)
@@ -59,11 +62,18 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
               int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk, T a0, T a1,
               int shifted, const T* __restrict__ xs, const T* __restrict__ dotv,
               double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out,
-              const SpmvFuse fz) {
+              const SpmvFuse fz, const __grid_constant__ PeerStep ps) {
     __shared__ T prod[SP_NNZ];
     __shared__ double red[32];
     __shared__ bool last;
     if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
+    if (ps.on && ps.seq_halo) {        // boundary rows of x arrive from the neighbours through the peer window
+        if (threadIdx.x == 0) {
+            if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
+            if (ps.wait_hi) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1)) < ps.seq_halo) {}
+        }
+        __syncthreads();
+    }
     const bool scaled = fz.xscale != nullptr;
     const T sc = scaled ? (T)(*fz.xscale) : (T)1;
     T* const vout = reinterpret_cast<T*>(fz.vout);
@@ -149,7 +159,10 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             const volatile double* pv = part;
             for (int g = tid; g < (int)gridDim.x; g += SP_BT) v2 += pv[g];
             const double tot = block_sum(v2, red);
-            if (tid == 0) *out = tot;
+            if (tid == 0) {
+                *out = tot;
+                if (ps.on && ps.seq_alpha) peer_publish1(ps.pd, PEER_CH_ALPHA, ps.seq_alpha, tot);
+            }
         }
     }
 }
@@ -190,7 +203,8 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk,
             const int32_t* __restrict__ pblk, int nblk, T a0, T a1, int shifted,
             const T* __restrict__ xs, const T* __restrict__ dotv, double* __restrict__ part,
-            unsigned* __restrict__ ticket, double* __restrict__ out, const SpmvFuse fz) {
+            unsigned* __restrict__ ticket, double* __restrict__ out, const SpmvFuse fz,
+            const __grid_constant__ PeerStep ps) {
     using LY = SppLayout<T>;
     extern __shared__ __align__(128) uint8_t smem[];
     if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
@@ -240,6 +254,13 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     }
     // ---------------------------------- consumers ----------------------------------
     const int tid = threadIdx.x, w = tid >> 5;
+    if (ps.on && ps.seq_halo) {        // boundary rows of x arrive from the neighbours through the peer window;
+        if (tid == 0) {                // the producer warp streams the matrix meanwhile
+            if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
+            if (ps.wait_hi) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1)) < ps.seq_halo) {}
+        }
+        named_bar_sync(1, SPP_CONS);
+    }
     const bool scaled = fz.xscale != nullptr;
     const T sc = scaled ? (T)(*fz.xscale) : (T)1;
     T* const vout = reinterpret_cast<T*>(fz.vout);
@@ -359,8 +380,39 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 double tot = 0.0;
                 for (int i = 0; i < SPP_CONS / 32; ++i) tot += red[i];
                 *out = tot;
+                if (ps.on && ps.seq_alpha) peer_publish1(ps.pd, PEER_CH_ALPHA, ps.seq_alpha, tot);
             }
         }
+    }
+}
+
+// Halo push through the peer window: my first send_lo entries go behind rank-1's lo entries (its hi halo), my
+// last send_hi entries to the start of rank+1's receive buffer (its lo halo); the last CTA raises the flags.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_halo_push(const T* __restrict__ x, int64_t n, const __grid_constant__ PeerStep ps, unsigned* __restrict__ ticket,
+            const int* __restrict__ stop) {
+    __shared__ bool last;
+    if (stop && *reinterpret_cast<const volatile int*>(stop)) return;
+    const PeerDev& pd = ps.pd;
+    T* dn = ps.send_lo ? reinterpret_cast<T*>(pd.win[pd.rank - 1] + ps.dn_off) : nullptr;
+    T* up = ps.send_hi ? reinterpret_cast<T*>(pd.win[pd.rank + 1] + ps.up_off) : nullptr;
+    const int64_t total = ps.send_lo + ps.send_hi;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < ps.send_lo) dn[i] = x[i];
+        else up[i - ps.send_lo] = x[n - ps.send_hi + (i - ps.send_lo)];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        if (dn) st_release_sys_u64(peer_hflag(pd, pd.rank - 1, ps.seq_halo, 1), ps.seq_halo);
+        if (up) st_release_sys_u64(peer_hflag(pd, pd.rank + 1, ps.seq_halo, 0), ps.seq_halo);
     }
 }
 
@@ -586,19 +638,11 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
         lo = std::max<int64_t>(0, col0 - (int64_t)mm[0]);
         hi = std::max<int64_t>(0, (int64_t)mm[1] - (col0 + n_loc - 1));
     }
-    // exchange (halo_lo, halo_hi, n_loc) with all ranks: 3 int64 each, through a double buffer
+    // exchange (halo_lo, halo_hi, n_loc) with all ranks over the node-local rendezvous (host side, no NCCL)
     const int R = ctx->nranks;
-    double* d_x;
-    B2K_CUDA(ctx, B2K_DMALLOC(&d_x, sizeof(double) * 3 * R));
     double mine[3] = {(double)lo, (double)hi, (double)n_loc};
-    B2K_CUDA(ctx, cudaMemcpyAsync(d_x + 3 * ctx->rank, mine, sizeof(mine), cudaMemcpyHostToDevice,
-                                  ctx->stream));
-    B2K_TRY(b2k_nccl_allgather(ctx, d_x + 3 * ctx->rank, d_x, sizeof(double) * 3));
     std::vector<double> all(3 * R);
-    B2K_CUDA(ctx, cudaMemcpyAsync(all.data(), d_x, sizeof(double) * 3 * R, cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    B2K_DFREE(d_x);
+    B2K_TRY(b2k_host_allgather(ctx, mine, sizeof(mine), all.data()));
     bool neighbour_ok = true;
     for (int r = 0; r < R; ++r) {
         const int64_t l = (int64_t)all[3 * r], h = (int64_t)all[3 * r + 1];
@@ -610,8 +654,28 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
         op->halo_hi = hi;
         op->send_hi = ctx->rank + 1 < R ? (int64_t)all[3 * (ctx->rank + 1)] : 0;      // rank+1's halo_lo
         op->send_lo = ctx->rank > 0 ? (int64_t)all[3 * (ctx->rank - 1) + 1] : 0;      // rank-1's halo_hi
-        if (lo + hi > 0) B2K_CUDA(ctx, B2K_DMALLOC(&op->halo, (size_t)(lo + hi) * ctx->esize));
+        op->dn_lo = ctx->rank > 0 ? (int64_t)all[3 * (ctx->rank - 1)] : 0;
+        // receive buffers: in the NVLink peer window when there is one (neighbours store into it directly),
+        // at a heap offset that is the same on every rank; else private memory filled by ncclSend/Recv
+        int64_t maxtot = 0;
+        for (int r = 0; r < R; ++r) maxtot = std::max<int64_t>(maxtot, (int64_t)all[3 * r] + (int64_t)all[3 * r + 1]);
+        if (b2k_peer_ok(ctx) && maxtot > 0) {
+            const size_t region = (((size_t)maxtot * ctx->esize) + 255) & ~(size_t)255;
+            const size_t off = b2k_peer_heap_alloc(ctx, 2 * region);          // same arithmetic on every rank
+            if (off != SIZE_MAX) {
+                op->peer_halo = 1;
+                op->halo_off = off;
+                op->halo_region = region;
+            }
+        }
+        if (!op->peer_halo && !b2k_has_nccl(ctx))
+            return b2k_fail(ctx, B2K_ENOTSUP, "halo of %lld entries does not fit the peer window (B2K_PEER_WINDOW_MB) "
+                                              "and NCCL is disabled", (long long)maxtot);
+        if (!op->peer_halo && lo + hi > 0) B2K_CUDA(ctx, B2K_DMALLOC(&op->halo, (size_t)(lo + hi) * ctx->esize));
     } else {
+        if (!b2k_has_nccl(ctx))
+            return b2k_fail(ctx, B2K_ENOTSUP, "operator couples non-adjacent row shards: needs the NCCL all-gather "
+                                              "fallback, but NCCL is disabled");
         for (int r = 0; r < R; ++r)
             if ((int64_t)all[3 * r + 2] != n_loc)
                 return b2k_fail(ctx, B2K_ENOTSUP,
@@ -982,6 +1046,22 @@ int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const
                                    dotv ? ctx->d_res + dot_slot : nullptr, nullptr);
 }
 
+// Halo traffic of one apply through the peer window, for sequence number `seq`: what I send where, what I wait for.
+int32_t b2k_op_peer_halo(const b2k_ctx* ctx, const b2k_op* op, unsigned long long seq, PeerStep* ps) {
+    if (!op->peer_halo) return B2K_ENOTSUP;
+    const size_t par = (size_t)(seq & 1ull) * op->halo_region;
+    ps->seq_halo = seq;
+    ps->send_lo = op->send_lo;
+    ps->send_hi = op->send_hi;
+    ps->dn_off = op->halo_off + par + (size_t)op->dn_lo * ctx->esize;     // behind rank-1's lo entries
+    ps->up_off = op->halo_off + par;                                      // start of rank+1's buffer
+    ps->wait_lo = op->halo_lo > 0;
+    ps->wait_hi = op->halo_hi > 0;
+    return B2K_OK;
+}
+
+bool b2k_op_has_peer_halo(const b2k_op* op) { return op->peer_halo != 0; }
+
 // fz (optional): normalise-on-gather / write the normalised operand / dot with it / skip flag — see SpmvFuse.
 int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,
                                 double a0, double a1, bool shifted, const VecRef* dotv, double* dot_out,
@@ -1015,8 +1095,36 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
     const void* xsrc = x.ptr;
     int32_t n_loc = (int32_t)x.n;
     const void* halo = op->halo;
+    PeerStep ps;
+    memset(&ps, 0, sizeof(ps));
+    if (ctx->nranks > 1 && b2k_peer_ok(ctx)) {
+        ps.pd = *b2k_peer_dev(ctx);
+        ps.on = 1;
+        ps.seq_alpha = fz.seq_alpha;
+    }
     if (ctx->nranks > 1) {
-        if (op->gather_all) {
+        if (op->peer_halo) {
+            // the neighbours store my boundary rows straight into my window; the kernel waits for their flags
+            unsigned long long hs = fz.seq_halo;
+            if (!hs) {
+                hs = b2k_peer_next_seq(ctx, 4);
+                B2K_TRY(b2k_op_peer_halo(ctx, op, hs, &ps));
+                const int64_t total = ps.send_lo + ps.send_hi;
+                if (total > 0) {
+                    const int g = (int)std::max<int64_t>(1, std::min<int64_t>((total + 1023) / 1024, ctx->num_sms));
+                    if (ctx->dtype == B2K_F64)
+                        k_halo_push<double><<<g, 256, 0, ctx->stream>>>((const double*)x.ptr, x.n, ps,
+                                                                        ctx->d_sync + B2K_SYNC_HALO, fz.stop);
+                    else
+                        k_halo_push<float><<<g, 256, 0, ctx->stream>>>((const float*)x.ptr, x.n, ps,
+                                                                       ctx->d_sync + B2K_SYNC_HALO, fz.stop);
+                    B2K_LAUNCH_CHECK(ctx);
+                }
+            } else {
+                B2K_TRY(b2k_op_peer_halo(ctx, op, hs, &ps));
+            }
+            halo = b2k_peer_local(ctx) + op->halo_off + (size_t)(hs & 1ull) * op->halo_region;
+        } else if (op->gather_all) {
             B2K_TRY(b2k_nccl_allgather(ctx, x.ptr, op->xall, (size_t)x.n * ctx->esize));
             xsrc = op->xall;
             n_loc = 0x7fffffff;
@@ -1047,7 +1155,7 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
     k_spmv_pipe<T><<<grid, SPP_THREADS, SppLayout<T>::SMEM, ctx->stream>>>(                    \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
         (T*)y.ptr, op->rowblk, op->pblk, op->nblk, (T)a0, (T)a1, shifted ? 1 : 0,              \
-        (const T*)x.ptr, dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz)
+        (const T*)x.ptr, dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz, ps)
         if (ctx->dtype == B2K_F64) LAUNCH(double);
         else LAUNCH(float);
 #undef LAUNCH
@@ -1056,7 +1164,7 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
     k_spmv_stream<T><<<op->nblk, SP_BT, 0, ctx->stream>>>(                                     \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
         (T*)y.ptr, op->rowblk, (T)a0, (T)a1, shifted ? 1 : 0, (const T*)x.ptr,                 \
-        dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz)
+        dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz, ps)
         if (ctx->dtype == B2K_F64) LAUNCH(double);
         else LAUNCH(float);
 #undef LAUNCH

@@ -82,6 +82,13 @@ struct PhaseParams {
     T c1, c2;
     const double* c1_dev;   // if set: c1 = -(*c1_dev)  (beta of the previous step, kept on the device)
     const double* c2_dev;   // if set: c2 = -(*c2_dev), a device scalar produced by the previous kernel
+    int32_t c2_sets;        // > 1: c2 = -(sum_g c2_dev[g * c2_stride]), the per-rank partials in the peer window
+    int32_t c2_stride;
+    // row-sharded contexts: the rows the neighbours need for their next SpMV are stored into their windows as
+    // the final vector is written (UPDATE phase with store_x): first send_lo rows -> halo_dn, last send_hi -> halo_up
+    T* halo_dn;
+    T* halo_up;
+    int64_t send_lo, send_hi;
     int32_t nvec;    // 1 or 3
     int32_t store_x; // write x'' (UPDATE) or x' (prologue write-back) to xout
     // UPDATE: x'' = betax*x' + sum_j Q[:,j]*cs[j],  cs[j] = alphac * sum_g coef[g*stride+j]
@@ -268,7 +275,13 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
     int buf = 0;
     T c1 = p.c1, c2 = p.c2;
     if (p.c1_dev) c1 = (T)(-(*reinterpret_cast<const volatile double*>(p.c1_dev)));
-    if (p.c2_dev) c2 = (T)(-(*reinterpret_cast<const volatile double*>(p.c2_dev)));
+    if (p.c2_dev) {
+        double a2 = 0.0;
+        const int ns = p.c2_sets > 1 ? p.c2_sets : 1;
+        for (int g = 0; g < ns; ++g)      // rank order: same bits on every rank (and in the finaliser)
+            a2 += *reinterpret_cast<const volatile double*>(p.c2_dev + (size_t)g * p.c2_stride);
+        c2 = (T)(-a2);
+    }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * R;
@@ -307,7 +320,14 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
             }
             if (tid >= rt) acc = (T)0;
         }
-        if (p.store_x && tid < rt) p.xout[r0 + tid] = acc;
+        if (p.store_x && tid < rt) {
+            p.xout[r0 + tid] = acc;
+            if (UPDATE && !PROJECT) {
+                const int64_t r = r0 + tid;
+                if (p.halo_dn && r < p.send_lo) p.halo_dn[r] = acc;
+                if (p.halo_up && r >= p.n - p.send_hi) p.halo_up[r - (p.n - p.send_hi)] = acc;
+            }
+        }
         if (p.part_n) nrm = fma(acc, acc, nrm);
         if (PROJECT) {
             T* wb = w1 + buf * R;
@@ -395,10 +415,15 @@ struct FinalizeParams {
     int* stop;
     unsigned* ticket;
     int enabled;
+    // row-sharded (peer window): A/B are then the per-rank sums in MY window (G = nranks, stride = PEER_SLOT),
+    // N the LOCAL per-CTA norm partials (G_local of them); the norm and <v, A v> are summed over ranks here
+    int peer;
+    int G_local;
 };
 
 // `sh` : >= 2 doubles of shared memory; `barrier_id` : named barrier the NCONS calling threads may use
-__device__ __forceinline__ void finalize_block(const FinalizeParams& f, int tid, double* sh) {
+__device__ __forceinline__ void finalize_block(const FinalizeParams& f, int tid, double* sh,
+                                               const PeerStep* ps = nullptr) {
     double hval = 0.0;
     if (f.k > 0) {
         const int L = coef_lanes(f.k);
@@ -414,15 +439,32 @@ __device__ __forceinline__ void finalize_block(const FinalizeParams& f, int tid,
     }
     double n2 = 0.0;
     if (f.N && tid < 32) {
-        double a = (tid < 16) ? partial_lane_sum(f.N, f.G, 1, tid, 16) : 0.0;
+        double a = (tid < 16) ? partial_lane_sum(f.N, f.peer ? f.G_local : f.G, 1, tid, 16) : 0.0;
         for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         n2 = a;
-        if (tid == 0 && f.res) f.res[f.noff] = a;
     }
+    double alpha0 = f.rec ? f.rec[0] : 0.0;
+    if (f.peer && ps) {
+        // ||w||^2: publish my partial to every rank, wait for theirs in my window, add in rank order
+        if (tid == 0) peer_publish1(ps->pd, PEER_CH_NORM, ps->seq_norm, n2);
+        peer_wait(ps->pd, PEER_CH_NORM, ps->seq_norm, tid);
+        named_bar_sync(1, NCONS);
+        if (tid == 0) {
+            n2 = peer_sum1(ps->pd, PEER_CH_NORM, ps->seq_norm, 0);
+            if (ps->seq_alpha) alpha0 = peer_sum1(ps->pd, PEER_CH_ALPHA, ps->seq_alpha, 0);
+            if (ps->seq_halo) {       // every CTA fenced its halo stores before taking its ticket
+                __threadfence_system();
+                if (ps->send_lo) st_release_sys_u64(peer_hflag(ps->pd, ps->pd.rank - 1, ps->seq_halo, 1), ps->seq_halo);
+                if (ps->send_hi) st_release_sys_u64(peer_hflag(ps->pd, ps->pd.rank + 1, ps->seq_halo, 0), ps->seq_halo);
+            }
+        }
+    }
+    if (f.N && tid == 0 && f.res) f.res[f.noff] = n2;
     if (f.rec) {
         named_bar_sync(1, NCONS);
         if (tid == 0) {
-            const double alpha = f.rec[0] + sh[0];
+            f.rec[0] = alpha0;
+            const double alpha = alpha0 + sh[0];
             const double beta = sqrt(n2);
             f.rec[1] = alpha;
             f.rec[2] = beta;

@@ -51,16 +51,21 @@ def localize_column(g: int, shard: RowShard, halo_lo: int) -> int:
     return shard.n_local + halo_lo + (g - (shard.row_offset + shard.n_local))
 
 
-def broadcast_nccl_uid(dist, lib, device) -> bytes:
-    """Rank 0 creates the 128-byte ncclUniqueId (b2k_nccl_unique_id); every rank receives it
-    through the torch.distributed process group that launched the job."""
-    import torch
-    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+def broadcast_nccl_uid(dist, lib, device=None) -> bytes:
+    """The 128-byte job-unique token every rank passes to b2k_ctx_create_dist: rank 0 creates it and every rank
+    receives it through the torch.distributed process group that launched the job (any backend).  It is an
+    ncclUniqueId (b2k_nccl_unique_id) when NCCL is in use; with B2K_NO_NCCL=1 — the NVLink peer window is then
+    the only transport, which also allows several ranks on ONE GPU — 128 random bytes do: the token only names
+    the node-local rendezvous."""
+    import os
+    payload = [None]
     if dist.get_rank() == 0:
-        buf = C.create_string_buffer(128)
-        st = lib.b2k_nccl_unique_id(buf)
-        if st != 0:
-            raise RuntimeError("b2k_nccl_unique_id failed")
-        uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device=device)
-    dist.broadcast(uid, 0)
-    return bytes(uid.cpu().tolist())
+        if os.environ.get("B2K_NO_NCCL", "") == "1":
+            payload[0] = os.urandom(128)
+        else:
+            buf = C.create_string_buffer(128)
+            if lib.b2k_nccl_unique_id(buf) != 0:
+                raise RuntimeError("b2k_nccl_unique_id failed")
+            payload[0] = bytes(buf.raw)
+    dist.broadcast_object_list(payload, src=0)
+    return bytes(payload[0])

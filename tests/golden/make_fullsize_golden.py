@@ -33,7 +33,8 @@ CONV = (4.0, -1.4, -0.6, -1.2, -0.8, 0, 0)       # convection-diffusion of confi
 
 def lanczos_case(nx, ny, nz, kd, cycles, orth, howmany=4):
     n = nx * ny * nz
-    A = native.CSR(ko.stencil_matrix(nx, ny, nz) if nz > 1 else ko.stencil_matrix(nx, ny))
+    # 5-point (diag 4) in 2-D, 7-point (diag 6) in 3-D — SURVEY §8d configs 2 and 5
+    A = native.CSR(ko.stencil_matrix(nx, ny, nz, (6.0, -1, -1, -1, -1, -1, -1)) if nz > 1 else ko.stencil_matrix(nx, ny))
     x0 = ko.splitmix_vector(SEED, n)
     out = {"grid": [nx, ny, nz], "n": n, "krylovdim": kd, "orth": orth, "howmany": howmany, "seed": SEED,
            "which": "SR", "tol": 0.0, "after_cycles": {}}

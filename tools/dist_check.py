@@ -2,6 +2,10 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29611 tools/dist_check.py
+
+B2K_ONE_GPU=1: all ranks share GPU 0 (torch.distributed over gloo, library transport = NVLink peer window only,
+B2K_NO_NCCL=1 — NCCL refuses two ranks on one device).  Same checks; this is how a single-GPU box exercises the
+sharded path, including the in-kernel cross-rank reductions (the ranks' kernels then alternate by time slicing).
 """
 import os
 import sys
@@ -23,9 +27,16 @@ from oracle import krylov_oracle as ko  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = sharding.broadcast_nccl_uid(dist, kk._lib.load(), torch.device("cuda", local))
+    one_gpu = os.environ.get("B2K_ONE_GPU", "") == "1"
+    if one_gpu:
+        os.environ["B2K_NO_NCCL"] = "1"
+        local = 0
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = "cpu" if one_gpu else "cuda"
+    uid = sharding.broadcast_nccl_uid(dist, kk._lib.load())
     nx, ny = 200, 151
     n = nx * ny
     shard = sharding.shard_grid_lines(nx, ny, rank, world)
@@ -61,19 +72,36 @@ def main():
         lam = ko.laplace_eigenvalues(nx, ny)
         assert np.allclose(vals[:3], lam[:3], rtol=1e-10)
         # gather one Ritz vector and check the residual globally
-        vloc = torch.from_numpy(vecs[0].to_host()).cuda()
+        vloc = torch.from_numpy(vecs[0].to_host()).to(dev)
         parts = [torch.zeros(sharding.shard_grid_lines(nx, ny, r, world).n_local, dtype=torch.float64,
-                             device="cuda") for r in range(world)]
+                             device=dev) for r in range(world)]
         dist.all_gather(parts, vloc)
         v = torch.cat(parts).cpu().numpy()
         assert np.linalg.norm(A @ v - vals[0] * v) < 1e-8
         del vecs
+    # 4b. the benchmark regime (fixed restart cycles, tol = 0) through the device-chained steps — in-kernel
+    #     cross-rank reductions and halo rows pushed by the Gram-Schmidt launch — vs the serial oracle, and vs the
+    #     same job with one synchronous step at a time (NCCL / peer all-reduce launches between the sweeps)
+    alg = kk.Lanczos(orth=kk.cgs2, krylovdim=40, maxiter=4, tol=0.0, verbosity=0)
+    lib = kk._lib.load()
+    res = {}
+    for chain in (1, 0):
+        lib.b2k_debug_set_chain(chain)
+        vals, vecs, info = kk.eigsolve(op, ctx.from_host(x0[sl]), 4, "SR", alg)
+        res[chain] = (np.array(vals[:4]), info.numops, np.array(info.normres[:4]))
+        del vecs
+    lib.b2k_debug_set_chain(1)
+    ovals, _, oinfo = ko.eigsolve_lanczos(A, x0, 4, "SR", krylovdim=40, maxiter=4, tol=0.0, orth=ko.Orth(ko.CGS2))
+    assert res[1][1] == res[0][1] == oinfo["numops"]
+    assert np.allclose(res[1][0], ovals[:4], rtol=1e-10) and np.allclose(res[0][0], ovals[:4], rtol=1e-10)
+    assert np.allclose(res[1][0], res[0][0], rtol=1e-12), (res[1][0], res[0][0])
+    assert np.allclose(res[1][2], oinfo["normres"][:4], rtol=1e-6)
     # 5. widened drivers on the sharded context: every scalar they see is all-reduced inside
     #    the library, so the host logic is rank-replicated; results = the serial oracle's
     def gather(vec):
-        loc = torch.from_numpy(vec.to_host()).cuda()
+        loc = torch.from_numpy(vec.to_host()).to(dev)
         parts = [torch.zeros(sharding.shard_grid_lines(nx, ny, r, world).n_local, dtype=torch.float64,
-                             device="cuda") for r in range(world)]
+                             device=dev) for r in range(world)]
         dist.all_gather(parts, loc)
         return torch.cat(parts).cpu().numpy()
 

@@ -35,7 +35,7 @@ def make_ctx(n_lines, line, ncols, dtype=np.float64):
     if world == 1:
         return kk.B200Context(n, ncols, dtype=dtype, device=local), sharding.RowShard(0, 1, 0, n, n)
     import torch
-    u = sharding.broadcast_nccl_uid(dist, kk._lib.load(), torch.device("cuda", local))
+    u = sharding.broadcast_nccl_uid(dist, kk._lib.load())
     sh = sharding.shard_grid_lines(line, n_lines, rank, world)
     return kk.B200Context(sh.n_local, ncols, dtype=dtype, device=local, rank=rank, nranks=world, nccl_uid=u,
                           n_global=n, row_offset=sh.row_offset), sh
