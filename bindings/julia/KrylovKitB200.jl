@@ -16,6 +16,7 @@ module KrylovKitB200
 using KrylovKit, VectorInterface, LinearAlgebra, SparseArrays
 import KrylovKit: OrthonormalBasis, Orthogonalizer, apply, apply_normal, apply_adjoint
 import KrylovKit: project!!, unproject!!, rank1update!, basistransform!, orthogonalize!!
+import KrylovKit: LanczosIterator, LanczosFactorization, expand!, normres
 import KrylovKit: ClassicalGramSchmidt, ModifiedGramSchmidt, ClassicalGramSchmidt2, ModifiedGramSchmidt2,
     ClassicalGramSchmidtIR, ModifiedGramSchmidtIR
 
@@ -34,16 +35,25 @@ end
 
 # ---- context -------------------------------------------------------------------------------------------
 mutable struct B200Ctx
-    h::Ptr{Cvoid}
-    n::Int
+    h::Ptr{Cvoid}          # C_NULL once destroyed: Julia runs finalizers in no particular order, so a vector's
+    n::Int                 # finalizer may run AFTER its context's — every call below checks `alive(ctx)` first
     T::DataType
+    spaces::Vector{Int}    # length of the vectors of each space (space 0 = n)
+end
+alive(ctx::B200Ctx) = ctx.h != C_NULL
+function destroy!(ctx::B200Ctx)
+    if alive(ctx)
+        ccall((:b2k_ctx_destroy, lib), Cint, (Ptr{Cvoid},), ctx.h)
+        ctx.h = C_NULL      # vectors / operators that outlive the context become inert instead of dangling
+    end
+    return nothing
 end
 function B200Ctx(n::Integer, ncols::Integer; T::Type{<:Union{Float64, Float32}} = Float64, device::Integer = 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(C_NULL, ccall((:b2k_ctx_create, lib), Cint, (Ref{Ptr{Cvoid}}, Cint, Int64, Cint, Cint),
                         h, device, n, ncols, T === Float64 ? 0 : 1))
-    ctx = B200Ctx(h[], n, T)
-    finalizer(c -> ccall((:b2k_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), ctx)
+    ctx = B200Ctx(h[], n, T, [Int(n)])
+    finalizer(destroy!, ctx)
     return ctx
 end
 # one process per GPU: uid = 128 bytes from b2k_nccl_unique_id on rank 0, broadcast by MPI / Distributed
@@ -53,9 +63,17 @@ function B200Ctx(nlocal::Integer, ncols::Integer, rank::Integer, nranks::Integer
     check(C_NULL, ccall((:b2k_ctx_create_dist, lib), Cint,
                         (Ref{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Cint, Cint, Ptr{UInt8}, Int64, Int64),
                         h, device, nlocal, ncols, T === Float64 ? 0 : 1, rank, nranks, uid, nglobal, rowoffset))
-    ctx = B200Ctx(h[], nlocal, T)
-    finalizer(c -> ccall((:b2k_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), ctx)
+    ctx = B200Ctx(h[], nlocal, T, [Int(nlocal)])
+    finalizer(destroy!, ctx)
     return ctx
+end
+# additional vector space (the short side of GKL / LSMR): returns its index
+function addspace!(ctx::B200Ctx, n::Integer, ncols::Integer; sharded::Bool = false)
+    sp = Ref{Cint}(0)
+    check(ctx.h, ccall((:b2k_space_create, lib), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ref{Cint}),
+                       ctx.h, n, ncols, sharded ? 1 : 0, sp))
+    push!(ctx.spaces, Int(n))
+    return Int(sp[])
 end
 
 # ---- vectors: one slab column each ----------------------------------------------------------------------
@@ -66,18 +84,31 @@ end
 function B200Vec(ctx::B200Ctx; space::Integer = 0)
     v = Ref{Int32}(0)
     check(ctx.h, ccall((:b2k_vec_alloc, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Int32}), ctx.h, space, v))
-    x = B200Vec{ctx.T}(ctx, v[])
-    finalizer(y -> ccall((:b2k_vec_free, lib), Cint, (Ptr{Cvoid}, Int32), y.ctx.h, y.handle), x)
+    return adopt(ctx, v[])
+end
+# wrap a column the library allocated (b2k_lanczos_expand_many); the finalizer returns it to the slab — unless the
+# context is already gone (then its slab is gone too) or the library took the column back (`disown!`)
+function adopt(ctx::B200Ctx, handle::Integer)
+    x = B200Vec{ctx.T}(ctx, Int32(handle))
+    finalizer(x) do y
+        if y.handle >= 0 && alive(y.ctx)
+            ccall((:b2k_vec_free, lib), Cint, (Ptr{Cvoid}, Int32), y.ctx.h, y.handle)
+        end
+    end
     return x
 end
-function B200Vec(ctx::B200Ctx, host::Vector{T}) where {T}
+disown!(x) = (x.handle = Int32(-1); x)
+Base.length(x::B200Vec) = x.ctx.spaces[space(x) + 1]
+function B200Vec(ctx::B200Ctx, host::Vector{T}; space::Integer = 0) where {T}
     T === ctx.T || throw(ArgumentError("host data must be $(ctx.T)"))
-    x = B200Vec(ctx)
+    length(host) == ctx.spaces[space + 1] ||
+        throw(DimensionMismatch("host vector has $(length(host)) entries, space $space holds $(ctx.spaces[space + 1])"))
+    x = B200Vec(ctx; space = space)
     check(ctx.h, ccall((:b2k_vec_upload, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{T}), ctx.h, x.handle, host))
     return x
 end
 function Base.Array(x::B200Vec{T}) where {T}
-    out = Vector{T}(undef, x.ctx.n)
+    out = Vector{T}(undef, length(x))
     check(x.ctx.h, ccall((:b2k_vec_download, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{T}), x.ctx.h, x.handle, out))
     return out
 end
@@ -246,9 +277,89 @@ function LinearAlgebra.rmul!(b::B200Basis, H::KrylovKit.Householder)            
     return b
 end
 
-# Optional fused steps (DESIGN.md §3): specialise KrylovKit.expand!(::LanczosIterator{<:B200CSR}, state) on
-# b2k_lanczos_expand, the inner loop of eigsolve(::Lanczos) on b2k_lanczos_expand_many, linsolve(::CG) on
-# b2k_cg_step and linsolve(::BiCGStab) on b2k_bicgstab_half/_full — same pairing as
-# krylovkit.jl_b200/factorizations/lanczos.py::expand_/expand_many_ and linsolve.py::_cg/_bicgstab.
+# ---- fused steps: the path bench.py times (DESIGN.md §3, §4) ---------------------------------------------------
+# expand!(iter::LanczosIterator, state) — src/factorizations/lanczos.jl:250-272.  For a device CSR operator one
+# C-ABI call does `V <- push!(V, r/β); w = A v; lanczosrecurrence` with ONE host synchronisation; with
+# ClassicalGramSchmidt2 it is two launches (SpMV with the normalisation fused into its gather + one cooperative
+# Gram-Schmidt kernel).  Same operation order as lanczos.jl:313-324, same α, β, V, r as the generic method.
+function expand!(iter::LanczosIterator{<:B200CSR}, state::LanczosFactorization; verbosity::Int = KrylovKit.KrylovDefaults.verbosity[])
+    expand_many!(iter, state, 1, zero(Float64))
+    return state
+end
+
+# `nsteps` consecutive expand! calls — the `while K < krylovdim && β > tol` loop of src/eigsolve/lanczos.jl:45-79 —
+# in one C-ABI call (b2k_lanczos_expand_many): with ClassicalGramSchmidt2 the steps are chained on the device and
+# the host synchronises ONCE for the whole batch; steps behind a β <= tol are skipped on the device.
+# Returns the number of steps done.  eigsolve's inner loop calls this instead of looping over expand!.
+function expand_many!(iter::LanczosIterator{<:B200CSR}, state::LanczosFactorization, nsteps::Integer, tol::Real)
+    iter.keepvecs || error("the fused Lanczos step keeps all Krylov vectors")
+    V, r = state.V, state.r
+    ctx, k = r.ctx, length(V)
+    cols = Vector{Int32}(undef, k + nsteps + 1)
+    for i in 1:k
+        cols[i] = V[i].handle
+    end
+    cols[k + 1] = r.handle
+    αs, βs = Vector{Float64}(undef, nsteps), Vector{Float64}(undef, nsteps)
+    done, rout = Ref{Cint}(0), Ref{Int32}(0)
+    tag, η = _tag(iter.orth)
+    st = ccall((:b2k_lanczos_expand_many, lib), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Cint, Float64, Float64, Cint, Float64, Ptr{Float64}, Ptr{Float64},
+                Ref{Cint}, Ref{Int32}),
+               ctx.h, iter.operator.h, cols, k, nsteps, normres(state), Float64(tol), tag, η, αs, βs, done, rout)
+    d = Int(done[])
+    if d > 0          # commit the completed steps BEFORE throwing (include/b200krylov.h, HANDLES)
+        if cols[k + 1] == r.handle
+            push!(V, r)                          # the residual's storage became the basis vector (lanczos.jl:257)
+        else
+            disown!(r)                           # the library released (and may have reused) that column
+            push!(V, adopt(ctx, cols[k + 1]))
+        end
+        for i in 2:d
+            push!(V, adopt(ctx, cols[k + i]))
+        end
+        state.r = adopt(ctx, rout[])
+        append!(state.αs, αs[1:d]); append!(state.βs, βs[1:d])
+        state.k += d
+    end
+    check(ctx.h, st)
+    return d
+end
+
+# linsolve(::CG) — src/linsolve/cg.jl:62-101: one iteration = one call, p <- r + β p; q = A p (shifted);
+# <p,q> in the SpMV epilogue; x += α p; r -= α q; ||r||² in the same sweep.  Returns (<p,q>, ||r||).
+function cg_step!(A::B200CSR, x::B200Vec, r::B200Vec, p::B200Vec, q::B200Vec, α₀::Real, α₁::Real, β::Real, ρ::Real)
+    pq, nr = Ref{Float64}(0), Ref{Float64}(0)
+    check(x.ctx.h, ccall((:b2k_cg_step, lib), Cint,
+                         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Int32, Float64, Float64, Float64, Float64, Ref{Float64}, Ref{Float64}),
+                         x.ctx.h, A.h, x.handle, r.handle, p.handle, q.handle, Float64(α₀), Float64(α₁), Float64(β), Float64(ρ), pq, nr))
+    return pq[], nr[]
+end
+# linsolve(::BiCGStab) — src/linsolve/bicgstab.jl:95-150 in two calls (the half-step exit of :117-131 sits between):
+#   half: p <- r + β(p − ω v) [first = true: p = r]; v = A p; σ = <r̃, v>; s = r − (ρ/σ) v; returns (σ, ||s||)
+#   full: t = A s; ω = <t,s>/<t,t>; x += α p + ω s; r = s − ω t; returns (ω, ||r||, <r̃, r>)
+function bicgstab_half!(A::B200CSR, r::B200Vec, rs::B200Vec, p::B200Vec, v::B200Vec, s::B200Vec,
+                        α₀::Real, α₁::Real, β::Real, ω::Real, ρ::Real, first::Bool)
+    σ, ns = Ref{Float64}(0), Ref{Float64}(0)
+    check(r.ctx.h, ccall((:b2k_bicgstab_half, lib), Cint,
+                         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Int32, Int32, Float64, Float64, Float64, Float64, Float64, Cint,
+                          Ref{Float64}, Ref{Float64}),
+                         r.ctx.h, A.h, rs.handle, r.handle, p.handle, v.handle, s.handle, Float64(α₀), Float64(α₁), Float64(β),
+                         Float64(ω), Float64(ρ), first ? 1 : 0, σ, ns))
+    return σ[], ns[]
+end
+function bicgstab_full!(A::B200CSR, x::B200Vec, r::B200Vec, rs::B200Vec, p::B200Vec, s::B200Vec, t::B200Vec,
+                        α₀::Real, α₁::Real, α::Real)
+    ω, nr, ρ = Ref{Float64}(0), Ref{Float64}(0), Ref{Float64}(0)
+    check(x.ctx.h, ccall((:b2k_bicgstab_full, lib), Cint,
+                         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Int32, Int32, Int32, Float64, Float64, Float64,
+                          Ref{Float64}, Ref{Float64}, Ref{Float64}),
+                         x.ctx.h, A.h, x.handle, r.handle, rs.handle, p.handle, s.handle, t.handle, Float64(α₀), Float64(α₁),
+                         Float64(α), ω, nr, ρ))
+    return ω[], nr[], ρ[]
+end
+# KrylovKit.linsolve(A::B200CSR, b, x₀, alg::CG / BiCGStab, a₀, a₁) are the reference drivers (cg.jl, bicgstab.jl)
+# with their loop bodies replaced by the calls above — krylovkit.jl_b200/linsolve.py::_cg/_bicgstab is that code,
+# statement for statement, and is what the test-suite runs.
 
 end # module

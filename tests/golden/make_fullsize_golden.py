@@ -4,7 +4,7 @@ at FULL size.  The GPU arm of bench.py and the `-m gpu` full-size parity tests c
 GPU box has the oracle too, but a whole config-2 job costs ~20 s of its 16-CPU quota (config 3/5 more), so the
 numbers are computed once here and committed.  Nothing in the product reads this file.
 
-    python tests/golden/make_fullsize_golden.py [c2 c2_mgs2 c2_1e6 c3 c3_mgs2 c5s]     (default: all)
+    python tests/golden/make_fullsize_golden.py [c2 c2_mgs2 c2_1e6 c3 c3_mgs2 c5s c5]     (default: all)
 
 Inputs are the synthetic ones SURVEY.md §8d fixes (stencils + splitmix64 start vectors, seed 20260923), so the
 file is reproducible bit for bit up to the summation order of the OpenMP reductions (<= 1e-13 relative).
@@ -82,6 +82,8 @@ CASES = {
     "c3_mgs2": lambda: gmres_case(4000, 2500, 40, (2,), "mgs2"),
     # configs[4] shape (7-point 3-D Laplacian, krylovdim 30) at a size one GPU test finishes quickly: n = 8e6
     "c5s": lambda: lanczos_case(200, 200, 200, 30, (2, 5), "cgs2"),
+    # configs[4] itself: 8e7 rows (625 x 500 x 256), krylovdim 30, 3 restart cycles (the bench's other_configs record)
+    "c5": lambda: lanczos_case(625, 500, 256, 30, (3,), "cgs2"),
 }
 
 
