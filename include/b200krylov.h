@@ -289,6 +289,22 @@ int32_t b2k_block_reorthogonalize(b2k_ctx* ctx, const b2k_vec* R, int32_t p,
 int32_t b2k_block_qr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, double tol, double* R_host,
                      int32_t* good, int32_t* drift);
 
+/* apply(A, X::Block) — blocklanczos.jl:38: Y[i] = A X[i], i < p.  A single-GPU CSR operator reads the matrix once
+ * per 8 vectors (SpMM); bit-identical to p calls of b2k_op_apply. */
+int32_t b2k_op_apply_block(b2k_ctx* ctx, const b2k_op* op, const b2k_vec* X, const b2k_vec* Y, int32_t p);
+/* B200-first replacement of block_reorthogonalize! (FLAGGED mode of the host driver, not the reference's
+ * arithmetic): block classical Gram-Schmidt of the p <= 8 vectors R against V, `passes` (1 or 2) times, the
+ * basis read once per pass for the whole block.  H_host (k x p col-major, may be NULL) = summed coefficients
+ * V'R, G_host (p x p, may be NULL) = Gram matrix of the orthogonalised block.  One host synchronisation. */
+int32_t b2k_block_orthogonalize(b2k_ctx* ctx, const b2k_vec* R, int32_t p, const b2k_vec* V, int32_t k,
+                                int32_t passes, double* H_host, double* G_host);
+/* B200-first block_qr! (FLAGGED): CholeskyQR2 of p <= 8 vectors, in place.  G0_host (may be NULL) = the Gram
+ * matrix X'X if the caller already has it.  R_host (p x p col-major) = the upper-triangular factor with positive
+ * diagonal (the factor block_qr!'s modified Gram-Schmidt produces, to rounding).  *ok = 0: the block is
+ * numerically rank deficient at the scale block_qr! drops vectors (100 tol) — X is untouched, call b2k_block_qr. */
+int32_t b2k_block_cholqr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, double tol, const double* G0_host,
+                         double* R_host, int32_t* ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,11 @@ _PROTOS = {
     "b2k_block_reorthogonalize": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, P(c_vec), C.c_int32]),
     "b2k_block_qr": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, C.c_double, P(C.c_double),
                                  P(C.c_int32), P(C.c_int32)]),
+    "b2k_op_apply_block": (C.c_int32, [c_ctx, c_op, P(c_vec), P(c_vec), C.c_int32]),
+    "b2k_block_orthogonalize": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, P(c_vec), C.c_int32, C.c_int32,
+                                            P(C.c_double), P(C.c_double)]),
+    "b2k_block_cholqr": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, C.c_double, P(C.c_double), P(C.c_double),
+                                     P(C.c_int32)]),
     # debugging knob (not part of the public header): 0 = one launch per phase, 1 = cooperative
     "b2k_debug_set_coop": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_spmv_pipe": (C.c_int32, [C.c_int32]),

@@ -96,6 +96,9 @@ class BlockLanczos:
     qr_tol: float = KrylovDefaults.tol
     eager: bool = False
     verbosity: int = KrylovDefaults.verbosity
+    # B200-specific, FLAGGED (default: the reference's arithmetic): block-classical Gram-Schmidt twice + CholeskyQR2
+    # instead of the modified Gram-Schmidt loops of block_reorthogonalize! / block_qr! — factorizations/blocklanczos.py
+    fast_block: bool = False
 
 
 @dataclass(frozen=True)

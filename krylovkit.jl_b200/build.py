@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200krylov.so")
-SOURCES = ["ctx.cu", "blas1.cu", "spmv.cu", "basis.cu", "dist.cu", "hostmath.cu"]
+SOURCES = ["ctx.cu", "blas1.cu", "spmv.cu", "basis.cu", "block.cu", "dist.cu", "hostmath.cu"]
 HEADERS = ["common.cuh", "tsk.cuh", os.path.join("..", "..", "include", "b200krylov.h")]
 
 NVCC_FLAGS = [

@@ -1522,31 +1522,7 @@ extern "C" int32_t b2k_basis_householder(b2k_ctx* ctx, const b2k_vec* cols, int3
 
 // ------------------------------------------------------------------ block ops ----
 
-extern "C" int32_t b2k_block_inner(b2k_ctx* ctx, const b2k_vec* X, int32_t p, const b2k_vec* Y,
-                                   int32_t q, double* M_host) {
-    if (!ctx || !X || !Y || !M_host || p < 1 || q < 1) return B2K_EINVAL;
-    if ((int64_t)p * q > B2K_RES_DOUBLES) return b2k_fail(ctx, B2K_ENOTSUP, "block_inner: p*q too large");
-    Panel pn;
-    B2K_TRY(make_panel(ctx, X, p, &pn));
-    for (int j = 0; j < q; ++j) {
-        VecRef ry;
-        B2K_TRY(b2k_resolve(ctx, Y[j], &ry));
-        if (ry.n != pn.n) return b2k_fail(ctx, B2K_EDIM, "block_inner: length mismatch");
-        if (ctx->dtype == B2K_F64) B2K_TRY(project_t<double>(ctx, pn, ry, p, j * p));
-        else B2K_TRY(project_t<float>(ctx, pn, ry, p, j * p));
-    }
-    B2K_TRY(b2k_fetch_results(ctx, p * q, pn.sharded));
-    memcpy(M_host, ctx->h_res, sizeof(double) * p * q);
-    return B2K_OK;
-}
-
-extern "C" int32_t b2k_block_axpy(b2k_ctx* ctx, const b2k_vec* Y, int32_t q, const b2k_vec* X,
-                                  int32_t p, const double* M_host, int32_t ldm) {
-    if (!ctx || !X || !Y || !M_host || p < 1 || q < 1 || ldm < p) return B2K_EINVAL;
-    for (int j = 0; j < q; ++j)
-        B2K_TRY(b2k_basis_unproject(ctx, Y[j], X, p, M_host + (size_t)j * ldm, -1.0, 1.0));
-    return B2K_OK;
-}
+// b2k_block_inner / b2k_block_axpy: multi-right-hand-side kernels, block.cu
 
 extern "C" int32_t b2k_block_reorthogonalize(b2k_ctx* ctx, const b2k_vec* Rb, int32_t p,
                                              const b2k_vec* V, int32_t k) {

@@ -1,0 +1,518 @@
+// block.cu — the B200-first block path: multi-right-hand-side tall-skinny products for
+// BlockLanczos.  The reference runs its block primitives as loops of single-vector calls
+// (src/factorizations/blocklanczos.jl:43-52 block_inner, :232-263 block_lanczosrecurrence, :277-284
+// block_reorthogonalize!, :312-353 block_qr!); on a GPU that reads the basis once per vector of the block.
+// Here a 256-row tile of the kq basis columns AND the p block columns is resident in shared memory (same TMA
+// ring as the single-vector engine, tsk.cuh), so the basis is read ONCE for all p vectors:
+//
+//   k_block_phase<PROJECT> : H = V' R          (kq + p) W bytes   (the reference loop: kq * p * 2W)
+//   k_block_phase<UPDATE>  : R -= V H, and the Gram matrix G = R' R of the result for free
+//                                               (kq + 2p) W bytes  (reference: kq * p * 3W)
+//
+// on top of which sit block_inner / the block residual update (exact same mathematics as the reference, one
+// launch per 48 basis columns), a flagged block-classical-Gram-Schmidt-twice orthogonalisation against V, and a
+// flagged CholeskyQR2 for block_qr! (Gram -> Cholesky on the host -> triangular basis transform, twice).
+// Everything is deterministic: per-CTA partials summed in CTA order.
+#include "tsk.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+using namespace tsk;
+
+namespace {
+
+constexpr int BK_QMAX = 48;    // basis columns per pass (6 per consumer warp)
+constexpr int BK_PMAX = 8;     // block size
+constexpr int BK_JW = BK_QMAX / 8;
+constexpr int BK_OFF_H = OFF_WRING;                     // coefficients (UPDATE): kq x p doubles <= 3 KB
+constexpr int BK_OFF_G = OFF_WRING + 4096;              // Gram reduction scratch: 8 warps x 36 doubles
+constexpr int BK_PART = BK_QMAX * BK_PMAX;              // doubles per CTA partial row (384)
+constexpr int BK_GRAM = BK_PMAX * BK_PMAX;              // 64
+
+template <typename T>
+struct BlockParams {
+    const T* base;        // slab base of the space
+    int64_t ld, n;
+    int32_t kq, p;        // basis columns in this pass, block size; columns list = [kq basis | p block]
+    const double* H;      // UPDATE: device coefficients, column-major kq x p with leading dimension ldh
+    int32_t ldh;
+    T alpha;              // UPDATE: R -= alpha-signed: r = fma(q, alpha * H[j][i], r)
+    double* part;         // PROJECT: [grid][BK_PART] partials (index i * BK_QMAX + j)
+    double* gpart;        // UPDATE: [grid][BK_GRAM] Gram partials (may be nullptr)
+    int32_t store;        // UPDATE: write the block back (0 when only the Gram matrix is wanted)
+};
+
+// the panel part of producer_phase (no streamed vector): chunk g of every tile is issued by producer warp g % NPROD
+template <typename T>
+__device__ __forceinline__ void producer_cols(const T* base, int64_t ld, int64_t n, int k, const ColList& cl,
+                                              const SmemView& sm) {
+    using CF = Cfg<T>;
+    constexpr int R = CF::R, C = CF::C;
+    const int lane = threadIdx.x & 31;
+    const uint32_t me = (threadIdx.x - NCONS) >> 5;
+    const int nch = (k + C - 1) / C;
+    const int64_t ntiles = (n + R - 1) / R;
+    uint32_t s = 0, ph = 0, g = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((n - r0) < R ? (n - r0) : R);
+        const uint32_t bytes = (uint32_t)((rt * sizeof(T) + 15) & ~(size_t)15);
+        for (int c = 0; c < nch; ++c) {
+            if ((g % NPROD) == me) {
+                mbar_wait(sm.empty + 8 * s, ph ^ 1);
+                const int ncol = (k - c * C) < C ? (k - c * C) : C;
+                if (lane == 0) mbar_expect_tx(sm.full + 8 * s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(sm.ring + s * SLOT_BYTES + lane * R * (int)sizeof(T),
+                             base + (int64_t)cl.c[c * C + lane] * ld + r0, bytes, sm.full + 8 * s);
+            }
+            ++g;
+            if (++s == NS) { s = 0; ph ^= 1; }
+        }
+    }
+}
+
+// column j of the resident tile that starts at ring slot s0
+template <typename T>
+__device__ __forceinline__ const T* tile_col(uint8_t* smem, uint32_t s0, int j) {
+    constexpr int C = Cfg<T>::C, R = Cfg<T>::R;
+    uint32_t s = s0 + (uint32_t)(j / C);
+    if (s >= NS) s -= NS;
+    return reinterpret_cast<const T*>(smem + OFF_RING + s * SLOT_BYTES) + (j % C) * R;
+}
+
+template <typename T, bool UPDATE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ ColList cl) {
+    using CF = Cfg<T>;
+    using V16 = typename CF::V16;
+    constexpr int R = CF::R, C = CF::C, VEC = CF::VEC;
+    constexpr int NLD = R / (32 * VEC);
+    extern __shared__ __align__(128) uint8_t smem[];
+    SmemView sm(smem);
+    pipe_setup(sm, true);     // ragged tiles multiply stale rows by nothing here, but keep the ring finite
+    const int kt = p.kq + p.p;
+    const int nch = (kt + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    if (threadIdx.x >= NCONS) {
+        producer_cols<T>(p.base, p.ld, p.n, kt, cl, sm);
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t s = 0, ph = 0;
+    if (!UPDATE) {
+        // ---- PROJECT: warp w owns basis columns j = w, w + 8, ...; lane <-> rows (128-bit LDS)
+        T acc[BK_JW][BK_PMAX];
+#pragma unroll
+        for (int a = 0; a < BK_JW; ++a)
+#pragma unroll
+            for (int i = 0; i < BK_PMAX; ++i) acc[a][i] = (T)0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t s0 = s;
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(sm.full + 8 * s, ph);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+#pragma unroll
+            for (int a = 0; a < BK_JW; ++a) {
+                const int j = a * 8 + w;
+                if (j < p.kq) {
+                    const T* qc = tile_col<T>(smem, s0, j);
+                    // rows >= rt of a ragged last tile hold stale but FINITE data (an earlier tile or the zeroed
+                    // ring): masking the block side below is enough
+                    V16 q[NLD];
+#pragma unroll
+                    for (int u = 0; u < NLD; ++u) q[u] = *reinterpret_cast<const V16*>(qc + VEC * lane + 32 * VEC * u);
+#pragma unroll
+                    for (int i = 0; i < BK_PMAX; ++i) {
+                        if (i < p.p) {
+                            const T* rc = tile_col<T>(smem, s0, p.kq + i);
+#pragma unroll
+                            for (int u = 0; u < NLD; ++u) {
+                                V16 x = *reinterpret_cast<const V16*>(rc + VEC * lane + 32 * VEC * u);
+                                T* xe = reinterpret_cast<T*>(&x);
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e)
+                                    if (VEC * lane + 32 * VEC * u + e >= rt) xe[e] = (T)0;
+                                VecOps<T>::fma_acc(acc[a][i], q[u], x);
+                            }
+                        }
+                    }
+                }
+            }
+            // release the tile
+            __syncwarp();
+            uint32_t ss = s0;
+            for (int c = 0; c < nch; ++c) {
+                if (lane == 0) mbar_arrive(sm.empty + 8 * ss);
+                if (++ss == NS) ss = 0;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < BK_JW; ++a) {
+            const int j = a * 8 + w;
+#pragma unroll
+            for (int i = 0; i < BK_PMAX; ++i) {
+                const double v = warp_sum((double)acc[a][i]);
+                if (j < p.kq && i < p.p && lane == 0)
+                    p.part[(size_t)blockIdx.x * BK_PART + i * BK_QMAX + j] = v;
+            }
+        }
+        return;
+    }
+    // ---- UPDATE: thread <-> row; r_i -= sum_j q_j H[j][i] (sequential fma over j: the association of the
+    // reference's chain of add!! calls), then the Gram matrix of the updated block
+    T* Hs = reinterpret_cast<T*>(smem + BK_OFF_H);
+    for (int idx = tid; idx < p.kq * BK_PMAX; idx += NCONS) {
+        const int j = idx / BK_PMAX, i = idx - j * BK_PMAX;
+        Hs[idx] = (i < p.p) ? p.alpha * (T)p.H[(size_t)i * p.ldh + j] : (T)0;
+    }
+    named_bar_sync(1, NCONS);
+    T g[BK_PMAX * (BK_PMAX + 1) / 2];
+#pragma unroll
+    for (int t = 0; t < BK_PMAX * (BK_PMAX + 1) / 2; ++t) g[t] = (T)0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        const uint32_t s0 = s;
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(sm.full + 8 * s, ph);
+            if (++s == NS) { s = 0; ph ^= 1; }
+        }
+        T r[BK_PMAX];
+#pragma unroll
+        for (int i = 0; i < BK_PMAX; ++i) r[i] = (i < p.p && tid < rt) ? tile_col<T>(smem, s0, p.kq + i)[tid] : (T)0;
+        for (int j = 0; j < p.kq; ++j) {
+            const T q = (tid < rt) ? tile_col<T>(smem, s0, j)[tid] : (T)0;
+            const T* h = Hs + j * BK_PMAX;
+#pragma unroll
+            for (int i = 0; i < BK_PMAX; ++i) r[i] = fma(q, h[i], r[i]);
+        }
+        if (p.store && tid < rt) {
+#pragma unroll
+            for (int i = 0; i < BK_PMAX; ++i)
+                if (i < p.p) const_cast<T*>(p.base)[(int64_t)cl.c[p.kq + i] * p.ld + r0 + tid] = r[i];
+        }
+        if (p.gpart) {
+            int t = 0;
+#pragma unroll
+            for (int i1 = 0; i1 < BK_PMAX; ++i1)
+#pragma unroll
+                for (int i2 = i1; i2 < BK_PMAX; ++i2) { g[t] = fma(r[i1], r[i2], g[t]); ++t; }
+        }
+        __syncwarp();
+        uint32_t ss = s0;
+        for (int c = 0; c < nch; ++c) {
+            if (lane == 0) mbar_arrive(sm.empty + 8 * ss);
+            if (++ss == NS) ss = 0;
+        }
+    }
+    if (p.gpart) {
+        double* red = reinterpret_cast<double*>(smem + BK_OFF_G);      // [8 warps][36]
+        constexpr int NT = BK_PMAX * (BK_PMAX + 1) / 2;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double v = warp_sum((double)g[t]);
+            if (lane == 0) red[w * NT + t] = v;
+        }
+        named_bar_sync(1, NCONS);
+        if (tid < NT) {
+            double a = 0.0;
+            for (int ww = 0; ww < NCONS / 32; ++ww) a += red[ww * NT + tid];
+            // unpack t -> (i1, i2)
+            int i1 = 0, t = tid;
+            while (t >= BK_PMAX - i1) { t -= BK_PMAX - i1; ++i1; }
+            const int i2 = i1 + t;
+            p.gpart[(size_t)blockIdx.x * BK_GRAM + i1 * BK_PMAX + i2] = a;
+            p.gpart[(size_t)blockIdx.x * BK_GRAM + i2 * BK_PMAX + i1] = a;
+        }
+    }
+}
+
+// out[idx] (+)= sum over CTAs of part[g * stride + map(idx)], fixed order.  PROJECT layout: idx = i * ldo + j
+// reads part[i * BK_QMAX + j]; Gram layout: idx = i1 * p + i2 reads part[i1 * BK_PMAX + i2].
+__global__ void __launch_bounds__(256)
+k_block_finalize(const double* __restrict__ part, int G, int stride, int rows, int cols, int src_ld, double* out,
+                 int out_ld, int accumulate) {
+    for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+        const int i = idx / rows, j = idx - i * rows;     // column i, row j of the (rows x cols) result
+        double a = 0.0;
+        for (int g = 0; g < G; ++g) a += part[(size_t)g * stride + i * src_ld + j];
+        double* o = out + (size_t)i * out_ld + j;
+        *o = accumulate ? (*o + a) : a;
+    }
+}
+
+int grid_rows(const b2k_ctx* ctx, int64_t n) {
+    int64_t ntiles = (n + 255) / 256;
+    if (ntiles < 1) ntiles = 1;
+    return (int)std::min<int64_t>(ntiles, ctx->num_sms);
+}
+
+struct BPanel {
+    void* base = nullptr;
+    int64_t ld = 0, n = 0;
+    int32_t sharded = 1, space = -1;
+    std::vector<int32_t> q, r;
+};
+
+int32_t make_bpanel(b2k_ctx* ctx, const b2k_vec* V, int32_t k, const b2k_vec* Rb, int32_t p, BPanel* bp) {
+    int32_t sv = -1, sr = -1;
+    B2K_TRY(b2k_resolve_cols(ctx, Rb, p, &sr, &bp->r));
+    if (k > 0) {
+        B2K_TRY(b2k_resolve_cols(ctx, V, k, &sv, &bp->q));
+        if (sv != sr) return b2k_fail(ctx, B2K_EDIM, "block operation: basis and block live in different spaces");
+    }
+    const B2kSpace& s = ctx->spaces[sr];
+    bp->base = s.base; bp->ld = s.ld; bp->n = s.n; bp->sharded = s.sharded; bp->space = sr;
+    return B2K_OK;
+}
+
+// d_blk layout (doubles): [0, HCAP) H1, [HCAP, 2 HCAP) H2, then the Gram matrix
+constexpr int HCAP = B2K_BLK_HCAP;
+static_assert(BK_PART == B2K_BLK_PART, "partial row size");
+
+template <typename T>
+int32_t launch_project(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, double* d_H, int ldh, bool accumulate) {
+    const int p = (int)bp.r.size();
+    ColList cl;
+    for (int j = 0; j < kq; ++j) cl.c[j] = bp.q[q0 + j];
+    for (int i = 0; i < p; ++i) cl.c[kq + i] = bp.r[i];
+    BlockParams<T> bpar;
+    memset(&bpar, 0, sizeof(bpar));
+    bpar.base = (const T*)bp.base; bpar.ld = bp.ld; bpar.n = bp.n; bpar.kq = kq; bpar.p = p;
+    bpar.part = ctx->d_blkpart;
+    const int grid = grid_rows(ctx, bp.n);
+    const int pr = b2k_prof_begin(ctx, 5, (double)(kq + p) * sizeof(T) * (double)bp.n);
+    k_block_phase<T, false><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    k_block_finalize<<<1, 256, 0, ctx->stream>>>(ctx->d_blkpart, grid, BK_PART, kq, p, BK_QMAX, d_H + q0, ldh,
+                                                accumulate ? 1 : 0);
+    B2K_LAUNCH_CHECK(ctx);
+    return B2K_OK;
+}
+
+template <typename T>
+int32_t launch_update(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, const double* d_H, int ldh, double alpha,
+                      double* d_G, bool store) {
+    const int p = (int)bp.r.size();
+    ColList cl;
+    for (int j = 0; j < kq; ++j) cl.c[j] = bp.q[q0 + j];
+    for (int i = 0; i < p; ++i) cl.c[kq + i] = bp.r[i];
+    BlockParams<T> bpar;
+    memset(&bpar, 0, sizeof(bpar));
+    bpar.base = (const T*)bp.base; bpar.ld = bp.ld; bpar.n = bp.n; bpar.kq = kq; bpar.p = p;
+    bpar.H = d_H ? d_H + q0 : nullptr; bpar.ldh = ldh; bpar.alpha = (T)alpha;
+    bpar.gpart = d_G ? ctx->d_blkpart : nullptr;
+    bpar.store = store ? 1 : 0;
+    const int grid = grid_rows(ctx, bp.n);
+    const int pr = b2k_prof_begin(ctx, 6, (double)(kq + (store ? 2 : 1) * p) * sizeof(T) * (double)bp.n);
+    k_block_phase<T, true><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    if (d_G) {
+        k_block_finalize<<<1, 256, 0, ctx->stream>>>(ctx->d_blkpart, grid, BK_GRAM, p, p, BK_PMAX, d_G, p, 0);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    return B2K_OK;
+}
+
+// H (k x p, ld = k) = V' R on the device, all passes; all-reduced when sharded
+int32_t block_project_dev(b2k_ctx* ctx, const BPanel& bp, double* d_H, bool accumulate) {
+    const int k = (int)bp.q.size(), p = (int)bp.r.size();
+    for (int q0 = 0; q0 < k; q0 += BK_QMAX) {
+        const int kq = std::min(BK_QMAX, k - q0);
+        if (ctx->dtype == B2K_F64) B2K_TRY(launch_project<double>(ctx, bp, q0, kq, d_H, k, accumulate));
+        else B2K_TRY(launch_project<float>(ctx, bp, q0, kq, d_H, k, accumulate));
+    }
+    if (!accumulate) B2K_TRY(b2k_allreduce(ctx, d_H, k * p, bp.sharded));
+    return B2K_OK;
+}
+
+// R += alpha * V H; optionally the Gram matrix of the result (last pass)
+int32_t block_update_dev(b2k_ctx* ctx, const BPanel& bp, const double* d_H, double alpha, double* d_G) {
+    const int k = (int)bp.q.size(), p = (int)bp.r.size();
+    for (int q0 = 0; q0 < k; q0 += BK_QMAX) {
+        const int kq = std::min(BK_QMAX, k - q0);
+        const bool lastp = q0 + kq >= k;
+        if (ctx->dtype == B2K_F64) B2K_TRY(launch_update<double>(ctx, bp, q0, kq, d_H, k, alpha, lastp ? d_G : nullptr, true));
+        else B2K_TRY(launch_update<float>(ctx, bp, q0, kq, d_H, k, alpha, lastp ? d_G : nullptr, true));
+    }
+    if (d_G) B2K_TRY(b2k_allreduce(ctx, d_G, p * p, bp.sharded));
+    return B2K_OK;
+}
+
+int32_t block_gram_dev(b2k_ctx* ctx, const BPanel& bp, double* d_G) {
+    const int p = (int)bp.r.size();
+    if (ctx->dtype == B2K_F64) B2K_TRY(launch_update<double>(ctx, bp, 0, 0, nullptr, 1, 0.0, d_G, false));
+    else B2K_TRY(launch_update<float>(ctx, bp, 0, 0, nullptr, 1, 0.0, d_G, false));
+    return b2k_allreduce(ctx, d_G, p * p, bp.sharded);
+}
+
+int32_t fetch(b2k_ctx* ctx, const double* d, double* h, int count) {
+    B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, d, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h, ctx->h_res, sizeof(double) * count);
+    return B2K_OK;
+}
+
+}  // namespace
+
+int32_t b2k_block_init(b2k_ctx* ctx) {
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ C ABI ----
+
+// block_inner(X, Y): M[i, j] = <X[i], Y[j]> — blocklanczos.jl:43-52 — one launch per 48 vectors of X
+extern "C" int32_t b2k_block_inner(b2k_ctx* ctx, const b2k_vec* X, int32_t p, const b2k_vec* Y,
+                                   int32_t q, double* M_host) {
+    if (!ctx || !X || !Y || !M_host || p < 1 || q < 1) return B2K_EINVAL;
+    if (p * BK_PMAX > HCAP || (int64_t)p * q > B2K_RES_DOUBLES) return b2k_fail(ctx, B2K_ENOTSUP, "block_inner: p*q too large");
+    for (int j0 = 0; j0 < q; j0 += BK_PMAX) {           // blocks of up to 8 right-hand sides
+        const int qq = std::min(BK_PMAX, q - j0);
+        BPanel bp;
+        B2K_TRY(make_bpanel(ctx, X, p, Y + j0, qq, &bp));
+        B2K_TRY(block_project_dev(ctx, bp, ctx->d_blk, false));
+        B2K_TRY(fetch(ctx, ctx->d_blk, M_host + (size_t)j0 * p, p * qq));
+    }
+    return B2K_OK;
+}
+
+// Y[j] -= sum_i X[i] M[i, j] — the double loops of blocklanczos.jl:177-181, 245-252 — one launch per 48 vectors of X
+extern "C" int32_t b2k_block_axpy(b2k_ctx* ctx, const b2k_vec* Y, int32_t q, const b2k_vec* X,
+                                  int32_t p, const double* M_host, int32_t ldm) {
+    if (!ctx || !X || !Y || !M_host || p < 1 || q < 1 || ldm < p) return B2K_EINVAL;
+    if (p * BK_PMAX > HCAP) return b2k_fail(ctx, B2K_ENOTSUP, "block_axpy: p too large");
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < q; ++j)
+            if (X[i] == Y[j]) return b2k_fail(ctx, B2K_EINVAL, "block_axpy: Y[%d] aliases X[%d]", j, i);
+    for (int j0 = 0; j0 < q; j0 += BK_PMAX) {
+        const int qq = std::min(BK_PMAX, q - j0);
+        BPanel bp;
+        B2K_TRY(make_bpanel(ctx, X, p, Y + j0, qq, &bp));
+        std::vector<double> Hc((size_t)p * qq);
+        for (int j = 0; j < qq; ++j)
+            for (int i = 0; i < p; ++i) Hc[(size_t)j * p + i] = M_host[(size_t)(j0 + j) * ldm + i];
+        if (p * qq > B2K_COEF_DOUBLES) return b2k_fail(ctx, B2K_ENOTSUP, "block_axpy: coefficient block too large");
+        B2K_TRY(b2k_put_coef(ctx, Hc.data(), p * qq, 0));
+        B2K_TRY(block_update_dev(ctx, bp, ctx->d_coef, -1.0, nullptr));
+    }
+    return B2K_OK;
+}
+
+// Flagged B200-first replacement of block_reorthogonalize! (blocklanczos.jl:277-284, one MGS sweep per vector):
+// block classical Gram-Schmidt against V, `passes` times (2 = BCGS2), the basis read once per pass for the whole
+// block.  H_host (k x p, column-major, may be NULL) receives the summed coefficients, G_host (p x p, may be NULL)
+// the Gram matrix R' R of the orthogonalised block (what CholeskyQR needs next).  One host synchronisation.
+extern "C" int32_t b2k_block_orthogonalize(b2k_ctx* ctx, const b2k_vec* Rb, int32_t p, const b2k_vec* V, int32_t k,
+                                           int32_t passes, double* H_host, double* G_host) {
+    if (!ctx || !Rb || p < 1 || p > BK_PMAX || k < 0 || (k > 0 && !V) || passes < 1 || passes > 2) return B2K_EINVAL;
+    if (k * p > HCAP) return b2k_fail(ctx, B2K_ENOTSUP, "block_orthogonalize: k * p > %d", HCAP);
+    BPanel bp;
+    B2K_TRY(make_bpanel(ctx, V, k, Rb, p, &bp));
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < k; ++j)
+            if (Rb[i] == V[j]) return b2k_fail(ctx, B2K_EINVAL, "block_orthogonalize: R[%d] aliases V[%d]", i, j);
+    double* d_H1 = ctx->d_blk;
+    double* d_H2 = ctx->d_blk + HCAP;
+    double* d_G = ctx->d_blk + 2 * HCAP;
+    if (k == 0) {
+        if (G_host) {
+            B2K_TRY(block_gram_dev(ctx, bp, d_G));
+            B2K_TRY(fetch(ctx, d_G, G_host, p * p));
+        }
+        return B2K_OK;
+    }
+    B2K_TRY(block_project_dev(ctx, bp, d_H1, false));
+    B2K_TRY(block_update_dev(ctx, bp, d_H1, -1.0, (passes == 1 && G_host) ? d_G : nullptr));
+    if (passes == 2) {
+        B2K_TRY(block_project_dev(ctx, bp, d_H2, false));
+        B2K_TRY(block_update_dev(ctx, bp, d_H2, -1.0, G_host ? d_G : nullptr));
+    }
+    static_assert(2 * HCAP + BK_GRAM <= B2K_RES_DOUBLES, "block results must fit the pinned result buffer");
+    B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_blk, sizeof(double) * (2 * HCAP + BK_GRAM), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (H_host)
+        for (int t = 0; t < k * p; ++t) H_host[t] = ctx->h_res[t] + (passes == 2 ? ctx->h_res[HCAP + t] : 0.0);
+    if (G_host) memcpy(G_host, ctx->h_res + 2 * HCAP, sizeof(double) * p * p);
+    return B2K_OK;
+}
+
+// Flagged B200-first block_qr! (blocklanczos.jl:312-353): CholeskyQR2.  G = X' X (one pass), G = L L' on the host,
+// X <- X L^-T (triangular basis transform, in place), twice; R = L2' L1' is upper triangular with a positive
+// diagonal, i.e. the SAME factor modified Gram-Schmidt produces (the QR factorization with positive diagonal is
+// unique), to rounding.  *ok = 0 when a Cholesky pivot falls below (100 tol)^2 relative to its column's norm^2
+// (numerically rank-deficient block: the caller falls back to the reference's MGS b2k_block_qr, which knows how
+// to drop vectors); X is then unchanged.
+extern "C" int32_t b2k_block_cholqr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, double tol, const double* G0_host,
+                                    double* R_host, int32_t* ok) {
+    if (!ctx || !X || !R_host || !ok || p < 1 || p > BK_PMAX) return B2K_EINVAL;
+    *ok = 0;
+    BPanel bp;
+    B2K_TRY(make_bpanel(ctx, nullptr, 0, X, p, &bp));
+    double* d_G = ctx->d_blk + 2 * HCAP;
+    std::vector<double> G(p * p), L(p * p), Rtot(p * p, 0.0), Linv(p * p);
+    for (int i = 0; i < p; ++i) Rtot[i * p + i] = 1.0;
+    for (int round = 0; round < 2; ++round) {
+        if (round == 0 && G0_host) {
+            memcpy(G.data(), G0_host, sizeof(double) * p * p);
+        } else {
+            B2K_TRY(block_gram_dev(ctx, bp, d_G));
+            B2K_TRY(fetch(ctx, d_G, G.data(), p * p));
+        }
+        // Cholesky G = L L' (column-major, lower)
+        std::fill(L.begin(), L.end(), 0.0);
+        for (int j = 0; j < p; ++j) {
+            double d = G[j * p + j];
+            for (int t = 0; t < j; ++t) d -= L[t * p + j] * L[t * p + j];
+            const double thr = (round == 0) ? (100.0 * tol) * (100.0 * tol) : 0.0;
+            if (!(d > thr) || !(d > 1e-28 * G[j * p + j])) {
+                if (round == 0) return B2K_OK;             // *ok = 0, X untouched
+                return b2k_fail(ctx, B2K_ECUDA, "block_cholqr: second Cholesky lost positivity");
+            }
+            L[j * p + j] = sqrt(d);
+            for (int i = j + 1; i < p; ++i) {
+                double s = G[j * p + i];
+                for (int t = 0; t < j; ++t) s -= L[t * p + i] * L[t * p + j];
+                L[j * p + i] = s / L[j * p + j];
+            }
+        }
+        // U = L^-T (upper triangular): X <- X U
+        std::fill(Linv.begin(), Linv.end(), 0.0);       // Linv = L^-1 (lower), column-major
+        for (int j = 0; j < p; ++j) {
+            Linv[j * p + j] = 1.0 / L[j * p + j];
+            for (int i = j + 1; i < p; ++i) {
+                double s = 0.0;
+                for (int t = j; t < i; ++t) s += L[t * p + i] * Linv[j * p + t];
+                Linv[j * p + i] = -s / L[i * p + i];
+            }
+        }
+        std::vector<double> U(p * p, 0.0);               // U[i, j] = Linv[j, i]
+        for (int j = 0; j < p; ++j)
+            for (int i = 0; i <= j; ++i) U[j * p + i] = Linv[i * p + j];
+        B2K_TRY(b2k_basis_transform(ctx, X, p, U.data(), p, p));
+        // R_total <- L' * R_total
+        std::vector<double> Rn(p * p, 0.0);
+        for (int j = 0; j < p; ++j)
+            for (int i = 0; i < p; ++i) {
+                double s = 0.0;
+                for (int t = i; t < p; ++t) s += L[i * p + t] * Rtot[j * p + t];    // L'[i, t] = L[t, i]
+                Rn[j * p + i] = s;
+            }
+        Rtot = Rn;
+    }
+    memcpy(R_host, Rtot.data(), sizeof(double) * p * p);
+    *ok = 1;
+    return B2K_OK;
+}

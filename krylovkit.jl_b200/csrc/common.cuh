@@ -68,6 +68,8 @@ struct b2k_ctx {
     double*   h_coef   = nullptr;   // pinned staging
     unsigned* d_sync   = nullptr;   // [0] ticket, [1] grid barrier counter, ... (B2K_SYNC_*)
     double*   d_steps  = nullptr;   // (B2K_MAX_CHAIN + 1) step records of B2K_REC doubles
+    double*   d_blk    = nullptr;   // block path (block.cu): coefficient blocks H1 | H2 | Gram
+    double*   d_blkpart = nullptr;  // block path: per-CTA partials
     cudaEvent_t ev_coef = nullptr;  // guards reuse of the pinned staging buffers
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // b2k_timer_start/stop
     bool      coef_busy = false;
@@ -190,6 +192,9 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
 // basis.cu / spmv.cu
 int32_t b2k_basis_init(b2k_ctx* ctx);
 int32_t b2k_spmv_init(b2k_ctx* ctx);
+int32_t b2k_block_init(b2k_ctx* ctx);
+constexpr int B2K_BLK_HCAP = 3968;        // doubles per coefficient block (k * p <= HCAP)
+constexpr int B2K_BLK_PART = 384;         // doubles per CTA partial row
 
 // ----------------------------------------------------------------------------------
 // NVLink peer window (dist.cu).  Every rank owns one cudaMalloc'ed window that all other ranks of the node

@@ -234,6 +234,8 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
     CK(b2k_hmalloc((void**)&ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES));
     CK(B2K_DMALLOC(&ctx->d_steps, sizeof(double) * B2K_REC * (B2K_MAX_CHAIN + 1)));
     CK(cudaMemsetAsync(ctx->d_steps, 0, sizeof(double) * B2K_REC * (B2K_MAX_CHAIN + 1), ctx->stream));
+    CK(B2K_DMALLOC(&ctx->d_blk, sizeof(double) * (2 * B2K_BLK_HCAP + 64)));
+    CK(B2K_DMALLOC(&ctx->d_blkpart, sizeof(double) * (size_t)B2K_MAX_GRID * B2K_BLK_PART));
     CK(B2K_DMALLOC(&ctx->d_sync, sizeof(unsigned) * 64));
     CK(cudaMemsetAsync(ctx->d_sync, 0, sizeof(unsigned) * 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_part, 0, sizeof(double) * 4 * (size_t)B2K_MAX_GRID * B2K_KSTRIDE,
@@ -243,6 +245,7 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
     int32_t sp = 0;
     int32_t rc = b2k_basis_init(ctx);
     if (rc == B2K_OK) rc = b2k_spmv_init(ctx);
+    if (rc == B2K_OK) rc = b2k_block_init(ctx);
     if (rc == B2K_OK) rc = make_space(ctx, n_local, ncols, 1, &sp);
     if (rc != B2K_OK) {
         g_b2k_create_error = ctx->err;
@@ -301,6 +304,8 @@ extern "C" int32_t b2k_ctx_destroy(b2k_ctx* ctx) {
     b2k_hfree(ctx->h_coef, sizeof(double) * B2K_COEF_DOUBLES);
     if (ctx->d_sync) B2K_DFREE(ctx->d_sync);
     if (ctx->d_steps) B2K_DFREE(ctx->d_steps);
+    if (ctx->d_blk) B2K_DFREE(ctx->d_blk);
+    if (ctx->d_blkpart) B2K_DFREE(ctx->d_blkpart);
     if (ctx->ev_coef) cudaEventDestroy(ctx->ev_coef);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);

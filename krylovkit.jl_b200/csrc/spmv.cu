@@ -386,6 +386,136 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     }
 }
 
+// SpMM for apply(A, ::Block) (blocklanczos.jl:38): the nonzero stream of a row block is staged ONCE (same TMA
+// ring as k_spmv_pipe) and used for all p <= 8 vectors of the block: 12*nnz + p*16n bytes instead of
+// p*(12*nnz + 16n).  One thread per row walks the row's staged nonzeros and keeps p running sums; products are
+// rounded before they are added, in CSR order — bit-identical to p single-vector applies.
+constexpr int SPM_PMAX = 8;
+struct SpmmCols {
+    int32_t x[SPM_PMAX], y[SPM_PMAX];
+};
+
+template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(SPP_THREADS, 3)
+k_spmm_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
+            T* __restrict__ base, int64_t ld, const __grid_constant__ SpmmCols cols, int np,
+            const int32_t* __restrict__ rowblk, const int32_t* __restrict__ pblk, int nblk) {
+    using LY = SppLayout<T>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + SPP_NSTG * 8;
+    double* red = reinterpret_cast<double*>(smem + LY::OFF_RED);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SPP_NSTG; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, SPP_CONS / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= SPP_CONS) {
+        // producer warp: identical to k_spmv_pipe
+        int tile = blockIdx.x;
+        int d = 0;
+        if (tile < nblk && lane < 4) d = (lane < 2) ? rowblk[tile + lane] : pblk[tile + lane - 2];
+        for (; tile < nblk; tile += gridDim.x) {
+            const int r0 = __shfl_sync(0xffffffffu, d, 0), r1 = __shfl_sync(0xffffffffu, d, 1);
+            const int p0 = __shfl_sync(0xffffffffu, d, 2), p1 = __shfl_sync(0xffffffffu, d, 3);
+            const int nt = tile + gridDim.x;
+            if (nt < nblk && lane < 4) d = (lane < 2) ? rowblk[nt + lane] : pblk[nt + lane - 2];
+            mbar_wait(empty + 8 * s, ph ^ 1);
+            const int nnzb = p1 - p0, nrows = r1 - r0;
+            if (nnzb <= SP_NNZ) {
+                const int p0a = p0 & ~3, cnt = ((p1 + 3) & ~3) - p0a;
+                const int r0a = r0 & ~3;
+                const int rcnt = (nrows <= SPP_RMAX) ? (((r1 + 1 + 3) & ~3) - r0a) : 0;
+                const uint32_t vb = (uint32_t)cnt * (uint32_t)sizeof(T), cb = (uint32_t)cnt * 4u, rb = (uint32_t)rcnt * 4u;
+                const uint32_t st = smem_u32(smem + s * LY::STAGE);
+                if (lane == 0) mbar_expect_tx(full + 8 * s, vb + cb + rb);
+                __syncwarp();
+                if (lane == 0 && vb) bulk_g2s(st, vals + p0a, vb, full + 8 * s);
+                if (lane == 1 && cb) bulk_g2s(st + LY::VAL_BYTES, colidx + p0a, cb, full + 8 * s);
+                if (lane == 2 && rb) bulk_g2s(st + LY::VAL_BYTES + LY::COL_BYTES, rowptr + r0a, rb, full + 8 * s);
+            } else {
+                if (lane == 0) mbar_arrive(full + 8 * s);
+            }
+            if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+        }
+        return;
+    }
+    const int tid = threadIdx.x, w = tid >> 5;
+    const T* xp[SPM_PMAX];
+    T* yp[SPM_PMAX];
+#pragma unroll
+    for (int i = 0; i < SPM_PMAX; ++i) {
+        xp[i] = base + (int64_t)cols.x[i < np ? i : 0] * ld;
+        yp[i] = base + (int64_t)cols.y[i < np ? i : 0] * ld;
+    }
+    int tile = blockIdx.x;
+    int4 dn = make_int4(0, 0, 0, 0);
+    if (tile < nblk) dn = make_int4(rowblk[tile], rowblk[tile + 1], pblk[tile], pblk[tile + 1]);
+    for (; tile < nblk; tile += gridDim.x) {
+        const int r0 = dn.x, r1 = dn.y, p0 = dn.z, p1 = dn.w;
+        const int nt = tile + gridDim.x;
+        if (nt < nblk) dn = make_int4(rowblk[nt], rowblk[nt + 1], pblk[nt], pblk[nt + 1]);
+        const int nnzb = p1 - p0, nrows = r1 - r0;
+        mbar_wait(full + 8 * s, ph);
+        if (nnzb <= SP_NNZ) {
+            const T* vs = reinterpret_cast<const T*>(smem + s * LY::STAGE);
+            const int32_t* cs = reinterpret_cast<const int32_t*>(smem + s * LY::STAGE + LY::VAL_BYTES);
+            const int32_t* rs = reinterpret_cast<const int32_t*>(smem + s * LY::STAGE + LY::VAL_BYTES + LY::COL_BYTES);
+            const int p0a = p0 & ~3, r0a = r0 & ~3;
+            const bool rp_staged = nrows <= SPP_RMAX;
+            for (int r = r0 + tid; r < r1; r += SPP_CONS) {
+                int a, b;
+                if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
+                else { a = rowptr[r]; b = rowptr[r + 1]; }
+                a -= p0a; b -= p0a;
+                T sum[SPM_PMAX];
+#pragma unroll
+                for (int i = 0; i < SPM_PMAX; ++i) sum[i] = (T)0;
+                for (int q = a; q < b; ++q) {
+                    const T v = vs[q];
+                    const int32_t c = cs[q];
+#pragma unroll
+                    for (int i = 0; i < SPM_PMAX; ++i)
+                        if (i < np) sum[i] = add_rn<T>(sum[i], mul_rn<T>(v, __ldg(xp[i] + c)));
+                }
+#pragma unroll
+                for (int i = 0; i < SPM_PMAX; ++i)
+                    if (i < np) yp[i][r] = sum[i];
+            }
+        } else {
+            // long row: the CTA owns exactly one row; one vector of the block at a time
+            for (int i = 0; i < np; ++i) {
+                double acc = 0.0;
+                for (int q = tid; q < nnzb; q += SPP_CONS)
+                    acc += (double)mul_rn<T>(vals[p0 + q], __ldg(xp[i] + colidx[p0 + q]));
+                acc = warp_sum(acc);
+                named_bar_sync(1, SPP_CONS);
+                if (lane == 0) red[w] = acc;
+                named_bar_sync(1, SPP_CONS);
+                if (tid == 0) {
+                    double tot = 0.0;
+                    for (int ww = 0; ww < SPP_CONS / 32; ++ww) tot += red[ww];
+                    yp[i][r0] = (T)tot;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8 * s);
+        if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+    }
+}
+
 // Halo push through the peer window: my first send_lo entries go behind rank-1's lo entries (its hi halo), my
 // last send_hi entries to the start of rank+1's receive buffer (its lo halo); the last CTA raises the flags.
 template <typename T>
@@ -1033,6 +1163,10 @@ extern "C" int32_t b2k_debug_set_spmv_pipe(int32_t on) {
 
 // opt in to > 48 KB dynamic shared memory for the pipelined SpMV (called per context)
 int32_t b2k_spmv_init(b2k_ctx* ctx) {
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmm_pipe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<double>::SMEM));
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmm_pipe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<float>::SMEM));
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmv_pipe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SppLayout<double>::SMEM));
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmv_pipe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1229,4 +1363,44 @@ extern "C" int32_t b2k_op_apply_adjoint(b2k_ctx* ctx, const b2k_op* op, b2k_vec 
                         (long long)rx.n, (long long)op->n_rows, (long long)ry.n, (long long)op->n_cols);
     return b2k_panel_project_dev(ctx, op->A, op->ld, op->n_rows, (int32_t)op->n_cols, rx, ry.ptr,
                                  rx.sharded);
+}
+
+// apply(A, X::Block) — blocklanczos.jl:38: Y[i] = A X[i] for the p vectors of a block.  Single-GPU CSR operators
+// read the matrix once per 8 vectors (k_spmm_pipe); everything else is the loop of single applies the
+// reference runs.  Same bits either way.
+extern "C" int32_t b2k_op_apply_block(b2k_ctx* ctx, const b2k_op* op, const b2k_vec* X, const b2k_vec* Y, int32_t p) {
+    if (!ctx || !op || !X || !Y || p < 1) return B2K_EINVAL;
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < p; ++j)
+            if (X[i] == Y[j]) return b2k_fail(ctx, B2K_EINVAL, "apply_block: Y[%d] aliases X[%d]", j, i);
+    bool fast = op->kind == 0 && ctx->nranks == 1 && g_spmv_pipe && p > 1;
+    int32_t sx = -1, sy = -1;
+    std::vector<int32_t> ix, iy;
+    B2K_TRY(b2k_resolve_cols(ctx, X, p, &sx, &ix));
+    B2K_TRY(b2k_resolve_cols(ctx, Y, p, &sy, &iy));
+    fast = fast && sx == sy && ctx->spaces[sx].n == op->n_rows && op->n_rows == op->n_cols;
+    if (!fast) {
+        for (int i = 0; i < p; ++i) B2K_TRY(b2k_op_apply(ctx, op, X[i], Y[i]));
+        return B2K_OK;
+    }
+    const B2kSpace& sp = ctx->spaces[sx];
+    const int grid = std::min(op->nblk, 3 * ctx->num_sms);
+    for (int i0 = 0; i0 < p; i0 += SPM_PMAX) {
+        const int np = std::min(SPM_PMAX, p - i0);
+        SpmmCols cols;
+        for (int i = 0; i < SPM_PMAX; ++i) { cols.x[i] = ix[i0 + (i < np ? i : 0)]; cols.y[i] = iy[i0 + (i < np ? i : 0)]; }
+        const int pr = b2k_prof_begin(ctx, 7, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
+                                                  2.0 * np * ctx->esize * op->n_rows);
+        if (ctx->dtype == B2K_F64)
+            k_spmm_pipe<double><<<grid, SPP_THREADS, SppLayout<double>::SMEM, ctx->stream>>>(
+                op->rowptr, op->colidx, (const double*)op->vals, (double*)sp.base, sp.ld, cols, np, op->rowblk,
+                op->pblk, op->nblk);
+        else
+            k_spmm_pipe<float><<<grid, SPP_THREADS, SppLayout<float>::SMEM, ctx->stream>>>(
+                op->rowptr, op->colidx, (const float*)op->vals, (float*)sp.base, sp.ld, cols, np, op->rowblk,
+                op->pblk, op->nblk);
+        b2k_prof_end(ctx, pr);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    return B2K_OK;
 }

@@ -287,7 +287,7 @@ def _eigsolve_blocklanczos(A, x0: "blz.Block", howmany: int, which: str, alg: Bl
         raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} eigenvalues")
     tol = alg.tol
     bs = len(x0)
-    it = blz.BlockLanczosIterator(A, x0, krylovdim + bs, alg.orth, alg.qr_tol)
+    it = blz.BlockLanczosIterator(A, x0, krylovdim + bs, alg.orth, alg.qr_tol, fast_block=alg.fast_block)
     fact = blz.initialize(it)
     if alg.verbosity >= WARN_LEVEL and blz.warn_nonhermitian(fact.H[:fact.k, :fact.k]):
         warnings.warn("ignoring the antihermitian part of the block triangular matrix: "
@@ -340,6 +340,7 @@ def _eigsolve_blocklanczos(A, x0: "blz.Block", howmany: int, which: str, alg: Bl
             R_new = OrthonormalBasis(fact.R.vec[:bs_R])
             basistransform_(R_new, H[keep + bs - bs_R:keep + bs, keep - bs_R:keep])
             fact.R.vec[:bs_R] = R_new.basis[:bs_R]
+            fact.gram_R = None
             while len(B) > keep:
                 B.pop().free()
             fact.k = keep

@@ -100,6 +100,7 @@ class BlockLanczosFactorization:
 
     def __init__(self, k, V: OrthonormalBasis, H: np.ndarray, R: Block, R_size: int, norm_R: float):
         self.k, self.V, self.H, self.R, self.R_size, self.norm_R = k, V, H, R, R_size, norm_R
+        self.gram_R = None          # R'R when the flagged fast mode has it (saves CholeskyQR's first Gram pass)
 
     def __len__(self):
         return self.k
@@ -117,7 +118,9 @@ class BlockLanczosFactorization:
 class BlockLanczosIterator:
     """BlockLanczosIterator(f, x₀, maxdim, orth, qr_tol) — blocklanczos.jl:131-157."""
 
-    def __init__(self, operator, x0: Block, maxdim: int, orth: Orthogonalizer = mgs2, qr_tol: float = 1e-12):
+    def __init__(self, operator, x0: Block, maxdim: int, orth: Orthogonalizer = mgs2, qr_tol: float = 1e-12,
+                 fast_block: bool = False):
+        self.fast_block = fast_block
         if x0.norm() < qr_tol:
             raise ValueError("initial vector should not have norm zero")
         if not isinstance(orth, ModifiedGramSchmidt2) and orth.tag != L.MGS2:
@@ -131,8 +134,48 @@ def warn_nonhermitian(M: np.ndarray) -> bool:
                            atol=np.finfo(np.float64).eps ** 0.4)
 
 
+# FLAGGED B200-first mode (off = the reference's arithmetic: modified Gram-Schmidt everywhere).  When on,
+# block_reorthogonalize! runs as block classical Gram-Schmidt twice (the basis is read once per pass for the whole
+# block instead of once per vector and basis column) and block_qr! as CholeskyQR2; the QR factor is the same matrix
+# (the QR factorization with positive diagonal is unique), the orthogonalisation coefficients differ at rounding
+# level, Ritz values agree with the reference mode to ~1e-12.  Rank-deficient blocks fall back to the reference's
+# block_qr!.  kk.BlockLanczos(..., fast_block=True) switches it on per solve.
+FAST_BLOCK = False
+
+
 def _apply_block(operator, X: Block) -> Block:
+    """apply(f, block::Block) — blocklanczos.jl:38.  A device CSR operator reads the matrix once for the whole
+    block (b2k_op_apply_block, SpMM); same bits as the loop of single applies."""
+    from ..operators import B200CSR
+    if isinstance(operator, B200CSR) and len(X) > 1:
+        ctx = X.ctx
+        Y = [ctx.empty(x.space) for x in X]
+        ctx.check(ctx.lib.b2k_op_apply_block(ctx.h, operator.h, handles(X.vec), handles(Y), len(X)))
+        return Block(Y)
     return Block([apply(operator, x) for x in X])
+
+
+def block_orthogonalize_fast_(R: Block, V: OrthonormalBasis, want_gram: bool = True):
+    """flagged: BCGS2 of the block R against V in 4 sweeps over V; returns (V'R summed over the passes, R'R)."""
+    ctx = R.ctx
+    p, k = len(R), len(V)
+    H = np.zeros((k, p), order="F")
+    G = np.zeros((p, p), order="F")
+    ctx.check(ctx.lib.b2k_block_orthogonalize(ctx.h, handles(R.vec), p, handles(V.basis), k, 2, _dptr(H),
+                                              _dptr(G) if want_gram else None))
+    return H, G
+
+
+def block_cholqr_(block: Block, tol: float, G0: np.ndarray | None = None):
+    """flagged: CholeskyQR2 in place.  Returns (R, ok); ok = False: the block is numerically rank deficient at the
+    scale block_qr! drops vectors — nothing was changed, use block_qr_ (reference MGS with rank detection)."""
+    ctx = block.ctx
+    p = len(block)
+    R = np.zeros((p, p), order="F")
+    ok = C.c_int32()
+    g0 = _dptr(np.asfortranarray(G0, dtype=np.float64)) if G0 is not None else None
+    ctx.check(ctx.lib.b2k_block_cholqr(ctx.h, handles(block.vec), p, float(tol), g0, _dptr(R), C.byref(ok)))
+    return R, bool(ok.value)
 
 
 def initialize(it: BlockLanczosIterator) -> BlockLanczosFactorization:
@@ -155,18 +198,25 @@ def initialize(it: BlockLanczosIterator) -> BlockLanczosFactorization:
     return BlockLanczosFactorization(bs, V, BTD, AX1, bs, AX1.norm())
 
 
-def block_lanczosrecurrence(operator, V: OrthonormalBasis, B: np.ndarray):
-    """block_lanczosrecurrence(…, ::ModifiedGramSchmidt2) — blocklanczos.jl:232-251."""
+def block_lanczosrecurrence(operator, V: OrthonormalBasis, B: np.ndarray, fast: bool = False):
+    """block_lanczosrecurrence(…, ::ModifiedGramSchmidt2) — blocklanczos.jl:232-251.
+    fast (flagged): AX is orthogonalised against ALL of V by BCGS2 — which removes the X M and Xprev B' terms of
+    the three-term recurrence as part of the same sweeps (X, Xprev are columns of V) — and M = X'AX is read off the
+    summed coefficients, like lanczos.jl:313-324 does for the single-vector CGS2 recurrence.  Returns the Gram
+    matrix of the new residual as a third value (None in the reference mode)."""
     bs, bs_prev = B.shape
     k = len(V)
     X = Block(V[k - bs:k])
     AX = _apply_block(operator, X)
+    if fast and bs <= 8:
+        H, G = block_orthogonalize_fast_(AX, V)
+        return AX, H[k - bs:k, :].copy(), G
     M = block_inner(X, AX)
     Xprev = V[k - bs_prev - bs:k - bs]
     # AX[j] -= Σ_i X[i] M[i,j] + Σ_i Xprev[i] B[j,i]: one fused sweep with the stacked coefficients
     block_axpy_(AX, X.vec + list(Xprev), np.vstack([M, B.T[:len(Xprev), :]]))
     block_reorthogonalize_(AX, V)
-    return AX, M
+    return AX, M, None
 
 
 def expand_(it: BlockLanczosIterator, state: BlockLanczosFactorization) -> BlockLanczosFactorization:
@@ -175,22 +225,32 @@ def expand_(it: BlockLanczosIterator, state: BlockLanczosFactorization) -> Block
     R = state.R[:state.R_size]
     bs = len(R)
     V = state.V
-    Rcopy = R.copy()
-    B, good, drift = block_qr_(R, it.qr_tol)
-    if drift:
-        # an excessively small β in block_qr! lets the column space of R drift: re-project and redo
-        block_reorthogonalize_(R, V)
-        _, good, drift = block_qr_(R, it.qr_tol)
-        B = block_inner(R[good], Rcopy)                # keeps R = X B
+    fast = (FAST_BLOCK or it.fast_block) and bs <= 8
+    B = good = None
+    if fast:
+        B, ok = block_cholqr_(R, it.qr_tol, state.gram_R)
+        if ok:
+            good = list(range(bs))
+        else:
+            fast = False                               # rank-deficient block: this step runs in the reference mode
+    if good is None:
+        Rcopy = R.copy()
+        B, good, drift = block_qr_(R, it.qr_tol)
+        if drift:
+            # an excessively small β in block_qr! lets the column space of R drift: re-project and redo
+            block_reorthogonalize_(R, V)
+            _, good, drift = block_qr_(R, it.qr_tol)
+            B = block_inner(R[good], Rcopy)            # keeps R = X B
     bs_next = len(good)
     for i in good:
         V.push(R[i])
     state.H[k:k + bs_next, k - bs:k] = B[:bs_next, :bs]
     state.H[k - bs:k, k:k + bs_next] = B[:bs_next, :bs].T
-    Rnext, Mnext = block_lanczosrecurrence(it.operator, V, B)
+    Rnext, Mnext, gram = block_lanczosrecurrence(it.operator, V, B, fast)
     state.H[k:k + bs_next, k:k + bs_next] = Mnext[:bs_next, :bs_next]
     state.R.vec[:bs_next] = Rnext.vec
-    state.norm_R = Rnext.norm()
+    state.gram_R = gram
+    state.norm_R = Rnext.norm() if gram is None else math.sqrt(max(float(np.trace(gram)), 0.0))
     state.k += bs_next
     state.R_size = bs_next
     return state

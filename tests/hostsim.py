@@ -629,6 +629,56 @@ class HostSimLib:
             self._setvec(ctx, c, acc)
         return L.OK
 
+    def b2k_op_apply_block(self, h, op, X, Y, p):
+        for x, y in zip(list(X)[:p], list(Y)[:p]):
+            st = self.b2k_op_apply(h, op, x, y)
+            if st != L.OK:
+                return st
+        return L.OK
+
+    def b2k_block_orthogonalize(self, h, R, p, V, k, passes, Hh, Gh):
+        """block classical Gram-Schmidt, `passes` times (the flagged B200 mode)"""
+        ctx = self._c(h)
+        sh = self._sh(ctx, list(R)[0])
+        Rs = np.column_stack([self._vec(ctx, c).astype(np.float64) for c in list(R)[:p]])
+        Hsum = np.zeros((k, p))
+        if k > 0:
+            Vs = np.column_stack([v.astype(np.float64) for v in self._cols(ctx, V, k)])
+            for _ in range(passes):
+                Hm = np.array([[ctx.allsum(np.dot(Vs[:, j], Rs[:, i]), sh)[0] for i in range(p)] for j in range(k)])
+                Rs = Rs - Vs @ Hm
+                Hsum += Hm
+        if Hh:
+            _view(Hh, k * p, C.c_double)[:] = Hsum.T.reshape(-1)
+        if Gh:
+            G = np.array([[ctx.allsum(np.dot(Rs[:, i], Rs[:, j]), sh)[0] for j in range(p)] for i in range(p)])
+            _view(Gh, p * p, C.c_double)[:] = G.T.reshape(-1)
+        for i, c in enumerate(list(R)[:p]):
+            self._setvec(ctx, c, Rs[:, i])
+        return L.OK
+
+    def b2k_block_cholqr(self, h, X, p, tol, G0, Rh, ok):
+        ctx = self._c(h)
+        sh = self._sh(ctx, list(X)[0])
+        Xs = np.column_stack([self._vec(ctx, c).astype(np.float64) for c in list(X)[:p]])
+        Rtot = np.eye(p)
+        _set(ok, 0)
+        for rnd in range(2):
+            G = np.array([[ctx.allsum(np.dot(Xs[:, i], Xs[:, j]), sh)[0] for j in range(p)] for i in range(p)])
+            try:
+                Lc = np.linalg.cholesky(G)
+            except np.linalg.LinAlgError:
+                return L.OK
+            if rnd == 0 and np.any(np.diag(Lc) ** 2 <= (100 * tol) ** 2):
+                return L.OK
+            Xs = np.linalg.solve(Lc, Xs.T).T
+            Rtot = Lc.T @ Rtot
+        _view(Rh, p * p, C.c_double)[:] = Rtot.T.reshape(-1)
+        for i, c in enumerate(list(X)[:p]):
+            self._setvec(ctx, c, Xs[:, i])
+        _set(ok, 1)
+        return L.OK
+
     def b2k_block_reorthogonalize(self, h, R, p, V, k):
         ctx = self._c(h)
         Vs = [v.astype(np.float64) for v in self._cols(ctx, V, k)]

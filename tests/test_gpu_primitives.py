@@ -359,3 +359,61 @@ def test_orthogonalize_float32_multi_tile(alg, n, k):
     assert abs(nrm - np.linalg.norm(out)) < 1e-5 * scale
     assert np.isfinite(out).all()
     ctx.close()
+
+
+def test_block_multi_rhs_kernels():
+    """block.cu: block_inner / block_axpy as multi-right-hand-side launches (incl. > 48 basis columns = several
+    passes and > 8 block columns), SpMM bit-identical to single applies, BCGS2 against a basis, CholeskyQR2
+    equal to the MGS factor and refusing a rank-deficient block."""
+    import ctypes as C
+    from krylovkit_jl_b200.factorizations import blocklanczos as blz
+    from krylovkit_jl_b200.orthonormal import OrthonormalBasis
+    rng = np.random.default_rng(5)
+    n = 70_001                                           # ragged last tile
+    ctx = kk.B200Context(n, 140)
+    Xh = rng.standard_normal((n, 60))
+    Yh = rng.standard_normal((n, 11))
+    X = [ctx.from_host(Xh[:, j]) for j in range(60)]
+    Y = [ctx.from_host(Yh[:, j]) for j in range(11)]
+    M = blz.block_inner(kk.Block(X), kk.Block(Y))
+    np.testing.assert_allclose(M, Xh.T @ Yh, rtol=1e-12, atol=1e-9)
+    C_ = rng.standard_normal((60, 11))
+    blz.block_axpy_(kk.Block(Y), X, C_)
+    Yn = Yh - Xh @ C_
+    np.testing.assert_allclose(np.column_stack([y.to_host() for y in Y]), Yn, rtol=1e-12, atol=1e-10)
+    # SpMM == loop of SpMVs, bit for bit
+    nx, ny = 271, 193
+    ctx2 = kk.B200Context(nx * ny, 40)
+    op = kk.B200CSR.stencil(ctx2, nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0, 0))
+    Z = [ctx2.from_host(rng.standard_normal(nx * ny)) for _ in range(5)]
+    AZ = blz._apply_block(op, kk.Block(Z))
+    for z, az in zip(Z, AZ):
+        assert np.array_equal(kk.apply(op, z).to_host(), az.to_host())
+    # BCGS2 + CholeskyQR2
+    Q, _ = np.linalg.qr(rng.standard_normal((n, 50)))
+    V = OrthonormalBasis([ctx.from_host(Q[:, j]) for j in range(50)])
+    Rh = rng.standard_normal((n, 4)) + Q[:, :4] * 100.0
+    Rb = kk.Block([ctx.from_host(Rh[:, i]) for i in range(4)])
+    H, G = blz.block_orthogonalize_fast_(Rb, V)
+    Ro = np.column_stack([r.to_host() for r in Rb])
+    assert np.abs(Q.T @ Ro).max() < 1e-12 * np.abs(Rh).max() * 50
+    np.testing.assert_allclose(H, Q.T @ Rh, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(G, Ro.T @ Ro, rtol=1e-12)
+    np.testing.assert_allclose(Ro, Rh - Q @ (Q.T @ Rh), atol=1e-9)
+    Rfac, ok = blz.block_cholqr_(Rb, 1e-12, G)
+    assert ok
+    Qo = np.column_stack([r.to_host() for r in Rb])
+    np.testing.assert_allclose(Qo.T @ Qo, np.eye(4), atol=1e-13)
+    np.testing.assert_allclose(Qo @ Rfac, Ro, rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.tril(Rfac, -1), 0) and np.all(np.diag(Rfac) > 0)
+    Rm = np.linalg.qr(Ro)[1]
+    np.testing.assert_allclose(Rfac, Rm * np.sign(np.diag(Rm))[:, None], rtol=1e-10, atol=1e-10)
+    # rank-deficient block: refused, untouched
+    D = [ctx.from_host(Rh[:, 0]), ctx.from_host(Rh[:, 1]), ctx.from_host(2.0 * Rh[:, 0] - Rh[:, 1])]
+    before = [d.to_host() for d in D]
+    _, ok = blz.block_cholqr_(kk.Block(D), 1e-12)
+    assert not ok
+    for d, b in zip(D, before):
+        assert np.array_equal(d.to_host(), b)
+    ctx.close()
+    ctx2.close()

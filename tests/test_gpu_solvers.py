@@ -841,3 +841,44 @@ def test_chained_lanczos_batch_stops_at_breakdown_on_the_device():
     assert np.array_equal(a1, a0) and np.array_equal(b1, b0)
     assert np.array_equal(V1, V0) and np.array_equal(r1, r0)
     assert b1[-1] <= 1e-9
+
+
+def test_blocklanczos_fast_block_mode_matches_reference_mode():
+    """The flagged B200 block mode (SpMM + block-classical Gram-Schmidt twice + CholeskyQR2) against the
+    reference's arithmetic (modified Gram-Schmidt loops) and the oracle: same Ritz values after a fixed number of
+    restart cycles, converged eigenpairs with the closed form, and the four-fold degenerate toric-code ground
+    space (test/eigsolve.jl:471-549)."""
+    nx, ny = 120, 91
+    n = nx * ny
+    A = ko.stencil_matrix(nx, ny)
+    X0 = [ko.splitmix_vector(100 + i, n) for i in range(4)]
+    ctx = kk.B200Context(n, 120)
+    op = kk.B200CSR.stencil(ctx, nx, ny)
+    res = {}
+    for fast in (False, True):
+        alg = kk.BlockLanczos(krylovdim=48, maxiter=4, tol=0.0, verbosity=0, fast_block=fast)
+        vals, vecs, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 4, "SR", alg)
+        res[fast] = (np.array(vals[:4]), info.numops)
+        del vecs, info
+    ovals, _, oinfo = ko.eigsolve_blocklanczos(A, X0, 4, "SR", krylovdim=48, maxiter=4, tol=0.0)
+    assert res[False][1] == res[True][1] == oinfo["numops"]
+    np.testing.assert_allclose(res[False][0], ovals[:4], rtol=1e-8)
+    np.testing.assert_allclose(res[True][0], ovals[:4], rtol=1e-8)
+    alg = kk.BlockLanczos(krylovdim=60, maxiter=200, tol=1e-10, verbosity=0, fast_block=True)
+    vals, vecs, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 4, "SR", alg)
+    assert info.converged >= 4
+    np.testing.assert_allclose(vals[:4], ko.laplace_eigenvalues(nx, ny)[:4], rtol=1e-9)
+    U = np.column_stack([v.to_host() for v in vecs[:4]])
+    np.testing.assert_allclose(U.T @ U, np.eye(4), atol=1e-9)
+    assert np.abs(A @ U - U * vals[:4]).max() < 1e-8
+    ctx.close()
+    H = ko.toric_code_hamiltonian(3, 3)
+    rng = np.random.default_rng(1)
+    X0 = [rng.random(H.shape[0]) for _ in range(5)]
+    ctx = kk.B200Context(H.shape[0], 120)
+    op = kk.B200CSR.from_scipy(ctx, (-H).tocsr())
+    alg = kk.BlockLanczos(tol=1e-8, krylovdim=40, maxiter=30, verbosity=0, fast_block=True)
+    D, U, info = kk.eigsolve(op, kk.Block([ctx.from_host(x) for x in X0]), 4, "SR", alg)
+    assert info.converged >= 4
+    np.testing.assert_allclose(D[:4], -16.0, atol=1e-7)
+    ctx.close()

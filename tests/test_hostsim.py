@@ -237,6 +237,13 @@ def test_fused_branches_bookkeeping(simf):
     G.test_invariant_subspace_early_exit()
 
 
+def test_block_fast_mode(sim):
+    """the flagged block mode's host logic (BCGS2 coefficients -> M, Gram -> CholeskyQR2, rank fallback)"""
+    import test_gpu_primitives as P
+    P.test_block_multi_rhs_kernels()
+    G.test_blocklanczos_fast_block_mode_matches_reference_mode()
+
+
 def test_chained_batch_bookkeeping(simf):
     """handle accounting of the device-chained b2k_lanczos_expand_many contract (new column per basis vector,
     the old residual's column recycled, breakdown in the middle of a batch) without a GPU"""
