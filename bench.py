@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=2500)
     ap.add_argument("--krylovdim", type=int, default=60)
     ap.add_argument("--cycles", type=int, default=5)
-    ap.add_argument("--orth", default="cgs2", choices=["cgs2", "mgs2", "cgs", "mgs"])
+    ap.add_argument("--orth", default="cgs2", choices=["cgs2", "mgs2", "cgs", "mgs", "mgs2b"])
     ap.add_argument("--cpu-steps", type=int, default=30, help="expand! steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -193,7 +193,7 @@ def cpu_sample(nx, ny, krylovdim, orth_name, nsteps, A=None):
     from oracle import krylov_oracle as ko
     native, patched, _, _ = _cpu_backend()
     orth = {"cgs2": ko.Orth(ko.CGS2), "mgs2": ko.Orth(ko.MGS2), "cgs": ko.Orth(ko.CGS),
-            "mgs": ko.Orth(ko.MGS)}[orth_name]
+            "mgs": ko.Orth(ko.MGS), "mgs2b": ko.Orth(ko.MGS2)}[orth_name]       # mgs2b is OUR flagged mode of MGS2
     if A is None:
         A = _cpu_operator(nx, ny, native)
     x0 = ko.splitmix_vector(SEED, nx * ny)
@@ -211,7 +211,8 @@ def cpu_full_job(a, A):
     """The whole workload on the host cores: the oracle's eigsolve driver, same restart cycles."""
     from oracle import krylov_oracle as ko
     _, patched, _, _ = _cpu_backend()
-    orth = {"cgs2": ko.Orth(ko.CGS2), "mgs2": ko.Orth(ko.MGS2), "cgs": ko.Orth(ko.CGS), "mgs": ko.Orth(ko.MGS)}[a.orth]
+    orth = {"cgs2": ko.Orth(ko.CGS2), "mgs2": ko.Orth(ko.MGS2), "cgs": ko.Orth(ko.CGS), "mgs": ko.Orth(ko.MGS),
+            "mgs2b": ko.Orth(ko.MGS2)}[a.orth]
     x0 = ko.splitmix_vector(SEED, a.nx * a.ny)
     with patched():
         t0 = time.perf_counter()
@@ -230,7 +231,8 @@ def golden_case(a):
     g = json.load(open(p))
     for name in ("c2", "c2_mgs2", "c2_1e6"):
         c = g.get(name)
-        if c and c["grid"] == [a.nx, a.ny, 1] and c["krylovdim"] == a.krylovdim and c["orth"] == a.orth \
+        if c and c["grid"] == [a.nx, a.ny, 1] and c["krylovdim"] == a.krylovdim \
+                and c["orth"] == ("mgs2" if a.orth == "mgs2b" else a.orth) \
                 and str(a.cycles) in c["after_cycles"]:
             return {"name": f"tests/golden/fullsize.json:{name}:after_cycles[{a.cycles}]", **c["after_cycles"][str(a.cycles)]}
     return None
@@ -324,7 +326,7 @@ def run_ours(a):
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     dist = None
     n = a.nx * a.ny
-    orth = {"cgs2": kk.cgs2, "mgs2": kk.mgs2, "cgs": kk.cgs, "mgs": kk.mgs}[a.orth]
+    orth = {"cgs2": kk.cgs2, "mgs2": kk.mgs2, "cgs": kk.cgs, "mgs": kk.mgs, "mgs2b": kk.mgs2b}[a.orth]
     alg = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=a.cycles, tol=0.0, verbosity=0)
     if world > 1:
         import torch

@@ -56,6 +56,13 @@ extern "C" {
 #define B2K_MGS2  3  /* ModifiedGramSchmidt2 (KrylovDefaults.orth, algorithms.jl:558) */
 #define B2K_CGSIR 4  /* ClassicalGramSchmidtIR(eta) */
 #define B2K_MGSIR 5  /* ModifiedGramSchmidtIR(eta)  */
+/* B200-specific, FLAGGED (not a KrylovKit orthogonalizer): ModifiedGramSchmidt2 with every sweep over the whole
+ * basis applied as ONE classical block (projection coefficients of a sweep all taken from the same vector)
+ * instead of k sequential modified steps.  In the Lanczos recurrence (lanczos.jl:325-338) the first, two-vector
+ * part stays exactly the reference's (w -= beta v_prev; alpha = <v, w>; w -= alpha v); only the second sweep over
+ * all of V is blocked.  Same O(eps) orthogonality (both are "twice is enough"), coefficients differ at rounding
+ * level.  Runs at the speed of ClassicalGramSchmidt2. */
+#define B2K_MGS2B 6
 
 typedef struct b2k_ctx b2k_ctx;   /* opaque: device, stream, slabs, scratch, NCCL comm */
 typedef struct b2k_op  b2k_op;    /* opaque: CSR / dense operator resident in HBM        */

@@ -13,7 +13,8 @@ from ._lib import B200Error, DimensionMismatch, LibraryMissing
 from .algorithms import (Arnoldi, BiCGStab, BlockLanczos, CG, ClassicalGramSchmidt, ClassicalGramSchmidt2,
                          ClassicalGramSchmidtIR, ConvergenceInfo, GKL, GMRES, KrylovDefaults,
                          Lanczos, LSMR, ModifiedGramSchmidt, ModifiedGramSchmidt2,
-                         ModifiedGramSchmidtIR, Orthogonalizer, cgs, cgs2, cgsr, mgs, mgs2, mgsr)
+                         ModifiedGramSchmidt2Blocked, ModifiedGramSchmidtIR, Orthogonalizer, cgs, cgs2, cgsr, mgs,
+                         mgs2, mgs2b, mgsr)
 from .operators import B200CSR, B200Dense, B200Operator, apply, apply_adjoint, apply_normal
 from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, orthonormalize_,
                           project_, rank1update_, rmul_givens_, rmul_householder_, unproject_)

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libb200krylov.so")
 # status codes / enums (mirror include/b200krylov.h)
 OK, EINVAL, EDIM, ECUDA, ENOMEM, ENCCL, ENOTSUP = 0, -1, -2, -3, -4, -5, -6
 F64, F32 = 0, 1
-CGS, MGS, CGS2, MGS2, CGSIR, MGSIR = range(6)
+CGS, MGS, CGS2, MGS2, CGSIR, MGSIR, MGS2B = range(7)
 
 
 class B200Error(RuntimeError):

@@ -21,7 +21,7 @@ class Orthogonalizer:
 
     @property
     def is_reorth2(self) -> bool:      # Union{ClassicalGramSchmidt2, ModifiedGramSchmidt2}
-        return self.tag in (L.CGS2, L.MGS2)
+        return self.tag in (L.CGS2, L.MGS2, L.MGS2B)
 
     @property
     def is_ir(self) -> bool:           # Union{ClassicalGramSchmidtIR, ModifiedGramSchmidtIR}
@@ -49,6 +49,16 @@ class ModifiedGramSchmidt2(Orthogonalizer):
 
 
 @dataclass(frozen=True)
+class ModifiedGramSchmidt2Blocked(Orthogonalizer):
+    """B200-specific, FLAGGED — not a KrylovKit orthogonalizer.  ModifiedGramSchmidt2 with every sweep over the
+    whole basis applied as ONE classical block (include/b200krylov.h B2K_MGS2B): the reference default's two
+    orthogonalisations at the speed of ClassicalGramSchmidt2.  In the Lanczos recurrence the two-vector first part
+    (β v₋ removed, then α = ⟨v, w⟩, lanczos.jl:326-328) is exactly the reference's; the second sweep over all of V
+    takes its coefficients from one vector instead of k successively updated ones — a rounding-level change."""
+    tag: int = L.MGS2B
+
+
+@dataclass(frozen=True)
 class ClassicalGramSchmidtIR(Orthogonalizer):
     tag: int = L.CGSIR
     eta: float = 1.0 / 2.0 ** 0.5       # algorithms.jl:67
@@ -63,6 +73,7 @@ class ModifiedGramSchmidtIR(Orthogonalizer):
 cgs, mgs, cgs2, mgs2 = (ClassicalGramSchmidt(), ModifiedGramSchmidt(), ClassicalGramSchmidt2(),
                         ModifiedGramSchmidt2())
 cgsr, mgsr = ClassicalGramSchmidtIR(), ModifiedGramSchmidtIR()
+mgs2b = ModifiedGramSchmidt2Blocked()          # flagged B200 mode, see the class
 
 
 # ---- KrylovDefaults — src/algorithms.jl:556-564 -------------------------------------

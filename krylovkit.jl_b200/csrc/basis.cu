@@ -898,7 +898,7 @@ extern "C" int32_t b2k_basis_orthogonalize(b2k_ctx* ctx, b2k_vec v, const b2k_ve
                                            double* h_host, int32_t alg, double eta,
                                            double* nrm_out, int32_t* passes_out) {
     if (!ctx || (k > 0 && !h_host)) return B2K_EINVAL;
-    if (alg < B2K_CGS || alg > B2K_MGSIR)
+    if (alg < B2K_CGS || alg > B2K_MGS2B)
         return b2k_fail(ctx, B2K_EINVAL, "basis_orthogonalize: unknown orthogonalizer %d", alg);
     VecRef rv;
     B2K_TRY(b2k_resolve(ctx, v, &rv));
@@ -955,6 +955,7 @@ extern "C" int32_t b2k_basis_orthogonalize(b2k_ctx* ctx, b2k_vec v, const b2k_ve
         case B2K_CGS:
             B2K_TRY(cgs_passes(1)); passes = 1; break;
         case B2K_CGS2:
+        case B2K_MGS2B:      // flagged: both sweeps as classical blocks
             B2K_TRY(cgs_passes(2)); passes = 2; break;
         case B2K_MGS:
             B2K_TRY(mgs_passes(1)); passes = 1; break;
@@ -996,7 +997,7 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
                                       int32_t alg, double eta, double* alpha_out,
                                       double* beta_out) {
     if (!ctx || !op || !cols || k < 1 || !alpha_out || !beta_out) return B2K_EINVAL;
-    if (alg < B2K_CGS || alg > B2K_MGSIR)
+    if (alg < B2K_CGS || alg > B2K_MGS2B)
         return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: unknown orthogonalizer %d", alg);
     if (cols[k] != r) return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: cols[k] must be r");
     if (beta_old == 0.0) return b2k_fail(ctx, B2K_EINVAL, "lanczos_expand: beta_old == 0");
@@ -1163,6 +1164,18 @@ extern "C" int32_t b2k_lanczos_expand(b2k_ctx* ctx, const b2k_op* op, const b2k_
         B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
         alpha = ctx->h_res[S_A0];
         beta = sqrt(ctx->h_res[S_N]);
+    } else if (alg == B2K_MGS2B) {
+        // flagged: the second sweep over all of V as ONE classical pass (project, update + norm)
+        if (fused_ok(ctx, K1, pn.sharded, ctx->dtype)) {
+            if (f64) B2K_TRY(cgs_fused_t<double>(ctx, pn, rw, K1, 1, g_use_coop));
+            else B2K_TRY(cgs_fused_t<float>(ctx, pn, rw, K1, 1, g_use_coop));
+        } else {
+            if (f64) B2K_TRY(cgs_pass_unfused_t<double>(ctx, pn, rw, K1, S_H, S_N));
+            else B2K_TRY(cgs_pass_unfused_t<float>(ctx, pn, rw, K1, S_H, S_N));
+        }
+        B2K_TRY(b2k_fetch_results(ctx, S_A0 + 1, 0));
+        alpha = ctx->h_res[S_A0] + ctx->h_res[S_H + k];   // α += s (coefficient vs V[end])
+        beta = sqrt(ctx->h_res[S_N]);
     } else if (alg == B2K_MGS2) {
         B2K_TRY(mgs_sweep(ctx, pn, rw, K1, S_H, -1));
         B2K_TRY(b2k_enqueue_dot(ctx, nullptr, rw.ptr, pn.n, nullptr, -1, S_N, -1));
@@ -1212,7 +1225,8 @@ bool g_use_chain = true;
 
 bool chain_ok(const b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, int32_t k, int32_t nsteps, int32_t alg,
               double beta_old) {
-    if (!g_use_chain || !g_use_coop || alg != B2K_CGS2 || nsteps < 1 || nsteps > B2K_MAX_CHAIN) return false;
+    if (!g_use_chain || !g_use_coop || (alg != B2K_CGS2 && alg != B2K_MGS2B) || nsteps < 1 || nsteps > B2K_MAX_CHAIN)
+        return false;
     int64_t op_rows = 0, op_cols = 0;
     int32_t op_kind = -1;
     if (b2k_op_info(op, &op_rows, &op_cols, nullptr, &op_kind) != B2K_OK) return false;
@@ -1288,7 +1302,7 @@ int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, c
 }
 
 int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, int32_t nsteps,
-                      double beta_old, double tol, double* alphas_out, double* betas_out,
+                      double beta_old, double tol, int32_t alg, double* alphas_out, double* betas_out,
                       int32_t* steps_done, b2k_vec* r_out) {
     const bool f64 = ctx->dtype == B2K_F64;
     const int32_t space = B2K_VEC_SPACE(cols[k]);
@@ -1329,6 +1343,10 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
         fz.vout = rV.ptr;
         fz.stop = d_stop;
         fz.dot_self = 1;
+        if (alg == B2K_MGS2B) {                  // alpha = <v, A v - beta v_prev>: the modified order
+            fz.dot_sub_vec = vprev.ptr;
+            fz.dot_sub_scale = rec_prev + 2;
+        }
         PeerStep ps;
         memset(&ps, 0, sizeof(ps));
         if (dist) {
@@ -1407,7 +1425,7 @@ extern "C" int32_t b2k_lanczos_expand_many(b2k_ctx* ctx, const b2k_op* op, b2k_v
     b2k_vec r = cols[k];
     *r_out = r;
     if (chain_ok(ctx, op, cols, k, nsteps, alg, beta_old))
-        return lanczos_chain(ctx, op, cols, k, nsteps, beta_old, tol, alphas_out, betas_out, steps_done, r_out);
+        return lanczos_chain(ctx, op, cols, k, nsteps, beta_old, tol, alg, alphas_out, betas_out, steps_done, r_out);
     double beta = beta_old;
     for (int32_t i = 0; i < nsteps; ++i) {
         b2k_vec w;

@@ -644,6 +644,7 @@ extern "C" int32_t b2k_vec_orthogonalize(b2k_ctx* ctx, b2k_vec v, b2k_vec q, int
     };
     (void)dist;
     double s = 0.0;
+    if (alg == B2K_MGS2B) alg = B2K_MGS2;      // one vector: blocked and sequential sweeps are the same thing
     if (alg == B2K_CGS || alg == B2K_MGS) {
         B2K_TRY(dot(0));
         B2K_TRY(b2k_enqueue_axpy_dev(ctx, rv.ptr, rq.ptr, 0, n));

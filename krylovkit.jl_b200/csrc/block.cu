@@ -476,7 +476,12 @@ extern "C" int32_t b2k_block_cholqr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, d
         for (int j = 0; j < p; ++j) {
             double d = G[j * p + j];
             for (int t = 0; t < j; ++t) d -= L[t * p + j] * L[t * p + j];
-            const double thr = (round == 0) ? (100.0 * tol) * (100.0 * tol) : 0.0;
+            // A Cholesky pivot is ||x_j - proj||^2 formed by SUBTRACTION: it carries an absolute error of
+            // ~eps ||x_j||^2, so CholeskyQR can neither resolve a residual below sqrt(eps) ||x_j|| nor
+            // orthogonalise a block with condition number above ~eps^-1/2.  Accept only pivots well above that
+            // noise (relative 1e-11, i.e. kappa < 3e5 — the second round then restores orthogonality to eps) AND
+            // above block_qr!'s own absolute scale (100 tol)^2; everything else goes to the reference MGS path.
+            const double thr = (round == 0) ? std::max((100.0 * tol) * (100.0 * tol), 1e-11 * G[j * p + j]) : 0.0;
             if (!(d > thr) || !(d > 1e-28 * G[j * p + j])) {
                 if (round == 0) return B2K_OK;             // *ok = 0, X untouched
                 return b2k_fail(ctx, B2K_ECUDA, "block_cholqr: second Cholesky lost positivity");

@@ -177,6 +177,10 @@ struct SpmvFuse {
     void* vout;
     const int* stop;
     int dot_self;
+    // the fused dot product is taken with y - (*dot_sub_scale) * dot_sub_vec instead of y (y itself is stored
+    // unchanged): alpha = <v, A v - beta v_prev>, the ModifiedGramSchmidt order of lanczos.jl:304-306, 326-328
+    const void* dot_sub_vec;
+    const double* dot_sub_scale;
     // row-sharded contexts with the peer window: sequence number under which <x, y> is published to all ranks
     // (0: not published), and the halo sequence number a previous kernel has already pushed this operand's
     // boundary rows under (0: the apply pushes them itself)

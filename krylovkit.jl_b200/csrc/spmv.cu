@@ -119,7 +119,11 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
                 if (vout) vout[r] = dv;
             }
             if (dotv && !fz.dot_self) dv = dotv[r];
-            if (dotv || fz.dot_self) dacc = fma(dv, s, dacc);
+            if (dotv || fz.dot_self) {
+                T sd = s;
+                if (fz.dot_sub_vec) sd = fma(-(T)(*fz.dot_sub_scale), reinterpret_cast<const T*>(fz.dot_sub_vec)[r], s);
+                dacc = fma(dv, sd, dacc);
+            }
         }
     } else {
         // long row: the CTA owns exactly one row
@@ -141,7 +145,11 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
                 if (vout) vout[r0] = dv;
             }
             if (dotv && !fz.dot_self) dv = dotv[r0];
-            if (dotv || fz.dot_self) dacc = dv * s;
+            if (dotv || fz.dot_self) {
+                T sd = s;
+                if (fz.dot_sub_vec) sd = fma(-(T)(*fz.dot_sub_scale), reinterpret_cast<const T*>(fz.dot_sub_vec)[r0], s);
+                dacc = dv * sd;
+            }
         }
     }
     if (dotv || fz.dot_self) {
@@ -266,6 +274,8 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     T* const vout = reinterpret_cast<T*>(fz.vout);
     const bool self = (vout != nullptr) || fz.dot_self;
     const bool want_dot = (dotv != nullptr) || fz.dot_self;
+    const T* const dsub = reinterpret_cast<const T*>(fz.dot_sub_vec);
+    const T dsc = dsub ? (T)(*fz.dot_sub_scale) : (T)0;
     T dacc = (T)0;
     int tile = blockIdx.x;
     int4 dn = make_int4(0, 0, 0, 0);
@@ -307,6 +317,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 T dv = (dotv && !fz.dot_self) ? __ldg(dotv + r) : (T)0;
                 const T xself = self ? __ldg(x + r) : (T)0;
                 const T xsr = shifted ? __ldg(xs + r) : (T)0;
+                const T dsv = dsub ? __ldg(dsub + r) : (T)0;
                 int a, b;
                 if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
                 else { a = rowptr[r]; b = rowptr[r + 1]; }
@@ -320,7 +331,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                     if (vout) vout[r] = vn;
                     if (fz.dot_self) dv = vn;
                 }
-                dacc = fma(dv, sum, dacc);
+                dacc = fma(dv, dsub ? fma(-dsc, dsv, sum) : sum, dacc);
             }
         } else {
             double acc = 0.0;
@@ -345,7 +356,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                     if (vout) vout[r0] = vn;
                     if (fz.dot_self) dv = vn;
                 }
-                if (want_dot) dacc = fma(dv, sum, dacc);
+                if (want_dot) dacc = fma(dv, dsub ? fma(-dsc, dsub[r0], sum) : sum, dacc);
             }
             named_bar_sync(1, SPP_CONS);
         }

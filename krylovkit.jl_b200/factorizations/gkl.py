@@ -75,6 +75,8 @@ def gklrecurrence(operator, U: OrthonormalBasis, V: OrthonormalBasis, beta: floa
     if t == L.MGS2:
         for q in V:
             v, _ = orthogonalize_(v, q, mgs)
+    elif t == L.MGS2B:                          # flagged: the same sweep as one classical block
+        v, _ = orthogonalize_(v, V, cgs)
     alpha = v.norm()
     if t in (L.CGSIR, L.MGSIR):
         nold = math.sqrt(alpha * alpha + beta * beta)
@@ -97,6 +99,9 @@ def gklrecurrence(operator, U: OrthonormalBasis, V: OrthonormalBasis, beta: floa
     elif t == L.MGS2:
         for q in U:
             r, _ = orthogonalize_(r, q, mgs)
+    elif t == L.MGS2B:
+        r, _ = orthogonalize_(r, U, cgs)
+        beta_known = orthogonalize_.last_norm
     beta = beta_known if beta_known is not None else r.norm()
     if t in (L.CGSIR, L.MGSIR):
         nold = math.sqrt(alpha * alpha + beta * beta)

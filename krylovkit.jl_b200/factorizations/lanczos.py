@@ -138,6 +138,14 @@ def lanczosrecurrence(operator, V: OrthonormalBasis, beta: float, orth: Orthogon
             w, s = orthogonalize_(w, q, mgs)
         alpha += s
         return w, alpha, w.norm()
+    if t == L.MGS2B:
+        # flagged: the reference's MGS2 recurrence with its second sweep over V applied as one classical block
+        from ..algorithms import cgs, mgs
+        w = w.add_(V[-2], -beta)
+        w, alpha = orthogonalize_(w, v, mgs)
+        w, s = orthogonalize_(w, V, cgs)
+        alpha += s[len(V) - 1]
+        return w, alpha, w.norm()
     if t == L.CGSIR:
         from ..algorithms import cgs
         alpha = v.inner(w)

@@ -430,8 +430,9 @@ class HostSimLib:
         hv = _view(hptr, k, C.c_double)
         b = [q.astype(np.float64) for q in self._cols(ctx, cols, k)]
         x = np.zeros(k)
+        oalg = ko.CGS2 if int(alg) == L.MGS2B else int(alg)        # blocked MGS2: both sweeps classical
         with _global_reductions(ctx, self._sh(ctx, v)):
-            w, x = ko.orthogonalize(self._vec(ctx, v).astype(np.float64), b, x, ko.Orth(int(alg), float(eta)))
+            w, x = ko.orthogonalize(self._vec(ctx, v).astype(np.float64), b, x, ko.Orth(oalg, float(eta)))
             nw = ko.norm(w)
         self._setvec(ctx, v, w)
         hv[:] = x
@@ -443,9 +444,10 @@ class HostSimLib:
 
     def b2k_vec_orthogonalize(self, h, v, q, alg, eta, s, nrm):
         ctx = self._c(h)
+        oalg = ko.MGS2 if int(alg) == L.MGS2B else int(alg)
         with _global_reductions(ctx, self._sh(ctx, v)):
             w, sv = ko.orthogonalize_vec(self._vec(ctx, v).astype(np.float64), self._vec(ctx, q).astype(np.float64),
-                                         ko.Orth(int(alg), float(eta)), eps=float(np.finfo(ctx.dtype).eps))
+                                         ko.Orth(oalg, float(eta)), eps=float(np.finfo(ctx.dtype).eps))
             nw = ko.norm(w)
         self._setvec(ctx, v, w)
         _set(s, float(sv))
@@ -508,8 +510,19 @@ class HostSimLib:
         self._setvec(ctx, r, self._vec(ctx, r) * (1.0 / beta_old))      # lanczos.jl:257
         V = [self._vec(ctx, c).astype(np.float64) for c in cl]
         with _global_reductions(ctx, self._sh(ctx, r)):
-            wn, alpha, beta = ko.lanczos_recurrence(self._OpView(ctx, self.ops[_key(op)]), V, float(beta_old),
-                                                    ko.Orth(int(alg), float(eta)))
+            if int(alg) == L.MGS2B:
+                # the reference's MGS2 recurrence (lanczos.jl:325-338) with the second sweep as one classical pass
+                A_ = self._OpView(ctx, self.ops[_key(op)])
+                wn = ko.apply(A_, V[-1])
+                wn = wn - float(beta_old) * V[-2]
+                alpha = ko.inner(V[-1], wn)
+                wn = wn - alpha * V[-1]
+                wn, sx = ko.orthogonalize(wn, V, np.zeros(len(V)), ko.Orth(ko.CGS))
+                alpha += sx[-1]
+                beta = ko.norm(wn)
+            else:
+                wn, alpha, beta = ko.lanczos_recurrence(self._OpView(ctx, self.ops[_key(op)]), V, float(beta_old),
+                                                        ko.Orth(int(alg), float(eta)))
         self._setvec(ctx, w, wn)
         _set(alpha_out, float(alpha))
         _set(beta_out, float(beta))
@@ -533,7 +546,7 @@ class HostSimLib:
                 self.b2k_vec_free(h, wref.value)
                 return st
             alphas[i], betas[i] = a.value, b.value
-            if self.chain and alg == L.CGS2:
+            if self.chain and alg in (L.CGS2, L.MGS2B):
                 # the device-chained contract: the normalised vector lives in a column of its own and the old
                 # residual's column goes back to the slab (it may be handed out again right away)
                 vref = C.c_int32()
@@ -669,7 +682,7 @@ class HostSimLib:
                 Lc = np.linalg.cholesky(G)
             except np.linalg.LinAlgError:
                 return L.OK
-            if rnd == 0 and np.any(np.diag(Lc) ** 2 <= (100 * tol) ** 2):
+            if rnd == 0 and np.any(np.diag(Lc) ** 2 <= np.maximum((100 * tol) ** 2, 1e-11 * np.diag(G))):
                 return L.OK
             Xs = np.linalg.solve(Lc, Xs.T).T
             Rtot = Lc.T @ Rtot

@@ -17,8 +17,10 @@ from oracle import krylov_oracle as ko
 SEED = 20260923
 PAIRS = [(kk.cgs, ko.Orth(ko.CGS)), (kk.mgs, ko.Orth(ko.MGS)), (kk.cgs2, ko.Orth(ko.CGS2)),
          (kk.mgs2, ko.Orth(ko.MGS2)), (kk.ClassicalGramSchmidtIR(eta=0.75), ko.Orth(ko.CGSIR, 0.75)),
-         (kk.ModifiedGramSchmidtIR(eta=0.75), ko.Orth(ko.MGSIR, 0.75))]
-IDS = ["cgs", "mgs", "cgs2", "mgs2", "cgsr", "mgsr"]
+         (kk.ModifiedGramSchmidtIR(eta=0.75), ko.Orth(ko.MGSIR, 0.75)),
+         # the flagged blocked mode of MGS2 (B2K_MGS2B) is checked against the REFERENCE's MGS2
+         (kk.mgs2b, ko.Orth(ko.MGS2))]
+IDS = ["cgs", "mgs", "cgs2", "mgs2", "cgsr", "mgsr", "mgs2b"]
 
 
 def conv_diff(nx, ny):
@@ -88,7 +90,7 @@ def test_arnoldi_steps_match_oracle(pair):
 
 
 @pytest.mark.parametrize("which", ["SR", "LR"])
-@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3], PAIRS[4]], ids=["cgs2", "mgs2", "cgsr"])
+@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3], PAIRS[4], PAIRS[6]], ids=["cgs2", "mgs2", "cgsr", "mgs2b"])
 def test_eigsolve_config1_matches_oracle_and_closed_form(pair, which):
     """BASELINE config 1 (1e4 x 1e4 5-point Laplacian, krylovdim 30, howmany 4): Ritz values
     within 1e-10 relative of the oracle and of the closed form, residuals within tol."""
@@ -165,7 +167,7 @@ def test_issue143_and_toric_on_gpu():
     assert info.converged >= 1 and abs(vals[0] + 16.0) < 1e-8
 
 
-@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3]], ids=["cgs2", "mgs2"])
+@pytest.mark.parametrize("pair", [PAIRS[2], PAIRS[3], PAIRS[6]], ids=["cgs2", "mgs2", "mgs2b"])
 @pytest.mark.parametrize("literal", [False, True])
 def test_gmres_matches_oracle(pair, literal):
     """config 3 at test size: nonsymmetric convection-diffusion, b = A*1, restarted GMRES."""
@@ -788,7 +790,7 @@ def test_zero_start_vector_raises():
     ctx.close()
 
 
-def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None):
+def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None, orth=None):
     """initialize + one b2k_lanczos_expand_many batch; returns (alphas, betas, V (host), r (host), free columns)."""
     lib = L.load()
     lib.b2k_debug_set_chain(1 if chain else 0)
@@ -801,7 +803,7 @@ def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None):
         else:
             op = kk.B200CSR.from_scipy(ctx, sp.diags(diag).tocsr())
             x0 = ctx.from_host(ko.splitmix_vector(5, n) + 0.5)
-        it = lz.LanczosIterator(op, x0, kk.cgs2)
+        it = lz.LanczosIterator(op, x0, orth or kk.cgs2)
         f = lz.initialize(it)
         done = lz.expand_many_(it, f, steps, tol)
         out = (done, np.array(f.alphas), np.array(f.betas), np.column_stack([v.to_host() for v in f.V]),
@@ -822,12 +824,20 @@ def test_chained_lanczos_batch_is_bit_identical_to_stepping():
     """b2k_lanczos_expand_many with the device-chained steps (normalisation fused into the SpMV gather, scalars
     kept in device records, in-kernel finalisation, no host round trip) gives the same bits as one synchronous
     b2k_lanczos_expand per step: same kernels' arithmetic, same operand bits (lanczos.jl:250-272, 313-324)."""
-    d1, a1, b1, V1, r1 = _expand_many_run(True)
-    d0, a0, b0, V0, r0 = _expand_many_run(False)
-    assert d1 == d0 == 30
-    assert np.array_equal(a1, a0) and np.array_equal(b1, b0)
-    assert np.array_equal(V1, V0) and np.array_equal(r1, r0)
-    assert np.abs(V1.T @ V1 - np.eye(V1.shape[1])).max() < 1e-12
+    for orth in (kk.cgs2, kk.mgs2b):
+        d1, a1, b1, V1, r1 = _expand_many_run(True, orth=orth)
+        d0, a0, b0, V0, r0 = _expand_many_run(False, orth=orth)
+        assert d1 == d0 == 30
+        if orth is kk.cgs2:
+            assert np.array_equal(a1, a0) and np.array_equal(b1, b0)
+            assert np.array_equal(V1, V0) and np.array_equal(r1, r0)
+        else:
+            # the synchronous mgs2b step computes alpha with a separate dot kernel (other summation order than
+            # the SpMV epilogue of the chained step): equal to rounding, not to the bit
+            np.testing.assert_allclose(a1, a0, rtol=1e-13)
+            np.testing.assert_allclose(b1, b0, rtol=1e-12)
+            np.testing.assert_allclose(V1, V0, atol=1e-11)
+        assert np.abs(V1.T @ V1 - np.eye(V1.shape[1])).max() < 1e-12
 
 
 def test_chained_lanczos_batch_stops_at_breakdown_on_the_device():

@@ -99,7 +99,7 @@ def test_lanczos_and_arnoldi_steps(sim, pair):
     G.test_arnoldi_steps_match_oracle(pair)
 
 
-@pytest.mark.parametrize("pair", [G.PAIRS[2], G.PAIRS[3]], ids=["cgs2", "mgs2"])
+@pytest.mark.parametrize("pair", [G.PAIRS[2], G.PAIRS[3], G.PAIRS[6]], ids=["cgs2", "mgs2", "mgs2b"])
 @pytest.mark.parametrize("literal", [False, True])
 def test_gmres(sim, pair, literal):
     G.test_gmres_matches_oracle(pair, literal)
@@ -229,7 +229,7 @@ def test_fused_branches_bookkeeping(simf):
     """Host-side bookkeeping of the fused branches — handle accounting of expand_/expand_many_ (library-
     allocated residual columns adopted by Python), the one-call CG step, the two-call BiCGStab flow with
     its half-step exit — against the oracle, exactly as the GPU tests run them."""
-    for pair in (G.PAIRS[2], G.PAIRS[3], G.PAIRS[4], G.PAIRS[0]):
+    for pair in (G.PAIRS[2], G.PAIRS[3], G.PAIRS[4], G.PAIRS[0], G.PAIRS[6]):
         G.test_lanczos_steps_match_oracle(pair, True)
     G.test_cg_matches_oracle(True)
     G.test_bicgstab_matches_oracle_and_reference_properties(True)
