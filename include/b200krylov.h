@@ -193,6 +193,15 @@ int32_t b2k_op_apply_dot(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec y, b
 int32_t b2k_cg_step(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec p, b2k_vec q,
                     double a0, double a1, double beta, double rho, double* pq_out, double* normr_out);
 
+/* Up to `nsteps` CG iterations (every iteration after the first, cg.jl:62-101) enqueued back to back with rho,
+ * beta, <p,q>, ||r|| kept on the device — three launches per iteration, ONE host synchronisation per call.  The
+ * last kernel of an iteration tests ||r|| < tol like the reference does; launches behind a hit do nothing.
+ * pq_out / normr_out: one entry per completed iteration (*steps_done of them); the iteration that reported
+ * ||r|| < tol, if any, is the last one.  Same iterates as b2k_cg_step called *steps_done times.  Single GPU. */
+int32_t b2k_cg_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec p, b2k_vec q,
+                     double a0, double a1, double beta, double rho, double tol, int32_t nsteps,
+                     double* pq_out, double* normr_out, int32_t* steps_done);
+
 /* One BiCGStab iteration (src/linsolve/bicgstab.jl:95-171) as two calls, one host round trip
  * each, with the half-step convergence test (:118) between them on the host as in the reference.
  * half (:97-116): p <- r + beta*(p - omega*v) [first != 0: p <- r]; v <- (a0 + a1*A) p with

@@ -93,6 +93,8 @@ _PROTOS = {
     "b2k_op_apply_dot": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, P(C.c_double)]),
     "b2k_cg_step": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, C.c_double, C.c_double, C.c_double,
                                 C.c_double, P(C.c_double), P(C.c_double)]),
+    "b2k_cg_chain": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_int32, P(C.c_double), P(C.c_double), P(C.c_int32)]),
     "b2k_bicgstab_half": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, c_vec, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.c_double, C.c_int32, P(C.c_double),
                                       P(C.c_double)]),

@@ -7,6 +7,15 @@
 
 namespace {
 
+// device-chained CG iterations (b2k_cg_chain): state = {rho, beta} on the device, rec = {<p,q>, ||r||} of this
+// iteration, stop = flag raised when ||r|| < tol (the launches enqueued behind it then do nothing)
+struct CgChain {
+    double* state;
+    double* rec;
+    int* stop;
+    double tol;
+};
+
 constexpr int BT = 256;            // threads per CTA
 constexpr int CTAS_PER_SM = 4;
 
@@ -249,12 +258,14 @@ template <typename T>
 __global__ void __launch_bounds__(BT)
 k_cg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ q, int64_t n,
         double rho, const double* __restrict__ pq, double* __restrict__ part, unsigned* __restrict__ ticket,
-        double* __restrict__ out) {
+        double* __restrict__ out, const CgChain ch) {
     __shared__ double red[32];
     __shared__ bool last;
+    if (ch.stop && *reinterpret_cast<const volatile int*>(ch.stop)) return;
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    if (ch.state) rho = *reinterpret_cast<const volatile double*>(ch.state);      // rho kept on the device
     const T alpha = (T)(rho / *pq);
     T acc = 0;
     _Pragma("unroll 4")
@@ -294,7 +305,43 @@ k_cg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* 
         const volatile double* pv2 = part;
         for (int g = threadIdx.x; g < (int)gridDim.x; g += BT) v += pv2[g];
         const double tot = block_sum(v, red);
-        if (threadIdx.x == 0) *out = tot;
+        if (threadIdx.x == 0) {
+            *out = tot;
+            if (ch.state) {
+                // cg.jl:74-77 on the device: normr = sqrt(||r||^2); rho_old = rho; rho = normr^2; beta = rho / rho_old
+                const double nr = sqrt(tot);
+                const double rho_new = nr * nr;
+                ch.state[1] = rho_new / rho;
+                ch.state[0] = rho_new;
+                ch.rec[0] = *pq;
+                ch.rec[1] = nr;
+                if (nr < ch.tol) *ch.stop = 1;     // cg.jl:68: the host takes over (explicit residual, restart)
+            }
+        }
+    }
+}
+
+// p <- r + beta p with beta on the device (same fma as k_axpby<T, 2> with alpha = 1)
+template <typename T>
+__global__ void __launch_bounds__(BT) k_xpby_dev(T* __restrict__ y, const T* __restrict__ x, int64_t n,
+                                                 const double* __restrict__ beta_dev, const int* __restrict__ stop) {
+    if (stop && *reinterpret_cast<const volatile int*>(stop)) return;
+    constexpr int V = Vec16<T>::N;
+    const int64_t nv = n / V;
+    const int64_t stride = (int64_t)gridDim.x * BT;
+    const T beta = (T)(*beta_dev);
+    _Pragma("unroll 4")
+    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
+        T a[V], b[V];
+        vload<T>(x + i * V, a);
+        vload<T>(y + i * V, b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) b[j] = fma((T)1, a[j], beta * b[j]);
+        vstore<T>(y + i * V, b);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
+        const int64_t i = nv * V + threadIdx.x;
+        y[i] = fma((T)1, x[i], beta * y[i]);
     }
 }
 
@@ -714,11 +761,11 @@ extern "C" int32_t b2k_cg_step(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_ve
     if (ctx->dtype == B2K_F64)
         k_cg_xr<double><<<grid, BT, 0, ctx->stream>>>((double*)rx.ptr, (double*)rr.ptr, (const double*)rp.ptr,
                                                       (const double*)rq.ptr, rx.n, rho, ctx->d_res,
-                                                      ctx->d_part_s, ctx->d_sync, ctx->d_res + 1);
+                                                      ctx->d_part_s, ctx->d_sync, ctx->d_res + 1, CgChain{});
     else
         k_cg_xr<float><<<grid, BT, 0, ctx->stream>>>((float*)rx.ptr, (float*)rr.ptr, (const float*)rp.ptr,
                                                      (const float*)rq.ptr, rx.n, rho, ctx->d_res,
-                                                     ctx->d_part_s, ctx->d_sync, ctx->d_res + 1);
+                                                     ctx->d_part_s, ctx->d_sync, ctx->d_res + 1, CgChain{});
     B2K_LAUNCH_CHECK(ctx);
     B2K_TRY(b2k_allreduce(ctx, ctx->d_res + 1, 1, rx.sharded));
     B2K_TRY(b2k_fetch_results(ctx, 2, 0));
@@ -727,6 +774,72 @@ extern "C" int32_t b2k_cg_step(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_ve
     return B2K_OK;
 }
 
+
+// Up to `nsteps` CG iterations (cg.jl:62-101, every iteration after the first) enqueued back to back with rho,
+// beta, <p,q> and ||r|| kept on the device: three launches per iteration (p <- r + beta p; q = A p with <p,q> in
+// its epilogue; x, r update + ||r||) and ONE host synchronisation per call.  The reference tests ||r|| < tol
+// after every iteration; so does the last kernel of each iteration, and the launches behind a hit do nothing.
+// pq_out / normr_out get one entry per completed iteration; the iteration that reported ||r|| < tol is the last.
+extern "C" int32_t b2k_cg_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec p, b2k_vec q,
+                                double a0, double a1, double beta, double rho, double tol, int32_t nsteps,
+                                double* pq_out, double* normr_out, int32_t* steps_done) {
+    if (!ctx || !op || !pq_out || !normr_out || !steps_done || nsteps < 1) return B2K_EINVAL;
+    *steps_done = 0;
+    if (nsteps > B2K_MAX_CHAIN) nsteps = B2K_MAX_CHAIN;
+    VecRef rx, rr, rp, rq;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    B2K_TRY(b2k_resolve(ctx, r, &rr));
+    B2K_TRY(b2k_resolve(ctx, p, &rp));
+    B2K_TRY(b2k_resolve(ctx, q, &rq));
+    if (rx.n != rr.n || rx.n != rp.n || rx.n != rq.n) return b2k_fail(ctx, B2K_EDIM, "cg_chain: length mismatch");
+    if (ctx->nranks > 1) return b2k_fail(ctx, B2K_ENOTSUP, "cg_chain: single-GPU contexts (use b2k_cg_step)");
+    int64_t orows = 0, ocols = 0;
+    int32_t okind = -1;
+    B2K_TRY(b2k_op_info(op, &orows, &ocols, nullptr, &okind));
+    if (okind != 0) return b2k_fail(ctx, B2K_ENOTSUP, "cg_chain: CSR operators only");
+    double* state = ctx->d_steps;                       // {rho, beta}
+    double* rec0 = ctx->d_steps + B2K_REC;
+    int* d_stop = reinterpret_cast<int*>(ctx->d_sync + B2K_SYNC_STOP);
+    const double seed[2] = {rho, beta};
+    B2K_TRY(b2k_put_coef(ctx, seed, 2, 0));
+    B2K_CUDA(ctx, cudaMemcpyAsync(state, ctx->d_coef, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    B2K_CUDA(ctx, cudaMemsetAsync(d_stop, 0, sizeof(int), ctx->stream));
+    const bool shifted = (a0 != 0.0) || (a1 != 1.0);
+    const int grid = grid_for(ctx, rx.n, 8);
+    for (int32_t i = 0; i < nsteps; ++i) {
+        double* rec = rec0 + (size_t)B2K_REC * i;
+        if (ctx->dtype == B2K_F64)
+            k_xpby_dev<double><<<grid, BT, 0, ctx->stream>>>((double*)rp.ptr, (const double*)rr.ptr, rx.n, state + 1, d_stop);
+        else
+            k_xpby_dev<float><<<grid, BT, 0, ctx->stream>>>((float*)rp.ptr, (const float*)rr.ptr, rx.n, state + 1, d_stop);
+        B2K_LAUNCH_CHECK(ctx);
+        SpmvFuse fz;
+        memset(&fz, 0, sizeof(fz));
+        fz.stop = d_stop;
+        B2K_TRY(b2k_enqueue_apply_fused(ctx, op, rp, rq, a0, a1, shifted, &rp, ctx->d_res, &fz));
+        CgChain ch;
+        ch.state = state; ch.rec = rec; ch.stop = d_stop; ch.tol = tol;
+        if (ctx->dtype == B2K_F64)
+            k_cg_xr<double><<<grid, BT, 0, ctx->stream>>>((double*)rx.ptr, (double*)rr.ptr, (const double*)rp.ptr,
+                                                          (const double*)rq.ptr, rx.n, 0.0, ctx->d_res,
+                                                          ctx->d_part_s, ctx->d_sync, ctx->d_res + 1, ch);
+        else
+            k_cg_xr<float><<<grid, BT, 0, ctx->stream>>>((float*)rx.ptr, (float*)rr.ptr, (const float*)rp.ptr,
+                                                         (const float*)rq.ptr, rx.n, 0.0, ctx->d_res,
+                                                         ctx->d_part_s, ctx->d_sync, ctx->d_res + 1, ch);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, rec0, sizeof(double) * B2K_REC * nsteps, cudaMemcpyDeviceToHost, ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int32_t d = nsteps;
+    for (int32_t i = 0; i < nsteps; ++i) {
+        pq_out[i] = ctx->h_res[(size_t)B2K_REC * i];
+        normr_out[i] = ctx->h_res[(size_t)B2K_REC * i + 1];
+        if (normr_out[i] < tol) { d = i + 1; break; }
+    }
+    *steps_done = d;
+    return B2K_OK;
+}
 
 // BiCGStab iteration in two calls with one host round trip each — src/linsolve/bicgstab.jl:97-117 and
 // :139-150.  The half-step convergence test (:118) sits between them, on the host, as in the reference.

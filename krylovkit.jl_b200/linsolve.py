@@ -204,6 +204,8 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
 
 
 USE_FUSED_CG = True      # b2k_cg_step (one host round trip per iteration) for device CSR operators
+USE_CG_CHAIN = True      # b2k_cg_chain: iterations chained on the device, one host round trip per CG_CHAIN_LEN
+CG_CHAIN_LEN = 32
 
 
 def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
@@ -227,8 +229,20 @@ def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
     q = r.zerovector() if fused else None
     beta = 0.0           # first iteration: p = r  (cg.jl:35)
     first = True
+    chain = fused and USE_CG_CHAIN and ctx.nranks == 1
+    pending: list[float] = []      # ||r|| of iterations the device has already run (b2k_cg_chain), oldest first
     while True:
-        if fused:
+        if fused and chain and not first:
+            if not pending:
+                # nothing in the reference's loop needs the host between iterations except the two exit tests;
+                # the device applies the ||r|| < tol test itself, the iteration count is bounded here
+                m = max(1, min(CG_CHAIN_LEN, maxiter - numiter))
+                pqs, nrs, done = (C.c_double * m)(), (C.c_double * m)(), C.c_int32()
+                ctx.check(ctx.lib.b2k_cg_chain(ctx.h, operator.h, x.handle, r.handle, p.handle, q.handle, a0, a1,
+                                               beta, rho, tol, m, pqs, nrs, C.byref(done)))
+                pending = [nrs[i] for i in range(done.value)]
+            normr = pending.pop(0)
+        elif fused:
             pq, nr = C.c_double(), C.c_double()
             ctx.check(ctx.lib.b2k_cg_step(ctx.h, operator.h, x.handle, r.handle, p.handle, q.handle, a0, a1,
                                           beta, rho, C.byref(pq), C.byref(nr)))

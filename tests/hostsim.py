@@ -586,6 +586,23 @@ class HostSimLib:
         _set(normr_out, float(np.sqrt(ctx.allsum(np.dot(rn, rn), sh)[0])))
         return L.OK
 
+    def b2k_cg_chain(self, h, op, x, r, p, q, a0, a1, beta, rho, tol, nsteps, pq_out, normr_out, done):
+        d = 0
+        for i in range(nsteps):
+            pq, nr = C.c_double(), C.c_double()
+            st = self.b2k_cg_step(h, op, x, r, p, q, a0, a1, beta, rho, pq, nr)
+            if st != L.OK:
+                return st
+            pq_out[i], normr_out[i] = pq.value, nr.value
+            d = i + 1
+            if nr.value < tol:
+                break
+            rho_old = rho
+            rho = nr.value ** 2
+            beta = rho / rho_old
+        _set(done, d)
+        return L.OK
+
     def b2k_bicgstab_half(self, h, op, rs, r, p, v, s, a0, a1, beta, omega, rho, first, sigma_out, norms_out):
         ctx = self._c(h)
         sh = self._sh(ctx, r)

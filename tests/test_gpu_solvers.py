@@ -892,3 +892,32 @@ def test_blocklanczos_fast_block_mode_matches_reference_mode():
     assert info.converged >= 4
     np.testing.assert_allclose(D[:4], -16.0, atol=1e-7)
     ctx.close()
+
+
+def test_cg_chained_iterations_equal_stepwise():
+    """b2k_cg_chain (rho, beta, <p,q>, ||r|| on the device; one host sync per 32 iterations; convergence test on the
+    device) gives the same iterates as one b2k_cg_step per iteration: same numiter / numops, same x bit for bit."""
+    import importlib
+    ls = importlib.import_module("krylovkit_jl_b200.linsolve")
+    nx, ny = 181, 97
+    n = nx * ny
+    A = ko.stencil_matrix(nx, ny)
+    b = A @ np.ones(n) + 0.01 * ko.splitmix_vector(3, n)
+    ctx = kk.B200Context(n, 16)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    out = {}
+    try:
+        for chain in (True, False):
+            ls.USE_CG_CHAIN = chain
+            res = []
+            for alg in (kk.CG(maxiter=2000, tol=1e-9, verbosity=0), kk.CG(maxiter=45, tol=1e-300, verbosity=0)):
+                x, info = kk.linsolve(op, ctx.from_host(b), None, alg, 0.1, 1.2)
+                res.append((x.to_host(), info.numiter, info.numops, info.converged, info.normres))
+            out[chain] = res
+    finally:
+        ls.USE_CG_CHAIN = True
+    for (x1, it1, ops1, c1, nr1), (x0, it0, ops0, c0, nr0) in zip(out[True], out[False]):
+        assert (it1, ops1, c1) == (it0, ops0, c0)
+        assert np.array_equal(x1, x0) and nr1 == nr0
+    assert out[True][0][3] == 1 and out[True][1][3] == 0 and out[True][1][1] == 45
+    ctx.close()

@@ -237,6 +237,10 @@ def test_fused_branches_bookkeeping(simf):
     G.test_invariant_subspace_early_exit()
 
 
+def test_cg_chain_bookkeeping(simf):
+    G.test_cg_chained_iterations_equal_stepwise()
+
+
 def test_block_fast_mode(sim):
     """the flagged block mode's host logic (BCGS2 coefficients -> M, Gram -> CholeskyQR2, rank fallback)"""
     import test_gpu_primitives as P
