@@ -3,8 +3,8 @@
 # then the sharded path with two ranks on the one GPU
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-( time timeout 900 python -m pytest tests -m gpu -x -q -k "not one_gpu" ) > gpurun_out/r02a_pytest.log 2>&1
-tail -5 gpurun_out/r02a_pytest.log
+( time timeout 1200 python -m pytest tests -m gpu -q --maxfail=12 --timeout 300 -k "not one_gpu" ) > gpurun_out/r02a_pytest.log 2>&1
+grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/r02a_pytest.log | tail -30
 timeout 300 compute-sanitizer --tool racecheck --racecheck-report analysis python -m pytest tests/test_gpu_solvers.py -x -q -k "chained" > gpurun_out/r02a_racecheck.log 2>&1
 tail -8 gpurun_out/r02a_racecheck.log
 timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_solvers.py -x -q -k "chained or invariant" > gpurun_out/r02a_memcheck.log 2>&1
