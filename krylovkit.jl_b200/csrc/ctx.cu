@@ -332,6 +332,13 @@ extern "C" int32_t b2k_ctx_sync(b2k_ctx* ctx) {
 }
 
 extern "C" int64_t b2k_ctx_launch_count(const b2k_ctx* ctx) { return ctx ? ctx->launches : 0; }
+// debugging aid (not in the public header): number of slab columns of a space currently handed out
+extern "C" int32_t b2k_debug_used_columns(const b2k_ctx* ctx, int32_t space) {
+    if (!ctx || space < 0 || space >= (int32_t)ctx->spaces.size()) return -1;
+    int32_t c = 0;
+    for (uint8_t u : ctx->spaces[space].used) c += u ? 1 : 0;
+    return c;
+}
 extern "C" void* b2k_ctx_stream(b2k_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 // ------------------------------------------------------------------ handles ----

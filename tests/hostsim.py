@@ -123,6 +123,9 @@ class HostSimLib:
         self.err = b""
         self.chain = True          # b2k_lanczos_expand_many follows the device-chained handle contract (CGS2)
 
+    def b2k_debug_used_columns(self, h, space):
+        return len(self._c(h).spaces[space].cols)
+
     def b2k_debug_set_chain(self, on):
         self.chain = bool(on)
         return L.OK

@@ -804,16 +804,18 @@ def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None, or
             op = kk.B200CSR.from_scipy(ctx, sp.diags(diag).tocsr())
             x0 = ctx.from_host(ko.splitmix_vector(5, n) + 0.5)
         it = lz.LanczosIterator(op, x0, orth or kk.cgs2)
+        used = lambda: lib.b2k_debug_used_columns(ctx.h, 0)
         f = lz.initialize(it)
+        u0 = used()
         done = lz.expand_many_(it, f, steps, tol)
+        # x0, the basis, the residual — and nothing else (the batch recycles columns internally)
+        assert u0 == 3 and used() == 2 + len(f.V) + 1, (u0, used(), done, len(f.V), list(f.betas))
         out = (done, np.array(f.alphas), np.array(f.betas), np.column_stack([v.to_host() for v in f.V]),
                f.r.to_host())
         del f, it, x0
         import gc
         gc.collect()
-        # every slab column is free again: nothing leaked by the batch's internal column recycling
-        spare = [ctx.empty() for _ in range(steps + 8)]
-        del spare
+        assert used() == 0, used()
         ctx.close()
         return out
     finally:

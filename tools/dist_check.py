@@ -45,6 +45,15 @@ def main():
     A = ko.stencil_matrix(nx, ny)
     x0 = ko.splitmix_vector(20260923, n)
     sl = slice(shard.row_offset, shard.row_offset + shard.n_local)
+    sizes = [sharding.shard_grid_lines(nx, ny, r, world).n_local for r in range(world)]
+
+    def gather(vec):
+        """the global vector from its row shards (padded to equal length: gloo's all_gather wants that)"""
+        loc = torch.zeros(max(sizes), dtype=torch.float64, device=dev)
+        loc[:shard.n_local] = torch.from_numpy(vec.to_host()).to(dev)
+        parts = [torch.zeros(max(sizes), dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(parts, loc)
+        return torch.cat([p[:m] for p, m in zip(parts, sizes)]).cpu().numpy()
     # 1. device-side start vector is the global splitmix sequence
     xd = ctx.splitmix(20260923)
     assert np.array_equal(xd.to_host(), x0[sl])
@@ -72,11 +81,7 @@ def main():
         lam = ko.laplace_eigenvalues(nx, ny)
         assert np.allclose(vals[:3], lam[:3], rtol=1e-10)
         # gather one Ritz vector and check the residual globally
-        vloc = torch.from_numpy(vecs[0].to_host()).to(dev)
-        parts = [torch.zeros(sharding.shard_grid_lines(nx, ny, r, world).n_local, dtype=torch.float64,
-                             device=dev) for r in range(world)]
-        dist.all_gather(parts, vloc)
-        v = torch.cat(parts).cpu().numpy()
+        v = gather(vecs[0])
         assert np.linalg.norm(A @ v - vals[0] * v) < 1e-8
         del vecs
     # 4b. the benchmark regime (fixed restart cycles, tol = 0) through the device-chained steps — in-kernel
@@ -98,12 +103,6 @@ def main():
     assert np.allclose(res[1][2], oinfo["normres"][:4], rtol=1e-6)
     # 5. widened drivers on the sharded context: every scalar they see is all-reduced inside
     #    the library, so the host logic is rank-replicated; results = the serial oracle's
-    def gather(vec):
-        loc = torch.from_numpy(vec.to_host()).to(dev)
-        parts = [torch.zeros(sharding.shard_grid_lines(nx, ny, r, world).n_local, dtype=torch.float64,
-                             device=dev) for r in range(world)]
-        dist.all_gather(parts, loc)
-        return torch.cat(parts).cpu().numpy()
 
     import importlib
     ls = importlib.import_module("krylovkit_jl_b200.linsolve")
