@@ -53,7 +53,7 @@ def initialize(it: GKLIterator) -> GKLFactorization:
     v0 = apply_adjoint(it.operator, u0)
     alpha = v0.norm() / beta0
     Av0 = apply_normal(it.operator, v0)
-    alpha2 = u0.inner(Av0) / beta0 ** 2
+    alpha2 = u0.inner(Av0) / (beta0 * beta0)
     if not math.isclose(alpha2, alpha * alpha, rel_tol=math.sqrt(_eps(u0))):
         raise ValueError("operator and its adjoint are not compatible")
     u = u0.scale(1 / beta0)

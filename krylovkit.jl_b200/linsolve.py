@@ -224,7 +224,7 @@ def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
         return x, ConvergenceInfo(1, r, normr, numiter, numops)
     ctx = b.ctx
     fused = USE_FUSED_CG and isinstance(operator, B200CSR)
-    rho = normr ** 2
+    rho = normr * normr           # Julia: normr^2 is literal_pow = normr*normr
     p = r.zerovector()
     q = r.zerovector() if fused else None
     beta = 0.0           # first iteration: p = r  (cg.jl:35)
@@ -259,11 +259,11 @@ def _cg(operator, b: B200Vec, x0: B200Vec, alg: CG, a0: float, a1: float):
             r = r.scale_(1.0, b)
             r = r.add_(apply(operator, x, a0, a1), -1.0)
             normr = r.norm()
-            rho = normr ** 2
+            rho = normr * normr           # Julia: normr^2 is literal_pow = normr*normr
             beta = 0.0
         else:
             rhoold = rho
-            rho = normr ** 2
+            rho = normr * normr           # Julia: normr^2 is literal_pow = normr*normr
             beta = rho / rhoold
         was_first, first = first, False
         numops += 1

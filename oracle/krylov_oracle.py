@@ -1045,7 +1045,7 @@ def linsolve_cg(A, b, x0=None, maxiter=100, tol=1e-12, a0=0.0, a1=1.0):
     numops, numiter = 1, 0
     if normr < tol:
         return x, dict(converged=1, residual=r, normres=normr, numiter=numiter, numops=numops)
-    rho = normr ** 2
+    rho = normr * normr       # Julia literal_pow: normr^2 = normr*normr
     p = r * 1.0
     q = apply(A, p, a0, a1)
     alpha = rho / inner(p, q)
@@ -1053,7 +1053,7 @@ def linsolve_cg(A, b, x0=None, maxiter=100, tol=1e-12, a0=0.0, a1=1.0):
     r = r - alpha * q
     normr = norm(r)
     rhoold = rho
-    rho = normr ** 2
+    rho = normr * normr       # Julia literal_pow: normr^2 = normr*normr
     beta = rho / rhoold
     numops += 1
     numiter += 1
@@ -1069,11 +1069,11 @@ def linsolve_cg(A, b, x0=None, maxiter=100, tol=1e-12, a0=0.0, a1=1.0):
         if normr < tol:
             r = b - apply(A, x, a0, a1)
             normr = norm(r)
-            rho = normr ** 2
+            rho = normr * normr       # Julia literal_pow: normr^2 = normr*normr
             beta = 0.0
         else:
             rhoold = rho
-            rho = normr ** 2
+            rho = normr * normr       # Julia literal_pow: normr^2 = normr*normr
             beta = rho / rhoold
         numops += 1
         numiter += 1
@@ -1387,7 +1387,7 @@ def gkl_initialize(A, u0, orth: Orth):
     v0 = apply_adjoint(A, u0)
     alpha = norm(v0) / beta0
     Av0 = apply_normal(A, v0)
-    alpha2 = inner(u0, Av0) / beta0 ** 2
+    alpha2 = inner(u0, Av0) / (beta0 * beta0)
     if not np.isclose(alpha2, alpha * alpha, rtol=math.sqrt(np.finfo(np.asarray(u0).dtype).eps)):
         raise ValueError("operator and its adjoint are not compatible")
     T = np.asarray(u0).dtype.type

@@ -601,7 +601,7 @@ class HostSimLib:
             if nr.value < tol:
                 break
             rho_old = rho
-            rho = nr.value ** 2
+            rho = nr.value * nr.value
             beta = rho / rho_old
         _set(done, d)
         return L.OK

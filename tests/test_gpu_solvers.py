@@ -809,7 +809,7 @@ def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None, or
         u0 = used()
         done = lz.expand_many_(it, f, steps, tol)
         # x0, the basis, the residual — and nothing else (the batch recycles columns internally)
-        assert u0 == 3 and used() == 2 + len(f.V) + 1, (u0, used(), done, len(f.V), list(f.betas))
+        assert u0 == 3 and used() == 1 + len(f.V) + 1, (u0, used(), done, len(f.V), list(f.betas))
         out = (done, np.array(f.alphas), np.array(f.betas), np.column_stack([v.to_host() for v in f.V]),
                f.r.to_host())
         del f, it, x0
