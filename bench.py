@@ -573,7 +573,8 @@ def other_configs(kk, a, rank, world, local_rank, dist):
         b = kk.apply(op, ones)
         rec = {"workload": f"linsolve(GMRES, krylovdim={kd}) on the {n}x{n} convection-diffusion CSR (5-point, "
                            "nonsymmetric), b = A*1, x0 = 0, 5 restart cycles (tol -> 0: fixed work)"}
-        for name, orth, gname in (("cgs2", kk.cgs2, "c3"), ("mgs2_reference_default", kk.mgs2, None)):
+        for name, orth, gname in (("cgs2", kk.cgs2, "c3"), ("mgs2_reference_default", kk.mgs2, None),
+                                  ("mgs2_blocked_flagged", kk.mgs2b, None)):
             alg = kk.GMRES(orth=orth, krylovdim=kd, maxiter=5, tol=1e-300, verbosity=0)
             (x, info), t = timed(ctx, lambda: kk.linsolve(op, b, None, alg))
             chk = kk.apply(op, x)

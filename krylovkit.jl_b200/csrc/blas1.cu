@@ -321,7 +321,12 @@ k_cg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* 
     }
 }
 
-// p <- r + beta p with beta on the device (same fma as k_axpby<T, 2> with alpha = 1)
+// x + beta*y with the product rounded first: what k_axpby<T, 2> computes for alpha = 1, fma(1, x, rn(beta*y)).
+// (Written with the explicit-rounding intrinsics: `x + beta*y` would be contracted into ONE fma(beta, y, x).)
+__device__ __forceinline__ double xpby_rn(double x, double beta, double y) { return __dadd_rn(x, __dmul_rn(beta, y)); }
+__device__ __forceinline__ float xpby_rn(float x, float beta, float y) { return __fadd_rn(x, __fmul_rn(beta, y)); }
+
+// p <- r + beta p with beta on the device (same bits as k_axpby<T, 2> with alpha = 1)
 template <typename T>
 __global__ void __launch_bounds__(BT) k_xpby_dev(T* __restrict__ y, const T* __restrict__ x, int64_t n,
                                                  const double* __restrict__ beta_dev, const int* __restrict__ stop) {
@@ -336,12 +341,12 @@ __global__ void __launch_bounds__(BT) k_xpby_dev(T* __restrict__ y, const T* __r
         vload<T>(x + i * V, a);
         vload<T>(y + i * V, b);
 #pragma unroll
-        for (int j = 0; j < V; ++j) b[j] = fma((T)1, a[j], beta * b[j]);
+        for (int j = 0; j < V; ++j) b[j] = xpby_rn(a[j], beta, b[j]);
         vstore<T>(y + i * V, b);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         const int64_t i = nv * V + threadIdx.x;
-        y[i] = fma((T)1, x[i], beta * y[i]);
+        y[i] = xpby_rn(x[i], beta, y[i]);
     }
 }
 

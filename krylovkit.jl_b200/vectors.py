@@ -213,9 +213,12 @@ def _free_handle(lib, ctx_h, handle, alive):
     if not alive[0]:
         return
     try:
-        lib.b2k_vec_free(ctx_h, handle)
+        st = lib.b2k_vec_free(ctx_h, handle)
     except Exception:  # interpreter shutdown
-        pass
+        return
+    if st != 0:        # a finalizer cannot raise usefully, but a failing free is a bookkeeping bug: say so
+        import sys
+        sys.stderr.write(f"b200krylov: b2k_vec_free(handle {handle:#x}) failed with status {st}\n")
 
 
 def _destroy_ctx(lib, ctx_h, alive):

@@ -812,10 +812,11 @@ def _expand_many_run(chain: bool, nx=97, ny=61, steps=30, tol=0.0, diag=None, or
         assert u0 == 3 and used() == 1 + len(f.V) + 1, (u0, used(), done, len(f.V), list(f.betas))
         out = (done, np.array(f.alphas), np.array(f.betas), np.column_stack([v.to_host() for v in f.V]),
                f.r.to_host())
+        live = {"x0": hex(x0.handle), "V": [hex(v.handle) for v in f.V], "r": hex(f.r.handle)}
         del f, it, x0
         import gc
         gc.collect()
-        assert used() == 0, used()
+        assert used() == 0, (used(), live, [o for o in gc.get_objects() if type(o).__name__ == "B200Vec"])
         ctx.close()
         return out
     finally:
