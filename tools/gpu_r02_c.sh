@@ -4,6 +4,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
+bash tools/gpu_r02_e.sh
 ( time timeout 600 python -m pytest tests/test_gpu_dist.py -q --timeout 500 ) > gpurun_out/r02c_dist_n$N.log 2>&1
 grep -E "Error|assert|passed|failed|dist_check" gpurun_out/r02c_dist_n$N.log | tail -12
 P=29800
