@@ -188,13 +188,13 @@ constexpr int SPP_RMAX = 1024;            // rowptr entries staged per block
 constexpr int SPP_TV = SP_NNZ + 8;        // staged nonzeros (block + alignment slack)
 constexpr int SPP_CONS = 256;
 constexpr int SPP_THREADS = SPP_CONS + 32;
-template <typename T> struct SppLayout {
+template <typename T, int NSTG = SPP_NSTG> struct SppLayout {
     static constexpr int VAL_BYTES = SPP_TV * (int)sizeof(T);
     static constexpr int COL_BYTES = SPP_TV * 4;
     static constexpr int RP_BYTES = (SPP_RMAX + 8) * 4;
     static constexpr int STAGE = VAL_BYTES + COL_BYTES + RP_BYTES;
-    static constexpr int OFF_BAR = SPP_NSTG * STAGE;
-    static constexpr int OFF_RED = OFF_BAR + 2 * SPP_NSTG * 8 + 16;
+    static constexpr int OFF_BAR = NSTG * STAGE;
+    static constexpr int OFF_RED = OFF_BAR + 2 * NSTG * 8 + 16;
     static constexpr int SMEM = OFF_RED + 32 * 8 + 16;
 };
 
@@ -204,8 +204,10 @@ __global__ void k_pblk(const int32_t* __restrict__ rowptr, const int32_t* __rest
     if (b < count) pblk[b] = rowptr[rowblk[b]];
 }
 
-template <typename T>
-__global__ void __launch_bounds__(SPP_THREADS, 3)
+// NSTG ring stages, MINB CTAs per SM (variants: (3, 3) = round 1; (2, 4): fewer stages, more resident warps to
+// hide the x-gather latency — the kernel is latency-, not bandwidth-bound: ncu r02 DRAM 51 %, warps active 42 %)
+template <typename T, int NSTG, int MINB>
+__global__ void __launch_bounds__(SPP_THREADS, MINB)
 k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
             const T* __restrict__ vals, const T* __restrict__ x, const T* __restrict__ halo,
             int32_t n_loc, T* __restrict__ y, const int32_t* __restrict__ rowblk,
@@ -213,14 +215,14 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const T* __restrict__ xs, const T* __restrict__ dotv, double* __restrict__ part,
             unsigned* __restrict__ ticket, double* __restrict__ out, const SpmvFuse fz,
             const __grid_constant__ PeerStep ps) {
-    using LY = SppLayout<T>;
+    using LY = SppLayout<T, NSTG>;
     extern __shared__ __align__(128) uint8_t smem[];
     if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
-    const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + SPP_NSTG * 8;
+    const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + NSTG * 8;
     double* red = reinterpret_cast<double*>(smem + LY::OFF_RED);
     int* flag = reinterpret_cast<int*>(smem + LY::OFF_RED + 32 * 8);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SPP_NSTG; ++i) {
+        for (int i = 0; i < NSTG; ++i) {
             mbar_init(full + 8 * i, 1);
             mbar_init(empty + 8 * i, SPP_CONS / 32);
         }
@@ -256,7 +258,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             } else {
                 if (lane == 0) mbar_arrive(full + 8 * s);   // long row: consumers read global memory
             }
-            if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+            if (++s == NSTG) { s = 0; ph ^= 1; }
         }
         return;
     }
@@ -363,7 +365,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
         fence_proxy_async();   // generic-proxy writes to the stage precede its reuse by the TMA unit
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8 * s);
-        if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+        if (++s == NSTG) { s = 0; ph ^= 1; }
     }
     if (want_dot) {
         double v = warp_sum((double)dacc);
@@ -1166,6 +1168,7 @@ extern "C" int32_t b2k_op_csr_download(b2k_ctx* ctx, const b2k_op* op, int32_t* 
 // ------------------------------------------------------------------ apply ----
 
 static bool g_spmv_pipe = true;
+static int g_spmv_variant = 0;     // 0: 3 stages x 3 CTAs/SM, 1: 2 stages x 4 CTAs/SM (B2K_SPMV_VARIANT)
 
 extern "C" int32_t b2k_debug_set_spmv_pipe(int32_t on) {
     g_spmv_pipe = on != 0;
@@ -1178,10 +1181,16 @@ int32_t b2k_spmv_init(b2k_ctx* ctx) {
                                        SppLayout<double>::SMEM));
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmm_pipe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SppLayout<float>::SMEM));
-    B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmv_pipe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SppLayout<double>::SMEM));
-    B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmv_pipe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SppLayout<float>::SMEM));
+    B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<double, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<double, 3>::SMEM));
+    B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<float, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<float, 3>::SMEM));
+    B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<double, 2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<double, 2>::SMEM));
+    B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<float, 2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SppLayout<float, 2>::SMEM));
+    const char* sv = getenv("B2K_SPMV_VARIANT");
+    if (sv) g_spmv_variant = atoi(sv);
     return B2K_OK;
 }
 
@@ -1295,15 +1304,21 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
     const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
                                               2.0 * ctx->esize * op->n_rows);
     if (g_spmv_pipe) {
-        const int grid = std::min(op->nblk, 3 * ctx->num_sms);
-#define LAUNCH(T)                                                                              \
-    k_spmv_pipe<T><<<grid, SPP_THREADS, SppLayout<T>::SMEM, ctx->stream>>>(                    \
+        const int per_sm = g_spmv_variant == 1 ? 4 : 3;
+        const int grid = std::min(op->nblk, per_sm * ctx->num_sms);
+#define LAUNCH_V(T, NS, MB)                                                                    \
+    k_spmv_pipe<T, NS, MB><<<grid, SPP_THREADS, SppLayout<T, NS>::SMEM, ctx->stream>>>(        \
         op->rowptr, op->colidx, (const T*)op->vals, (const T*)xsrc, (const T*)halo, n_loc,     \
         (T*)y.ptr, op->rowblk, op->pblk, op->nblk, (T)a0, (T)a1, shifted ? 1 : 0,              \
         (const T*)x.ptr, dotv ? (const T*)dotv->ptr : nullptr, op->part, ctx->d_sync, out, fz, ps)
-        if (ctx->dtype == B2K_F64) LAUNCH(double);
-        else LAUNCH(float);
-#undef LAUNCH
+        if (g_spmv_variant == 1) {
+            if (ctx->dtype == B2K_F64) LAUNCH_V(double, 2, 4);
+            else LAUNCH_V(float, 2, 4);
+        } else {
+            if (ctx->dtype == B2K_F64) LAUNCH_V(double, 3, 3);
+            else LAUNCH_V(float, 3, 3);
+        }
+#undef LAUNCH_V
     } else {
 #define LAUNCH(T)                                                                              \
     k_spmv_stream<T><<<op->nblk, SP_BT, 0, ctx->stream>>>(                                     \

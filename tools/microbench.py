@@ -101,6 +101,15 @@ def main():
     d = C.c_double()
     h = (C.c_double * (k + 1))()
 
+    # bring the clocks up first: a B200 idles at 120 MHz and needs tens of milliseconds of load to reach its
+    # running clocks — r01's BLAS-1 figures (0.38-0.57) were taken cold and were clock ramp, not kernel quality
+    # (tools/probes/blas1_probe.cu: the same launch shape runs at 0.83-0.87 once warm)
+    nrm0, ps0 = C.c_double(), C.c_int32()
+    for _ in range(30):
+        lib.b2k_basis_orthogonalize(ctx.h, y.handle, hs, k, h, L.CGS2, 0.0, C.byref(nrm0), C.byref(ps0))
+    lib.b2k_vec_fill_splitmix(ctx.h, y.handle, 2)
+    # scalars-returning calls block on a D2H copy + stream sync per call (the KrylovKit contract): their time
+    # includes that round trip; the *_async rows time the same kernels without it
     rec("vec_inner", tm.time(lambda: lib.b2k_vec_inner(ctx.h, x.handle, y.handle, C.byref(d)), a.reps), 2 * W)
     rec("vec_norm", tm.time(lambda: lib.b2k_vec_norm(ctx.h, x.handle, C.byref(d)), a.reps), W)
     rec("vec_axpby", tm.time(lambda: lib.b2k_vec_axpby(ctx.h, y.handle, x.handle, 1e-9, 1.0), a.reps), 3 * W)
