@@ -561,6 +561,8 @@ int32_t enqueue_finalize(b2k_ctx* ctx, const double* A, const double* B, const d
     return B2K_OK;
 }
 
+bool g_l2_hints = true;      // B2K_L2_HINTS=0 switches the eviction-priority hints off (A/B measurements)
+
 struct Panel {
     void* base;      // space base pointer
     int64_t ld, n;
@@ -602,6 +604,7 @@ PhaseParams<T> base_params(const Panel& pn, int k, const void* x, void* xout) {
     p.beta_mode = 1;
     p.betax = (T)1;
     p.alphac = (T)1;
+    p.l2_hints = g_l2_hints ? 1 : 0;
     return p;
 }
 
@@ -788,6 +791,7 @@ int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res
 
 // called once per context (ctx.cu): opt in to > 48 KB dynamic shared memory
 int32_t b2k_basis_init(b2k_ctx* ctx) {
+    if (const char* e = getenv("B2K_L2_HINTS")) g_l2_hints = e[0] != '0';
 #define SETATTR(fn, bytes) \
     B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
     SETATTR((k_phase<double, false, true>), SMEM_BYTES);
@@ -1343,6 +1347,7 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
         fz.vout = rV.ptr;
         fz.stop = d_stop;
         fz.dot_self = 1;
+        fz.l2_hints = g_l2_hints ? 1 : 0;
         if (alg == B2K_MGS2B) {                  // alpha = <v, A v - beta v_prev>: the modified order
             fz.dot_sub_vec = vprev.ptr;
             fz.dot_sub_scale = rec_prev + 2;

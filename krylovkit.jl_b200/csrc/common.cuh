@@ -177,6 +177,7 @@ struct SpmvFuse {
     void* vout;
     const int* stop;
     int dot_self;
+    int l2_hints;          // matrix stream evict_first, y = A x evict_last (it is the next kernel's operand)
     // the fused dot product is taken with y - (*dot_sub_scale) * dot_sub_vec instead of y (y itself is stored
     // unchanged): alpha = <v, A v - beta v_prev>, the ModifiedGramSchmidt order of lanczos.jl:304-306, 326-328
     const void* dot_sub_vec;
@@ -352,6 +353,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// L2 eviction-priority hints.  The step alternates between streams that are read once (basis panels, the CSR
+// arrays: evict_first) and ONE vector that the next kernel gathers from or re-reads (w = A v, the updated w:
+// evict_last) — 80 MB against 126 MB of L2; without hints the multi-GB streams flush it.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void st_hint(double* p, double v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_hint(float* p, float v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

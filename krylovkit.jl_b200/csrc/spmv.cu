@@ -252,9 +252,16 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 const uint32_t st = smem_u32(smem + s * LY::STAGE);
                 if (lane == 0) mbar_expect_tx(full + 8 * s, vb + cb + rb);
                 __syncwarp();
-                if (lane == 0 && vb) bulk_g2s(st, vals + p0a, vb, full + 8 * s);
-                if (lane == 1 && cb) bulk_g2s(st + LY::VAL_BYTES, colidx + p0a, cb, full + 8 * s);
-                if (lane == 2 && rb) bulk_g2s(st + LY::VAL_BYTES + LY::COL_BYTES, rowptr + r0a, rb, full + 8 * s);
+                if (fz.l2_hints) {
+                    const uint64_t pol = l2_policy_evict_first();
+                    if (lane == 0 && vb) bulk_g2s_hint(st, vals + p0a, vb, full + 8 * s, pol);
+                    if (lane == 1 && cb) bulk_g2s_hint(st + LY::VAL_BYTES, colidx + p0a, cb, full + 8 * s, pol);
+                    if (lane == 2 && rb) bulk_g2s_hint(st + LY::VAL_BYTES + LY::COL_BYTES, rowptr + r0a, rb, full + 8 * s, pol);
+                } else {
+                    if (lane == 0 && vb) bulk_g2s(st, vals + p0a, vb, full + 8 * s);
+                    if (lane == 1 && cb) bulk_g2s(st + LY::VAL_BYTES, colidx + p0a, cb, full + 8 * s);
+                    if (lane == 2 && rb) bulk_g2s(st + LY::VAL_BYTES + LY::COL_BYTES, rowptr + r0a, rb, full + 8 * s);
+                }
             } else {
                 if (lane == 0) mbar_arrive(full + 8 * s);   // long row: consumers read global memory
             }
@@ -276,6 +283,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     T* const vout = reinterpret_cast<T*>(fz.vout);
     const bool self = (vout != nullptr) || fz.dot_self;
     const bool want_dot = (dotv != nullptr) || fz.dot_self;
+    const uint64_t pol_last = fz.l2_hints ? l2_policy_evict_last() : 0;
     const T* const dsub = reinterpret_cast<const T*>(fz.dot_sub_vec);
     const T dsc = dsub ? (T)(*fz.dot_sub_scale) : (T)0;
     T dacc = (T)0;
@@ -327,7 +335,8 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 T sum = (T)0;
                 for (int p = a; p < b; ++p) sum += vs[p];
                 if (shifted) sum = fma(a0, xsr, a1 * sum);
-                y[r] = sum;
+                if (fz.l2_hints) st_hint(y + r, sum, pol_last);
+                else y[r] = sum;
                 if (self) {
                     const T vn = xself * sc;
                     if (vout) vout[r] = vn;

@@ -91,6 +91,7 @@ struct PhaseParams {
     int64_t send_lo, send_hi;
     int32_t nvec;    // 1 or 3
     int32_t store_x; // write x'' (UPDATE) or x' (prologue write-back) to xout
+    int32_t l2_hints; // panel loads evict_first, the stored vector evict_last (common.cuh)
     // UPDATE: x'' = betax*x' + sum_j Q[:,j]*cs[j],  cs[j] = alphac * sum_g coef[g*stride+j]
     const double* coef;
     const T* coef_t;     // alternative: coefficients stored as a device vector of T
@@ -183,6 +184,7 @@ __device__ __forceinline__ void producer_phase(const PhaseParams<T>& p, const Co
     const uint32_t me = (threadIdx.x - NCONS) >> 5;     // producer warp index
     const int nch = (p.k + C - 1) / C;
     const int64_t ntiles = (p.n + R - 1) / R;
+    const uint64_t pol = p.l2_hints ? l2_policy_evict_first() : 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * R;
         const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
@@ -209,8 +211,12 @@ __device__ __forceinline__ void producer_phase(const PhaseParams<T>& p, const Co
                 __syncwarp();
                 if (lane < ncol) {
                     const T* src = p.base + (int64_t)cl.c[c * C + lane] * p.ld + r0;
-                    bulk_g2s(sm.ring + st.s * SLOT_BYTES + lane * R * (int)sizeof(T), src, bytes,
-                             sm.full + 8 * st.s);
+                    if (p.l2_hints)
+                        bulk_g2s_hint(sm.ring + st.s * SLOT_BYTES + lane * R * (int)sizeof(T), src, bytes,
+                                      sm.full + 8 * st.s, pol);
+                    else
+                        bulk_g2s(sm.ring + st.s * SLOT_BYTES + lane * R * (int)sizeof(T), src, bytes,
+                                 sm.full + 8 * st.s);
                 }
             }
             ++st.g;
@@ -273,6 +279,7 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
         for (int cc = 0; cc < CPW; ++cc) acc_h[c][cc] = (T)0;
     T nrm = (T)0;
     int buf = 0;
+    const uint64_t pol_last = p.l2_hints ? l2_policy_evict_last() : 0;
     T c1 = p.c1, c2 = p.c2;
     if (p.c1_dev) c1 = (T)(-(*reinterpret_cast<const volatile double*>(p.c1_dev)));
     if (p.c2_dev) {
@@ -321,7 +328,8 @@ __device__ __forceinline__ void consumer_phase(const PhaseParams<T>& p, const Sm
             if (tid >= rt) acc = (T)0;
         }
         if (p.store_x && tid < rt) {
-            p.xout[r0 + tid] = acc;
+            if (p.l2_hints) st_hint(p.xout + r0 + tid, acc, pol_last);
+            else p.xout[r0 + tid] = acc;
             if (UPDATE && !PROJECT) {
                 const int64_t r = r0 + tid;
                 if (p.halo_dn && r < p.send_lo) p.halo_dn[r] = acc;
