@@ -99,9 +99,11 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
     pipe_setup(sm, ragged);
     Pipe st;
     const bool prod = threadIdx.x >= NCONS;
-    if (fp.ps.on && fp.ps.seq_alpha) {       // <v, A v>: every rank's partial must be in my window
+    if (fp.ps.on && fp.ps.seq_alpha && !prod) {
+        // <v, A v>: every rank's partial must be in my window before the prologue; the producer warps do not
+        // wait — they fill the ring with the first basis tiles meanwhile
         peer_wait(fp.ps.pd, PEER_CH_ALPHA, fp.ps.seq_alpha, threadIdx.x);
-        __syncthreads();
+        named_bar_sync(1, NCONS);
     }
     for (int i = 0; i < fp.nph; ++i) {
         if (prod) {

@@ -130,6 +130,13 @@ def _eigsolve_arnoldi_host(A, x0, howmany, which, alg, device=0):
 
 
 USE_NATIVE_RESTART = True      # b2k_host_lanczos_restart (C++) instead of the numpy loop below
+HOSTPROF: dict | None = None   # set to {} to accumulate wall seconds per driver section (bench.py reports them)
+
+
+def _tick(name, t0):
+    if HOSTPROF is not None:
+        import time
+        HOSTPROF[name] = HOSTPROF.get(name, 0.0) + (time.perf_counter() - t0)
 
 
 def restart_lanczos_form(HH, D, f, U, keep, alphas, betas):
@@ -191,6 +198,11 @@ def _eigsolve_host(A, x0, howmany, which, alg, out_vectors=None, shard=None, ncc
         ctx.close()
 
 
+def _now():
+    import time
+    return time.perf_counter()
+
+
 def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, sink=None):
     krylovdim, maxiter = alg.krylovdim, alg.maxiter
     if howmany > krylovdim:
@@ -209,6 +221,7 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
             warnings.warn(f"Invariant subspace of dimension {K} (up to requested tolerance `tol = {tol}`), "
                           f"which is smaller than the number of requested eigenvalues (i.e. `howmany == {howmany}`).")
         if K == krylovdim or beta <= tol or (alg.eager and K >= howmany):
+            _t0 = _now()
             if K == 1:
                 D = np.array([fact.alphas[0]])
                 U = np.ones((1, 1))
@@ -223,6 +236,7 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
                 converged = 0
                 while converged < K and abs(f[converged]) <= tol:
                     converged += 1
+            _tick("projected_eigenproblem", _t0)
             if converged >= howmany or beta <= tol:
                 break
         if K < krylovdim:
@@ -232,10 +246,13 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
             else:
                 # nothing happens between expansions until K == krylovdim or β <= tol
                 # (eigsolve/lanczos.jl:45,77-79): run them back to back
+                _t0 = _now()
                 numops += lz.expand_many_(it, fact, krylovdim - K, tol)
+                _tick("expand", _t0)
         else:
             if numiter == maxiter:
                 break
+            _t0 = _now()
             keep = (3 * krylovdim + 2 * converged) // 5
             # restore Lanczos form in the first keep columns — eigsolve/lanczos.jl:88-105
             if USE_NATIVE_RESTART:
@@ -254,6 +271,8 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
             B[keep] = B[keep].scale_(1 / beta, r)     # B[keep+1] = scale!!(r, 1/β): column reuse
             fact = lz.shrink_(fact, keep)
             numiter += 1
+            _tick("restart", _t0)
+    _t0 = _now()
     hm = howmany
     if converged > howmany:
         hm = converged
@@ -272,6 +291,7 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
             sink(i, v)
             v.free()
     normres = np.abs(f[:hm])
+    _tick("ritz_vectors", _t0)
     if converged < howmany and alg.verbosity >= WARN_LEVEL:
         warnings.warn(f"Lanczos eigsolve stopped without convergence after {numiter} iterations: "
                       f"{converged} eigenvalues converged, normres = {normres}, numops = {numops}")
