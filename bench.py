@@ -25,11 +25,15 @@ applications per second (KrylovKit's numops/s, SURVEY §5 "iterations/sec").
              multi-threaded Array fast path; no Julia in the image) on a bounded sample of the
              same workload at full n: initialize + 30 expand! steps (31 operator applications at
              basis sizes 1..31 — the cheap early part of a cycle, so the CPU figure is optimistic).
-  --impl reference : the same CPU path on the WHOLE job per step (the oracle's eigsolve driver with
-             the same restart cycles) when that fits the time budget, else a bounded sample.
+  --impl reference : the same CPU path on the WHOLE job (the oracle's eigsolve driver with the same restart
+             cycles), as many whole jobs as fit a ~200 s budget (steps_timed); prints its Ritz values.
+  parity   : every arm asserts its Ritz values against the oracle's committed full-size results
+             (tests/golden/fullsize.json): <= 1e-10 relative (+ 4 ulp(||A||) floor), numops equal.
+  other_configs : BASELINE.json configs 3, 4, 5 measured after the headline, with their own parity evidence.
 
-N > 1: STRONG scaling — the same 1e7-row problem row-sharded over N ranks (halo exchange
-for the SpMV + NCCL all-reduce of the projection coefficients).
+N > 1: STRONG scaling — the same 1e7-row problem row-sharded over N ranks; halo rows, <v,Av>, the projection
+coefficients and ||w||^2 are exchanged inside the two kernels of a step through the NVLink peer window
+(B2K_PEER=0 falls back to NCCL calls between the sweeps).
 """
 from __future__ import annotations
 
@@ -418,7 +422,11 @@ def run_ours(a):
                 "bound": "hbm", "achieved": gs.get("GBs"), "peak": pk, "unit": "GB/s",
                 "frac": gs.get("frac"), "peak_kind": pk_kind, "traffic": traffic, "traffic_note": traffic_note,
                 "algorithmic_bytes": "(2k+3)*8n per launch, k = basis size incl. the new vector; summed over launches",
-                "avg_launch_ms": gs.get("avg_ms")}
+                "avg_launch_ms": gs.get("avg_ms"),
+                "includes": ("kernel only" if world == 1 else
+                             "kernel INCLUDING its in-kernel cross-GPU exchanges over the NVLink peer window (waiting for "
+                             "<v,Av>, the coefficient sum at the phase boundary and ||w||^2 of the slowest rank): at "
+                             "N > 1 this is kernel + collective time, not a pure HBM figure")}
 
     # ---- end to end through the host-buffer API: every rank uploads ITS rows of A (CSR with global
     # column indices) and its slice of x0 from pinned memory, solves, downloads its slice of the vectors

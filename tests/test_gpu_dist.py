@@ -19,8 +19,8 @@ def _ngpus():
         return 0
 
 
-def _run(port, extra_env, timeout=600):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+def _run(port, extra_env, timeout=600, nproc=2):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py")]
     env = dict(os.environ, **extra_env)
     # own process group: on a timeout the launcher AND its workers (whose kernels may be spinning on a flag that
@@ -47,3 +47,11 @@ def test_row_sharded_two_ranks_on_one_gpu():
     """Two processes on GPU 0: CUDA-IPC peer windows, no NCCL.  Every cross-rank wait is resolved by the
     driver's time slicing between the two contexts, so this is slow per step but exercises the same kernels."""
     _run(29613, {"B2K_ONE_GPU": "1", "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]})
+
+
+def test_row_sharded_three_ranks_on_one_gpu():
+    """Three ranks on GPU 0: the middle rank has TWO neighbours (halo rows pushed both ways by the Gram-Schmidt
+    launch, three-way rank-ordered sums) and the shards are unequal (151 grid lines over 3 ranks).  Primitives, the
+    converged eigsolve and the device-chained fixed-cycle job against the serial oracle (the short form of dist_check)."""
+    _run(29615, {"B2K_ONE_GPU": "1", "DIST_CHECK_SHORT": "1",
+                 "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]}, nproc=3)

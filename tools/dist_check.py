@@ -101,6 +101,13 @@ def main():
     assert np.allclose(res[1][0], ovals[:4], rtol=1e-10) and np.allclose(res[0][0], ovals[:4], rtol=1e-10)
     assert np.allclose(res[1][0], res[0][0], rtol=1e-12), (res[1][0], res[0][0])
     assert np.allclose(res[1][2], oinfo["normres"][:4], rtol=1e-6)
+    if os.environ.get("DIST_CHECK_SHORT", "") == "1":
+        if rank == 0:
+            print(f"dist_check ok on {world} ranks (short): Ritz values {res[1][0][:3]}")
+        dist.barrier()
+        ctx.close()
+        dist.destroy_process_group()
+        return
     # 5. widened drivers on the sharded context: every scalar they see is all-reduced inside
     #    the library, so the host logic is rank-replicated; results = the serial oracle's
 
