@@ -163,6 +163,13 @@ int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx, int64_t ny
                               int64_t nz, const double c[7]);
 /* Dense column-major m x n matrix (apply_normal / apply_adjoint, src/apply.jl:14-15).
  * x in `space_in` (length n), y in `space_out` (length m, row-sharded in dist mode). */
+/* Matrix-free form of b2k_op_create_stencil: nothing is assembled, every apply evaluates the
+ * 5-/7-point stencil from the vector itself — 16 n bytes instead of 12 nnz + 20 n per apply — with the products
+ * rounded and summed in the assembled operator's order (bit-identical results).  Works with every call that takes
+ * a b2k_op (apply, shifted apply, fused dot, the device-chained Lanczos steps, CG / BiCGStab steps); row-sharded
+ * contexts must shard by whole grid lines (2-D) / planes (3-D). */
+int32_t b2k_op_create_stencil_free(b2k_ctx* ctx, b2k_op** out, int64_t nx, int64_t ny, int64_t nz,
+                                   const double c[7]);
 int32_t b2k_op_create_dense(b2k_ctx* ctx, b2k_op** out, int64_t m_local, int64_t n,
                             const void* host_colmajor, int64_t ld);
 /* Dense m x n with entries uniform(-0.5,0.5) from the counter RNG, generated on device:

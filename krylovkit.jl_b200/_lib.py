@@ -82,6 +82,8 @@ _PROTOS = {
                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "b2k_op_create_stencil": (C.c_int32, [c_ctx, P(c_op), C.c_int64, C.c_int64, C.c_int64,
                                           P(C.c_double)]),
+    "b2k_op_create_stencil_free": (C.c_int32, [c_ctx, P(c_op), C.c_int64, C.c_int64, C.c_int64,
+                                               P(C.c_double)]),
     "b2k_op_create_dense": (C.c_int32, [c_ctx, P(c_op), C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "b2k_op_create_dense_splitmix": (C.c_int32, [c_ctx, P(c_op), C.c_int64, C.c_int64, C.c_uint64]),
     "b2k_op_destroy": (C.c_int32, [c_ctx, c_op]),

@@ -1236,7 +1236,7 @@ bool chain_ok(const b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, int32_t
     int64_t op_rows = 0, op_cols = 0;
     int32_t op_kind = -1;
     if (b2k_op_info(op, &op_rows, &op_cols, nullptr, &op_kind) != B2K_OK) return false;
-    if (op_kind != 0 || beta_old == 0.0 || !(beta_old == beta_old)) return false;
+    if ((op_kind != 0 && op_kind != 2) || beta_old == 0.0 || !(beta_old == beta_old)) return false;
     const int32_t sp = B2K_VEC_SPACE(cols[k]);
     if (sp < 0 || sp >= (int32_t)ctx->spaces.size()) return false;
     const B2kSpace& s = ctx->spaces[sp];

@@ -28,7 +28,10 @@ constexpr int SP_NNZ = 1536;      // nonzeros per CTA tile
 constexpr int SP_ROWS = 2048;     // max rows per CTA tile (empty rows)
 
 struct b2k_op {
-    int32_t kind = 0;             // 0 = CSR, 1 = dense
+    int32_t kind = 0;             // 0 = CSR, 1 = dense, 2 = matrix-free stencil
+    // matrix-free stencil (kind 2): grid and coefficients; rows [row0, row0 + n_rows) of the global grid
+    int64_t  snx = 0, sny = 0, snz = 0, srow0 = 0;
+    double   sc[7] = {0, 0, 0, 0, 0, 0, 0};
     int64_t n_rows = 0, n_cols = 0, nnz = 0;
     // CSR (device)
     int32_t* rowptr = nullptr;
@@ -535,6 +538,97 @@ k_spmm_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8 * s);
         if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+    }
+}
+
+// Matrix-free stencil apply: y = A x for the 5-/7-point Dirichlet stencil WITHOUT a stored matrix —
+// 16 n bytes per apply instead of 12 nnz + 20 n (160 MB instead of 800 MB at n = 1e7).  One thread per row; the
+// neighbours x[i ± 1], x[i ± nx], x[i ± nx ny] are L1/L2 hits (each row of the grid is read by three consecutive
+// thread rows).  Products are rounded before they are added, in ascending column order — the CSR kernels' order — so
+// the result is bit-identical to the assembled operator of b2k_op_create_stencil.  Carries the same fusions as
+// k_spmv_pipe (shift, dot epilogue, normalise-on-load + vout, MGS-order dot, skip flag, peer window).
+struct StencilApply {
+    int64_t nx, ny, nz, row0;       // global grid, first global row of this shard
+    int64_t n_rows;                 // local rows
+    int64_t n_loc;                  // local x entries (== n_rows); beyond: halo [lo | hi]
+    int64_t halo_lo;                // entries of the lo halo (plane below the shard)
+    double c[7];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_stencil_apply(const __grid_constant__ StencilApply sa, const T* __restrict__ x, const T* __restrict__ halo,
+                T* __restrict__ y, T a0, T a1, int shifted, const T* __restrict__ dotv, double* __restrict__ part,
+                unsigned* __restrict__ ticket, double* __restrict__ out, const SpmvFuse fz,
+                const __grid_constant__ PeerStep ps) {
+    __shared__ double red[32];
+    __shared__ bool last;
+    if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
+    if (ps.on && ps.seq_halo) {
+        if (threadIdx.x == 0) {
+            if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
+            if (ps.wait_hi) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1)) < ps.seq_halo) {}
+        }
+        __syncthreads();
+    }
+    const bool scaled = fz.xscale != nullptr;
+    const T sc = scaled ? (T)(*fz.xscale) : (T)1;
+    T* const vout = reinterpret_cast<T*>(fz.vout);
+    const bool want_dot = (dotv != nullptr) || fz.dot_self;
+    const T* const dsub = reinterpret_cast<const T*>(fz.dot_sub_vec);
+    const T dsc = dsub ? (T)(*fz.dot_sub_scale) : (T)0;
+    const int64_t plane = sa.nx * sa.ny;
+    const T c0 = (T)sa.c[0], cw = (T)sa.c[1], ce = (T)sa.c[2], cs = (T)sa.c[3], cn = (T)sa.c[4], cd = (T)sa.c[5],
+            cu = (T)sa.c[6];
+    // x at local index l (may be below 0 / beyond n_loc: halo), already normalised
+    auto X = [&](int64_t l) -> T {
+        T v;
+        if (l >= 0 && l < sa.n_loc) v = __ldg(x + l);
+        else if (l < 0) v = __ldg(halo + (sa.halo_lo + l));
+        else v = __ldg(halo + sa.halo_lo + (l - sa.n_loc));
+        return scaled ? v * sc : v;
+    };
+    T dacc = (T)0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < sa.n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = sa.row0 + i;
+        const int64_t ix = g % sa.nx, iy = (g / sa.nx) % sa.ny, iz = g / plane;
+        T sum = (T)0;
+        if (sa.nz > 1 && iz > 0) sum = add_rn<T>(sum, mul_rn<T>(cd, X(i - plane)));
+        if (iy > 0) sum = add_rn<T>(sum, mul_rn<T>(cs, X(i - sa.nx)));
+        if (ix > 0) sum = add_rn<T>(sum, mul_rn<T>(cw, X(i - 1)));
+        const T xi = X(i);
+        sum = add_rn<T>(sum, mul_rn<T>(c0, xi));
+        if (ix < sa.nx - 1) sum = add_rn<T>(sum, mul_rn<T>(ce, X(i + 1)));
+        if (iy < sa.ny - 1) sum = add_rn<T>(sum, mul_rn<T>(cn, X(i + sa.nx)));
+        if (sa.nz > 1 && iz < sa.nz - 1) sum = add_rn<T>(sum, mul_rn<T>(cu, X(i + plane)));
+        if (shifted) sum = fma(a0, __ldg(x + i), a1 * sum);
+        y[i] = sum;
+        if (vout) vout[i] = xi;
+        if (want_dot) {
+            const T dv = fz.dot_self ? xi : __ldg(dotv + i);
+            dacc = fma(dv, dsub ? fma(-dsc, __ldg(dsub + i), sum) : sum, dacc);
+        }
+    }
+    if (want_dot) {
+        const double sblk = block_sum((double)dacc, red);
+        if (threadIdx.x == 0) {
+            part[blockIdx.x] = sblk;
+            __threadfence();
+            const unsigned t = atomicInc(ticket, gridDim.x - 1);
+            last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            double v2 = 0.0;
+            const volatile double* pv = part;
+            for (int gidx = threadIdx.x; gidx < (int)gridDim.x; gidx += blockDim.x) v2 += pv[gidx];
+            const double tot = block_sum(v2, red);
+            if (threadIdx.x == 0) {
+                *out = tot;
+                if (ps.on && ps.seq_alpha) peer_publish1(ps.pd, PEER_CH_ALPHA, ps.seq_alpha, tot);
+            }
+        }
     }
 }
 
@@ -1073,6 +1167,58 @@ extern "C" int32_t b2k_op_create_stencil(b2k_ctx* ctx, b2k_op** out, int64_t nx,
     return B2K_OK;
 }
 
+// Matrix-free form of b2k_op_create_stencil: nothing is assembled, `apply` evaluates the stencil (k_stencil_apply).
+// Row-sharded contexts shard by whole grid lines (2-D) / planes (3-D); the halo is one line / plane per neighbour.
+extern "C" int32_t b2k_op_create_stencil_free(b2k_ctx* ctx, b2k_op** out, int64_t nx, int64_t ny, int64_t nz,
+                                              const double c[7]) {
+    if (!ctx || !out || !c || nx < 1 || ny < 1 || nz < 1) return B2K_EINVAL;
+    const int64_t nglob = nx * ny * nz;
+    const int64_t n_loc = ctx->spaces[0].n;
+    if (ctx->nranks == 1 && nglob != n_loc)
+        return b2k_fail(ctx, B2K_EDIM, "stencil: grid has %lld points, space 0 holds %lld", (long long)nglob, (long long)n_loc);
+    if (ctx->nranks > 1 && nglob != ctx->n_global)
+        return b2k_fail(ctx, B2K_EDIM, "stencil: grid has %lld points, n_global is %lld", (long long)nglob,
+                        (long long)ctx->n_global);
+    const int64_t unit = nz > 1 ? nx * ny : nx;           // one plane / one line
+    if (ctx->nranks > 1 && (ctx->row_offset % unit != 0 || n_loc % unit != 0 || n_loc < unit))
+        return b2k_fail(ctx, B2K_ENOTSUP, "matrix-free stencil: shards must be whole grid %s", nz > 1 ? "planes" : "lines");
+    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
+    b2k_op* op = new b2k_op();
+    op->kind = 2;
+    op->n_rows = n_loc;
+    op->n_cols = nglob;
+    op->nnz = 0;
+    op->snx = nx; op->sny = ny; op->snz = nz; op->srow0 = ctx->row_offset;
+    for (int i = 0; i < 7; ++i) op->sc[i] = c[i];
+    op->n_loc_cols = n_loc;
+    op->nblk = 0;
+    int32_t rc = B2K_OK;
+    if (ctx->nranks > 1) {
+        // same halo plan as a CSR operator with this column range: one unit below, one above
+        op->halo_lo = ctx->rank > 0 ? unit : 0;
+        op->halo_hi = ctx->rank + 1 < ctx->nranks ? unit : 0;
+        op->send_lo = op->halo_lo;      // symmetric: what I need from rank-1 is what it needs from me
+        op->send_hi = op->halo_hi;
+        op->dn_lo = ctx->rank > 1 ? unit : 0;             // rank-1's own lo halo (0 if rank-1 is rank 0)
+        const size_t region = (((size_t)2 * unit * ctx->esize) + 255) & ~(size_t)255;
+        if (b2k_peer_ok(ctx)) {
+            const size_t off = b2k_peer_heap_alloc(ctx, 2 * region);
+            if (off != SIZE_MAX) { op->peer_halo = 1; op->halo_off = off; op->halo_region = region; }
+        }
+        if (!op->peer_halo) {
+            if (!b2k_has_nccl(ctx)) rc = b2k_fail(ctx, B2K_ENOTSUP, "stencil halo does not fit the peer window and NCCL is disabled");
+            else if (B2K_DMALLOC(&op->halo, (size_t)(op->halo_lo + op->halo_hi) * ctx->esize) != cudaSuccess)
+                rc = b2k_fail(ctx, B2K_ENOMEM, "stencil: halo allocation failed");
+        }
+    }
+    if (rc == B2K_OK && B2K_DMALLOC(&op->part, sizeof(double) * 4096) != cudaSuccess)
+        rc = b2k_fail(ctx, B2K_ENOMEM, "stencil: partial buffer allocation failed");
+    if (rc != B2K_OK) { b2k_op_release(ctx, op); return rc; }
+    ctx->ops.push_back(op);
+    *out = op;
+    return B2K_OK;
+}
+
 static int32_t alloc_dense(b2k_ctx* ctx, b2k_op** out, int64_t m_local, int64_t n) {
     if (m_local < 1 || n < 1) return b2k_fail(ctx, B2K_EINVAL, "dense: bad shape");
     if (m_local != ctx->spaces[0].n)
@@ -1159,7 +1305,8 @@ extern "C" int32_t b2k_op_info(const b2k_op* op, int64_t* n_rows, int64_t* n_col
 
 extern "C" int32_t b2k_op_csr_download(b2k_ctx* ctx, const b2k_op* op, int32_t* rowptr,
                                        int32_t* colidx, void* vals) {
-    if (!ctx || !op || op->kind != 0) return B2K_EINVAL;
+    if (!ctx || !op) return B2K_EINVAL;
+    if (op->kind != 0) return b2k_fail(ctx, B2K_ENOTSUP, "op_csr_download: not an assembled CSR operator");
     B2K_CUDA(ctx, cudaSetDevice(ctx->device));
     if (rowptr)
         B2K_CUDA(ctx, cudaMemcpyAsync(rowptr, op->rowptr, sizeof(int32_t) * (op->n_rows + 1),
@@ -1232,7 +1379,7 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
     SpmvFuse fz;
     memset(&fz, 0, sizeof(fz));
     if (fzp) fz = *fzp;
-    if (fzp && op->kind != 0) return b2k_fail(ctx, B2K_ENOTSUP, "fused apply: CSR operators only");
+    if (fzp && op->kind == 1) return b2k_fail(ctx, B2K_ENOTSUP, "fused apply: CSR / stencil operators only");
     if ((fz.vout || fz.dot_self) && (op->n_rows != x.n))
         return b2k_fail(ctx, B2K_EDIM, "fused apply: needs a square operator (row r <-> x[r])");
     if (fz.dot_self && !dot_out) return b2k_fail(ctx, B2K_EINVAL, "fused apply: dot_self without an output slot");
@@ -1310,6 +1457,26 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
         n_loc = 0x7fffffff;
     }
     double* out = (dotv || fz.dot_self) ? dot_out : nullptr;
+    if (op->kind == 2) {
+        StencilApply sa;
+        sa.nx = op->snx; sa.ny = op->sny; sa.nz = op->snz; sa.row0 = op->srow0;
+        sa.n_rows = op->n_rows; sa.n_loc = x.n; sa.halo_lo = op->halo_lo;
+        for (int i = 0; i < 7; ++i) sa.c[i] = op->sc[i];
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((op->n_rows + 255) / 256, (int64_t)ctx->num_sms * 8));
+        const int pr2 = b2k_prof_begin(ctx, 0, 2.0 * ctx->esize * op->n_rows);
+        if (ctx->dtype == B2K_F64)
+            k_stencil_apply<double><<<grid, 256, 0, ctx->stream>>>(sa, (const double*)xsrc, (const double*)halo, (double*)y.ptr,
+                                                                   a0, a1, shifted ? 1 : 0, dotv ? (const double*)dotv->ptr : nullptr,
+                                                                   op->part, ctx->d_sync, out, fz, ps);
+        else
+            k_stencil_apply<float><<<grid, 256, 0, ctx->stream>>>(sa, (const float*)xsrc, (const float*)halo, (float*)y.ptr,
+                                                                  (float)a0, (float)a1, shifted ? 1 : 0,
+                                                                  dotv ? (const float*)dotv->ptr : nullptr, op->part,
+                                                                  ctx->d_sync, out, fz, ps);
+        b2k_prof_end(ctx, pr2);
+        B2K_LAUNCH_CHECK(ctx);
+        return B2K_OK;
+    }
     const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
                                               2.0 * ctx->esize * op->n_rows);
     if (g_spmv_pipe) {
@@ -1408,7 +1575,7 @@ extern "C" int32_t b2k_op_apply_block(b2k_ctx* ctx, const b2k_op* op, const b2k_
     for (int i = 0; i < p; ++i)
         for (int j = 0; j < p; ++j)
             if (X[i] == Y[j]) return b2k_fail(ctx, B2K_EINVAL, "apply_block: Y[%d] aliases X[%d]", j, i);
-    bool fast = op->kind == 0 && ctx->nranks == 1 && g_spmv_pipe && p > 1;
+    bool fast = op->kind == 0 && ctx->nranks == 1 && g_spmv_pipe && p > 1;     // (stencil: the loop of applies)
     int32_t sx = -1, sy = -1;
     std::vector<int32_t> ix, iy;
     B2K_TRY(b2k_resolve_cols(ctx, X, p, &sx, &ix));

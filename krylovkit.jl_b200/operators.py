@@ -115,6 +115,18 @@ class B200CSR(B200Operator):
         ctx.check(ctx.lib.b2k_op_create_stencil(ctx.h, C.byref(h), nx, ny, nz, c))
         return cls(ctx, h)
 
+    @classmethod
+    def stencil_free(cls, ctx: B200Context, nx: int, ny: int, nz: int = 1,
+                     coeffs=(4.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0)) -> "B200CSR":
+        """The same Dirichlet stencil, MATRIX-FREE: nothing is stored, every apply evaluates the stencil from the
+        vector (16 n bytes per apply instead of 12 nnz + 20 n) with the assembled operator's rounding — results are
+        bit-identical to `stencil(...)`.  KrylovKit takes any function as its linear map; this is the device form of
+        such a function for the grids of the BASELINE configs.  (`to_scipy` is not available.)"""
+        c = (C.c_double * 7)(*[float(v) for v in coeffs])
+        h = L.c_op()
+        ctx.check(ctx.lib.b2k_op_create_stencil_free(ctx.h, C.byref(h), nx, ny, nz, c))
+        return cls(ctx, h)
+
     def to_scipy(self):
         import scipy.sparse as sp
         rp = np.empty(self.n_rows + 1, dtype=np.int32)

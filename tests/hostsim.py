@@ -662,6 +662,9 @@ class HostSimLib:
             self._setvec(ctx, c, acc)
         return L.OK
 
+    def b2k_op_create_stencil_free(self, h, out, nx, ny, nz, c):
+        return self.b2k_op_create_stencil(h, out, nx, ny, nz, c)
+
     def b2k_op_apply_block(self, h, op, X, Y, p):
         for x, y in zip(list(X)[:p], list(Y)[:p]):
             st = self.b2k_op_apply(h, op, x, y)

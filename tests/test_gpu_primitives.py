@@ -417,3 +417,37 @@ def test_block_multi_rhs_kernels():
         assert np.array_equal(d.to_host(), b)
     ctx.close()
     ctx2.close()
+
+
+@pytest.mark.parametrize("grid,coeffs", [((97, 61, 1), (4.0, -1.0, -1.0, -1.0, -1.0, 0.0, 0.0)),
+                                          ((64, 50, 1), (4.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0)),
+                                          ((23, 17, 13), (6.0, -1.0, -1.1, -0.9, -1.0, -1.2, -0.8))])
+def test_matrix_free_stencil_equals_assembled_operator(grid, coeffs):
+    """b2k_op_create_stencil_free evaluates the stencil from the vector (no stored matrix): apply, shifted apply and
+    the fused dot are bit-identical to the assembled CSR operator; the device-chained Lanczos steps run on it too."""
+    from krylovkit_jl_b200.factorizations import lanczos as lz
+    nx, ny, nz = grid
+    n = nx * ny * nz
+    rng = np.random.default_rng(8)
+    ctx = kk.B200Context(n, 48)
+    A = kk.B200CSR.stencil(ctx, nx, ny, nz, coeffs)
+    F = kk.B200CSR.stencil_free(ctx, nx, ny, nz, coeffs)
+    assert F.n_rows == n               # (the real library reports nnz == 0: nothing is stored)
+    x = ctx.from_host(rng.standard_normal(n))
+    v = ctx.from_host(rng.standard_normal(n))
+    assert np.array_equal(kk.apply(F, x).to_host(), kk.apply(A, x).to_host())
+    assert np.array_equal(kk.apply(F, x, 0.3, 1.7).to_host(), kk.apply(A, x, 0.3, 1.7).to_host())
+    ya, yf = ctx.empty(), ctx.empty()
+    da, df = A.apply_dot_into(ya, x, v), F.apply_dot_into(yf, x, v)
+    assert np.array_equal(ya.to_host(), yf.to_host())
+    assert abs(da - df) <= 1e-13 * abs(da)            # same products, other partition of the final sum
+    res = []
+    for op in (A, F):
+        it = lz.LanczosIterator(op, ctx.from_host(ko.splitmix_vector(3, n)), kk.cgs2)
+        f = lz.initialize(it)
+        lz.expand_many_(it, f, 20, 0.0)
+        res.append((np.array(f.alphas), np.array(f.betas)))
+        del f, it
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-13)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-12)
+    ctx.close()

@@ -237,6 +237,11 @@ def test_fused_branches_bookkeeping(simf):
     G.test_invariant_subspace_early_exit()
 
 
+def test_matrix_free_stencil(simf):
+    import test_gpu_primitives as P
+    P.test_matrix_free_stencil_equals_assembled_operator((23, 17, 13), (6.0, -1.0, -1.1, -0.9, -1.0, -1.2, -0.8))
+
+
 def test_cg_chain_bookkeeping(simf):
     G.test_cg_chained_iterations_equal_stepwise()
 

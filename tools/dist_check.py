@@ -67,6 +67,9 @@ def main():
                                      Aloc.indices.astype(np.int64), Aloc.data)
     y2 = kk.apply(op2, xd)
     assert np.array_equal(y2.to_host(), y.to_host())
+    # 2b. the matrix-free stencil operator: the same bits as the assembled one (halo = one grid line per neighbour)
+    opf = kk.B200CSR.stencil_free(ctx, nx, ny)
+    assert np.array_equal(kk.apply(opf, xd).to_host(), y.to_host())
     # 3. global reductions
     assert abs(xd.inner(y) - x0 @ ref) < 1e-9 * abs(x0 @ ref)
     assert abs(xd.norm() - np.linalg.norm(x0)) < 1e-12 * np.linalg.norm(x0)
