@@ -74,7 +74,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=30, help="expand! steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra", default="c3,c4,c5",
+    ap.add_argument("--extra", default="c2f,c3,c4,c5",
                     help="other BASELINE.json configs measured after the headline (records under 'other_configs'); "
                          "'' = none")
     return ap.parse_args()
@@ -576,6 +576,22 @@ def other_configs(kk, a, rank, world, local_rank, dist):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t = float(tt.item())
         return res, t
+
+    if "c2f" in want:
+        # the headline job with the MATRIX-FREE stencil operator (KrylovKit takes any function as its linear map):
+        # same arithmetic, same Ritz values, 16n instead of 12 nnz + 20n bytes per operator application
+        ctx, n = make_ctx(a.ny, a.nx, a.krylovdim + 2 * HOWMANY + 8)
+        op = kk.B200CSR.stencil_free(ctx, a.nx, a.ny)
+        x0 = ctx.splitmix(SEED)
+        orth = {"cgs2": kk.cgs2, "mgs2": kk.mgs2, "cgs": kk.cgs, "mgs": kk.mgs, "mgs2b": kk.mgs2b}[a.orth]
+        alg = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=a.cycles, tol=0.0, verbosity=0)
+        (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, HOWMANY, "SR", alg))
+        del vecs
+        out["c2_matrix_free"] = {
+            "workload": workload_config(a)["workload"].replace("CSR 5-point", "matrix-free 5-point"),
+            "numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
+            "ritz": [float(v) for v in vals[:HOWMANY]], "parity": check_parity(a, vals, info.numops, "matrix-free operator")}
+        ctx.close()
 
     if "c3" in want:
         nx, ny, kd = 4000, 2500, 40
