@@ -141,6 +141,7 @@ _PROTOS = {
     "b2k_debug_set_dmma": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_chain": (C.c_int32, [C.c_int32]),
     "b2k_debug_used_columns": (C.c_int32, [c_ctx, C.c_int32]),
+    "b2k_debug_set_chain_mode": (C.c_int32, [C.c_int32]),
 }
 
 EXPORTED = tuple(k for k in _PROTOS if not k.startswith("b2k_debug"))

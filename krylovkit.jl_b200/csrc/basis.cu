@@ -64,8 +64,21 @@ __device__ __forceinline__ void peer_boundary(const FusedParams<T>& fp, int i, u
     }
     __syncthreads();
     const PeerDev& pd = fp.ps.pd;
-    const unsigned long long seq = fp.ps.seq_coef[i];
     const int tid = threadIdx.x;
+    if (fp.ph[i].part_h == nullptr) {
+        // boundary in front of a scale phase: the quantity to sum over the ranks is ||w||^2 (channel 2)
+        const unsigned long long sq = fp.ps.seq_norm;
+        if (*flag && tid < 32) {
+            __threadfence();
+            double a = (tid < 16) ? partial_lane_sum(fp.ph[i].part_n, gridDim.x, 1, tid, 16) : 0.0;
+            for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (tid == 0) peer_publish1(pd, PEER_CH_NORM, sq, a);
+        }
+        peer_wait(pd, PEER_CH_NORM, sq, tid);
+        __syncthreads();
+        return;
+    }
+    const unsigned long long seq = fp.ps.seq_coef[i];
     if (*flag && tid < NCONS) {
         __threadfence();
         const int k = fp.ph[i].k;
@@ -145,7 +158,7 @@ k_finalize(const double* __restrict__ A, const double* __restrict__ B, const dou
     FinalizeParams f;
     f.A = A; f.B = B; f.N = N; f.G = G; f.stride = stride; f.k = k; f.res = res; f.off = off; f.noff = noff;
     f.rec = nullptr; f.alpha_col = -1; f.tol = 0.0; f.stop = nullptr; f.ticket = nullptr; f.enabled = 1;
-    f.peer = 0; f.G_local = G;
+    f.peer = 0; f.G_local = G; f.norm_done = 0;
     finalize_block(f, threadIdx.x, sh);
 }
 
@@ -564,6 +577,13 @@ int32_t enqueue_finalize(b2k_ctx* ctx, const double* A, const double* B, const d
 }
 
 bool g_l2_hints = true;      // B2K_L2_HINTS=0 switches the eviction-priority hints off (A/B measurements)
+// How a chained step gets its normalised vector v = r/beta:
+//   1 (default): a third "scale" phase of the Gram-Schmidt launch normalises w in place while its tiles are hot in
+//      L2; the SpMV is the plain one and finds its operand warm — the layout of the reference (lanczos.jl:257: the
+//      residual's storage becomes the basis vector);
+//   0: normalisation fused into the SpMV's gather, v written to a column of its own (r's column is recycled).
+// B2K_CHAIN_MODE selects; both are bit-identical to stepping.
+int g_chain_mode = 1;
 
 struct Panel {
     void* base;      // space base pointer
@@ -794,6 +814,7 @@ int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res
 // called once per context (ctx.cu): opt in to > 48 KB dynamic shared memory
 int32_t b2k_basis_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_L2_HINTS")) g_l2_hints = e[0] != '0';
+    if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '0' ? 0 : 1;
 #define SETATTR(fn, bytes) \
     B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
     SETATTR((k_phase<double, false, true>), SMEM_BYTES);
@@ -1253,7 +1274,8 @@ bool chain_ok(const b2k_ctx* ctx, const b2k_op* op, const b2k_vec* cols, int32_t
 
 template <typename T>
 int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, const VecRef& vprev,
-                      const VecRef& rv, double* rec_prev, double* rec, double tol, const PeerStep* psp) {
+                      const VecRef& rv, double* rec_prev, double* rec, double tol, const PeerStep* psp,
+                      bool scale_after) {
     const int grid = grid_for_rows<T>(ctx, pn.n);
     ColList cl;
     for (int i = 0; i < K1; ++i) cl.c[i] = pn.idx[i];
@@ -1270,13 +1292,20 @@ int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, c
     c.store_x = 1; c.coef = PA; c.coef_sets = grid; c.coef_stride = B2K_KSTRIDE;
     c.alphac = (T)-1; c.part_n = PN;
     fp.ph[0] = a; fp.kind[0] = 0; fp.ph[1] = c; fp.kind[1] = 2; fp.nph = 2;
+    if (scale_after) {
+        // third phase: w <- w / beta in place while its tiles are hot in L2 — the next step's v (lanczos.jl:257)
+        PhaseParams<T> sc = base_params<T>(pn, 0, rw.ptr, rw.ptr);
+        sc.store_x = 1; sc.beta_mode = 2; sc.scale_mode = 1;
+        sc.scale_norm = PN; sc.scale_G = grid; sc.scale_stride = 1; sc.scale_tol = tol;
+        fp.ph[2] = sc; fp.kind[2] = 2; fp.nph = 3;
+    }
     fp.stop = reinterpret_cast<const int*>(ctx->d_sync + B2K_SYNC_STOP);
     fp.fin.A = PA; fp.fin.B = nullptr; fp.fin.N = PN; fp.fin.G = grid; fp.fin.stride = B2K_KSTRIDE;
     fp.fin.k = K1; fp.fin.res = nullptr; fp.fin.off = 0; fp.fin.noff = 0; fp.fin.rec = rec;
     fp.fin.alpha_col = K1 - 1; fp.fin.tol = tol;
     fp.fin.stop = reinterpret_cast<int*>(ctx->d_sync + B2K_SYNC_STOP);
     fp.fin.ticket = ctx->d_sync + B2K_SYNC_GSFIN; fp.fin.enabled = 1;
-    fp.fin.peer = 0; fp.fin.G_local = grid;
+    fp.fin.peer = 0; fp.fin.G_local = grid; fp.fin.norm_done = 0;
     if (psp && psp->on) {
         const PeerStep& ps = *psp;
         fp.ps = ps;
@@ -1293,12 +1322,19 @@ int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, c
         fp.ph[1].coef_sets = ps.pd.nranks;
         fp.ph[1].coef_stride = PEER_SLOT;
         fp.fin.A = fp.ph[1].coef; fp.fin.G = ps.pd.nranks; fp.fin.stride = PEER_SLOT; fp.fin.peer = 1;
+        const int last = fp.nph - 1;      // the phase that stores the vector the next SpMV reads
+        if (scale_after) {
+            fp.ph[2].scale_norm = slot(PEER_CH_NORM, ps.seq_norm);
+            fp.ph[2].scale_G = ps.pd.nranks;
+            fp.ph[2].scale_stride = PEER_SLOT;
+            fp.fin.norm_done = 1;         // exchanged at the boundary in front of the scale phase
+        }
         // rows the neighbours need for their next SpMV leave with the final store
         if (ps.seq_halo) {
-            fp.ph[1].send_lo = ps.send_lo;
-            fp.ph[1].send_hi = ps.send_hi;
-            fp.ph[1].halo_dn = ps.send_lo ? reinterpret_cast<T*>(ps.pd.win[ps.pd.rank - 1] + ps.dn_off) : nullptr;
-            fp.ph[1].halo_up = ps.send_hi ? reinterpret_cast<T*>(ps.pd.win[ps.pd.rank + 1] + ps.up_off) : nullptr;
+            fp.ph[last].send_lo = ps.send_lo;
+            fp.ph[last].send_hi = ps.send_hi;
+            fp.ph[last].halo_dn = ps.send_lo ? reinterpret_cast<T*>(ps.pd.win[ps.pd.rank - 1] + ps.dn_off) : nullptr;
+            fp.ph[last].halo_up = ps.send_hi ? reinterpret_cast<T*>(ps.pd.win[ps.pd.rank + 1] + ps.up_off) : nullptr;
         }
     }
     const int pr = b2k_prof_begin(ctx, 1, (2.0 * K1 + 3.0) * sizeof(T) * (double)pn.n);
@@ -1320,20 +1356,24 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
     }
     k_lanczos_seed<<<1, 1, 0, ctx->stream>>>(rec0, beta_old, d_stop);
     B2K_LAUNCH_CHECK(ctx);
+    const bool inplace = g_chain_mode == 1;
     std::vector<b2k_vec> touched, Vh, Wh;
     touched.push_back(cols[k]);
     int32_t enq = 0, rc = B2K_OK;
     const bool dist = ctx->nranks > 1;
     unsigned long long halo_seq = 0;
+    if (inplace) B2K_TRY(b2k_vec_scale(ctx, cols[k], cols[k], 1.0 / beta_old));   // v = r/beta of the first step
     for (int32_t i = 0; i < nsteps; ++i) {
         const int32_t K = k + i;                 // basis size before this step's push!
         const b2k_vec R = cols[K];
-        b2k_vec V = -1, W = -1;
-        rc = b2k_vec_alloc(ctx, space, &V);
-        if (rc != B2K_OK) break;
+        b2k_vec V = R, W = -1;
+        if (!inplace) {
+            rc = b2k_vec_alloc(ctx, space, &V);
+            if (rc != B2K_OK) break;
+            touched.push_back(V);
+        }
         rc = b2k_vec_alloc(ctx, space, &W);
-        if (rc != B2K_OK) { b2k_vec_free(ctx, V); break; }
-        touched.push_back(V);
+        if (rc != B2K_OK) break;
         touched.push_back(W);
         VecRef rR, rV, rW, vprev;
         rc = b2k_resolve(ctx, R, &rR);
@@ -1343,10 +1383,13 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
         if (rc != B2K_OK) break;
         double* rec_prev = rec0 + (size_t)B2K_REC * i;
         double* rec = rec0 + (size_t)B2K_REC * (i + 1);
+        const bool scale_after = inplace && (i + 1 < nsteps);   // the batch's last residual stays unnormalised
         SpmvFuse fz;
         memset(&fz, 0, sizeof(fz));
-        fz.xscale = rec_prev + 3;
-        fz.vout = rV.ptr;
+        if (!inplace) {
+            fz.xscale = rec_prev + 3;
+            fz.vout = rV.ptr;
+        }
         fz.stop = d_stop;
         fz.dot_self = 1;
         fz.l2_hints = g_l2_hints ? 1 : 0;
@@ -1363,10 +1406,13 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
             ps.seq_coef[0] = b2k_peer_next_seq(ctx, PEER_CH_COEF);
             ps.seq_norm = b2k_peer_next_seq(ctx, PEER_CH_NORM);
             fz.seq_alpha = ps.seq_alpha;
-            fz.seq_halo = halo_seq;                    // 0 on the first step: the apply pushes r's boundary rows
-            halo_seq = b2k_peer_next_seq(ctx, 4);      // this step's Gram-Schmidt launch pushes w's
-            rc = b2k_op_peer_halo(ctx, op, halo_seq, &ps);
-            if (rc != B2K_OK) break;
+            fz.seq_halo = halo_seq;                    // 0: the apply pushes its operand's boundary rows itself
+            halo_seq = 0;
+            if (!inplace || scale_after) {             // this step's Gram-Schmidt launch pushes the next operand's
+                halo_seq = b2k_peer_next_seq(ctx, 4);
+                rc = b2k_op_peer_halo(ctx, op, halo_seq, &ps);
+                if (rc != B2K_OK) break;
+            }
         }
         rc = b2k_enqueue_apply_fused(ctx, op, rR, rW, 0.0, 1.0, false, nullptr, rec + 0, &fz);
         if (rc != B2K_OK) break;
@@ -1374,14 +1420,14 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
         Panel pn;
         rc = make_panel(ctx, cols, K + 1, &pn);
         if (rc != B2K_OK) break;
-        rc = f64 ? chain_step_gs<double>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol, &ps)
-                 : chain_step_gs<float>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol, &ps);
+        rc = f64 ? chain_step_gs<double>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol, &ps, scale_after)
+                 : chain_step_gs<float>(ctx, pn, K + 1, rW, vprev, rV, rec_prev, rec, tol, &ps, scale_after);
         if (rc != B2K_OK) break;
         cols[K + 1] = W;                         // ... and w the new residual
         Vh.push_back(V);
         Wh.push_back(W);
-        // r's column has been consumed; later steps may reuse it (stream order keeps that safe)
-        ctx->spaces[space].used[B2K_VEC_COL(R)] = 0;
+        // mode 0: r's column has been consumed; later steps may reuse it (stream order keeps that safe)
+        if (!inplace) ctx->spaces[space].used[B2K_VEC_COL(R)] = 0;
         ++enq;
     }
     int32_t d = 0;
@@ -1411,6 +1457,11 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
     } else {
         sp.used[B2K_VEC_COL(touched[0])] = 1;    // nothing ran: r is still r
         cols[k] = touched[0];
+        if (inplace) {
+            // the residual was normalised for a first step that could not be enqueued: undo (an error path —
+            // slab exhausted — where the caller gets its r back to rounding)
+            b2k_vec_scale(ctx, cols[k], cols[k], beta_old);
+        }
     }
     *steps_done = d;
     *r_out = cols[k + d];
@@ -1419,6 +1470,11 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
 
 extern "C" int32_t b2k_debug_set_chain(int32_t on) {
     g_use_chain = on != 0;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_debug_set_chain_mode(int32_t mode) {
+    g_chain_mode = mode == 0 ? 0 : 1;
     return B2K_OK;
 }
 
