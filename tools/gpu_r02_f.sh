@@ -13,12 +13,14 @@ except Exception as e:
     print('$name failed', e); print(open('gpurun_out/r02f_$name.err').read()[-1500:])
 PY
 }
-run hints1_var0 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=0
-run hints0_var0 B2K_L2_HINTS=0 B2K_SPMV_VARIANT=0
-run hints1_var1 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=1
-run hints0_var1 B2K_L2_HINTS=0 B2K_SPMV_VARIANT=1
-run hints1_var0_again B2K_L2_HINTS=1 B2K_SPMV_VARIANT=0
+run m1_h1_v0 B2K_CHAIN_MODE=1 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=0
+run m1_h0_v0 B2K_CHAIN_MODE=1 B2K_L2_HINTS=0 B2K_SPMV_VARIANT=0
+run m0_h1_v0 B2K_CHAIN_MODE=0 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=0
+run m0_h0_v0 B2K_CHAIN_MODE=0 B2K_L2_HINTS=0 B2K_SPMV_VARIANT=0
+run m1_h1_v1 B2K_CHAIN_MODE=1 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=1
+run m0_h1_v1 B2K_CHAIN_MODE=0 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=1
+run m1_h1_v0_again B2K_CHAIN_MODE=1 B2K_L2_HINTS=1 B2K_SPMV_VARIANT=0
 timeout 200 python tools/microbench.py --reps 10 > gpurun_out/r02f_microbench.log 2>&1
 cut -c1-160 gpurun_out/r02f_microbench.log
-timeout 300 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_solvers.py -q --timeout 200 -k "block or chained or cg_chained or blocklanczos" > gpurun_out/r02f_pytest.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_solvers.py -q --timeout 200 -k "block or chained or cg_chained or blocklanczos or matrix_free" > gpurun_out/r02f_pytest.log 2>&1
 grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/r02f_pytest.log | tail
