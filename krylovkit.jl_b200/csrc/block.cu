@@ -16,6 +16,7 @@
 #include "tsk.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 using namespace tsk;
@@ -363,7 +364,13 @@ int32_t fetch(b2k_ctx* ctx, const double* d, double* h, int count) {
 
 }  // namespace
 
+// B2K_BLOCK_KERNELS=0 routes block_inner / block_axpy / apply_block through loops of the single-vector entry points
+// (the round-1 behaviour) — an escape hatch and the A/B baseline for the multi-right-hand-side kernels.
+static bool g_block_kernels = true;
+bool b2k_block_kernels_enabled() { return g_block_kernels; }
+
 int32_t b2k_block_init(b2k_ctx* ctx) {
+    if (const char* e = getenv("B2K_BLOCK_KERNELS")) g_block_kernels = e[0] != '0';
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -377,6 +384,10 @@ int32_t b2k_block_init(b2k_ctx* ctx) {
 extern "C" int32_t b2k_block_inner(b2k_ctx* ctx, const b2k_vec* X, int32_t p, const b2k_vec* Y,
                                    int32_t q, double* M_host) {
     if (!ctx || !X || !Y || !M_host || p < 1 || q < 1) return B2K_EINVAL;
+    if (!g_block_kernels) {
+        for (int j = 0; j < q; ++j) B2K_TRY(b2k_basis_project(ctx, X, p, Y[j], 1.0, 0.0, M_host + (size_t)j * p));
+        return B2K_OK;
+    }
     if (p * BK_PMAX > HCAP || (int64_t)p * q > B2K_RES_DOUBLES) return b2k_fail(ctx, B2K_ENOTSUP, "block_inner: p*q too large");
     for (int j0 = 0; j0 < q; j0 += BK_PMAX) {           // blocks of up to 8 right-hand sides
         const int qq = std::min(BK_PMAX, q - j0);
@@ -392,6 +403,11 @@ extern "C" int32_t b2k_block_inner(b2k_ctx* ctx, const b2k_vec* X, int32_t p, co
 extern "C" int32_t b2k_block_axpy(b2k_ctx* ctx, const b2k_vec* Y, int32_t q, const b2k_vec* X,
                                   int32_t p, const double* M_host, int32_t ldm) {
     if (!ctx || !X || !Y || !M_host || p < 1 || q < 1 || ldm < p) return B2K_EINVAL;
+    if (!g_block_kernels) {
+        for (int j = 0; j < q; ++j)
+            B2K_TRY(b2k_basis_unproject(ctx, Y[j], X, p, M_host + (size_t)j * ldm, -1.0, 1.0));
+        return B2K_OK;
+    }
     if (p * BK_PMAX > HCAP) return b2k_fail(ctx, B2K_ENOTSUP, "block_axpy: p too large");
     for (int i = 0; i < p; ++i)
         for (int j = 0; j < q; ++j)

@@ -198,6 +198,7 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
 int32_t b2k_basis_init(b2k_ctx* ctx);
 int32_t b2k_spmv_init(b2k_ctx* ctx);
 int32_t b2k_block_init(b2k_ctx* ctx);
+bool    b2k_block_kernels_enabled();
 constexpr int B2K_BLK_HCAP = 3968;        // doubles per coefficient block (k * p <= HCAP)
 constexpr int B2K_BLK_PART = 384;         // doubles per CTA partial row
 

@@ -1575,7 +1575,8 @@ extern "C" int32_t b2k_op_apply_block(b2k_ctx* ctx, const b2k_op* op, const b2k_
     for (int i = 0; i < p; ++i)
         for (int j = 0; j < p; ++j)
             if (X[i] == Y[j]) return b2k_fail(ctx, B2K_EINVAL, "apply_block: Y[%d] aliases X[%d]", j, i);
-    bool fast = op->kind == 0 && ctx->nranks == 1 && g_spmv_pipe && p > 1;     // (stencil: the loop of applies)
+    bool fast = op->kind == 0 && ctx->nranks == 1 && g_spmv_pipe && p > 1 &&   // (stencil: the loop of applies)
+                b2k_block_kernels_enabled();
     int32_t sx = -1, sy = -1;
     std::vector<int32_t> ix, iy;
     B2K_TRY(b2k_resolve_cols(ctx, X, p, &sx, &ix));
