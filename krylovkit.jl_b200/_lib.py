@@ -139,6 +139,7 @@ _PROTOS = {
     "b2k_debug_set_coop": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_spmv_pipe": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_dmma": (C.c_int32, [C.c_int32]),
+    "b2k_debug_set_transform": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_chain": (C.c_int32, [C.c_int32]),
     "b2k_debug_used_columns": (C.c_int32, [c_ctx, C.c_int32]),
     "b2k_debug_set_chain_mode": (C.c_int32, [C.c_int32]),

@@ -511,6 +511,130 @@ k_transform_dmma(const __grid_constant__ TransformParams p, const __grid_constan
     }
 }
 
+// FP64 restart GEMM on the DFMA pipe with U in the constant bank.  `DMMA.8x8x4` issues through the XU pipe on
+// B200 and saturates it at ~30 FMA/clk/SM (profiles/r02_transform_pipes.md); the DFMA pipe is ~2.5x faster but the
+// FMA kernel above starved it on the shared-memory broadcast of U (two wavefronts per double).  Here U travels as
+// a kernel parameter: a warp-uniform constant index compiles to `LDCU.64 URx, c[0x0][UR+imm]` + `DFMA R, R, URx, R`
+// (cuobjdump -sass), so U costs no LSU wavefront at all and shared memory only serves the ROWS LDS.64 of Q per
+// basis vector.  thread <-> ROWS rows x TH outputs; keep <= 36 is one pass, so chunks are consumed and released as
+// they land (TMA overlaps the arithmetic).  Sums run over i in increasing order with fma: the same bits as
+// k_transform.
+constexpr int UR_J = 36;                                  // outputs per pass == row pitch of U in the parameter
+constexpr int UR_MAXM = 96;                               // NS * 8 basis vectors
+struct UPar {
+    double u[UR_MAXM * UR_J];                             // u[i * UR_J + j], zero-padded to UR_J columns (27 KB)
+};
+
+template <int ROWS, int TH, int HOFF>
+__device__ __forceinline__ void ur_consume(const UPar& U, const TransformParams& p, const ColList& cl,
+                                           const uint8_t* smem, uint32_t full, uint32_t empty, uint32_t& s,
+                                           uint32_t& ph, int rp, int lane) {
+    constexpr int R = 256, C = 8, RS = R / ROWS;
+    const int nch = (p.m + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    double* base = reinterpret_cast<double*>(p.base);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        double acc[ROWS][TH];
+#pragma unroll
+        for (int e = 0; e < ROWS; ++e)
+#pragma unroll
+            for (int t = 0; t < TH; ++t) acc[e][t] = 0.0;
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(full + 8 * s, ph);
+            const double* slot = reinterpret_cast<const double*>(smem + s * SLOT_BYTES) + rp;
+            const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+            const double* urow = U.u + c * C * UR_J + HOFF;
+            if (ncol == C) {
+#pragma unroll
+                for (int jj = 0; jj < C; ++jj) {
+                    double q[ROWS];
+#pragma unroll
+                    for (int e = 0; e < ROWS; ++e) q[e] = slot[jj * R + e * RS];
+#pragma unroll
+                    for (int t = 0; t < TH; ++t) {
+                        const double u = urow[jj * UR_J + t];
+#pragma unroll
+                        for (int e = 0; e < ROWS; ++e) acc[e][t] = fma(q[e], u, acc[e][t]);
+                    }
+                }
+            } else {
+                for (int jj = 0; jj < ncol; ++jj) {
+                    double q[ROWS];
+#pragma unroll
+                    for (int e = 0; e < ROWS; ++e) q[e] = slot[jj * R + e * RS];
+#pragma unroll
+                    for (int t = 0; t < TH; ++t) {
+                        const double u = urow[jj * UR_J + t];
+#pragma unroll
+                        for (int e = 0; e < ROWS; ++e) acc[e][t] = fma(q[e], u, acc[e][t]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * s);
+            if (++s == NS) { s = 0; ph ^= 1; }
+        }
+#pragma unroll
+        for (int t = 0; t < TH; ++t)
+            if (HOFF + t < p.keep) {
+                double* col = base + (int64_t)cl.c[HOFF + t] * p.ld + r0 + rp;
+#pragma unroll
+                for (int e = 0; e < ROWS; ++e)
+                    if (rp + e * RS < rt) col[e * RS] = acc[e][t];
+            }
+    }
+}
+
+template <int ROWS, int TH>
+__global__ void __launch_bounds__(TR_THREADS, 1)
+k_transform_ur(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl,
+               const __grid_constant__ UPar U) {
+    constexpr int R = 256, C = 8, RS = R / ROWS;
+    constexpr int NT = RS * (UR_J / TH);                  // consumer threads that have work
+    static_assert(UR_J % TH == 0 && NT <= NCONS && NT % 32 == 0, "consumer layout");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full = smem_u32(smem + TR_OFF_BAR), empty = full + NS * 8;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, NT / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= NCONS) {
+        const int nch = (p.m + C - 1) / C;
+        const int64_t ntiles = (p.n + R - 1) / R;
+        const double* base = reinterpret_cast<const double*>(p.base);
+        const int lane = threadIdx.x & 31;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(empty + 8 * s, ph ^ 1);
+                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+                if (lane == 0) mbar_expect_tx(full + 8 * s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(ring + s * SLOT_BYTES + lane * R * 8,
+                             base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes, full + 8 * s);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+    if (threadIdx.x >= NT) return;
+    const int tid = threadIdx.x, lane = tid & 31, rp = tid % RS;
+    // the output group is warp-uniform; dispatching on it keeps every index into U a uniform constant-bank address
+    if (UR_J / TH == 1 || tid < RS) ur_consume<ROWS, TH, 0>(U, p, cl, smem, full, empty, s, ph, rp, lane);
+    else ur_consume<ROWS, TH, (UR_J / TH == 1 ? 0 : TH)>(U, p, cl, smem, full, empty, s, ph, rp, lane);
+}
+
 // rank1update!: b[cols[i]] = beta*b[cols[i]] + (alpha*conj(x[i])) * y   — orthonormal.jl:219-227
 struct CoefList {
     double c[256];
@@ -578,12 +702,13 @@ int32_t enqueue_finalize(b2k_ctx* ctx, const double* A, const double* B, const d
 
 bool g_l2_hints = true;      // B2K_L2_HINTS=0 switches the eviction-priority hints off (A/B measurements)
 // How a chained step gets its normalised vector v = r/beta:
-//   1 (default): a third "scale" phase of the Gram-Schmidt launch normalises w in place while its tiles are hot in
-//      L2; the SpMV is the plain one and finds its operand warm — the layout of the reference (lanczos.jl:257: the
-//      residual's storage becomes the basis vector);
-//   0: normalisation fused into the SpMV's gather, v written to a column of its own (r's column is recycled).
+//   0 (default): normalisation fused into the SpMV's gather, v written to a column of its own (r's column is
+//      recycled); with the L2 eviction hints r is still partly L2-resident when the SpMV gathers it;
+//   1: a third "scale" phase of the Gram-Schmidt launch normalises w in place — the layout of the reference
+//      (lanczos.jl:257: the residual's storage becomes the basis vector).  Measured on the headline job
+//      (gpurun_out/r02f_*): the extra phase costs the sweep 68 us, the plain SpMV gains 14 us: 680 vs 705 it/s.
 // B2K_CHAIN_MODE selects; both are bit-identical to stepping.
-int g_chain_mode = 1;
+int g_chain_mode = 0;
 
 struct Panel {
     void* base;      // space base pointer
@@ -762,6 +887,7 @@ bool fused_ok(const b2k_ctx* ctx, int k, int sharded, int dtype) {
 
 bool g_use_coop = true;
 bool g_use_dmma = true;
+int g_transform_ur = 0;      // B2K_TRANSFORM_UR: 0 = DMMA kernel, 1 = <2 rows x 18>, 2 = <2 x 36>, 3 = <4 x 18> (DFMA, U in the constant bank)
 
 // modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
 // s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
@@ -814,7 +940,8 @@ int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res
 // called once per context (ctx.cu): opt in to > 48 KB dynamic shared memory
 int32_t b2k_basis_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_L2_HINTS")) g_l2_hints = e[0] != '0';
-    if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '0' ? 0 : 1;
+    if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '1' ? 1 : 0;
+    if (const char* e = getenv("B2K_TRANSFORM_UR")) g_transform_ur = (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
 #define SETATTR(fn, bytes) \
     B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
     SETATTR((k_phase<double, false, true>), SMEM_BYTES);
@@ -826,6 +953,9 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR(k_gs_fused<double>, SMEM_BYTES);
     SETATTR(k_gs_fused<float>, SMEM_BYTES);
     SETATTR(k_transform_dmma, TD_SMEM);
+    SETATTR((k_transform_ur<2, 18>), TR_SMEM);
+    SETATTR((k_transform_ur<2, 36>), TR_SMEM);
+    SETATTR((k_transform_ur<4, 18>), TR_SMEM);
     SETATTR((k_transform<double, true>), TR_SMEM);
     SETATTR((k_transform<double, false>), TR_SMEM);
     SETATTR((k_transform<float, true>), TR_SMEM);
@@ -838,6 +968,12 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
 
 extern "C" int32_t b2k_debug_set_dmma(int32_t on) {
     g_use_dmma = on != 0;
+    return B2K_OK;
+}
+
+// 0 = DMMA restart GEMM, 1..3 = the DFMA / constant-bank variants (k_transform_ur)
+extern "C" int32_t b2k_debug_set_transform(int32_t mode) {
+    g_transform_ur = (mode >= 0 && mode <= 3) ? mode : 0;
     return B2K_OK;
 }
 
@@ -1548,6 +1684,15 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm);
         if (f64) k_transform_big<double><<<grid, TB_THREADS, smem, ctx->stream>>>(p, cl);
         else k_transform_big<float><<<grid, TB_THREADS, smem, ctx->stream>>>(p, cl);
+    } else if (f64 && g_transform_ur && keep <= UR_J && m <= UR_MAXM) {
+        UPar up;                                          // by-value kernel parameter: copied at launch
+        memset(&up, 0, sizeof(up));
+        for (int j = 0; j < keep; ++j)
+            for (int i = 0; i < m; ++i) up.u[i * UR_J + j] = U_host[(size_t)j * ldu + i];
+        const int grid = grid_for_rows<double>(ctx, pn.n);
+        if (g_transform_ur == 1) k_transform_ur<2, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
+        else if (g_transform_ur == 2) k_transform_ur<2, 36><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
+        else k_transform_ur<4, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
     } else if (dmma_ok) {
         k_transform_dmma<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
     } else if (f64) {

@@ -1477,8 +1477,9 @@ int32_t b2k_enqueue_apply_fused(b2k_ctx* ctx, const b2k_op* op, const VecRef& x,
         B2K_LAUNCH_CHECK(ctx);
         return B2K_OK;
     }
+    // algorithmic bytes: matrix + x + y, plus the normalised copy of x a chained Lanczos step stores (fz.vout)
     const int pr = b2k_prof_begin(ctx, 0, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
-                                              2.0 * ctx->esize * op->n_rows);
+                                              (fz.vout ? 3.0 : 2.0) * ctx->esize * op->n_rows);
     if (g_spmv_pipe) {
         const int per_sm = g_spmv_variant == 1 ? 4 : 3;
         const int grid = std::min(op->nblk, per_sm * ctx->num_sms);

@@ -122,13 +122,16 @@ class HostSimLib:
         self.next_id = 1000
         self.err = b""
         self.chain = True          # b2k_lanczos_expand_many follows the device-chained handle contract (CGS2)
-        self.chain_mode = 1        # 1: residual normalised in place (reference layout); 0: v in a column of its own
+        self.chain_mode = 0        # 0 (library default): v in a column of its own; 1: residual normalised in place
 
     def b2k_debug_used_columns(self, h, space):
         return len(self._c(h).spaces[space].cols)
 
     def b2k_debug_set_chain_mode(self, mode):
         self.chain_mode = 0 if mode == 0 else 1
+        return L.OK
+
+    def b2k_debug_set_transform(self, mode):
         return L.OK
 
     def b2k_debug_set_chain(self, on):

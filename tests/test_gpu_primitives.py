@@ -262,6 +262,36 @@ def test_basistransform(n, m, keep, dtype):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("n,m,keep", [(70001, 60, 36), (5000, 30, 18), (257, 61, 35), (100003, 96, 36), (999, 5, 1)])
+def test_basistransform_constant_bank_variants(n, m, keep, mode):
+    """k_transform_ur (DFMA with U in the kernel-parameter constant bank; thread <-> 2x18, 2x36, 4x18 register
+    tiles) against the dense product; sums in increasing i with fma, so the three layouts agree bit for bit."""
+    lib = L.load()
+    rng = np.random.default_rng(n + m)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    U, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    ref = Q @ U[:, :keep]
+    outs = []
+    try:
+        for md in (mode, 1):
+            lib.b2k_debug_set_transform(md)
+            ctx = kk.B200Context(n, m + 4)
+            vecs = ctx.empty_range(m)
+            for j, v in enumerate(vecs):
+                v.upload(Q[:, j])
+            b = kk.OrthonormalBasis(vecs)
+            kk.basistransform_(b, U[:, :keep])
+            out = np.column_stack([b[j].to_host() for j in range(m)])
+            np.testing.assert_allclose(out[:, :keep], ref, rtol=1e-12, atol=1e-12)
+            np.testing.assert_array_equal(out[:, keep:], Q[:, keep:])
+            outs.append(out)
+            ctx.close()
+    finally:
+        lib.b2k_debug_set_transform(0)
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_givens_householder_rank1(dtype):
     """test/linalg.jl:27-44: Givens / Householder on a basis equal the dense result."""

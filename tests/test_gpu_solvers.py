@@ -823,7 +823,7 @@ def _expand_many_run(chain, nx=97, ny=61, steps=30, tol=0.0, diag=None, orth=Non
         return out
     finally:
         lib.b2k_debug_set_chain(1)
-        lib.b2k_debug_set_chain_mode(1)
+        lib.b2k_debug_set_chain_mode(0)
 
 
 def test_chained_lanczos_batch_is_bit_identical_to_stepping():
