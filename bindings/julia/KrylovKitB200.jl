@@ -358,6 +358,31 @@ function bicgstab_full!(A::B200CSR, x::B200Vec, r::B200Vec, rs::B200Vec, p::B200
                          Float64(α), ω, nr, ρ))
     return ω[], nr[], ρ[]
 end
+# The same two loops with their iterations chained on the device (one host synchronisation per call): the scalar
+# recurrences and the convergence tests of cg.jl:68 / bicgstab.jl:118,152 run in the kernels that produce the norms.
+# cg_chain! returns (<p,q> per iteration, ||r|| per iteration); the iteration that met ||r|| < tol is the last.
+function cg_chain!(A::B200CSR, x::B200Vec, r::B200Vec, p::B200Vec, q::B200Vec, α₀::Real, α₁::Real, β::Real, ρ::Real,
+                   tol::Real, nsteps::Integer)
+    pq, nr, done = zeros(Float64, nsteps), zeros(Float64, nsteps), Ref{Int32}(0)
+    check(x.ctx.h, ccall((:b2k_cg_chain, lib), Cint,
+                         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Int32, Float64, Float64, Float64, Float64, Float64, Int32,
+                          Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+                         x.ctx.h, A.h, x.handle, r.handle, p.handle, q.handle, Float64(α₀), Float64(α₁), Float64(β), Float64(ρ),
+                         Float64(tol), Int32(nsteps), pq, nr, done))
+    return pq[1:done[]], nr[1:done[]]
+end
+# bicgstab_chain! returns an 8 × done matrix, one column per completed iteration:
+# (ρ, σ, α, ||s||, ω, ||r||, next ρ, stop code); stop code 1: ||s|| < tol (the full step has not run), 2: ||r|| < tol.
+function bicgstab_chain!(A::B200CSR, x::B200Vec, r::B200Vec, rs::B200Vec, p::B200Vec, v::B200Vec, s::B200Vec, t::B200Vec,
+                         α₀::Real, α₁::Real, ρ::Real, ρold::Real, α::Real, ω::Real, tol::Real, nsteps::Integer)
+    rec, done = zeros(Float64, 8, nsteps), Ref{Int32}(0)
+    check(x.ctx.h, ccall((:b2k_bicgstab_chain, lib), Cint,
+                         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Int32, Int32, Int32, Int32, Float64, Float64, Float64,
+                          Float64, Float64, Float64, Float64, Int32, Ptr{Float64}, Ref{Int32}),
+                         x.ctx.h, A.h, x.handle, r.handle, rs.handle, p.handle, v.handle, s.handle, t.handle, Float64(α₀),
+                         Float64(α₁), Float64(ρ), Float64(ρold), Float64(α), Float64(ω), Float64(tol), Int32(nsteps), rec, done))
+    return rec[:, 1:done[]]
+end
 # KrylovKit.linsolve(A::B200CSR, b, x₀, alg::CG / BiCGStab, a₀, a₁) are the reference drivers (cg.jl, bicgstab.jl)
 # with their loop bodies replaced by the calls above — krylovkit.jl_b200/linsolve.py::_cg/_bicgstab is that code,
 # statement for statement, and is what the test-suite runs.

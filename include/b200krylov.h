@@ -223,6 +223,18 @@ int32_t b2k_bicgstab_full(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, 
                           b2k_vec s, b2k_vec t, double a0, double a1, double alpha, double* omega_out,
                           double* normr_out, double* rho_out);
 
+/* Up to `nsteps` BiCGStab iterations (every iteration after the first, bicgstab.jl:95-171) enqueued back to back:
+ * rho, rho_old, alpha, omega stay on the device, the kernels that produce ||s|| and ||r|| make the reference's two
+ * convergence tests (:118, :152) and launches behind a hit do nothing — ONE host synchronisation per call instead
+ * of two per iteration.  rho = <rs, r> of the current residual, rho_old / alpha / omega from the previous iteration.
+ * rec_out: 8 doubles per completed iteration {rho, sigma, alpha, ||s||, omega, ||r||, next rho, stop code}; stop
+ * code 1 = ||s|| < tol (the full step of that iteration has not run), 2 = ||r|| < tol; the stopping iteration is
+ * the last of *steps_done.  Same iterates as b2k_bicgstab_half/_full called in turn.  Single GPU, CSR operator. */
+int32_t b2k_bicgstab_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec rs, b2k_vec p,
+                           b2k_vec v, b2k_vec s, b2k_vec t, double a0, double a1, double rho, double rho_old,
+                           double alpha, double omega, double tol, int32_t nsteps, double* rec_out,
+                           int32_t* steps_done);
+
 /* ---------------------------------------------- basis (OrthonormalBasis) ---- */
 /* project!!(y, b, x, alpha, beta, r): h[j] = beta*h[j] + alpha*<b[cols[j]], x>
  * — src/orthonormal.jl:88-118.  h is a HOST vector (orthonormal.jl:374, arnoldi.jl:212). */

@@ -102,6 +102,8 @@ _PROTOS = {
                                       P(C.c_double)]),
     "b2k_bicgstab_full": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, c_vec, c_vec, C.c_double,
                                       C.c_double, C.c_double, P(C.c_double), P(C.c_double), P(C.c_double)]),
+    "b2k_bicgstab_chain": (C.c_int32, [c_ctx, c_op] + [c_vec] * 7 + [C.c_double] * 7 +
+                           [C.c_int32, P(C.c_double), P(C.c_int32)]),
     "b2k_basis_project": (C.c_int32, [c_ctx, P(c_vec), C.c_int32, c_vec, C.c_double, C.c_double,
                                       P(C.c_double)]),
     "b2k_basis_unproject": (C.c_int32, [c_ctx, c_vec, P(c_vec), C.c_int32, P(C.c_double), C.c_double,

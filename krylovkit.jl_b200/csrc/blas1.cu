@@ -16,6 +16,15 @@ struct CgChain {
     double tol;
 };
 
+// device-chained BiCGStab iterations (b2k_bicgstab_chain): st = {rho, rho_old, alpha, omega} on the device,
+// rec = {rho, sigma, alpha, ||s||, omega, ||r||, next rho, stop code} of this iteration
+struct BicgChain {
+    double* st;
+    double* rec;
+    int* stop;
+    double tol;
+};
+
 constexpr int BT = 256;            // threads per CTA
 constexpr int CTAS_PER_SM = 4;
 
@@ -356,7 +365,15 @@ __global__ void __launch_bounds__(BT) k_xpby_dev(T* __restrict__ y, const T* __r
 // p <- r + beta*(p - omega*v)   (bicgstab.jl:101-102: p = add!!(p, v, -ω); p = add!!(p, r, 1, β))
 template <typename T>
 __global__ void __launch_bounds__(BT)
-k_bicg_p(T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ v, int64_t n, T beta, T omega) {
+k_bicg_p(T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ v, int64_t n, T beta, T omega,
+         const BicgChain ch) {
+    if (ch.stop && *reinterpret_cast<const volatile int*>(ch.stop)) return;
+    if (ch.st) {   // bicgstab.jl:98-100 on the device: beta = (rho / rho_old) * (alpha / omega)
+        const volatile double* st = ch.st;
+        const double om = st[3];
+        beta = (T)((st[0] / st[1]) * (st[2] / om));
+        omega = (T)om;
+    }
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
@@ -412,12 +429,14 @@ template <typename T>
 __global__ void __launch_bounds__(BT)
 k_bicg_s(T* __restrict__ s, const T* __restrict__ r, const T* __restrict__ v, int64_t n, double rho,
          const double* __restrict__ sigma, double* __restrict__ part, unsigned* __restrict__ ticket,
-         double* __restrict__ out) {
+         double* __restrict__ out, const BicgChain ch) {
     __shared__ double red[32];
     __shared__ bool last;
+    if (ch.stop && *reinterpret_cast<const volatile int*>(ch.stop)) return;
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    if (ch.st) rho = *reinterpret_cast<const volatile double*>(ch.st);
     const T alpha = (T)(rho / *sigma);
     T acc = 0;
     _Pragma("unroll 4")
@@ -440,6 +459,16 @@ k_bicg_s(T* __restrict__ s, const T* __restrict__ r, const T* __restrict__ v, in
     }
     const double blk[1] = {block_sum((double)acc, red)};
     finish_sums<1>(blk, part, ticket, out, red, &last);
+    if (ch.st && last && threadIdx.x == 0) {
+        // bicgstab.jl:106-118 on the device: alpha = rho / sigma, the half-step residual norm and its test
+        const double sg = *sigma, al = rho / sg, ns = sqrt(out[0]);
+        ch.rec[0] = rho; ch.rec[1] = sg; ch.rec[2] = al; ch.rec[3] = ns;
+        ch.st[2] = al;
+        if (ns < ch.tol) {
+            ch.rec[7] = 1.0;
+            *ch.stop = 1;
+        }
+    }
 }
 
 // x <- (x + alpha*p) + omega*s ; r <- s - omega*t with omega = *ts / *tt (device scalars);
@@ -449,12 +478,14 @@ __global__ void __launch_bounds__(BT)
 k_bicg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ rs, const T* __restrict__ p,
           const T* __restrict__ s, const T* __restrict__ t, int64_t n, T alpha, const double* __restrict__ ts,
           const double* __restrict__ tt, double* __restrict__ part, unsigned* __restrict__ ticket,
-          double* __restrict__ out) {
+          double* __restrict__ out, const BicgChain ch) {
     __shared__ double red[32];
     __shared__ bool last;
+    if (ch.stop && *reinterpret_cast<const volatile int*>(ch.stop)) return;
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
+    if (ch.st) alpha = (T)(*reinterpret_cast<const volatile double*>(ch.st + 2));
     const T omega = (T)(*ts / *tt);
     T a1 = 0, a2 = 0;
     _Pragma("unroll 4")
@@ -487,6 +518,18 @@ k_bicg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ rs, const 
     blk[0] = block_sum((double)a1, red);
     blk[1] = block_sum((double)a2, red);
     finish_sums<2>(blk, part, ticket, out, red, &last);
+    if (ch.st && last && threadIdx.x == 0) {
+        // bicgstab.jl:141-152 and the next iteration's :97-98 on the device
+        const double om = *ts / *tt, nr = sqrt(out[0]), rho_next = out[1];
+        ch.rec[4] = om; ch.rec[5] = nr; ch.rec[6] = rho_next;
+        ch.st[3] = om;
+        ch.st[1] = ch.st[0];
+        ch.st[0] = rho_next;
+        if (nr < ch.tol) {
+            ch.rec[7] = 2.0;
+            *ch.stop = 1;
+        }
+    }
 }
 
 }  // namespace
@@ -870,11 +913,11 @@ extern "C" int32_t b2k_bicgstab_half(b2k_ctx* ctx, const b2k_op* op, b2k_vec rs,
         B2K_TRY(b2k_vec_copy(ctx, p, r));
     } else if (ctx->dtype == B2K_F64) {
         k_bicg_p<double><<<grid, BT, 0, ctx->stream>>>((double*)rp.ptr, (const double*)rr.ptr,
-                                                       (const double*)rv.ptr, n, beta, omega);
+                                                       (const double*)rv.ptr, n, beta, omega, BicgChain{});
         B2K_LAUNCH_CHECK(ctx);
     } else {
         k_bicg_p<float><<<grid, BT, 0, ctx->stream>>>((float*)rp.ptr, (const float*)rr.ptr, (const float*)rv.ptr,
-                                                      n, (float)beta, (float)omega);
+                                                      n, (float)beta, (float)omega, BicgChain{});
         B2K_LAUNCH_CHECK(ctx);
     }
     const bool shifted = (a0 != 0.0) || (a1 != 1.0);
@@ -883,11 +926,11 @@ extern "C" int32_t b2k_bicgstab_half(b2k_ctx* ctx, const b2k_op* op, b2k_vec rs,
     if (ctx->dtype == B2K_F64)
         k_bicg_s<double><<<grid, BT, 0, ctx->stream>>>((double*)rsv.ptr, (const double*)rr.ptr,
                                                        (const double*)rv.ptr, n, rho, ctx->d_res, ctx->d_part_s,
-                                                       ctx->d_sync, ctx->d_res + 1);
+                                                       ctx->d_sync, ctx->d_res + 1, BicgChain{});
     else
         k_bicg_s<float><<<grid, BT, 0, ctx->stream>>>((float*)rsv.ptr, (const float*)rr.ptr, (const float*)rv.ptr,
                                                       n, rho, ctx->d_res, ctx->d_part_s, ctx->d_sync,
-                                                      ctx->d_res + 1);
+                                                      ctx->d_res + 1, BicgChain{});
     B2K_LAUNCH_CHECK(ctx);
     B2K_TRY(b2k_allreduce(ctx, ctx->d_res + 1, 1, rr.sharded));
     B2K_TRY(b2k_fetch_results(ctx, 2, 0));
@@ -920,18 +963,109 @@ extern "C" int32_t b2k_bicgstab_full(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, 
                                                         (const double*)rp.ptr, (const double*)rsv.ptr,
                                                         (const double*)rt.ptr, n, alpha, ctx->d_res,
                                                         ctx->d_res + 1, ctx->d_part_s, ctx->d_sync,
-                                                        ctx->d_res + 2);
+                                                        ctx->d_res + 2, BicgChain{});
     else
         k_bicg_xr<float><<<grid, BT, 0, ctx->stream>>>((float*)rx.ptr, (float*)rr.ptr, (const float*)rrs.ptr,
                                                        (const float*)rp.ptr, (const float*)rsv.ptr,
                                                        (const float*)rt.ptr, n, (float)alpha, ctx->d_res,
                                                        ctx->d_res + 1, ctx->d_part_s, ctx->d_sync,
-                                                       ctx->d_res + 2);
+                                                       ctx->d_res + 2, BicgChain{});
     B2K_LAUNCH_CHECK(ctx);
     B2K_TRY(b2k_allreduce(ctx, ctx->d_res + 2, 2, rr.sharded));
     B2K_TRY(b2k_fetch_results(ctx, 4, 0));
     *omega_out = ctx->h_res[0] / ctx->h_res[1];
     *normr_out = sqrt(ctx->h_res[2]);
     *rho_out = ctx->h_res[3];
+    return B2K_OK;
+}
+
+// Up to `nsteps` BiCGStab iterations (bicgstab.jl:95-171, every iteration after the first) enqueued back to back:
+// rho, rho_old, alpha, omega live on the device, the two convergence tests of an iteration (:118 after the half
+// step, :152 after the full step) are made by the kernels that produce the norms, and the launches behind a hit do
+// nothing.  ONE host synchronisation per call instead of two per iteration.  rec_out gets 8 doubles per completed
+// iteration: {rho, sigma, alpha, ||s||, omega, ||r||, next rho, stop code (0: none, 1: ||s|| < tol — the full step
+// of that iteration has NOT run —, 2: ||r|| < tol)}.  The host handles what follows a hit (explicit residual).
+extern "C" int32_t b2k_bicgstab_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec r, b2k_vec rs, b2k_vec p,
+                                      b2k_vec v, b2k_vec s, b2k_vec t, double a0, double a1, double rho,
+                                      double rho_old, double alpha, double omega, double tol, int32_t nsteps,
+                                      double* rec_out, int32_t* steps_done) {
+    if (!ctx || !op || !rec_out || !steps_done || nsteps < 1) return B2K_EINVAL;
+    *steps_done = 0;
+    if (nsteps > B2K_MAX_CHAIN - 1) nsteps = B2K_MAX_CHAIN - 1;
+    VecRef rx, rr, rrs, rp, rv, rsv, rt;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    B2K_TRY(b2k_resolve(ctx, r, &rr));
+    B2K_TRY(b2k_resolve(ctx, rs, &rrs));
+    B2K_TRY(b2k_resolve(ctx, p, &rp));
+    B2K_TRY(b2k_resolve(ctx, v, &rv));
+    B2K_TRY(b2k_resolve(ctx, s, &rsv));
+    B2K_TRY(b2k_resolve(ctx, t, &rt));
+    const int64_t n = rr.n;
+    if (rx.n != n || rrs.n != n || rp.n != n || rv.n != n || rsv.n != n || rt.n != n)
+        return b2k_fail(ctx, B2K_EDIM, "bicgstab_chain: length mismatch");
+    if (ctx->nranks > 1)
+        return b2k_fail(ctx, B2K_ENOTSUP, "bicgstab_chain: single-GPU contexts (use b2k_bicgstab_half/_full)");
+    int64_t orows = 0, ocols = 0;
+    int32_t okind = -1;
+    B2K_TRY(b2k_op_info(op, &orows, &ocols, nullptr, &okind));
+    if (okind != 0) return b2k_fail(ctx, B2K_ENOTSUP, "bicgstab_chain: CSR operators only");
+    double* st = ctx->d_steps;                          // {rho, rho_old, alpha, omega}
+    double* rec0 = ctx->d_steps + B2K_REC;
+    int* d_stop = reinterpret_cast<int*>(ctx->d_sync + B2K_SYNC_STOP);
+    const double seed[4] = {rho, rho_old, alpha, omega};
+    B2K_TRY(b2k_put_coef(ctx, seed, 4, 0));
+    B2K_CUDA(ctx, cudaMemcpyAsync(st, ctx->d_coef, 4 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    B2K_CUDA(ctx, cudaMemsetAsync(rec0, 0, sizeof(double) * B2K_REC * nsteps, ctx->stream));
+    B2K_CUDA(ctx, cudaMemsetAsync(d_stop, 0, sizeof(int), ctx->stream));
+    const bool shifted = (a0 != 0.0) || (a1 != 1.0);
+    const int grid = grid_for(ctx, n, 8);
+    const bool f64 = ctx->dtype == B2K_F64;
+    SpmvFuse fz;
+    memset(&fz, 0, sizeof(fz));
+    fz.stop = d_stop;
+    for (int32_t i = 0; i < nsteps; ++i) {
+        BicgChain ch;
+        ch.st = st; ch.rec = rec0 + (size_t)B2K_REC * i; ch.stop = d_stop; ch.tol = tol;
+        if (f64)
+            k_bicg_p<double><<<grid, BT, 0, ctx->stream>>>((double*)rp.ptr, (const double*)rr.ptr,
+                                                           (const double*)rv.ptr, n, 0.0, 0.0, ch);
+        else
+            k_bicg_p<float><<<grid, BT, 0, ctx->stream>>>((float*)rp.ptr, (const float*)rr.ptr,
+                                                          (const float*)rv.ptr, n, 0.f, 0.f, ch);
+        B2K_LAUNCH_CHECK(ctx);
+        B2K_TRY(b2k_enqueue_apply_fused(ctx, op, rp, rv, a0, a1, shifted, &rrs, ctx->d_res, &fz));   // sigma
+        if (f64)
+            k_bicg_s<double><<<grid, BT, 0, ctx->stream>>>((double*)rsv.ptr, (const double*)rr.ptr,
+                                                           (const double*)rv.ptr, n, 0.0, ctx->d_res, ctx->d_part_s,
+                                                           ctx->d_sync, ctx->d_res + 1, ch);
+        else
+            k_bicg_s<float><<<grid, BT, 0, ctx->stream>>>((float*)rsv.ptr, (const float*)rr.ptr,
+                                                          (const float*)rv.ptr, n, 0.0, ctx->d_res, ctx->d_part_s,
+                                                          ctx->d_sync, ctx->d_res + 1, ch);
+        B2K_LAUNCH_CHECK(ctx);
+        B2K_TRY(b2k_enqueue_apply_fused(ctx, op, rsv, rt, a0, a1, shifted, &rsv, ctx->d_res, &fz));  // <s, t>
+        B2K_TRY(b2k_enqueue_dot(ctx, rt.ptr, rt.ptr, n, nullptr, -1, 1, -1));                        // <t, t>
+        if (f64)
+            k_bicg_xr<double><<<grid, BT, 0, ctx->stream>>>((double*)rx.ptr, (double*)rr.ptr, (const double*)rrs.ptr,
+                                                            (const double*)rp.ptr, (const double*)rsv.ptr,
+                                                            (const double*)rt.ptr, n, 0.0, ctx->d_res,
+                                                            ctx->d_res + 1, ctx->d_part_s, ctx->d_sync,
+                                                            ctx->d_res + 2, ch);
+        else
+            k_bicg_xr<float><<<grid, BT, 0, ctx->stream>>>((float*)rx.ptr, (float*)rr.ptr, (const float*)rrs.ptr,
+                                                           (const float*)rp.ptr, (const float*)rsv.ptr,
+                                                           (const float*)rt.ptr, n, 0.f, ctx->d_res,
+                                                           ctx->d_res + 1, ctx->d_part_s, ctx->d_sync,
+                                                           ctx->d_res + 2, ch);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, rec0, sizeof(double) * B2K_REC * nsteps, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int32_t d = nsteps;
+    for (int32_t i = 0; i < nsteps; ++i)
+        if (ctx->h_res[(size_t)B2K_REC * i + 7] != 0.0) { d = i + 1; break; }
+    memcpy(rec_out, ctx->h_res, sizeof(double) * B2K_REC * d);
+    *steps_done = d;
     return B2K_OK;
 }

@@ -204,6 +204,8 @@ def _gmres(operator, b: B200Vec, x0: B200Vec, alg: GMRES, a0: float, a1: float):
 
 
 USE_FUSED_CG = True      # b2k_cg_step (one host round trip per iteration) for device CSR operators
+USE_BICGSTAB_CHAIN = True   # b2k_bicgstab_chain: same for BiCGStab (two device-side convergence tests per iteration)
+BICG_CHAIN_LEN = 32
 USE_CG_CHAIN = True      # b2k_cg_chain: iterations chained on the device, one host round trip per CG_CHAIN_LEN
 CG_CHAIN_LEN = 32
 
@@ -323,11 +325,35 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
     p = v = None
     s, xhalf = r.zerovector(), x.zerovector()
     t = r.zerovector() if fused else None
+    chain = fused and USE_BICGSTAB_CHAIN and ctx.nranks == 1
+    rec = np.zeros((BICG_CHAIN_LEN, 8)) if chain else None
     while True:
         numiter += 1
         rhoold, rho = rho, (r_shadow.inner(r) if rho_next is None else rho_next)
         rho_next = None
         first = p is None
+        half_done = full_done = False
+        if chain and not first:
+            # iterations 2, 3, ... enqueued back to back (b2k_bicgstab_chain): the scalar recurrences and both
+            # convergence tests of each iteration run on the device; the host sees the batch once it stops
+            nsteps = max(1, min(BICG_CHAIN_LEN, maxiter - numiter + 1))
+            done = C.c_int32()
+            ctx.check(ctx.lib.b2k_bicgstab_chain(ctx.h, operator.h, x.handle, r.handle, r_shadow.handle, p.handle,
+                                                 v.handle, s.handle, t.handle, a0, a1, rho, rhoold, alpha, omega,
+                                                 tol, nsteps, rec.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 C.byref(done)))
+            d = done.value
+            last = rec[d - 1]
+            numiter += d - 1
+            rho, alpha = float(last[0]), float(last[2])
+            half_done = True
+            if last[7] == 1.0:                   # ‖s‖ < tol: the full step of the last iteration has not run
+                numops += 2 * d - 1
+                normr = float(last[3])
+            else:
+                numops += 2 * d
+                omega, normr, rho_next = float(last[4]), float(last[5]), float(last[6])
+                full_done = True
         if first:
             if rho == 0.0:                       # `ρ ≈ 0.0` (bicgstab.jl:36): the method breaks down
                 if alg.verbosity >= WARN_LEVEL:
@@ -336,7 +362,9 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
             beta = 0.0
         else:
             beta = (rho / rhoold) * (alpha / omega)
-        if fused:
+        if half_done:
+            pass
+        elif fused:
             if first:
                 p, v = r.zerovector(), r.zerovector()
             sg, ns = C.c_double(), C.c_double()
@@ -360,7 +388,7 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
             xhalf = xhalf.scale_(1.0, x)
             xhalf = xhalf.add_(p, alpha)         # half step iterate
             normr = s.norm()
-        if normr < tol:
+        if normr < tol and not full_done:
             # replace the recurrence residual by the actual one before trusting it
             if fused:
                 xhalf = xhalf.scale_(1.0, x)
@@ -371,7 +399,9 @@ def _bicgstab(operator, b: B200Vec, x0: B200Vec, alg: BiCGStab, a0: float, a1: f
             normr_act = s.norm()
             if normr_act < tol:
                 return xhalf, ConvergenceInfo(1, s, normr_act, numiter, numops)
-        if fused:
+        if full_done:
+            pass
+        elif fused:
             om, nr, rn = C.c_double(), C.c_double(), C.c_double()
             ctx.check(ctx.lib.b2k_bicgstab_full(ctx.h, operator.h, x.handle, r.handle, r_shadow.handle, p.handle,
                                                 s.handle, t.handle, a0, a1, alpha, C.byref(om), C.byref(nr),

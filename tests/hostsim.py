@@ -646,6 +646,37 @@ class HostSimLib:
         _set(rho_out, float(rho))
         return L.OK
 
+    def b2k_bicgstab_chain(self, h, op, x, r, rs, p, v, s, t, a0, a1, rho, rho_old, alpha, omega, tol, nsteps,
+                           rec_out, done):
+        d = 0
+        for i in range(nsteps):
+            beta = (rho / rho_old) * (alpha / omega)
+            sg, ns = C.c_double(), C.c_double()
+            st = self.b2k_bicgstab_half(h, op, rs, r, p, v, s, a0, a1, beta, omega, rho, 0, sg, ns)
+            if st != L.OK:
+                return st
+            alpha = rho / sg.value
+            rec = [rho, sg.value, alpha, ns.value, 0.0, 0.0, 0.0, 0.0]
+            d = i + 1
+            if ns.value < tol:
+                rec[7] = 1.0
+            else:
+                om, nr, rn = C.c_double(), C.c_double(), C.c_double()
+                st = self.b2k_bicgstab_full(h, op, x, r, rs, p, s, t, a0, a1, alpha, om, nr, rn)
+                if st != L.OK:
+                    return st
+                omega = om.value
+                rec[4:7] = [omega, nr.value, rn.value]
+                rho_old, rho = rho, rn.value
+                if nr.value < tol:
+                    rec[7] = 2.0
+            for j in range(8):
+                rec_out[8 * i + j] = rec[j]
+            if rec[7] != 0.0:
+                break
+        _set(done, d)
+        return L.OK
+
     def b2k_host_lanczos_restart(self, *args):
         # host-only helper: the real library runs it without a GPU
         return _real_lib().b2k_host_lanczos_restart(*args)

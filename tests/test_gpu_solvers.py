@@ -928,3 +928,40 @@ def test_cg_chained_iterations_equal_stepwise():
         assert np.array_equal(x1, x0) and nr1 == nr0
     assert out[True][0][3] == 1 and out[True][1][3] == 0 and out[True][1][1] == 45
     ctx.close()
+
+
+def test_bicgstab_chained_iterations_equal_stepwise():
+    """b2k_bicgstab_chain (rho, rho_old, alpha, omega on the device; both convergence tests of an iteration made by
+    the kernels; one host sync per 32 iterations) gives the same iterates as b2k_bicgstab_half/_full called in turn:
+    same numiter / numops / converged, same x bit for bit — for a converging run (which ends through one of the two
+    device-side tests), a fixed iteration budget, and a tolerance the half step meets first."""
+    import importlib
+    ls = importlib.import_module("krylovkit_jl_b200.linsolve")
+    rng = np.random.default_rng(5)
+    n = 6000
+    A = (sp.diags([-1.3, 2.6, -0.7], [-1, 0, 1], shape=(n, n)) +
+         sp.random(n, n, density=1e-3, random_state=4) * 0.05).tocsr()
+    b = rng.random(n)
+    nb = float(np.linalg.norm(b))
+    ctx = kk.B200Context(n, 20)
+    op = kk.B200CSR.from_scipy(ctx, A)
+    algs = [kk.BiCGStab(maxiter=4 * n, tol=1e-12 * nb, verbosity=0), kk.BiCGStab(maxiter=37, tol=1e-300, verbosity=0),
+            kk.BiCGStab(maxiter=4 * n, tol=3e-4 * nb, verbosity=0), kk.BiCGStab(maxiter=4 * n, tol=1e-9 * nb, verbosity=0)]
+    out = {}
+    try:
+        for chain in (True, False):
+            ls.USE_BICGSTAB_CHAIN = chain
+            res = []
+            for alg in algs:
+                x, info = kk.linsolve(op, ctx.from_host(b), None, alg, 0.2, 0.9)
+                res.append((x.to_host(), info.numiter, info.numops, info.converged, info.normres))
+            out[chain] = res
+    finally:
+        ls.USE_BICGSTAB_CHAIN = True
+    for (x1, it1, ops1, c1, nr1), (x0, it0, ops0, c0, nr0) in zip(out[True], out[False]):
+        assert (it1, ops1, c1) == (it0, ops0, c0), ((it1, ops1, c1), (it0, ops0, c0))
+        assert np.array_equal(x1, x0) and nr1 == nr0
+    assert [r[3] for r in out[True]] == [1, 0, 1, 1] and out[True][1][1] == 37
+    # both exits are taken: run 0 ends through the full-step test (numops = 2 numiter + 2), run 3 through the half step
+    assert out[True][0][2] == 2 * out[True][0][1] + 2 and out[True][3][2] == 2 * out[True][3][1] + 1
+    ctx.close()

@@ -246,6 +246,10 @@ def test_cg_chain_bookkeeping(simf):
     G.test_cg_chained_iterations_equal_stepwise()
 
 
+def test_bicgstab_chain_bookkeeping(simf):
+    G.test_bicgstab_chained_iterations_equal_stepwise()
+
+
 def test_block_fast_mode(sim):
     """the flagged block mode's host logic (BCGS2 coefficients -> M, Gram -> CholeskyQR2, rank fallback)"""
     import test_gpu_primitives as P

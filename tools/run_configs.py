@@ -225,8 +225,9 @@ def cg():
     out = {}
     W = 8.0 * sh.n_local
     spmv_bytes = op.nnz * 12 + 4 * (sh.n_local + 1) + 2 * W
-    for name, fused in (("fused_step", True), ("literal_mirror", False)):
+    for name, fused, chain in (("chained_32", True, True), ("fused_step", True, False), ("literal_mirror", False, False)):
         ls.USE_FUSED_CG = fused
+        ls.USE_CG_CHAIN = chain
         alg = kk.CG(maxiter=200, tol=1e-300, verbosity=0)
         (x, info), t_dev, t_wall = timed(lambda: kk.linsolve(op, b, None, alg), ctx)
         chk = kk.apply(op, x)
@@ -237,6 +238,7 @@ def cg():
                      "algorithmic_GBs (SpMV + 9W fused / 12W literal)":
                          (spmv_bytes + (9 if fused else 12) * W) * it_s / 1e9}
     ls.USE_FUSED_CG = True
+    ls.USE_CG_CHAIN = True
     ctx.close()
     return out
 
@@ -282,11 +284,13 @@ def widened(nx=4000, ny=2500, lnx=2000, lny=2000):
     del vecs, info
     # BlockLanczos, block of 4, krylovdim 32, 3 restart cycles
     X0 = kk.Block([ctx.splitmix(SEED + i) for i in range(4)])
-    alg = kk.BlockLanczos(krylovdim=32, maxiter=3, tol=0.0, verbosity=0)
-    (vals, vecs, info), t_dev, _ = timed(lambda: kk.eigsolve(lap, X0, 4, "SR", alg), ctx)
-    out["blocklanczos_p4"] = {"numops": info.numops, "numiter": info.numiter, "s": t_dev, "it_per_s": info.numops / t_dev,
-                              "ritz": [float(v) for v in vals[:4]], "normres": [float(v) for v in info.normres[:4]]}
-    del vecs, info, X0
+    for key, fast in (("blocklanczos_p4", False), ("blocklanczos_p4_fast_block", True)):
+        alg = kk.BlockLanczos(krylovdim=32, maxiter=3, tol=0.0, verbosity=0, fast_block=fast)
+        (vals, vecs, info), t_dev, _ = timed(lambda: kk.eigsolve(lap, X0, 4, "SR", alg), ctx)
+        out[key] = {"numops": info.numops, "numiter": info.numiter, "s": t_dev, "it_per_s": info.numops / t_dev,
+                    "ritz": [float(v) for v in vals[:4]], "normres": [float(v) for v in info.normres[:4]]}
+        del vecs, info
+    del X0
     # exponentiate: w = exp(-0.5 A) x0 with Lanczos, krylovdim 30
     alg = kk.Lanczos(orth=kk.cgs2, krylovdim=30, maxiter=10, tol=1e-10, verbosity=0)
     (w, info), t_dev, _ = timed(lambda: kk.exponentiate(lap, -0.5, x0, alg), ctx)
