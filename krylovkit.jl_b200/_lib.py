@@ -140,6 +140,7 @@ _PROTOS = {
     # debugging knob (not part of the public header): 0 = one launch per phase, 1 = cooperative
     "b2k_debug_set_coop": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_spmv_pipe": (C.c_int32, [C.c_int32]),
+    "b2k_debug_set_spmv_variant": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_dmma": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_transform": (C.c_int32, [C.c_int32]),
     "b2k_debug_set_chain": (C.c_int32, [C.c_int32]),

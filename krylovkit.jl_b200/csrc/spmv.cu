@@ -1324,10 +1324,16 @@ extern "C" int32_t b2k_op_csr_download(b2k_ctx* ctx, const b2k_op* op, int32_t* 
 // ------------------------------------------------------------------ apply ----
 
 static bool g_spmv_pipe = true;
-static int g_spmv_variant = 0;     // 0: 3 stages x 3 CTAs/SM, 1: 2 stages x 4 CTAs/SM (B2K_SPMV_VARIANT)
+static int g_spmv_variant = 1;     // 1 (default): 2 stages x 4 CTAs/SM, 0: 3 stages x 3 CTAs/SM (B2K_SPMV_VARIANT); measured
+                                   // 0.141 vs 0.150 ms standalone, 0.174 vs 0.179 ms in the Lanczos step (gpurun_out/r02g_*)
 
 extern "C" int32_t b2k_debug_set_spmv_pipe(int32_t on) {
     g_spmv_pipe = on != 0;
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_debug_set_spmv_variant(int32_t v) {
+    g_spmv_variant = v == 0 ? 0 : 1;
     return B2K_OK;
 }
 
@@ -1346,7 +1352,7 @@ int32_t b2k_spmv_init(b2k_ctx* ctx) {
     B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<float, 2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SppLayout<float, 2>::SMEM));
     const char* sv = getenv("B2K_SPMV_VARIANT");
-    if (sv) g_spmv_variant = atoi(sv);
+    if (sv) g_spmv_variant = atoi(sv) == 0 ? 0 : 1;
     return B2K_OK;
 }
 

@@ -70,11 +70,15 @@ def test_splitmix_matches_host():
     ctx.close()
 
 
-@pytest.fixture(params=[1, 0], ids=["pipe", "stream"])
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 1)], ids=["pipe-2x4", "pipe-3x3", "stream"])
 def spmv_kernel(request):
-    L.load().b2k_debug_set_spmv_pipe(request.param)
-    yield request.param
-    L.load().b2k_debug_set_spmv_pipe(1)
+    """the TMA-pipelined SpMV in its two stage/occupancy variants and the plain streaming kernel"""
+    lib = L.load()
+    lib.b2k_debug_set_spmv_pipe(request.param[0])
+    lib.b2k_debug_set_spmv_variant(request.param[1])
+    yield request.param[0]
+    lib.b2k_debug_set_spmv_pipe(1)
+    lib.b2k_debug_set_spmv_variant(1)
 
 
 @pytest.mark.parametrize("nx,ny", [(100, 100), (125, 80), (1, 7), (2048, 3), (37, 1), (1000, 700)])
