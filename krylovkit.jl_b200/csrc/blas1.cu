@@ -49,6 +49,17 @@ template <> __device__ __forceinline__ void vstore<float>(float* p, const float 
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Streaming loops are written as TRIPS of UN grid-strided vectors per thread: all loads of a trip are issued before its
+// first store.  (A plain `#pragma unroll 4` grid-stride loop does NOT do that: the store of iteration u may alias the
+// load of iteration u+1 as far as the compiler knows, so the unrolled body stays load -> compute -> store, 32 bytes in
+// flight per thread, and the kernels ran at 2.9-3.2 TB/s on cold data — ncu list of a CG run, gpurun_out/r02j_cg.csv.)
+// The order in which a thread visits its elements is unchanged, so every reduction keeps its bits.
+#define B2K_TRIP(UN)                                                                                   \
+    for (int64_t i0 = blockIdx.x * (int64_t)BT + threadIdx.x; i0 < nv; i0 += (int64_t)(UN) * stride)
+#define B2K_EACH(UN, u, i)                                                                             \
+    _Pragma("unroll") for (int u = 0; u < (UN); ++u)                                                   \
+        if (const int64_t i = i0 + (int64_t)u * stride; i < nv)
+
 inline int grid_for(const b2k_ctx* ctx, int64_t n, int per_thread) {
     int64_t want = (n + (int64_t)BT * per_thread - 1) / ((int64_t)BT * per_thread);
     int64_t cap = (int64_t)ctx->num_sms * CTAS_PER_SM;
@@ -78,13 +89,14 @@ __global__ void __launch_bounds__(BT) k_scale(T* __restrict__ y, const T* __rest
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V];
-        vload<T>(x + i * V, a);
+    B2K_TRIP(4) {
+        T a[4][V];
+        B2K_EACH(4, u, i) vload<T>(x + i * V, a[u]);
+        B2K_EACH(4, u, i) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) a[j] *= alpha;
-        vstore<T>(y + i * V, a);
+            for (int j = 0; j < V; ++j) a[u][j] *= alpha;
+            vstore<T>(y + i * V, a[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         int64_t i = nv * V + threadIdx.x;
@@ -99,18 +111,21 @@ __global__ void __launch_bounds__(BT) k_axpby(T* __restrict__ y, const T* __rest
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V], b[V];
-        vload<T>(x + i * V, a);
-        if (MODE != 0) vload<T>(y + i * V, b);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            if (MODE == 0) b[j] = alpha * a[j];
-            else if (MODE == 1) b[j] = fma(alpha, a[j], b[j]);
-            else b[j] = fma(alpha, a[j], beta * b[j]);
+    B2K_TRIP(4) {
+        T a[4][V], b[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(x + i * V, a[u]);
+            if (MODE != 0) vload<T>(y + i * V, b[u]);
         }
-        vstore<T>(y + i * V, b);
+        B2K_EACH(4, u, i) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (MODE == 0) b[u][j] = alpha * a[u][j];
+                else if (MODE == 1) b[u][j] = fma(alpha, a[u][j], b[u][j]);
+                else b[u][j] = fma(alpha, a[u][j], beta * b[u][j]);
+            }
+            vstore<T>(y + i * V, b[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         int64_t i = nv * V + threadIdx.x;
@@ -127,15 +142,18 @@ __global__ void __launch_bounds__(BT) k_axpy2(T* __restrict__ y, const T* __rest
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V], b[V], c[V];
-        vload<T>(y + i * V, c);
-        vload<T>(x1 + i * V, a);
-        vload<T>(x2 + i * V, b);
+    B2K_TRIP(4) {
+        T a[4][V], b[4][V], c[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(y + i * V, c[u]);
+            vload<T>(x1 + i * V, a[u]);
+            vload<T>(x2 + i * V, b[u]);
+        }
+        B2K_EACH(4, u, i) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) c[j] = fma(a2, b[j], fma(a1, a[j], c[j]));
-        vstore<T>(y + i * V, c);
+            for (int j = 0; j < V; ++j) c[u][j] = fma(a2, b[u][j], fma(a1, a[u][j], c[u][j]));
+            vstore<T>(y + i * V, c[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         int64_t i = nv * V + threadIdx.x;
@@ -150,18 +168,22 @@ __global__ void __launch_bounds__(BT) k_givens(T* __restrict__ q1, T* __restrict
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V], b[V], o1[V], o2[V];
-        vload<T>(q1 + i * V, a);
-        vload<T>(q2 + i * V, b);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            o1[j] = c * a[j] - s * b[j];
-            o2[j] = s * a[j] + c * b[j];
+    B2K_TRIP(4) {
+        T a[4][V], b[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(q1 + i * V, a[u]);
+            vload<T>(q2 + i * V, b[u]);
         }
-        vstore<T>(q1 + i * V, o1);
-        vstore<T>(q2 + i * V, o2);
+        B2K_EACH(4, u, i) {
+            T o1[V], o2[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                o1[j] = c * a[u][j] - s * b[u][j];
+                o2[j] = s * a[u][j] + c * b[u][j];
+            }
+            vstore<T>(q1 + i * V, o1);
+            vstore<T>(q2 + i * V, o2);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         int64_t i = nv * V + threadIdx.x;
@@ -189,24 +211,26 @@ k_dot(const T* __restrict__ q, T* __restrict__ x, int64_t n, const T* __restrict
     T sp = 0;
     if (UPDATE) sp = (T)(*sprev);
     T acc = 0;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V], b[V];
-        vload<T>(x + i * V, b);
-        if (UPDATE) {
-            T c[V];
-            vload<T>(qprev + i * V, c);
-#pragma unroll
-            for (int j = 0; j < V; ++j) b[j] = fma(-sp, c[j], b[j]);
-            vstore<T>(x + i * V, b);
+    B2K_TRIP(4) {
+        T a[4][V], b[4][V], c[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(x + i * V, b[u]);
+            if (UPDATE) vload<T>(qprev + i * V, c[u]);
+            if (!NORM) vload<T>(q + i * V, a[u]);
         }
-        if (NORM) {
+        B2K_EACH(4, u, i) {
+            if (UPDATE) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc = fma(b[j], b[j], acc);
-        } else {
-            vload<T>(q + i * V, a);
+                for (int j = 0; j < V; ++j) b[u][j] = fma(-sp, c[u][j], b[u][j]);
+                vstore<T>(x + i * V, b[u]);
+            }
+            if (NORM) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc = fma(a[j], b[j], acc);
+                for (int j = 0; j < V; ++j) acc = fma(b[u][j], b[u][j], acc);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc = fma(a[u][j], b[u][j], acc);
+            }
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
@@ -246,14 +270,17 @@ k_axpy_dev(T* __restrict__ x, const T* __restrict__ q, const double* __restrict_
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V], b[V];
-        vload<T>(x + i * V, b);
-        vload<T>(q + i * V, a);
+    B2K_TRIP(4) {
+        T a[4][V], b[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(x + i * V, b[u]);
+            vload<T>(q + i * V, a[u]);
+        }
+        B2K_EACH(4, u, i) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) b[j] = fma(-sp, a[j], b[j]);
-        vstore<T>(x + i * V, b);
+            for (int j = 0; j < V; ++j) b[u][j] = fma(-sp, a[u][j], b[u][j]);
+            vstore<T>(x + i * V, b[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         int64_t i = nv * V + threadIdx.x;
@@ -277,21 +304,24 @@ k_cg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* 
     if (ch.state) rho = *reinterpret_cast<const volatile double*>(ch.state);      // rho kept on the device
     const T alpha = (T)(rho / *pq);
     T acc = 0;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T xv[V], rv[V], pv[V], qv[V];
-        vload<T>(x + i * V, xv);
-        vload<T>(r + i * V, rv);
-        vload<T>(p + i * V, pv);
-        vload<T>(q + i * V, qv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            xv[j] = fma(alpha, pv[j], xv[j]);
-            rv[j] = fma(-alpha, qv[j], rv[j]);
-            acc = fma(rv[j], rv[j], acc);
+    B2K_TRIP(2) {
+        T xv[2][V], rv[2][V], pv[2][V], qv[2][V];
+        B2K_EACH(2, u, i) {
+            vload<T>(x + i * V, xv[u]);
+            vload<T>(r + i * V, rv[u]);
+            vload<T>(p + i * V, pv[u]);
+            vload<T>(q + i * V, qv[u]);
         }
-        vstore<T>(x + i * V, xv);
-        vstore<T>(r + i * V, rv);
+        B2K_EACH(2, u, i) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                xv[u][j] = fma(alpha, pv[u][j], xv[u][j]);
+                rv[u][j] = fma(-alpha, qv[u][j], rv[u][j]);
+                acc = fma(rv[u][j], rv[u][j], acc);
+            }
+            vstore<T>(x + i * V, xv[u]);
+            vstore<T>(r + i * V, rv[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         const int64_t i = nv * V + threadIdx.x;
@@ -344,14 +374,17 @@ __global__ void __launch_bounds__(BT) k_xpby_dev(T* __restrict__ y, const T* __r
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
     const T beta = (T)(*beta_dev);
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T a[V], b[V];
-        vload<T>(x + i * V, a);
-        vload<T>(y + i * V, b);
+    B2K_TRIP(4) {
+        T a[4][V], b[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(x + i * V, a[u]);
+            vload<T>(y + i * V, b[u]);
+        }
+        B2K_EACH(4, u, i) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) b[j] = xpby_rn(a[j], beta, b[j]);
-        vstore<T>(y + i * V, b);
+            for (int j = 0; j < V; ++j) b[u][j] = xpby_rn(a[u][j], beta, b[u][j]);
+            vstore<T>(y + i * V, b[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         const int64_t i = nv * V + threadIdx.x;
@@ -377,18 +410,21 @@ k_bicg_p(T* __restrict__ p, const T* __restrict__ r, const T* __restrict__ v, in
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T pv[V], rv[V], vv[V];
-        vload<T>(p + i * V, pv);
-        vload<T>(r + i * V, rv);
-        vload<T>(v + i * V, vv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const T tmp = fma(-omega, vv[j], pv[j]);          // add!!(p, v, -ω)       (k_axpby MODE 1)
-            pv[j] = fma((T)1, rv[j], beta * tmp);             // add!!(p, r, 1, β)     (k_axpby MODE 2)
+    B2K_TRIP(4) {
+        T pv[4][V], rv[4][V], vv[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(p + i * V, pv[u]);
+            vload<T>(r + i * V, rv[u]);
+            vload<T>(v + i * V, vv[u]);
         }
-        vstore<T>(p + i * V, pv);
+        B2K_EACH(4, u, i) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const T tmp = fma(-omega, vv[u][j], pv[u][j]);    // add!!(p, v, -ω)       (k_axpby MODE 1)
+                pv[u][j] = fma((T)1, rv[u][j], beta * tmp);       // add!!(p, r, 1, β)     (k_axpby MODE 2)
+            }
+            vstore<T>(p + i * V, pv[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         const int64_t i = nv * V + threadIdx.x;
@@ -439,17 +475,20 @@ k_bicg_s(T* __restrict__ s, const T* __restrict__ r, const T* __restrict__ v, in
     if (ch.st) rho = *reinterpret_cast<const volatile double*>(ch.st);
     const T alpha = (T)(rho / *sigma);
     T acc = 0;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T rv[V], vv[V];
-        vload<T>(r + i * V, rv);
-        vload<T>(v + i * V, vv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            rv[j] = fma(-alpha, vv[j], rv[j]);
-            acc = fma(rv[j], rv[j], acc);
+    B2K_TRIP(4) {
+        T rv[4][V], vv[4][V];
+        B2K_EACH(4, u, i) {
+            vload<T>(r + i * V, rv[u]);
+            vload<T>(v + i * V, vv[u]);
         }
-        vstore<T>(s + i * V, rv);
+        B2K_EACH(4, u, i) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                rv[u][j] = fma(-alpha, vv[u][j], rv[u][j]);
+                acc = fma(rv[u][j], rv[u][j], acc);
+            }
+            vstore<T>(s + i * V, rv[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         const int64_t i = nv * V + threadIdx.x;
@@ -488,23 +527,26 @@ k_bicg_xr(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ rs, const 
     if (ch.st) alpha = (T)(*reinterpret_cast<const volatile double*>(ch.st + 2));
     const T omega = (T)(*ts / *tt);
     T a1 = 0, a2 = 0;
-    _Pragma("unroll 4")
-    for (int64_t i = blockIdx.x * (int64_t)BT + threadIdx.x; i < nv; i += stride) {
-        T xv[V], pv[V], sv[V], tv[V], qv[V];
-        vload<T>(x + i * V, xv);
-        vload<T>(p + i * V, pv);
-        vload<T>(s + i * V, sv);
-        vload<T>(t + i * V, tv);
-        vload<T>(rs + i * V, qv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            xv[j] = fma(omega, sv[j], fma(alpha, pv[j], xv[j]));
-            tv[j] = fma(-omega, tv[j], sv[j]);
-            a1 = fma(tv[j], tv[j], a1);
-            a2 = fma(qv[j], tv[j], a2);
+    B2K_TRIP(2) {
+        T xv[2][V], pv[2][V], sv[2][V], tv[2][V], qv[2][V];
+        B2K_EACH(2, u, i) {
+            vload<T>(x + i * V, xv[u]);
+            vload<T>(p + i * V, pv[u]);
+            vload<T>(s + i * V, sv[u]);
+            vload<T>(t + i * V, tv[u]);
+            vload<T>(rs + i * V, qv[u]);
         }
-        vstore<T>(x + i * V, xv);
-        vstore<T>(r + i * V, tv);
+        B2K_EACH(2, u, i) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                xv[u][j] = fma(omega, sv[u][j], fma(alpha, pv[u][j], xv[u][j]));
+                tv[u][j] = fma(-omega, tv[u][j], sv[u][j]);
+                a1 = fma(tv[u][j], tv[u][j], a1);
+                a2 = fma(qv[u][j], tv[u][j], a2);
+            }
+            vstore<T>(x + i * V, xv[u]);
+            vstore<T>(r + i * V, tv[u]);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n - nv * V)) {
         const int64_t i = nv * V + threadIdx.x;

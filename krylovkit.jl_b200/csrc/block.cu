@@ -242,9 +242,99 @@ k_block_finalize(const double* __restrict__ part, int G, int stride, int rows, i
     for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
         const int i = idx / rows, j = idx - i * rows;     // column i, row j of the (rows x cols) result
         double a = 0.0;
-        for (int g = 0; g < G; ++g) a += part[(size_t)g * stride + i * src_ld + j];
+        const double* src = part + i * src_ld + j;
+        int g = 0;
+        for (; g + 8 <= G; g += 8) {           // eight independent loads in flight, added in CTA order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(g + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a += v[u];
+        }
+        for (; g < G; ++g) a += src[(size_t)g * stride];
         double* o = out + (size_t)i * out_ld + j;
         *o = accumulate ? (*o + a) : a;
+    }
+}
+
+// X <- X U in place for a block of P <= 8 columns and an UPPER triangular U (the CholeskyQR step X L^-T):
+// thread <-> row, out_j = sum_{i <= j} x_i U[i, j] by fma over i in increasing order (k_transform's order), plain
+// 128-bit streaming accesses with all loads of a trip ahead of its stores; optionally the Gram matrix of the
+// RESULT (per-CTA partials in the k_block_phase<UPDATE> layout), which is the second round's input — CholeskyQR2
+// costs two passes over the block instead of three.
+struct RmulParams {
+    void* base;
+    int64_t ld, n;
+    int32_t cols[BK_PMAX];
+    double u[BK_PMAX * BK_PMAX];      // column-major P x P
+    double* gpart;                    // [grid][BK_GRAM] or nullptr
+};
+
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_block_rmul(const __grid_constant__ RmulParams rp) {
+    __shared__ double red[8][P * (P + 1) / 2];
+    constexpr int NT = P * (P + 1) / 2;
+    T* base = reinterpret_cast<T*>(rp.base);
+    T* col[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) col[i] = base + (int64_t)rp.cols[i] * rp.ld;
+    T g[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) g[t] = (T)0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r0 < rp.n; r0 += 2 * stride) {
+        const int64_t r1 = r0 + stride;
+        const bool two = r1 < rp.n;
+        T x0[P], x1[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            x0[i] = col[i][r0];
+            x1[i] = two ? col[i][r1] : (T)0;
+        }
+        T o0[P], o1[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            T a0 = (T)0, a1 = (T)0;
+#pragma unroll
+            for (int i = 0; i <= j; ++i) {
+                const T u = (T)rp.u[j * P + i];
+                a0 = fma(x0[i], u, a0);
+                a1 = fma(x1[i], u, a1);
+            }
+            o0[j] = a0; o1[j] = a1;
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            col[j][r0] = o0[j];
+            if (two) col[j][r1] = o1[j];
+        }
+        if (rp.gpart) {
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < P; ++a)
+#pragma unroll
+                for (int b = a; b < P; ++b) { g[t] = fma(o0[a], o0[b], g[t]); g[t] = fma(o1[a], o1[b], g[t]); ++t; }
+        }
+    }
+    if (!rp.gpart) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        double v = (double)g[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NT) {
+        double a = 0.0;
+        for (int ww = 0; ww < 8; ++ww) a += red[ww][threadIdx.x];
+        int t = threadIdx.x, i1 = 0;
+        while (t >= P - i1) { t -= P - i1; ++i1; }
+        const int i2 = i1 + t;
+        rp.gpart[(size_t)blockIdx.x * BK_GRAM + i1 * BK_PMAX + i2] = a;
+        rp.gpart[(size_t)blockIdx.x * BK_GRAM + i2 * BK_PMAX + i1] = a;
     }
 }
 
@@ -345,6 +435,37 @@ int32_t block_update_dev(b2k_ctx* ctx, const BPanel& bp, const double* d_H, doub
         else B2K_TRY(launch_update<float>(ctx, bp, q0, kq, d_H, k, alpha, lastp ? d_G : nullptr, true));
     }
     if (d_G) B2K_TRY(b2k_allreduce(ctx, d_G, p * p, bp.sharded));
+    return B2K_OK;
+}
+
+// X <- X U (U upper triangular, column-major p x p on the host); d_G != nullptr: Gram matrix of the result
+int32_t block_rmul_upper(b2k_ctx* ctx, const BPanel& bp, const double* U, double* d_G) {
+    const int p = (int)bp.r.size();
+    RmulParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.base = bp.base; rp.ld = bp.ld; rp.n = bp.n;
+    for (int i = 0; i < p; ++i) rp.cols[i] = bp.r[i];
+    memcpy(rp.u, U, sizeof(double) * p * p);
+    rp.gpart = d_G ? ctx->d_blkpart : nullptr;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((bp.n + 511) / 512, 4 * (int64_t)ctx->num_sms));
+    const int pr = b2k_prof_begin(ctx, 6, 2.0 * p * ctx->esize * (double)bp.n);
+#define RMUL(T, P) k_block_rmul<T, P><<<grid, 256, 0, ctx->stream>>>(rp)
+#define RMUL_P(T)                                                                                      \
+    switch (p) {                                                                                       \
+        case 1: RMUL(T, 1); break; case 2: RMUL(T, 2); break; case 3: RMUL(T, 3); break;               \
+        case 4: RMUL(T, 4); break; case 5: RMUL(T, 5); break; case 6: RMUL(T, 6); break;               \
+        case 7: RMUL(T, 7); break; default: RMUL(T, 8); break;                                         \
+    }
+    if (ctx->dtype == B2K_F64) { RMUL_P(double) } else { RMUL_P(float) }
+#undef RMUL_P
+#undef RMUL
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    if (d_G) {
+        k_block_finalize<<<1, 256, 0, ctx->stream>>>(ctx->d_blkpart, grid, BK_GRAM, p, p, BK_PMAX, d_G, p, 0);
+        B2K_LAUNCH_CHECK(ctx);
+        B2K_TRY(b2k_allreduce(ctx, d_G, p * p, bp.sharded));
+    }
     return B2K_OK;
 }
 
@@ -484,7 +605,7 @@ extern "C" int32_t b2k_block_cholqr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, d
         if (round == 0 && G0_host) {
             memcpy(G.data(), G0_host, sizeof(double) * p * p);
         } else {
-            B2K_TRY(block_gram_dev(ctx, bp, d_G));
+            if (round == 0) B2K_TRY(block_gram_dev(ctx, bp, d_G));      // round 1: left by the first X <- X U pass
             B2K_TRY(fetch(ctx, d_G, G.data(), p * p));
         }
         // Cholesky G = L L' (column-major, lower)
@@ -522,7 +643,7 @@ extern "C" int32_t b2k_block_cholqr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, d
         std::vector<double> U(p * p, 0.0);               // U[i, j] = Linv[j, i]
         for (int j = 0; j < p; ++j)
             for (int i = 0; i <= j; ++i) U[j * p + i] = Linv[i * p + j];
-        B2K_TRY(b2k_basis_transform(ctx, X, p, U.data(), p, p));
+        B2K_TRY(block_rmul_upper(ctx, bp, U.data(), round == 0 ? d_G : nullptr));
         // R_total <- L' * R_total
         std::vector<double> Rn(p * p, 0.0);
         for (int j = 0; j < p; ++j)

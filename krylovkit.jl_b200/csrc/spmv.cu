@@ -413,8 +413,18 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
 
 // SpMM for apply(A, ::Block) (blocklanczos.jl:38): the nonzero stream of a row block is staged ONCE (same TMA
 // ring as k_spmv_pipe) and used for all p <= 8 vectors of the block: 12*nnz + p*16n bytes instead of
-// p*(12*nnz + 16n).  One thread per row walks the row's staged nonzeros and keeps p running sums; products are
-// rounded before they are added, in CSR order — bit-identical to p single-vector applies.
+// p*(12*nnz + 16n).  Per vector the consumers do what k_spmv_pipe does — thread <-> nonzero gathers x_i and writes the
+// rounded product into a product buffer (two of them, alternating, so one barrier per vector), thread <-> row sums
+// its products in CSR order — bit-identical to p single-vector applies.  (The first version let one thread per row
+// walk its nonzeros for all p vectors: a fifth of the gathers in flight, 0.78 ms for p = 4 at n = 1e7 — slower than
+// four SpMVs; ncu list gpurun_out/r02k_block.csv.)
+constexpr int SPM_NSTG = 2;
+template <typename T> struct SpmLayout {
+    using LY = SppLayout<T, SPM_NSTG>;
+    static constexpr int OFF_PROD = LY::SMEM;                              // two product buffers
+    static constexpr int PROD_BYTES = SPP_TV * (int)sizeof(T);
+    static constexpr int SMEM = OFF_PROD + 2 * PROD_BYTES;
+};
 constexpr int SPM_PMAX = 8;
 struct SpmmCols {
     int32_t x[SPM_PMAX], y[SPM_PMAX];
@@ -432,12 +442,12 @@ __global__ void __launch_bounds__(SPP_THREADS, 3)
 k_spmm_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
             T* __restrict__ base, int64_t ld, const __grid_constant__ SpmmCols cols, int np,
             const int32_t* __restrict__ rowblk, const int32_t* __restrict__ pblk, int nblk) {
-    using LY = SppLayout<T>;
+    using LY = SppLayout<T, SPM_NSTG>;
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + SPP_NSTG * 8;
+    const uint32_t full = smem_u32(smem + LY::OFF_BAR), empty = full + SPM_NSTG * 8;
     double* red = reinterpret_cast<double*>(smem + LY::OFF_RED);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SPP_NSTG; ++i) {
+        for (int i = 0; i < SPM_NSTG; ++i) {
             mbar_init(full + 8 * i, 1);
             mbar_init(empty + 8 * i, SPP_CONS / 32);
         }
@@ -472,18 +482,13 @@ k_spmm_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             } else {
                 if (lane == 0) mbar_arrive(full + 8 * s);
             }
-            if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+            if (++s == SPM_NSTG) { s = 0; ph ^= 1; }
         }
         return;
     }
     const int tid = threadIdx.x, w = tid >> 5;
-    const T* xp[SPM_PMAX];
-    T* yp[SPM_PMAX];
-#pragma unroll
-    for (int i = 0; i < SPM_PMAX; ++i) {
-        xp[i] = base + (int64_t)cols.x[i < np ? i : 0] * ld;
-        yp[i] = base + (int64_t)cols.y[i < np ? i : 0] * ld;
-    }
+    auto xcol = [&](int i) -> const T* { return base + (int64_t)cols.x[i] * ld; };
+    auto ycol = [&](int i) -> T* { return base + (int64_t)cols.y[i] * ld; };
     int tile = blockIdx.x;
     int4 dn = make_int4(0, 0, 0, 0);
     if (tile < nblk) dn = make_int4(rowblk[tile], rowblk[tile + 1], pblk[tile], pblk[tile + 1]);
@@ -499,31 +504,49 @@ k_spmm_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
             const int32_t* rs = reinterpret_cast<const int32_t*>(smem + s * LY::STAGE + LY::VAL_BYTES + LY::COL_BYTES);
             const int p0a = p0 & ~3, r0a = r0 & ~3;
             const bool rp_staged = nrows <= SPP_RMAX;
-            for (int r = r0 + tid; r < r1; r += SPP_CONS) {
-                int a, b;
-                if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
-                else { a = rowptr[r]; b = rowptr[r + 1]; }
-                a -= p0a; b -= p0a;
-                T sum[SPM_PMAX];
+            const int off = p0 - p0a;
+            constexpr int U = SP_NNZ / SPP_CONS;
+            // my nonzeros' values and columns are the same for every vector of the block: registers
+            T vv[U];
+            int32_t cc[U];
 #pragma unroll
-                for (int i = 0; i < SPM_PMAX; ++i) sum[i] = (T)0;
-                for (int q = a; q < b; ++q) {
-                    const T v = vs[q];
-                    const int32_t c = cs[q];
-#pragma unroll
-                    for (int i = 0; i < SPM_PMAX; ++i)
-                        if (i < np) sum[i] = add_rn<T>(sum[i], mul_rn<T>(v, __ldg(xp[i] + c)));
-                }
-#pragma unroll
-                for (int i = 0; i < SPM_PMAX; ++i)
-                    if (i < np) yp[i][r] = sum[i];
+            for (int u = 0; u < U; ++u) {
+                const int i = tid + u * SPP_CONS;
+                vv[u] = (i < nnzb) ? vs[off + i] : (T)0;
+                cc[u] = (i < nnzb) ? cs[off + i] : 0;
             }
+            for (int iv = 0; iv < np; ++iv) {
+                T* prod = reinterpret_cast<T*>(smem + SpmLayout<T>::OFF_PROD + (iv & 1) * SpmLayout<T>::PROD_BYTES);
+                const T* xi = xcol(iv);
+                T xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] = __ldg(xi + cc[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = tid + u * SPP_CONS;
+                    if (i < nnzb) prod[off + i] = mul_rn<T>(vv[u], xv[u]);
+                }
+                named_bar_sync(1, SPP_CONS);
+                T* yi = ycol(iv);
+                for (int r = r0 + tid; r < r1; r += SPP_CONS) {
+                    int a, b;
+                    if (rp_staged) { a = rs[r - r0a]; b = rs[r + 1 - r0a]; }
+                    else { a = rowptr[r]; b = rowptr[r + 1]; }
+                    a -= p0a; b -= p0a;
+                    T sum = (T)0;
+                    for (int q = a; q < b; ++q) sum = add_rn<T>(sum, prod[q]);
+                    yi[r] = sum;
+                }
+                // the buffer written next is the one summed one vector ago: every thread has passed that sum
+                // before it reaches the barrier above again
+            }
+            named_bar_sync(1, SPP_CONS);      // all row sums done before the stage (rowptr segment) is released
         } else {
             // long row: the CTA owns exactly one row; one vector of the block at a time
             for (int i = 0; i < np; ++i) {
                 double acc = 0.0;
                 for (int q = tid; q < nnzb; q += SPP_CONS)
-                    acc += (double)mul_rn<T>(vals[p0 + q], __ldg(xp[i] + colidx[p0 + q]));
+                    acc += (double)mul_rn<T>(vals[p0 + q], __ldg(xcol(i) + colidx[p0 + q]));
                 acc = warp_sum(acc);
                 named_bar_sync(1, SPP_CONS);
                 if (lane == 0) red[w] = acc;
@@ -531,13 +554,13 @@ k_spmm_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 if (tid == 0) {
                     double tot = 0.0;
                     for (int ww = 0; ww < SPP_CONS / 32; ++ww) tot += red[ww];
-                    yp[i][r0] = (T)tot;
+                    ycol(i)[r0] = (T)tot;
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8 * s);
-        if (++s == SPP_NSTG) { s = 0; ph ^= 1; }
+        if (++s == SPM_NSTG) { s = 0; ph ^= 1; }
     }
 }
 
@@ -589,25 +612,52 @@ k_stencil_apply(const __grid_constant__ StencilApply sa, const T* __restrict__ x
         return scaled ? v * sc : v;
     };
     T dacc = (T)0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < sa.n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool small = plane * sa.nz < ((int64_t)1 << 31);
+    const uint32_t nx32 = (uint32_t)sa.nx, ny32 = (uint32_t)sa.ny;
+    // one stencil row: returns (a0 + a1 A) x at local row i and x_i itself (normalised)
+    auto row = [&](int64_t i, T& xi) -> T {
         const int64_t g = sa.row0 + i;
-        const int64_t ix = g % sa.nx, iy = (g / sa.nx) % sa.ny, iz = g / plane;
+        int64_t ix, iy, iz;
+        if (small) {          // 32-bit index arithmetic: a 64-bit div/mod pair costs more than the whole stencil
+            const uint32_t g32 = (uint32_t)g, t32 = g32 / nx32;
+            ix = g32 - t32 * nx32;
+            const uint32_t z32 = t32 / ny32;
+            iy = t32 - z32 * ny32;
+            iz = z32;
+        } else {
+            ix = g % sa.nx; iy = (g / sa.nx) % sa.ny; iz = g / plane;
+        }
         T sum = (T)0;
         if (sa.nz > 1 && iz > 0) sum = add_rn<T>(sum, mul_rn<T>(cd, X(i - plane)));
         if (iy > 0) sum = add_rn<T>(sum, mul_rn<T>(cs, X(i - sa.nx)));
         if (ix > 0) sum = add_rn<T>(sum, mul_rn<T>(cw, X(i - 1)));
-        const T xi = X(i);
+        xi = X(i);
         sum = add_rn<T>(sum, mul_rn<T>(c0, xi));
         if (ix < sa.nx - 1) sum = add_rn<T>(sum, mul_rn<T>(ce, X(i + 1)));
         if (iy < sa.ny - 1) sum = add_rn<T>(sum, mul_rn<T>(cn, X(i + sa.nx)));
         if (sa.nz > 1 && iz < sa.nz - 1) sum = add_rn<T>(sum, mul_rn<T>(cu, X(i + plane)));
         if (shifted) sum = fma(a0, __ldg(x + i), a1 * sum);
+        return sum;
+    };
+    auto finish = [&](int64_t i, T sum, T xi) {
         y[i] = sum;
         if (vout) vout[i] = xi;
         if (want_dot) {
             const T dv = fz.dot_self ? xi : __ldg(dotv + i);
             dacc = fma(dv, dsub ? fma(-dsc, __ldg(dsub + i), sum) : sum, dacc);
         }
+    };
+    // two grid-strided rows per trip, both evaluated before either is stored (twice the loads in flight per thread;
+    // the order in which a thread visits its rows — and with it the fused dot product — is unchanged)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < sa.n_rows; i += 2 * stride) {
+        const int64_t i2 = i + stride;
+        const bool two = i2 < sa.n_rows;
+        T xa, xb = (T)0;
+        const T sa_ = row(i, xa);
+        const T sb_ = two ? row(i2, xb) : (T)0;
+        finish(i, sa_, xa);
+        if (two) finish(i2, sb_, xb);
     }
     if (want_dot) {
         const double sblk = block_sum((double)dacc, red);
@@ -1340,9 +1390,9 @@ extern "C" int32_t b2k_debug_set_spmv_variant(int32_t v) {
 // opt in to > 48 KB dynamic shared memory for the pipelined SpMV (called per context)
 int32_t b2k_spmv_init(b2k_ctx* ctx) {
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmm_pipe<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SppLayout<double>::SMEM));
+                                       SpmLayout<double>::SMEM));
     B2K_CUDA(ctx, cudaFuncSetAttribute(k_spmm_pipe<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SppLayout<float>::SMEM));
+                                       SpmLayout<float>::SMEM));
     B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<double, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SppLayout<double, 3>::SMEM));
     B2K_CUDA(ctx, cudaFuncSetAttribute((k_spmv_pipe<float, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1602,11 +1652,11 @@ extern "C" int32_t b2k_op_apply_block(b2k_ctx* ctx, const b2k_op* op, const b2k_
         const int pr = b2k_prof_begin(ctx, 7, (double)op->nnz * (ctx->esize + 4) + 4.0 * (op->n_rows + 1) +
                                                   2.0 * np * ctx->esize * op->n_rows);
         if (ctx->dtype == B2K_F64)
-            k_spmm_pipe<double><<<grid, SPP_THREADS, SppLayout<double>::SMEM, ctx->stream>>>(
+            k_spmm_pipe<double><<<grid, SPP_THREADS, SpmLayout<double>::SMEM, ctx->stream>>>(
                 op->rowptr, op->colidx, (const double*)op->vals, (double*)sp.base, sp.ld, cols, np, op->rowblk,
                 op->pblk, op->nblk);
         else
-            k_spmm_pipe<float><<<grid, SPP_THREADS, SppLayout<float>::SMEM, ctx->stream>>>(
+            k_spmm_pipe<float><<<grid, SPP_THREADS, SpmLayout<float>::SMEM, ctx->stream>>>(
                 op->rowptr, op->colidx, (const float*)op->vals, (float*)sp.base, sp.ld, cols, np, op->rowblk,
                 op->pblk, op->nblk);
         b2k_prof_end(ctx, pr);
