@@ -262,6 +262,23 @@ k_block_finalize(const double* __restrict__ part, int G, int stride, int rows, i
 // 128-bit streaming accesses with all loads of a trip ahead of its stores; optionally the Gram matrix of the
 // RESULT (per-CTA partials in the k_block_phase<UPDATE> layout), which is the second round's input — CholeskyQR2
 // costs two passes over the block instead of three.
+template <typename T> __device__ __forceinline__ void ld_vec(const T* p, T (&v)[16 / sizeof(T)]);
+template <> __device__ __forceinline__ void ld_vec<double>(const double* p, double (&v)[2]) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void ld_vec<float>(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <typename T> __device__ __forceinline__ void st_vec(T* p, const T (&v)[16 / sizeof(T)]);
+template <> __device__ __forceinline__ void st_vec<double>(double* p, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void st_vec<float>(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 struct RmulParams {
     void* base;
     int64_t ld, n;
@@ -282,39 +299,58 @@ k_block_rmul(const __grid_constant__ RmulParams rp) {
     T g[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) g[t] = (T)0;
+    // thread <-> VEC consecutive rows (one 128-bit access per column); the products are formed in place, last
+    // output column first (out_j needs x_0..x_j only), to keep the kernel at 4 CTAs per SM
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int64_t nv = rp.n / VEC;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t r0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r0 < rp.n; r0 += 2 * stride) {
-        const int64_t r1 = r0 + stride;
-        const bool two = r1 < rp.n;
-        T x0[P], x1[P];
+    for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < nv; v0 += stride) {
+        T x[P][VEC];
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-            x0[i] = col[i][r0];
-            x1[i] = two ? col[i][r1] : (T)0;
-        }
-        T o0[P], o1[P];
+        for (int i = 0; i < P; ++i) ld_vec<T>(col[i] + v0 * VEC, x[i]);
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            T a0 = (T)0, a1 = (T)0;
+        for (int j = P - 1; j >= 0; --j) {
 #pragma unroll
-            for (int i = 0; i <= j; ++i) {
-                const T u = (T)rp.u[j * P + i];
-                a0 = fma(x0[i], u, a0);
-                a1 = fma(x1[i], u, a1);
+            for (int e = 0; e < VEC; ++e) {
+                T a = (T)0;
+#pragma unroll
+                for (int i = 0; i <= j; ++i) a = fma(x[i][e], (T)rp.u[j * P + i], a);
+                x[j][e] = a;
             }
-            o0[j] = a0; o1[j] = a1;
         }
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            col[j][r0] = o0[j];
-            if (two) col[j][r1] = o1[j];
+        for (int j = 0; j < P; ++j) st_vec<T>(col[j] + v0 * VEC, x[j]);
+        if (rp.gpart) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                int t = 0;
+#pragma unroll
+                for (int a = 0; a < P; ++a)
+#pragma unroll
+                    for (int b = a; b < P; ++b) { g[t] = fma(x[a][e], x[b][e], g[t]); ++t; }
+            }
         }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < rp.n - nv * VEC) {      // tail rows
+        const int64_t r = nv * VEC + threadIdx.x;
+        T x[P], o[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) x[i] = col[i][r];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            T a = (T)0;
+#pragma unroll
+            for (int i = 0; i <= j; ++i) a = fma(x[i], (T)rp.u[j * P + i], a);
+            o[j] = a;
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) col[j][r] = o[j];
         if (rp.gpart) {
             int t = 0;
 #pragma unroll
             for (int a = 0; a < P; ++a)
 #pragma unroll
-                for (int b = a; b < P; ++b) { g[t] = fma(o0[a], o0[b], g[t]); g[t] = fma(o1[a], o1[b], g[t]); ++t; }
+                for (int b = a; b < P; ++b) { g[t] = fma(o[a], o[b], g[t]); ++t; }
         }
     }
     if (!rp.gpart) return;
