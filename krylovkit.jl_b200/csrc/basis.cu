@@ -921,6 +921,11 @@ int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res
         Pin(b2k_ctx* c_, const VecRef& v_, bool on_) : c(c_), v(v_), on(on_) { if (on) mgs_pin_vector(c, v, true); }
         ~Pin() { if (on) mgs_pin_vector(c, v, false); }
     } pin(ctx, v, k >= 4);
+    struct Hints {     // without a set-aside the vector is kept L2-resident by eviction-priority hints instead
+        b2k_ctx* c;
+        explicit Hints(b2k_ctx* c_, bool on) : c(c_) { c->dot_hints = (on && g_l2_hints) ? 1 : 0; }
+        ~Hints() { c->dot_hints = 0; }
+    } hints(ctx, k >= 4);
     for (int j = 0; j < k; ++j) {
         const char* qj = (const char*)pn.base + (size_t)pn.idx[j] * pn.ld * es;
         const char* qp = j > 0 ? (const char*)pn.base + (size_t)pn.idx[j - 1] * pn.ld * es : nullptr;

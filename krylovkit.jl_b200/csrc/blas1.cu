@@ -60,6 +60,24 @@ template <> __device__ __forceinline__ void vstore<float>(float* p, const float 
     _Pragma("unroll") for (int u = 0; u < (UN); ++u)                                                   \
         if (const int64_t i = i0 + (int64_t)u * stride; i < nv)
 
+// 128-bit accesses with an L2 eviction-priority hint (createpolicy policies, see common.cuh)
+template <typename T> __device__ __forceinline__ void vload_hint(const T* p, T (&v)[Vec16<T>::N], uint64_t pol);
+template <> __device__ __forceinline__ void vload_hint<double>(const double* p, double (&v)[2], uint64_t pol) {
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol));
+}
+template <> __device__ __forceinline__ void vload_hint<float>(const float* p, float (&v)[4], uint64_t pol) {
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(pol));
+}
+template <typename T> __device__ __forceinline__ void vstore_hint(T* p, const T (&v)[Vec16<T>::N], uint64_t pol);
+template <> __device__ __forceinline__ void vstore_hint<double>(double* p, const double (&v)[2], uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v[0]), "d"(v[1]), "l"(pol) : "memory");
+}
+template <> __device__ __forceinline__ void vstore_hint<float>(float* p, const float (&v)[4], uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "l"(pol) : "memory");
+}
+
 inline int grid_for(const b2k_ctx* ctx, int64_t n, int per_thread) {
     int64_t want = (n + (int64_t)BT * per_thread - 1) / ((int64_t)BT * per_thread);
     int64_t cap = (int64_t)ctx->num_sms * CTAS_PER_SM;
@@ -202,9 +220,12 @@ template <typename T, bool UPDATE, bool NORM>
 __global__ void __launch_bounds__(BT)
 k_dot(const T* __restrict__ q, T* __restrict__ x, int64_t n, const T* __restrict__ qprev,
       const double* __restrict__ sprev, double* __restrict__ part, unsigned* __restrict__ ticket,
-      double* __restrict__ out, double* __restrict__ accum_into) {
+      double* __restrict__ out, double* __restrict__ accum_into, int hints) {
     __shared__ double red[32];
     __shared__ bool last;
+    // hints (the MGS sweep): x is re-read and re-written once per basis column — keep it in L2 (evict_last);
+    // the basis columns pass once (evict_first)
+    const uint64_t pol_keep = hints ? l2_policy_evict_last() : 0, pol_once = hints ? l2_policy_evict_first() : 0;
     constexpr int V = Vec16<T>::N;
     const int64_t nv = n / V;
     const int64_t stride = (int64_t)gridDim.x * BT;
@@ -213,16 +234,25 @@ k_dot(const T* __restrict__ q, T* __restrict__ x, int64_t n, const T* __restrict
     T acc = 0;
     B2K_TRIP(4) {
         T a[4][V], b[4][V], c[4][V];
-        B2K_EACH(4, u, i) {
-            vload<T>(x + i * V, b[u]);
-            if (UPDATE) vload<T>(qprev + i * V, c[u]);
-            if (!NORM) vload<T>(q + i * V, a[u]);
+        if (hints) {
+            B2K_EACH(4, u, i) {
+                vload_hint<T>(x + i * V, b[u], pol_keep);
+                if (UPDATE) vload_hint<T>(qprev + i * V, c[u], pol_once);
+                if (!NORM) vload_hint<T>(q + i * V, a[u], pol_once);
+            }
+        } else {
+            B2K_EACH(4, u, i) {
+                vload<T>(x + i * V, b[u]);
+                if (UPDATE) vload<T>(qprev + i * V, c[u]);
+                if (!NORM) vload<T>(q + i * V, a[u]);
+            }
         }
         B2K_EACH(4, u, i) {
             if (UPDATE) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) b[u][j] = fma(-sp, c[u][j], b[u][j]);
-                vstore<T>(x + i * V, b[u]);
+                if (hints) vstore_hint<T>(x + i * V, b[u], pol_keep);
+                else vstore<T>(x + i * V, b[u]);
             }
             if (NORM) {
 #pragma unroll
@@ -589,7 +619,7 @@ int32_t b2k_enqueue_dot(b2k_ctx* ctx, const void* q, void* x, int64_t n, const v
     unsigned* ticket = ctx->d_sync;
 #define LAUNCH(T, UPD, NRM)                                                              \
     k_dot<T, UPD, NRM><<<grid, BT, 0, ctx->stream>>>((const T*)q, (T*)x, n, (const T*)qprev, \
-                                                     sp, ctx->d_part_s, ticket, out, acc)
+                                                     sp, ctx->d_part_s, ticket, out, acc, ctx->dot_hints)
     const bool upd = qprev != nullptr, nrm = q == nullptr;
     if (ctx->dtype == B2K_F64) {
         if (upd && nrm) LAUNCH(double, true, true);

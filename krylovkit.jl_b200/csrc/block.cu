@@ -84,7 +84,9 @@ __device__ __forceinline__ const T* tile_col(uint8_t* smem, uint32_t s0, int j) 
     return reinterpret_cast<const T*>(smem + OFF_RING + s * SLOT_BYTES) + (j % C) * R;
 }
 
-template <typename T, bool UPDATE>
+// PP = 4 or 8: register block of the block dimension (p <= PP); p <= 4 halves the broadcast loads of H and the
+// accumulators
+template <typename T, bool UPDATE, int PP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ ColList cl) {
     using CF = Cfg<T>;
@@ -105,11 +107,11 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
     uint32_t s = 0, ph = 0;
     if (!UPDATE) {
         // ---- PROJECT: warp w owns basis columns j = w, w + 8, ...; lane <-> rows (128-bit LDS)
-        T acc[BK_JW][BK_PMAX];
+        T acc[BK_JW][PP];
 #pragma unroll
         for (int a = 0; a < BK_JW; ++a)
 #pragma unroll
-            for (int i = 0; i < BK_PMAX; ++i) acc[a][i] = (T)0;
+            for (int i = 0; i < PP; ++i) acc[a][i] = (T)0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t r0 = tile * R;
             const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
@@ -118,30 +120,35 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
                 mbar_wait(sm.full + 8 * s, ph);
                 if (++s == NS) { s = 0; ph ^= 1; }
             }
+            const T* qc[BK_JW];
+            const T* rc[PP];
 #pragma unroll
-            for (int a = 0; a < BK_JW; ++a) {
-                const int j = a * 8 + w;
-                if (j < p.kq) {
-                    const T* qc = tile_col<T>(smem, s0, j);
-                    // rows >= rt of a ragged last tile hold stale but FINITE data (an earlier tile or the zeroed
-                    // ring): masking the block side below is enough
-                    V16 q[NLD];
+            for (int a = 0; a < BK_JW; ++a) qc[a] = tile_col<T>(smem, s0, (a * 8 + w < p.kq) ? a * 8 + w : 0);
 #pragma unroll
-                    for (int u = 0; u < NLD; ++u) q[u] = *reinterpret_cast<const V16*>(qc + VEC * lane + 32 * VEC * u);
+            for (int i = 0; i < PP; ++i) rc[i] = tile_col<T>(smem, s0, p.kq + (i < p.p ? i : 0));
+            // one row chunk at a time: the p block columns are read once per chunk and feed every basis column of
+            // this warp (they were re-read per basis column before: 88 % LSU utilisation at k = 20, p = 4).
+            // Rows >= rt of a ragged last tile hold stale but FINITE data: masking the block side is enough.
 #pragma unroll
-                    for (int i = 0; i < BK_PMAX; ++i) {
-                        if (i < p.p) {
-                            const T* rc = tile_col<T>(smem, s0, p.kq + i);
+            for (int u = 0; u < NLD; ++u) {
+                V16 x[PP];
 #pragma unroll
-                            for (int u = 0; u < NLD; ++u) {
-                                V16 x = *reinterpret_cast<const V16*>(rc + VEC * lane + 32 * VEC * u);
-                                T* xe = reinterpret_cast<T*>(&x);
+                for (int i = 0; i < PP; ++i) {
+                    if (i < p.p) {
+                        x[i] = *reinterpret_cast<const V16*>(rc[i] + VEC * lane + 32 * VEC * u);
+                        T* xe = reinterpret_cast<T*>(&x[i]);
 #pragma unroll
-                                for (int e = 0; e < VEC; ++e)
-                                    if (VEC * lane + 32 * VEC * u + e >= rt) xe[e] = (T)0;
-                                VecOps<T>::fma_acc(acc[a][i], q[u], x);
-                            }
-                        }
+                        for (int e = 0; e < VEC; ++e)
+                            if (VEC * lane + 32 * VEC * u + e >= rt) xe[e] = (T)0;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < BK_JW; ++a) {
+                    if (a * 8 + w < p.kq) {
+                        const V16 q = *reinterpret_cast<const V16*>(qc[a] + VEC * lane + 32 * VEC * u);
+#pragma unroll
+                        for (int i = 0; i < PP; ++i)
+                            if (i < p.p) VecOps<T>::fma_acc(acc[a][i], q, x[i]);
                     }
                 }
             }
@@ -157,7 +164,7 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
         for (int a = 0; a < BK_JW; ++a) {
             const int j = a * 8 + w;
 #pragma unroll
-            for (int i = 0; i < BK_PMAX; ++i) {
+            for (int i = 0; i < PP; ++i) {
                 const double v = warp_sum((double)acc[a][i]);
                 if (j < p.kq && i < p.p && lane == 0)
                     p.part[(size_t)blockIdx.x * BK_PART + i * BK_QMAX + j] = v;
@@ -168,14 +175,14 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
     // ---- UPDATE: thread <-> row; r_i -= sum_j q_j H[j][i] (sequential fma over j: the association of the
     // reference's chain of add!! calls), then the Gram matrix of the updated block
     T* Hs = reinterpret_cast<T*>(smem + BK_OFF_H);
-    for (int idx = tid; idx < p.kq * BK_PMAX; idx += NCONS) {
-        const int j = idx / BK_PMAX, i = idx - j * BK_PMAX;
+    for (int idx = tid; idx < p.kq * PP; idx += NCONS) {
+        const int j = idx / PP, i = idx - j * PP;
         Hs[idx] = (i < p.p) ? p.alpha * (T)p.H[(size_t)i * p.ldh + j] : (T)0;
     }
     named_bar_sync(1, NCONS);
-    T g[BK_PMAX * (BK_PMAX + 1) / 2];
+    T g[PP * (PP + 1) / 2];
 #pragma unroll
-    for (int t = 0; t < BK_PMAX * (BK_PMAX + 1) / 2; ++t) g[t] = (T)0;
+    for (int t = 0; t < PP * (PP + 1) / 2; ++t) g[t] = (T)0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * R;
         const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
@@ -184,26 +191,26 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
             mbar_wait(sm.full + 8 * s, ph);
             if (++s == NS) { s = 0; ph ^= 1; }
         }
-        T r[BK_PMAX];
+        T r[PP];
 #pragma unroll
-        for (int i = 0; i < BK_PMAX; ++i) r[i] = (i < p.p && tid < rt) ? tile_col<T>(smem, s0, p.kq + i)[tid] : (T)0;
+        for (int i = 0; i < PP; ++i) r[i] = (i < p.p && tid < rt) ? tile_col<T>(smem, s0, p.kq + i)[tid] : (T)0;
         for (int j = 0; j < p.kq; ++j) {
             const T q = (tid < rt) ? tile_col<T>(smem, s0, j)[tid] : (T)0;
-            const T* h = Hs + j * BK_PMAX;
+            const T* h = Hs + j * PP;
 #pragma unroll
-            for (int i = 0; i < BK_PMAX; ++i) r[i] = fma(q, h[i], r[i]);
+            for (int i = 0; i < PP; ++i) r[i] = fma(q, h[i], r[i]);
         }
         if (p.store && tid < rt) {
 #pragma unroll
-            for (int i = 0; i < BK_PMAX; ++i)
+            for (int i = 0; i < PP; ++i)
                 if (i < p.p) const_cast<T*>(p.base)[(int64_t)cl.c[p.kq + i] * p.ld + r0 + tid] = r[i];
         }
         if (p.gpart) {
             int t = 0;
 #pragma unroll
-            for (int i1 = 0; i1 < BK_PMAX; ++i1)
+            for (int i1 = 0; i1 < PP; ++i1)
 #pragma unroll
-                for (int i2 = i1; i2 < BK_PMAX; ++i2) { g[t] = fma(r[i1], r[i2], g[t]); ++t; }
+                for (int i2 = i1; i2 < PP; ++i2) { g[t] = fma(r[i1], r[i2], g[t]); ++t; }
         }
         __syncwarp();
         uint32_t ss = s0;
@@ -214,7 +221,7 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
     }
     if (p.gpart) {
         double* red = reinterpret_cast<double*>(smem + BK_OFF_G);      // [8 warps][36]
-        constexpr int NT = BK_PMAX * (BK_PMAX + 1) / 2;
+        constexpr int NT = PP * (PP + 1) / 2;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             const double v = warp_sum((double)g[t]);
@@ -226,7 +233,7 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
             for (int ww = 0; ww < NCONS / 32; ++ww) a += red[ww * NT + tid];
             // unpack t -> (i1, i2)
             int i1 = 0, t = tid;
-            while (t >= BK_PMAX - i1) { t -= BK_PMAX - i1; ++i1; }
+            while (t >= PP - i1) { t -= PP - i1; ++i1; }
             const int i2 = i1 + t;
             p.gpart[(size_t)blockIdx.x * BK_GRAM + i1 * BK_PMAX + i2] = a;
             p.gpart[(size_t)blockIdx.x * BK_GRAM + i2 * BK_PMAX + i1] = a;
@@ -415,7 +422,8 @@ int32_t launch_project(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, double* d
     bpar.part = ctx->d_blkpart;
     const int grid = grid_rows(ctx, bp.n);
     const int pr = b2k_prof_begin(ctx, 5, (double)(kq + p) * sizeof(T) * (double)bp.n);
-    k_block_phase<T, false><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    if (p <= 4) k_block_phase<T, false, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    else k_block_phase<T, false, 8><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     k_block_finalize<<<1, 256, 0, ctx->stream>>>(ctx->d_blkpart, grid, BK_PART, kq, p, BK_QMAX, d_H + q0, ldh,
@@ -439,7 +447,8 @@ int32_t launch_update(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, const doub
     bpar.store = store ? 1 : 0;
     const int grid = grid_rows(ctx, bp.n);
     const int pr = b2k_prof_begin(ctx, 6, (double)(kq + (store ? 2 : 1) * p) * sizeof(T) * (double)bp.n);
-    k_block_phase<T, true><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    if (p <= 4) k_block_phase<T, true, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    else k_block_phase<T, true, 8><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     if (d_G) {
@@ -528,10 +537,11 @@ bool b2k_block_kernels_enabled() { return g_block_kernels; }
 
 int32_t b2k_block_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_BLOCK_KERNELS")) g_block_kernels = e[0] != '0';
-    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    B2K_CUDA(ctx, cudaFuncSetAttribute(k_block_phase<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define BK_ATTR(T, U, PP) \
+    B2K_CUDA(ctx, cudaFuncSetAttribute((k_block_phase<T, U, PP>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))
+    BK_ATTR(double, false, 4); BK_ATTR(double, false, 8); BK_ATTR(double, true, 4); BK_ATTR(double, true, 8);
+    BK_ATTR(float, false, 4); BK_ATTR(float, false, 8); BK_ATTR(float, true, 4); BK_ATTR(float, true, 8);
+#undef BK_ATTR
     return B2K_OK;
 }
 

@@ -54,6 +54,7 @@ struct b2k_ctx {
     int32_t esize  = 8;
     int32_t num_sms = 0;
     size_t  l2_persist_bytes = 0;   // persisting-L2 carve-out (0 = unavailable)
+    int     dot_hints = 0;          // set by the MGS sweep: its k_dot launches carry L2 eviction-priority hints
     size_t  l2_window_max = 0;      // max access-policy window
     cudaStream_t stream = nullptr;
     std::vector<B2kSpace> spaces;

@@ -218,9 +218,20 @@ static int32_t ctx_create_common(b2k_ctx** out, int32_t device, int64_t n_local,
         fprintf(stderr, "[b200krylov] warning: device %s is sm_%d%d; this library is built for "
                         "sm_100a only\n", prop.name, prop.major, prop.minor);
     ctx->num_sms = prop.multiProcessorCount;
-    if (prop.persistingL2CacheMaxSize > 0 &&
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
-        ctx->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+    // No persisting-L2 set-aside by default.  Round 1 reserved the device maximum (83 of 133 MB) for the access-policy
+    // window that pins the MGS sweep's vector; measured in round 2 (gpurun_out/r02o_*): with that set-aside in place
+    // every plain streaming kernel of the process runs at 2.7-3.0 instead of 6.2 TB/s (80 MB vectors; probe and
+    // library alike), CG at 2 400 instead of 3 750 it/s.  Residency is now requested per access with L2
+    // eviction-priority hints, which need no set-aside.  B2K_L2_CARVE=<bytes> restores it (and the window).
+    size_t carve = 0;
+    if (const char* e = getenv("B2K_L2_CARVE"))
+        carve = std::min((size_t)(prop.persistingL2CacheMaxSize > 0 ? prop.persistingL2CacheMaxSize : 0),
+                         (size_t)strtoull(e, nullptr, 10));
+    if (carve == 0) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);      // another library in the process may have set one
+        cudaGetLastError();
+    } else if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+        ctx->l2_persist_bytes = carve;
         ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     } else {
         cudaGetLastError();

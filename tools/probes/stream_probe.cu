@@ -101,6 +101,12 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dptr, 6 * sizeof(double*)));
     CK(cudaMemcpy(dptr, buf, 6 * sizeof(double*), cudaMemcpyHostToDevice));
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (argc > 3) {                                           // persisting-L2 set-aside, like the library's contexts
+        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+        const size_t want = (size_t)atol(argv[3]) < (size_t)prop.persistingL2CacheMaxSize ? (size_t)atol(argv[3]) : (size_t)prop.persistingL2CacheMaxSize;
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        printf("persisting L2 set-aside %zu bytes (device max %d, L2 %d)\n", want, prop.persistingL2CacheMaxSize, prop.l2CacheSize);
+    }
     // warm the clocks
     timeit([&]() { k_persist<1, 1, 4><<<sms * 4, 256>>>(dptr, (const double* const*)(dptr + 2), nv, 0.0); }, 30);
 #define RUN(NR, NW, name, launch) { float ms = timeit([&]() { launch; }, 10); printf("%-46s %8.1f us  %7.1f GB/s\n", name, ms * 1e3, (NR + 2.0 * NW) * n * 8 / ms / 1e6); }
