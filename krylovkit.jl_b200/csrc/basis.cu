@@ -511,6 +511,155 @@ k_transform_dmma(const __grid_constant__ TransformParams p, const __grid_constan
     }
 }
 
+// Hybrid restart GEMM: DMMA and DFMA at once.  k_transform_dmma saturates the XU pipe `DMMA.8x8x4` issues through
+// (30 FMA/clk/SM, profiles/r02_transform_pipes.md) while the DFMA pipe idles; a DFMA-only kernel is bound by the
+// shared-memory broadcast of U (2 LSU cycles per double).  Here every consumer warp does both per staged chunk: output
+// columns [0, 24) as three 8-column DMMA blocks for its 32 rows (14 smem wavefronts per 3072 FMA), columns [24, 36) as
+// register-blocked DFMA — warp <-> 64 rows x 6 columns, lane <-> 2 rows, 12 accumulators, 16 wavefronts per 384 FMA.
+// Budget per 256-row tile (60 -> 36): DMMA 12 300 clk, DFMA 2 900 clk/SMSP, LSU 9 400 wavefronts, HBM 8 500 clk.
+// keep <= 36 only (one pass, chunks consumed and released as they land); wider restarts use k_transform_dmma.
+constexpr int TH_DCB = 3;                                 // DMMA column blocks: columns [0, 24)
+constexpr int TH_DF0 = 8 * TH_DCB;                        // first DFMA column
+constexpr int TH_DFW = 6;                                 // DFMA columns per warp (two warp groups: 12 columns)
+constexpr int TH_MAXKEEP = TH_DF0 + 2 * TH_DFW;           // 36
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+k_transform_hyb(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
+    constexpr int R = 256, C = 8;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full = smem_u32(smem + TD_OFF_BAR), empty = full + NS * 8;
+    double* Us = reinterpret_cast<double*>(smem + TD_OFF_U);
+    constexpr int pitch = 40;                             // U rows zero-padded to 40 columns
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, NCONS / 32);
+        }
+        fence_mbar_init();
+    }
+    for (int idx = threadIdx.x; idx < p.m * pitch; idx += blockDim.x) {
+        const int i = idx / pitch, j = idx - i * pitch;
+        Us[idx] = (j < p.keep) ? p.U[(size_t)j * p.ldu + i] : 0.0;
+    }
+    __syncthreads();
+    const int nch = (p.m + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    double* base = reinterpret_cast<double*>(p.base);
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= NCONS) {
+        const int lane = threadIdx.x & 31;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(empty + 8 * s, ph ^ 1);
+                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+                if (lane == 0) mbar_expect_tx(full + 8 * s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(ring + s * TD_SLOT + lane * TD_PITCH * 8,
+                             base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes, full + 8 * s);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ncb = ((p.keep + 7) / 8) < TH_DCB ? ((p.keep + 7) / 8) : TH_DCB;
+    const int frow = 64 * (w & 3) + lane;                 // DFMA rows frow, frow + 32
+    const int fcol = TH_DF0 + TH_DFW * (w >> 2);          // DFMA columns fcol .. fcol + 5
+    const bool df_on = fcol < p.keep;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        double acc[4][TH_DCB][2];
+        double fa[2][TH_DFW];
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+            for (int cb = 0; cb < TH_DCB; ++cb) { acc[rb][cb][0] = 0.0; acc[rb][cb][1] = 0.0; }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int u = 0; u < TH_DFW; ++u) fa[e][u] = 0.0;
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(full + 8 * s, ph);
+            const double* slot = reinterpret_cast<const double*>(smem + s * TD_SLOT);
+            const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int k0 = ks * 4;
+                if (k0 < ncol) {
+                    const bool kv = (k0 + t) < ncol;          // tail of the last chunk: zero operands
+                    double a[4], b[TH_DCB];
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) {
+                        const int row = 32 * w + 8 * rb + g;
+                        a[rb] = (kv && row < rt) ? slot[(k0 + t) * TD_PITCH + row] : 0.0;   // stale rows: zero
+                    }
+                    const double* urow = Us + (size_t)(c * C + k0 + t) * pitch + g;
+#pragma unroll
+                    for (int cb = 0; cb < TH_DCB; ++cb) b[cb] = (kv && cb < ncb) ? urow[cb * 8] : 0.0;
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                        for (int cb = 0; cb < TH_DCB; ++cb)
+                            if (cb < ncb) dmma884(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
+                    // the DFMA share of the same four basis vectors (sums over i in increasing order)
+                    if (df_on) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (k0 + kk < ncol) {
+                                const double q0 = slot[(k0 + kk) * TD_PITCH + frow];
+                                const double q1 = slot[(k0 + kk) * TD_PITCH + frow + 32];
+                                const double2* uf = reinterpret_cast<const double2*>(
+                                    Us + (size_t)(c * C + k0 + kk) * pitch + fcol);
+#pragma unroll
+                                for (int u = 0; u < TH_DFW / 2; ++u) {
+                                    const double2 uu = uf[u];
+                                    fa[0][2 * u] = fma(q0, uu.x, fa[0][2 * u]);
+                                    fa[1][2 * u] = fma(q1, uu.x, fa[1][2 * u]);
+                                    fa[0][2 * u + 1] = fma(q0, uu.y, fa[0][2 * u + 1]);
+                                    fa[1][2 * u + 1] = fma(q1, uu.y, fa[1][2 * u + 1]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * s);
+            if (++s == NS) { s = 0; ph ^= 1; }
+        }
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+            const int row = 32 * w + 8 * rb + g;
+#pragma unroll
+            for (int cb = 0; cb < TH_DCB; ++cb) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = cb * 8 + 2 * t + e;
+                    if (cb < ncb && col < p.keep && row < rt)
+                        base[(int64_t)cl.c[col] * p.ld + r0 + row] = acc[rb][cb][e];
+                }
+            }
+        }
+        if (df_on) {
+#pragma unroll
+            for (int u = 0; u < TH_DFW; ++u) {
+                if (fcol + u < p.keep) {
+                    double* col = base + (int64_t)cl.c[fcol + u] * p.ld + r0;
+                    if (frow < rt) col[frow] = fa[0][u];
+                    if (frow + 32 < rt) col[frow + 32] = fa[1][u];
+                }
+            }
+        }
+    }
+}
+
 // FP64 restart GEMM on the DFMA pipe with U in the constant bank.  `DMMA.8x8x4` issues through the XU pipe on
 // B200 and saturates it at ~30 FMA/clk/SM (profiles/r02_transform_pipes.md); the DFMA pipe is ~2.5x faster but the
 // FMA kernel above starved it on the shared-memory broadcast of U (two wavefronts per double).  Here U travels as
@@ -888,6 +1037,7 @@ bool fused_ok(const b2k_ctx* ctx, int k, int sharded, int dtype) {
 bool g_use_coop = true;
 bool g_use_dmma = true;
 int g_transform_ur = 0;      // B2K_TRANSFORM_UR: 0 = DMMA kernel, 1 = <2 rows x 18>, 2 = <2 x 36>, 3 = <4 x 18> (DFMA, U in the constant bank)
+int g_transform_hyb = 0;     // B2K_TRANSFORM_HYB=1: DMMA + DFMA hybrid for keep <= 36 (k_transform_hyb)
 
 // modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
 // s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
@@ -947,6 +1097,7 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_L2_HINTS")) g_l2_hints = e[0] != '0';
     if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '1' ? 1 : 0;
     if (const char* e = getenv("B2K_TRANSFORM_UR")) g_transform_ur = (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+    if (const char* e = getenv("B2K_TRANSFORM_HYB")) g_transform_hyb = e[0] == '1' ? 1 : 0;
 #define SETATTR(fn, bytes) \
     B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
     SETATTR((k_phase<double, false, true>), SMEM_BYTES);
@@ -958,6 +1109,7 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR(k_gs_fused<double>, SMEM_BYTES);
     SETATTR(k_gs_fused<float>, SMEM_BYTES);
     SETATTR(k_transform_dmma, TD_SMEM);
+    SETATTR(k_transform_hyb, TD_SMEM);
     SETATTR((k_transform_ur<2, 18>), TR_SMEM);
     SETATTR((k_transform_ur<2, 36>), TR_SMEM);
     SETATTR((k_transform_ur<4, 18>), TR_SMEM);
@@ -979,6 +1131,7 @@ extern "C" int32_t b2k_debug_set_dmma(int32_t on) {
 // 0 = DMMA restart GEMM, 1..3 = the DFMA / constant-bank variants (k_transform_ur)
 extern "C" int32_t b2k_debug_set_transform(int32_t mode) {
     g_transform_ur = (mode >= 0 && mode <= 3) ? mode : 0;
+    g_transform_hyb = mode == 4 ? 1 : 0;                  // 4 = the DMMA + DFMA hybrid
     return B2K_OK;
 }
 
@@ -1698,6 +1851,8 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
         if (g_transform_ur == 1) k_transform_ur<2, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else if (g_transform_ur == 2) k_transform_ur<2, 36><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else k_transform_ur<4, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
+    } else if (dmma_ok && g_transform_hyb && keep <= TH_MAXKEEP && (size_t)m * 40 * 8 <= (size_t)TD_U_BYTES) {
+        k_transform_hyb<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
     } else if (dmma_ok) {
         k_transform_dmma<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
     } else if (f64) {

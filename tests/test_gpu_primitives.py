@@ -296,6 +296,32 @@ def test_basistransform_constant_bank_variants(n, m, keep, mode):
     np.testing.assert_array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("n,m,keep", [(70001, 60, 36), (5000, 30, 18), (257, 61, 35), (100003, 96, 36), (999, 5, 1),
+                                      (4096, 40, 25), (3001, 59, 31), (777, 36, 36)])
+def test_basistransform_hybrid_dmma_dfma(n, m, keep):
+    """k_transform_hyb (output columns [0, 24) on the FP64 tensor pipe, [24, 36) as register-blocked DFMA, in the same
+    warps) against the dense product, ragged tiles and chunk tails included."""
+    lib = L.load()
+    rng = np.random.default_rng(7 * n + m)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    U, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    ref = Q @ U[:, :keep]
+    lib.b2k_debug_set_transform(4)
+    try:
+        ctx = kk.B200Context(n, m + 4)
+        vecs = ctx.empty_range(m)
+        for j, v in enumerate(vecs):
+            v.upload(Q[:, j])
+        b = kk.OrthonormalBasis(vecs)
+        kk.basistransform_(b, U[:, :keep])
+        out = np.column_stack([b[j].to_host() for j in range(m)])
+        np.testing.assert_allclose(out[:, :keep], ref, rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(out[:, keep:], Q[:, keep:])
+        ctx.close()
+    finally:
+        lib.b2k_debug_set_transform(0)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_givens_householder_rank1(dtype):
     """test/linalg.jl:27-44: Givens / Householder on a basis equal the dense result."""
