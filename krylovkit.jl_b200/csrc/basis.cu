@@ -511,6 +511,117 @@ k_transform_dmma(const __grid_constant__ TransformParams p, const __grid_constan
     }
 }
 
+// Pure-DFMA restart GEMM with an 8 x 9 register tile.  DMMA runs on the FP64 datapath at under half the DFMA rate
+// (k_transform_hyb, measured), so the only way below the DMMA kernel is DFMA fed fast enough.  The operand costs are
+// LSU cycles: a row value is an LDS.128 per two rows (2 cycles per double pair... 4 wavefronts per warp instruction), a
+// U value a broadcast (2 cycles per double).  thread <-> 8 rows x 9 outputs: 16 + 18 = 34 LSU cycles per 72 warp-DFMAs
+// (144 pipe cycles) and warp — four such warps, one per scheduler, put the LSU at 94 % and the FP64 pipe at its limit,
+// where k_transform's 2 x 18 tile spent 40 per 36.  U sits in shared memory as [group][i][10] (9 outputs + pad: 16-byte
+// aligned rows for the broadcast LDS.128).  keep <= 36: one pass, chunks consumed and released as they land.
+constexpr int F89_G = 4, F89_TH = 9, F89_UP = 10;         // column groups, outputs per group, padded row of U
+constexpr int F89_WARPS = 4;                              // consumer warps with work (256 rows / (32 lanes x 8 rows) x 4 groups)
+
+// 4 consumer warps + 1 producer warp = 160 threads: registers are granted per 4 warps, so 5 warps get the 255-register
+// ceiling the 72 accumulators need (the 9-warp kernels above are capped at 168)
+constexpr int F89_THREADS = 32 * (F89_WARPS + 1);
+__global__ void __launch_bounds__(F89_THREADS, 1)
+k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
+    constexpr int R = 256, C = 8;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full = smem_u32(smem + TR_OFF_BAR), empty = full + NS * 8;
+    double* Us = reinterpret_cast<double*>(smem + TR_OFF_U);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, F89_WARPS);
+        }
+        fence_mbar_init();
+    }
+    for (int idx = threadIdx.x; idx < F89_G * p.m * F89_UP; idx += blockDim.x) {
+        const int gq = idx / (p.m * F89_UP), rem = idx - gq * p.m * F89_UP;
+        const int i = rem / F89_UP, t = rem - i * F89_UP;
+        const int j = gq * F89_TH + t;
+        Us[idx] = (t < F89_TH && j < p.keep) ? p.U[(size_t)j * p.ldu + i] : 0.0;
+    }
+    __syncthreads();
+    const int nch = (p.m + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    double* base = reinterpret_cast<double*>(p.base);
+    uint32_t s = 0, ph = 0;
+    if (threadIdx.x >= 32 * F89_WARPS) {
+        const int lane = threadIdx.x & 31;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t r0 = tile * R;
+            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+            const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(empty + 8 * s, ph ^ 1);
+                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+                if (lane == 0) mbar_expect_tx(full + 8 * s, bytes * (uint32_t)ncol);
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(ring + s * SLOT_BYTES + lane * R * 8,
+                             base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes, full + 8 * s);
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;
+    const double* ug = Us + (size_t)cg * p.m * F89_UP;    // my group's U rows
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        double acc[8][F89_TH];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int t = 0; t < F89_TH; ++t) acc[e][t] = 0.0;
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(full + 8 * s, ph);
+            const double* slot = reinterpret_cast<const double*>(smem + s * SLOT_BYTES) + 2 * lane;
+            const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+            const double* urow = ug + (size_t)c * C * F89_UP;
+#pragma unroll 2
+            for (int jj = 0; jj < ncol; ++jj) {
+                double q[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {             // rows 2 lane, 2 lane + 1 (+ 64 e)
+                    const double2 v = *reinterpret_cast<const double2*>(slot + jj * R + 64 * e);
+                    q[2 * e] = v.x; q[2 * e + 1] = v.y;
+                }
+                double u[F89_UP];
+#pragma unroll
+                for (int t = 0; t < F89_UP; t += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(urow + jj * F89_UP + t);
+                    u[t] = v.x; u[t + 1] = v.y;
+                }
+#pragma unroll
+                for (int t = 0; t < F89_TH; ++t)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e][t] = fma(q[e], u[t], acc[e][t]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * s);
+            if (++s == NS) { s = 0; ph ^= 1; }
+        }
+#pragma unroll
+        for (int t = 0; t < F89_TH; ++t) {
+            const int j = cg * F89_TH + t;
+            if (j < p.keep) {
+                double* col = base + (int64_t)cl.c[j] * p.ld + r0 + 2 * lane;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 2 * lane + 64 * e;
+                    if (row + 1 < rt) *reinterpret_cast<double2*>(col + 64 * e) = make_double2(acc[2 * e][t], acc[2 * e + 1][t]);
+                    else if (row < rt) col[64 * e] = acc[2 * e][t];
+                }
+            }
+        }
+    }
+}
+
 // Hybrid restart GEMM: DMMA and DFMA at once.  k_transform_dmma saturates the XU pipe `DMMA.8x8x4` issues through
 // (30 FMA/clk/SM, profiles/r02_transform_pipes.md) while the DFMA pipe idles; a DFMA-only kernel is bound by the
 // shared-memory broadcast of U (2 LSU cycles per double).  Here every consumer warp does both per staged chunk: output
@@ -1037,7 +1148,7 @@ bool fused_ok(const b2k_ctx* ctx, int k, int sharded, int dtype) {
 bool g_use_coop = true;
 bool g_use_dmma = true;
 int g_transform_ur = 0;      // B2K_TRANSFORM_UR: 0 = DMMA kernel, 1 = <2 rows x 18>, 2 = <2 x 36>, 3 = <4 x 18> (DFMA, U in the constant bank)
-int g_transform_hyb = 0;     // B2K_TRANSFORM_HYB=1: DMMA + DFMA hybrid for keep <= 36 (k_transform_hyb)
+int g_transform_hyb = 0;     // B2K_TRANSFORM_HYB=1: DMMA + DFMA hybrid for keep <= 36 (k_transform_hyb); 2: DFMA 8 x 9 tile (k_transform_f89)
 
 // modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
 // s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
@@ -1097,7 +1208,7 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_L2_HINTS")) g_l2_hints = e[0] != '0';
     if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '1' ? 1 : 0;
     if (const char* e = getenv("B2K_TRANSFORM_UR")) g_transform_ur = (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
-    if (const char* e = getenv("B2K_TRANSFORM_HYB")) g_transform_hyb = e[0] == '1' ? 1 : 0;
+    if (const char* e = getenv("B2K_TRANSFORM_HYB")) g_transform_hyb = e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0);
 #define SETATTR(fn, bytes) \
     B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
     SETATTR((k_phase<double, false, true>), SMEM_BYTES);
@@ -1110,6 +1221,7 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR(k_gs_fused<float>, SMEM_BYTES);
     SETATTR(k_transform_dmma, TD_SMEM);
     SETATTR(k_transform_hyb, TD_SMEM);
+    SETATTR(k_transform_f89, TR_SMEM);
     SETATTR((k_transform_ur<2, 18>), TR_SMEM);
     SETATTR((k_transform_ur<2, 36>), TR_SMEM);
     SETATTR((k_transform_ur<4, 18>), TR_SMEM);
@@ -1131,7 +1243,7 @@ extern "C" int32_t b2k_debug_set_dmma(int32_t on) {
 // 0 = DMMA restart GEMM, 1..3 = the DFMA / constant-bank variants (k_transform_ur)
 extern "C" int32_t b2k_debug_set_transform(int32_t mode) {
     g_transform_ur = (mode >= 0 && mode <= 3) ? mode : 0;
-    g_transform_hyb = mode == 4 ? 1 : 0;                  // 4 = the DMMA + DFMA hybrid
+    g_transform_hyb = mode == 4 ? 1 : (mode == 5 ? 2 : 0);   // 4 = the DMMA + DFMA hybrid, 5 = the DFMA 8 x 9 tile
     return B2K_OK;
 }
 
@@ -1851,7 +1963,10 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
         if (g_transform_ur == 1) k_transform_ur<2, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else if (g_transform_ur == 2) k_transform_ur<2, 36><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else k_transform_ur<4, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
-    } else if (dmma_ok && g_transform_hyb && keep <= TH_MAXKEEP && (size_t)m * 40 * 8 <= (size_t)TD_U_BYTES) {
+    } else if (f64 && g_transform_hyb == 2 && keep <= F89_G * F89_TH &&
+               (size_t)F89_G * m * F89_UP * 8 <= (size_t)TR_U_BYTES) {
+        k_transform_f89<<<grid_for_rows<double>(ctx, pn.n), F89_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
+    } else if (dmma_ok && g_transform_hyb == 1 && keep <= TH_MAXKEEP && (size_t)m * 40 * 8 <= (size_t)TD_U_BYTES) {
         k_transform_hyb<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
     } else if (dmma_ok) {
         k_transform_dmma<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
