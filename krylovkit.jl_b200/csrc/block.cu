@@ -84,15 +84,72 @@ __device__ __forceinline__ const T* tile_col(uint8_t* smem, uint32_t s0, int j) 
     return reinterpret_cast<const T*>(smem + OFF_RING + s * SLOT_BYTES) + (j % C) * R;
 }
 
+// PROJECT work on one resident tile: warp w owns basis columns j = w, w + 8, ...; lane <-> rows (128-bit LDS).
+// One row chunk at a time: the p block columns are read once per chunk and feed every basis column of this warp
+// (they were re-read per basis column before: 88 % LSU utilisation at k = 20, p = 4).  Rows >= rt of a ragged last
+// tile hold stale but FINITE data: masking the block side is enough.
+template <typename T, int PP>
+__device__ __forceinline__ void block_project_tile(uint8_t* smem, uint32_t s0, int kq, int pb, int rt, int lane, int w,
+                                                   T (&acc)[BK_JW][PP]) {
+    using CF = Cfg<T>;
+    using V16 = typename CF::V16;
+    constexpr int R = CF::R, VEC = CF::VEC;
+    constexpr int NLD = R / (32 * VEC);
+    const T* qc[BK_JW];
+    const T* rc[PP];
+#pragma unroll
+    for (int a = 0; a < BK_JW; ++a) qc[a] = tile_col<T>(smem, s0, (a * 8 + w < kq) ? a * 8 + w : 0);
+#pragma unroll
+    for (int i = 0; i < PP; ++i) rc[i] = tile_col<T>(smem, s0, kq + (i < pb ? i : 0));
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+        V16 x[PP];
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+            if (i < pb) {
+                x[i] = *reinterpret_cast<const V16*>(rc[i] + VEC * lane + 32 * VEC * u);
+                T* xe = reinterpret_cast<T*>(&x[i]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    if (VEC * lane + 32 * VEC * u + e >= rt) xe[e] = (T)0;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < BK_JW; ++a) {
+            if (a * 8 + w < kq) {
+                const V16 q = *reinterpret_cast<const V16*>(qc[a] + VEC * lane + 32 * VEC * u);
+#pragma unroll
+                for (int i = 0; i < PP; ++i)
+                    if (i < pb) VecOps<T>::fma_acc(acc[a][i], q, x[i]);
+            }
+        }
+    }
+}
+
+// per-CTA partials of the projection: part[cta][i * BK_QMAX + j]
+template <typename T, int PP>
+__device__ __forceinline__ void block_project_partials(const T (&acc)[BK_JW][PP], double* part, int kq, int pb, int lane,
+                                                       int w) {
+#pragma unroll
+    for (int a = 0; a < BK_JW; ++a) {
+        const int j = a * 8 + w;
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+            const double v = warp_sum((double)acc[a][i]);
+            if (j < kq && i < pb && lane == 0) part[(size_t)blockIdx.x * BK_PART + i * BK_QMAX + j] = v;
+        }
+    }
+}
+
+// MODE 0: PROJECT, 1: UPDATE (+ Gram matrix of the result), 2: UPDATE followed by the PROJECT of the updated block on
+// the same resident tile (the middle sweep of BCGS2: three passes over V instead of four).
 // PP = 4 or 8: register block of the block dimension (p <= PP); p <= 4 halves the broadcast loads of H and the
 // accumulators
-template <typename T, bool UPDATE, int PP>
+template <typename T, int MODE, int PP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ ColList cl) {
     using CF = Cfg<T>;
-    using V16 = typename CF::V16;
-    constexpr int R = CF::R, C = CF::C, VEC = CF::VEC;
-    constexpr int NLD = R / (32 * VEC);
+    constexpr int R = CF::R, C = CF::C;
     extern __shared__ __align__(128) uint8_t smem[];
     SmemView sm(smem);
     pipe_setup(sm, true);     // ragged tiles multiply stale rows by nothing here, but keep the ring finite
@@ -105,8 +162,7 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
     }
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint32_t s = 0, ph = 0;
-    if (!UPDATE) {
-        // ---- PROJECT: warp w owns basis columns j = w, w + 8, ...; lane <-> rows (128-bit LDS)
+    if (MODE == 0) {
         T acc[BK_JW][PP];
 #pragma unroll
         for (int a = 0; a < BK_JW; ++a)
@@ -120,38 +176,7 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
                 mbar_wait(sm.full + 8 * s, ph);
                 if (++s == NS) { s = 0; ph ^= 1; }
             }
-            const T* qc[BK_JW];
-            const T* rc[PP];
-#pragma unroll
-            for (int a = 0; a < BK_JW; ++a) qc[a] = tile_col<T>(smem, s0, (a * 8 + w < p.kq) ? a * 8 + w : 0);
-#pragma unroll
-            for (int i = 0; i < PP; ++i) rc[i] = tile_col<T>(smem, s0, p.kq + (i < p.p ? i : 0));
-            // one row chunk at a time: the p block columns are read once per chunk and feed every basis column of
-            // this warp (they were re-read per basis column before: 88 % LSU utilisation at k = 20, p = 4).
-            // Rows >= rt of a ragged last tile hold stale but FINITE data: masking the block side is enough.
-#pragma unroll
-            for (int u = 0; u < NLD; ++u) {
-                V16 x[PP];
-#pragma unroll
-                for (int i = 0; i < PP; ++i) {
-                    if (i < p.p) {
-                        x[i] = *reinterpret_cast<const V16*>(rc[i] + VEC * lane + 32 * VEC * u);
-                        T* xe = reinterpret_cast<T*>(&x[i]);
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e)
-                            if (VEC * lane + 32 * VEC * u + e >= rt) xe[e] = (T)0;
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < BK_JW; ++a) {
-                    if (a * 8 + w < p.kq) {
-                        const V16 q = *reinterpret_cast<const V16*>(qc[a] + VEC * lane + 32 * VEC * u);
-#pragma unroll
-                        for (int i = 0; i < PP; ++i)
-                            if (i < p.p) VecOps<T>::fma_acc(acc[a][i], q, x[i]);
-                    }
-                }
-            }
+            block_project_tile<T, PP>(smem, s0, p.kq, p.p, rt, lane, w, acc);
             // release the tile
             __syncwarp();
             uint32_t ss = s0;
@@ -160,29 +185,27 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
                 if (++ss == NS) ss = 0;
             }
         }
-#pragma unroll
-        for (int a = 0; a < BK_JW; ++a) {
-            const int j = a * 8 + w;
-#pragma unroll
-            for (int i = 0; i < PP; ++i) {
-                const double v = warp_sum((double)acc[a][i]);
-                if (j < p.kq && i < p.p && lane == 0)
-                    p.part[(size_t)blockIdx.x * BK_PART + i * BK_QMAX + j] = v;
-            }
-        }
+        block_project_partials<T, PP>(acc, p.part, p.kq, p.p, lane, w);
         return;
     }
     // ---- UPDATE: thread <-> row; r_i -= sum_j q_j H[j][i] (sequential fma over j: the association of the
-    // reference's chain of add!! calls), then the Gram matrix of the updated block
+    // reference's chain of add!! calls), then the Gram matrix of the updated block (MODE 1) or its projection (MODE 2)
     T* Hs = reinterpret_cast<T*>(smem + BK_OFF_H);
     for (int idx = tid; idx < p.kq * PP; idx += NCONS) {
         const int j = idx / PP, i = idx - j * PP;
         Hs[idx] = (i < p.p) ? p.alpha * (T)p.H[(size_t)i * p.ldh + j] : (T)0;
     }
     named_bar_sync(1, NCONS);
-    T g[PP * (PP + 1) / 2];
+    constexpr int NG = (MODE == 1) ? PP * (PP + 1) / 2 : 1;
+    T g[NG];
 #pragma unroll
-    for (int t = 0; t < PP * (PP + 1) / 2; ++t) g[t] = (T)0;
+    for (int t = 0; t < NG; ++t) g[t] = (T)0;
+    constexpr int NA = (MODE == 2) ? BK_JW : 1;
+    T acc[NA][PP];
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int i = 0; i < PP; ++i) acc[a][i] = (T)0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * R;
         const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
@@ -205,12 +228,21 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
             for (int i = 0; i < PP; ++i)
                 if (i < p.p) const_cast<T*>(p.base)[(int64_t)cl.c[p.kq + i] * p.ld + r0 + tid] = r[i];
         }
-        if (p.gpart) {
+        if (MODE == 1 && p.gpart) {
             int t = 0;
 #pragma unroll
             for (int i1 = 0; i1 < PP; ++i1)
 #pragma unroll
                 for (int i2 = i1; i2 < PP; ++i2) { g[t] = fma(r[i1], r[i2], g[t]); ++t; }
+        }
+        if constexpr (MODE == 2) {
+            // the updated block replaces the staged one in the resident tile, then every warp projects it
+#pragma unroll
+            for (int i = 0; i < PP; ++i)
+                if (i < p.p) const_cast<T*>(tile_col<T>(smem, s0, p.kq + i))[tid] = r[i];
+            named_bar_sync(1, NCONS);
+            block_project_tile<T, PP>(smem, s0, p.kq, p.p, rt, lane, w, acc);
+            fence_proxy_async();      // generic-proxy writes to the slots precede their reuse by the TMA unit
         }
         __syncwarp();
         uint32_t ss = s0;
@@ -219,7 +251,8 @@ k_block_phase(const __grid_constant__ BlockParams<T> p, const __grid_constant__ 
             if (++ss == NS) ss = 0;
         }
     }
-    if (p.gpart) {
+    if constexpr (MODE == 2) block_project_partials<T, PP>(acc, p.part, p.kq, p.p, lane, w);
+    if (MODE == 1 && p.gpart) {
         double* red = reinterpret_cast<double*>(smem + BK_OFF_G);      // [8 warps][36]
         constexpr int NT = PP * (PP + 1) / 2;
 #pragma unroll
@@ -422,8 +455,8 @@ int32_t launch_project(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, double* d
     bpar.part = ctx->d_blkpart;
     const int grid = grid_rows(ctx, bp.n);
     const int pr = b2k_prof_begin(ctx, 5, (double)(kq + p) * sizeof(T) * (double)bp.n);
-    if (p <= 4) k_block_phase<T, false, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
-    else k_block_phase<T, false, 8><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    if (p <= 4) k_block_phase<T, 0, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    else k_block_phase<T, 0, 8><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     k_block_finalize<<<1, 256, 0, ctx->stream>>>(ctx->d_blkpart, grid, BK_PART, kq, p, BK_QMAX, d_H + q0, ldh,
@@ -447,8 +480,8 @@ int32_t launch_update(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, const doub
     bpar.store = store ? 1 : 0;
     const int grid = grid_rows(ctx, bp.n);
     const int pr = b2k_prof_begin(ctx, 6, (double)(kq + (store ? 2 : 1) * p) * sizeof(T) * (double)bp.n);
-    if (p <= 4) k_block_phase<T, true, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
-    else k_block_phase<T, true, 8><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    if (p <= 4) k_block_phase<T, 1, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    else k_block_phase<T, 1, 8><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
     b2k_prof_end(ctx, pr);
     B2K_LAUNCH_CHECK(ctx);
     if (d_G) {
@@ -456,6 +489,29 @@ int32_t launch_update(b2k_ctx* ctx, const BPanel& bp, int q0, int kq, const doub
         B2K_LAUNCH_CHECK(ctx);
     }
     return B2K_OK;
+}
+
+// R += alpha V H1 and H2 = V' R_new in ONE sweep (k <= BK_QMAX, p <= 4): the middle of BCGS2
+template <typename T>
+int32_t launch_update_project(b2k_ctx* ctx, const BPanel& bp, const double* d_H1, double alpha, double* d_H2) {
+    const int k = (int)bp.q.size(), p = (int)bp.r.size();
+    ColList cl;
+    for (int j = 0; j < k; ++j) cl.c[j] = bp.q[j];
+    for (int i = 0; i < p; ++i) cl.c[k + i] = bp.r[i];
+    BlockParams<T> bpar;
+    memset(&bpar, 0, sizeof(bpar));
+    bpar.base = (const T*)bp.base; bpar.ld = bp.ld; bpar.n = bp.n; bpar.kq = k; bpar.p = p;
+    bpar.H = d_H1; bpar.ldh = k; bpar.alpha = (T)alpha;
+    bpar.part = ctx->d_blkpart;
+    bpar.store = 1;
+    const int grid = grid_rows(ctx, bp.n);
+    const int pr = b2k_prof_begin(ctx, 6, (double)(k + 2 * p) * sizeof(T) * (double)bp.n);
+    k_block_phase<T, 2, 4><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(bpar, cl);
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    k_block_finalize<<<1, 256, 0, ctx->stream>>>(ctx->d_blkpart, grid, BK_PART, k, p, BK_QMAX, d_H2, k, 0);
+    B2K_LAUNCH_CHECK(ctx);
+    return b2k_allreduce(ctx, d_H2, k * p, bp.sharded);
 }
 
 // H (k x p, ld = k) = V' R on the device, all passes; all-reduced when sharded
@@ -533,14 +589,16 @@ int32_t fetch(b2k_ctx* ctx, const double* d, double* h, int count) {
 // B2K_BLOCK_KERNELS=0 routes block_inner / block_axpy / apply_block through loops of the single-vector entry points
 // (the round-1 behaviour) — an escape hatch and the A/B baseline for the multi-right-hand-side kernels.
 static bool g_block_kernels = true;
+static bool g_block_fuse = true;      // B2K_BLOCK_FUSE=0: BCGS2 as four separate sweeps (A/B switch)
 bool b2k_block_kernels_enabled() { return g_block_kernels; }
 
 int32_t b2k_block_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_BLOCK_KERNELS")) g_block_kernels = e[0] != '0';
+    if (const char* e = getenv("B2K_BLOCK_FUSE")) g_block_fuse = e[0] != '0';
 #define BK_ATTR(T, U, PP) \
     B2K_CUDA(ctx, cudaFuncSetAttribute((k_block_phase<T, U, PP>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))
-    BK_ATTR(double, false, 4); BK_ATTR(double, false, 8); BK_ATTR(double, true, 4); BK_ATTR(double, true, 8);
-    BK_ATTR(float, false, 4); BK_ATTR(float, false, 8); BK_ATTR(float, true, 4); BK_ATTR(float, true, 8);
+    BK_ATTR(double, 0, 4); BK_ATTR(double, 0, 8); BK_ATTR(double, 1, 4); BK_ATTR(double, 1, 8); BK_ATTR(double, 2, 4);
+    BK_ATTR(float, 0, 4); BK_ATTR(float, 0, 8); BK_ATTR(float, 1, 4); BK_ATTR(float, 1, 8); BK_ATTR(float, 2, 4);
 #undef BK_ATTR
     return B2K_OK;
 }
@@ -617,10 +675,17 @@ extern "C" int32_t b2k_block_orthogonalize(b2k_ctx* ctx, const b2k_vec* Rb, int3
         return B2K_OK;
     }
     B2K_TRY(block_project_dev(ctx, bp, d_H1, false));
-    B2K_TRY(block_update_dev(ctx, bp, d_H1, -1.0, (passes == 1 && G_host) ? d_G : nullptr));
-    if (passes == 2) {
-        B2K_TRY(block_project_dev(ctx, bp, d_H2, false));
+    if (passes == 2 && p <= 4 && k <= BK_QMAX && g_block_fuse) {
+        // three sweeps over V: project | update + project of the updated block on the resident tile | update (+ Gram)
+        if (ctx->dtype == B2K_F64) B2K_TRY(launch_update_project<double>(ctx, bp, d_H1, -1.0, d_H2));
+        else B2K_TRY(launch_update_project<float>(ctx, bp, d_H1, -1.0, d_H2));
         B2K_TRY(block_update_dev(ctx, bp, d_H2, -1.0, G_host ? d_G : nullptr));
+    } else {
+        B2K_TRY(block_update_dev(ctx, bp, d_H1, -1.0, (passes == 1 && G_host) ? d_G : nullptr));
+        if (passes == 2) {
+            B2K_TRY(block_project_dev(ctx, bp, d_H2, false));
+            B2K_TRY(block_update_dev(ctx, bp, d_H2, -1.0, G_host ? d_G : nullptr));
+        }
     }
     static_assert(2 * HCAP + BK_GRAM <= B2K_RES_DOUBLES, "block results must fit the pinned result buffer");
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_blk, sizeof(double) * (2 * HCAP + BK_GRAM), cudaMemcpyDeviceToHost,
