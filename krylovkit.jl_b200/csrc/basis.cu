@@ -939,6 +939,8 @@ int grid_for_rows(const b2k_ctx* ctx, int64_t n) {
     return (int)std::min<int64_t>(ntiles, ctx->num_sms);
 }
 
+bool g_coop_launch = true;   // B2K_COOP_LAUNCH=0: plain launch of the fused sweep (measurement only: no co-residency guarantee)
+
 template <typename T>
 int32_t launch_fused(b2k_ctx* ctx, FusedParams<T>& fp, const ColList& cl, int grid) {
     // the barrier counter only ever increases; wrap-around is handled by the signed compare
@@ -946,8 +948,11 @@ int32_t launch_fused(b2k_ctx* ctx, FusedParams<T>& fp, const ColList& cl, int gr
     fp.barrier_base = ctx->barrier_base;
     ctx->barrier_base += (unsigned)(fp.nph - 1) * (unsigned)grid;
     void* args[] = {(void*)&fp, (void*)&cl};
-    B2K_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_gs_fused<T>, dim3(grid), dim3(NTHREADS),
-                                              args, SMEM_BYTES, ctx->stream));
+    if (g_coop_launch)
+        B2K_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_gs_fused<T>, dim3(grid), dim3(NTHREADS),
+                                                  args, SMEM_BYTES, ctx->stream));
+    else    // A/B switch: grid <= #SMs and one CTA per SM by shared memory, i.e. co-resident on an idle device
+        k_gs_fused<T><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(fp, cl);
     B2K_LAUNCH_CHECK(ctx);
     return B2K_OK;
 }
@@ -1207,6 +1212,7 @@ int32_t mgs_sweep(b2k_ctx* ctx, const Panel& pn, const VecRef& v, int k, int res
 int32_t b2k_basis_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_L2_HINTS")) g_l2_hints = e[0] != '0';
     if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '1' ? 1 : 0;
+    if (const char* e = getenv("B2K_COOP_LAUNCH")) g_coop_launch = e[0] != '0';
     if (const char* e = getenv("B2K_TRANSFORM_UR")) g_transform_ur = (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
     if (const char* e = getenv("B2K_TRANSFORM_HYB")) g_transform_hyb = e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0);
 #define SETATTR(fn, bytes) \

@@ -166,6 +166,16 @@ __device__ __forceinline__ int coef_lanes(int k) {
 __device__ __forceinline__ double partial_lane_sum(const double* P, int G, int stride, int l, int L) {
     double a = 0.0;
     int g = l;
+    // twelve loads in flight per lane (148 CTAs / 4 lanes = 37 partials per lane at k = 60: three round trips to L2
+    // instead of ten — this sum sits on the critical path of every phase boundary, 2-3 times per Lanczos step);
+    // the additions stay in the order g = l, l + L, l + 2L, ...
+    for (; g + 11 * L < G; g += 12 * L) {
+        double t[12];
+#pragma unroll
+        for (int u = 0; u < 12; ++u) t[u] = __ldcg(P + (size_t)(g + u * L) * stride);
+#pragma unroll
+        for (int u = 0; u < 12; ++u) a += t[u];
+    }
     for (; g + 3 * L < G; g += 4 * L) {
         const double t0 = __ldcg(P + (size_t)g * stride), t1 = __ldcg(P + (size_t)(g + L) * stride);
         const double t2 = __ldcg(P + (size_t)(g + 2 * L) * stride), t3 = __ldcg(P + (size_t)(g + 3 * L) * stride);
