@@ -1153,7 +1153,8 @@ bool fused_ok(const b2k_ctx* ctx, int k, int sharded, int dtype) {
 bool g_use_coop = true;
 bool g_use_dmma = true;
 int g_transform_ur = 0;      // B2K_TRANSFORM_UR: 0 = DMMA kernel, 1 = <2 rows x 18>, 2 = <2 x 36>, 3 = <4 x 18> (DFMA, U in the constant bank)
-int g_transform_hyb = 0;     // B2K_TRANSFORM_HYB=1: DMMA + DFMA hybrid for keep <= 36 (k_transform_hyb); 2: DFMA 8 x 9 tile (k_transform_f89)
+int g_transform_hyb = 2;     // B2K_TRANSFORM_HYB: 2 (default) = DFMA 8 x 9 tile for keep <= 36 (k_transform_f89: 2.36 vs 2.58 ms
+                             // at 60 -> 36, gpurun_out/r02r_*), 0 = DMMA kernel, 1 = DMMA + DFMA hybrid (k_transform_hyb)
 
 // modified Gram-Schmidt sweep, pipelined: launch j computes v -= s_{j-1} q_{j-1} and
 // s_j = <q_j, v> in one pass (orthonormal.jl:417-421).  d_res[res_off + j] = s_j;
@@ -1246,10 +1247,11 @@ extern "C" int32_t b2k_debug_set_dmma(int32_t on) {
     return B2K_OK;
 }
 
-// 0 = DMMA restart GEMM, 1..3 = the DFMA / constant-bank variants (k_transform_ur)
+// restart-GEMM kernel for tests / A-B runs: 0 = default, 1..3 = constant-bank DFMA variants (k_transform_ur),
+// 4 = DMMA + DFMA hybrid, 5 = DFMA 8 x 9 tile, 6 = DMMA
 extern "C" int32_t b2k_debug_set_transform(int32_t mode) {
     g_transform_ur = (mode >= 0 && mode <= 3) ? mode : 0;
-    g_transform_hyb = mode == 4 ? 1 : (mode == 5 ? 2 : 0);   // 4 = the DMMA + DFMA hybrid, 5 = the DFMA 8 x 9 tile
+    g_transform_hyb = mode == 4 ? 1 : (mode == 5 ? 2 : (mode == 0 ? 2 : 0));   // 0 = default (DFMA 8 x 9 tile), 4 = hybrid, 5 = 8 x 9, 6 = DMMA
     return B2K_OK;
 }
 

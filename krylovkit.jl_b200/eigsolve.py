@@ -203,6 +203,20 @@ def _now():
     return time.perf_counter()
 
 
+FUSED_RITZ_VECTORS = True      # the hm Ritz vectors V U[:, 1:hm] in one multi-right-hand-side sweep over the basis
+
+
+def _ritz_vectors(B, U: np.ndarray, hm: int):
+    """[B * U[:, i] for i in 1:hm] (eigsolve/lanczos.jl:118): with the block kernels the basis is read once for all
+    hm vectors instead of hm times (b2k_block_axpy on zero vectors: the same chain of fma over the basis columns)."""
+    if FUSED_RITZ_VECTORS and 1 < hm <= 8 and len(B) >= 1:
+        from .factorizations.blocklanczos import Block, block_axpy_
+        Y = [B[0].zerovector() for _ in range(hm)]
+        block_axpy_(Block(Y), B.basis, -np.asfortranarray(U[:len(B), :hm]))
+        return Y
+    return [B * U[:, i] for i in range(hm)]
+
+
 def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, sink=None):
     krylovdim, maxiter = alg.krylovdim, alg.maxiter
     if howmany > krylovdim:
@@ -281,7 +295,7 @@ def _eigsolve_lanczos(A, x0: B200Vec, howmany: int, which: str, alg: Lanczos, si
     values = D[:hm].copy()
     B = fact.basis()
     if sink is None:
-        vectors = [B * U[:, i] for i in range(hm)]
+        vectors = _ritz_vectors(B, U, hm)
         r = fact.residual()
         residuals = [r.scale(U[-1, i]) for i in range(hm)]
     else:       # host-buffer path: stream the Ritz vectors out one at a time
