@@ -513,17 +513,21 @@ k_transform_dmma(const __grid_constant__ TransformParams p, const __grid_constan
 
 // Pure-DFMA restart GEMM with an 8 x 9 register tile.  DMMA runs on the FP64 datapath at under half the DFMA rate
 // (k_transform_hyb, measured), so the only way below the DMMA kernel is DFMA fed fast enough.  The operand costs are
-// LSU cycles: a row value is an LDS.128 per two rows (2 cycles per double pair... 4 wavefronts per warp instruction), a
-// U value a broadcast (2 cycles per double).  thread <-> 8 rows x 9 outputs: 16 + 18 = 34 LSU cycles per 72 warp-DFMAs
-// (144 pipe cycles) and warp — four such warps, one per scheduler, put the LSU at 94 % and the FP64 pipe at its limit,
-// where k_transform's 2 x 18 tile spent 40 per 36.  U sits in shared memory as [group][i][10] (9 outputs + pad: 16-byte
+// LSU cycles: a row value is an LDS.128 per two rows (2 cycles per double), a U value a broadcast (2 cycles per
+// double).  thread <-> 8 rows x 9 outputs: 16 + 18 = 34 LSU cycles per 72 warp-DFMAs (144 pipe cycles) and warp, where
+// k_transform's 2 x 18 tile spent 40 per 36.  U sits in shared memory as [group][i][10] (9 outputs + pad: 16-byte
 // aligned rows for the broadcast LDS.128).  keep <= 36: one pass, chunks consumed and released as they land.
+//
+// Warps: a 256-row tile is covered by FOUR warps (32 lanes x 8 rows, 4 column groups).  The first version ran those
+// four + a producer warp per CTA and reached 2.36 ms: ncu (gpurun_out/r02u_f89.ncu-rep) showed the FP64 pipe 52 %
+// active, LSU 36 %, issue slots 36 %, `stall_wait` dominant — ONE warp per scheduler cannot issue DFMAs back to back.
+// Registers are granted per four warps (8 x 32 x 255 = the whole file), so a ninth (producer) warp is not affordable:
+// here EIGHT consumer warps work as two sets on alternate tiles of the SAME FIFO ring (set 1 trails set 0 by half a
+// tile), and the TMA refill of a slot is issued by the first warp of the set that just consumed it (chunk g + NS goes
+// into the slot of chunk g; dependencies only point backwards in g, so the two sets cannot deadlock each other).
 constexpr int F89_G = 4, F89_TH = 9, F89_UP = 10;         // column groups, outputs per group, padded row of U
-constexpr int F89_WARPS = 4;                              // consumer warps with work (256 rows / (32 lanes x 8 rows) x 4 groups)
+constexpr int F89_THREADS = 256;                          // two sets of four warps
 
-// 4 consumer warps + 1 producer warp = 160 threads: registers are granted per 4 warps, so 5 warps get the 255-register
-// ceiling the 72 accumulators need (the 9-warp kernels above are capped at 168)
-constexpr int F89_THREADS = 32 * (F89_WARPS + 1);
 __global__ void __launch_bounds__(F89_THREADS, 1)
 k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
     constexpr int R = 256, C = 8;
@@ -534,7 +538,7 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
             mbar_init(full + 8 * i, 1);
-            mbar_init(empty + 8 * i, F89_WARPS);
+            mbar_init(empty + 8 * i, F89_G);              // the four warps of the set that consumes the chunk
         }
         fence_mbar_init();
     }
@@ -547,31 +551,30 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
     __syncthreads();
     const int nch = (p.m + C - 1) / C;
     const int64_t ntiles = (p.n + R - 1) / R;
+    const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_chunks = my_tiles * nch;
     double* base = reinterpret_cast<double*>(p.base);
-    uint32_t s = 0, ph = 0;
-    if (threadIdx.x >= 32 * F89_WARPS) {
-        const int lane = threadIdx.x & 31;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t r0 = tile * R;
-            const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
-            const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
-            for (int c = 0; c < nch; ++c) {
-                mbar_wait(empty + 8 * s, ph ^ 1);
-                const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
-                if (lane == 0) mbar_expect_tx(full + 8 * s, bytes * (uint32_t)ncol);
-                __syncwarp();
-                if (lane < ncol)
-                    bulk_g2s(ring + s * SLOT_BYTES + lane * R * 8,
-                             base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes, full + 8 * s);
-                if (++s == NS) { s = 0; ph ^= 1; }
-            }
-        }
-        return;
-    }
-    const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, cg = (tid >> 5) & 3, set = tid >> 7;
+    // chunk g (tile g / nch of this CTA, columns 8 (g % nch) ...) -> ring slot g % NS; issued by one whole warp
+    auto issue = [&](int64_t g) {
+        const int64_t tl = g / nch;
+        const int c = (int)(g - tl * nch);
+        const int64_t r0 = ((int64_t)blockIdx.x + tl * gridDim.x) * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
+        const uint32_t sl = (uint32_t)(g % NS);
+        const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+        if (lane == 0) mbar_expect_tx(full + 8 * sl, bytes * (uint32_t)ncol);
+        __syncwarp();
+        if (lane < ncol)
+            bulk_g2s(ring + sl * SLOT_BYTES + lane * R * 8, base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes,
+                     full + 8 * sl);
+    };
+    if (tid < 32)
+        for (int64_t g = 0; g < NS && g < total_chunks; ++g) issue(g);
     const double* ug = Us + (size_t)cg * p.m * F89_UP;    // my group's U rows
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = tile * R;
+    for (int64_t tl = set; tl < my_tiles; tl += 2) {
+        const int64_t r0 = ((int64_t)blockIdx.x + tl * gridDim.x) * R;
         const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
         double acc[8][F89_TH];
 #pragma unroll
@@ -579,8 +582,10 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
 #pragma unroll
             for (int t = 0; t < F89_TH; ++t) acc[e][t] = 0.0;
         for (int c = 0; c < nch; ++c) {
-            mbar_wait(full + 8 * s, ph);
-            const double* slot = reinterpret_cast<const double*>(smem + s * SLOT_BYTES) + 2 * lane;
+            const int64_t g = tl * nch + c;
+            const uint32_t sl = (uint32_t)(g % NS), ph = (uint32_t)((g / NS) & 1);
+            mbar_wait(full + 8 * sl, ph);
+            const double* slot = reinterpret_cast<const double*>(smem + sl * SLOT_BYTES) + 2 * lane;
             const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
             const double* urow = ug + (size_t)c * C * F89_UP;
 #pragma unroll 2
@@ -603,8 +608,11 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
                     for (int e = 0; e < 8; ++e) acc[e][t] = fma(q[e], u[t], acc[e][t]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty + 8 * s);
-            if (++s == NS) { s = 0; ph ^= 1; }
+            if (lane == 0) mbar_arrive(empty + 8 * sl);
+            if (cg == 0 && g + NS < total_chunks) {       // refill the slot this set has just consumed
+                mbar_wait(empty + 8 * sl, ph);
+                issue(g + NS);
+            }
         }
 #pragma unroll
         for (int t = 0; t < F89_TH; ++t) {
