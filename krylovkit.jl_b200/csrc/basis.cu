@@ -45,6 +45,7 @@ struct FusedParams {
     const int* stop;         // device flag: when set, the launch does nothing (see FinalizeParams)
     FinalizeParams fin;      // optional in-kernel finalisation by the last CTA
     PeerStep ps;             // row-sharded contexts: cross-GPU exchanges of this launch (ps.on == 0: one GPU)
+    unsigned long long* trace;   // optional event trace
 };
 
 // Phase boundary of a row-sharded launch.  The local grid barrier and the cross-GPU sum of the projection
@@ -106,6 +107,8 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
         return;
     }
     SmemView sm(smem);
+    const bool tr0 = fp.trace && blockIdx.x == 0 && threadIdx.x == 0;
+    if (tr0) b2k_trace(fp.trace, 10);
     const int64_t n = fp.ph[0].n;
     const int64_t ntiles = (n + Cfg<T>::R - 1) / Cfg<T>::R;
     const bool ragged = (n % Cfg<T>::R) != 0 && ((ntiles - 1) % gridDim.x) == blockIdx.x;
@@ -118,6 +121,7 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
         peer_wait(fp.ps.pd, PEER_CH_ALPHA, fp.ps.seq_alpha, threadIdx.x);
         named_bar_sync(1, NCONS);
     }
+    if (tr0) b2k_trace(fp.trace, 11);
     for (int i = 0; i < fp.nph; ++i) {
         if (prod) {
             producer_phase<T>(fp.ph[i], cl, sm, st);
@@ -126,9 +130,11 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
             else if (fp.kind[i] == 1) consumer_phase<T, true, true>(fp.ph[i], sm, st);
             else consumer_phase<T, true, false>(fp.ph[i], sm, st);
         }
+        if (tr0) b2k_trace(fp.trace, 12 + i);           // CTA 0 has finished the phase's tiles
         if (i + 1 < fp.nph) {
             if (fp.ps.on) peer_boundary<T>(fp, i, smem);
             else grid_barrier(fp.barrier, fp.barrier_base + (unsigned)(i + 1) * gridDim.x);
+            if (tr0) b2k_trace(fp.trace, 15 + i);       // ... and left the boundary
         }
     }
     if (fp.fin.enabled && !prod) {
@@ -145,7 +151,9 @@ k_gs_fused(const __grid_constant__ FusedParams<T> fp, const __grid_constant__ Co
         named_bar_sync(1, NCONS);
         if (*flag) {
             __threadfence();
+            if (fp.trace && threadIdx.x == 0) b2k_trace(fp.trace, 18);      // last CTA enters the finaliser
             finalize_block(fp.fin, threadIdx.x, sh, fp.ps.on ? &fp.ps : nullptr);
+            if (fp.trace && threadIdx.x == 0) b2k_trace(fp.trace, 19);
         }
     }
 }
@@ -1722,6 +1730,7 @@ int32_t chain_step_gs(b2k_ctx* ctx, const Panel& pn, int K1, const VecRef& rw, c
         fp.ph[2] = sc; fp.kind[2] = 2; fp.nph = 3;
     }
     fp.stop = reinterpret_cast<const int*>(ctx->d_sync + B2K_SYNC_STOP);
+    fp.trace = ctx->d_trace;
     fp.fin.A = PA; fp.fin.B = nullptr; fp.fin.N = PN; fp.fin.G = grid; fp.fin.stride = B2K_KSTRIDE;
     fp.fin.k = K1; fp.fin.res = nullptr; fp.fin.off = 0; fp.fin.noff = 0; fp.fin.rec = rec;
     fp.fin.alpha_col = K1 - 1; fp.fin.tol = tol;
@@ -1815,6 +1824,7 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
         fz.stop = d_stop;
         fz.dot_self = 1;
         fz.l2_hints = g_l2_hints ? 1 : 0;
+        fz.trace = ctx->d_trace;
         if (alg == B2K_MGS2B) {                  // alpha = <v, A v - beta v_prev>: the modified order
             fz.dot_sub_vec = vprev.ptr;
             fz.dot_sub_scale = rec_prev + 2;
@@ -2093,5 +2103,36 @@ extern "C" int32_t b2k_block_qr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, doubl
             good[j] = 1;
         }
     }
+    return B2K_OK;
+}
+
+// Event trace of the chained Lanczos step (tools/trace_step.py).  on != 0 allocates / clears the buffer and makes the
+// kernels of b2k_lanczos_expand_many record (globaltimer ns, code) pairs: SpMV 1 begin, 2 halo rows present, 3 CTA 0
+// done, 4 <v, Av> published by the last CTA; sweep 10 begin, 11 alpha present, 12/13/14 CTA 0 finished phase 1/2/3,
+// 15/16 CTA 0 left boundary 1/2, 18/19 the last CTA enters / leaves the finaliser.
+extern "C" int32_t b2k_debug_trace(b2k_ctx* ctx, int32_t on) {
+    if (!ctx) return B2K_EINVAL;
+    if (on) {
+        if (!ctx->d_trace) B2K_CUDA(ctx, cudaMalloc(&ctx->d_trace, sizeof(unsigned long long) * (2 + 2 * B2K_TRACE_CAP)));
+        B2K_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, sizeof(unsigned long long) * 2, ctx->stream));
+    } else if (ctx->d_trace) {
+        B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_trace);
+        ctx->d_trace = nullptr;
+    }
+    return B2K_OK;
+}
+
+extern "C" int32_t b2k_debug_trace_read(b2k_ctx* ctx, unsigned long long* out, int64_t cap_events, int64_t* n_events) {
+    if (!ctx || !out || !n_events) return B2K_EINVAL;
+    *n_events = 0;
+    if (!ctx->d_trace) return B2K_OK;
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long cnt = 0;
+    B2K_CUDA(ctx, cudaMemcpy(&cnt, ctx->d_trace, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (cnt > B2K_TRACE_CAP) cnt = B2K_TRACE_CAP;
+    if ((int64_t)cnt > cap_events) cnt = (unsigned long long)cap_events;
+    B2K_CUDA(ctx, cudaMemcpy(out, ctx->d_trace + 2, sizeof(unsigned long long) * 2 * cnt, cudaMemcpyDeviceToHost));
+    *n_events = (int64_t)cnt;
     return B2K_OK;
 }

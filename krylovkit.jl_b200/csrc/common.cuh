@@ -55,6 +55,7 @@ struct b2k_ctx {
     int32_t num_sms = 0;
     size_t  l2_persist_bytes = 0;   // persisting-L2 carve-out (0 = unavailable)
     int     dot_hints = 0;          // set by the MGS sweep: its k_dot launches carry L2 eviction-priority hints
+    unsigned long long* d_trace = nullptr;   // b2k_debug_trace: [0] event count, then (globaltimer ns, code) pairs
     size_t  l2_window_max = 0;      // max access-policy window
     cudaStream_t stream = nullptr;
     std::vector<B2kSpace> spaces;
@@ -165,6 +166,19 @@ static inline double* b2k_part_set(b2k_ctx* ctx, int set) {
 // spmv.cu: free the device arrays of an operator (called by b2k_op_destroy / b2k_ctx_destroy)
 void b2k_op_release(b2k_ctx* ctx, b2k_op* op);
 
+// Lightweight in-kernel event trace (b2k_debug_trace): thread 0 of CTA 0 (and the "last CTA" paths) append
+// (globaltimer, code) pairs; tools/trace_step.py turns them into the timeline of a chained Lanczos step.
+constexpr unsigned long long B2K_TRACE_CAP = 1ull << 16;
+#ifdef __CUDACC__
+__device__ __forceinline__ void b2k_trace(unsigned long long* tr, unsigned code) {
+    if (!tr) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(tr, 1ull);
+    if (i < B2K_TRACE_CAP) { tr[2 + 2 * i] = t; tr[3 + 2 * i] = code; }
+}
+#endif
+
 // Optional fusions of the Lanczos step into the SpMV (basis.cu, b2k_lanczos_expand_many):
 //   xscale   : device scalar; the operand is x*(*xscale) — the normalisation v = r/β of lanczos.jl:257 applied
 //              while gathering (each gathered entry is rounded exactly like the separate scale!! pass);
@@ -187,6 +201,7 @@ struct SpmvFuse {
     // (0: not published), and the halo sequence number a previous kernel has already pushed this operand's
     // boundary rows under (0: the apply pushes them itself)
     unsigned long long seq_alpha, seq_halo;
+    unsigned long long* trace;     // optional event trace (b2k_debug_trace)
 };
 
 int32_t b2k_enqueue_apply(b2k_ctx* ctx, const b2k_op* op, const VecRef& x, const VecRef& y,

@@ -274,6 +274,8 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     }
     // ---------------------------------- consumers ----------------------------------
     const int tid = threadIdx.x, w = tid >> 5;
+    const bool tr0 = fz.trace && blockIdx.x == 0 && tid == 0;
+    if (tr0) b2k_trace(fz.trace, 1);
     if (ps.on && ps.seq_halo) {        // boundary rows of x arrive from the neighbours through the peer window;
         if (tid == 0) {                // the producer warp streams the matrix meanwhile
             if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
@@ -281,6 +283,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
         }
         named_bar_sync(1, SPP_CONS);
     }
+    if (tr0) b2k_trace(fz.trace, 2);
     const bool scaled = fz.xscale != nullptr;
     const T sc = scaled ? (T)(*fz.xscale) : (T)1;
     T* const vout = reinterpret_cast<T*>(fz.vout);
@@ -379,6 +382,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
         if (lane == 0) mbar_arrive(empty + 8 * s);
         if (++s == NSTG) { s = 0; ph ^= 1; }
     }
+    if (tr0) b2k_trace(fz.trace, 3);
     if (want_dot) {
         double v = warp_sum((double)dacc);
         if (lane == 0) red[w] = v;
@@ -406,6 +410,7 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
                 for (int i = 0; i < SPP_CONS / 32; ++i) tot += red[i];
                 *out = tot;
                 if (ps.on && ps.seq_alpha) peer_publish1(ps.pd, PEER_CH_ALPHA, ps.seq_alpha, tot);
+                if (fz.trace) b2k_trace(fz.trace, 4);
             }
         }
     }
