@@ -965,3 +965,37 @@ def test_bicgstab_chained_iterations_equal_stepwise():
     # both exits are taken: run 0 ends through the full-step test (numops = 2 numiter + 2), run 3 through the half step
     assert out[True][0][2] == 2 * out[True][0][1] + 2 and out[True][3][2] == 2 * out[True][3][1] + 1
     ctx.close()
+
+
+def test_chained_step_event_trace():
+    """b2k_debug_trace: the kernels of a device-chained batch record one event per stage and step (SpMV begin / halo
+    present / CTA 0 done / <v,Av> published; sweep begin / alpha present / three phases, two boundaries / finaliser in
+    and out), in time order within a step; with the trace off nothing is recorded."""
+    import ctypes as C
+    lib = L.load()
+    nx, ny, steps = 301, 97, 12
+    ctx = kk.B200Context(nx * ny, steps + 8)
+    op = kk.B200CSR.stencil(ctx, nx, ny)
+    it = lz.LanczosIterator(op, ctx.from_host(ko.splitmix_vector(SEED, nx * ny)), kk.cgs2)
+    f = lz.initialize(it)
+    ctx.check(lib.b2k_debug_trace(ctx.h, 1))
+    done = lz.expand_many_(it, f, steps, 0.0)
+    assert done == steps
+    buf = (C.c_uint64 * (2 * 4096))()
+    n = C.c_int64()
+    ctx.check(lib.b2k_debug_trace_read(ctx.h, buf, 4096, C.byref(n)))
+    ev = np.frombuffer(buf, dtype=np.uint64)[: 2 * n.value].reshape(-1, 2).astype(np.int64)
+    ev = ev[np.argsort(ev[:, 0], kind="stable")]
+    codes = ev[:, 1].tolist()
+    per_step = [1, 2, 3, 4, 10, 11, 12, 15, 13, 16, 14, 18, 19]
+    assert n.value == steps * len(per_step), (n.value, codes[:30])
+    assert sorted(codes) == sorted(per_step * steps)
+    starts = [i for i, c in enumerate(codes) if c == 1]
+    assert len(starts) == steps
+    t = ev[:, 0]
+    assert t[-1] > t[0]
+    ctx.check(lib.b2k_debug_trace(ctx.h, 0))
+    lz.expand_many_(it, f, 2, 0.0)
+    ctx.check(lib.b2k_debug_trace_read(ctx.h, buf, 4096, C.byref(n)))
+    assert n.value == 0
+    ctx.close()

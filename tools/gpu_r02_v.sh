@@ -20,3 +20,4 @@ tail -2 gpurun_out/r02v_ncu.log
 timeout 900 python -m pytest tests/test_gpu_solvers.py tests/test_gpu_fullsize.py -m gpu -q --timeout 600 -k "eigsolve or lanczos or fullsize" > gpurun_out/r02v_pytest2.log 2>&1
 grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/r02v_pytest2.log | tail -5
 timeout 200 python tools/trace_step.py 2>&1 | tail -18
+timeout 300 python -m pytest tests/test_gpu_solvers.py -m gpu -q --timeout 200 -k "event_trace" 2>&1 | tail -3
