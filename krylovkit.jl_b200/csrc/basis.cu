@@ -543,10 +543,16 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
     const uint32_t ring = smem_u32(smem);
     const uint32_t full = smem_u32(smem + TR_OFF_BAR), empty = full + NS * 8;
     double* Us = reinterpret_cast<double*>(smem + TR_OFF_U);
+    // uses[s] = how many loads have been posted to slot s.  A set skips the uses of a slot that belong to the other
+    // set's tiles, and an mbarrier wait only knows a phase PARITY: waiting for use u while use u - 1 has not landed
+    // yet would return at once (parity of the unfinished phase u - 1 != parity u).  So a consumer first waits until
+    // the load of ITS use has been posted (the barrier is then in phase u or beyond) and only then on the parity.
+    volatile int* uses = reinterpret_cast<volatile int*>(smem + TR_OFF_U + TR_U_BYTES - 64);
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
             mbar_init(full + 8 * i, 1);
             mbar_init(empty + 8 * i, F89_G);              // the four warps of the set that consumes the chunk
+            uses[i] = 0;
         }
         fence_mbar_init();
     }
@@ -572,7 +578,11 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
         const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
         const uint32_t sl = (uint32_t)(g % NS);
         const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
-        if (lane == 0) mbar_expect_tx(full + 8 * sl, bytes * (uint32_t)ncol);
+        if (lane == 0) {
+            mbar_expect_tx(full + 8 * sl, bytes * (uint32_t)ncol);
+            __threadfence_block();
+            uses[sl] = (int)(g / NS) + 1;
+        }
         __syncwarp();
         if (lane < ncol)
             bulk_g2s(ring + sl * SLOT_BYTES + lane * R * 8, base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes,
@@ -592,6 +602,7 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
         for (int c = 0; c < nch; ++c) {
             const int64_t g = tl * nch + c;
             const uint32_t sl = (uint32_t)(g % NS), ph = (uint32_t)((g / NS) & 1);
+            while (uses[sl] < (int)(g / NS) + 1) {}       // my use of the slot has been posted (see `uses`)
             mbar_wait(full + 8 * sl, ph);
             const double* slot = reinterpret_cast<const double*>(smem + sl * SLOT_BYTES) + 2 * lane;
             const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
@@ -1990,7 +2001,7 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
         else if (g_transform_ur == 2) k_transform_ur<2, 36><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else k_transform_ur<4, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
     } else if (f64 && g_transform_hyb == 2 && keep <= F89_G * F89_TH &&
-               (size_t)F89_G * m * F89_UP * 8 <= (size_t)TR_U_BYTES) {
+               (size_t)F89_G * m * F89_UP * 8 <= (size_t)TR_U_BYTES - 64) {
         k_transform_f89<<<grid_for_rows<double>(ctx, pn.n), F89_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
     } else if (dmma_ok && g_transform_hyb == 1 && keep <= TH_MAXKEEP && (size_t)m * 40 * 8 <= (size_t)TD_U_BYTES) {
         k_transform_hyb<<<grid_for_rows<double>(ctx, pn.n), TR_THREADS, TD_SMEM, ctx->stream>>>(p, cl);
@@ -2108,8 +2119,8 @@ extern "C" int32_t b2k_block_qr(b2k_ctx* ctx, const b2k_vec* X, int32_t p, doubl
 
 // Event trace of the chained Lanczos step (tools/trace_step.py).  on != 0 allocates / clears the buffer and makes the
 // kernels of b2k_lanczos_expand_many record (globaltimer ns, code) pairs: SpMV 1 begin, 2 halo rows present, 3 CTA 0
-// done, 4 <v, Av> published by the last CTA; sweep 10 begin, 11 alpha present, 12/13/14 CTA 0 finished phase 1/2/3,
-// 15/16 CTA 0 left boundary 1/2, 18/19 the last CTA enters / leaves the finaliser.
+// done, 4 <v, Av> published by the last CTA; sweep 10 begin, 11 alpha present, 12 + i CTA 0 finished phase i,
+// 15 + i CTA 0 left boundary i, 18/19 the last CTA enters / leaves the finaliser.
 extern "C" int32_t b2k_debug_trace(b2k_ctx* ctx, int32_t on) {
     if (!ctx) return B2K_EINVAL;
     if (on) {

@@ -969,7 +969,7 @@ def test_bicgstab_chained_iterations_equal_stepwise():
 
 def test_chained_step_event_trace():
     """b2k_debug_trace: the kernels of a device-chained batch record one event per stage and step (SpMV begin / halo
-    present / CTA 0 done / <v,Av> published; sweep begin / alpha present / three phases, two boundaries / finaliser in
+    present / CTA 0 done / <v,Av> published; sweep begin / alpha present / two phases, one boundary / finaliser in
     and out), in time order within a step; with the trace off nothing is recorded."""
     import ctypes as C
     lib = L.load()
@@ -987,7 +987,7 @@ def test_chained_step_event_trace():
     ev = np.frombuffer(buf, dtype=np.uint64)[: 2 * n.value].reshape(-1, 2).astype(np.int64)
     ev = ev[np.argsort(ev[:, 0], kind="stable")]
     codes = ev[:, 1].tolist()
-    per_step = [1, 2, 3, 4, 10, 11, 12, 15, 13, 16, 14, 18, 19]
+    per_step = [1, 2, 3, 4, 10, 11, 12, 15, 13, 18, 19]       # two phases: prologue + projection | update + norm
     assert n.value == steps * len(per_step), (n.value, codes[:30])
     assert sorted(codes) == sorted(per_step * steps)
     starts = [i for i, c in enumerate(codes) if c == 1]

@@ -48,10 +48,10 @@ ctx.check(lib.b2k_debug_trace_read(ctx.h, buf, cap, C.byref(n)))
 ev = np.frombuffer(buf, dtype=np.uint64)[: 2 * n.value].reshape(-1, 2).astype(np.int64)
 ev = ev[np.argsort(ev[:, 0], kind="stable")]
 names = {1: "spmv begin", 2: "spmv halo rows present", 3: "spmv CTA0 tiles done", 4: "spmv <v,Av> published (last CTA)",
-         10: "sweep begin", 11: "sweep alpha present", 12: "phase 1 done (CTA0)", 15: "boundary 1 left",
-         13: "phase 2 done (CTA0)", 16: "boundary 2 left", 14: "phase 3 done (CTA0)", 18: "finaliser entered (last CTA)",
-         19: "finaliser left"}
-order = [1, 2, 3, 4, 10, 11, 12, 15, 13, 16, 14, 18, 19]
+         10: "sweep begin", 11: "sweep alpha present", 12: "project phase done (CTA0)", 15: "boundary left",
+         13: "update phase done (CTA0)", 18: "finaliser entered (last CTA)", 19: "finaliser left"}
+# the Lanczos CGS2 step (lanczos.jl:313-324) is two phases: [three-term prologue + projection] | [update + norm]
+order = [1, 2, 3, 4, 10, 11, 12, 15, 13, 18, 19]
 # split into steps at every "spmv begin"
 starts = np.flatnonzero(ev[:, 1] == 1)
 steps = []
