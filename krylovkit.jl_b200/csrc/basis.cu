@@ -649,6 +649,113 @@ k_transform_f89(const __grid_constant__ TransformParams p, const __grid_constant
     }
 }
 
+// The 8 x 9 DFMA tile on 512-row tiles: both warp sets consume the SAME chunk (4 basis columns x 512 rows, still one
+// 16 KB slot; set 0 takes rows 0..255, set 1 rows 256..511), so every load keeps the full 12-slot lead of the FIFO.
+// (With the sets on alternate 256-row tiles the lead at a tile switch is 3-4 chunks of that set's time: ncu showed 20 %
+// of the samples on the wait for the `full` barrier and the FP64 pipe at 56 %, gpurun_out/r02v_f89.ncu-rep.)
+constexpr int F89W_R = 512, F89W_C = 4;
+
+__global__ void __launch_bounds__(F89_THREADS, 1)
+k_transform_f89w(const __grid_constant__ TransformParams p, const __grid_constant__ ColList cl) {
+    constexpr int R = F89W_R, C = F89W_C;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full = smem_u32(smem + TR_OFF_BAR), empty = full + NS * 8;
+    double* Us = reinterpret_cast<double*>(smem + TR_OFF_U);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, F89_THREADS / 32);   // all eight warps consume every chunk
+        }
+        fence_mbar_init();
+    }
+    for (int idx = threadIdx.x; idx < F89_G * p.m * F89_UP; idx += blockDim.x) {
+        const int gq = idx / (p.m * F89_UP), rem = idx - gq * p.m * F89_UP;
+        const int i = rem / F89_UP, t = rem - i * F89_UP;
+        const int j = gq * F89_TH + t;
+        Us[idx] = (t < F89_TH && j < p.keep) ? p.U[(size_t)j * p.ldu + i] : 0.0;
+    }
+    __syncthreads();
+    const int nch = (p.m + C - 1) / C;
+    const int64_t ntiles = (p.n + R - 1) / R;
+    const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_chunks = my_tiles * nch;
+    double* base = reinterpret_cast<double*>(p.base);
+    const int tid = threadIdx.x, lane = tid & 31, cg = (tid >> 5) & 3, set = tid >> 7;
+    auto issue = [&](int64_t g) {                         // one whole warp
+        const int64_t tl = g / nch;
+        const int c = (int)(g - tl * nch);
+        const int64_t r0 = ((int64_t)blockIdx.x + tl * gridDim.x) * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        const uint32_t bytes = (uint32_t)((rt * sizeof(double) + 15) & ~(size_t)15);
+        const uint32_t sl = (uint32_t)(g % NS);
+        const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+        if (lane == 0) mbar_expect_tx(full + 8 * sl, bytes * (uint32_t)ncol);
+        __syncwarp();
+        if (lane < ncol)
+            bulk_g2s(ring + sl * SLOT_BYTES + lane * R * 8, base + (int64_t)cl.c[c * C + lane] * p.ld + r0, bytes,
+                     full + 8 * sl);
+    };
+    if (tid < 32)
+        for (int64_t g = 0; g < NS && g < total_chunks; ++g) issue(g);
+    const double* ug = Us + (size_t)cg * p.m * F89_UP;
+    int64_t g = 0;
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+        const int64_t r0 = ((int64_t)blockIdx.x + tl * gridDim.x) * R;
+        const int rt = (int)((p.n - r0) < R ? (p.n - r0) : R);
+        double acc[8][F89_TH];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int t = 0; t < F89_TH; ++t) acc[e][t] = 0.0;
+        for (int c = 0; c < nch; ++c, ++g) {
+            const uint32_t sl = (uint32_t)(g % NS), ph = (uint32_t)((g / NS) & 1);
+            mbar_wait(full + 8 * sl, ph);
+            const double* slot = reinterpret_cast<const double*>(smem + sl * SLOT_BYTES) + 256 * set + 2 * lane;
+            const int ncol = (p.m - c * C) < C ? (p.m - c * C) : C;
+            const double* urow = ug + (size_t)c * C * F89_UP;
+#pragma unroll 2
+            for (int jj = 0; jj < ncol; ++jj) {
+                double q[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {             // rows 256 set + 2 lane, + 1 (+ 64 e)
+                    const double2 v = *reinterpret_cast<const double2*>(slot + jj * R + 64 * e);
+                    q[2 * e] = v.x; q[2 * e + 1] = v.y;
+                }
+                double u[F89_UP];
+#pragma unroll
+                for (int t = 0; t < F89_UP; t += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(urow + jj * F89_UP + t);
+                    u[t] = v.x; u[t + 1] = v.y;
+                }
+#pragma unroll
+                for (int t = 0; t < F89_TH; ++t)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e][t] = fma(q[e], u[t], acc[e][t]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * sl);
+            if (tid < 32 && g + NS < total_chunks) {      // warp 0 refills the slot once all eight warps are done with it
+                mbar_wait(empty + 8 * sl, ph);
+                issue(g + NS);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < F89_TH; ++t) {
+            const int j = cg * F89_TH + t;
+            if (j < p.keep) {
+                double* col = base + (int64_t)cl.c[j] * p.ld + r0 + 256 * set + 2 * lane;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 256 * set + 2 * lane + 64 * e;
+                    if (row + 1 < rt) *reinterpret_cast<double2*>(col + 64 * e) = make_double2(acc[2 * e][t], acc[2 * e + 1][t]);
+                    else if (row < rt) col[64 * e] = acc[2 * e][t];
+                }
+            }
+        }
+    }
+}
+
 // Hybrid restart GEMM: DMMA and DFMA at once.  k_transform_dmma saturates the XU pipe `DMMA.8x8x4` issues through
 // (30 FMA/clk/SM, profiles/r02_transform_pipes.md) while the DFMA pipe idles; a DFMA-only kernel is bound by the
 // shared-memory broadcast of U (2 LSU cycles per double).  Here every consumer warp does both per staged chunk: output
@@ -1242,7 +1349,7 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     if (const char* e = getenv("B2K_CHAIN_MODE")) g_chain_mode = e[0] == '1' ? 1 : 0;
     if (const char* e = getenv("B2K_COOP_LAUNCH")) g_coop_launch = e[0] != '0';
     if (const char* e = getenv("B2K_TRANSFORM_UR")) g_transform_ur = (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
-    if (const char* e = getenv("B2K_TRANSFORM_HYB")) g_transform_hyb = e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0);
+    if (const char* e = getenv("B2K_TRANSFORM_HYB")) g_transform_hyb = (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
 #define SETATTR(fn, bytes) \
     B2K_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
     SETATTR((k_phase<double, false, true>), SMEM_BYTES);
@@ -1256,6 +1363,7 @@ int32_t b2k_basis_init(b2k_ctx* ctx) {
     SETATTR(k_transform_dmma, TD_SMEM);
     SETATTR(k_transform_hyb, TD_SMEM);
     SETATTR(k_transform_f89, TR_SMEM);
+    SETATTR(k_transform_f89w, TR_SMEM);
     SETATTR((k_transform_ur<2, 18>), TR_SMEM);
     SETATTR((k_transform_ur<2, 36>), TR_SMEM);
     SETATTR((k_transform_ur<4, 18>), TR_SMEM);
@@ -1278,7 +1386,7 @@ extern "C" int32_t b2k_debug_set_dmma(int32_t on) {
 // 4 = DMMA + DFMA hybrid, 5 = DFMA 8 x 9 tile, 6 = DMMA
 extern "C" int32_t b2k_debug_set_transform(int32_t mode) {
     g_transform_ur = (mode >= 0 && mode <= 3) ? mode : 0;
-    g_transform_hyb = mode == 4 ? 1 : (mode == 5 ? 2 : (mode == 0 ? 2 : 0));   // 0 = default (DFMA 8 x 9 tile), 4 = hybrid, 5 = 8 x 9, 6 = DMMA
+    g_transform_hyb = mode == 4 ? 1 : (mode == 5 ? 2 : (mode == 7 ? 3 : (mode == 0 ? 2 : 0)));   // 0 = default, 4 = hybrid, 5 = 8 x 9 (two sets, alternate tiles), 6 = DMMA, 7 = 8 x 9 on 512-row tiles
     return B2K_OK;
 }
 
@@ -2000,6 +2108,10 @@ extern "C" int32_t b2k_basis_transform(b2k_ctx* ctx, const b2k_vec* cols, int32_
         if (g_transform_ur == 1) k_transform_ur<2, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else if (g_transform_ur == 2) k_transform_ur<2, 36><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
         else k_transform_ur<4, 18><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(p, cl, up);
+    } else if (f64 && g_transform_hyb == 3 && keep <= F89_G * F89_TH &&
+               (size_t)F89_G * m * F89_UP * 8 <= (size_t)TR_U_BYTES - 64) {
+        const int64_t nt = (pn.n + F89W_R - 1) / F89W_R;
+        k_transform_f89w<<<(int)std::max<int64_t>(1, std::min<int64_t>(nt, ctx->num_sms)), F89_THREADS, TR_SMEM, ctx->stream>>>(p, cl);
     } else if (f64 && g_transform_hyb == 2 && keep <= F89_G * F89_TH &&
                (size_t)F89_G * m * F89_UP * 8 <= (size_t)TR_U_BYTES - 64) {
         k_transform_f89<<<grid_for_rows<double>(ctx, pn.n), F89_THREADS, TR_SMEM, ctx->stream>>>(p, cl);

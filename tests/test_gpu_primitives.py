@@ -298,7 +298,7 @@ def test_basistransform_constant_bank_variants(n, m, keep, mode):
 
 @pytest.mark.parametrize("n,m,keep", [(70001, 60, 36), (5000, 30, 18), (257, 61, 35), (100003, 96, 36), (999, 5, 1),
                                       (4096, 40, 25), (3001, 59, 31), (777, 36, 36)])
-@pytest.mark.parametrize("mode", [4, 5, 6], ids=["dmma+dfma", "dfma8x9", "dmma"])
+@pytest.mark.parametrize("mode", [4, 5, 6, 7], ids=["dmma+dfma", "dfma8x9", "dmma", "dfma8x9-512"])
 def test_basistransform_hybrid_dmma_dfma(n, m, keep, mode):
     """k_transform_hyb (output columns [0, 24) on the FP64 tensor pipe, [24, 36) as register-blocked DFMA, in the same
     warps) and k_transform_f89 (DFMA only, thread <-> 8 rows x 9 outputs) against the dense product, ragged tiles and
