@@ -712,8 +712,8 @@ k_halo_push(const T* __restrict__ x, int64_t n, const __grid_constant__ PeerStep
     __syncthreads();
     if (last && threadIdx.x == 0) {
         __threadfence_system();
-        if (dn) st_release_sys_u64(peer_hflag(pd, pd.rank - 1, ps.seq_halo, 1), ps.seq_halo);
-        if (up) st_release_sys_u64(peer_hflag(pd, pd.rank + 1, ps.seq_halo, 0), ps.seq_halo);
+        if (dn) st_relaxed_sys_u64(peer_hflag(pd, pd.rank - 1, ps.seq_halo, 1), ps.seq_halo);
+        if (up) st_relaxed_sys_u64(peer_hflag(pd, pd.rank + 1, ps.seq_halo, 0), ps.seq_halo);
     }
 }
 

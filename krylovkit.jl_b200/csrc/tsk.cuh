@@ -504,8 +504,8 @@ __device__ __forceinline__ void finalize_block(const FinalizeParams& f, int tid,
             if (ps->seq_alpha) alpha0 = peer_sum1(ps->pd, PEER_CH_ALPHA, ps->seq_alpha, 0);
             if (ps->seq_halo) {       // every CTA fenced its halo stores before taking its ticket
                 __threadfence_system();
-                if (ps->send_lo) st_release_sys_u64(peer_hflag(ps->pd, ps->pd.rank - 1, ps->seq_halo, 1), ps->seq_halo);
-                if (ps->send_hi) st_release_sys_u64(peer_hflag(ps->pd, ps->pd.rank + 1, ps->seq_halo, 0), ps->seq_halo);
+                if (ps->send_lo) st_relaxed_sys_u64(peer_hflag(ps->pd, ps->pd.rank - 1, ps->seq_halo, 1), ps->seq_halo);
+                if (ps->send_hi) st_relaxed_sys_u64(peer_hflag(ps->pd, ps->pd.rank + 1, ps->seq_halo, 0), ps->seq_halo);
             }
         }
     }
