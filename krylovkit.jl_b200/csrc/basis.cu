@@ -1985,9 +1985,9 @@ int32_t lanczos_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec* cols, int32_t k, 
     if (enq > 0) {
         cudaError_t e = cudaMemcpyAsync(ctx->h_res, rec0 + B2K_REC, sizeof(double) * B2K_REC * enq,
                                         cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess)
             return b2k_fail(ctx, B2K_ECUDA, "lanczos_expand_many: %s", cudaGetErrorString(e));
+        B2K_TRY(b2k_stream_sync(ctx));           // ... and the peer-window watchdog latch of the batch
         d = enq;
         for (int32_t i = 0; i < enq; ++i) {
             alphas_out[i] = ctx->h_res[(size_t)B2K_REC * i + 1];
@@ -2239,7 +2239,7 @@ extern "C" int32_t b2k_debug_trace(b2k_ctx* ctx, int32_t on) {
         if (!ctx->d_trace) B2K_CUDA(ctx, cudaMalloc(&ctx->d_trace, sizeof(unsigned long long) * (2 + 2 * B2K_TRACE_CAP)));
         B2K_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, sizeof(unsigned long long) * 2, ctx->stream));
     } else if (ctx->d_trace) {
-        B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B2K_TRY(b2k_stream_sync(ctx));
         cudaFree(ctx->d_trace);
         ctx->d_trace = nullptr;
     }
@@ -2250,7 +2250,7 @@ extern "C" int32_t b2k_debug_trace_read(b2k_ctx* ctx, unsigned long long* out, i
     if (!ctx || !out || !n_events) return B2K_EINVAL;
     *n_events = 0;
     if (!ctx->d_trace) return B2K_OK;
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     unsigned long long cnt = 0;
     B2K_CUDA(ctx, cudaMemcpy(&cnt, ctx->d_trace, sizeof(cnt), cudaMemcpyDeviceToHost));
     if (cnt > B2K_TRACE_CAP) cnt = B2K_TRACE_CAP;

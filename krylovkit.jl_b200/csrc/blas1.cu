@@ -950,7 +950,7 @@ extern "C" int32_t b2k_cg_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_v
         B2K_LAUNCH_CHECK(ctx);
     }
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, rec0, sizeof(double) * B2K_REC * nsteps, cudaMemcpyDeviceToHost, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     int32_t d = nsteps;
     for (int32_t i = 0; i < nsteps; ++i) {
         pq_out[i] = ctx->h_res[(size_t)B2K_REC * i];
@@ -1133,7 +1133,7 @@ extern "C" int32_t b2k_bicgstab_chain(b2k_ctx* ctx, const b2k_op* op, b2k_vec x,
     }
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, rec0, sizeof(double) * B2K_REC * nsteps, cudaMemcpyDeviceToHost,
                                   ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     int32_t d = nsteps;
     for (int32_t i = 0; i < nsteps; ++i)
         if (ctx->h_res[(size_t)B2K_REC * i + 7] != 0.0) { d = i + 1; break; }

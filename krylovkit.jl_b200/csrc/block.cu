@@ -579,7 +579,7 @@ int32_t block_gram_dev(b2k_ctx* ctx, const BPanel& bp, double* d_G) {
 
 int32_t fetch(b2k_ctx* ctx, const double* d, double* h, int count) {
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, d, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     memcpy(h, ctx->h_res, sizeof(double) * count);
     return B2K_OK;
 }
@@ -690,7 +690,7 @@ extern "C" int32_t b2k_block_orthogonalize(b2k_ctx* ctx, const b2k_vec* Rb, int3
     static_assert(2 * HCAP + BK_GRAM <= B2K_RES_DOUBLES, "block results must fit the pinned result buffer");
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_blk, sizeof(double) * (2 * HCAP + BK_GRAM), cudaMemcpyDeviceToHost,
                                   ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     if (H_host)
         for (int t = 0; t < k * p; ++t) H_host[t] = ctx->h_res[t] + (passes == 2 ? ctx->h_res[HCAP + t] : 0.0);
     if (G_host) memcpy(G_host, ctx->h_res + 2 * HCAP, sizeof(double) * p * p);

@@ -241,6 +241,13 @@ constexpr size_t PEER_OFF_HEAP   = PEER_OFF_SLOTS + 8 * (size_t)(PEER_NCH * 2 * 
 struct PeerDev {
     char* win[PEER_MAXR];      // win[p] = rank p's window as mapped in THIS process (win[rank] = own)
     int rank, nranks;
+    // Watchdog of the in-kernel waits (peer_spin): a flag that has not arrived after timeout_ns (0: wait for
+    // ever) latches *err — one int in mapped pinned host memory — and the wait gives up, as does every later
+    // wait as soon as it sees the latch.  The host looks at the latch after each stream synchronisation
+    // (b2k_stream_sync) and fails the call with B2K_ENCCL: a rank of the job died or left the SPMD call order,
+    // and the survivors return an error instead of spinning on the GPU until somebody kills them.
+    int* err;
+    unsigned long long timeout_ns;
 };
 // what one kernel launch needs to know about the exchanges it takes part in (all seq == 0: single GPU)
 struct PeerStep {
@@ -265,6 +272,9 @@ void    b2k_nccl_destroy(b2k_ctx* ctx);
 int32_t b2k_nccl_allreduce_f64(b2k_ctx* ctx, double* dptr, int32_t count);
 // NVLink peer-memory all-reduce of a small vector (dist.cu); b2k_peer_ok says whether it is usable
 bool    b2k_peer_ok(const b2k_ctx* ctx);
+// cudaStreamSynchronize(ctx->stream) + the peer-window watchdog latch (see PeerDev): B2K_ENCCL if an in-kernel
+// wait for another rank timed out in the work just completed.  Every synchronising entry point goes through it.
+int32_t b2k_stream_sync(b2k_ctx* ctx);
 bool    b2k_has_nccl(const b2k_ctx* ctx);
 int32_t b2k_peer_allreduce(b2k_ctx* ctx, double* dptr, int32_t count);
 // device view of the windows + host-side sequence counters (identical on every rank: SPMD call order)
@@ -321,12 +331,28 @@ __device__ __forceinline__ unsigned long long* peer_hflag(const PeerDev& pd, int
 }
 // one thread per rank waits until that rank's contribution `seq` has landed in MY window (local polling);
 // the caller synchronises its threads afterwards
-__device__ __forceinline__ void peer_wait(const PeerDev& pd, int ch, unsigned long long seq, int tid) {
-    if (tid < pd.nranks) {
-        const unsigned long long* f = peer_flag(pd, pd.rank, ch, seq, tid);
-        while (ld_acquire_sys_u64(f) < seq) {
+// Spin on a flag of MY window until it reaches seq.  The fast path is the bare acquire-load loop; every 1024
+// polls (about a millisecond: only a wait that is already hopelessly late gets there) the watchdog described at
+// PeerDev looks at the latch and at the clock.
+__device__ __forceinline__ void peer_spin(const PeerDev& pd, const unsigned long long* f, unsigned long long seq) {
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys_u64(f) < seq) {
+        if ((++polls & 1023u) != 0 || pd.err == nullptr) continue;
+        if (*(volatile int*)pd.err != 0) return;                  // an earlier wait has given up: so do we
+        if (pd.timeout_ns == 0) continue;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > pd.timeout_ns) {
+            *(volatile int*)pd.err = 1;
+            __threadfence_system();
+            return;
         }
     }
+}
+__device__ __forceinline__ void peer_wait(const PeerDev& pd, int ch, unsigned long long seq, int tid) {
+    if (tid < pd.nranks) peer_spin(pd, peer_flag(pd, pd.rank, ch, seq, tid), seq);
 }
 // single-thread publication of ONE double to every rank (SpMV dot epilogue, norm partial)
 __device__ __forceinline__ void peer_publish1(const PeerDev& pd, int ch, unsigned long long seq, double v) {

@@ -338,7 +338,7 @@ extern "C" int32_t b2k_space_create(b2k_ctx* ctx, int64_t n_local, int32_t ncols
 
 extern "C" int32_t b2k_ctx_sync(b2k_ctx* ctx) {
     if (!ctx) return B2K_EINVAL;
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     return B2K_OK;
 }
 
@@ -436,7 +436,7 @@ extern "C" int32_t b2k_vec_upload(b2k_ctx* ctx, b2k_vec v, const void* host) {
     B2K_CUDA(ctx, cudaSetDevice(ctx->device));
     B2K_CUDA(ctx, cudaMemcpyAsync(r.ptr, host, (size_t)r.n * ctx->esize, cudaMemcpyHostToDevice,
                                   ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     return B2K_OK;
 }
 
@@ -447,7 +447,7 @@ extern "C" int32_t b2k_vec_download(b2k_ctx* ctx, b2k_vec v, void* host) {
     B2K_CUDA(ctx, cudaSetDevice(ctx->device));
     B2K_CUDA(ctx, cudaMemcpyAsync(host, r.ptr, (size_t)r.n * ctx->esize, cudaMemcpyDeviceToHost,
                                   ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     return B2K_OK;
 }
 
@@ -492,7 +492,7 @@ int32_t b2k_fetch_results(b2k_ctx* ctx, int32_t count, int32_t sharded) {
     B2K_TRY(b2k_allreduce(ctx, ctx->d_res, count, sharded));
     B2K_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(double) * count,
                                   cudaMemcpyDeviceToHost, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     return B2K_OK;
 }
 
@@ -554,7 +554,7 @@ extern "C" int32_t b2k_prof_enable(b2k_ctx* ctx, int32_t on) {
 
 extern "C" int32_t b2k_prof_reset(b2k_ctx* ctx) {
     if (!ctx) return B2K_EINVAL;
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     ctx->prof.recs.clear();
     ctx->prof.next = 0;
     return B2K_OK;
@@ -563,7 +563,7 @@ extern "C" int32_t b2k_prof_reset(b2k_ctx* ctx) {
 extern "C" int32_t b2k_prof_read(b2k_ctx* ctx, int32_t cls, int64_t* count, double* ms,
                                  double* bytes) {
     if (!ctx || cls < 0 || cls >= B2K_PROF_CLASSES) return B2K_EINVAL;
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     int64_t c = 0;
     double t = 0.0, b = 0.0;
     for (const B2kProfRec& r : ctx->prof.recs) {
@@ -605,7 +605,7 @@ extern "C" int32_t b2k_timer_start(b2k_ctx* ctx) {
         B2K_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
         B2K_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
     }
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     B2K_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
     return B2K_OK;
 }

@@ -48,6 +48,7 @@ struct B2kNccl {
     char* win_local = nullptr;          // my window (cudaMalloc)
     size_t win_bytes = 0, heap_used = 0;
     PeerDev pd;
+    int* h_err = nullptr;               // watchdog latch of the in-kernel waits (mapped pinned; see PeerDev)
     unsigned long long seq[5] = {0, 0, 0, 0, 0};   // channels 0..3 + halo
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
@@ -212,6 +213,25 @@ static void peer_setup(b2k_ctx* ctx, B2kNccl* n) {
     n->pd.rank = ctx->rank;
     n->pd.nranks = R;
     n->peer_ok = good != 0;
+    if (n->peer_ok) {
+        // watchdog latch: one int the kernels can write and the host can read without a copy.  Without it (the
+        // allocation failed) the waits are the plain unbounded loops.
+        const char* e = getenv("B2K_PEER_TIMEOUT_S");
+        const double secs = e ? atof(e) : 120.0;
+        void* dp = nullptr;
+        if (cudaHostAlloc((void**)&n->h_err, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(&dp, n->h_err, 0) == cudaSuccess) {
+            *n->h_err = 0;
+            n->pd.err = (int*)dp;
+            n->pd.timeout_ns = secs > 0.0 ? (unsigned long long)(secs * 1e9) : 0ull;
+        } else {
+            cudaGetLastError();
+            if (n->h_err) cudaFreeHost(n->h_err);
+            n->h_err = nullptr;
+            n->pd.err = nullptr;
+            n->pd.timeout_ns = 0;
+        }
+    }
     n->heap_used = 0;
     for (int c = 0; c < 5; ++c) n->seq[c] = 0;
     if (!n->peer_ok && n->win_local) {
@@ -223,6 +243,17 @@ static void peer_setup(b2k_ctx* ctx, B2kNccl* n) {
 }
 
 bool b2k_peer_ok(const b2k_ctx* ctx) { return ctx->nccl && ctx->nccl->peer_ok; }
+
+int32_t b2k_stream_sync(b2k_ctx* ctx) {
+    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const B2kNccl* n = ctx->nccl;
+    if (n && n->h_err && *(volatile int*)n->h_err != 0)
+        return b2k_fail(ctx, B2K_ENCCL,
+                        "peer window: an in-kernel wait for another rank's flag timed out (B2K_PEER_TIMEOUT_S, "
+                        "default 120 s) - a rank of the job has died or left the SPMD call order; the results of "
+                        "this rank are invalid and the context must be destroyed");
+    return B2K_OK;
+}
 bool b2k_has_nccl(const b2k_ctx* ctx) { return ctx->nccl && ctx->nccl->comm != nullptr; }
 const PeerDev* b2k_peer_dev(const b2k_ctx* ctx) { return &ctx->nccl->pd; }
 char* b2k_peer_local(const b2k_ctx* ctx) { return ctx->nccl->win_local; }
@@ -259,6 +290,9 @@ static int g_comm_rank = -1, g_comm_nranks = -1, g_comm_device = -1;
 static bool g_comm_in_use = false;
 
 int32_t b2k_nccl_init(b2k_ctx* ctx, const void* uid) {
+    if (g_comm_cache && !g_comm_in_use && g_comm_cache->h_err && *(volatile int*)g_comm_cache->h_err != 0)
+        return b2k_fail(ctx, B2K_ENCCL, "the peer window of this process is out of step with its peers (an "
+                                        "in-kernel wait timed out in an earlier context); restart the job");
     if (g_comm_cache && !g_comm_in_use && g_comm_rank == ctx->rank && g_comm_nranks == ctx->nranks &&
         g_comm_device == ctx->device) {
         ctx->nccl = g_comm_cache;
@@ -318,6 +352,7 @@ void b2k_nccl_destroy(b2k_ctx* ctx) {
         for (int p = 0; p < ctx->nranks; ++p)
             if (p != ctx->rank) cudaIpcCloseMemHandle(ctx->nccl->pd.win[p]);
     if (ctx->nccl->win_local) cudaFree(ctx->nccl->win_local);
+    if (ctx->nccl->h_err) cudaFreeHost(ctx->nccl->h_err);
     rv_close(&ctx->nccl->rv);
     if (ctx->nccl->comm) ctx->nccl->CommDestroy(ctx->nccl->comm);
     delete ctx->nccl;

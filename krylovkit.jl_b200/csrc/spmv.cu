@@ -72,8 +72,8 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
     if (ps.on && ps.seq_halo) {        // boundary rows of x arrive from the neighbours through the peer window
         if (threadIdx.x == 0) {
-            if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
-            if (ps.wait_hi) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1)) < ps.seq_halo) {}
+            if (ps.wait_lo) peer_spin(ps.pd, peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0), ps.seq_halo);
+            if (ps.wait_hi) peer_spin(ps.pd, peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1), ps.seq_halo);
         }
         __syncthreads();
     }
@@ -278,8 +278,8 @@ k_spmv_pipe(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ coli
     if (tr0) b2k_trace(fz.trace, 1);
     if (ps.on && ps.seq_halo) {        // boundary rows of x arrive from the neighbours through the peer window;
         if (tid == 0) {                // the producer warp streams the matrix meanwhile
-            if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
-            if (ps.wait_hi) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1)) < ps.seq_halo) {}
+            if (ps.wait_lo) peer_spin(ps.pd, peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0), ps.seq_halo);
+            if (ps.wait_hi) peer_spin(ps.pd, peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1), ps.seq_halo);
         }
         named_bar_sync(1, SPP_CONS);
     }
@@ -594,8 +594,8 @@ k_stencil_apply(const __grid_constant__ StencilApply sa, const T* __restrict__ x
     if (fz.stop && *reinterpret_cast<const volatile int*>(fz.stop)) return;
     if (ps.on && ps.seq_halo) {
         if (threadIdx.x == 0) {
-            if (ps.wait_lo) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0)) < ps.seq_halo) {}
-            if (ps.wait_hi) while (ld_acquire_sys_u64(peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1)) < ps.seq_halo) {}
+            if (ps.wait_lo) peer_spin(ps.pd, peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 0), ps.seq_halo);
+            if (ps.wait_hi) peer_spin(ps.pd, peer_hflag(ps.pd, ps.pd.rank, ps.seq_halo, 1), ps.seq_halo);
         }
         __syncthreads();
     }
@@ -868,7 +868,7 @@ int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
         B2K_LAUNCH_CHECK(ctx);
     }
     B2K_CUDA(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     B2K_DFREE(d_stats);
     if (h_stats[1] != 0) return b2k_fail(ctx, B2K_EINVAL, "CSR: rowptr is not non-decreasing");
     const int maxrow = h_stats[0];
@@ -884,13 +884,13 @@ int32_t finish_csr(b2k_ctx* ctx, b2k_op* op) {
         std::vector<int32_t> h_rowptr(n + 1), blk;
         B2K_CUDA(ctx, cudaMemcpyAsync(h_rowptr.data(), op->rowptr, sizeof(int32_t) * (n + 1),
                                       cudaMemcpyDeviceToHost, ctx->stream));
-        B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B2K_TRY(b2k_stream_sync(ctx));
         build_rowblocks(h_rowptr.data(), n, &blk);
         op->nblk = (int32_t)blk.size() - 1;
         B2K_CUDA(ctx, B2K_DMALLOC(&op->rowblk, sizeof(int32_t) * blk.size()));
         B2K_CUDA(ctx, cudaMemcpyAsync(op->rowblk, blk.data(), sizeof(int32_t) * blk.size(),
                                       cudaMemcpyHostToDevice, ctx->stream));
-        B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B2K_TRY(b2k_stream_sync(ctx));
     }
     B2K_CUDA(ctx, B2K_DMALLOC(&op->pblk, sizeof(int32_t) * (op->nblk + 1)));
     k_pblk<<<(op->nblk + 1 + 255) / 256, 256, 0, ctx->stream>>>(op->rowptr, op->rowblk, op->nblk + 1, op->pblk);
@@ -931,7 +931,7 @@ int32_t plan_halo(b2k_ctx* ctx, b2k_op* op, const int64_t* d_gcol) {
     }
     unsigned long long mm[2];
     B2K_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     B2K_DFREE(d_mm);
     const int64_t col0 = ctx->row_offset, n_loc = op->n_loc_cols;
     int64_t lo = 0, hi = 0;
@@ -1307,7 +1307,7 @@ extern "C" int32_t b2k_op_create_dense(b2k_ctx* ctx, b2k_op** out, int64_t m_loc
     B2K_CUDA(ctx, cudaMemcpy2DAsync(op->A, (size_t)op->ld * ctx->esize, host_colmajor,
                                     (size_t)ld * ctx->esize, (size_t)m_local * ctx->esize, n,
                                     cudaMemcpyHostToDevice, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     return B2K_OK;
 }
 
@@ -1372,7 +1372,7 @@ extern "C" int32_t b2k_op_csr_download(b2k_ctx* ctx, const b2k_op* op, int32_t* 
     if (vals)
         B2K_CUDA(ctx, cudaMemcpyAsync(vals, op->vals, (size_t)ctx->esize * op->nnz,
                                       cudaMemcpyDeviceToHost, ctx->stream));
-    B2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2K_TRY(b2k_stream_sync(ctx));
     return B2K_OK;
 }
 

@@ -55,3 +55,10 @@ def test_row_sharded_three_ranks_on_one_gpu():
     converged eigsolve and the device-chained fixed-cycle job against the serial oracle (the short form of dist_check)."""
     _run(29615, {"B2K_ONE_GPU": "1", "DIST_CHECK_SHORT": "1",
                  "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]}, nproc=3)
+
+
+def test_peer_wait_watchdog():
+    """A rank that drops out must not leave the others spinning inside a kernel: the in-kernel waits of the peer
+    window give up after B2K_PEER_TIMEOUT_S and the call fails with B2K_ENCCL (tools/dist_check.py: watchdog_check)."""
+    _run(29617, {"B2K_ONE_GPU": "1", "DIST_CHECK_WATCHDOG": "1",
+                 "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]}, timeout=240)

@@ -25,6 +25,36 @@ from krylovkit_jl_b200 import sharding  # noqa: E402
 from oracle import krylov_oracle as ko  # noqa: E402
 
 
+def watchdog_check(rank, world, local):
+    """DIST_CHECK_WATCHDOG=1: a rank that leaves the SPMD call order must not leave its peers spinning on the GPU.
+    Rank 0 calls one all-reduce more than the others; its in-kernel wait for the missing flags gives up after
+    B2K_PEER_TIMEOUT_S and the call returns B2K_ENCCL (csrc/common.cuh: peer_spin, csrc/dist.cu: b2k_stream_sync)."""
+    import time
+    os.environ["B2K_PEER_TIMEOUT_S"] = "2"
+    uid = sharding.broadcast_nccl_uid(dist, kk._lib.load())
+    n_loc = 4096
+    ctx = kk.B200Context(n_loc, 8, device=local, rank=rank, nranks=world, nccl_uid=uid,
+                         n_global=n_loc * world, row_offset=n_loc * rank)
+    x = ctx.splitmix(7)
+    nrm = x.norm()                                  # every rank takes part: works
+    assert nrm > 0.0
+    dist.barrier()
+    if rank == 0:
+        t0 = time.time()
+        try:
+            x.norm()                                # nobody else comes
+        except kk.B200Error as e:
+            assert "timed out" in str(e), str(e)
+            dt = time.time() - t0
+            assert 1.5 < dt < 60.0, dt
+            print(f"dist_check ok on {world} ranks (watchdog): B2K_ENCCL after {dt:.1f} s")
+        else:
+            raise AssertionError("the lone all-reduce returned without an error")
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     one_gpu = os.environ.get("B2K_ONE_GPU", "") == "1"
@@ -36,6 +66,8 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = "cpu" if one_gpu else "cuda"
+    if os.environ.get("DIST_CHECK_WATCHDOG", "") == "1":
+        return watchdog_check(rank, world, local)
     uid = sharding.broadcast_nccl_uid(dist, kk._lib.load())
     nx, ny = 200, 151
     n = nx * ny
