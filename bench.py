@@ -74,10 +74,14 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=30, help="expand! steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra", default="c2f,c3,c4,c5",
+    ap.add_argument("--extra", default=None,
                     help="other BASELINE.json configs measured after the headline (records under 'other_configs'); "
-                         "'' = none")
-    return ap.parse_args()
+                         "'' = none.  Default: c2f,c3,c4,c5 on one GPU; c5 — the configuration BASELINE.json names "
+                         "for 8 GPUs — under torchrun")
+    a = ap.parse_args()
+    if a.extra is None:
+        a.extra = "c2f,c3,c4,c5" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
+    return a
 
 
 # ---------------------------------------------------------------------------------------
@@ -551,6 +555,18 @@ def other_configs(kk, a, rank, world, local_rank, dist):
         gold = json.load(open(gp))
     out = {}
 
+    def config_failed(e, ctx):
+        """an exception inside one of the extra configs (raised alike on every rank: the host logic is
+        rank-replicated) becomes that config's record; its context is closed so the next one finds the memory"""
+        import traceback
+        sys.stderr.write(traceback.format_exc())
+        try:
+            if ctx is not None:
+                ctx.close()
+        except Exception:
+            pass
+        return {"ok": False, "error": f"{type(e).__name__}: {e}"[:600]}
+
     def make_ctx(n_lines, line, ncols, dtype=np.float64):
         n = n_lines * line
         if world == 1:
@@ -579,110 +595,127 @@ def other_configs(kk, a, rank, world, local_rank, dist):
         return res, t
 
     if "c2f" in want:
-        # the headline job with the MATRIX-FREE stencil operator (KrylovKit takes any function as its linear map):
-        # same arithmetic, same Ritz values, 16n instead of 12 nnz + 20n bytes per operator application
-        ctx, n = make_ctx(a.ny, a.nx, a.krylovdim + 2 * HOWMANY + 8)
-        op = kk.B200CSR.stencil_free(ctx, a.nx, a.ny)
-        x0 = ctx.splitmix(SEED)
-        orth = {"cgs2": kk.cgs2, "mgs2": kk.mgs2, "cgs": kk.cgs, "mgs": kk.mgs, "mgs2b": kk.mgs2b}[a.orth]
-        alg = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=a.cycles, tol=0.0, verbosity=0)
-        (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, HOWMANY, "SR", alg))
-        del vecs
-        out["c2_matrix_free"] = {
-            "workload": workload_config(a)["workload"].replace("CSR 5-point", "matrix-free 5-point"),
-            "numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
-            "ritz": [float(v) for v in vals[:HOWMANY]], "parity": check_parity(a, vals, info.numops, "matrix-free operator")}
-        ctx.close()
+        ctx = None
+        try:
+            # the headline job with the MATRIX-FREE stencil operator (KrylovKit takes any function as its linear map):
+            # same arithmetic, same Ritz values, 16n instead of 12 nnz + 20n bytes per operator application
+            ctx, n = make_ctx(a.ny, a.nx, a.krylovdim + 2 * HOWMANY + 8)
+            op = kk.B200CSR.stencil_free(ctx, a.nx, a.ny)
+            x0 = ctx.splitmix(SEED)
+            orth = {"cgs2": kk.cgs2, "mgs2": kk.mgs2, "cgs": kk.cgs, "mgs": kk.mgs, "mgs2b": kk.mgs2b}[a.orth]
+            alg = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=a.cycles, tol=0.0, verbosity=0)
+            (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, HOWMANY, "SR", alg))
+            del vecs
+            out["c2_matrix_free"] = {
+                "workload": workload_config(a)["workload"].replace("CSR 5-point", "matrix-free 5-point"),
+                "numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
+                "ritz": [float(v) for v in vals[:HOWMANY]], "parity": check_parity(a, vals, info.numops, "matrix-free operator")}
+            ctx.close()
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["c2_matrix_free"] = config_failed(e, ctx)
 
     if "c3" in want:
-        nx, ny, kd = 4000, 2500, 40
-        ctx, n = make_ctx(ny, nx, kd + 16)
-        op = kk.B200CSR.stencil(ctx, nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0))
-        ones = ctx.full(1.0)
-        b = kk.apply(op, ones)
-        rec = {"workload": f"linsolve(GMRES, krylovdim={kd}) on the {n}x{n} convection-diffusion CSR (5-point, "
-                           "nonsymmetric), b = A*1, x0 = 0, 5 restart cycles (tol -> 0: fixed work)"}
-        for name, orth, gname in (("cgs2", kk.cgs2, "c3"), ("mgs2_reference_default", kk.mgs2, None),
-                                  ("mgs2_blocked_flagged", kk.mgs2b, None)):
-            alg = kk.GMRES(orth=orth, krylovdim=kd, maxiter=5, tol=1e-300, verbosity=0)
-            (x, info), t = timed(ctx, lambda: kk.linsolve(op, b, None, alg))
-            chk = kk.apply(op, x)
-            chk.add_(info.residual, 1.0).add_(b, -1.0)          # b = A x + r  (test/linsolve.jl:230)
-            r = {"numops": info.numops, "numiter": info.numiter, "ms": 1000 * t, "value": info.numops / t,
-                 "unit": "it/s", "normres": float(info.normres), "||A x + r - b||/||b||": chk.norm() / b.norm()}
-            g = gold.get(gname, {}).get("after_cycles", {}).get("5") if gname else None
-            if g:
-                rel = abs(info.normres - g["normres"]) / g["normres"]
-                xn = x.norm()
-                r["parity"] = {"against": f"tests/golden/fullsize.json:{gname}:after_cycles[5] (oracle at full size)",
-                               "numops_oracle": g["numops"], "normres_rel_diff": rel,
-                               "x_norm_rel_diff": abs(xn - g["x_norm"]) / g["x_norm"],
-                               "ok": bool(info.numops == g["numops"] and rel <= 1e-8 and abs(xn - g["x_norm"]) <= 1e-10 * g["x_norm"])}
-                if not r["parity"]["ok"]:
-                    raise AssertionError(f"config 3: parity with the oracle lost: {r}")
-            rec[name] = r
-            del x, info, chk
-        out["c3"] = rec
-        ctx.close()
+        ctx = None
+        try:
+            nx, ny, kd = 4000, 2500, 40
+            ctx, n = make_ctx(ny, nx, kd + 16)
+            op = kk.B200CSR.stencil(ctx, nx, ny, 1, (4.0, -1.4, -0.6, -1.2, -0.8, 0.0, 0.0))
+            ones = ctx.full(1.0)
+            b = kk.apply(op, ones)
+            rec = {"workload": f"linsolve(GMRES, krylovdim={kd}) on the {n}x{n} convection-diffusion CSR (5-point, "
+                               "nonsymmetric), b = A*1, x0 = 0, 5 restart cycles (tol -> 0: fixed work)"}
+            for name, orth, gname in (("cgs2", kk.cgs2, "c3"), ("mgs2_reference_default", kk.mgs2, None),
+                                      ("mgs2_blocked_flagged", kk.mgs2b, None)):
+                alg = kk.GMRES(orth=orth, krylovdim=kd, maxiter=5, tol=1e-300, verbosity=0)
+                (x, info), t = timed(ctx, lambda: kk.linsolve(op, b, None, alg))
+                chk = kk.apply(op, x)
+                chk.add_(info.residual, 1.0).add_(b, -1.0)          # b = A x + r  (test/linsolve.jl:230)
+                r = {"numops": info.numops, "numiter": info.numiter, "ms": 1000 * t, "value": info.numops / t,
+                     "unit": "it/s", "normres": float(info.normres), "||A x + r - b||/||b||": chk.norm() / b.norm()}
+                g = gold.get(gname, {}).get("after_cycles", {}).get("5") if gname else None
+                if g:
+                    rel = abs(info.normres - g["normres"]) / g["normres"]
+                    xn = x.norm()
+                    r["parity"] = {"against": f"tests/golden/fullsize.json:{gname}:after_cycles[5] (oracle at full size)",
+                                   "numops_oracle": g["numops"], "normres_rel_diff": rel,
+                                   "x_norm_rel_diff": abs(xn - g["x_norm"]) / g["x_norm"],
+                                   "ok": bool(info.numops == g["numops"] and rel <= 1e-8 and abs(xn - g["x_norm"]) <= 1e-10 * g["x_norm"])}
+                    if not r["parity"]["ok"]:
+                        raise AssertionError(f"config 3: parity with the oracle lost: {r}")
+                rec[name] = r
+                del x, info, chk
+            out["c3"] = rec
+            ctx.close()
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["c3"] = config_failed(e, ctx)
 
     if "c4" in want and world == 1:
-        m, nn, kd = 2_000_000, 512, 30
-        ctx = kk.B200Context(m, kd + 24, dtype=np.float32, device=local_rank)
-        sv = ctx.add_space(nn, kd + 24, sharded=False)
-        op = kk.B200Dense.splitmix(ctx, m, nn, SEED, sv)
-        u0 = ctx.splitmix(SEED + 1)
-        rec = {"workload": f"svdsolve(GKL, krylovdim={kd}, tol=1e-5) on the dense {m}x{nn} Float32 matrix (splitmix "
-                           "entries in (-0.5, 0.5)), 6 triplets :LR",
-               "note": "with ClassicalGramSchmidt2 the Float32 recurrence loses orthogonality on this clustered spectrum "
-                       "(in the CPU oracle too) and the driver raises B200Error; reported with the reference's default "
-                       "orthogonalizer and with the iterative-refinement one its Float32 tests use (test/runtests.jl:18)"}
-        for name, orth in (("mgs2_reference_default", kk.mgs2), ("cgsr_eta0.75", kk.ClassicalGramSchmidtIR(eta=0.75)),
-                           ("cgs2", kk.cgs2)):
-            alg = kk.GKL(orth=orth, krylovdim=kd, maxiter=100, tol=1e-5, verbosity=0)
-            try:
-                (S, Lv, Rv, info), t = timed(ctx, lambda: kk.svdsolve(op, u0, 6, "LR", alg))
-            except kk.B200Error as e:
-                rec[name] = {"raised": "B200Error: " + str(e)[:160]}
-                continue
-            res = []
-            for i in range(3):                                  # A v = s u + r, A' u = s v on the device
-                w = kk.apply_normal(op, Rv[i])
-                w.add_(Lv[i], -float(S[i]))
-                z = kk.apply_adjoint(op, Lv[i])
-                z.add_(Rv[i], -float(S[i]))
-                res.append([float(w.norm() / S[i]), float(z.norm() / S[i])])
-            rec[name] = {"numops": info.numops, "numiter": info.numiter, "converged": info.converged, "ms": 1000 * t,
-                         "value": info.numops / t, "unit": "it/s", "sigma": [float(v) for v in S[:6]],
-                         "rel_residuals(Av-su, A'u-sv)": res}
-            del Lv, Rv, info
-        out["c4"] = rec
-        ctx.close()
+        ctx = None
+        try:
+            m, nn, kd = 2_000_000, 512, 30
+            ctx = kk.B200Context(m, kd + 24, dtype=np.float32, device=local_rank)
+            sv = ctx.add_space(nn, kd + 24, sharded=False)
+            op = kk.B200Dense.splitmix(ctx, m, nn, SEED, sv)
+            u0 = ctx.splitmix(SEED + 1)
+            rec = {"workload": f"svdsolve(GKL, krylovdim={kd}, tol=1e-5) on the dense {m}x{nn} Float32 matrix (splitmix "
+                               "entries in (-0.5, 0.5)), 6 triplets :LR",
+                   "note": "with ClassicalGramSchmidt2 the Float32 recurrence loses orthogonality on this clustered spectrum "
+                           "(in the CPU oracle too) and the driver raises B200Error; reported with the reference's default "
+                           "orthogonalizer and with the iterative-refinement one its Float32 tests use (test/runtests.jl:18)"}
+            for name, orth in (("mgs2_reference_default", kk.mgs2), ("cgsr_eta0.75", kk.ClassicalGramSchmidtIR(eta=0.75)),
+                               ("cgs2", kk.cgs2)):
+                alg = kk.GKL(orth=orth, krylovdim=kd, maxiter=100, tol=1e-5, verbosity=0)
+                try:
+                    (S, Lv, Rv, info), t = timed(ctx, lambda: kk.svdsolve(op, u0, 6, "LR", alg))
+                except kk.B200Error as e:
+                    rec[name] = {"raised": "B200Error: " + str(e)[:160]}
+                    continue
+                res = []
+                for i in range(3):                                  # A v = s u + r, A' u = s v on the device
+                    w = kk.apply_normal(op, Rv[i])
+                    w.add_(Lv[i], -float(S[i]))
+                    z = kk.apply_adjoint(op, Lv[i])
+                    z.add_(Rv[i], -float(S[i]))
+                    res.append([float(w.norm() / S[i]), float(z.norm() / S[i])])
+                rec[name] = {"numops": info.numops, "numiter": info.numiter, "converged": info.converged, "ms": 1000 * t,
+                             "value": info.numops / t, "unit": "it/s", "sigma": [float(v) for v in S[:6]],
+                             "rel_residuals(Av-su, A'u-sv)": res}
+                del Lv, Rv, info
+            out["c4"] = rec
+            ctx.close()
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["c4"] = config_failed(e, ctx)
 
     if "c5" in want:
-        nx, ny, nz, kd = 625, 500, 256, 30
-        ctx, n = make_ctx(nz, nx * ny, kd + 14)
-        op = kk.B200CSR.stencil(ctx, nx, ny, nz, (6.0, -1, -1, -1, -1, -1, -1))
-        x0 = ctx.splitmix(SEED)
-        alg = kk.Lanczos(orth=kk.cgs2, krylovdim=kd, maxiter=3, tol=0.0, verbosity=0)
-        (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, 4, "SR", alg))
-        del vecs
-        lam_min = 6.0 - 2.0 * (np.cos(np.pi / (nx + 1)) + np.cos(np.pi / (ny + 1)) + np.cos(np.pi / (nz + 1)))
-        rec = {"workload": f"eigsolve(Lanczos, :SR, 4) on the {n}x{n} 7-point Laplacian ({nx}x{ny}x{nz}), Float64, "
-                           f"krylovdim={kd}, orth=cgs2, 3 restart cycles, rows sharded by z-planes over {world} GPU(s)",
-               "numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
-               "ritz": [float(v) for v in vals[:4]], "closed_form_lambda_min": float(lam_min),
-               "ritz_above_lambda_min": bool(vals[0] >= lam_min * (1 - 1e-12))}
-        g = gold.get("c5", {}).get("after_cycles", {}).get("3")
-        if g:
-            ref = np.array(g["ritz"])
-            rel = float(np.max(np.abs(np.array(vals[:4]) - ref) / np.abs(ref)))
-            rec["parity"] = {"against": "tests/golden/fullsize.json:c5:after_cycles[3] (oracle at full size)",
-                             "max_rel_diff_ritz": rel, "numops_oracle": g["numops"],
-                             "ok": bool(rel <= 1e-10 and info.numops == g["numops"])}
-            if not rec["parity"]["ok"]:
-                raise AssertionError(f"config 5: parity with the oracle lost: {rec}")
-        out["c5"] = rec
-        ctx.close()
+        ctx = None
+        try:
+            nx, ny, nz, kd = 625, 500, 256, 30
+            ctx, n = make_ctx(nz, nx * ny, kd + 14)
+            op = kk.B200CSR.stencil(ctx, nx, ny, nz, (6.0, -1, -1, -1, -1, -1, -1))
+            x0 = ctx.splitmix(SEED)
+            alg = kk.Lanczos(orth=kk.cgs2, krylovdim=kd, maxiter=3, tol=0.0, verbosity=0)
+            (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, 4, "SR", alg))
+            del vecs
+            lam_min = 6.0 - 2.0 * (np.cos(np.pi / (nx + 1)) + np.cos(np.pi / (ny + 1)) + np.cos(np.pi / (nz + 1)))
+            rec = {"workload": f"eigsolve(Lanczos, :SR, 4) on the {n}x{n} 7-point Laplacian ({nx}x{ny}x{nz}), Float64, "
+                               f"krylovdim={kd}, orth=cgs2, 3 restart cycles, rows sharded by z-planes over {world} GPU(s)",
+                   "numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
+                   "ritz": [float(v) for v in vals[:4]], "closed_form_lambda_min": float(lam_min),
+                   "ritz_above_lambda_min": bool(vals[0] >= lam_min * (1 - 1e-12))}
+            g = gold.get("c5", {}).get("after_cycles", {}).get("3")
+            if g:
+                ref = np.array(g["ritz"])
+                rel = float(np.max(np.abs(np.array(vals[:4]) - ref) / np.abs(ref)))
+                rec["parity"] = {"against": "tests/golden/fullsize.json:c5:after_cycles[3] (oracle at full size)",
+                                 "max_rel_diff_ritz": rel, "numops_oracle": g["numops"],
+                                 "ok": bool(rel <= 1e-10 and info.numops == g["numops"])}
+                if not rec["parity"]["ok"]:
+                    raise AssertionError(f"config 5: parity with the oracle lost: {rec}")
+            out["c5"] = rec
+            ctx.close()
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["c5"] = config_failed(e, ctx)
+
     return out
 
 
