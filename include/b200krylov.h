@@ -42,7 +42,10 @@ extern "C" {
 #define B2K_EDIM         -2  /* -> DimensionMismatch (orthonormal.jl:93,140,158-161)        */
 #define B2K_ECUDA        -3  /* CUDA runtime failure                                        */
 #define B2K_ENOMEM       -4  /* slab has no free column / device allocation failed           */
-#define B2K_ENCCL        -5  /* NCCL failure                                                */
+#define B2K_ENCCL        -5  /* multi-GPU transport failure: NCCL, the NVLink peer-window
+                                * rendezvous, or the watchdog of an in-kernel wait for another
+                                * rank (B2K_PEER_TIMEOUT_S, default 120 s): a peer died or left
+                                * the SPMD call order; destroy the context                  */
 #define B2K_ENOTSUP      -6  /* combination not supported by this build                      */
 
 /* dtypes (real only; KrylovKit also supports complex — out of scope) */
