@@ -46,7 +46,7 @@ def watchdog_check(rank, world, local):
         except kk.B200Error as e:
             assert "timed out" in str(e), str(e)
             dt = time.time() - t0
-            assert 1.5 < dt < 60.0, dt
+            assert 1.0 < dt < 150.0, dt             # 2 s on an idle box (profiles/r02_watchdog_test.txt)
             print(f"dist_check ok on {world} ranks (watchdog): B2K_ENCCL after {dt:.1f} s")
         else:
             raise AssertionError("the lone all-reduce returned without an error")
