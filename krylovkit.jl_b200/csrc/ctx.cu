@@ -317,6 +317,7 @@ extern "C" int32_t b2k_ctx_destroy(b2k_ctx* ctx) {
     if (ctx->d_steps) B2K_DFREE(ctx->d_steps);
     if (ctx->d_blk) B2K_DFREE(ctx->d_blk);
     if (ctx->d_blkpart) B2K_DFREE(ctx->d_blkpart);
+    if (ctx->d_trace) cudaFree(ctx->d_trace);           // b2k_debug_trace left on
     if (ctx->ev_coef) cudaEventDestroy(ctx->ev_coef);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
