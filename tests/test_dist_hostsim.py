@@ -105,6 +105,25 @@ def _worker(rank, world, port, out, fused):
         np.testing.assert_allclose(gather(w), ow, rtol=1e-9, atol=1e-12)
         report["ok"] = True
         ctx.close()
+
+        # the host-buffer (end-to-end) entry in its row-sharded form — what bench.py's e2e leg calls on every rank:
+        # local rows as a CSR triple with GLOBAL column indices, the local slice of x0, Ritz vectors into
+        # caller-provided host arrays; a context per call, twice (the second call reuses what the first left)
+        Aloc = A[sl].tocsr()
+        alg = kk.Lanczos(orth=kk.cgs2, krylovdim=20, maxiter=3, tol=0.0, verbosity=0)
+        ovals, ovecs, oinfo = ko.eigsolve_lanczos(A, x0, 2, "SR", krylovdim=20, maxiter=3, tol=0.0, orth=ko.Orth(ko.CGS2))
+        for _ in range(2):
+            outs = [np.empty(shard.n_local) for _ in range(2)]
+            vals, vecs_h, info = kk.eigsolve((Aloc.indptr.astype(np.int32), Aloc.indices.astype(np.int32), Aloc.data),
+                                             x0[sl].copy(), 2, "SR", alg, out_vectors=outs, shard=shard,
+                                             nccl_uid=bytes(128))
+            assert info.numops == oinfo["numops"]
+            np.testing.assert_allclose(vals[:2], ovals[:2], rtol=1e-10)
+            assert vecs_h[0] is outs[0]                          # written in place
+            parts = [None] * world
+            dist.all_gather_object(parts, outs[0])
+            vg = np.concatenate(parts)
+            assert abs(abs(vg @ ovecs[0]) - 1.0) < 1e-8          # the oracle's Ritz vector up to sign
     if rank == 0:
         np.save(out, np.array(report["lanczos"]))
     dist.barrier()
