@@ -226,3 +226,63 @@ def test_driver_agrees_with_oracle(seed):
         ctx = kk.B200Context(n, 600)
         KINDS[seed % len(KINDS)](rng, seed, ctx, n)
         ctx.close()
+
+
+def _blocklanczos_fast_block(rng, seed, ctx, n):
+    """The flagged block mode (SpMM + BCGS2 + CholeskyQR2, falling back to the reference block_qr! when a pivot is
+    too small): a different orthogonalisation, the same counts and Ritz values as the reference algorithm."""
+    A = sp.csr_matrix(_sym(rng.standard_normal((n, n))))
+    p = int(rng.integers(1, 5))
+    X0 = [rng.random(n) for _ in range(p)]
+    if p > 1 and seed % 8 == 4:
+        X0[1] = 2 * X0[0]
+    kd = int(rng.integers(p + 1, min(n, 18) + 1))
+    hm = int(rng.integers(1, kd + 1))
+    alg = kk.BlockLanczos(krylovdim=kd, maxiter=int(rng.integers(1, 5)), tol=1e-9, qr_tol=1e-10,
+                          eager=bool(rng.integers(0, 2)), verbosity=0, fast_block=True)
+    D, V, info = kk.eigsolve(kk.B200CSR.from_scipy(ctx, A), kk.Block([ctx.from_host(x) for x in X0]), hm, "SR", alg)
+    oD, _, oinfo = ko.eigsolve_blocklanczos(A, [x.copy() for x in X0], hm, "SR", krylovdim=kd, maxiter=alg.maxiter,
+                                            tol=1e-9, qr_tol=1e-10, eager=alg.eager)
+    _counts(info, oinfo)
+    assert len(D) == len(oD)
+    np.testing.assert_allclose(D, oD, rtol=1e-6, atol=1e-8)
+    for i in range(min(2, len(V))):                                    # A v = λ v + r
+        assert np.linalg.norm(A @ V[i].to_host() - D[i] * V[i].to_host() - info.residual[i].to_host()) < 1e-8
+    del V, info
+
+
+def _blocked_mgs2(rng, seed, ctx, n):
+    """The flagged blocked form of the reference-default orthogonalizer (kk.mgs2b) in the Lanczos and GMRES drivers
+    against the oracle's literal ModifiedGramSchmidt2."""
+    A = sp.csr_matrix(_sym(rng.standard_normal((n, n))))
+    x0 = rng.random(n)
+    kd = int(rng.integers(2, min(n, 20) + 1))
+    hm = int(rng.integers(1, kd + 1))
+    which = ["SR", "LR", "LM"][int(rng.integers(0, 3))]
+    mi, eager = int(rng.integers(1, 8)), bool(rng.integers(0, 2))
+    alg = kk.Lanczos(orth=kk.mgs2b, krylovdim=kd, maxiter=mi, tol=1e-9, eager=eager, verbosity=0)
+    D, _, info = kk.eigsolve(kk.B200CSR.from_scipy(ctx, A), ctx.from_host(x0), hm, which, alg)
+    oD, _, oinfo = ko.eigsolve_lanczos(A, x0, hm, which, krylovdim=kd, maxiter=mi, tol=1e-9, orth=ko.Orth(ko.MGS2), eager=eager)
+    _counts(info, oinfo)
+    np.testing.assert_allclose(D, oD, rtol=1e-7, atol=1e-9)
+    G = sp.csr_matrix(np.eye(n) * 3 + 0.5 * (rng.random((n, n)) - 0.5))
+    b = rng.random(n)
+    kd, mi = int(rng.integers(2, 12)), int(rng.integers(1, 6))
+    x, info = kk.linsolve(kk.B200CSR.from_scipy(ctx, G), ctx.from_host(b), None,
+                          kk.GMRES(orth=kk.mgs2b, krylovdim=kd, maxiter=mi, tol=1e-10, verbosity=0))
+    ox, oinfo = ko.linsolve_gmres(G, b, krylovdim=kd, maxiter=mi, tol=1e-10, orth=ko.Orth(ko.MGS2))
+    _counts(info, oinfo, ("numops", "converged"))
+    np.testing.assert_allclose(x.to_host(), ox, rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("kind", [_blocklanczos_fast_block, _blocked_mgs2], ids=["fast_block", "mgs2b"])
+def test_flagged_modes_agree_with_oracle(kind, seed):
+    """(300 seeds of each ran clean when these were added.)"""
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(10_000 + seed)
+    with hostsim.installed(fused=True):
+        n = int(rng.integers(8, 60))
+        ctx = kk.B200Context(n, 600)
+        kind(rng, 10_000 + seed, ctx, n)
+        ctx.close()
