@@ -4,7 +4,7 @@ two ranks against tests/hostsim.py in its sharded mode — local rows, all-reduc
 for NCCL), gathered x standing in for the halo exchange.  What this proves is the property the multi-GPU
 design rests on: the host logic is rank-replicated — every rank sees the same scalars, takes
 the same branches, issues the same collectives in the same order — and the sharded results equal the
-serial oracle's.  The same checks run on real GPUs in tools/dist_check.py (tests/test_gpu_dist.py)."""
+serial oracle's.  The same checks run on real GPUs in tools/dist_check.py (tests/test_gpu_zz_dist.py)."""
 import os
 import sys
 

@@ -1,6 +1,10 @@
 """Row-sharded parity through tools/dist_check.py under torchrun: with one rank per GPU over NCCL + the NVLink
 peer window when the box has >= 2 GPUs, and ALWAYS with two ranks sharing GPU 0 (peer window only, gloo for the
-test's own gathers) so that a single-GPU box exercises the sharded path too."""
+test's own gathers) so that a single-GPU box exercises the sharded path too.
+
+(The file name sorts last on purpose: these are the slow multi-process tests — minutes of CPU oracle work per case —
+and a `pytest -x` run should have been through every single-process GPU test before it gets here.  The round-2 GPU
+scripts under tools/ still name the file as it was called then, tests/test_gpu_dist.py.)"""
 import os
 import subprocess
 import sys
