@@ -76,11 +76,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", default=None,
                     help="other BASELINE.json configs measured after the headline (records under 'other_configs'); "
-                         "'' = none.  Default: c2f,c3,c4,c5 on one GPU; c5 — the configuration BASELINE.json names "
+                         "'' = none.  Default: c2f,c2m,c3,c4,c5 on one GPU; c5 — the configuration BASELINE.json names "
                          "for 8 GPUs — under torchrun")
     a = ap.parse_args()
     if a.extra is None:
-        a.extra = "c2f,c3,c4,c5" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
+        a.extra = "c2f,c2m,c3,c4,c5" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
     return a
 
 
@@ -613,6 +613,42 @@ def other_configs(kk, a, rank, world, local_rank, dist):
             ctx.close()
         except Exception as e:      # the headline line must still be printed: record the failure instead
             out["c2_matrix_free"] = config_failed(e, ctx)
+
+    if "c2m" in want:
+        # the headline job with the REFERENCE-DEFAULT orthogonalizer (KrylovDefaults.orth = ModifiedGramSchmidt2,
+        # algorithms.jl:558): literal MGS2 and the flagged blocked form kk.mgs2b.  Timed on the same
+        # restart cycles as the headline; parity on the 2-cycle job the oracle's full-size MGS2 result exists for.
+        ctx = None
+        try:
+            ctx, n = make_ctx(a.ny, a.nx, a.krylovdim + 2 * HOWMANY + 8)
+            op = kk.B200CSR.stencil(ctx, a.nx, a.ny)
+            x0 = ctx.splitmix(SEED)
+            gm = gold.get("c2_mgs2", {})
+            g2 = gm.get("after_cycles", {}).get("2") if gm.get("grid") == [a.nx, a.ny, 1] and gm.get("krylovdim") == a.krylovdim else None
+            rec = {"workload": workload_config(a)["workload"].replace(f"orth={a.orth}", "orth=mgs2 (reference default) / mgs2b (flagged blocked form)")}
+            for name, orth in (("mgs2_reference_default", kk.mgs2), ("mgs2_blocked_flagged", kk.mgs2b)):
+                alg = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=a.cycles, tol=0.0, verbosity=0)
+                (vals, vecs, info), t = timed(ctx, lambda: kk.eigsolve(op, x0, HOWMANY, "SR", alg))
+                r = {"numops": info.numops, "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
+                     "ritz": [float(v) for v in vals[:HOWMANY]]}
+                del vecs, info                    # Ritz vectors and residuals hold slab columns the next solve needs
+                if g2:
+                    alg2 = kk.Lanczos(orth=orth, krylovdim=a.krylovdim, maxiter=2, tol=0.0, verbosity=0)
+                    v2, vecs2, info2 = kk.eigsolve(op, x0, HOWMANY, "SR", alg2)
+                    numops2 = int(info2.numops)
+                    del vecs2, info2
+                    ref = np.array(g2["ritz"])
+                    diff = np.abs(np.array(v2[:len(ref)]) - ref)
+                    floor = 4 * 8.0 * np.finfo(np.float64).eps
+                    r["parity"] = {"against": "tests/golden/fullsize.json:c2_mgs2:after_cycles[2] (the oracle's literal MGS2 at full size)",
+                                   "max_rel_diff_ritz": float(np.max(diff / np.abs(ref))), "max_abs_diff_ritz": float(diff.max()),
+                                   "numops": numops2, "numops_oracle": int(g2["numops"]),
+                                   "ok": bool(np.all(diff <= 1e-10 * np.abs(ref) + floor) and numops2 == int(g2["numops"]))}
+                rec[name] = r
+            out["c2_reference_default_orth"] = rec
+            ctx.close()
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["c2_reference_default_orth"] = config_failed(e, ctx)
 
     if "c3" in want:
         ctx = None

@@ -19,7 +19,7 @@ def test_default_extras_depend_on_world_size(monkeypatch):
     bench = _load_bench()
     monkeypatch.setattr(sys, "argv", ["bench.py"])
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    assert bench.parse().extra == "c2f,c3,c4,c5"
+    assert bench.parse().extra == "c2f,c2m,c3,c4,c5"
     monkeypatch.setenv("WORLD_SIZE", "8")
     assert bench.parse().extra == "c5"           # the configuration BASELINE.json names for 8 GPUs
     monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", ""])
@@ -55,8 +55,34 @@ def test_failing_extra_config_becomes_a_record(monkeypatch, capsys):
         B200CSR=types.SimpleNamespace(stencil_free=fail, stencil=fail),
         cgs2=None, mgs2=None, cgs=None, mgs=None, mgs2b=None)
     out = bench.other_configs(fake, a, 0, 1, 0, None)
-    assert set(out) == {"c2_matrix_free", "c3", "c4", "c5"}
+    assert set(out) == {"c2_matrix_free", "c2_reference_default_orth", "c3", "c4", "c5"}
     for rec in out.values():
         assert rec["ok"] is False and "Boom: no device" in rec["error"]
-    assert len(closed) == 4                     # every failed configuration gave its context back
+    assert len(closed) == 5                     # every failed configuration gave its context back
     assert "Boom" in capsys.readouterr().err    # the traceback goes to stderr, the JSON line stays clean
+
+
+def test_reference_default_orth_extra_runs_on_the_simulator(monkeypatch):
+    """The success path of an extra configuration — bench.other_configs 'c2m' (literal MGS2 and the flagged blocked
+    form on the headline operator, parity against a committed oracle result) — on tests/hostsim.py at a small size,
+    with a golden record made by the oracle on the spot.  Also proves the slab column budget of that block."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostsim
+    import krylovkit_jl_b200 as kk
+    from oracle import krylov_oracle as ko
+    bench = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--nx", "30", "--ny", "22", "--krylovdim", "12", "--cycles", "3",
+                                      "--extra", "c2m"])
+    a = bench.parse()
+    A, x0 = ko.stencil_matrix(30, 22), ko.splitmix_vector(bench.SEED, 660)
+    ov, _, oi = ko.eigsolve_lanczos(A, x0, 4, "SR", krylovdim=12, maxiter=2, tol=0.0, orth=ko.Orth(ko.MGS2))
+    fake = {"c2_mgs2": {"grid": [30, 22, 1], "krylovdim": 12,
+                        "after_cycles": {"2": {"ritz": [float(v) for v in ov[:4]], "numops": oi["numops"]}}}}
+    monkeypatch.setattr(bench.json, "load", lambda f: fake)
+    with hostsim.installed(fused=True):
+        out = bench.other_configs(kk, a, 0, 1, 0, None)
+    rec = out["c2_reference_default_orth"]
+    assert "error" not in rec, rec
+    for name in ("mgs2_reference_default", "mgs2_blocked_flagged"):
+        assert rec[name]["numops"] == 12 + 2 * (12 - (3 * 12) // 5) and rec[name]["value"] > 0
+        assert rec[name]["parity"]["ok"] and rec[name]["parity"]["numops"] == oi["numops"]
