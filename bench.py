@@ -76,11 +76,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", default=None,
                     help="other BASELINE.json configs measured after the headline (records under 'other_configs'); "
-                         "'' = none.  Default: c2f,c2m,c3,c4,c5 on one GPU; c5 — the configuration BASELINE.json names "
+                         "'' = none.  Default: c2f,c2m,w,c3,c4,c5 on one GPU; c5 — the configuration BASELINE.json names "
                          "for 8 GPUs — under torchrun")
     a = ap.parse_args()
     if a.extra is None:
-        a.extra = "c2f,c2m,c3,c4,c5" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
+        a.extra = "c2f,c2m,w,c3,c4,c5" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
     return a
 
 
@@ -649,6 +649,25 @@ def other_configs(kk, a, rank, world, local_rank, dist):
             ctx.close()
         except Exception as e:      # the headline line must still be printed: record the failure instead
             out["c2_reference_default_orth"] = config_failed(e, ctx)
+
+    if "w" in want and world == 1:
+        # the widened solvers at the 1e7 scale, as tools/run_configs.py measures them: CG (device-
+        # chained / one call per iteration / literal), BiCGStab (chained vs literal), Arnoldi eigsolve, BlockLanczos
+        # p = 4 in the reference mode and the flagged block mode, exponentiate — each with its residual identity
+        ctx = None
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_b2k_run_configs", os.path.join(ROOT, "tools", "run_configs.py"))
+            rc = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(rc)
+            rec = {"workload": "linsolve(CG, 200 iterations) / linsolve(BiCGStab, 40) / eigsolve(Arnoldi, krylovdim 30, 3 cycles) / "
+                               "eigsolve(BlockLanczos p = 4, krylovdim 32, 3 cycles) / exponentiate(Lanczos 30) on the 1e7-row 5-point "
+                               "operators (tools/run_configs.py cg, widened)",
+                   "cg": rc.cg()}
+            rec.update(rc.widened(lsmr=False))
+            out["widened_solvers"] = rec
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["widened_solvers"] = config_failed(e, ctx)
 
     if "c3" in want:
         ctx = None

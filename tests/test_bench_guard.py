@@ -19,7 +19,7 @@ def test_default_extras_depend_on_world_size(monkeypatch):
     bench = _load_bench()
     monkeypatch.setattr(sys, "argv", ["bench.py"])
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    assert bench.parse().extra == "c2f,c2m,c3,c4,c5"
+    assert bench.parse().extra == "c2f,c2m,w,c3,c4,c5"
     monkeypatch.setenv("WORLD_SIZE", "8")
     assert bench.parse().extra == "c5"           # the configuration BASELINE.json names for 8 GPUs
     monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", ""])
@@ -55,9 +55,13 @@ def test_failing_extra_config_becomes_a_record(monkeypatch, capsys):
         B200CSR=types.SimpleNamespace(stencil_free=fail, stencil=fail),
         cgs2=None, mgs2=None, cgs=None, mgs=None, mgs2b=None)
     out = bench.other_configs(fake, a, 0, 1, 0, None)
-    assert set(out) == {"c2_matrix_free", "c2_reference_default_orth", "c3", "c4", "c5"}
-    for rec in out.values():
-        assert rec["ok"] is False and "Boom: no device" in rec["error"]
+    assert set(out) == {"c2_matrix_free", "c2_reference_default_orth", "widened_solvers", "c3", "c4", "c5"}
+    for name, rec in out.items():
+        assert rec["ok"] is False
+        if name == "widened_solvers":          # runs tools/run_configs.py on the real package: here "no CUDA device"
+            assert "B200Error" in rec["error"] or "Boom" in rec["error"]
+        else:
+            assert "Boom: no device" in rec["error"]
     assert len(closed) == 5                     # every failed configuration gave its context back
     assert "Boom" in capsys.readouterr().err    # the traceback goes to stderr, the JSON line stays clean
 
@@ -86,3 +90,23 @@ def test_reference_default_orth_extra_runs_on_the_simulator(monkeypatch):
     for name in ("mgs2_reference_default", "mgs2_blocked_flagged"):
         assert rec[name]["numops"] == 12 + 2 * (12 - (3 * 12) // 5) and rec[name]["value"] > 0
         assert rec[name]["parity"]["ok"] and rec[name]["parity"]["numops"] == oi["numops"]
+
+
+def test_widened_solver_records_run_on_the_simulator():
+    """What bench.other_configs 'w' calls — tools/run_configs.py cg() and widened(lsmr=False), loaded by path — on
+    tests/hostsim.py at a small size: every record is produced and carries its residual identity."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostsim
+    spec = importlib.util.spec_from_file_location("_rc_under_test", os.path.join(ROOT, "tools", "run_configs.py"))
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    with hostsim.installed(fused=True):
+        cg = rc.cg(40, 30)
+        rec = rc.widened(40, 30, lsmr=False)
+    assert set(cg) == {"chained_32", "fused_step", "literal_mirror"}
+    for r in cg.values():
+        assert r["numiter"] == 200 and r["||A x + r - b||/||b||"] < 1e-12
+    assert set(rec) == {"bicgstab", "arnoldi_eigsolve", "blocklanczos_p4", "blocklanczos_p4_fast_block", "exponentiate"}
+    assert rec["bicgstab"]["||A x - b||/||b||"] < 1e-10 and rec["exponentiate"]["converged"] == 1
+    assert rec["blocklanczos_p4"]["numops"] == rec["blocklanczos_p4_fast_block"]["numops"]
+    assert abs(rec["blocklanczos_p4"]["ritz"][0] - rec["blocklanczos_p4_fast_block"]["ritz"][0]) < 1e-10
