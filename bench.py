@@ -76,11 +76,13 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", default=None,
                     help="other BASELINE.json configs measured after the headline (records under 'other_configs'); "
-                         "'' = none.  Default: c2f,c2m,w,c3,c4,c5 on one GPU; c5 — the configuration BASELINE.json names "
-                         "for 8 GPUs — under torchrun")
+                         "'' = none.  Default: c2f,c2m,w,c3,c4,c5,c4o on one GPU (c4o = config 4 in the flagged one-pass "
+                         "GKL mode, run LAST: its kernel had not run on a B200 when the round's GPU budget ended); c5 — the "
+                         "configuration BASELINE.json names for 8 GPUs — under torchrun")
+    ap.add_argument("--c4-rows", type=int, default=2_000_000, help="rows of config 4's dense matrix (tests use fewer)")
     a = ap.parse_args()
     if a.extra is None:
-        a.extra = "c2f,c2m,w,c3,c4,c5" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
+        a.extra = "c2f,c2m,w,c3,c4,c5,c4o" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c5"
     return a
 
 
@@ -707,7 +709,7 @@ def other_configs(kk, a, rank, world, local_rank, dist):
     if "c4" in want and world == 1:
         ctx = None
         try:
-            m, nn, kd = 2_000_000, 512, 30
+            m, nn, kd = a.c4_rows, 512, 30
             ctx = kk.B200Context(m, kd + 24, dtype=np.float32, device=local_rank)
             sv = ctx.add_space(nn, kd + 24, sharded=False)
             op = kk.B200Dense.splitmix(ctx, m, nn, SEED, sv)
@@ -770,6 +772,70 @@ def other_configs(kk, a, rank, world, local_rank, dist):
             ctx.close()
         except Exception as e:      # the headline line must still be printed: record the failure instead
             out["c5"] = config_failed(e, ctx)
+
+    if "c4o" in want and world == 1:
+        # config 4 in the flagged ONE-PASS mode of the GKL step: z = A'(A v) comes out of the
+        # pass that forms A v (b2k_op_apply_normal_gram) and A'u_{k+1} is recovered from it, guarded by an error
+        # estimate that falls back to a direct A'u.  Each orthogonalizer is run in the reference's two-pass form and in
+        # the one-pass form in the same process: singular values side by side, passes over A counted, the SVD
+        # residual identities evaluated on the device, the fused kernel's own event-timed bandwidth.
+        ctx = None
+        try:
+            m, nn, kd = a.c4_rows, 512, 30
+            ctx = kk.B200Context(m, kd + 24, dtype=np.float32, device=local_rank)
+            sv = ctx.add_space(nn, 2 * kd + 40, sharded=False)
+            op = kk.B200Dense.splitmix(ctx, m, nn, SEED, sv)
+            u0 = ctx.splitmix(SEED + 1)
+            pk, _ = peak_hbm()
+            rec = {"workload": f"svdsolve(GKL, krylovdim={kd}, tol=1e-5) on the dense {m}x{nn} Float32 matrix, 6 triplets "
+                               ":LR; reference two-pass step vs the flagged one-pass step (GKL(onepass=True))",
+                   "note": "numops counts both products of a step in both modes (as the reference does); passes = what was "
+                           "streamed from HBM: 2 per step in the reference's form, 1 per step in the one-pass form unless "
+                           "the error estimate of the recycled A'u forces a direct product"}
+            for oname, orth in (("mgs2", kk.mgs2), ("cgsr_eta0.75", kk.ClassicalGramSchmidtIR(eta=0.75))):
+                sig = {}
+                for mode, onepass in (("two_pass_reference", False), ("one_pass_flagged", True)):
+                    alg = kk.GKL(orth=orth, krylovdim=kd, maxiter=100, tol=1e-5, verbosity=0, onepass=onepass)
+                    lib.b2k_prof_reset(ctx.h)
+                    (S, Lv, Rv, info), t = timed(ctx, lambda: kk.svdsolve(op, u0, 6, "LR", alg))
+                    res = []
+                    for i in range(3):                                  # A v = s u + r, A' u = s v on the device
+                        w = kk.apply_normal(op, Rv[i])
+                        w.add_(Lv[i], -float(S[i]))
+                        z = kk.apply_adjoint(op, Lv[i])
+                        z.add_(Rv[i], -float(S[i]))
+                        res.append([float(w.norm() / S[i]), float(z.norm() / S[i])])
+                        del w, z
+                    r = {"numops": info.numops, "numiter": info.numiter, "converged": info.converged,
+                         "passes_over_A": int(info.passes), "ms": 1000 * t, "value": info.numops / t, "unit": "it/s",
+                         "sigma": [float(v) for v in S[:6]], "rel_residuals(Av-su, A'u-sv)": res}
+                    sig[mode] = np.array(S[:6], dtype=np.float64)
+                    del Lv, Rv, info
+                    if onepass:
+                        # the fused kernel alone: event-timed launches of one more pass (profile class 8)
+                        x = ctx.splitmix(SEED + 2, sv)
+                        lib.b2k_prof_reset(ctx.h)
+                        lib.b2k_prof_enable(ctx.h, 1)
+                        for _ in range(12):
+                            y, z = kk.operators.apply_normal_gram(op, x)
+                            del y, z
+                        c, ms, b = C.c_int64(), C.c_double(), C.c_double()
+                        lib.b2k_prof_read(ctx.h, 8, C.byref(c), C.byref(ms), C.byref(b))
+                        lib.b2k_prof_enable(ctx.h, 0)
+                        if c.value:
+                            r["kernel_k_dense_onepass"] = {
+                                "launches": c.value, "avg_ms": ms.value / c.value, "GBs": b.value / ms.value / 1e6,
+                                "frac_of_hbm_peak": b.value / ms.value / 1e6 / pk,
+                                "algorithmic_bytes": "4 (m n + m + n) per launch: A read ONCE for A v and A'(A v)"}
+                        r["max_rel_diff_sigma_vs_two_pass"] = float(np.max(np.abs(sig[mode] - sig["two_pass_reference"])
+                                                                           / sig["two_pass_reference"]))
+                        r["ok"] = bool(r["max_rel_diff_sigma_vs_two_pass"] <= 3e-5 and r["converged"] >= 6)
+                        del x
+                    rec[f"{oname}:{mode}"] = r
+            out["c4_onepass"] = rec
+            ctx.close()
+        except Exception as e:      # the headline line must still be printed: record the failure instead
+            out["c4_onepass"] = config_failed(e, ctx)
 
     return out
 

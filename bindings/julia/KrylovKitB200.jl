@@ -206,6 +206,17 @@ function apply_adjoint(A::B200Dense, x::B200Vec)                                
     return y
 end
 apply(A::B200Dense, x::B200Vec) = apply_normal(A, x)
+# (A x, A'(A x)) from ONE pass over the dense A — the building block of the flagged one-pass GKL step (no KrylovKit
+# counterpart: gkl.jl:308-323 calls apply_adjoint and apply_normal separately).  A gklrecurrence specialisation on
+# `GKLIterator{<:B200Dense}` would keep G = A'U next to U and recover A'u_{k+1} = (z - G c) / beta with unproject!!,
+# guarded by the error estimate described in krylovkit.jl_b200/factorizations/gkl.py.
+function apply_normal_gram(A::B200Dense, x::B200Vec)
+    y = B200Vec(x.ctx; space = 0)
+    z = B200Vec(x.ctx; space = A.space_in)
+    check(x.ctx.h, ccall((:b2k_op_apply_normal_gram, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32),
+                         x.ctx.h, A.h, x.handle, y.handle, z.handle))
+    return y, z
+end
 
 # ---- basis fast path: what `Array` gets via _use_multithreaded_array_kernel (orthonormal.jl:66-73) --------
 const B200Basis = OrthonormalBasis{<:B200Vec}

@@ -15,7 +15,8 @@ from .algorithms import (Arnoldi, BiCGStab, BlockLanczos, CG, ClassicalGramSchmi
                          Lanczos, LSMR, ModifiedGramSchmidt, ModifiedGramSchmidt2,
                          ModifiedGramSchmidt2Blocked, ModifiedGramSchmidtIR, Orthogonalizer, cgs, cgs2, cgsr, mgs,
                          mgs2, mgs2b, mgsr)
-from .operators import B200CSR, B200Dense, B200Operator, apply, apply_adjoint, apply_normal
+from .operators import (B200CSR, B200Dense, B200Operator, apply, apply_adjoint, apply_normal,
+                        apply_normal_gram)
 from .orthonormal import (OrthonormalBasis, basistransform_, orthogonalize_, orthonormalize_,
                           project_, rank1update_, rmul_givens_, rmul_householder_, unproject_)
 from .vectors import B200Context, B200Vec, cache_release, inner, norm

@@ -92,6 +92,7 @@ _PROTOS = {
     "b2k_op_apply": (C.c_int32, [c_ctx, c_op, c_vec, c_vec]),
     "b2k_op_apply_shifted": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, C.c_double, C.c_double]),
     "b2k_op_apply_adjoint": (C.c_int32, [c_ctx, c_op, c_vec, c_vec]),
+    "b2k_op_apply_normal_gram": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec]),
     "b2k_op_apply_dot": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, P(C.c_double)]),
     "b2k_cg_step": (C.c_int32, [c_ctx, c_op, c_vec, c_vec, c_vec, c_vec, C.c_double, C.c_double, C.c_double,
                                 C.c_double, P(C.c_double), P(C.c_double)]),

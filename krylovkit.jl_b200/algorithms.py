@@ -130,6 +130,9 @@ class GKL:
     tol: float = KrylovDefaults.tol
     eager: bool = False
     verbosity: int = KrylovDefaults.verbosity
+    # flagged, not a reference field: one pass over a dense device operator per GKL step instead of two
+    # (factorizations/gkl.py); coefficients differ from the reference step by rounding only
+    onepass: bool = False
 
 
 @dataclass(frozen=True)

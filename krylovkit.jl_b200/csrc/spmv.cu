@@ -40,7 +40,8 @@ struct b2k_op {
     int32_t* rowblk = nullptr;    // CTA row-block boundaries
     int32_t* pblk = nullptr;      // rowptr[rowblk[b]] (first nonzero of each block)
     int32_t  nblk = 0;
-    double*  part = nullptr;      // per-CTA dot partials
+    double*  part = nullptr;      // per-CTA dot partials (CSR / stencil); per-CTA z partials of the one-pass dense step
+    size_t   part_bytes = 0;      // size of `part` when the one-pass dense step allocated it
     // halo plan (dist)
     int64_t  n_loc_cols = 0;      // columns owned locally = length of the local x
     int64_t  halo_lo = 0, halo_hi = 0;         // entries needed from rank-1 / rank+1
@@ -1627,6 +1628,239 @@ extern "C" int32_t b2k_op_apply_adjoint(b2k_ctx* ctx, const b2k_op* op, b2k_vec 
                         (long long)rx.n, (long long)op->n_rows, (long long)ry.n, (long long)op->n_cols);
     return b2k_panel_project_dev(ctx, op->A, op->ld, op->n_rows, (int32_t)op->n_cols, rx, ry.ptr,
                                  rx.sharded);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One pass over a dense A for BOTH products of a Golub-Kahan-Lanczos step (the flagged
+// `onepass` mode of the GKL mirror; the reference's step reads A twice: gkl.jl:308-323 `apply_adjoint` then
+// `apply_normal`).  While y = A x is formed, z = A'(A x) is accumulated from the same resident row tile; the
+// host recovers A'u_{k+1} = (z - sum_j c_j A'u_j) / beta_k from it (factorizations/gkl.py) without a second
+// pass.  The reduction over rows of y = A x is LOCAL to a row tile, so no grid-wide barrier is needed:
+//
+//   tile   = 32 rows x n columns of the column-major A (n <= 1700 Float32 / 850 Float64), parked in shared
+//            memory with a column stride of 33 words: conflict-free both for lane <-> row (the tile stores)
+//            and for lane <-> column (phase 2);
+//   load   : every thread issues 8 independent 16-byte loads (4 Float32 / 2 Float64 consecutive rows of one
+//            column) per batch; its partial y for those rows is accumulated straight from the registers;
+//   phase 1: partial y summed over the threads that hold the same rows (shuffles, then the 8 warps in fixed
+//            order) -> y[32], written to global memory;
+//   phase 2: thread <-> column: z_c += sum_rows tile[c][row] * y[row]  (T per tile, double across tiles);
+//   end    : per-CTA partial z (double) -> k_onepass_reduce sums the CTAs in fixed order (deterministic).
+//
+// Rows [m, ld) of A are zero (alloc_dense memsets, both fills write rows < m only) and ld is a multiple of 32,
+// so every tile is loaded without row guards.  Algorithmic traffic: sizeof(T) * (m n + m + n) bytes per call —
+// half of the two-pass step.  3 CTAs per SM for n = 512 Float32 (71 KB of shared memory each): the loads of one
+// CTA overlap the phases of the others; no asynchronous copies, no spin waits.
+constexpr int OP_T = 256;        // threads per CTA
+constexpr int OP_ROWS = 32;      // rows per tile
+constexpr int OP_PAD = 33;       // column stride of the tile in shared memory (words)
+constexpr int OP_ZMAX = 7;       // columns per thread in phase 2: n <= OP_ZMAX * OP_T
+constexpr int OP_UNR = 8;        // 16-byte loads in flight per thread
+
+namespace {
+
+template <typename T> struct OpVecT;
+template <> struct OpVecT<float>  { using type = float4; };
+template <> struct OpVecT<double> { using type = double2; };
+__device__ __forceinline__ void op_unpack(const float4& a, float* e)  { e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; }
+__device__ __forceinline__ void op_unpack(const double2& a, double* e) { e[0] = a.x; e[1] = a.y; }
+__device__ __forceinline__ float4 op_ld_stream(const float4* p) {        // read-once stream: no L1 allocation
+    float4 a;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ double2 op_ld_stream(const double2* p) {
+    double2 a;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "l"(p));
+    return a;
+}
+
+template <typename T, int NZ>               // NZ = columns per thread in phase 2: n <= NZ * OP_T
+__global__ void __launch_bounds__(OP_T, NZ <= 2 ? 3 : 1)
+k_dense_onepass(const T* __restrict__ A, int64_t ld, int64_t m, int32_t n, const T* __restrict__ x,
+                T* __restrict__ y, double* __restrict__ zpart, int64_t ntiles) {
+    using V = typename OpVecT<T>::type;
+    constexpr int VEC = 16 / (int)sizeof(T);        // rows per 16-byte load
+    constexpr int VPC = OP_ROWS / VEC;              // loads per tile column
+    constexpr int CSTEP = OP_T / VPC;               // columns covered by one load of the whole CTA
+    static_assert(OP_T % VPC == 0 && 32 % VPC == 0, "a thread keeps the same rows for every column it loads");
+    extern __shared__ __align__(16) unsigned char op_smem[];
+    T* As = reinterpret_cast<T*>(op_smem);          // [n][OP_PAD]
+    T* xs = As + (size_t)n * OP_PAD;                // [n]
+    T* ys_part = xs + n;                            // [8 warps][32 rows]
+    T* ys = ys_part + (OP_T / 32) * OP_ROWS;        // [32 rows]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rq = tid % VPC;                       // which 16-byte row group of a column this thread loads
+    const int c0 = tid / VPC;                       // its first column; the others follow at CSTEP
+    for (int j = tid; j < n; j += OP_T) xs[j] = x[j];
+    double zacc[NZ];
+#pragma unroll
+    for (int s = 0; s < NZ; ++s) zacc[s] = 0.0;
+    __syncthreads();
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i0 = tile * OP_ROWS;
+        const T* At = A + i0 + rq * VEC;
+        T acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = (T)0;
+        for (int cb = c0; cb < n; cb += CSTEP * OP_UNR) {
+            V a[OP_UNR];
+#pragma unroll
+            for (int u = 0; u < OP_UNR; ++u) {
+                const int c = cb + u * CSTEP;
+                if (c < n) a[u] = op_ld_stream(reinterpret_cast<const V*>(At + (int64_t)c * ld));
+            }
+#pragma unroll
+            for (int u = 0; u < OP_UNR; ++u) {
+                const int c = cb + u * CSTEP;
+                if (c < n) {
+                    T e4[VEC];
+                    op_unpack(a[u], e4);
+                    const T xc = xs[c];
+                    T* dst = As + (size_t)c * OP_PAD + rq * VEC;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        acc[e] = fma(e4[e], xc, acc[e]);
+                        dst[e] = e4[e];
+                    }
+                }
+            }
+        }
+        // the threads of a warp that hold the same rows: lanes rq, rq + VPC, rq + 2 VPC, ...
+#pragma unroll
+        for (int off = VPC; off < 32; off <<= 1)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+        if (lane < VPC)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ys_part[warp * OP_ROWS + lane * VEC + e] = acc[e];
+        __syncthreads();                            // the tile and the per-warp partial y are complete
+        if (tid < OP_ROWS) {
+            T s = (T)0;
+#pragma unroll
+            for (int w = 0; w < OP_T / 32; ++w) s += ys_part[w * OP_ROWS + tid];
+            ys[tid] = s;
+            if (i0 + tid < m) y[i0 + tid] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < NZ; ++s) {
+            const int c = s * OP_T + tid;
+            if (c < n) {
+                const T* col = As + (size_t)c * OP_PAD;
+                T p = (T)0;
+#pragma unroll
+                for (int row = 0; row < OP_ROWS; ++row) p = fma(col[row], ys[row], p);
+                zacc[s] += (double)p;
+            }
+        }
+        __syncthreads();                            // phase 2 has read the tile: the next one may overwrite it
+    }
+#pragma unroll
+    for (int s = 0; s < NZ; ++s) {
+        const int c = s * OP_T + tid;
+        if (c < n) zpart[(size_t)blockIdx.x * n + c] = zacc[s];
+    }
+}
+
+// z[c] = sum over the CTAs' partials, in a fixed order: 8 groups of threads take every 8th partial with four
+// independent running sums each (loads batched), then the groups are added in order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_onepass_reduce(const double* __restrict__ zpart, int nparts, int n, double* __restrict__ dres, T* __restrict__ zout) {
+    __shared__ double red[8][32];
+    const int g = threadIdx.x >> 5, jl = threadIdx.x & 31;
+    const int c = blockIdx.x * 32 + jl;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (c < n) {
+        int p = g;
+        for (; p + 24 < nparts; p += 32) {
+            const double a0 = zpart[(size_t)p * n + c], a1 = zpart[(size_t)(p + 8) * n + c];
+            const double a2 = zpart[(size_t)(p + 16) * n + c], a3 = zpart[(size_t)(p + 24) * n + c];
+            s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+        }
+        for (; p < nparts; p += 8) s0 += zpart[(size_t)p * n + c];
+    }
+    red[g][jl] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (g == 0 && c < n) {
+        double s = red[0][jl];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += red[w][jl];
+        dres[c] = s;
+        if (zout) zout[c] = (T)s;
+    }
+}
+
+template <typename T>
+__global__ void k_onepass_store(const double* __restrict__ dres, T* __restrict__ zout, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) zout[c] = (T)dres[c];
+}
+
+template <typename T>
+int32_t onepass_t(b2k_ctx* ctx, b2k_op* op, const VecRef& x, const VecRef& y, const VecRef& z) {
+    const int n = (int)op->n_cols;
+    const size_t smem = ((size_t)n * OP_PAD + n + (OP_T / 32) * OP_ROWS + OP_ROWS) * sizeof(T);
+    if (smem > 227u * 1024u)
+        return b2k_fail(ctx, B2K_ENOTSUP, "one-pass dense step: a 32 x %d tile needs %zu bytes of shared memory", n, smem);
+    void (*kern)(const T*, int64_t, int64_t, int32_t, const T*, T*, double*, int64_t) =
+        n <= OP_T ? k_dense_onepass<T, 1> : n <= 2 * OP_T ? k_dense_onepass<T, 2> :
+        n <= 4 * OP_T ? k_dense_onepass<T, 4> : k_dense_onepass<T, OP_ZMAX>;
+    B2K_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    B2K_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OP_T, smem));
+    if (occ < 1) return b2k_fail(ctx, B2K_ENOTSUP, "one-pass dense step: a %d-column tile does not fit an SM", n);
+    const int64_t ntiles = op->ld / OP_ROWS;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)occ * ctx->num_sms);
+    const size_t need = (size_t)grid * n * sizeof(double);
+    if (op->part_bytes < need) {
+        if (op->part) B2K_DFREE(op->part);
+        op->part = nullptr;
+        op->part_bytes = 0;
+        B2K_CUDA(ctx, B2K_DMALLOC(&op->part, need));
+        op->part_bytes = need;
+    }
+    const int pr = b2k_prof_begin(ctx, 8, (double)sizeof(T) * ((double)op->n_rows * n + (double)op->n_rows + n));
+    kern<<<grid, OP_T, smem, ctx->stream>>>((const T*)op->A, op->ld, op->n_rows, n, (const T*)x.ptr,
+                                                           (T*)y.ptr, op->part, ntiles);
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    const bool reduce_ranks = ctx->nranks > 1 && y.sharded;
+    k_onepass_reduce<T><<<(n + 31) / 32, 256, 0, ctx->stream>>>(op->part, grid, n, ctx->d_res,
+                                                                reduce_ranks ? nullptr : (T*)z.ptr);
+    B2K_LAUNCH_CHECK(ctx);
+    if (reduce_ranks) {
+        B2K_TRY(b2k_allreduce(ctx, ctx->d_res, n, 1));
+        k_onepass_store<T><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_res, (T*)z.ptr, n);
+        B2K_LAUNCH_CHECK(ctx);
+    }
+    return B2K_OK;
+}
+
+}  // namespace
+
+// y = A x and z = A'(A x) from ONE pass over the dense A (see k_dense_onepass).  x, z: length n_cols (the
+// operator's input space); y: length n_rows (space 0).  Dense operators only; everything else is B2K_ENOTSUP.
+extern "C" int32_t b2k_op_apply_normal_gram(b2k_ctx* ctx, const b2k_op* op, b2k_vec x, b2k_vec y, b2k_vec z) {
+    if (!ctx || !op) return B2K_EINVAL;
+    VecRef rx, ry, rz;
+    B2K_TRY(b2k_resolve(ctx, x, &rx));
+    B2K_TRY(b2k_resolve(ctx, y, &ry));
+    B2K_TRY(b2k_resolve(ctx, z, &rz));
+    if (op->kind != 1)
+        return b2k_fail(ctx, B2K_ENOTSUP, "apply_normal_gram: dense operators only (the one-pass GKL step)");
+    if (rx.n != op->n_cols || rz.n != op->n_cols || ry.n != op->n_rows)
+        return b2k_fail(ctx, B2K_EDIM, "apply_normal_gram: x has %lld, z has %lld (want %lld), y has %lld (want %lld)",
+                        (long long)rx.n, (long long)rz.n, (long long)op->n_cols, (long long)ry.n, (long long)op->n_rows);
+    if (rx.ptr == rz.ptr) return b2k_fail(ctx, B2K_EINVAL, "apply_normal_gram: z must not alias x");
+    if (op->n_cols > OP_ZMAX * OP_T || op->n_cols > B2K_RES_DOUBLES)
+        return b2k_fail(ctx, B2K_ENOTSUP, "apply_normal_gram: more than %d columns", OP_ZMAX * OP_T);
+    B2K_CUDA(ctx, cudaSetDevice(ctx->device));
+    b2k_op* mop = const_cast<b2k_op*>(op);          // the per-CTA partial buffer is allocated on first use
+    if (ctx->dtype == B2K_F64) return onepass_t<double>(ctx, mop, rx, ry, rz);
+    return onepass_t<float>(ctx, mop, rx, ry, rz);
 }
 
 // apply(A, X::Block) — blocklanczos.jl:38: Y[i] = A X[i] for the p vectors of a block.  Single-GPU CSR operators

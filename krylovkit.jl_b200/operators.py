@@ -197,6 +197,17 @@ def apply_normal(op, x: B200Vec) -> B200Vec:
     return op(x, False)
 
 
+def apply_normal_gram(op: "B200Dense", x: B200Vec):
+    """(A x, A'(A x)) from ONE pass over a dense device operator — b2k_op_apply_normal_gram; the flagged
+    one-pass mode of the GKL step (factorizations/gkl.py).  Not a reference function."""
+    if not isinstance(op, B200Dense):
+        raise L.B200Error("apply_normal_gram: dense device operators only")
+    y = x.ctx.empty(op.space_out)
+    z = x.ctx.empty(op.space_in)
+    x.ctx.check(x.ctx.lib.b2k_op_apply_normal_gram(x.ctx.h, op.h, x.handle, y.handle, z.handle))
+    return y, z
+
+
 def apply_adjoint(op, x: B200Vec) -> B200Vec:
     """apply_adjoint — src/apply.jl:15,17,19."""
     if isinstance(op, B200Dense):

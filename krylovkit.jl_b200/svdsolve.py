@@ -38,7 +38,7 @@ def svdsolve(A, u0=None, howmany: int = 1, which: str = "LR", alg: GKL | None = 
     # live in space 0, V and the right vectors in the short space
     ctx = B200Context(m, 3 * alg.krylovdim + 12, dtype=A.dtype if A.dtype == np.float32 else np.float64)
     try:
-        sv = ctx.add_space(n, 2 * alg.krylovdim + 10, sharded=False)
+        sv = ctx.add_space(n, (3 if getattr(alg, "onepass", False) else 2) * alg.krylovdim + 14, sharded=False)
         op = B200Dense.from_host(ctx, A, sv)
         S, Uv, Vv, info = _svdsolve_gkl(op, ctx.from_host(u0), howmany, which, alg)
         info.residual = [r.to_host() for r in info.residual]
@@ -73,7 +73,10 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
     if howmany > krylovdim:
         raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} singular values")
     numiter = 1
-    it = gkl.GKLIterator(A, u0, alg.orth)
+    onepass = getattr(alg, "onepass", False)
+    # a recycled A'u may carry the rounding of at most 4 direct products, or 1 % of the tolerance asked for
+    eta_max = max(4.0, 0.01 * alg.tol / float(np.finfo(u0.ctx.np_dtype).eps))
+    it = gkl.GKLIterator(A, u0, alg.orth, onepass=onepass, onepass_eta=eta_max)
     fact = gkl.initialize(it)
     numops = 2
     tol = alg.tol
@@ -109,6 +112,16 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
             U, V = fact.basis("U"), fact.basis("V")
             basistransform_(U, P[:, :keep])
             basistransform_(V, Q.T[:, :keep])
+            G = fact.G                                            # onepass mode: G = A'U rotates with U
+            g_lost = False
+            if G is not None:
+                basistransform_(G, P[:, :keep])
+                fact.eta[:] = [max(fact.eta)] * len(fact.eta)     # an orthogonal mix of the columns and their errors
+                if fact.g_next is not None:
+                    G[keep], fact.g_next = fact.g_next, None      # the image of U[keep] = r/β below
+                    fact.eta[keep] = fact.eta_next
+                else:
+                    g_lost = True
             r = fact.residual()
             U[keep] = U[keep].scale_(1 / fact.normres(), r)       # U[keep+1] = scale!!(r, 1/β)
             H = HH[: keep + 1, :keep]
@@ -128,10 +141,14 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
                 H[:j, j] = 0
                 lmul_householder(h, H, range(0, j))
                 rmul_householder_(U, h.beta, h.v, h.r)
+                if G is not None:
+                    rmul_householder_(G, h.beta, h.v, h.r)
             for j in range(keep):
                 fact.alphas[j] = H[j, j]
                 fact.betas[j] = H[j + 1, j]
             fact = gkl.shrink_(fact, keep)
+            if g_lost:
+                fact.g_next = None                                # the next step forms A'u directly
             numiter += 1
     if converged > howmany:
         howmany = converged
@@ -145,4 +162,6 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
     if converged < howmany and alg.verbosity >= WARN_LEVEL:
         warnings.warn(f"GKL svdsolve finished without convergence after {numiter} iterations: "
                       f"{converged} singular values converged, normres = {normres}, numops = {numops}")
-    return values, left, right, ConvergenceInfo(converged, residuals, normres, numiter, numops)
+    info = ConvergenceInfo(converged, residuals, normres, numiter, numops)
+    info.passes = fact.passes             # passes over A (numops counts products, as the reference does)
+    return values, left, right, info

@@ -218,6 +218,19 @@ class HostSimLib:
         _set(ms, (time.perf_counter() - self._c(h).t0) * 1e3)
         return L.OK
 
+    # the per-kernel event profile has no meaning here: accepted, always empty
+    def b2k_prof_enable(self, h, on):
+        return L.OK
+
+    def b2k_prof_reset(self, h):
+        return L.OK
+
+    def b2k_prof_read(self, h, cls, count, ms, nbytes):
+        _set(count, 0)
+        _set(ms, 0.0)
+        _set(nbytes, 0.0)
+        return L.OK
+
     # ---- vectors ------------------------------------------------------------------------------
     def b2k_vec_alloc(self, h, space, out):
         return self.b2k_vec_alloc_range(h, space, 1, out)
@@ -398,6 +411,26 @@ class HostSimLib:
         if sp.issparse(self.ops[_key(op)]):
             return self._fail(ctx, L.ENOTSUP, "apply_adjoint on a CSR operator")
         return self._apply(ctx, op, x, y, adjoint=True)
+
+    def b2k_op_apply_normal_gram(self, h, op, x, y, z):
+        """y = A x and z = A'(A x): one pass over a dense A on the device, two numpy products here (working
+        precision, like the kernel's per-tile sums)."""
+        ctx = self._c(h)
+        A = self.ops[_key(op)]
+        if sp.issparse(A):
+            return self._fail(ctx, L.ENOTSUP, "apply_normal_gram: dense operators only")
+        if ctx.dist is not None:
+            return self._fail(ctx, L.ENOTSUP, "hostsim: only sharded CSR operators are simulated")
+        xv, yv, zv = self._vec(ctx, x), self._vec(ctx, y), self._vec(ctx, z)
+        if A.shape[1] != len(xv) or A.shape[1] != len(zv) or A.shape[0] != len(yv):
+            return self._fail(ctx, L.EDIM, "apply_normal_gram: length mismatch")
+        if _key(x) == _key(z):
+            return self._fail(ctx, L.EINVAL, "apply_normal_gram: z must not alias x")
+        ctx.launches += 2
+        r = A @ xv
+        self._setvec(ctx, y, r)
+        self._setvec(ctx, z, A.T @ r)
+        return L.OK
 
     def b2k_op_apply_dot(self, h, op, x, y, v, out):
         ctx = self._c(h)

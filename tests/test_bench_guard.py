@@ -19,7 +19,7 @@ def test_default_extras_depend_on_world_size(monkeypatch):
     bench = _load_bench()
     monkeypatch.setattr(sys, "argv", ["bench.py"])
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    assert bench.parse().extra == "c2f,c2m,w,c3,c4,c5"
+    assert bench.parse().extra == "c2f,c2m,w,c3,c4,c5,c4o"
     monkeypatch.setenv("WORLD_SIZE", "8")
     assert bench.parse().extra == "c5"           # the configuration BASELINE.json names for 8 GPUs
     monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", ""])
@@ -55,14 +55,14 @@ def test_failing_extra_config_becomes_a_record(monkeypatch, capsys):
         B200CSR=types.SimpleNamespace(stencil_free=fail, stencil=fail),
         cgs2=None, mgs2=None, cgs=None, mgs=None, mgs2b=None)
     out = bench.other_configs(fake, a, 0, 1, 0, None)
-    assert set(out) == {"c2_matrix_free", "c2_reference_default_orth", "widened_solvers", "c3", "c4", "c5"}
+    assert set(out) == {"c2_matrix_free", "c2_reference_default_orth", "widened_solvers", "c3", "c4", "c5", "c4_onepass"}
     for name, rec in out.items():
         assert rec["ok"] is False
         if name == "widened_solvers":          # runs tools/run_configs.py on the real package: here "no CUDA device"
             assert "B200Error" in rec["error"] or "Boom" in rec["error"]
         else:
             assert "Boom: no device" in rec["error"]
-    assert len(closed) == 5                     # every failed configuration gave its context back
+    assert len(closed) == 6                     # every failed configuration gave its context back
     assert "Boom" in capsys.readouterr().err    # the traceback goes to stderr, the JSON line stays clean
 
 
@@ -110,3 +110,24 @@ def test_widened_solver_records_run_on_the_simulator():
     assert rec["bicgstab"]["||A x - b||/||b||"] < 1e-10 and rec["exponentiate"]["converged"] == 1
     assert rec["blocklanczos_p4"]["numops"] == rec["blocklanczos_p4_fast_block"]["numops"]
     assert abs(rec["blocklanczos_p4"]["ritz"][0] - rec["blocklanczos_p4_fast_block"]["ritz"][0]) < 1e-10
+
+
+def test_onepass_extra_runs_on_the_simulator(monkeypatch):
+    """The success path of bench.other_configs 'c4o' (config 4, two-pass reference step against the flagged one-pass
+    step, run last) on tests/hostsim.py at 20 000 rows: every record is produced, the singular values of the two modes
+    agree within the Float32 bar, the one-pass mode streams fewer passes; also proves the column budgets of that block."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostsim
+    import krylovkit_jl_b200 as kk
+    bench = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", "c4o", "--c4-rows", "20000"])
+    a = bench.parse()
+    with hostsim.installed(fused=True):
+        out = bench.other_configs(kk, a, 0, 1, 0, None)
+    rec = out["c4_onepass"]
+    assert "error" not in rec, rec
+    for oname in ("mgs2", "cgsr_eta0.75"):
+        two, one = rec[f"{oname}:two_pass_reference"], rec[f"{oname}:one_pass_flagged"]
+        assert two["converged"] >= 6 and one["converged"] >= 6 and one["ok"]
+        assert two["passes_over_A"] == two["numops"] and one["passes_over_A"] < one["numops"]
+        assert one["max_rel_diff_sigma_vs_two_pass"] <= 3e-5

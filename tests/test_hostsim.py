@@ -282,3 +282,27 @@ def test_fused_eigsolve_with_restarts(simf):
         # every column the library allocated inside expand_many was adopted and released again
         assert len(ctx.lib.ctxs[ctx.h.value].spaces[0].cols) == live0, "leaked slab columns"
     ctx.close()
+
+
+# ---- the flagged one-pass GKL mode (tests/test_gpu_zzz_onepass.py bodies on the simulator) ----------------------
+import test_gpu_zzz_onepass as OP  # noqa: E402
+
+
+@pytest.mark.parametrize("m,n,dtype", [(2000, 64, np.float32), (500, 70, np.float64)])
+def test_onepass_apply(sim, m, n, dtype):
+    OP.test_apply_normal_gram(m, n, dtype)
+
+
+def test_onepass_apply_errors(sim):
+    OP.test_apply_normal_gram_errors()
+
+
+@pytest.mark.parametrize("which", [0, 1, 2], ids=["mgs2", "cgs2", "cgsr"])
+def test_onepass_svdsolve_f64(sim, which):
+    orth, oorth = [(kk.mgs2, ko.Orth(ko.MGS2)), (kk.cgs2, ko.Orth(ko.CGS2)),
+                   (kk.ClassicalGramSchmidtIR(eta=0.75), ko.Orth(ko.CGSIR, 0.75))][which]
+    OP.test_svdsolve_onepass_f64(orth, oorth)
+
+
+def test_onepass_svdsolve_f32(sim):
+    OP.test_svdsolve_onepass_config4_small_f32()
