@@ -1854,7 +1854,8 @@ extern "C" int32_t b2k_op_apply_normal_gram(b2k_ctx* ctx, const b2k_op* op, b2k_
     if (rx.n != op->n_cols || rz.n != op->n_cols || ry.n != op->n_rows)
         return b2k_fail(ctx, B2K_EDIM, "apply_normal_gram: x has %lld, z has %lld (want %lld), y has %lld (want %lld)",
                         (long long)rx.n, (long long)rz.n, (long long)op->n_cols, (long long)ry.n, (long long)op->n_rows);
-    if (rx.ptr == rz.ptr) return b2k_fail(ctx, B2K_EINVAL, "apply_normal_gram: z must not alias x");
+    if (rx.ptr == rz.ptr || rx.ptr == ry.ptr || ry.ptr == rz.ptr)
+        return b2k_fail(ctx, B2K_EINVAL, "apply_normal_gram: x, y and z must be three different vectors");
     if (op->n_cols > OP_ZMAX * OP_T || op->n_cols > B2K_RES_DOUBLES)
         return b2k_fail(ctx, B2K_ENOTSUP, "apply_normal_gram: more than %d columns", OP_ZMAX * OP_T);
     B2K_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -4,7 +4,7 @@ at FULL size.  The GPU arm of bench.py and the `-m gpu` full-size parity tests c
 GPU box has the oracle too, but a whole config-2 job costs ~20 s of its 16-CPU quota (config 3/5 more), so the
 numbers are computed once here and committed.  Nothing in the product reads this file.
 
-    python tests/golden/make_fullsize_golden.py [c2 c2_mgs2 c2_1e6 c3 c3_mgs2 c5s c5]     (default: all)
+    python tests/golden/make_fullsize_golden.py [c2 c2_mgs2 c2_1e6 c3 c3_mgs2 c5s c5 c4_truth]     (default: all)
 
 Inputs are the synthetic ones SURVEY.md §8d fixes (stencils + splitmix64 start vectors, seed 20260923), so the
 file is reproducible bit for bit up to the summation order of the OpenMP reductions (<= 1e-13 relative).
@@ -72,6 +72,23 @@ def gmres_case(nx, ny, kd, cycles, orth):
     return out
 
 
+def dense_truth_case(m, n, howmany=6):
+    """configs[3] (svdsolve on the dense 2e6 x 512 Float32 splitmix matrix): the largest singular values of the matrix
+    the device generates, from the Float64 Gram matrix A'A accumulated blockwise (sqrt of its eigenvalues) — the
+    truth the Float32 runs of bench.py's c4 / c4_onepass records are compared with (3e-5 relative)."""
+    t0 = time.perf_counter()
+    A = ko.dense_splitmix(SEED, m, n)
+    G = np.zeros((n, n))
+    for i in range(0, m, 100_000):
+        blk = A[i:i + 100_000].astype(np.float64)
+        G += blk.T @ blk
+    sig = np.sqrt(np.sort(np.linalg.eigvalsh(G))[::-1][:howmany])
+    out = {"shape": [m, n], "dtype": "float32", "seed": SEED, "howmany": howmany, "which": "LR",
+           "sigma_float64_truth": [float(v) for v in sig], "oracle_seconds": round(time.perf_counter() - t0, 1)}
+    print(m, n, out, flush=True)
+    return out
+
+
 CASES = {
     # BASELINE.json configs[1]: the bench workload (5 cycles) and the 2-cycle prefix the GPU test checks
     "c2": lambda: lanczos_case(4000, 2500, 1, 60, (2, 5), "cgs2"),
@@ -84,6 +101,8 @@ CASES = {
     "c5s": lambda: lanczos_case(200, 200, 200, 30, (2, 5), "cgs2"),
     # configs[4] itself: 8e7 rows (625 x 500 x 256), krylovdim 30, 3 restart cycles (the bench's other_configs record)
     "c5": lambda: lanczos_case(625, 500, 256, 30, (3,), "cgs2"),
+    # configs[3]: the Float64 truth of the dense Float32 matrix's top singular values
+    "c4_truth": lambda: dense_truth_case(2_000_000, 512),
 }
 
 

@@ -424,8 +424,8 @@ class HostSimLib:
         xv, yv, zv = self._vec(ctx, x), self._vec(ctx, y), self._vec(ctx, z)
         if A.shape[1] != len(xv) or A.shape[1] != len(zv) or A.shape[0] != len(yv):
             return self._fail(ctx, L.EDIM, "apply_normal_gram: length mismatch")
-        if _key(x) == _key(z):
-            return self._fail(ctx, L.EINVAL, "apply_normal_gram: z must not alias x")
+        if len({_key(x), _key(y), _key(z)}) < 3:
+            return self._fail(ctx, L.EINVAL, "apply_normal_gram: x, y and z must be three different vectors")
         ctx.launches += 2
         r = A @ xv
         self._setvec(ctx, y, r)
