@@ -787,7 +787,22 @@ def other_configs(kk, a, rank, world, local_rank, dist):
         except Exception as e:      # the headline line must still be printed: record the failure instead
             out["c5"] = config_failed(e, ctx)
 
-    if "c4o" in want and world == 1:
+    if "c4o" in want and world == 1 and os.environ.get("B2K_BENCH_CHILD") != "1":
+        # the one-pass kernel has not run on a B200 yet: its record is produced by a CHILD process (this script with
+        # --extra c4o and B2K_BENCH_CHILD=1), so that nothing it does — a crash, a hang, a poisoned CUDA context — can
+        # take the headline line of this process with it
+        try:
+            env = dict(os.environ, B2K_BENCH_CHILD="1")
+            cmd = [sys.executable, os.path.abspath(__file__), "--extra", "c4o", "--c4-rows", str(a.c4_rows)]
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+            lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            if res.returncode == 0 and lines:
+                out["c4_onepass"] = json.loads(lines[-1])
+            else:
+                out["c4_onepass"] = {"ok": False, "error": f"child exited with {res.returncode}: " + res.stderr[-500:]}
+        except Exception as e:
+            out["c4_onepass"] = {"ok": False, "error": f"{type(e).__name__}: {e}"[:600]}
+    elif "c4o" in want and world == 1:
         # config 4 in the flagged ONE-PASS mode of the GKL step: z = A'(A v) comes out of the
         # pass that forms A v (b2k_op_apply_normal_gram) and A'u_{k+1} is recovered from it, guarded by an error
         # estimate that falls back to a direct A'u.  Each orthogonalizer is run in the reference's two-pass form and in
@@ -860,6 +875,12 @@ def other_configs(kk, a, rank, world, local_rank, dist):
 
 def main():
     a = parse()
+    if os.environ.get("B2K_BENCH_CHILD") == "1":
+        # child of other_configs' c4o leg: that one record, as one JSON line, nothing else
+        import krylovkit_jl_b200 as kk
+        rec = other_configs(kk, a, 0, 1, int(os.environ.get("LOCAL_RANK", "0")), None).get("c4_onepass")
+        print(json.dumps(rec), flush=True)
+        return
     if a.impl == "reference":
         run_reference(a)
     else:

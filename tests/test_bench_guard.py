@@ -58,11 +58,11 @@ def test_failing_extra_config_becomes_a_record(monkeypatch, capsys):
     assert set(out) == {"c2_matrix_free", "c2_reference_default_orth", "widened_solvers", "c3", "c4", "c5", "c4_onepass"}
     for name, rec in out.items():
         assert rec["ok"] is False
-        if name == "widened_solvers":          # runs tools/run_configs.py on the real package: here "no CUDA device"
-            assert "B200Error" in rec["error"] or "Boom" in rec["error"]
+        if name in ("widened_solvers", "c4_onepass"):   # tools/run_configs.py on the real package / bench.py's child
+            assert "B200Error" in rec["error"] or "Boom" in rec["error"] or "CUDA" in rec["error"]   # process: "no CUDA device"
         else:
             assert "Boom: no device" in rec["error"]
-    assert len(closed) == 6                     # every failed configuration gave its context back
+    assert len(closed) == 5                     # every failed in-process configuration gave its context back
     assert "Boom" in capsys.readouterr().err    # the traceback goes to stderr, the JSON line stays clean
 
 
@@ -121,6 +121,7 @@ def test_onepass_extra_runs_on_the_simulator(monkeypatch):
     import krylovkit_jl_b200 as kk
     bench = _load_bench()
     monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", "c4o", "--c4-rows", "20000"])
+    monkeypatch.setenv("B2K_BENCH_CHILD", "1")          # the in-process body (bench.py runs it in a child process)
     a = bench.parse()
     with hostsim.installed(fused=True):
         out = bench.other_configs(kk, a, 0, 1, 0, None)
@@ -131,3 +132,17 @@ def test_onepass_extra_runs_on_the_simulator(monkeypatch):
         assert two["converged"] >= 6 and one["converged"] >= 6 and one["ok"]
         assert two["passes_over_A"] == two["numops"] and one["passes_over_A"] < one["numops"]
         assert one["max_rel_diff_sigma_vs_two_pass"] <= 3e-5
+
+
+def test_onepass_extra_is_isolated_in_a_child_process(monkeypatch):
+    """bench.other_configs 'c4o' without B2K_BENCH_CHILD spawns `bench.py --extra c4o` as a child and turns whatever
+    happens there into a record: here (no CUDA device) the child's context creation fails, the child still prints its
+    record, and the parent carries it — the parent itself never touches the one-pass kernel."""
+    bench = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", "c4o", "--c4-rows", "4000"])
+    monkeypatch.delenv("B2K_BENCH_CHILD", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    a = bench.parse()
+    out = bench.other_configs(types.SimpleNamespace(_lib=types.SimpleNamespace(load=lambda: None)), a, 0, 1, 0, None)
+    rec = out["c4_onepass"]
+    assert rec["ok"] is False and "error" in rec and ("B200Error" in rec["error"] or "CUDA" in rec["error"] or "cuda" in rec["error"])
