@@ -1764,6 +1764,100 @@ k_dense_onepass(const T* __restrict__ A, int64_t ld, int64_t m, int32_t n, const
     }
 }
 
+// Variant B of the same step for the shape config 4 has (Float32, n <= 512): 64-row tiles — 256-byte column segments
+// instead of 128 — in a 512-thread CTA that owns the SM (139 KB of shared memory), with the overlap a single CTA
+// per SM cannot get from its neighbours made explicit: every thread keeps its 16 loads of the NEXT tile in flight
+// in registers while the CTA reduces y and forms z for the current one; a register is refilled from the next tile
+// as soon as its value has been parked in shared memory.  Column stride 65 words (lane <-> column reads in phase 2
+// are conflict-free; the stores of 16 row groups x 2 columns per warp are two-way conflicted).  Selected by
+// b2k_debug_set_onepass_variant(1); the default stays variant A until both have been measured on a B200.
+constexpr int OPW_T = 512;
+constexpr int OPW_ROWS = 64;
+constexpr int OPW_PAD = 65;
+constexpr int OPW_LD = 16;       // loads per thread per tile: n <= OPW_LD * (OPW_T / 16) = 512
+
+__global__ void __launch_bounds__(OPW_T, 1)
+k_dense_onepass_w(const float* __restrict__ A, int64_t ld, int64_t m, int32_t n, const float* __restrict__ x,
+                  float* __restrict__ y, double* __restrict__ zpart, int64_t ntiles) {
+    constexpr int VPC = OPW_ROWS / 4;               // 16 float4 per tile column
+    constexpr int CSTEP = OPW_T / VPC;              // 32 columns per load of the whole CTA
+    extern __shared__ __align__(16) unsigned char op_smem[];
+    float* As = reinterpret_cast<float*>(op_smem);  // [n][OPW_PAD]
+    float* xs = As + (size_t)n * OPW_PAD;           // [n]
+    float* ys_part = xs + n;                        // [16 warps][64 rows]
+    float* ys = ys_part + (OPW_T / 32) * OPW_ROWS;  // [64 rows]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rq = tid % VPC;
+    const int c0 = tid / VPC;
+    for (int j = tid; j < n; j += OPW_T) xs[j] = x[j];
+    double zacc = 0.0;
+    float4 a[OPW_LD];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // rows [ld, ...) do not exist (ld is a multiple of 32, a tile has 64 rows): such a row group loads as zero
+    {
+        const int64_t r0 = (int64_t)blockIdx.x * OPW_ROWS + rq * 4;
+        const bool rows_ok = (int64_t)blockIdx.x < ntiles && r0 < ld;
+        const float* At = A + r0;
+#pragma unroll
+        for (int u = 0; u < OPW_LD; ++u) {
+            const int c = c0 + u * CSTEP;
+            a[u] = (rows_ok && c < n) ? op_ld_stream(reinterpret_cast<const float4*>(At + (int64_t)c * ld)) : zero4;
+        }
+    }
+    __syncthreads();
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i0 = tile * OPW_ROWS;
+        const int64_t next = tile + gridDim.x;
+        const int64_t r0n = next * OPW_ROWS + rq * 4;
+        const bool next_ok = next < ntiles && r0n < ld;
+        const float* Atn = A + r0n;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < OPW_LD; ++u) {
+            const int c = c0 + u * CSTEP;
+            if (c < n) {
+                float e4[4];
+                op_unpack(a[u], e4);
+                const float xc = xs[c];
+                float* dst = As + (size_t)c * OPW_PAD + rq * 4;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[e] = fmaf(e4[e], xc, acc[e]);
+                    dst[e] = e4[e];
+                }
+                // the register is free again: refill it from the next tile of this CTA
+                a[u] = next_ok ? op_ld_stream(reinterpret_cast<const float4*>(Atn + (int64_t)c * ld)) : zero4;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        if (lane < VPC)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ys_part[warp * OPW_ROWS + lane * 4 + e] = acc[e];
+        __syncthreads();
+        if (tid < OPW_ROWS) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < OPW_T / 32; ++w) s += ys_part[w * OPW_ROWS + tid];
+            ys[tid] = s;
+            if (i0 + tid < m) y[i0 + tid] = s;
+        }
+        __syncthreads();
+        if (tid < n) {
+            const float* col = As + (size_t)tid * OPW_PAD;
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int row = 0; row < OPW_ROWS; row += 2) {
+                p0 = fmaf(col[row], ys[row], p0);
+                p1 = fmaf(col[row + 1], ys[row + 1], p1);
+            }
+            zacc += (double)(p0 + p1);
+        }
+        __syncthreads();
+    }
+    if (tid < n) zpart[(size_t)blockIdx.x * n + tid] = zacc;
+}
+
 // z[c] = sum over the CTAs' partials, in a fixed order: 8 groups of threads take every 8th partial with four
 // independent running sums each (loads batched), then the groups are added in order.
 template <typename T>
@@ -1799,34 +1893,11 @@ __global__ void k_onepass_store(const double* __restrict__ dres, T* __restrict__
     if (c < n) zout[c] = (T)dres[c];
 }
 
+int g_onepass_variant = 0;       // 0: 32-row tiles, 3 CTAs per SM (A); 1: 64-row tiles, register-pipelined (B, Float32 n <= 512)
+
+// per-CTA partials -> z (and the sum over the ranks of a row-sharded context)
 template <typename T>
-int32_t onepass_t(b2k_ctx* ctx, b2k_op* op, const VecRef& x, const VecRef& y, const VecRef& z) {
-    const int n = (int)op->n_cols;
-    const size_t smem = ((size_t)n * OP_PAD + n + (OP_T / 32) * OP_ROWS + OP_ROWS) * sizeof(T);
-    if (smem > 227u * 1024u)
-        return b2k_fail(ctx, B2K_ENOTSUP, "one-pass dense step: a 32 x %d tile needs %zu bytes of shared memory", n, smem);
-    void (*kern)(const T*, int64_t, int64_t, int32_t, const T*, T*, double*, int64_t) =
-        n <= OP_T ? k_dense_onepass<T, 1> : n <= 2 * OP_T ? k_dense_onepass<T, 2> :
-        n <= 4 * OP_T ? k_dense_onepass<T, 4> : k_dense_onepass<T, OP_ZMAX>;
-    B2K_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    B2K_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OP_T, smem));
-    if (occ < 1) return b2k_fail(ctx, B2K_ENOTSUP, "one-pass dense step: a %d-column tile does not fit an SM", n);
-    const int64_t ntiles = op->ld / OP_ROWS;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)occ * ctx->num_sms);
-    const size_t need = (size_t)grid * n * sizeof(double);
-    if (op->part_bytes < need) {
-        if (op->part) B2K_DFREE(op->part);
-        op->part = nullptr;
-        op->part_bytes = 0;
-        B2K_CUDA(ctx, B2K_DMALLOC(&op->part, need));
-        op->part_bytes = need;
-    }
-    const int pr = b2k_prof_begin(ctx, 8, (double)sizeof(T) * ((double)op->n_rows * n + (double)op->n_rows + n));
-    kern<<<grid, OP_T, smem, ctx->stream>>>((const T*)op->A, op->ld, op->n_rows, n, (const T*)x.ptr,
-                                                           (T*)y.ptr, op->part, ntiles);
-    b2k_prof_end(ctx, pr);
-    B2K_LAUNCH_CHECK(ctx);
+int32_t onepass_finish(b2k_ctx* ctx, b2k_op* op, int grid, int n, const VecRef& y, const VecRef& z) {
     const bool reduce_ranks = ctx->nranks > 1 && y.sharded;
     k_onepass_reduce<T><<<(n + 31) / 32, 256, 0, ctx->stream>>>(op->part, grid, n, ctx->d_res,
                                                                 reduce_ranks ? nullptr : (T*)z.ptr);
@@ -1837,6 +1908,58 @@ int32_t onepass_t(b2k_ctx* ctx, b2k_op* op, const VecRef& x, const VecRef& y, co
         B2K_LAUNCH_CHECK(ctx);
     }
     return B2K_OK;
+}
+
+int32_t onepass_part(b2k_ctx* ctx, b2k_op* op, size_t need) {
+    if (op->part_bytes < need) {
+        if (op->part) B2K_DFREE(op->part);
+        op->part = nullptr;
+        op->part_bytes = 0;
+        B2K_CUDA(ctx, B2K_DMALLOC(&op->part, need));
+        op->part_bytes = need;
+    }
+    return B2K_OK;
+}
+
+int32_t onepass_w(b2k_ctx* ctx, b2k_op* op, const VecRef& x, const VecRef& y, const VecRef& z) {
+    const int n = (int)op->n_cols;
+    const size_t smem = ((size_t)n * OPW_PAD + n + (OPW_T / 32) * OPW_ROWS + OPW_ROWS) * sizeof(float);
+    B2K_CUDA(ctx, cudaFuncSetAttribute(k_dense_onepass_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (op->ld + OPW_ROWS - 1) / OPW_ROWS;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
+    B2K_TRY(onepass_part(ctx, op, (size_t)grid * n * sizeof(double)));
+    const int pr = b2k_prof_begin(ctx, 8, 4.0 * ((double)op->n_rows * n + (double)op->n_rows + n));
+    k_dense_onepass_w<<<grid, OPW_T, smem, ctx->stream>>>((const float*)op->A, op->ld, op->n_rows, n, (const float*)x.ptr,
+                                                         (float*)y.ptr, op->part, ntiles);
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    return onepass_finish<float>(ctx, op, grid, n, y, z);
+}
+
+template <typename T>
+int32_t onepass_t(b2k_ctx* ctx, b2k_op* op, const VecRef& x, const VecRef& y, const VecRef& z) {
+    const int n = (int)op->n_cols;
+    const size_t smem = ((size_t)n * OP_PAD + n + (OP_T / 32) * OP_ROWS + OP_ROWS) * sizeof(T);
+    if (smem > 227u * 1024u)
+        return b2k_fail(ctx, B2K_ENOTSUP, "one-pass dense step: a 32 x %d tile needs %zu bytes of shared memory", n, smem);
+    if (sizeof(T) == 4 && g_onepass_variant == 1 && n <= OPW_LD * (OPW_T / (OPW_ROWS / 4)))
+        return onepass_w(ctx, op, x, y, z);
+    void (*kern)(const T*, int64_t, int64_t, int32_t, const T*, T*, double*, int64_t) =
+        n <= OP_T ? k_dense_onepass<T, 1> : n <= 2 * OP_T ? k_dense_onepass<T, 2> :
+        n <= 4 * OP_T ? k_dense_onepass<T, 4> : k_dense_onepass<T, OP_ZMAX>;
+    B2K_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    B2K_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OP_T, smem));
+    if (occ < 1) return b2k_fail(ctx, B2K_ENOTSUP, "one-pass dense step: a %d-column tile does not fit an SM", n);
+    const int64_t ntiles = op->ld / OP_ROWS;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)occ * ctx->num_sms);
+    B2K_TRY(onepass_part(ctx, op, (size_t)grid * n * sizeof(double)));
+    const int pr = b2k_prof_begin(ctx, 8, (double)sizeof(T) * ((double)op->n_rows * n + (double)op->n_rows + n));
+    kern<<<grid, OP_T, smem, ctx->stream>>>((const T*)op->A, op->ld, op->n_rows, n, (const T*)x.ptr,
+                                                           (T*)y.ptr, op->part, ntiles);
+    b2k_prof_end(ctx, pr);
+    B2K_LAUNCH_CHECK(ctx);
+    return onepass_finish<T>(ctx, op, grid, n, y, z);
 }
 
 }  // namespace
@@ -1862,6 +1985,13 @@ extern "C" int32_t b2k_op_apply_normal_gram(b2k_ctx* ctx, const b2k_op* op, b2k_
     b2k_op* mop = const_cast<b2k_op*>(op);          // the per-CTA partial buffer is allocated on first use
     if (ctx->dtype == B2K_F64) return onepass_t<double>(ctx, mop, rx, ry, rz);
     return onepass_t<float>(ctx, mop, rx, ry, rz);
+}
+
+// A/B switch of the one-pass dense step (tools / tests / bench.py's c4o child): 0 = variant A, 1 = variant B
+extern "C" int32_t b2k_debug_set_onepass_variant(int32_t v) {
+    if (v < 0 || v > 1) return B2K_EINVAL;
+    g_onepass_variant = v;
+    return B2K_OK;
 }
 
 // apply(A, X::Block) — blocklanczos.jl:38: Y[i] = A X[i] for the p vectors of a block.  Single-GPU CSR operators

@@ -131,6 +131,9 @@ class HostSimLib:
         self.chain_mode = 0 if mode == 0 else 1
         return L.OK
 
+    def b2k_debug_set_onepass_variant(self, v):
+        return L.OK if v in (0, 1) else L.EINVAL            # one numpy product stands for both kernels
+
     def b2k_debug_set_transform(self, mode):
         return L.OK
 

@@ -17,6 +17,24 @@ pytestmark = pytest.mark.gpu
 SEED = 20260923
 
 
+@pytest.fixture()
+def variant_b():
+    """kernel variant B (64-row tiles, register-pipelined; Float32 with n <= 512, everything else runs variant A)"""
+    lib = kk._lib.load()
+    assert lib.b2k_debug_set_onepass_variant(1) == 0
+    yield
+    assert lib.b2k_debug_set_onepass_variant(0) == 0
+
+
+@pytest.mark.parametrize("m,n", [(20000, 512), (33, 300), (70001, 256), (96, 500), (160, 512), (100, 70), (4000, 6)])
+def test_apply_normal_gram_variant_b(variant_b, m, n):
+    test_apply_normal_gram(m, n, np.float32)
+
+
+def test_svdsolve_onepass_config4_small_f32_variant_b(variant_b):
+    test_svdsolve_onepass_config4_small_f32()
+
+
 @pytest.mark.parametrize("m,n,dtype", [(20000, 512, np.float32), (1000, 70, np.float64), (33, 300, np.float32),
                                        (5000, 1030, np.float32), (4097, 600, np.float64), (96, 6, np.float64),
                                        (70001, 256, np.float32)])

@@ -293,6 +293,12 @@ def test_onepass_apply(sim, m, n, dtype):
     OP.test_apply_normal_gram(m, n, dtype)
 
 
+def test_onepass_variant_switch(sim):
+    lib = kk._lib.load()
+    assert lib.b2k_debug_set_onepass_variant(1) == 0 and lib.b2k_debug_set_onepass_variant(0) == 0
+    assert lib.b2k_debug_set_onepass_variant(2) != 0
+
+
 def test_onepass_apply_errors(sim):
     OP.test_apply_normal_gram_errors()
 
