@@ -79,3 +79,35 @@ def test_gmres_full_size_matches_oracle(case):
     chk.add_(info.residual, 1.0).add_(b, -1.0)
     assert chk.norm() <= 1e-10 * b.norm()
     ctx.close()
+
+
+@pytest.mark.parametrize("orth_name", ["mgs2", "cgsr"])
+def test_svdsolve_config4_full_size_vs_float64_truth(orth_name):
+    """configs[3] at its full size (dense 2e6 x 512 Float32 splitmix matrix, GKL krylovdim 30, tol 1e-5, 6 triplets :LR)
+    through the reference's two-pass step, with the reference-default MGS2 and with the iterative-refinement
+    orthogonalizer the reference's own Float32 tests use: the converged singular values against the Float64 truth of the
+    same matrix (tests/golden/fullsize.json:c4_truth — sqrt eig of the Float64 Gram matrix) within the Float32 bar 3e-5,
+    and the SVD relations A v = s u (+ residual), A'u = s v evaluated on the device."""
+    g = GOLD["c4_truth"]
+    m, n = g["shape"]
+    kd = 30
+    ctx = kk.B200Context(m, kd + 24, dtype=np.float32)
+    sv = ctx.add_space(n, kd + 24, sharded=False)
+    op = kk.B200Dense.splitmix(ctx, m, n, g["seed"], sv)
+    u0 = ctx.splitmix(g["seed"] + 1)
+    orth = {"mgs2": kk.mgs2, "cgsr": kk.ClassicalGramSchmidtIR(eta=0.75)}[orth_name]
+    alg = kk.GKL(orth=orth, krylovdim=kd, maxiter=100, tol=1e-5, verbosity=0)
+    S, Lv, Rv, info = kk.svdsolve(op, u0, 6, "LR", alg)
+    assert info.converged >= 6
+    ref = np.array(g["sigma_float64_truth"])
+    rel = np.abs(np.array(S[:6], dtype=np.float64) - ref) / ref
+    assert rel.max() <= 3e-5, (list(S[:6]), list(ref))
+    for i in range(3):
+        w = kk.apply_normal(op, Rv[i])
+        w.add_(Lv[i], -float(S[i]))
+        z = kk.apply_adjoint(op, Lv[i])
+        z.add_(Rv[i], -float(S[i]))
+        assert w.norm() / S[i] < 1e-4 and z.norm() / S[i] < 1e-4
+        del w, z
+    assert info.passes == info.numops           # the reference's step: both products stream A
+    ctx.close()
