@@ -218,6 +218,45 @@ function apply_normal_gram(A::B200Dense, x::B200Vec)
     return y, z
 end
 
+# ---- Block (BlockLanczos) — factorizations/blocklanczos.jl:10-52, 277-353 -----------------------------------
+# The reference runs these as loops of single-vector calls (p applies, p*q inners, p*k MGS steps); here each is one
+# library call: SpMM for apply(A, ::Block), one multi-right-hand-side launch for block_inner, the library's
+# block_reorthogonalize! / block_qr! with the reference's arithmetic (rank drop below tol, DGKS drift pass).
+import KrylovKit: Block, block_inner, block_reorthogonalize!, block_qr!
+const B200Block = Block{<:B200Vec}
+_handles(b::B200Block) = Int32[v.handle for v in b.vec]
+_ctx(b::B200Block) = b.vec[1].ctx
+
+function apply(A::B200CSR, X::B200Block)                                         # blocklanczos.jl:38
+    Y = [B200Vec(x.ctx; space = space(x)) for x in X.vec]
+    hy = Int32[y.handle for y in Y]
+    check(_ctx(X).h, ccall((:b2k_op_apply_block, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Cint),
+                           _ctx(X).h, A.h, _handles(X), hy, length(X)))
+    return Block(Y)
+end
+function block_inner(B₁::B200Block, B₂::B200Block)                               # blocklanczos.jl:43-52
+    M = Matrix{Float64}(undef, length(B₁), length(B₂))
+    check(_ctx(B₁).h, ccall((:b2k_block_inner, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Ptr{Float64}),
+                            _ctx(B₁).h, _handles(B₁), length(B₁), _handles(B₂), length(B₂), M))
+    return M
+end
+function block_reorthogonalize!(R::B200Block, V::OrthonormalBasis{<:B200Vec})    # blocklanczos.jl:277-284
+    hv = Int32[q.handle for q in V]
+    check(_ctx(R).h, ccall((:b2k_block_reorthogonalize, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int32}, Cint),
+                           _ctx(R).h, _handles(R), length(R), hv, length(hv)))
+    return R
+end
+function block_qr!(block::B200Block, tol::Real)                                  # blocklanczos.jl:312-353
+    p = length(block)
+    R = zeros(Float64, p, p)
+    good = zeros(Int32, p)
+    drift = Ref{Int32}(0)
+    check(_ctx(block).h, ccall((:b2k_block_qr, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Float64, Ptr{Float64}, Ptr{Int32}, Ref{Int32}),
+                               _ctx(block).h, _handles(block), p, Float64(tol), R, good, drift))
+    good_idx = findall(!=(0), good)
+    return R[good_idx, :], good_idx, drift[] != 0
+end
+
 # ---- basis fast path: what `Array` gets via _use_multithreaded_array_kernel (orthonormal.jl:66-73) --------
 const B200Basis = OrthonormalBasis{<:B200Vec}
 _cols(b::B200Basis, r) = Int32[b[i].handle for i in r]
