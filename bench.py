@@ -794,7 +794,7 @@ def other_configs(kk, a, rank, world, local_rank, dist):
         try:
             env = dict(os.environ, B2K_BENCH_CHILD="1")
             cmd = [sys.executable, os.path.abspath(__file__), "--extra", "c4o", "--c4-rows", str(a.c4_rows)]
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
             lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
             if res.returncode == 0 and lines:
                 out["c4_onepass"] = json.loads(lines[-1])
