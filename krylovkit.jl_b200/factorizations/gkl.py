@@ -18,7 +18,8 @@ matrix.  So every recycled image carries an error estimate eta (in units of one 
 
     eta_{k+1} = ( sum_j |c_j| eta_j + 2 ||B|| ) / beta_k,       ||B|| = max_k hypot(alpha_k, beta_k) <= ||A||
 
-and an image whose estimate exceeds `onepass_eta` is thrown away: that step forms A'u directly (eta = 1), exactly
+and an image whose estimate exceeds max(`onepass_eta` = 4, 0.01 tol / (eps ||B||)) — four roundings of a direct product,
+or an absolute error of 1 % of the caller's tolerance — is thrown away: that step forms A'u directly (eta = 1), exactly
 like the reference.  One pass where it is safe, two where it is not; `passes` counts what was actually streamed,
 `numops` keeps counting both products per step, like the reference.  With the estimate in place the results differ
 from the two-pass step by rounding at the level of the tolerance asked for (tools/onepass_gkl_study.py)."""
@@ -39,7 +40,7 @@ class GKLIterator:
     """GKLIterator(f, u₀, orth, keepvecs) — gkl.jl:123-139.  u₀ lives in the codomain."""
 
     def __init__(self, operator, u0: B200Vec, orth: Orthogonalizer, keepvecs: bool = True, onepass: bool = False,
-                 onepass_eta: float = 4.0):
+                 onepass_eta: float = 4.0, onepass_eta_tol: float = 0.0):
         if not keepvecs and (orth.is_reorth2 or orth.is_ir):
             raise ValueError("Cannot use reorthogonalization without keeping all Krylov vectors")
         if onepass and not isinstance(operator, B200Dense):
@@ -47,7 +48,12 @@ class GKLIterator:
         if onepass and not keepvecs:
             raise ValueError("GKL onepass mode keeps all Krylov vectors")
         self.operator, self.u0, self.orth, self.keepvecs, self.onepass = operator, u0, orth, keepvecs, onepass
-        self.onepass_eta = float(onepass_eta)    # largest error estimate a recycled A'u may carry (see module doc)
+        # largest error estimate a recycled A'u may carry (module doc): onepass_eta roundings of a direct product, or
+        # an absolute error onepass_eta_tol * eps (= a fraction of the caller's tolerance), whichever is larger
+        self.onepass_eta, self.onepass_eta_tol = float(onepass_eta), float(onepass_eta_tol)
+
+    def eta_max(self, anorm: float) -> float:
+        return max(self.onepass_eta, self.onepass_eta_tol / anorm if anorm > 0 else 0.0)
 
 
 class GKLFactorization:
@@ -107,7 +113,7 @@ def initialize(it: GKLIterator) -> GKLFactorization:
         anorm = math.hypot(alpha, beta)
         eta_next = (alpha + 2 * anorm) / beta if beta > 0 else math.inf
         g_next = None
-        if eta_next <= it.onepass_eta:
+        if eta_next <= it.eta_max(anorm):
             g_next = unproject_(z, G, [alpha], -1 / beta, 1 / (alpha * beta0 * beta))
         else:
             z.free()
@@ -119,7 +125,7 @@ def initialize(it: GKLIterator) -> GKLFactorization:
 
 
 def gklrecurrence(operator, U: OrthonormalBasis, V: OrthonormalBasis, beta: float,
-                  orth: Orthogonalizer, state: GKLFactorization | None = None, eta_max: float = 4.0):
+                  orth: Orthogonalizer, state: GKLFactorization | None = None, eta_max=None):
     """gklrecurrence ×5 — gkl.jl:294-404.  `state` (onepass mode): its G / g_next are consumed and renewed."""
     t = orth.tag
     u = U[-1]
@@ -194,7 +200,7 @@ def gklrecurrence(operator, U: OrthonormalBasis, V: OrthonormalBasis, beta: floa
         state.anorm = max(state.anorm, math.hypot(alpha, beta))
         ok = beta > 0 and math.isfinite(beta) and math.isfinite(alpha)
         state.eta_next = (float(np.dot(np.abs(c), state.eta)) + 2 * state.anorm) / beta if ok else math.inf
-        if state.eta_next <= eta_max:
+        if state.eta_next <= (eta_max(state.anorm) if callable(eta_max) else 4.0):
             state.g_next = unproject_(z, state.G, c, -1 / beta, 1 / beta)     # A'(r / beta)
         else:
             z.free()                              # too much inherited error: the next step forms A'u directly
@@ -206,7 +212,7 @@ def expand_(it: GKLIterator, state: GKLFactorization) -> GKLFactorization:
     betaold = state.normres()
     U, V, r = state.U, state.V, state.r
     U.push(r.scale_(1 / betaold))
-    v, r, alpha, beta = gklrecurrence(it.operator, U, V, betaold, it.orth, state, it.onepass_eta)
+    v, r, alpha, beta = gklrecurrence(it.operator, U, V, betaold, it.orth, state, it.eta_max)
     V.push(v)
     state.alphas.append(alpha)
     state.betas.append(beta)
@@ -233,7 +239,7 @@ def shrink_(state: GKLFactorization, k: int) -> GKLFactorization:
         while len(state.G) > k + 1:
             state.G.pop()
             state.eta.pop()
-        state.g_next, state.eta_next = state.G.pop(), state.eta.pop()      # (every estimate kept is <= onepass_eta)
+        state.g_next, state.eta_next = state.G.pop(), state.eta.pop()      # (every estimate kept passed the check when it was made)
     del state.alphas[k:]
     del state.betas[k:]
     state.k = k

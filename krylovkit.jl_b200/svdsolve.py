@@ -74,9 +74,10 @@ def _svdsolve_gkl(A, u0: B200Vec, howmany: int, which: str, alg: GKL):
         raise ValueError(f"krylov dimension {krylovdim} too small to compute {howmany} singular values")
     numiter = 1
     onepass = getattr(alg, "onepass", False)
-    # a recycled A'u may carry the rounding of at most 4 direct products, or 1 % of the tolerance asked for
-    eta_max = max(4.0, 0.01 * alg.tol / float(np.finfo(u0.ctx.np_dtype).eps))
-    it = gkl.GKLIterator(A, u0, alg.orth, onepass=onepass, onepass_eta=eta_max)
+    # a recycled A'u may carry the rounding of at most 4 direct products, or an absolute error of 1 % of the tolerance
+    # asked for (eta counts roundings of size eps ||A||: the iterator divides by its running estimate of ||A||)
+    eta_tol = 0.01 * alg.tol / float(np.finfo(u0.ctx.np_dtype).eps)
+    it = gkl.GKLIterator(A, u0, alg.orth, onepass=onepass, onepass_eta=4.0, onepass_eta_tol=eta_tol)
     fact = gkl.initialize(it)
     numops = 2
     tol = alg.tol

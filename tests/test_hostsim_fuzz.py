@@ -275,8 +275,40 @@ def _blocked_mgs2(rng, seed, ctx, n):
     np.testing.assert_allclose(x.to_host(), ox, rtol=1e-7, atol=1e-9)
 
 
+def _gkl_onepass(rng, seed, ctx, n):
+    """The flagged one-pass GKL step (GKL(onepass=True): A'u recovered from z = A'(A v), with the error estimate that
+    falls back to a direct product) through svdsolve on random problems — all six orthogonalizers, :LR / :SR, eager or
+    not, few restarts, start vectors inside and outside range(A), rank-deficient A: the same counts and singular values
+    as the oracle's two-pass svdsolve, and never more passes over A than the two-pass step."""
+    name, o, ov = _orth_pair(rng)
+    m = n + int(rng.integers(0, 40))
+    A = rng.standard_normal((m, n))
+    if seed % 5 == 0:
+        A[:, -1] = A[:, 0]                                       # rank deficient
+    u0 = rng.random(m) if seed % 3 else A @ rng.random(n)         # every third start vector lies in range(A)
+    kd = int(rng.integers(2, min(n, 12) + 1))
+    hm = int(rng.integers(1, kd + 1))
+    which = ["LR", "SR"][int(rng.integers(0, 2))]
+    alg = kk.GKL(orth=o, krylovdim=kd, maxiter=int(rng.integers(1, 6)), tol=1e-9, eager=bool(rng.integers(0, 2)), verbosity=0,
+                 onepass=True)
+    S, Lv, Rv, info = kk.svdsolve(A, u0, hm, which, alg)
+    oS, _, _, oinfo = ko.svdsolve_gkl(A, u0, hm, which, krylovdim=kd, maxiter=alg.maxiter, tol=1e-9, orth=ov, eager=alg.eager)
+    # (without reorthogonalisation — cgs / mgs — a residual at rounding level makes the count of "converged" values
+    # noise, in the two-pass step as much as here)
+    _counts(info, oinfo, ("numops", "numiter") if name in ("cgs", "mgs") else ("numops", "numiter", "converged"))
+    assert info.numops // 2 + 1 <= info.passes <= info.numops
+    if name not in ("cgs", "mgs"):
+        assert len(S) == len(oS)
+        np.testing.assert_allclose(S, oS, rtol=1e-6, atol=1e-8)
+        for i in range(min(2, len(S))):                          # A v = s u + r, A'u = s v (u is arbitrary for s = 0)
+            if S[i] < 1e-8 * max(S):
+                continue
+            assert np.linalg.norm(A.T @ Lv[i] - S[i] * Rv[i]) < 1e-6 * max(1.0, S[0])
+            assert np.linalg.norm(A @ Rv[i] - S[i] * Lv[i] - info.residual[i]) < 1e-6 * max(1.0, S[0])
+
+
 @pytest.mark.parametrize("seed", range(24))
-@pytest.mark.parametrize("kind", [_blocklanczos_fast_block, _blocked_mgs2], ids=["fast_block", "mgs2b"])
+@pytest.mark.parametrize("kind", [_blocklanczos_fast_block, _blocked_mgs2, _gkl_onepass], ids=["fast_block", "mgs2b", "gkl_onepass"])
 def test_flagged_modes_agree_with_oracle(kind, seed):
     """(300 seeds of each ran clean when these were added.)"""
     warnings.simplefilter("ignore")
