@@ -821,6 +821,51 @@ def other_configs(kk, a, rank, world, local_rank, dist):
                    "note": "numops counts both products of a step in both modes (as the reference does); passes = what was "
                            "streamed from HBM: 2 per step in the reference's form, 1 per step in the one-pass form unless "
                            "the error estimate of the recycled A'u forces a direct product"}
+            # 1) the fused kernel alone, both variants: 12 event-timed launches each (profile class 8); each variant's y
+            #    and z against the library's two separate products (same arithmetic, different summation order).  The
+            #    faster variant that passed its check is the one the solver legs below use.
+            x = ctx.splitmix(SEED + 2, sv)
+            y2 = kk.apply_normal(op, x)
+            z2 = kk.apply_adjoint(op, y2)
+            ref = (y2.to_host().astype(np.float64), z2.to_host().astype(np.float64))
+            del y2, z2
+            names = {0: "A_32row_tiles_3cta_per_sm", 1: "B_64row_tiles_register_pipelined"}
+            best = None
+            for vid in (0, 1):
+                if lib.b2k_debug_set_onepass_variant(vid) != 0:
+                    continue
+                try:
+                    lib.b2k_prof_reset(ctx.h)
+                    lib.b2k_prof_enable(ctx.h, 1)
+                    for _ in range(12):
+                        y, z = kk.apply_normal_gram(op, x)
+                        del y, z
+                    c, ms, b = C.c_int64(), C.c_double(), C.c_double()
+                    lib.b2k_prof_read(ctx.h, 8, C.byref(c), C.byref(ms), C.byref(b))
+                    lib.b2k_prof_enable(ctx.h, 0)
+                    y, z = kk.apply_normal_gram(op, x)
+                    yh, zh = y.to_host().astype(np.float64), z.to_host().astype(np.float64)
+                    del y, z
+                    k = {"launches": c.value}
+                    if c.value:
+                        k.update({"avg_ms": ms.value / c.value, "GBs": b.value / ms.value / 1e6,
+                                  "frac_of_hbm_peak": b.value / ms.value / 1e6 / pk,
+                                  "algorithmic_bytes": "4 (m n + m + n) per launch: A read ONCE for A v and A'(A v)"})
+                    k["max_rel_diff_y_vs_separate_products"] = float(np.abs(yh - ref[0]).max() / np.abs(ref[0]).max())
+                    k["max_rel_diff_z_vs_separate_products"] = float(np.abs(zh - ref[1]).max() / np.abs(ref[1]).max())
+                    k["ok"] = bool(k["max_rel_diff_y_vs_separate_products"] < 1e-4 and k["max_rel_diff_z_vs_separate_products"] < 1e-4)
+                    rec["kernel:" + names[vid]] = k
+                    if k["ok"] and (best is None or k.get("avg_ms", 1e30) < best[1]):
+                        best = (vid, k.get("avg_ms", 1e30))
+                except Exception as e:
+                    rec["kernel:" + names[vid]] = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+                finally:
+                    lib.b2k_debug_set_onepass_variant(0)
+            del x
+            use = best[0] if best is not None else 0
+            rec["kernel_variant_used_by_the_solver"] = names[use] + ("" if best is not None else " (no variant passed its check)")
+            # 2) the solver, two-pass reference step against the one-pass step, per orthogonalizer
+            lib.b2k_debug_set_onepass_variant(use)
             for oname, orth in (("mgs2", kk.mgs2), ("cgsr_eta0.75", kk.ClassicalGramSchmidtIR(eta=0.75))):
                 sig = {}
                 for mode, onepass in (("two_pass_reference", False), ("one_pass_flagged", True)):
@@ -844,44 +889,12 @@ def other_configs(kk, a, rank, world, local_rank, dist):
                         r["max_rel_err_sigma_vs_float64_truth"] = err
                     del Lv, Rv, info
                     if onepass:
-                        r["kernel_variant_used_by_the_solver"] = "A (32-row tiles, 3 CTAs per SM)"
                         r["max_rel_diff_sigma_vs_two_pass"] = float(np.max(np.abs(sig[mode] - sig["two_pass_reference"])
                                                                            / sig["two_pass_reference"]))
                         r["ok"] = bool(r["max_rel_diff_sigma_vs_two_pass"] <= 3e-5 and r["converged"] >= 6 and
                                        r.get("max_rel_err_sigma_vs_float64_truth", 0.0) <= 3e-5)
                     rec[f"{oname}:{mode}"] = r
-            # the fused kernel alone, both variants: 12 event-timed launches each (profile class 8), and variant B's
-            # results against variant A's on the same x (same arithmetic, different summation order)
-            x = ctx.splitmix(SEED + 2, sv)
-            ref = None
-            for vname, vid in (("A_32row_tiles_3cta_per_sm", 0), ("B_64row_tiles_register_pipelined", 1)):
-                if lib.b2k_debug_set_onepass_variant(vid) != 0:
-                    continue
-                try:
-                    lib.b2k_prof_reset(ctx.h)
-                    lib.b2k_prof_enable(ctx.h, 1)
-                    for _ in range(12):
-                        y, z = kk.apply_normal_gram(op, x)
-                        yh, zh = y.to_host().astype(np.float64), z.to_host().astype(np.float64)
-                        del y, z
-                    c, ms, b = C.c_int64(), C.c_double(), C.c_double()
-                    lib.b2k_prof_read(ctx.h, 8, C.byref(c), C.byref(ms), C.byref(b))
-                    lib.b2k_prof_enable(ctx.h, 0)
-                    k = {"launches": c.value}
-                    if c.value:
-                        k.update({"avg_ms": ms.value / c.value, "GBs": b.value / ms.value / 1e6,
-                                  "frac_of_hbm_peak": b.value / ms.value / 1e6 / pk,
-                                  "algorithmic_bytes": "4 (m n + m + n) per launch: A read ONCE for A v and A'(A v)"})
-                    if ref is None:
-                        ref = (yh, zh)
-                    else:
-                        k["max_rel_diff_y_vs_variant_A"] = float(np.abs(yh - ref[0]).max() / np.abs(ref[0]).max())
-                        k["max_rel_diff_z_vs_variant_A"] = float(np.abs(zh - ref[1]).max() / np.abs(ref[1]).max())
-                        k["ok"] = bool(k["max_rel_diff_y_vs_variant_A"] < 1e-4 and k["max_rel_diff_z_vs_variant_A"] < 1e-4)
-                    rec["kernel:" + vname] = k
-                finally:
-                    lib.b2k_debug_set_onepass_variant(0)
-            del x
+            lib.b2k_debug_set_onepass_variant(0)
             out["c4_onepass"] = rec
             ctx.close()
         except Exception as e:      # the headline line must still be printed: record the failure instead
