@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200krylov.so")
 SOURCES = ["ctx.cu", "blas1.cu", "spmv.cu", "basis.cu", "block.cu", "dist.cu", "hostmath.cu"]
-HEADERS = ["common.cuh", "tsk.cuh", os.path.join("..", "..", "include", "b200krylov.h")]
+HEADERS = ["common.cuh", "tsk.cuh", "onepass_kernels.cuh", os.path.join("..", "..", "include", "b200krylov.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
