@@ -84,6 +84,12 @@ static int run_case(int64_t m, int n, int grid_cap, int variant) {
 int main(int argc, char** argv) {
     const bool quick = argc > 1 && std::atoi(argv[1]) == 1;
     int bad = 0;
+    if (argc > 1 && std::atoi(argv[1]) == 2) {          // a longer run by hand: many tiles per CTA at config 4's width
+        bad += run_case<float>(3000, 512, 4, 0);
+        bad += run_case<float>(3000, 512, 3, 1);
+        std::printf(bad ? "FAILED\n" : "all ok\n");
+        return bad ? 1 : 0;
+    }
     bad += run_case<float>(100, 70, 3, 0);
     bad += run_case<float>(100, 70, 2, 1);
     bad += run_case<float>(96, 300, 2, 1);          // ld = 96: the last 64-row tile of variant B is half outside A
