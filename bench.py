@@ -143,6 +143,25 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def json_safe(obj):
+    """json.dumps writes NaN / Infinity for non-finite floats, which a strict JSON parser rejects: the one line this
+    script prints must stay parseable whatever an (extra) configuration measured, so they become strings."""
+    if isinstance(obj, dict):
+        return {str(k): json_safe(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [json_safe(v) for v in obj]
+    if isinstance(obj, (np.floating, float)):
+        f = float(obj)
+        return f if np.isfinite(f) else repr(f)
+    if isinstance(obj, np.integer):
+        return int(obj)
+    if isinstance(obj, np.bool_):
+        return bool(obj)
+    if isinstance(obj, np.ndarray):
+        return json_safe(obj.tolist())
+    return obj
+
+
 def pinned_array(lib, count, dtype):
     dt = np.dtype(dtype)
     p = C.c_void_p()
@@ -313,7 +332,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(json_safe(line), allow_nan=False, default=str), flush=True)
 
 
 def workload_config(a):
@@ -535,7 +554,7 @@ def run_ours(a):
             "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "other_configs": extras,
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(json_safe(line), allow_nan=False, default=str), flush=True)
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -909,7 +928,7 @@ def main():
         # child of other_configs' c4o leg: that one record, as one JSON line, nothing else
         import krylovkit_jl_b200 as kk
         rec = other_configs(kk, a, 0, 1, int(os.environ.get("LOCAL_RANK", "0")), None).get("c4_onepass")
-        print(json.dumps(rec), flush=True)
+        print(json.dumps(json_safe(rec), allow_nan=False, default=str), flush=True)
         return
     if a.impl == "reference":
         run_reference(a)
