@@ -211,6 +211,22 @@ class HostSimLib:
     def b2k_device_sync(self):
         return L.OK
 
+    # "pinned" host buffers: plain host memory, kept alive until freed
+    def b2k_pinned_alloc(self, nbytes, out):
+        buf = (C.c_byte * max(1, int(nbytes)))()
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        self._pinned[C.addressof(buf)] = buf
+        _set(out, C.addressof(buf))
+        return L.OK
+
+    def b2k_pinned_free(self, p):
+        getattr(self, "_pinned", {}).pop(_key(p), None)
+        return L.OK
+
+    def b2k_cache_release(self):
+        return L.OK
+
     def b2k_timer_start(self, h):
         import time
         self._c(h).t0 = time.perf_counter()

@@ -146,3 +146,47 @@ def test_onepass_extra_is_isolated_in_a_child_process(monkeypatch):
     out = bench.other_configs(types.SimpleNamespace(_lib=types.SimpleNamespace(load=lambda: None)), a, 0, 1, 0, None)
     rec = out["c4_onepass"]
     assert rec["ok"] is False and "error" in rec and ("B200Error" in rec["error"] or "CUDA" in rec["error"] or "cuda" in rec["error"])
+
+
+def test_headline_path_runs_on_the_simulator_and_prints_the_contract(monkeypatch, capsys):
+    """bench.run_ours end to end on tests/hostsim.py at a small size — the resident job, the host-buffer (e2e) leg with
+    its pinned buffers, the per-kernel profile and the assembly of the one JSON line — so that the host code of the
+    headline is exercised on a box without a GPU.  The line must parse STRICTLY (no NaN / Infinity tokens) and carry
+    the keys of the bench contract; the Ritz values of both legs must agree with the oracle on the same (A, x0)."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostsim
+    from oracle import krylov_oracle as ko
+    bench = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--nx", "40", "--ny", "30", "--krylovdim", "12", "--cycles", "3", "--steps", "2",
+                                      "--warmup", "1", "--no-cpu-baseline", "--extra", ""])
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("B2K_BENCH_CHILD", raising=False)
+    a = bench.parse()
+    with hostsim.installed(fused=True):
+        bench.run_ours(a)
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 1                                         # ONE line
+
+    def no_constants(tok):
+        raise AssertionError(f"non-standard JSON token {tok}")
+    line = json.loads(out[0], parse_constant=no_constants)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["dtype"] == "f64" and line["gpu_launches"] > 0
+    assert line["numops_per_step"] == 12 + 2 * (12 - (3 * 12) // 5) and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
+    ov, _, oi = ko.eigsolve_lanczos(ko.stencil_matrix(40, 30), ko.splitmix_vector(bench.SEED, 1200), 4, "SR", krylovdim=12,
+                                    maxiter=3, tol=0.0, orth=ko.Orth(ko.CGS2))
+    assert oi["numops"] == line["numops_per_step"]
+    assert max(abs(x - y) for x, y in zip(line["ritz_values"], ov[:4])) < 1e-10
+
+
+def test_json_safe_makes_any_record_strictly_parseable():
+    import json
+    import numpy as np
+    bench = _load_bench()
+    rec = {"a": float("nan"), "b": [np.float32(1.5), np.inf, {"c": np.int64(3), "d": np.bool_(True)}], "e": np.array([1.0, np.nan])}
+    txt = json.dumps(bench.json_safe(rec), allow_nan=False, default=str)
+    assert json.loads(txt) == {"a": "nan", "b": [1.5, "inf", {"c": 3, "d": True}], "e": [1.0, "nan"]}
