@@ -190,3 +190,24 @@ def test_json_safe_makes_any_record_strictly_parseable():
     rec = {"a": float("nan"), "b": [np.float32(1.5), np.inf, {"c": np.int64(3), "d": np.bool_(True)}], "e": np.array([1.0, np.nan])}
     txt = json.dumps(bench.json_safe(rec), allow_nan=False, default=str)
     assert json.loads(txt) == {"a": "nan", "b": [1.5, "inf", {"c": 3, "d": True}], "e": [1.0, "nan"]}
+
+
+def test_config4_extra_runs_on_the_simulator_with_the_truth_check(monkeypatch):
+    """bench.other_configs 'c4' (two-pass GKL, three orthogonalizers) on the simulator at 4000 rows, once without a
+    committed truth for that shape and once with one: the record gains the distance from the truth and its verdict."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostsim
+    import krylovkit_jl_b200 as kk
+    bench = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--extra", "c4", "--c4-rows", "4000"])
+    a = bench.parse()
+    with hostsim.installed(fused=True):
+        rec = bench.other_configs(kk, a, 0, 1, 0, None)["c4"]
+    assert "error" not in rec and "max_rel_err_sigma_vs_float64_truth" not in rec["mgs2_reference_default"]
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize.json")))
+    gold["c4_truth"] = {"shape": [4000, 512], "sigma_float64_truth": rec["mgs2_reference_default"]["sigma"]}
+    monkeypatch.setattr(bench.json, "load", lambda f: gold)
+    with hostsim.installed(fused=True):
+        rec = bench.other_configs(kk, a, 0, 1, 0, None)["c4"]
+    assert rec["cgsr_eta0.75"]["ok"] and rec["cgsr_eta0.75"]["max_rel_err_sigma_vs_float64_truth"] < 3e-5
