@@ -1380,6 +1380,7 @@ extern "C" int32_t b2k_op_csr_download(b2k_ctx* ctx, const b2k_op* op, int32_t* 
 // ------------------------------------------------------------------ apply ----
 
 static bool g_spmv_pipe = true;
+extern "C" int32_t b2k_debug_set_onepass_variant(int32_t v);     // defined with the one-pass dense step below
 static int g_spmv_variant = 1;     // 1 (default): 2 stages x 4 CTAs/SM, 0: 3 stages x 3 CTAs/SM (B2K_SPMV_VARIANT); measured
                                    // 0.141 vs 0.150 ms standalone, 0.174 vs 0.179 ms in the Lanczos step (gpurun_out/r02g_*)
 
@@ -1409,6 +1410,8 @@ int32_t b2k_spmv_init(b2k_ctx* ctx) {
                                        SppLayout<float, 2>::SMEM));
     const char* sv = getenv("B2K_SPMV_VARIANT");
     if (sv) g_spmv_variant = atoi(sv) == 0 ? 0 : 1;
+    const char* ov = getenv("B2K_ONEPASS_VARIANT");       // kernel of the flagged one-pass GKL step: 0 = A (default), 1 = B
+    if (ov && (ov[0] == '0' || ov[0] == '1')) b2k_debug_set_onepass_variant(ov[0] - '0');
     return B2K_OK;
 }
 
