@@ -87,6 +87,8 @@ int main(int argc, char** argv) {
     if (argc > 1 && std::atoi(argv[1]) == 2) {          // a longer run by hand: many tiles per CTA at config 4's width
         bad += run_case<float>(3000, 512, 4, 0);
         bad += run_case<float>(3000, 512, 3, 1);
+        bad += run_case<float>(3040, 512, 1, 1);        // ld = 3040 = 47.5 tiles of 64 rows, one CTA walks them all
+        bad += run_case<float>(3040, 512, 7, 0);
         std::printf(bad ? "FAILED\n" : "all ok\n");
         return bad ? 1 : 0;
     }
