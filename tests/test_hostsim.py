@@ -312,3 +312,15 @@ def test_onepass_svdsolve_f64(sim, which):
 
 def test_onepass_svdsolve_f32(sim):
     OP.test_svdsolve_onepass_config4_small_f32()
+
+
+def test_config4_fullsize_test_body_on_the_simulator(sim, monkeypatch):
+    """tests/test_gpu_fullsize.py::test_svdsolve_config4_full_size_vs_float64_truth with the truth of a 6000-row matrix of
+    the same generator: the body (column budgets, residual identities on the device vectors, pass count) runs here too."""
+    import test_gpu_fullsize as F
+    m, n = 6000, 512
+    A = ko.dense_splitmix(F.SEED, m, n)
+    truth = np.linalg.svd(A.astype(np.float64), compute_uv=False)[:6]
+    monkeypatch.setitem(F.GOLD, "c4_truth", {"shape": [m, n], "seed": F.SEED, "sigma_float64_truth": [float(x) for x in truth]})
+    for orth_name in ("mgs2", "cgsr"):
+        F.test_svdsolve_config4_full_size_vs_float64_truth(orth_name)
