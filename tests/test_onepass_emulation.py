@@ -36,9 +36,19 @@ def _build(tmp_path, sanitizer):
     return exe
 
 
+def _skip_if_the_sanitizer_cannot_start(res):
+    """a sanitizer runtime that cannot set up its shadow memory on this kernel / address-space layout says so before main()
+    runs: that is the host's business, not the kernels'"""
+    for msg in ("FATAL: ThreadSanitizer", "unexpected memory mapping", "Shadow memory range interleaves",
+                "ReserveShadowMemoryRange failed", "failed to allocate"):
+        if msg in res.stderr and "ok m=" not in res.stdout:
+            pytest.skip("sanitizer runtime cannot start here: " + msg)
+
+
 def test_kernel_sources_run_clean_under_address_sanitizer(tmp_path):
     exe = _build(tmp_path, "address")
     res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    _skip_if_the_sanitizer_cannot_start(res)
     assert res.returncode == 0 and "all ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count("ok m=") == 11 and "ERROR: AddressSanitizer" not in res.stderr
 
@@ -46,5 +56,6 @@ def test_kernel_sources_run_clean_under_address_sanitizer(tmp_path):
 def test_kernel_sources_have_no_shared_memory_race(tmp_path):
     exe = _build(tmp_path, "thread")
     res = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900)
+    _skip_if_the_sanitizer_cannot_start(res)
     assert res.returncode == 0 and "all ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
     assert "ThreadSanitizer" not in res.stderr
