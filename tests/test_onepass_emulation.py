@@ -40,7 +40,7 @@ def _skip_if_the_sanitizer_cannot_start(res):
     """a sanitizer runtime that cannot set up its shadow memory on this kernel / address-space layout says so before main()
     runs: that is the host's business, not the kernels'"""
     for msg in ("FATAL: ThreadSanitizer", "unexpected memory mapping", "Shadow memory range interleaves",
-                "ReserveShadowMemoryRange failed", "failed to allocate"):
+                "ReserveShadowMemoryRange failed", "failed to allocate", "Resource temporarily unavailable"):   # (pids limit)
         if msg in res.stderr and "ok m=" not in res.stdout:
             pytest.skip("sanitizer runtime cannot start here: " + msg)
 
